@@ -1,0 +1,454 @@
+// gta_b200.cu -- C-ABI host layer of libgtessla_b200.so (declared in include/gta_b200.h).
+//
+// Replaces the reference's OpenMP frame loop (src/gta_tri.c:90-95, :106, :301) by
+// pinned-buffer batched frame staging with async H2D on several streams, one fused kernel
+// launch per chunk (gta_kernel.cuh) and a slice-wise D2H of the per-frame results.
+// Frames are independent: multi-GPU = contiguous frame ranges, no collective.
+//
+// There is deliberately no CPU path in this file: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+#include "gta_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+thread_local double g_last_kernel_ms = 0.0;
+thread_local int g_last_launches = 0;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(GTA_B200_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+int round_even(int v) { return (v + 1) & ~1; }
+int pow2_ge(int v) { int p = 2; while (p < v) p <<= 1; return p; }
+
+struct Shape { int threads; size_t smem; int cap, cap_p2; };
+
+int smem_limit() {
+    static int lim = -1;
+    if (lim < 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 227 * 1024;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || v <= 0) v = 227 * 1024;
+        lim = v;
+    }
+    return lim;
+}
+
+Shape shape_for(int max_points) {
+    Shape s;
+    s.cap = round_even(std::max(max_points, 4));
+    s.cap_p2 = pow2_ge(s.cap);
+    s.smem = gt::smem_bytes_for(s.cap, s.cap_p2);
+    s.threads = s.cap <= 192 ? 32 : (s.cap <= 512 ? 64 : 128);
+    return s;
+}
+
+template <int T, int MINB>
+int launch_t(const gt::KParams& p, const Shape& s, cudaStream_t st) {
+    auto kern = gt::tessellate_kernel<T, MINB>;
+    static std::mutex mu;
+    static size_t configured[64] = {0};
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (dev < 64 && configured[dev] < s.smem) {
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem));
+            configured[dev] = s.smem;
+        }
+    }
+    int occ = 0, sms = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, s.smem));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (occ < 1) return fail(GTA_B200_E_TOO_LARGE, "kernel does not fit on an SM");
+    int grid = std::min(p.nframes, occ * sms);           // persistent CTAs, frames handed out by an atomic counter
+    if (grid < 1) grid = 1;
+    kern<<<grid, T, s.smem, st>>>(p);
+    CK(cudaGetLastError());
+    return GTA_B200_OK;
+}
+
+int launch(const gt::KParams& p, const Shape& s, cudaStream_t st) {
+    switch (s.threads) {
+        case 32: return launch_t<32, 8>(p, s, st);
+        case 64: return launch_t<64, 4>(p, s, st);
+        default: return launch_t<128, 3>(p, s, st);
+    }
+}
+
+int occupancy_for(const Shape& s) {
+    int occ = 0;
+    if (s.threads == 32) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gt::tessellate_kernel<32, 8>, 32, s.smem);
+    else if (s.threads == 64) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gt::tessellate_kernel<64, 4>, 64, s.smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gt::tessellate_kernel<128, 3>, 128, s.smem);
+    return occ;
+}
+
+bool have_device() {
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess && n > 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gta_b200_last_error(void) { return g_err.c_str(); }
+double gta_b200_last_kernel_ms(void) { return g_last_kernel_ms; }
+int gta_b200_last_launches(void) { return g_last_launches; }
+
+int gta_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int gta_b200_max_points(void) {
+    // ~64 bytes of shared memory per point (see smem_bytes_for)
+    int lim = have_device() ? smem_limit() : 227 * 1024;
+    int lo = 4, hi = 8192;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) / 2;
+        Shape s = shape_for(mid);
+        if (s.smem <= (size_t)lim && gt::pool_edges(s.cap) < 32760) lo = mid; else hi = mid - 1;
+    }
+    return lo & ~1;
+}
+
+int gta_b200_max_points_for(const double* box, int box_stride, int nframes, int natoms, double espace, unsigned flags) {
+    if (!(flags & GTA_B200_CORRECT) || !box) return natoms;
+    int by_off = box_stride == 9 ? 4 : 1, best = 0;
+    for (int f = 0; f < nframes; ++f) {
+        int nx = (int)(box[(size_t)f * box_stride] / espace), ny = (int)(box[(size_t)f * box_stride + by_off] / espace);
+        if (nx < 0 || ny < 0 || nx > (1 << 20) || ny > (1 << 20)) continue;
+        best = std::max(best, 4 + 2 * nx + 2 * ny);
+    }
+    return natoms + best;
+}
+
+int gta_b200_launch_shape(int max_points, int* threads_per_frame, size_t* smem_bytes, int* frames_per_sm) {
+    Shape s = shape_for(max_points);
+    if (threads_per_frame) *threads_per_frame = s.threads;
+    if (smem_bytes) *smem_bytes = s.smem;
+    if (frames_per_sm) {
+        *frames_per_sm = 0;
+        if (have_device() && s.smem <= (size_t)smem_limit()) {
+            // the attribute must be raised before the occupancy query sees > 48 KB
+            if (s.threads == 32) cudaFuncSetAttribute(gt::tessellate_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem);
+            else if (s.threads == 64) cudaFuncSetAttribute(gt::tessellate_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem);
+            else cudaFuncSetAttribute(gt::tessellate_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem);
+            *frames_per_sm = occupancy_for(s);
+        }
+    }
+    return GTA_B200_OK;
+}
+
+int gta_b200_tessellate_device(const double* d_xyz, int in_dim, const double* d_box, int box_stride,
+                               int nframes, int natoms, int max_points, double espace, unsigned flags,
+                               double* d_area, double* d_area2d, double* d_areabox, int* d_status,
+                               int* d_tri, int tri_cap, int* d_ntri,
+                               double* d_corr, int corr_cap, int* d_ncorr,
+                               unsigned int* d_work, void* stream) {
+    if (!have_device()) return fail(GTA_B200_E_NO_DEVICE, "no CUDA device: libgtessla_b200 has no CPU path");
+    if (nframes < 0 || natoms < 0 || (in_dim != 2 && in_dim != 3) || !d_xyz || !d_work)
+        return fail(GTA_B200_E_ARG, "bad argument");
+    if ((flags & GTA_B200_CORRECT) && (!d_box || !(espace > 0.0)))
+        return fail(GTA_B200_E_ARG, "-corr needs the box and espace > 0");
+    if (nframes == 0) return GTA_B200_OK;
+    Shape s = shape_for(std::max(max_points, natoms));
+    if (s.smem > (size_t)smem_limit() || gt::pool_edges(s.cap) >= 32760)
+        return fail(GTA_B200_E_TOO_LARGE, "max_points exceeds the shared-memory kernel (see gta_b200_max_points)");
+    cudaStream_t st = (cudaStream_t)stream;
+    gt::KParams p;
+    p.xyz = d_xyz; p.in_dim = in_dim; p.box = d_box; p.box_stride = box_stride; p.by_off = (box_stride == 9) ? 4 : 1;
+    p.nframes = nframes; p.natoms = natoms; p.cap = s.cap; p.cap_p2 = s.cap_p2;
+    p.espace = espace; p.flags = flags;
+    p.area = d_area; p.area2d = d_area2d; p.areabox = d_areabox; p.status = d_status;
+    p.tri = d_tri; p.tri_cap = tri_cap; p.ntri = d_ntri;
+    p.corr = d_corr; p.corr_cap = corr_cap; p.ncorr = d_ncorr;
+    p.work = d_work;
+    CK(cudaMemsetAsync(d_work, 0, sizeof(unsigned int), st));
+    return launch(p, s, st);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// Host-buffer pipeline
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct Job {
+    const double* xyz = nullptr;             // flat [nframes][natoms][in_dim] or
+    const double* const* frames = nullptr;   // one pointer per frame (reference layout)
+    int in_dim = 3;
+    const double* box = nullptr; int box_stride = 0;
+    int nframes = 0, natoms = 0; double espace = 0.8; unsigned flags = 0;
+    int max_points = 0;
+    double *area = nullptr, *area2d = nullptr, *areabox = nullptr; int* status = nullptr;
+    int* tri = nullptr; int tri_cap = 0; int* ntri = nullptr;
+    double* corr = nullptr; int corr_cap = 0; int* ncorr = nullptr;
+};
+
+// One in-flight chunk: pinned + device buffers, a stream and two events.
+struct Slot {
+    cudaStream_t st = nullptr; cudaEvent_t k0 = nullptr, k1 = nullptr;
+    double *h_in = nullptr, *d_in = nullptr;           // coords
+    double *h_box = nullptr, *d_box = nullptr;
+    double *h_out = nullptr, *d_out = nullptr;         // area | area2d | areabox  (3 * chunk)
+    int *h_st = nullptr, *d_st = nullptr;              // status | ntri | ncorr    (3 * chunk)
+    int* d_tri = nullptr; double* d_corr = nullptr;    // optional, copied straight to the caller
+    unsigned int* d_work = nullptr;
+    size_t in_bytes = 0; int chunk = 0, box_stride = 0; size_t tri_elems = 0, corr_elems = 0;
+    int f0 = 0, nf = 0; bool busy = false;
+};
+
+void slot_free(Slot& s) {
+    if (s.st) cudaStreamDestroy(s.st);
+    if (s.k0) cudaEventDestroy(s.k0);
+    if (s.k1) cudaEventDestroy(s.k1);
+    cudaFreeHost(s.h_in); cudaFree(s.d_in); cudaFreeHost(s.h_box); cudaFree(s.d_box);
+    cudaFreeHost(s.h_out); cudaFree(s.d_out); cudaFreeHost(s.h_st); cudaFree(s.d_st);
+    cudaFree(s.d_tri); cudaFree(s.d_corr); cudaFree(s.d_work);
+    s = Slot();
+}
+
+int slot_ensure(Slot& s, int chunk, size_t frame_bytes, int box_stride, size_t tri_elems, size_t corr_elems) {
+    size_t in_bytes = frame_bytes * (size_t)chunk;
+    if (s.st && s.in_bytes >= in_bytes && s.chunk >= chunk && s.box_stride >= box_stride &&
+        s.tri_elems >= tri_elems && s.corr_elems >= corr_elems) return GTA_B200_OK;
+    slot_free(s);
+    CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&s.k0)); CK(cudaEventCreate(&s.k1));
+    CK(cudaHostAlloc((void**)&s.h_in, in_bytes, cudaHostAllocDefault)); CK(cudaMalloc((void**)&s.d_in, in_bytes));
+    size_t bb = sizeof(double) * (size_t)std::max(box_stride, 1) * chunk;
+    CK(cudaHostAlloc((void**)&s.h_box, bb, cudaHostAllocDefault)); CK(cudaMalloc((void**)&s.d_box, bb));
+    CK(cudaHostAlloc((void**)&s.h_out, sizeof(double) * 3 * (size_t)chunk, cudaHostAllocDefault));
+    CK(cudaMalloc((void**)&s.d_out, sizeof(double) * 3 * (size_t)chunk));
+    CK(cudaHostAlloc((void**)&s.h_st, sizeof(int) * 3 * (size_t)chunk, cudaHostAllocDefault));
+    CK(cudaMalloc((void**)&s.d_st, sizeof(int) * 3 * (size_t)chunk));
+    if (tri_elems) CK(cudaMalloc((void**)&s.d_tri, sizeof(int) * tri_elems));
+    if (corr_elems) CK(cudaMalloc((void**)&s.d_corr, sizeof(double) * corr_elems));
+    CK(cudaMalloc((void**)&s.d_work, sizeof(unsigned int)));
+    s.in_bytes = in_bytes; s.chunk = chunk; s.box_stride = box_stride; s.tri_elems = tri_elems; s.corr_elems = corr_elems;
+    return GTA_B200_OK;
+}
+
+// Per host thread and device: a small set of reusable slots (pinned allocations are expensive).
+struct SlotCache { int device = -1; std::vector<Slot> slots; ~SlotCache() { for (auto& s : slots) slot_free(s); } };
+thread_local SlotCache g_cache;
+
+int drain(Slot& s, const Job& j, double* kernel_ms) {
+    if (!s.busy) return GTA_B200_OK;
+    CK(cudaStreamSynchronize(s.st));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s.k0, s.k1) == cudaSuccess) *kernel_ms += ms;
+    const int c = s.chunk;
+    if (j.area) memcpy(j.area + s.f0, s.h_out, sizeof(double) * s.nf);
+    if (j.area2d && (j.flags & GTA_B200_2D)) memcpy(j.area2d + s.f0, s.h_out + c, sizeof(double) * s.nf);
+    if (j.areabox) memcpy(j.areabox + s.f0, s.h_out + 2 * (size_t)c, sizeof(double) * s.nf);
+    if (j.status) memcpy(j.status + s.f0, s.h_st, sizeof(int) * s.nf);
+    if (j.ntri) memcpy(j.ntri + s.f0, s.h_st + c, sizeof(int) * s.nf);
+    if (j.ncorr) memcpy(j.ncorr + s.f0, s.h_st + 2 * (size_t)c, sizeof(int) * s.nf);
+    s.busy = false;
+    return GTA_B200_OK;
+}
+
+int submit(Slot& s, const Job& j, const Shape& shp, int f0, int nf, bool src_pinned) {
+    const size_t frame_elems = (size_t)j.natoms * j.in_dim, frame_bytes = frame_elems * sizeof(double);
+    s.f0 = f0; s.nf = nf;
+    // stage coordinates
+    const double* h_src;
+    if (j.frames) {
+        for (int f = 0; f < nf; ++f) memcpy(s.h_in + (size_t)f * frame_elems, j.frames[f0 + f], frame_bytes);
+        h_src = s.h_in;
+    } else if (src_pinned) {
+        h_src = j.xyz + (size_t)f0 * frame_elems;              // caller's buffer is already page-locked
+    } else {
+        memcpy(s.h_in, j.xyz + (size_t)f0 * frame_elems, frame_bytes * nf);
+        h_src = s.h_in;
+    }
+    CK(cudaMemcpyAsync(s.d_in, h_src, frame_bytes * nf, cudaMemcpyHostToDevice, s.st));
+    if (j.box) {
+        memcpy(s.h_box, j.box + (size_t)f0 * j.box_stride, sizeof(double) * j.box_stride * nf);
+        CK(cudaMemcpyAsync(s.d_box, s.h_box, sizeof(double) * j.box_stride * nf, cudaMemcpyHostToDevice, s.st));
+    }
+    const int c = s.chunk;
+    gt::KParams p;
+    p.xyz = s.d_in; p.in_dim = j.in_dim; p.box = j.box ? s.d_box : nullptr; p.box_stride = j.box_stride;
+    p.by_off = (j.box_stride == 9) ? 4 : 1;
+    p.nframes = nf; p.natoms = j.natoms; p.cap = shp.cap; p.cap_p2 = shp.cap_p2; p.espace = j.espace; p.flags = j.flags;
+    p.area = s.d_out; p.area2d = s.d_out + c; p.areabox = s.d_out + 2 * (size_t)c;
+    p.status = s.d_st; p.ntri = s.d_st + c; p.ncorr = s.d_st + 2 * (size_t)c;
+    p.tri = j.tri ? s.d_tri : nullptr; p.tri_cap = j.tri_cap;
+    p.corr = j.corr ? s.d_corr : nullptr; p.corr_cap = j.corr_cap;
+    p.work = s.d_work;
+    CK(cudaMemsetAsync(s.d_work, 0, sizeof(unsigned int), s.st));
+    CK(cudaMemsetAsync(s.d_st, 0, sizeof(int) * 3 * (size_t)c, s.st));
+    CK(cudaEventRecord(s.k0, s.st));
+    int rc = launch(p, shp, s.st);
+    if (rc) return rc;
+    CK(cudaEventRecord(s.k1, s.st));
+    CK(cudaMemcpyAsync(s.h_out, s.d_out, sizeof(double) * 3 * (size_t)c, cudaMemcpyDeviceToHost, s.st));
+    CK(cudaMemcpyAsync(s.h_st, s.d_st, sizeof(int) * 3 * (size_t)c, cudaMemcpyDeviceToHost, s.st));
+    if (j.tri) CK(cudaMemcpyAsync(j.tri + (size_t)f0 * j.tri_cap * 3, s.d_tri, sizeof(int) * 3 * (size_t)j.tri_cap * nf, cudaMemcpyDeviceToHost, s.st));
+    if (j.corr) CK(cudaMemcpyAsync(j.corr + (size_t)f0 * j.corr_cap * 3, s.d_corr, sizeof(double) * 3 * (size_t)j.corr_cap * nf, cudaMemcpyDeviceToHost, s.st));
+    s.busy = true;
+    return GTA_B200_OK;
+}
+
+int run_job(Job j, int device, int nstreams) {
+    if (!have_device()) return fail(GTA_B200_E_NO_DEVICE, "no CUDA device: libgtessla_b200 has no CPU path");
+    if (j.nframes < 0 || j.natoms < 0 || (j.in_dim != 2 && j.in_dim != 3) || (!j.xyz && !j.frames))
+        return fail(GTA_B200_E_ARG, "bad argument");
+    if ((j.flags & GTA_B200_CORRECT) && (!j.box || !(j.espace > 0.0)))
+        return fail(GTA_B200_E_ARG, "-corr needs the box and espace > 0");
+    g_last_kernel_ms = 0.0; g_last_launches = 0;
+    if (j.nframes == 0) return GTA_B200_OK;
+    if (device >= 0) CK(cudaSetDevice(device));
+    CK(cudaGetDevice(&device));
+    j.max_points = gta_b200_max_points_for(j.box, j.box_stride, j.nframes, j.natoms, j.espace, j.flags);
+    Shape shp = shape_for(j.max_points);
+    if (shp.smem > (size_t)smem_limit() || gt::pool_edges(shp.cap) >= 32760)
+        return fail(GTA_B200_E_TOO_LARGE, "frame too large for the shared-memory kernel (see gta_b200_max_points)");
+
+    nstreams = std::max(1, std::min(nstreams <= 0 ? 3 : nstreams, 8));
+    const size_t frame_bytes = (size_t)j.natoms * j.in_dim * sizeof(double);
+    // chunk: enough frames for several waves of persistent CTAs, bounded to ~64 MB of coordinates
+    long long chunk = (j.nframes + nstreams - 1) / nstreams;
+    chunk = std::min<long long>(chunk, std::max<long long>(256, (64ll << 20) / (long long)std::max<size_t>(frame_bytes, 1)));
+    chunk = std::max<long long>(chunk, 1);
+    if (j.tri) chunk = std::min<long long>(chunk, std::max<long long>(1, (256ll << 20) / (12ll * std::max(j.tri_cap, 1))));
+
+    bool src_pinned = false;
+    if (j.xyz) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, j.xyz) == cudaSuccess) src_pinned = (at.type == cudaMemoryTypeHost);
+        else cudaGetLastError();
+    }
+    if (g_cache.device != device) { for (auto& s : g_cache.slots) slot_free(s); g_cache.slots.clear(); g_cache.device = device; }
+    if ((int)g_cache.slots.size() < nstreams) g_cache.slots.resize(nstreams);
+    for (int i = 0; i < nstreams; ++i) {
+        int rc = slot_ensure(g_cache.slots[i], (int)chunk, frame_bytes, std::max(j.box_stride, 1),
+                             j.tri ? (size_t)chunk * j.tri_cap * 3 : 0, j.corr ? (size_t)chunk * j.corr_cap * 3 : 0);
+        if (rc) return rc;
+    }
+    double kms = 0.0; int launches = 0, rc = GTA_B200_OK, si = 0;
+    for (int f0 = 0; f0 < j.nframes && rc == GTA_B200_OK; f0 += (int)chunk) {
+        Slot& s = g_cache.slots[si];
+        si = (si + 1) % nstreams;
+        rc = drain(s, j, &kms);
+        if (rc) break;
+        int nf = std::min<long long>(chunk, j.nframes - f0);
+        rc = submit(s, j, shp, f0, nf, src_pinned);
+        ++launches;
+    }
+    for (int i = 0; i < nstreams; ++i) { int r2 = drain(g_cache.slots[i], j, &kms); if (rc == GTA_B200_OK) rc = r2; }
+    g_last_kernel_ms = kms; g_last_launches = launches;
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gta_b200_tessellate_batch(const double* xyz, int in_dim, const double* box, int box_stride,
+                              int nframes, int natoms, double espace, unsigned flags,
+                              int device, int nstreams,
+                              double* area, double* area2d, double* areabox, int* status,
+                              int* tri, int tri_cap, int* ntri,
+                              double* corr, int corr_cap, int* ncorr) {
+    Job j;
+    j.xyz = xyz; j.in_dim = in_dim; j.box = box; j.box_stride = box_stride; j.nframes = nframes; j.natoms = natoms;
+    j.espace = espace; j.flags = flags; j.area = area; j.area2d = area2d; j.areabox = areabox; j.status = status;
+    j.tri = tri; j.tri_cap = tri_cap; j.ntri = ntri; j.corr = corr; j.corr_cap = corr_cap; j.ncorr = ncorr;
+    return run_job(j, device, nstreams);
+}
+
+static int run_sharded(const Job& base, int ngpus, int nstreams) {
+    int avail = gta_b200_device_count();
+    if (avail < 1) return fail(GTA_B200_E_NO_DEVICE, "no CUDA device: libgtessla_b200 has no CPU path");
+    ngpus = std::max(1, std::min(ngpus <= 0 ? avail : ngpus, avail));
+    const int per = (base.nframes + ngpus - 1) / ngpus;     // contiguous ranges [g*per, (g+1)*per)
+    std::vector<int> rcs(ngpus, GTA_B200_OK);
+    std::vector<std::string> errs(ngpus);
+    std::vector<double> kms(ngpus, 0.0);
+    std::vector<int> ln(ngpus, 0);
+    std::vector<std::thread> th;
+    for (int g = 0; g < ngpus; ++g) {
+        th.emplace_back([&, g]() {
+            int f0 = g * per, f1 = std::min(base.nframes, f0 + per);
+            if (f0 >= f1) return;
+            Job j = base;
+            const size_t fe = (size_t)j.natoms * j.in_dim;
+            if (j.xyz) j.xyz += (size_t)f0 * fe;
+            if (j.frames) j.frames += f0;
+            if (j.box) j.box += (size_t)f0 * j.box_stride;
+            j.nframes = f1 - f0;
+            if (j.area) j.area += f0;
+            if (j.area2d) j.area2d += f0;
+            if (j.areabox) j.areabox += f0;
+            if (j.status) j.status += f0;
+            rcs[g] = run_job(j, g, nstreams);
+            errs[g] = g_err; kms[g] = g_last_kernel_ms; ln[g] = g_last_launches;
+        });
+    }
+    for (auto& t : th) t.join();
+    g_last_kernel_ms = *std::max_element(kms.begin(), kms.end());
+    g_last_launches = 0; for (int v : ln) g_last_launches += v;
+    for (int g = 0; g < ngpus; ++g) if (rcs[g]) return fail(rcs[g], errs[g]);
+    return GTA_B200_OK;
+}
+
+int gta_b200_tessellate_multi(const double* xyz, int in_dim, const double* box, int box_stride,
+                              int nframes, int natoms, double espace, unsigned flags,
+                              int ngpus, int nstreams,
+                              double* area, double* area2d, double* areabox, int* status) {
+    Job j;
+    j.xyz = xyz; j.in_dim = in_dim; j.box = box; j.box_stride = box_stride; j.nframes = nframes; j.natoms = natoms;
+    j.espace = espace; j.flags = flags; j.area = area; j.area2d = area2d; j.areabox = areabox; j.status = status;
+    return run_sharded(j, ngpus, nstreams);
+}
+
+int gta_b200_tessellate_frames(const double* const* x, const double* box9, int nframes, int natoms,
+                               double espace, unsigned flags, int ngpus, int nthreads,
+                               double* area, double* area2d, double* areabox, int* status) {
+    Job j;
+    j.frames = x; j.in_dim = 3; j.box = box9; j.box_stride = 9; j.nframes = nframes; j.natoms = natoms;
+    j.espace = espace; j.flags = flags; j.area = area; j.area2d = area2d; j.areabox = areabox; j.status = status;
+    int nstreams = nthreads <= 0 ? 4 : std::max(1, std::min(nthreads, 8));
+    return run_sharded(j, ngpus <= 0 ? 1 : ngpus, nstreams);
+}
+
+static int signs_common(const double* pts, int n, int* out, int device, int width) {
+    if (!have_device()) return fail(GTA_B200_E_NO_DEVICE, "no CUDA device: libgtessla_b200 has no CPU path");
+    if (n <= 0) return GTA_B200_OK;
+    if (device >= 0) CK(cudaSetDevice(device));
+    double* d = nullptr; int* o = nullptr;
+    CK(cudaMalloc((void**)&d, sizeof(double) * width * (size_t)n));
+    CK(cudaMalloc((void**)&o, sizeof(int) * (size_t)n));
+    CK(cudaMemcpy(d, pts, sizeof(double) * width * (size_t)n, cudaMemcpyHostToDevice));
+    if (width == 6) gt::orient2d_signs_kernel<<<(n + 127) / 128, 128>>>(d, n, o);
+    else gt::incircle_signs_kernel<<<(n + 127) / 128, 128>>>(d, n, o);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, o, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
+    cudaFree(d); cudaFree(o);
+    return GTA_B200_OK;
+}
+int gta_b200_orient2d_signs(const double* pts, int n, int* sign_out, int device) { return signs_common(pts, n, sign_out, device, 6); }
+int gta_b200_incircle_signs(const double* pts, int n, int* sign_out, int device) { return signs_common(pts, n, sign_out, device, 8); }
+
+}  // extern "C"

@@ -1,0 +1,340 @@
+// gta_kernel.cuh -- the batched per-frame kernel: one CTA per frame, whole frame in shared memory.
+//
+// Replaces, per frame, the body of the reference's OpenMP loop (src/gta_tri.c:106-296):
+//   K0  -corr box-edge point generation            gta_tri.c:112-272
+//   K1  lexicographic sort + Delaunay D&C           delaunay_tri.c:436, :511-601
+//   K2  triangle enumeration + area sum             delaunay_tri.c:606-635, gta_tri.c:368-410
+// fused in one launch: coordinates are read from HBM once (coalesced), everything else lives in
+// shared memory (<= ~64 B per point), and 8-24 bytes per frame go back.
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include "dt_core.cuh"
+#include "../../include/gta_b200.h"
+
+namespace gt {
+
+struct KParams {
+    const double* xyz; int in_dim;            // [nframes][natoms][in_dim]
+    const double* box; int box_stride, by_off;
+    int nframes, natoms, cap;                  // cap = max points per frame (even)
+    int cap_p2;                                // power of two >= cap (sort network width bound)
+    double espace; unsigned flags;
+    double* area; double* area2d; double* areabox; int* status;
+    int* tri; int tri_cap; int* ntri;
+    double* corr; int corr_cap; int* ncorr;
+    unsigned int* work;                        // global frame counter
+};
+
+__host__ __device__ inline int pool_edges(int cap) { return 3 * cap + 64; }
+// dynamic shared memory for a capacity of `cap` points
+__host__ __device__ inline size_t smem_bytes_for(int cap, int cap_p2) {
+    size_t b = 0;
+    b += sizeof(Pt) * (size_t)cap;             // sorted xy
+    b += sizeof(double) * (size_t)cap;         // sorted z
+    b += 12 * (size_t)pool_edges(cap);         // half-edge pool (dst, nxt, prv: u16 x 2 per edge each)
+    b += 2 * (size_t)cap_p2;                   // perm
+    b += 2 * (size_t)cap;                      // head
+    b = (b + 15) & ~(size_t)15;
+    b += 16 * 4 + 64 * 8 + 32 * 4;             // ctl, reduction scratch, scan scratch
+    return b;
+}
+
+__device__ __forceinline__ unsigned long long okey(double v) {   // order-preserving bits
+    unsigned long long b = (unsigned long long)__double_as_longlong(v + 0.0);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+template <int T>
+__device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* scratch, unsigned* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (T > 32) {
+        if (lane == 31) scratch[warp] = inc;
+        __syncthreads();
+        unsigned base = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < T / 32; ++w) { unsigned s = scratch[w]; if (w < warp) base += s; tot += s; }
+        __syncthreads();
+        *total = tot;
+        return base + inc - v;
+    } else {
+        *total = __shfl_sync(0xffffffffu, inc, 31);
+        return inc - v;
+    }
+}
+
+template <int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) tessellate_kernel(const KParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int cap = p.cap, cap_e = pool_edges(cap);
+    Pt* pt = reinterpret_cast<Pt*>(smem);
+    double* zs = reinterpret_cast<double*>(pt + cap);
+    unsigned char* pool = reinterpret_cast<unsigned char*>(zs + cap);
+    u16* dst = reinterpret_cast<u16*>(pool);
+    u16* nxt = dst + 2 * cap_e;
+    u16* prv = nxt + 2 * cap_e;
+    Pt* tmp_xy = reinterpret_cast<Pt*>(pool);                  // setup-time alias of the pool
+    double* tmp_z = reinterpret_cast<double*>(tmp_xy + cap);
+    u16* perm = reinterpret_cast<u16*>(pool + 12 * (size_t)cap_e);
+    u16* head = perm + p.cap_p2;
+    size_t off = (size_t)(reinterpret_cast<unsigned char*>(head + cap) - smem);
+    off = (off + 15) & ~(size_t)15;
+    uint32_t* ctl = reinterpret_cast<uint32_t*>(smem + off);    // [0] bump [1] stack [2] err [3] frame [4] status
+    double* red = reinterpret_cast<double*>(ctl + 16);
+    unsigned* scan = reinterpret_cast<unsigned*>(red + 64);
+    // -corr scratch aliases the (not yet filled) sorted-xy region
+    unsigned long long* ckey = reinterpret_cast<unsigned long long*>(pt);
+
+    const bool corr = (p.flags & GTA_B200_CORRECT) != 0, want2d = (p.flags & GTA_B200_2D) != 0;
+    const int natoms = p.natoms;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) { ctl[3] = atomicAdd(p.work, 1u); ctl[4] = 0; ctl[0] = 0; ctl[1] = GT_NIL; ctl[2] = 0; }
+        __syncthreads();
+        const int fr = (int)ctl[3];
+        if (fr >= p.nframes) break;
+
+        // ------------------------------------------------------------ load (coalesced)
+        const double* src = p.xyz + (size_t)fr * natoms * p.in_dim;
+        bool bad = false;
+        if (p.in_dim == 3) {
+            for (int k = tid; k < 3 * natoms; k += T) {
+                double v = src[k];
+                bad |= !isfinite(v);
+                int a = k / 3, c = k - 3 * a;
+                if (c == 0) tmp_xy[a].x = v; else if (c == 1) tmp_xy[a].y = v; else tmp_z[a] = v;
+            }
+        } else {
+            for (int k = tid; k < 2 * natoms; k += T) {
+                double v = src[k];
+                bad |= !isfinite(v);
+                if (k & 1) tmp_xy[k >> 1].y = v; else { tmp_xy[k >> 1].x = v; tmp_z[k >> 1] = 0.0; }
+            }
+        }
+        double bx = 0.0, by = 0.0;
+        if (p.box) { bx = p.box[(size_t)fr * p.box_stride]; by = p.box[(size_t)fr * p.box_stride + p.by_off]; }
+        if (bad) atomicOr(&ctl[4], GTA_B200_ST_NONFINITE);
+        int n = natoms;
+
+        // ------------------------------------------------------------ K0: -corr points
+        if (corr) {
+            const int nx = (int)(bx / p.espace), ny = (int)(by / p.espace);      // gta_tri.c:112-113
+            const bool boxok = isfinite(bx) && isfinite(by) && nx >= 0 && ny >= 0 && natoms >= 1;
+            const int ncorr = boxok ? 4 + 2 * nx + 2 * ny : 0;
+            const int K = ncorr + 4;                                             // 4 corners + 2(nx+1) + 2(ny+1) slots
+            int* cidx = reinterpret_cast<int*>(ckey + K);
+            if (!boxok) { if (tid == 0) atomicOr(&ctl[4], natoms < 1 ? GTA_B200_ST_TOO_FEW_POINTS : GTA_B200_ST_NONFINITE); }
+            else if (natoms + ncorr > cap) { if (tid == 0) atomicOr(&ctl[4], GTA_B200_ST_CAPACITY); }
+            else {
+                const int oymin = 4, oymax = 4 + (nx + 1), oxmin = 4 + 2 * (nx + 1), oxmax = oxmin + (ny + 1);
+                const unsigned long long kmin0 = okey((double)FLT_MAX), kmax0 = okey((double)FLT_MIN);   // gta_tri.c:119-120,137-144
+                for (int s = tid; s < K; s += T) {
+                    bool ismin = (s == 0 || s == 2) || (s >= oymin && s < oymax) || (s >= oxmin && s < oxmax);
+                    ckey[s] = ismin ? kmin0 : kmax0;
+                    cidx[s] = 0x7fffffff;
+                }
+                __syncthreads();
+                // pass 1: extreme values per slot (gta_tri.c:153-202)
+                for (int j = tid; j < natoms; j += T) {
+                    double X = tmp_xy[j].x, Y = tmp_xy[j].y;
+                    double d0 = X * X + Y * Y, dY = by - Y, d1 = X * X + dY * dY;
+                    double fx = (X / bx) * nx, fy = (Y / by) * ny;
+                    if (!(fx > -1.0 && fx < (double)(nx + 1) && fy > -1.0 && fy < (double)(ny + 1))) {
+                        atomicOr(&ctl[4], GTA_B200_ST_OUT_OF_BOX);
+                        continue;
+                    }
+                    int xi = (int)fx, yi = (int)fy;
+                    atomicMin(&ckey[0], okey(d0)); atomicMax(&ckey[1], okey(d0));
+                    atomicMin(&ckey[2], okey(d1)); atomicMax(&ckey[3], okey(d1));
+                    atomicMin(&ckey[oymin + xi], okey(Y)); atomicMax(&ckey[oymax + xi], okey(Y));
+                    atomicMin(&ckey[oxmin + yi], okey(X)); atomicMax(&ckey[oxmax + yi], okey(X));
+                }
+                __syncthreads();
+                // pass 2: lowest atom index attaining the extreme (strict < / > keeps the first one)
+                if (!(ctl[4] & GTA_B200_ST_OUT_OF_BOX)) {
+                    for (int j = tid; j < natoms; j += T) {
+                        double X = tmp_xy[j].x, Y = tmp_xy[j].y;
+                        double d0 = X * X + Y * Y, dY = by - Y, d1 = X * X + dY * dY;
+                        int xi = (int)((X / bx) * nx), yi = (int)((Y / by) * ny);
+                        const double fmx = (double)FLT_MAX, fmn = (double)FLT_MIN;
+                        if (d0 < fmx && okey(d0) == ckey[0]) atomicMin(&cidx[0], j);
+                        if (d0 > fmn && okey(d0) == ckey[1]) atomicMin(&cidx[1], j);
+                        if (d1 < fmx && okey(d1) == ckey[2]) atomicMin(&cidx[2], j);
+                        if (d1 > fmn && okey(d1) == ckey[3]) atomicMin(&cidx[3], j);
+                        if (Y < fmx && okey(Y) == ckey[oymin + xi]) atomicMin(&cidx[oymin + xi], j);
+                        if (Y > fmn && okey(Y) == ckey[oymax + xi]) atomicMin(&cidx[oymax + xi], j);
+                        if (X < fmx && okey(X) == ckey[oxmin + yi]) atomicMin(&cidx[oxmin + yi], j);
+                        if (X > fmn && okey(X) == ckey[oxmax + yi]) atomicMin(&cidx[oxmax + yi], j);
+                    }
+                }
+                __syncthreads();
+                for (int s = tid; s < K; s += T) if (cidx[s] == 0x7fffffff) cidx[s] = 0;      // index arrays start at 0 (gta_tri.c:146-149)
+                __syncthreads();
+                // corner z (gta_tri.c:209-212) and the appended points in the reference's order (:220-272)
+                const double zc = (tmp_z[cidx[0]] + tmp_z[cidx[1]] + tmp_z[cidx[2]] + tmp_z[cidx[3]]) / 4.0;
+                for (int s = tid; s < ncorr; s += T) {
+                    double X, Y, Z;
+                    if (s < 4) {
+                        X = (s == 1 || s == 2) ? bx : 0.0; Y = (s >= 2) ? by : 0.0; Z = zc;
+                    } else if (s < 4 + 2 * nx) {
+                        int j = (s - 4) >> 1;
+                        int imin = cidx[oymin + j], imax = cidx[oymax + j];
+                        double dist1 = tmp_xy[imin].y, dist2 = by - tmp_xy[imax].y, dist = dist1 + dist2;
+                        Z = tmp_z[imin] - (dist1 / dist) * tmp_z[imin] + tmp_z[imax] - (dist2 / dist) * tmp_z[imax];
+                        X = j * p.espace + p.espace / 2; Y = ((s - 4) & 1) ? by : 0.0;
+                    } else {
+                        int j = (s - 4 - 2 * nx) >> 1;
+                        int imin = cidx[oxmin + j], imax = cidx[oxmax + j];
+                        double dist1 = tmp_xy[imin].x, dist2 = bx - tmp_xy[imax].x, dist = dist1 + dist2;
+                        Z = tmp_z[imin] - (dist1 / dist) * tmp_z[imin] + tmp_z[imax] - (dist2 / dist) * tmp_z[imax];
+                        Y = j * p.espace + p.espace / 2; X = ((s - 4 - 2 * nx) & 1) ? bx : 0.0;
+                    }
+                    tmp_xy[natoms + s].x = X; tmp_xy[natoms + s].y = Y; tmp_z[natoms + s] = Z;
+                    if (p.corr && s < p.corr_cap) {
+                        double* o = p.corr + ((size_t)fr * p.corr_cap + s) * 3;
+                        o[0] = X; o[1] = Y; o[2] = Z;
+                    }
+                }
+                n = natoms + ncorr;
+            }
+            if (tid == 0 && p.ncorr) p.ncorr[fr] = ncorr;
+        } else if (natoms > cap) {
+            if (tid == 0) atomicOr(&ctl[4], GTA_B200_ST_CAPACITY);
+        }
+        if (n < 2 && tid == 0) atomicOr(&ctl[4], GTA_B200_ST_TOO_FEW_POINTS);    // delaunay_tri.c:416-421
+        __syncthreads();
+
+        double a3 = 0.0, a2 = 0.0;
+        unsigned ntri_total = 0;
+        if (ctl[4] == 0) {
+            // -------------------------------------------------------- K1a: sort positions by (x, y)
+            int np2 = 2; while (np2 < n) np2 <<= 1;
+            for (int i = tid; i < np2; i += T) perm[i] = (i < n) ? (u16)i : (u16)GT_NIL;
+            __syncthreads();
+            for (int k = 2; k <= np2; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int t = tid; t < (np2 >> 1); t += T) {
+                        int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));      // lower index of the pair
+                        int l = i | j;
+                        unsigned a = perm[i], b = perm[l];
+                        // strict (x, y) order, GT_NIL padding = +inf; exact duplicates tie and stay put
+                        auto greater = [&](unsigned u, unsigned v) -> bool {
+                            if (u == GT_NIL) return v != GT_NIL;
+                            if (v == GT_NIL) return false;
+                            Pt pu = tmp_xy[u], pv = tmp_xy[v];
+                            return (pu.x > pv.x) || (pu.x == pv.x && pu.y > pv.y);
+                        };
+                        bool up = ((i & k) == 0);
+                        if (up ? greater(a, b) : greater(b, a)) { perm[i] = (u16)b; perm[l] = (u16)a; }
+                    }
+                    __syncthreads();
+                }
+            }
+            // gather into sorted order (the -corr scratch in `pt` is dead now)
+            for (int i = tid; i < n; i += T) { int o = perm[i]; pt[i] = tmp_xy[o]; zs[i] = tmp_z[o]; }
+            __syncthreads();
+            // input contract of the reference's sort / duplicate pass (delaunay_tri.c:115-123, :440-452)
+            for (int i = tid + 1; i < n; i += T) {
+                double dx = pt[i].x - pt[i - 1].x, dy = pt[i].y - pt[i - 1].y;
+                if (dx < 1e-12 && dx > -1e-12) {
+                    if (dy < 1e-12 && dy > -1e-12) atomicOr(&ctl[4], GTA_B200_ST_DUPLICATE);
+                    else if (dx != 0.0) atomicOr(&ctl[4], GTA_B200_ST_NEAR_TIE_X);
+                }
+            }
+            for (int i = tid; i < n; i += T) head[i] = (u16)GT_NIL;
+            __syncthreads();
+        }
+        if (ctl[4] == 0) {
+            // -------------------------------------------------------- K1b: bottom-up D&C
+            Frame f;
+            f.pt = pt; f.head = head; f.dst = dst; f.nxt = nxt; f.prv = prv;
+            f.bump = &ctl[0]; f.stack = &ctl[1]; f.err = &ctl[2]; f.n = n; f.cap_e = cap_e;
+            Lane ln; ln.free_head = GT_NIL;
+            const int D = tree_depth(n);
+            for (int d = D; d >= 0; --d) {
+                for (int k = tid; k < (1 << d); k += T) process_node(f, ln, d, k);
+                __syncthreads();
+                flush_lane(f, ln);
+                __syncthreads();
+                if (ctl[2]) break;
+            }
+            // -------------------------------------------------------- K2: enumerate + area
+            if (ctl[2] == 0) {
+                unsigned base = 0;
+                for (int i0 = 0; i0 < n; i0 += T) {
+                    const int i = i0 + tid;
+                    unsigned offs = 0, tot = 0;
+                    if (p.tri || p.ntri) {
+                        unsigned cnt = (i < n) ? (unsigned)vertex_triangles(f, i, [](int, int) {}) : 0u;
+                        offs = block_exclusive_scan<T>(cnt, scan, &tot) + base;
+                    }
+                    if (i < n) {
+                        const Pt pi = pt[i]; const double zi = zs[i];
+                        const int oi = perm[i];
+                        int* out = p.tri ? p.tri + ((size_t)fr * p.tri_cap) * 3 : nullptr;
+                        vertex_triangles(f, i, [&](int n1, int n2) {
+                            Pt p1 = pt[n1], p2 = pt[n2];
+                            a3 += tri_area3(pi.x, pi.y, zi, p1.x, p1.y, zs[n1], p2.x, p2.y, zs[n2]);
+                            if (want2d) a2 += tri_area3(pi.x, pi.y, 0.0, p1.x, p1.y, 0.0, p2.x, p2.y, 0.0);
+                            if (out && (int)offs < p.tri_cap) {
+                                out[3 * offs] = oi; out[3 * offs + 1] = perm[n1]; out[3 * offs + 2] = perm[n2];
+                            }
+                            ++offs;
+                        });
+                    }
+                    base += tot;
+                }
+                ntri_total = base;
+            }
+        }
+        // ------------------------------------------------------------ block reduction (fixed order)
+        {
+            const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a3 += __shfl_down_sync(0xffffffffu, a3, o);
+                a2 += __shfl_down_sync(0xffffffffu, a2, o);
+            }
+            if (lane == 0) { red[warp] = a3; red[32 + warp] = a2; }
+            __syncthreads();
+            if (tid == 0) {
+                double s3 = 0.0, s2 = 0.0;
+                for (int w = 0; w < T / 32; ++w) { s3 += red[w]; s2 += red[32 + w]; }
+                unsigned e = ctl[2];
+                int st = (int)ctl[4];
+                if (e & GT_ERR_POOL) st |= GTA_B200_ST_POOL;
+                if (e & GT_ERR_RANGE) st |= GTA_B200_ST_PRECISION_RANGE;
+                if (e & GT_ERR_RING) st |= GTA_B200_ST_INTERNAL;
+                if (st & ~GTA_B200_ST_TOO_FEW_POINTS) { s3 = __longlong_as_double(0x7ff8000000000000ll); s2 = s3; }
+                if (p.area) p.area[fr] = s3;
+                if (p.area2d && want2d) p.area2d[fr] = s2;
+                if (p.areabox) p.areabox[fr] = bx * by;                       // gta_tri.c:116, :316
+                if (p.status) p.status[fr] = st;
+                if (p.ntri) p.ntri[fr] = st ? 0 : (int)ntri_total;
+            }
+        }
+    }
+}
+
+// Array evaluation of the predicates (self-test hook; also exercises the exact stage directly).
+__global__ void orient2d_signs_kernel(const double* pts, int n, int* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* c = pts + 6 * (size_t)i; int re = 0;
+    int s = orient2d_sign(c[0], c[1], c[2], c[3], c[4], c[5], &re);
+    out[i] = re ? 2 : s;
+}
+__global__ void incircle_signs_kernel(const double* pts, int n, int* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* c = pts + 8 * (size_t)i; int re = 0;
+    int s = incircle_sign(c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], &re);
+    out[i] = re ? 2 : s;
+}
+
+}  // namespace gt

@@ -1,0 +1,100 @@
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def _has_gpu():
+    try:
+        import g_tessla_b200 as g
+        return g.lib().gta_b200_device_count() > 0
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    # -m gpu on a box without a device must fail loudly, not skip: only skip when not selected
+    pass
+
+
+@pytest.fixture(scope="session")
+def port():
+    from oracle import PortOracle
+    return PortOracle()
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """The unmodified reference (oracle/_ref); prebuilt .so travels to the GPU box."""
+    from oracle import RefOracle, ref_available, build_oracles
+    if not ref_available():
+        if os.path.isdir("/root/reference/src"):
+            build_oracles(ref=True)
+        else:
+            pytest.skip("oracle/_ref not built and /root/reference absent")
+    return RefOracle()
+
+
+@pytest.fixture(scope="session")
+def checker(port):
+    """Best available CPU checker: the compiled reference if present, else the pinned port."""
+    from oracle import RefOracle, ref_available
+    return RefOracle() if ref_available() else port
+
+
+@pytest.fixture(scope="session")
+def emu():
+    """Host build of the device headers (tests/emu/emu_dt.cpp) -- test infrastructure."""
+    d = os.path.join(ROOT, "tests", "emu")
+    so = os.path.join(d, "libemu_dt.so")
+    srcs = [os.path.join(d, "emu_dt.cpp")] + [os.path.join(ROOT, "g_tessla_b200", "csrc", f)
+                                               for f in ("dt_core.cuh", "gt_predicates.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++",
+                               "-o", so, srcs[0]])
+    L = C.CDLL(so)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    L.emu_triangulate.argtypes = [dp, C.c_int, ip]
+    for n in ("emu_orient2d_signs", "emu_incircle_signs", "emu_orient2d_exact", "emu_incircle_exact"):
+        getattr(L, n).argtypes = [dp, C.c_int, ip]
+
+    class Emu:
+        def triangulate(self, p):
+            p = np.ascontiguousarray(p, dtype=np.float64)
+            out = np.empty(3 * 2 * max(len(p), 1), dtype=np.int32)
+            nt = L.emu_triangulate(p.ctypes.data_as(dp), len(p), out.ctypes.data_as(ip))
+            assert nt >= 0, "emu error %d" % nt
+            return out[:3 * nt].reshape(-1, 3).copy()
+
+        def signs(self, fn, p, w):
+            p = np.ascontiguousarray(p, dtype=np.float64).reshape(-1, w)
+            out = np.empty(len(p), dtype=np.int32)
+            getattr(L, fn)(p.ctypes.data_as(dp), len(p), out.ctypes.data_as(ip))
+            return out
+    return Emu()
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return {k: np.load(os.path.join(GOLDEN, k + ".npz")) for k in ("dtriangulate", "tessellate", "predicates")}
+
+
+@pytest.fixture(scope="session")
+def gta():
+    """The product binding; on the GPU box the library must load and see a device."""
+    import g_tessla_b200 as g
+    L = g.lib()
+    assert L.gta_b200_device_count() > 0, "no CUDA device visible to libgtessla_b200.so"
+    return g

@@ -1,0 +1,67 @@
+// tests/emu/emu_dt.cpp -- TEST INFRASTRUCTURE ONLY.
+// Host build of the device headers (g_tessla_b200/csrc/dt_core.cuh, gt_predicates.cuh) driven
+// sequentially in the kernel's order (sort -> bottom-up levels -> enumeration), so the merge
+// logic and the exact predicates can be checked against the oracle without a GPU.
+// Never linked into libgtessla_b200.so; the product has no CPU path.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <vector>
+#include "../../g_tessla_b200/csrc/dt_core.cuh"
+
+extern "C" {
+
+// points [n][2] -> triangles in emission order (indices into the input). Returns ntri or -(err bits).
+int emu_triangulate(const double* points, int n, int* tri_out) {
+    using namespace gt;
+    if (n < 2) return -1000;
+    std::vector<int> perm(n);
+    std::iota(perm.begin(), perm.end(), 0);
+    std::sort(perm.begin(), perm.end(), [&](int u, int v) {
+        double ux = points[2 * u], uy = points[2 * u + 1], vx = points[2 * v], vy = points[2 * v + 1];
+        return ux < vx || (ux == vx && uy < vy);
+    });
+    std::vector<Pt> pt(n);
+    for (int i = 0; i < n; ++i) { pt[i].x = points[2 * perm[i]]; pt[i].y = points[2 * perm[i] + 1]; }
+    const int cap_e = 3 * n + 64;
+    std::vector<u16> head(n, GT_NIL), dst(2 * cap_e), nxt(2 * cap_e), prv(2 * cap_e);
+    uint32_t bump = 0, stack = GT_NIL, err = 0;
+    Frame f;
+    f.pt = pt.data(); f.head = head.data(); f.dst = dst.data(); f.nxt = nxt.data(); f.prv = prv.data();
+    f.bump = &bump; f.stack = &stack; f.err = &err; f.n = n; f.cap_e = cap_e;
+    const int D = tree_depth(n);
+    for (int d = D; d >= 0; --d) {
+        // one "lane" per node, flushed at the end of the level like the kernel does
+        std::vector<Lane> lanes(1 << d);
+        for (int k = 0; k < (1 << d); ++k) { lanes[k].free_head = GT_NIL; process_node(f, lanes[k], d, k); }
+        for (int k = 0; k < (1 << d); ++k) flush_lane(f, lanes[k]);
+        if (err) return -(int)err;
+    }
+    int nt = 0;
+    for (int i = 0; i < n; ++i)
+        vertex_triangles(f, i, [&](int n1, int n2) {
+            tri_out[3 * nt] = perm[i]; tri_out[3 * nt + 1] = perm[n1]; tri_out[3 * nt + 2] = perm[n2];
+            ++nt;
+        });
+    return nt;
+}
+
+void emu_orient2d_signs(const double* p, int n, int* out) {
+    for (int i = 0; i < n; ++i) { int re = 0; const double* c = p + 6 * (size_t)i;
+        int s = gt::orient2d_sign(c[0], c[1], c[2], c[3], c[4], c[5], &re); out[i] = re ? 2 : s; }
+}
+void emu_incircle_signs(const double* p, int n, int* out) {
+    for (int i = 0; i < n; ++i) { int re = 0; const double* c = p + 8 * (size_t)i;
+        int s = gt::incircle_sign(c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], &re); out[i] = re ? 2 : s; }
+}
+// exact stage only (bypasses the FP64 filter)
+void emu_orient2d_exact(const double* p, int n, int* out) {
+    for (int i = 0; i < n; ++i) { int re = 0; const double* c = p + 6 * (size_t)i;
+        int s = gt::orient2d_exact(c[0], c[1], c[2], c[3], c[4], c[5], &re); out[i] = re ? 2 : s; }
+}
+void emu_incircle_exact(const double* p, int n, int* out) {
+    for (int i = 0; i < n; ++i) { int re = 0; const double* c = p + 8 * (size_t)i;
+        int s = gt::incircle_exact(c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], &re); out[i] = re ? 2 : s; }
+}
+}

@@ -1,0 +1,142 @@
+"""GPU: the CUDA path, called through the C-ABI, against the CPU oracle and the golden fixtures."""
+import numpy as np
+import pytest
+
+from g_tessla_b200 import synth
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12      # north_star: per-frame areas within 1e-12 relative in FP64
+
+
+def _canon(t):
+    return synth.canonical_triangles(t)
+
+
+def test_predicate_signs(gta, golden):
+    g = golden["predicates"]
+    assert np.array_equal(gta.api.orient2d_signs(g["o2d"]), g["o2d_sign"])
+    assert np.array_equal(gta.api.incircle_signs(g["icc"]), g["icc_sign"])
+
+
+def test_golden_triangulations(gta, golden):
+    g = golden["dtriangulate"]
+    for k in g.files:
+        if not k.startswith("pts_"):
+            continue
+        tri, st = gta.triangulate(g[k])
+        assert st == 0, (k, st)
+        want = g["tri_" + k[4:]]
+        assert np.array_equal(_canon(tri), _canon(want)), k          # bit-exact index set
+        assert np.array_equal(tri, want), k                          # and the reference's emission order
+
+
+@pytest.mark.parametrize("cfg", [1, 2, 3, 5])
+def test_golden_tessellate(gta, golden, cfg):
+    t = golden["tessellate"]
+    nfr = int(t["cfg%d_nframes" % cfg])
+    c = synth.config(cfg, nframes=nfr)
+    r = gta.tessellate(c["xyz"], c["box"], c["espace"], c["flags"], want_tri=True, want_corr=True)
+    assert (r["status"] == 0).all(), r["status"]
+    assert np.array_equal(r["ncorr"], t["cfg%d_ncorr" % cfg])
+    nc = int(r["ncorr"].max())
+    assert np.array_equal(r["corr"][:, :nc], t["cfg%d_corr" % cfg][:, :nc])      # appended points bit-exact
+    assert np.array_equal(r["areabox"], t["cfg%d_areabox" % cfg])
+    assert np.allclose(r["area"], t["cfg%d_area" % cfg], rtol=RTOL, atol=0)
+    if cfg == 2:
+        assert np.allclose(r["area2d"], t["cfg2_area2d"], rtol=RTOL, atol=0)
+        assert np.allclose(r["area2d"], r["areabox"], rtol=RTOL, atol=0)
+    assert np.array_equal(_canon(r["tri"][0]), _canon(t["cfg%d_tri0" % cfg]))
+
+
+@pytest.mark.parametrize("cfg,nfr", [(1, 1000), (2, 300), (3, 200), (5, 200)])
+def test_configs_vs_oracle(gta, checker, cfg, nfr):
+    c = synth.config(cfg, nframes=nfr)
+    want = checker.tessellate(c["xyz"], c["box"], c["espace"], c["flags"], nthreads=0, want_corr=True)
+    r = gta.tessellate(c["xyz"], c["box"], c["espace"], c["flags"], want_tri=True, want_corr=True)
+    assert (r["status"] == 0).all()
+    nc = int(r["ncorr"].max())
+    assert np.array_equal(r["ncorr"], want["ncorr"])
+    assert np.array_equal(r["corr"][:, :nc], want["corr"][:, :nc])
+    assert np.array_equal(r["areabox"], want["areabox"])
+    assert np.allclose(r["area"], want["area"], rtol=RTOL, atol=0)
+    if cfg == 2:
+        assert np.allclose(r["area2d"], want["area2d"], rtol=RTOL, atol=0)
+    for f in range(0, nfr, max(1, nfr // 25)):
+        p = np.concatenate([c["xyz"][f, :, :2], want["corr"][f, :int(want["ncorr"][f]), :2]])
+        tri, _ = checker.triangulate(p)
+        assert np.array_equal(_canon(r["tri"][f]), _canon(tri)), (cfg, f)
+        assert len(tri) == r["ntri"][f]
+
+
+def test_raw_point_sets_many_sizes(gta, checker):
+    rng = np.random.default_rng(21)
+    for n in [2, 3, 4, 5, 6, 7, 8, 9, 15, 16, 17, 31, 32, 33, 64, 100, 191, 192, 193, 511, 512, 513, 1156, 2047, 3000]:
+        p = rng.random((3, n, 2)) * 10
+        tris, st = gta.triangulate(p)
+        assert (st == 0).all(), (n, st)
+        for f in range(3):
+            want, _ = checker.triangulate(p[f])
+            assert np.array_equal(tris[f], want), (n, f)
+
+
+def test_status_codes(gta):
+    # duplicate point
+    p = np.random.default_rng(1).random((2, 20, 2))
+    p[1, 7] = p[1, 3]
+    _, st = gta.triangulate(p)
+    assert st[0] == 0 and st[1] & 2
+    # non-finite
+    p = np.random.default_rng(1).random((1, 20, 2)); p[0, 0, 0] = np.nan
+    _, st = gta.triangulate(p)
+    assert st[0] & 64
+    # atom outside the box with -corr
+    c = synth.config(1, nframes=2)
+    c["xyz"][1, 5, 0] = c["box"][1, 0] * 3.0
+    r = gta.tessellate(c["xyz"], c["box"], c["espace"], c["flags"])
+    assert r["status"][0] == 0 and r["status"][1] & 16 and np.isnan(r["area"][1])
+    # a single point: the reference prints TRIANGULATION ERROR and produces nothing
+    r = gta.tessellate(np.zeros((1, 1, 3)), None, flags=0)
+    assert r["status"][0] & 1
+
+
+def test_empty_and_chunked(gta, checker):
+    r = gta.tessellate(np.zeros((0, 64, 3)), np.zeros((0, 3)))
+    assert len(r["area"]) == 0
+    c = synth.config(1, nframes=777)
+    a = gta.tessellate(c["xyz"], c["box"], c["espace"], c["flags"], nstreams=1)
+    b = gta.tessellate(c["xyz"], c["box"], c["espace"], c["flags"], nstreams=5)
+    assert np.array_equal(a["area"], b["area"])                 # chunking never changes results
+    # logical shards concatenated == unsharded (multi-GPU correctness on one GPU)
+    parts = [gta.tessellate(c["xyz"][s], c["box"][s], c["espace"], c["flags"])["area"]
+             for s in (slice(0, 300), slice(300, 777))]
+    assert np.array_equal(np.concatenate(parts), a["area"])
+
+
+def test_full_size_properties(gta):
+    """cfg 3 at a large frame count: size-independent properties (no oracle at this size)."""
+    c = synth.config(3, nframes=4000)
+    fl = c["flags"] | synth.GTA_2D
+    r = gta.tessellate(c["xyz"], c["box"], c["espace"], fl)
+    assert (r["status"] == 0).all()
+    assert np.allclose(r["area2d"], r["areabox"], rtol=RTOL, atol=0)      # reference README.md:16
+    assert (r["area"] >= r["area2d"] * (1 - 1e-12)).all()                   # lifting never shrinks a triangle
+    nx = (c["box"][:, 0] / 0.8).astype(int); ny = (c["box"][:, 1] / 0.8).astype(int)
+    n = 1024 + 4 + 2 * nx + 2 * ny
+    h = 4 + 2 * nx + 2 * ny                                                  # every -corr point is on the hull
+    assert np.array_equal(r["ntri"], 2 * (n - 1) - h)                        # reference delaunay_tri.c:608
+    # permuting the atoms of a frame permutes indices only: areas agree to rounding of the sum order
+    perm = np.random.default_rng(0).permutation(1024)
+    r2 = gta.tessellate(c["xyz"][:200, perm], c["box"][:200], c["espace"], fl)
+    assert np.allclose(r2["area"], r["area"][:200], rtol=1e-9, atol=0)
+
+
+def test_device_resident_entry(gta):
+    import torch
+    c = synth.config(3, nframes=64)
+    want = gta.tessellate(c["xyz"], c["box"], c["espace"], c["flags"])
+    T = gta.Tessellator(64, 1024, 1024 + 140, c["espace"], c["flags"])
+    dx = torch.from_numpy(c["xyz"]).cuda(); db = torch.from_numpy(c["box"]).cuda()
+    T.run(dx, db, 3)
+    torch.cuda.synchronize()
+    assert np.array_equal(T.area.cpu().numpy(), want["area"])
+    assert (T.status.cpu().numpy() == 0).all()
