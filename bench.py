@@ -229,7 +229,11 @@ def run_native(args):
     e2e_s = time.perf_counter() - t0
     clk = clocks.stop() if rank == 0 else None
     if not np.array_equal(area, area_dev) or status.any() or status_bad:
-        raise SystemExit("bench.py: device-resident and host-batch results differ or a frame failed (status != 0)")
+        st_dev = T.status.cpu().numpy()
+        raise SystemExit("bench.py: device-resident and host-batch results differ or a frame failed: "
+                         "status(dev) %s status(host) %s, %d areas differ, first %s vs %s" % (
+                             np.unique(st_dev, return_counts=True), np.unique(status, return_counts=True),
+                             int((area != area_dev).sum()), area[:3], area_dev[:3]))
 
     times = torch.tensor([total_ms, e2e_s * 1e3, kern_ms], dtype=torch.float64, device=dev)
     if world > 1:

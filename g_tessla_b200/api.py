@@ -83,8 +83,9 @@ def tessellate(xyz, box, espace=0.8, flags=GTA_CORRECT, device=-1, nstreams=0, n
     F, N, D = xyz.shape
     bstride = 0
     if box is not None:
-        box = np.ascontiguousarray(box, dtype=np.float64).reshape(F, -1)
-        bstride = box.shape[1]
+        box = np.ascontiguousarray(box, dtype=np.float64)
+        bstride = int(np.prod(box.shape[1:]))
+        box = box.reshape(F, bstride)
         if bstride not in (2, 3, 9):
             raise ValueError("box must be [F,2], [F,3] (diagonal) or [F,9] (matrix)")
     area = np.zeros(F); areabox = np.zeros(F)

@@ -55,25 +55,28 @@ GT_INLINE void atomic_or_u32(uint32_t* p, uint32_t v) { *p |= v; }
 #endif
 
 // ---------------------------------------------------------------- predicates on vertices
-GT_INLINE bool ccw(const Frame& f, int a, int b, int c) {
-    Pt pa = f.pt[a], pb = f.pt[b], pc = f.pt[c];
-    int re = 0;
-    int s = orient2d_sign(pa.x, pa.y, pb.x, pb.y, pc.x, pc.y, &re);
-    if (re) atomic_or_u32(f.err, GT_ERR_RANGE);
+// Out of line on the device: the merge code calls them from ~20 sites, and one shared copy keeps
+// the kernel's register count and instruction-cache footprint down (the walk is latency bound,
+// a call costs less than the i-cache misses of 20 inlined incircle bodies).
+GT_NOINLINE bool ccw_pts(const Pt* pt, uint32_t* err, int a, int b, int c) {
+    Pt pa = pt[a], pb = pt[b], pc = pt[c];
+    int s = orient2d_sign(pa.x, pa.y, pb.x, pb.y, pc.x, pc.y);
+    if (s == GT_RANGE_ERR) { atomic_or_u32(err, GT_ERR_RANGE); return false; }
     return s > 0;
 }
-GT_INLINE bool right_of(const Frame& f, int x, int ea, int eb) { return ccw(f, x, eb, ea); }   // reference :141-145
-GT_INLINE bool left_of(const Frame& f, int x, int ea, int eb) { return ccw(f, x, ea, eb); }    // reference :147-151
-GT_INLINE bool in_circle(const Frame& f, int a, int b, int c, int d) {
+GT_NOINLINE bool in_circle_pts(const Pt* pt, uint32_t* err, int a, int b, int c, int d) {
     // incircle with a repeated point is exactly 0 (two equal rows) -- the commonest
     // degenerate call of the merge loop (r2 == li when ri has two neighbours); skip the math.
     if (a == d || b == d || c == d || a == b || a == c || b == c) return false;
-    Pt pa = f.pt[a], pb = f.pt[b], pc = f.pt[c], pd = f.pt[d];
-    int re = 0;
-    int s = incircle_sign(pa.x, pa.y, pb.x, pb.y, pc.x, pc.y, pd.x, pd.y, &re);
-    if (re) atomic_or_u32(f.err, GT_ERR_RANGE);
+    Pt pa = pt[a], pb = pt[b], pc = pt[c], pd = pt[d];
+    int s = incircle_sign(pa.x, pa.y, pb.x, pb.y, pc.x, pc.y, pd.x, pd.y);
+    if (s == GT_RANGE_ERR) { atomic_or_u32(err, GT_ERR_RANGE); return false; }
     return s > 0;
 }
+GT_INLINE bool ccw(const Frame& f, int a, int b, int c) { return ccw_pts(f.pt, f.err, a, b, c); }
+GT_INLINE bool right_of(const Frame& f, int x, int ea, int eb) { return ccw(f, x, eb, ea); }   // reference :141-145
+GT_INLINE bool left_of(const Frame& f, int x, int ea, int eb) { return ccw(f, x, ea, eb); }    // reference :147-151
+GT_INLINE bool in_circle(const Frame& f, int a, int b, int c, int d) { return in_circle_pts(f.pt, f.err, a, b, c, d); }
 
 // ---------------------------------------------------------------- edge pool
 GT_INLINE int edge_alloc(const Frame& f, Lane& ln) {
@@ -143,6 +146,35 @@ GT_INLINE void ring_insert(const Frame& f, int parent, int in, int h) {
     }
 }
 
+// insertNode with the position known from the topology of the merge. The reference finds the slot
+// by orientation scans from "first" (:216-238). Its first test (is the new neighbour right of the
+// "first" ray?) also decides whether "first" moves, so it is kept, and so is the clockwise scan that
+// follows a positive answer (:217-224). When the answer is negative the reference walks CCW until the
+// new ray is no longer left of the current one, i.e. to the ray's angular slot; inside a merge that
+// slot is known (next to the previous cross edge, or in the hull gap), so the walk and its orient2d
+// calls are skipped. -DGT_VERIFY_HINT re-runs the walk and flags any disagreement (host fuzz only).
+GT_INLINE void ring_insert_hint(const Frame& f, int parent, int in, int h, int after) {
+    f.dst[h] = (u16)in;
+    int hd = f.head[parent];
+    if (right_of(f, in, parent, f.dst[hd])) {
+        int cur = f.prv[hd];
+        while (cur != hd && right_of(f, in, parent, f.dst[cur])) cur = f.prv[cur];
+        if (cur == hd) {
+            f.head[parent] = (u16)h;
+            link_after(f, f.prv[cur], h);
+        } else {
+            link_after(f, cur, h);
+        }
+    } else {
+#ifdef GT_VERIFY_HINT
+        int cur = f.nxt[hd];
+        while (cur != hd && left_of(f, in, parent, f.dst[cur])) cur = f.nxt[cur];
+        if (f.prv[cur] != after) atomic_or_u32(f.err, GT_ERR_RING);
+#endif
+        link_after(f, after, h);
+    }
+}
+
 // connectVerts (reference :270-275): returns the half-edge a->b (its twin b->a is h^1).
 GT_INLINE int connect(const Frame& f, Lane& ln, int a, int b) {
     int e = edge_alloc(f, ln);
@@ -201,10 +233,19 @@ GT_INLINE void merge(const Frame& f, Lane& ln, int mid) {
             else break;
         }
     }
+    // First cross edge = lower tangent: both ends receive it in their hull gap (before "first").
     int li = lx, ri = ly;
+    int e;                                      // e = li->ri, e^1 = ri->li
+    {
+        int ne = edge_alloc(f, ln);
+        if (ne < 0) return;
+        e = 2 * ne;
+        ring_insert_hint(f, li, ri, e, f.prv[f.head[li]]);
+        ring_insert_hint(f, ri, li, e ^ 1, f.prv[f.head[ri]]);
+    }
+    int guard = 8 * f.n + 64;
     while (li != ux || ri != uy) {
-        int e = connect(f, ln, li, ri);         // e = li->ri, e^1 = ri->li
-        if (e < 0) return;
+        if (--guard < 0) { atomic_or_u32(f.err, GT_ERR_RING); return; }
         bool a = false, b = false;
         int hr1 = f.prv[e ^ 1];                 // ri -> pred(ri, li)
         int r1 = f.dst[hr1];
@@ -228,12 +269,25 @@ GT_INLINE void merge(const Frame& f, Lane& ln, int mid) {
                 hl2 = f.nxt[hl1]; l2 = f.dst[hl2];
             }
         } else b = true;
-        if (a) li = l1;
-        else if (b) ri = r1;
-        else if (!in_circle(f, li, ri, r1, l1)) ri = r1;     // ties prefer the right candidate (:588-593)
-        else li = l1;
+        // ties prefer the right candidate (:588-593)
+        const bool go_left = a ? true : (b ? false : in_circle(f, li, ri, r1, l1));
+        int ne = edge_alloc(f, ln);
+        if (ne < 0) return;
+        if (go_left) {
+            // new edge l1 -> ri: at l1 it follows (CCW) the edge back to the old li, at ri it
+            // precedes the old cross edge ri -> li
+            ring_insert_hint(f, l1, ri, 2 * ne, hl1 ^ 1);
+            ring_insert_hint(f, ri, l1, 2 * ne + 1, f.prv[e ^ 1]);
+            li = l1;
+        } else {
+            // new edge li -> r1: at li it follows the old cross edge li -> ri, at r1 it precedes
+            // the edge back to the old ri
+            ring_insert_hint(f, li, r1, 2 * ne, e);
+            ring_insert_hint(f, r1, li, 2 * ne + 1, f.prv[hr1 ^ 1]);
+            ri = r1;
+        }
+        e = 2 * ne;
     }
-    connect(f, ln, ux, uy);
 }
 
 // ---------------------------------------------------------------- recursion tree

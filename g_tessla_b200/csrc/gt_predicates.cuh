@@ -18,8 +18,9 @@
 //      polynomial evaluated without rounding.  Branch-light, no local-memory expansions;
 //      this replaces Shewchuk's adaptive expansion stages B-D, which are a poor fit for a
 //      GPU (up to 2 x 1152-double scratch per thread, predicates.c:2674).
-//      Operands whose bit spread exceeds 251 bits (e.g. 1e-40 next to 1e+20) are reported
-//      through *range_err; the frame is then flagged GTA_B200_ST_PRECISION_RANGE.
+//      Operands whose bit spread exceeds 251 bits (e.g. 1e-40 next to 1e+20) return
+//      GT_RANGE_ERR instead of a sign (by value: an out-parameter would force a local-memory
+//      round trip on every call); the frame is then flagged GTA_B200_ST_PRECISION_RANGE.
 //
 // The file is also compilable as plain host C++ (tests/emu only) so that the kernel logic
 // can be exercised without a GPU; the product library contains the device build only.
@@ -45,6 +46,7 @@ namespace gt {
 #define GT_EPS 1.1102230246251565e-16
 #define GT_CCW_ERRBOUND_A ((3.0 + 16.0 * GT_EPS) * GT_EPS)
 #define GT_ICC_ERRBOUND_A ((10.0 + 96.0 * GT_EPS) * GT_EPS)
+#define GT_RANGE_ERR 2      // returned instead of a sign when the exact stage cannot represent the operands
 
 GT_INLINE int64_t dbl_bits(double v) {
 #if defined(__CUDA_ARCH__)
@@ -188,7 +190,7 @@ template <int W> GT_INLINE int incircle_big(const double* c, int base) {
 
 // Exact sign of orient2d. Word count from the operands' bit spread: every coordinate needs
 // spread+1 bits, differences one more, the degree-2 determinant 2*(spread+2)+1 <= 128*W - 1.
-GT_NOINLINE int orient2d_exact(double ax, double ay, double bx, double by, double cx, double cy, int* range_err) {
+GT_NOINLINE int orient2d_exact(double ax, double ay, double bx, double by, double cx, double cy) {
     double c[6] = {ax, ay, bx, by, cx, cy};
     Spread s; s.lo = 1 << 30; s.hi = -(1 << 30);
 #pragma unroll
@@ -198,12 +200,11 @@ GT_NOINLINE int orient2d_exact(double ax, double ay, double bx, double by, doubl
     if (span <= 59) return orient2d_big<1>(c, s.lo);
     if (span <= 123) return orient2d_big<2>(c, s.lo);
     if (span <= 251) return orient2d_big<4>(c, s.lo);
-    *range_err = 1;
-    return 0;
+    return GT_RANGE_ERR;
 }
 // Exact sign of incircle: degree 4, 4*(spread+2)+3 <= 256*W - 1.
 GT_NOINLINE int incircle_exact(double ax, double ay, double bx, double by, double cx, double cy,
-                               double dx, double dy, int* range_err) {
+                               double dx, double dy) {
     double c[8] = {ax, ay, bx, by, cx, cy, dx, dy};
     Spread s; s.lo = 1 << 30; s.hi = -(1 << 30);
 #pragma unroll
@@ -213,14 +214,11 @@ GT_NOINLINE int incircle_exact(double ax, double ay, double bx, double by, doubl
     if (span <= 59) return incircle_big<1>(c, s.lo);
     if (span <= 123) return incircle_big<2>(c, s.lo);
     if (span <= 251) return incircle_big<4>(c, s.lo);
-    *range_err = 1;
-    return 0;
+    return GT_RANGE_ERR;
 }
 
 // ---------------------------------------------------------------- public predicates
-// Counters (optional, nullptr in the product kernel's fast build) let tests see how often
-// the exact stage ran.
-GT_INLINE int orient2d_sign(double ax, double ay, double bx, double by, double cx, double cy, int* range_err) {
+GT_INLINE int orient2d_sign(double ax, double ay, double bx, double by, double cx, double cy) {
     // stage A: reference predicates.c:1628-1651
     double detleft = (ax - cx) * (by - cy);
     double detright = (ay - cy) * (bx - cx);
@@ -238,11 +236,11 @@ GT_INLINE int orient2d_sign(double ax, double ay, double bx, double by, double c
     double errbound = GT_CCW_ERRBOUND_A * detsum;
     if (det >= errbound) return 1;
     if (-det >= errbound) return -1;
-    return orient2d_exact(ax, ay, bx, by, cx, cy, range_err);
+    return orient2d_exact(ax, ay, bx, by, cx, cy);
 }
 
 GT_INLINE int incircle_sign(double ax, double ay, double bx, double by, double cx, double cy,
-                            double dx, double dy, int* range_err) {
+                            double dx, double dy) {
     // stage A: reference predicates.c:3238-3267
     double adx = ax - dx, bdx = bx - dx, cdx = cx - dx;
     double ady = ay - dy, bdy = by - dy, cdy = cy - dy;
@@ -255,7 +253,7 @@ GT_INLINE int incircle_sign(double ax, double ay, double bx, double by, double c
     double errbound = GT_ICC_ERRBOUND_A * permanent;
     if (det > errbound) return 1;
     if (-det > errbound) return -1;
-    return incircle_exact(ax, ay, bx, by, cx, cy, dx, dy, range_err);
+    return incircle_exact(ax, ay, bx, by, cx, cy, dx, dy);
 }
 
 }  // namespace gt

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -22,6 +23,7 @@ namespace {
 thread_local std::string g_err;
 thread_local double g_last_kernel_ms = 0.0;
 thread_local int g_last_launches = 0;
+unsigned long long* g_dbg = nullptr;      // device phase-timer array (debug builds only)
 
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define CK(call)                                                                              \
@@ -32,6 +34,14 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
     } while (0)
 
 int round_even(int v) { return (v + 1) & ~1; }
+// Levels of the recursion tree with at most this many nodes run as 16-lane cooperative merges
+// (tunable for experiments: GTA_B200_COOP_NODES).
+int coop_nodes_for(int threads) {
+    static int env = -2;
+    if (env == -2) { const char* e = getenv("GTA_B200_COOP_NODES"); env = e ? atoi(e) : -1; }
+    if (env >= 0) return env;
+    return threads >= 128 ? 32 : (threads >= 64 ? 16 : 4);
+}
 int pow2_ge(int v) { int p = 2; while (p < v) p <<= 1; return p; }
 
 struct Shape { int threads; size_t smem; int cap, cap_p2; };
@@ -47,11 +57,11 @@ int smem_limit() {
     return lim;
 }
 
-Shape shape_for(int max_points) {
+Shape shape_for(int max_points, int natoms = 0) {
     Shape s;
     s.cap = round_even(std::max(max_points, 4));
     s.cap_p2 = pow2_ge(s.cap);
-    s.smem = gt::smem_bytes_for(s.cap, s.cap_p2);
+    s.smem = gt::smem_bytes_for(s.cap, s.cap_p2, natoms);
     s.threads = s.cap <= 192 ? 32 : (s.cap <= 512 ? 64 : 128);
     return s;
 }
@@ -168,7 +178,7 @@ int gta_b200_tessellate_device(const double* d_xyz, int in_dim, const double* d_
     if ((flags & GTA_B200_CORRECT) && (!d_box || !(espace > 0.0)))
         return fail(GTA_B200_E_ARG, "-corr needs the box and espace > 0");
     if (nframes == 0) return GTA_B200_OK;
-    Shape s = shape_for(std::max(max_points, natoms));
+    Shape s = shape_for(std::max(max_points, natoms), natoms);
     if (s.smem > (size_t)smem_limit() || gt::pool_edges(s.cap) >= 32760)
         return fail(GTA_B200_E_TOO_LARGE, "max_points exceeds the shared-memory kernel (see gta_b200_max_points)");
     cudaStream_t st = (cudaStream_t)stream;
@@ -179,7 +189,7 @@ int gta_b200_tessellate_device(const double* d_xyz, int in_dim, const double* d_
     p.area = d_area; p.area2d = d_area2d; p.areabox = d_areabox; p.status = d_status;
     p.tri = d_tri; p.tri_cap = tri_cap; p.ntri = d_ntri;
     p.corr = d_corr; p.corr_cap = corr_cap; p.ncorr = d_ncorr;
-    p.work = d_work;
+    p.work = d_work; p.coop_nodes = coop_nodes_for(s.threads); p.dbg = g_dbg;
     CK(cudaMemsetAsync(d_work, 0, sizeof(unsigned int), st));
     return launch(p, s, st);
 }
@@ -295,7 +305,7 @@ int submit(Slot& s, const Job& j, const Shape& shp, int f0, int nf, bool src_pin
     p.status = s.d_st; p.ntri = s.d_st + c; p.ncorr = s.d_st + 2 * (size_t)c;
     p.tri = j.tri ? s.d_tri : nullptr; p.tri_cap = j.tri_cap;
     p.corr = j.corr ? s.d_corr : nullptr; p.corr_cap = j.corr_cap;
-    p.work = s.d_work;
+    p.work = s.d_work; p.coop_nodes = coop_nodes_for(shp.threads); p.dbg = g_dbg;
     CK(cudaMemsetAsync(s.d_work, 0, sizeof(unsigned int), s.st));
     CK(cudaMemsetAsync(s.d_st, 0, sizeof(int) * 3 * (size_t)c, s.st));
     CK(cudaEventRecord(s.k0, s.st));
@@ -321,7 +331,7 @@ int run_job(Job j, int device, int nstreams) {
     if (device >= 0) CK(cudaSetDevice(device));
     CK(cudaGetDevice(&device));
     j.max_points = gta_b200_max_points_for(j.box, j.box_stride, j.nframes, j.natoms, j.espace, j.flags);
-    Shape shp = shape_for(j.max_points);
+    Shape shp = shape_for(j.max_points, j.natoms);
     if (shp.smem > (size_t)smem_limit() || gt::pool_edges(shp.cap) >= 32760)
         return fail(GTA_B200_E_TOO_LARGE, "frame too large for the shared-memory kernel (see gta_b200_max_points)");
 
@@ -447,6 +457,13 @@ static int signs_common(const double* pts, int n, int* out, int device, int widt
     CK(cudaMemcpy(out, o, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
     cudaFree(d); cudaFree(o);
     return GTA_B200_OK;
+}
+// Debug hook (not in the public header): allocate / read the phase timers of GT_PHASE_TIMING builds.
+int gta_b200_dbg_timers(unsigned long long* out32, int reset) {
+    if (!g_dbg) { if (cudaMalloc((void**)&g_dbg, 32 * 8) != cudaSuccess) return -1; cudaMemset(g_dbg, 0, 32 * 8); }
+    if (out32) cudaMemcpy(out32, g_dbg, 32 * 8, cudaMemcpyDeviceToHost);
+    if (reset) cudaMemset(g_dbg, 0, 32 * 8);
+    return 0;
 }
 int gta_b200_orient2d_signs(const double* pts, int n, int* sign_out, int device) { return signs_common(pts, n, sign_out, device, 6); }
 int gta_b200_incircle_signs(const double* pts, int n, int* sign_out, int device) { return signs_common(pts, n, sign_out, device, 8); }

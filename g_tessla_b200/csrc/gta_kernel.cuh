@@ -5,14 +5,23 @@
 //   K1  lexicographic sort + Delaunay D&C           delaunay_tri.c:436, :511-601
 //   K2  triangle enumeration + area sum             delaunay_tri.c:606-635, gta_tri.c:368-410
 // fused in one launch: coordinates are read from HBM once (coalesced), everything else lives in
-// shared memory (<= ~64 B per point), and 8-24 bytes per frame go back.
+// shared memory (<= ~56 B per point; z stays in global memory), and 8-24 bytes per frame go back.
 #pragma once
 #include <cuda_runtime.h>
 #include <float.h>
 #include "dt_core.cuh"
+#include "dt_coop.cuh"
 #include "../../include/gta_b200.h"
 
 namespace gt {
+
+// -DGT_PHASE_TIMING: thread 0 of every CTA adds clock64() deltas per phase into p.dbg
+// (slots: 0 load, 1 corr, 2 sort, 3 post-sort, 4..19 D&C level d = slot-4, 20 enumerate+area, 21 frames).
+#ifdef GT_PHASE_TIMING
+#define GT_TICK(slot) do { if (tid == 0 && p.dbg) { long long t_ = clock64(); atomicAdd(&p.dbg[slot], (unsigned long long)(t_ - tick_)); tick_ = t_; } } while (0)
+#else
+#define GT_TICK(slot) do { } while (0)
+#endif
 
 struct KParams {
     const double* xyz; int in_dim;            // [nframes][natoms][in_dim]
@@ -24,17 +33,21 @@ struct KParams {
     int* tri; int tri_cap; int* ntri;
     double* corr; int corr_cap; int* ncorr;
     unsigned int* work;                        // global frame counter
+    unsigned long long* dbg;                   // phase timers (GT_PHASE_TIMING builds), else unused
+    int coop_nodes;                            // levels with at most this many nodes use 16-lane cooperative merges
 };
 
 __host__ __device__ inline int pool_edges(int cap) { return 3 * cap + 64; }
-// dynamic shared memory for a capacity of `cap` points
-__host__ __device__ inline size_t smem_bytes_for(int cap, int cap_p2) {
+// dynamic shared memory for a capacity of `cap` points of which `natoms` come from the caller
+// (the other cap - natoms slots can only be -corr points, whose z is generated in the kernel)
+__host__ __device__ inline size_t smem_bytes_for(int cap, int cap_p2, int natoms) {
     size_t b = 0;
     b += sizeof(Pt) * (size_t)cap;             // sorted xy
-    b += sizeof(double) * (size_t)cap;         // sorted z
     b += 12 * (size_t)pool_edges(cap);         // half-edge pool (dst, nxt, prv: u16 x 2 per edge each)
     b += 2 * (size_t)cap_p2;                   // perm
     b += 2 * (size_t)cap;                      // head
+    b = (b + 7) & ~(size_t)7;
+    b += 8 * (size_t)(cap > natoms ? cap - natoms : 0);   // z of the -corr points
     b = (b + 15) & ~(size_t)15;
     b += 16 * 4 + 64 * 8 + 32 * 4;             // ctl, reduction scratch, scan scratch
     return b;
@@ -72,16 +85,17 @@ __global__ void __launch_bounds__(T, MINB) tessellate_kernel(const KParams p) {
     const int tid = threadIdx.x;
     const int cap = p.cap, cap_e = pool_edges(cap);
     Pt* pt = reinterpret_cast<Pt*>(smem);
-    double* zs = reinterpret_cast<double*>(pt + cap);
-    unsigned char* pool = reinterpret_cast<unsigned char*>(zs + cap);
+    unsigned char* pool = reinterpret_cast<unsigned char*>(pt + cap);
     u16* dst = reinterpret_cast<u16*>(pool);
     u16* nxt = dst + 2 * cap_e;
     u16* prv = nxt + 2 * cap_e;
-    Pt* tmp_xy = reinterpret_cast<Pt*>(pool);                  // setup-time alias of the pool
-    double* tmp_z = reinterpret_cast<double*>(tmp_xy + cap);
+    Pt* tmp_xy = reinterpret_cast<Pt*>(pool);                  // setup-time alias of the pool (input order)
     u16* perm = reinterpret_cast<u16*>(pool + 12 * (size_t)cap_e);
     u16* head = perm + p.cap_p2;
     size_t off = (size_t)(reinterpret_cast<unsigned char*>(head + cap) - smem);
+    off = (off + 7) & ~(size_t)7;
+    double* zcorr = reinterpret_cast<double*>(smem + off);     // z of the appended -corr points
+    off += 8 * (size_t)(cap > p.natoms ? cap - p.natoms : 0);
     off = (off + 15) & ~(size_t)15;
     uint32_t* ctl = reinterpret_cast<uint32_t*>(smem + off);    // [0] bump [1] stack [2] err [3] frame [4] status
     double* red = reinterpret_cast<double*>(ctl + 16);
@@ -99,28 +113,35 @@ __global__ void __launch_bounds__(T, MINB) tessellate_kernel(const KParams p) {
         const int fr = (int)ctl[3];
         if (fr >= p.nframes) break;
 
+#ifdef GT_PHASE_TIMING
+        long long tick_ = clock64();
+#endif
         // ------------------------------------------------------------ load (coalesced)
         const double* src = p.xyz + (size_t)fr * natoms * p.in_dim;
         bool bad = false;
+        // z stays in global memory (L2-resident after this pass): it is needed again only by the
+        // -corr z interpolation and the area epilogue.
         if (p.in_dim == 3) {
             for (int k = tid; k < 3 * natoms; k += T) {
                 double v = src[k];
                 bad |= !isfinite(v);
                 int a = k / 3, c = k - 3 * a;
-                if (c == 0) tmp_xy[a].x = v; else if (c == 1) tmp_xy[a].y = v; else tmp_z[a] = v;
+                if (c == 0) tmp_xy[a].x = v; else if (c == 1) tmp_xy[a].y = v;
             }
         } else {
             for (int k = tid; k < 2 * natoms; k += T) {
                 double v = src[k];
                 bad |= !isfinite(v);
-                if (k & 1) tmp_xy[k >> 1].y = v; else { tmp_xy[k >> 1].x = v; tmp_z[k >> 1] = 0.0; }
+                if (k & 1) tmp_xy[k >> 1].y = v; else tmp_xy[k >> 1].x = v;
             }
         }
+        auto atom_z = [&](int a) -> double { return p.in_dim == 3 ? src[3 * a + 2] : 0.0; };
         double bx = 0.0, by = 0.0;
         if (p.box) { bx = p.box[(size_t)fr * p.box_stride]; by = p.box[(size_t)fr * p.box_stride + p.by_off]; }
         if (bad) atomicOr(&ctl[4], GTA_B200_ST_NONFINITE);
         int n = natoms;
 
+        __syncthreads(); GT_TICK(0);
         // ------------------------------------------------------------ K0: -corr points
         if (corr) {
             const int nx = (int)(bx / p.espace), ny = (int)(by / p.espace);      // gta_tri.c:112-113
@@ -176,7 +197,7 @@ __global__ void __launch_bounds__(T, MINB) tessellate_kernel(const KParams p) {
                 for (int s = tid; s < K; s += T) if (cidx[s] == 0x7fffffff) cidx[s] = 0;      // index arrays start at 0 (gta_tri.c:146-149)
                 __syncthreads();
                 // corner z (gta_tri.c:209-212) and the appended points in the reference's order (:220-272)
-                const double zc = (tmp_z[cidx[0]] + tmp_z[cidx[1]] + tmp_z[cidx[2]] + tmp_z[cidx[3]]) / 4.0;
+                const double zc = (atom_z(cidx[0]) + atom_z(cidx[1]) + atom_z(cidx[2]) + atom_z(cidx[3])) / 4.0;
                 for (int s = tid; s < ncorr; s += T) {
                     double X, Y, Z;
                     if (s < 4) {
@@ -185,16 +206,18 @@ __global__ void __launch_bounds__(T, MINB) tessellate_kernel(const KParams p) {
                         int j = (s - 4) >> 1;
                         int imin = cidx[oymin + j], imax = cidx[oymax + j];
                         double dist1 = tmp_xy[imin].y, dist2 = by - tmp_xy[imax].y, dist = dist1 + dist2;
-                        Z = tmp_z[imin] - (dist1 / dist) * tmp_z[imin] + tmp_z[imax] - (dist2 / dist) * tmp_z[imax];
+                        double zmin = atom_z(imin), zmax = atom_z(imax);
+                        Z = zmin - (dist1 / dist) * zmin + zmax - (dist2 / dist) * zmax;
                         X = j * p.espace + p.espace / 2; Y = ((s - 4) & 1) ? by : 0.0;
                     } else {
                         int j = (s - 4 - 2 * nx) >> 1;
                         int imin = cidx[oxmin + j], imax = cidx[oxmax + j];
                         double dist1 = tmp_xy[imin].x, dist2 = bx - tmp_xy[imax].x, dist = dist1 + dist2;
-                        Z = tmp_z[imin] - (dist1 / dist) * tmp_z[imin] + tmp_z[imax] - (dist2 / dist) * tmp_z[imax];
+                        double zmin = atom_z(imin), zmax = atom_z(imax);
+                        Z = zmin - (dist1 / dist) * zmin + zmax - (dist2 / dist) * zmax;
                         Y = j * p.espace + p.espace / 2; X = ((s - 4 - 2 * nx) & 1) ? bx : 0.0;
                     }
-                    tmp_xy[natoms + s].x = X; tmp_xy[natoms + s].y = Y; tmp_z[natoms + s] = Z;
+                    tmp_xy[natoms + s].x = X; tmp_xy[natoms + s].y = Y; zcorr[s] = Z;
                     if (p.corr && s < p.corr_cap) {
                         double* o = p.corr + ((size_t)fr * p.corr_cap + s) * 3;
                         o[0] = X; o[1] = Y; o[2] = Z;
@@ -209,6 +232,7 @@ __global__ void __launch_bounds__(T, MINB) tessellate_kernel(const KParams p) {
         if (n < 2 && tid == 0) atomicOr(&ctl[4], GTA_B200_ST_TOO_FEW_POINTS);    // delaunay_tri.c:416-421
         __syncthreads();
 
+        GT_TICK(1);
         double a3 = 0.0, a2 = 0.0;
         unsigned ntri_total = 0;
         if (ctl[4] == 0) {
@@ -235,20 +259,42 @@ __global__ void __launch_bounds__(T, MINB) tessellate_kernel(const KParams p) {
                     __syncthreads();
                 }
             }
+            GT_TICK(2);
             // gather into sorted order (the -corr scratch in `pt` is dead now)
-            for (int i = tid; i < n; i += T) { int o = perm[i]; pt[i] = tmp_xy[o]; zs[i] = tmp_z[o]; }
+            for (int i = tid; i < n; i += T) pt[i] = tmp_xy[perm[i]];
             __syncthreads();
-            // input contract of the reference's sort / duplicate pass (delaunay_tri.c:115-123, :440-452)
+            // The reference comparator (delaunay_tri.c:115-123) treats |dx| < 1e-12 as an x-tie and then
+            // orders by y. For exact-x ties that is the order just produced. A run of sorted points whose
+            // consecutive x gaps are all < 1e-12 but not all 0 (e.g. a float32 atom at x = 2.0 next to the
+            // -corr points at 2*0.8+0.4 = 2.0000000000000004) must be re-ordered by y alone; the thread
+            // owning the run's first element does it (runs are a handful of points). If the run is wider
+            // than 1e-12 the comparator is not transitive and qsort's result is unspecified: flagged.
+            for (int i = tid; i < n; i += T) {
+                auto tie = [&](int a, int b) { double d = pt[a].x - pt[b].x; return d < 1e-12 && d > -1e-12; };
+                if ((i == 0 || !tie(i, i - 1)) && i + 1 < n && tie(i + 1, i)) {
+                    int e = i + 1; bool inexact = false;
+                    while (e < n && tie(e, e - 1)) { inexact |= (pt[e].x != pt[e - 1].x); ++e; }
+                    if (inexact) {
+                        if (!tie(e - 1, i)) atomicOr(&ctl[4], GTA_B200_ST_NEAR_TIE_X);
+                        for (int a = i + 1; a < e; ++a) {          // insertion sort of [i, e) by y
+                            Pt pa = pt[a]; u16 oa = perm[a];
+                            int b = a - 1;
+                            while (b >= i && pt[b].y > pa.y) { pt[b + 1] = pt[b]; perm[b + 1] = perm[b]; --b; }
+                            pt[b + 1] = pa; perm[b + 1] = oa;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // duplicates within 1e-12 in x and y corrupt the reference's vertex array (delaunay_tri.c:440-452)
             for (int i = tid + 1; i < n; i += T) {
                 double dx = pt[i].x - pt[i - 1].x, dy = pt[i].y - pt[i - 1].y;
-                if (dx < 1e-12 && dx > -1e-12) {
-                    if (dy < 1e-12 && dy > -1e-12) atomicOr(&ctl[4], GTA_B200_ST_DUPLICATE);
-                    else if (dx != 0.0) atomicOr(&ctl[4], GTA_B200_ST_NEAR_TIE_X);
-                }
+                if (dx < 1e-12 && dx > -1e-12 && dy < 1e-12 && dy > -1e-12) atomicOr(&ctl[4], GTA_B200_ST_DUPLICATE);
             }
             for (int i = tid; i < n; i += T) head[i] = (u16)GT_NIL;
             __syncthreads();
         }
+        GT_TICK(3);
         if (ctl[4] == 0) {
             // -------------------------------------------------------- K1b: bottom-up D&C
             Frame f;
@@ -257,10 +303,31 @@ __global__ void __launch_bounds__(T, MINB) tessellate_kernel(const KParams p) {
             Lane ln; ln.free_head = GT_NIL;
             const int D = tree_depth(n);
             for (int d = D; d >= 0; --d) {
-                for (int k = tid; k < (1 << d); k += T) process_node(f, ln, d, k);
+                const int nodes = 1 << d;
+                if (nodes > p.coop_nodes) {
+                    // deep levels: many short merges, one lane each. Lanes of one warp that walk
+                    // different merges diverge and serialise, so nodes are dealt to warps round-robin
+                    // (node k -> warp k % W, lane k / W): every warp carries as few of them as possible.
+                    constexpr int W = T / 32;
+                    const int slot = (tid & 31) * W + (tid >> 5);
+                    for (int k = slot; k < nodes; k += T) process_node(f, ln, d, k);
+                } else {
+                    // upper levels: few long merges, 16 lanes each (dt_coop.cuh)
+                    const int gl = tid & (GT_G - 1);
+                    const unsigned gmask = ((1u << GT_G) - 1u) << ((tid & 31) & ~(GT_G - 1));
+                    constexpr int NG = T / GT_G;                   // groups per CTA, dealt to warps round-robin too
+                    const int grp = ((tid >> 4) & 1) * (T / 32) + (tid >> 5);
+                    for (int k = grp; k < nodes; k += NG) {
+                        int ia, ib;
+                        if (!tree_node(n, d, k, &ia, &ib) || ib - ia < 1) continue;
+                        if (ib - ia < 3) { if (gl == 0) leaf(f, ln, ia, ib); }
+                        else coop_merge(f, ln, (ia + ib) / 2, gmask, gl);
+                    }
+                }
                 __syncthreads();
                 flush_lane(f, ln);
                 __syncthreads();
+                GT_TICK(4 + d);
                 if (ctl[2]) break;
             }
             // -------------------------------------------------------- K2: enumerate + area
@@ -274,12 +341,13 @@ __global__ void __launch_bounds__(T, MINB) tessellate_kernel(const KParams p) {
                         offs = block_exclusive_scan<T>(cnt, scan, &tot) + base;
                     }
                     if (i < n) {
-                        const Pt pi = pt[i]; const double zi = zs[i];
+                        auto zof = [&](int v) -> double { int o = perm[v]; return o < natoms ? atom_z(o) : zcorr[o - natoms]; };
+                        const Pt pi = pt[i]; const double zi = zof(i);
                         const int oi = perm[i];
                         int* out = p.tri ? p.tri + ((size_t)fr * p.tri_cap) * 3 : nullptr;
                         vertex_triangles(f, i, [&](int n1, int n2) {
                             Pt p1 = pt[n1], p2 = pt[n2];
-                            a3 += tri_area3(pi.x, pi.y, zi, p1.x, p1.y, zs[n1], p2.x, p2.y, zs[n2]);
+                            a3 += tri_area3(pi.x, pi.y, zi, p1.x, p1.y, zof(n1), p2.x, p2.y, zof(n2));
                             if (want2d) a2 += tri_area3(pi.x, pi.y, 0.0, p1.x, p1.y, 0.0, p2.x, p2.y, 0.0);
                             if (out && (int)offs < p.tri_cap) {
                                 out[3 * offs] = oi; out[3 * offs + 1] = perm[n1]; out[3 * offs + 2] = perm[n2];
@@ -292,6 +360,10 @@ __global__ void __launch_bounds__(T, MINB) tessellate_kernel(const KParams p) {
                 ntri_total = base;
             }
         }
+        GT_TICK(20);
+#ifdef GT_PHASE_TIMING
+        if (tid == 0 && p.dbg) atomicAdd(&p.dbg[21], 1ull);
+#endif
         // ------------------------------------------------------------ block reduction (fixed order)
         {
             const int lane = tid & 31, warp = tid >> 5;
@@ -325,16 +397,14 @@ __global__ void __launch_bounds__(T, MINB) tessellate_kernel(const KParams p) {
 __global__ void orient2d_signs_kernel(const double* pts, int n, int* out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double* c = pts + 6 * (size_t)i; int re = 0;
-    int s = orient2d_sign(c[0], c[1], c[2], c[3], c[4], c[5], &re);
-    out[i] = re ? 2 : s;
+    const double* c = pts + 6 * (size_t)i;
+    out[i] = orient2d_sign(c[0], c[1], c[2], c[3], c[4], c[5]);
 }
 __global__ void incircle_signs_kernel(const double* pts, int n, int* out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double* c = pts + 8 * (size_t)i; int re = 0;
-    int s = incircle_sign(c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], &re);
-    out[i] = re ? 2 : s;
+    const double* c = pts + 8 * (size_t)i;
+    out[i] = incircle_sign(c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]);
 }
 
 }  // namespace gt

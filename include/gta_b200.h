@@ -34,7 +34,7 @@ extern "C" {
 #define GTA_B200_ST_OUT_OF_BOX      16  /* -corr with an atom outside [0,bx]x[0,by]: reference indexes out of bounds (gta_tri.c:178-201) */
 #define GTA_B200_ST_POOL            32  /* internal edge pool exhausted (never on planar input) */
 #define GTA_B200_ST_NONFINITE       64  /* NaN / Inf coordinate or box */
-#define GTA_B200_ST_NEAR_TIE_X      128 /* 0 < |dx| < 1e-12: reference comparator is not transitive (delaunay_tri.c:115-123) */
+#define GTA_B200_ST_NEAR_TIE_X      128 /* a run of near-equal x (gaps < 1e-12) wider than 1e-12: reference comparator not transitive (delaunay_tri.c:115-123) */
 #define GTA_B200_ST_INTERNAL        256 /* ring inconsistency (bug guard) */
 
 /* return codes */

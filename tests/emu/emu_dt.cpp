@@ -22,6 +22,20 @@ int emu_triangulate(const double* points, int n, int* tri_out) {
         double ux = points[2 * u], uy = points[2 * u + 1], vx = points[2 * v], vy = points[2 * v + 1];
         return ux < vx || (ux == vx && uy < vy);
     });
+    // runs of |dx| < 1e-12 that are not exact ties are ordered by y (reference compareVerts), as in the kernel
+    {
+        auto X = [&](int i) { return points[2 * perm[i]]; };
+        auto tie = [&](int a, int b) { double d = X(a) - X(b); return d < 1e-12 && d > -1e-12; };
+        for (int i = 0; i + 1 < n;) {
+            int e = i + 1; bool inexact = false;
+            while (e < n && tie(e, e - 1)) { inexact |= (X(e) != X(e - 1)); ++e; }
+            if (inexact) {
+                if (!tie(e - 1, i)) return -2000;
+                std::stable_sort(perm.begin() + i, perm.begin() + e, [&](int u, int v) { return points[2 * u + 1] < points[2 * v + 1]; });
+            }
+            i = e;
+        }
+    }
     std::vector<Pt> pt(n);
     for (int i = 0; i < n; ++i) { pt[i].x = points[2 * perm[i]]; pt[i].y = points[2 * perm[i] + 1]; }
     const int cap_e = 3 * n + 64;
@@ -48,20 +62,20 @@ int emu_triangulate(const double* points, int n, int* tri_out) {
 }
 
 void emu_orient2d_signs(const double* p, int n, int* out) {
-    for (int i = 0; i < n; ++i) { int re = 0; const double* c = p + 6 * (size_t)i;
-        int s = gt::orient2d_sign(c[0], c[1], c[2], c[3], c[4], c[5], &re); out[i] = re ? 2 : s; }
+    for (int i = 0; i < n; ++i) { const double* c = p + 6 * (size_t)i;
+        out[i] = gt::orient2d_sign(c[0], c[1], c[2], c[3], c[4], c[5]); }
 }
 void emu_incircle_signs(const double* p, int n, int* out) {
-    for (int i = 0; i < n; ++i) { int re = 0; const double* c = p + 8 * (size_t)i;
-        int s = gt::incircle_sign(c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], &re); out[i] = re ? 2 : s; }
+    for (int i = 0; i < n; ++i) { const double* c = p + 8 * (size_t)i;
+        out[i] = gt::incircle_sign(c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]); }
 }
 // exact stage only (bypasses the FP64 filter)
 void emu_orient2d_exact(const double* p, int n, int* out) {
-    for (int i = 0; i < n; ++i) { int re = 0; const double* c = p + 6 * (size_t)i;
-        int s = gt::orient2d_exact(c[0], c[1], c[2], c[3], c[4], c[5], &re); out[i] = re ? 2 : s; }
+    for (int i = 0; i < n; ++i) { const double* c = p + 6 * (size_t)i;
+        out[i] = gt::orient2d_exact(c[0], c[1], c[2], c[3], c[4], c[5]); }
 }
 void emu_incircle_exact(const double* p, int n, int* out) {
-    for (int i = 0; i < n; ++i) { int re = 0; const double* c = p + 8 * (size_t)i;
-        int s = gt::incircle_exact(c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], &re); out[i] = re ? 2 : s; }
+    for (int i = 0; i < n; ++i) { const double* c = p + 8 * (size_t)i;
+        out[i] = gt::incircle_exact(c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]); }
 }
 }

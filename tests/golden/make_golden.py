@@ -41,6 +41,14 @@ def main():
     sets["equal_x_cols"] = np.stack([np.repeat(np.arange(4) * 1.0, 5), np.tile(np.arange(5) * 0.375, 4)], 1)
     th = np.arange(24) * (2 * np.pi / 24)
     sets["circle24_center"] = np.concatenate([np.stack([np.cos(th), np.sin(th)], 1), [[0.0, 0.0]]])
+    # near-ties in x (0 < |dx| < 1e-12): the reference comparator orders such runs by y
+    # (delaunay_tri.c:115-123); happens with float32 atoms at x = 2.0 next to -corr points at 2*0.8+0.4
+    nt = rng.random((60, 2)) * 6.4
+    nt[5] = (2.0, 3.1); nt[6] = (2 * 0.8 + 0.4, 0.0); nt[7] = (2 * 0.8 + 0.4, 6.4)
+    nt[8] = (7 * 0.8 + 0.4, 0.0); nt[9] = (6.0, 1.7); nt[10] = (6.0, 5.9); nt[11] = (7 * 0.8 + 0.4, 6.4)
+    nt[12] = (4.0, 2.0); nt[13] = (4.0 + 2 ** -50, 1.0); nt[14] = (4.0 - 2 ** -50, 3.0); nt[15] = (4.0 + 2 ** -49, 0.5)
+    assert 0 < nt[8, 0] - 6.0 < 1e-12
+    sets["near_tie_x"] = nt
     for name, p in sets.items():
         tri, nv = ref.triangulate(p)
         assert nv == len(p)
