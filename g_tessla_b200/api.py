@@ -57,6 +57,8 @@ def lib() -> C.CDLL:
     L.gta_b200_tessellate_multi.argtypes = [
         C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint, C.c_int, C.c_int,
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gta_b200_triangulate_large.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, _ip, _ip]
+    L.gta_b200_large_last_ms.restype = C.c_double
     L.gta_b200_orient2d_signs.argtypes = [_dp, C.c_int, _ip, C.c_int]
     L.gta_b200_incircle_signs.argtypes = [_dp, C.c_int, _ip, C.c_int]
     _lib = L
@@ -131,6 +133,18 @@ def triangulate(points, device=-1):
         p = p[None]
     r = tessellate(p, None, flags=0, device=device, want_tri=True)
     return (r["tri"][0], int(r["status"][0])) if single else (r["tri"], r["status"])
+
+
+def triangulate_large(points, device=-1):
+    """dtriangulate on one large raw 2-D point set [n,2] (the global-memory path, any n >= 2).
+
+    Returns (triangles [ntri,3] int32 in reference emission order, status, device_ms)."""
+    p = np.ascontiguousarray(points, dtype=np.float64)
+    n = len(p)
+    tri = np.zeros((max(2 * n, 1), 3), dtype=np.int32)
+    nt = C.c_int(0); st = C.c_int(0)
+    _check(lib().gta_b200_triangulate_large(_vp(p), n, int(device), _vp(tri), len(tri), C.byref(nt), C.byref(st)))
+    return tri[:nt.value].copy(), st.value, lib().gta_b200_large_last_ms()
 
 
 def orient2d_signs(pts, device=-1):

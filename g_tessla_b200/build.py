@@ -42,7 +42,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if os.path.exists(cli_src) and (force or _stale(CLI, [cli_src, LIB])):
         subprocess.check_call(["gcc", "-std=c99", "-O2", "-Wall", "-o", CLI, cli_src,
                                "-I" + os.path.join(HERE, "..", "include"), "-L" + HERE, "-lgtessla_b200",
-                               "-Wl,-rpath,$ORIGIN", "-lm"])
+                               "-Wl,-rpath,$ORIGIN", "-Wl,-rpath-link," + os.path.dirname(nvcc_path()) + "/../lib64", "-lm"])
     return LIB
 
 

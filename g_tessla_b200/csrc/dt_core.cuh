@@ -22,26 +22,41 @@
 namespace gt {
 
 typedef uint16_t u16;
-#define GT_NIL 0xFFFFu
+#define GT_NIL 0xFFFFu      // empty marker of the 16-bit frame type (FrameT<u16>::NIL)
+
+// Host-only work counters for the emulation build (tests/emu, -DGT_STATS); no-ops in the product.
+#if defined(GT_STATS) && !defined(__CUDA_ARCH__)
+struct Stats { long o2d, icc, steps, cuts, edges; };
+extern Stats g_stats;
+#define GT_STAT(x) (++g_stats.x)
+#else
+#define GT_STAT(x) ((void)0)
+#endif
 
 struct Pt { double x, y; };
 
-// Per-frame working set. On the device every pointer is shared memory.
-struct Frame {
+// Per-frame working set. Idx = 16-bit indices for the batched kernel (every pointer is shared memory,
+// n <= ~3.5k points) or 32-bit indices for the single-large-frame path (global memory).
+template <class Idx>
+struct FrameT {
+    typedef Idx idx;
+    enum : uint32_t { NIL = (uint32_t)(Idx)~(Idx)0 };     // empty marker (enum: usable in device code without a definition)
     Pt* pt;          // [n] sorted vertex coordinates
-    u16* head;       // [n] ring entry half-edge per vertex ("first", reference :285-289)
-    u16* dst;        // [2*cap_e] destination vertex of half-edge h
-    u16* nxt;        // [2*cap_e] CCW link in the origin's ring   (reference vertNode.next)
-    u16* prv;        // [2*cap_e] CW link in the origin's ring    (reference vertNode.prev)
+    Idx* head;       // [n] ring entry half-edge per vertex ("first", reference :285-289)
+    Idx* dst;        // [2*cap_e] destination vertex of half-edge h
+    Idx* nxt;        // [2*cap_e] CCW link in the origin's ring   (reference vertNode.next)
+    Idx* prv;        // [2*cap_e] CW link in the origin's ring    (reference vertNode.prev)
     uint32_t* bump;  // number of edges ever taken from the pool
-    uint32_t* stack; // block-shared free-edge stack head (edge index, GT_NIL if empty)
-    uint32_t* err;   // sticky per-frame error bits (GT_ERR_*)
+    uint32_t* stack; // shared free-edge stack head (edge index, NIL if empty); nullptr = no shared recycling
+    uint32_t* err;   // sticky error bits (GT_ERR_*)
     int n;
-    int cap_e;       // edge capacity of the pool
+    uint32_t cap_e;  // edge capacity of the pool
 };
+typedef FrameT<u16> Frame;
 enum { GT_ERR_POOL = 1, GT_ERR_RANGE = 2, GT_ERR_RING = 4 };
 
-// Lane state that survives across merges: a private list of free edges (linked through nxt[2e]).
+// Lane state that survives across merges: a private list of free edges (linked through nxt[2e]);
+// the empty list is F::NIL of the frame type in use.
 struct Lane { uint32_t free_head; };
 
 #if defined(__CUDA_ARCH__)
@@ -59,6 +74,7 @@ GT_INLINE void atomic_or_u32(uint32_t* p, uint32_t v) { *p |= v; }
 // the kernel's register count and instruction-cache footprint down (the walk is latency bound,
 // a call costs less than the i-cache misses of 20 inlined incircle bodies).
 GT_NOINLINE bool ccw_pts(const Pt* pt, uint32_t* err, int a, int b, int c) {
+    GT_STAT(o2d);
     Pt pa = pt[a], pb = pt[b], pc = pt[c];
     int s = orient2d_sign(pa.x, pa.y, pb.x, pb.y, pc.x, pc.y);
     if (s == GT_RANGE_ERR) { atomic_or_u32(err, GT_ERR_RANGE); return false; }
@@ -68,48 +84,58 @@ GT_NOINLINE bool in_circle_pts(const Pt* pt, uint32_t* err, int a, int b, int c,
     // incircle with a repeated point is exactly 0 (two equal rows) -- the commonest
     // degenerate call of the merge loop (r2 == li when ri has two neighbours); skip the math.
     if (a == d || b == d || c == d || a == b || a == c || b == c) return false;
+    GT_STAT(icc);
     Pt pa = pt[a], pb = pt[b], pc = pt[c], pd = pt[d];
     int s = incircle_sign(pa.x, pa.y, pb.x, pb.y, pc.x, pc.y, pd.x, pd.y);
     if (s == GT_RANGE_ERR) { atomic_or_u32(err, GT_ERR_RANGE); return false; }
     return s > 0;
 }
-GT_INLINE bool ccw(const Frame& f, int a, int b, int c) { return ccw_pts(f.pt, f.err, a, b, c); }
-GT_INLINE bool right_of(const Frame& f, int x, int ea, int eb) { return ccw(f, x, eb, ea); }   // reference :141-145
-GT_INLINE bool left_of(const Frame& f, int x, int ea, int eb) { return ccw(f, x, ea, eb); }    // reference :147-151
-GT_INLINE bool in_circle(const Frame& f, int a, int b, int c, int d) { return in_circle_pts(f.pt, f.err, a, b, c, d); }
+template <class F>
+GT_INLINE bool ccw(const F& f, int a, int b, int c) { return ccw_pts(f.pt, f.err, a, b, c); }
+template <class F>
+GT_INLINE bool right_of(const F& f, int x, int ea, int eb) { return ccw(f, x, eb, ea); }   // reference :141-145
+template <class F>
+GT_INLINE bool left_of(const F& f, int x, int ea, int eb) { return ccw(f, x, ea, eb); }    // reference :147-151
+template <class F>
+GT_INLINE bool in_circle(const F& f, int a, int b, int c, int d) { return in_circle_pts(f.pt, f.err, a, b, c, d); }
 
 // ---------------------------------------------------------------- edge pool
-GT_INLINE int edge_alloc(const Frame& f, Lane& ln) {
-    if (ln.free_head != GT_NIL) {
+template <class F>
+GT_INLINE int edge_alloc(const F& f, Lane& ln) {
+    if (ln.free_head != F::NIL) {
         int e = (int)ln.free_head;
         ln.free_head = f.nxt[2 * e];
         return e;
     }
     // block-shared stack: pops only happen inside a merge phase, pushes only between phases
     // (flush_lane), so there is no ABA window.
-    uint32_t top = *(volatile uint32_t*)f.stack;
-    while (top != GT_NIL) {
+    uint32_t top = f.stack ? *(volatile uint32_t*)f.stack : F::NIL;
+    while (top != F::NIL) {
         uint32_t next = f.nxt[2 * top];
         uint32_t seen = atomic_cas_u32(f.stack, top, next);
         if (seen == top) return (int)top;
         top = seen;
     }
+    GT_STAT(edges);
     uint32_t e = atomic_add_u32(f.bump, 1u);
-    if (e >= (uint32_t)f.cap_e) { atomic_or_u32(f.err, GT_ERR_POOL); return -1; }
+    if (e >= f.cap_e) { atomic_or_u32(f.err, GT_ERR_POOL); return -1; }
     return (int)e;
 }
-GT_INLINE void edge_free(const Frame& f, Lane& ln, int e) {
-    f.nxt[2 * e] = (u16)ln.free_head;
+template <class F>
+GT_INLINE void edge_free(const F& f, Lane& ln, int e) {
+    f.nxt[2 * e] = (typename F::idx)ln.free_head;
     ln.free_head = (uint32_t)e;
 }
 // Return a lane's private free edges to the shared stack (call between merge phases only).
-GT_INLINE void flush_lane(const Frame& f, Lane& ln) {
-    while (ln.free_head != GT_NIL) {
+template <class F>
+GT_INLINE void flush_lane(const F& f, Lane& ln) {
+    if (!f.stack) { ln.free_head = F::NIL; return; }          // large-frame mode: freed edges are not recycled across merges
+    while (ln.free_head != F::NIL) {
         uint32_t e = ln.free_head;
         ln.free_head = f.nxt[2 * e];
         uint32_t top = *(volatile uint32_t*)f.stack;
         for (;;) {
-            f.nxt[2 * e] = (u16)top;
+            f.nxt[2 * e] = (typename F::idx)top;
             uint32_t seen = atomic_cas_u32(f.stack, top, e);
             if (seen == top) break;
             top = seen;
@@ -118,22 +144,24 @@ GT_INLINE void flush_lane(const Frame& f, Lane& ln) {
 }
 
 // ---------------------------------------------------------------- rings
-GT_INLINE void link_after(const Frame& f, int at, int h) {     // reference insertNodeAfter :202-208
+template <class F>
+GT_INLINE void link_after(const F& f, int at, int h) {     // reference insertNodeAfter :202-208
     int nx = f.nxt[at];
-    f.nxt[at] = (u16)h; f.prv[nx] = (u16)h; f.prv[h] = (u16)at; f.nxt[h] = (u16)nx;
+    f.nxt[at] = (typename F::idx)h; f.prv[nx] = (typename F::idx)h; f.prv[h] = (typename F::idx)at; f.nxt[h] = (typename F::idx)nx;
 }
 
 // Insert half-edge h (origin `parent`, destination `in`) into parent's CCW ring at the position
 // the reference's scan finds (insertNode :210-245), including its "first" update rule.
-GT_INLINE void ring_insert(const Frame& f, int parent, int in, int h) {
-    f.dst[h] = (u16)in;
+template <class F>
+GT_INLINE void ring_insert(const F& f, int parent, int in, int h) {
+    f.dst[h] = (typename F::idx)in;
     int hd = f.head[parent];
-    if (hd == GT_NIL) { f.head[parent] = (u16)h; f.prv[h] = (u16)h; f.nxt[h] = (u16)h; return; }
+    if (hd == F::NIL) { f.head[parent] = (typename F::idx)h; f.prv[h] = (typename F::idx)h; f.nxt[h] = (typename F::idx)h; return; }
     if (right_of(f, in, parent, f.dst[hd])) {
         int cur = f.prv[hd];
         while (cur != hd && right_of(f, in, parent, f.dst[cur])) cur = f.prv[cur];
         if (cur == hd) {                       // right of every ray: new hull successor
-            f.head[parent] = (u16)h;
+            f.head[parent] = (typename F::idx)h;
             link_after(f, f.prv[cur], h);
         } else {
             link_after(f, cur, h);
@@ -153,14 +181,15 @@ GT_INLINE void ring_insert(const Frame& f, int parent, int in, int h) {
 // new ray is no longer left of the current one, i.e. to the ray's angular slot; inside a merge that
 // slot is known (next to the previous cross edge, or in the hull gap), so the walk and its orient2d
 // calls are skipped. -DGT_VERIFY_HINT re-runs the walk and flags any disagreement (host fuzz only).
-GT_INLINE void ring_insert_hint(const Frame& f, int parent, int in, int h, int after) {
-    f.dst[h] = (u16)in;
+template <class F>
+GT_INLINE void ring_insert_hint(const F& f, int parent, int in, int h, int after) {
+    f.dst[h] = (typename F::idx)in;
     int hd = f.head[parent];
     if (right_of(f, in, parent, f.dst[hd])) {
         int cur = f.prv[hd];
         while (cur != hd && right_of(f, in, parent, f.dst[cur])) cur = f.prv[cur];
         if (cur == hd) {
-            f.head[parent] = (u16)h;
+            f.head[parent] = (typename F::idx)h;
             link_after(f, f.prv[cur], h);
         } else {
             link_after(f, cur, h);
@@ -176,7 +205,8 @@ GT_INLINE void ring_insert_hint(const Frame& f, int parent, int in, int h, int a
 }
 
 // connectVerts (reference :270-275): returns the half-edge a->b (its twin b->a is h^1).
-GT_INLINE int connect(const Frame& f, Lane& ln, int a, int b) {
+template <class F>
+GT_INLINE int connect(const F& f, Lane& ln, int a, int b) {
     int e = edge_alloc(f, ln);
     if (e < 0) return -1;
     ring_insert(f, a, b, 2 * e);
@@ -184,21 +214,25 @@ GT_INLINE int connect(const Frame& f, Lane& ln, int a, int b) {
     return 2 * e;
 }
 
-GT_INLINE void ring_unlink(const Frame& f, int origin, int h) {   // reference deleteNode :247-268
+template <class F>
+GT_INLINE void ring_unlink(const F& f, int origin, int h) {   // reference deleteNode :247-268
     int p = f.prv[h], nx = f.nxt[h];
-    f.nxt[p] = (u16)nx; f.prv[nx] = (u16)p;
-    if (f.head[origin] == h) f.head[origin] = (nx == h) ? (u16)GT_NIL : (u16)nx;
+    f.nxt[p] = (typename F::idx)nx; f.prv[nx] = (typename F::idx)p;
+    if (f.head[origin] == h) f.head[origin] = (nx == h) ? (typename F::idx)F::NIL : (typename F::idx)nx;
 }
 // cutVerts (reference :277-282) on the half-edge h = (a->b).
-GT_INLINE void cut(const Frame& f, Lane& ln, int h) {
+template <class F>
+GT_INLINE void cut(const F& f, Lane& ln, int h) {
     int a = f.dst[h ^ 1], b = f.dst[h];
     ring_unlink(f, a, h);
     ring_unlink(f, b, h ^ 1);
     edge_free(f, ln, h >> 1);
+    GT_STAT(cuts);
 }
 
 // ---------------------------------------------------------------- base cases (reference :516-531)
-GT_INLINE void leaf(const Frame& f, Lane& ln, int ia, int ib) {
+template <class F>
+GT_INLINE void leaf(const F& f, Lane& ln, int ia, int ib) {
     if (ib - ia == 1) { connect(f, ln, ia, ib); return; }
     connect(f, ln, ia, ia + 1);
     connect(f, ln, ia + 1, ib);
@@ -207,7 +241,8 @@ GT_INLINE void leaf(const Frame& f, Lane& ln, int ia, int ib) {
 
 // ---------------------------------------------------------------- merge (reference :535-599)
 // Left half = sorted positions ia..mid, right half = mid+1..ib, both already triangulated.
-GT_INLINE void merge(const Frame& f, Lane& ln, int mid) {
+template <class F>
+GT_INLINE void merge(const F& f, Lane& ln, int mid) {
     // lower common tangent (reference lct :337-370): walk starts at the rightmost vertex of the
     // left half (position mid) and the leftmost of the right half (mid+1).
     int lx = mid, ly = mid + 1;
@@ -246,6 +281,7 @@ GT_INLINE void merge(const Frame& f, Lane& ln, int mid) {
     int guard = 8 * f.n + 64;
     while (li != ux || ri != uy) {
         if (--guard < 0) { atomic_or_u32(f.err, GT_ERR_RING); return; }
+        GT_STAT(steps);
         bool a = false, b = false;
         int hr1 = f.prv[e ^ 1];                 // ri -> pred(ri, li)
         int r1 = f.dst[hr1];
@@ -310,7 +346,8 @@ GT_INLINE int tree_depth(int n) {       // deepest level that holds a node
     return d;
 }
 // One node of one level: base case or merge of its two finished children.
-GT_INLINE void process_node(const Frame& f, Lane& ln, int depth, int k) {
+template <class F>
+GT_INLINE void process_node(const F& f, Lane& ln, int depth, int k) {
     int ia, ib;
     if (!tree_node(f.n, depth, k, &ia, &ib)) return;
     if (ib - ia < 1) return;
@@ -323,10 +360,10 @@ GT_INLINE void process_node(const Frame& f, Lane& ln, int depth, int k) {
 // starting at "first", with both neighbours sorting after i (the reference's "adjacency list not
 // freed yet"), except the wrap-around pair when it spans the hull gap (:619-621).
 // visit(n1, n2) is called in emission order; returns the count.
-template <class Visit>
-GT_INLINE int vertex_triangles(const Frame& f, int i, Visit&& visit) {
+template <class F, class Visit>
+GT_INLINE int vertex_triangles(const F& f, int i, Visit&& visit) {
     int hd = f.head[i];
-    if (hd == GT_NIL || f.nxt[hd] == hd) return 0;
+    if (hd == F::NIL || f.nxt[hd] == hd) return 0;
     int cnt = 0, h = hd;
     do {
         int hn = f.nxt[h];

@@ -30,11 +30,11 @@
 #if defined(__CUDACC__)
 #define GT_HD __host__ __device__
 #define GT_INLINE __host__ __device__ __forceinline__
-#define GT_NOINLINE __host__ __device__ __noinline__
+#define GT_NOINLINE static __host__ __device__ __noinline__
 #else
 #define GT_HD
 #define GT_INLINE inline
-#define GT_NOINLINE __attribute__((noinline))
+#define GT_NOINLINE static __attribute__((noinline))
 #include <math.h>
 #include <string.h>
 #endif

@@ -34,13 +34,13 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
     } while (0)
 
 int round_even(int v) { return (v + 1) & ~1; }
-// Levels of the recursion tree with at most this many nodes run as 16-lane cooperative merges
+// Levels of the recursion tree with at most this many nodes run as warp-cooperative merges
 // (tunable for experiments: GTA_B200_COOP_NODES).
 int coop_nodes_for(int threads) {
     static int env = -2;
     if (env == -2) { const char* e = getenv("GTA_B200_COOP_NODES"); env = e ? atoi(e) : -1; }
     if (env >= 0) return env;
-    return threads >= 128 ? 32 : (threads >= 64 ? 16 : 4);
+    return threads / 32;
 }
 int pow2_ge(int v) { int p = 2; while (p < v) p <<= 1; return p; }
 
@@ -63,6 +63,9 @@ Shape shape_for(int max_points, int natoms = 0) {
     s.cap_p2 = pow2_ge(s.cap);
     s.smem = gt::smem_bytes_for(s.cap, s.cap_p2, natoms);
     s.threads = s.cap <= 192 ? 32 : (s.cap <= 512 ? 64 : 128);
+    static int env_t = -2;                                   // experiments: GTA_B200_THREADS = 32 | 64 | 128
+    if (env_t == -2) { const char* e = getenv("GTA_B200_THREADS"); env_t = e ? atoi(e) : -1; }
+    if (env_t == 32 || env_t == 64 || env_t == 128) s.threads = env_t;
     return s;
 }
 
@@ -116,7 +119,8 @@ bool have_device() {
 
 extern "C" {
 
-const char* gta_b200_last_error(void) { return g_err.c_str(); }
+const char* gta_b200_large_error(void);
+const char* gta_b200_last_error(void) { return g_err.empty() ? gta_b200_large_error() : g_err.c_str(); }
 double gta_b200_last_kernel_ms(void) { return g_last_kernel_ms; }
 int gta_b200_last_launches(void) { return g_last_launches; }
 

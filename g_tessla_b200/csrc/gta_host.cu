@@ -1,0 +1,402 @@
+// gta_host.cu -- the reference's C entry points (include/delaunay_tri.h, include/gta_tri.h,
+// include/gta_io.h) on top of the batch C-ABI of gta_b200.cu.
+//
+// Mirrors, call for call, what the reference does around its hot path:
+//   dtinit / dtriangulate                    src/delaunay_tri.c:409-507
+//   tessellate_area / delaunay_tessellate    src/gta_tri.c:41-78, :80-329
+//   delaunay_surface_area                    src/gta_tri.c:332-413
+//   print_areas / free_tri_area              src/gta_tri.c:448-473, :500-504
+//   init_log / print_log / close_log         extern/gkut/src/gkut_log.c:21-50
+//   read_traj / ndx_filter_traj              extern/gkut/src/gkut_io.c:20-97 (formats decoded here, no GROMACS)
+// None of these functions computes a triangulation or an area on the CPU: they stage buffers and call
+// gta_b200_tessellate_*; without a CUDA device they report the library error and produce no result.
+#include <cuda_runtime.h>
+#include <cctype>
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <string>
+#include <vector>
+#include "../../include/gta_b200.h"
+#include "../../include/delaunay_tri.h"
+#include "../../include/gta_tri.h"
+#include "../../include/gta_io.h"
+
+namespace {
+thread_local int g_dt_status = 0;
+thread_local std::vector<int> g_frame_status;
+FILE* g_log = nullptr;
+
+int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+}  // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------ logging
+void init_log(const char* logfile, int argc, char* argv[]) {
+    g_log = fopen(logfile, "a");
+    if (!g_log) return;
+    time_t t = time(nullptr);
+    struct tm* lt = localtime(&t);
+    fprintf(g_log, "\n");
+    for (int i = 0; i < argc; ++i) fprintf(g_log, "%s ", argv[i]);
+    fprintf(g_log, "\nRun: %d-%d-%d %d:%d:%d\n", lt->tm_mon + 1, lt->tm_mday, lt->tm_year + 1900, lt->tm_hour, lt->tm_min, lt->tm_sec);
+}
+void close_log(void) { if (g_log) fclose(g_log); g_log = nullptr; }
+void print_log(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt); vprintf(fmt, ap); va_end(ap);
+    if (g_log) { va_start(ap, fmt); vfprintf(g_log, fmt, ap); va_end(ap); }
+}
+
+// ------------------------------------------------------------------------------------------ triangulator
+void dtinit(void) {
+    if (gta_b200_device_count() < 1)
+        fprintf(stderr, "TRIANGULATION ERROR: no CUDA device; libgtessla_b200 has no CPU implementation.\n");
+}
+int dt_last_status(void) { return g_dt_status; }
+
+void dtriangulate(struct dTriangulation* tri) {
+    g_dt_status = 0;
+    if (tri->npoints < 2) {                                   // reference delaunay_tri.c:416-421
+        fprintf(stderr, "TRIANGULATION ERROR: Only %d point(s)? That's not enough!\n", tri->npoints);
+        g_dt_status = GTA_B200_ST_TOO_FEW_POINTS;
+        return;
+    }
+    const int n = tri->npoints, cap = 2 * n;                  // at most 2(n-1)-2 triangles (delaunay_tri.c:608)
+    int* t = (int*)malloc(sizeof(int) * 3 * (size_t)cap);
+    int ntri = 0, status = 0;
+    int rc;
+    if (n <= gta_b200_max_points())
+        rc = gta_b200_tessellate_batch(tri->points, 2, nullptr, 0, 1, n, 0.0, 0u, -1, 1,
+                                       nullptr, nullptr, nullptr, &status, t, cap, &ntri, nullptr, 0, nullptr);
+    else
+        rc = gta_b200_triangulate_large(tri->points, n, -1, t, cap, &ntri, &status);
+    if (rc != GTA_B200_OK) {
+        fprintf(stderr, "TRIANGULATION ERROR: %s\n", gta_b200_last_error());
+        g_dt_status = GTA_B200_ST_INTERNAL; free(t); return;
+    }
+    g_dt_status = status;
+    if (status != 0) {
+        if (status & GTA_B200_ST_DUPLICATE)
+            fprintf(stderr, "TRIANGULATION ERROR: duplicate points (closer than 1e-12 in x and y) are not supported.\n");
+        else
+            fprintf(stderr, "TRIANGULATION ERROR: input rejected (status %d, see gta_b200.h).\n", status);
+        free(t); return;                                       // struct left untouched, as on the reference's error paths
+    }
+    tri->triangles = (int*)realloc(t, sizeof(int) * 3 * (size_t)(ntri > 0 ? ntri : 1));
+    tri->ntriangles = ntri;
+    tri->nverts = n;
+}
+
+// ------------------------------------------------------------------------------------------ area pipeline
+const int* gta_last_frame_status(void) { return g_frame_status.empty() ? nullptr : g_frame_status.data(); }
+
+static void write_showme(const char* node, const char* ele, const double* xy, int npts, const int* tri, int ntri) {
+    // reference print_dtrifiles, src/gta_tri.c:475-498
+    FILE* f = fopen(node, "w");
+    if (f) {
+        fprintf(f, "%d\t2\t0\t0\n", npts);
+        for (int i = 0; i < npts; ++i) fprintf(f, "%d\t%f\t%f\n", i, xy[2 * i], xy[2 * i + 1]);
+        fclose(f);
+    }
+    f = fopen(ele, "w");
+    if (f) {
+        fprintf(f, "%d\t3\t0\n", ntri);
+        for (int i = 0; i < ntri; ++i) fprintf(f, "%d\t%d\t%d\t%d\n", i, tri[3 * i], tri[3 * i + 1], tri[3 * i + 2]);
+        fclose(f);
+    }
+}
+
+void delaunay_tessellate(rvec** x, matrix* box, real espace, int nthreads, struct tri_area* areas, unsigned char flags) {
+    const int F = areas->nframes, N = areas->natoms;
+    if (nthreads > 1 || nthreads <= 0) print_log("Triangulation will be parallelized.\n");   // gta_tri.c:93-94
+    dtinit();
+    areas->area = (real*)calloc((size_t)(F > 0 ? F : 1), sizeof(real));
+    areas->area2Dbox = (real*)calloc((size_t)(F > 0 ? F : 1), sizeof(real));
+    if (flags & GTA_2D) areas->area2D = (real*)calloc((size_t)(F > 0 ? F : 1), sizeof(real));
+    if (flags & GTA_CORRECT) print_log("Triangulating and correcting %d frames...\n", F);  // gta_tri.c:104
+    else print_log("Triangulating %d frames...\n", F);                                        // gta_tri.c:299
+    g_frame_status.assign((size_t)(F > 0 ? F : 1), 0);
+    if (F <= 0) return;
+    const unsigned fl = flags & (GTA_CORRECT | GTA_2D);
+    int rc;
+    if (flags & GTA_PRINT) {
+        // one frame at a time (the reference also serialises -print, g_tessla.c:116); files are numbered from 1
+        static int iter = 0;
+        const int maxp = gta_b200_max_points_for(&box[0][0][0], 9, F, N, espace, fl);
+        std::vector<int> tri(3 * (size_t)(2 * maxp)); std::vector<double> corr(3 * (size_t)(maxp - N + 1)), xy(2 * (size_t)maxp);
+        rc = GTA_B200_OK;
+        for (int fr = 0; fr < F && rc == GTA_B200_OK; ++fr) {
+            int ntri = 0, ncorr = 0;
+            rc = gta_b200_tessellate_batch(&x[fr][0][0], 3, &box[fr][0][0], 9, 1, N, espace, fl, -1, 1,
+                                           areas->area + fr, areas->area2D ? areas->area2D + fr : nullptr, areas->area2Dbox + fr,
+                                           &g_frame_status[fr], tri.data(), 2 * maxp, &ntri, corr.data(), maxp - N + 1, &ncorr);
+            if (rc != GTA_B200_OK) break;
+            for (int i = 0; i < N; ++i) { xy[2 * i] = x[fr][i][XX]; xy[2 * i + 1] = x[fr][i][YY]; }
+            for (int i = 0; i < ncorr; ++i) { xy[2 * (N + i)] = corr[3 * i]; xy[2 * (N + i) + 1] = corr[3 * i + 1]; }
+            char n1[64], n2[64];
+            ++iter;
+            snprintf(n1, sizeof n1, "triangles%d.node", iter); snprintf(n2, sizeof n2, "triangles%d.ele", iter);
+            write_showme(n1, n2, xy.data(), N + ncorr, tri.data(), ntri);
+        }
+    } else {
+        const int ngpus = env_int("GTA_B200_NGPUS", 0);
+        rc = gta_b200_tessellate_frames((const double* const*)x, &box[0][0][0], F, N, espace, fl, ngpus <= 0 ? gta_b200_device_count() : ngpus,
+                                        nthreads, areas->area, areas->area2D, areas->area2Dbox, g_frame_status.data());
+    }
+    if (rc != GTA_B200_OK) { print_log("TESSELLATION ERROR: %s\n", gta_b200_last_error()); return; }
+    int bad = 0;
+    for (int fr = 0; fr < F; ++fr) bad += g_frame_status[fr] != 0;
+    if (bad) print_log("WARNING: %d frame(s) were rejected (NaN area); see gta_last_frame_status().\n", bad);
+}
+
+void delaunay_surface_area(const rvec* x, matrix box, int natoms, unsigned char flags, real* a2D, real* a3D) {
+    (void)box; (void)flags;
+    g_dt_status = 0;
+    if (!a2D && !a3D) return;
+    double a3 = 0.0, a2 = 0.0; int st = 0;
+    int rc = gta_b200_tessellate_batch(&x[0][0], 3, nullptr, 0, 1, natoms, 0.0, a2D ? GTA_B200_2D : 0u, -1, 1,
+                                       &a3, a2D ? &a2 : nullptr, nullptr, &st, nullptr, 0, nullptr, nullptr, 0, nullptr);
+    if (rc != GTA_B200_OK) { fprintf(stderr, "TRIANGULATION ERROR: %s\n", gta_b200_last_error()); g_dt_status = GTA_B200_ST_INTERNAL; return; }
+    g_dt_status = st;
+    if (st & GTA_B200_ST_TOO_FEW_POINTS) fprintf(stderr, "TRIANGULATION ERROR: Only %d point(s)? That's not enough!\n", natoms);
+    if (a3D) *a3D = a3;
+    if (a2D) *a2D = a2;
+}
+
+void tessellate_area(const char* traj_fname, const char* ndx_fname, output_env_t* oenv, real espace, int nthreads,
+                     struct tri_area* areas, unsigned char flags) {
+    rvec **pre_x = nullptr, **x = nullptr;
+    matrix* box = nullptr;
+    areas->area = areas->area2D = areas->area2Dbox = nullptr;          // gta_tri.c:51-53
+    read_traj(traj_fname, &pre_x, &box, &areas->nframes, &areas->natoms, oenv);
+    if (ndx_fname) {
+        ndx_filter_traj(ndx_fname, pre_x, &x, areas->nframes, &areas->natoms);
+        for (int i = 0; i < areas->nframes; ++i) free(pre_x[i]);
+        free(pre_x);
+    } else x = pre_x;
+    delaunay_tessellate(x, box, espace, nthreads, areas, flags);
+    for (int i = 0; i < areas->nframes; ++i) free(x[i]);
+    free(x); free(box);
+}
+
+void print_areas(const char* fname, const struct tri_area* areas) {
+    FILE* f = fopen(fname, "w");
+    if (!f) { print_log("Could not open %s for writing.\n", fname); return; }
+    real sum = 0;
+    if (areas->area2D) {
+        fprintf(f, "# FRAME\tAREA\t2DAREA\tBOX-AREA\t\"\"/PARTICLE\n");
+        for (int i = 0; i < areas->nframes; ++i) {
+            fprintf(f, "%d\t%f\t%f\t%f\t%f\t%f\t%f\n", i, areas->area[i], areas->area2D[i], areas->area2Dbox[i],
+                    areas->area[i] / areas->natoms, areas->area2D[i] / areas->natoms, areas->area2Dbox[i] / areas->natoms);
+            sum += areas->area[i];
+        }
+    } else {
+        fprintf(f, "# FRAME\tAREA\tBOX-AREA\t\"\"/PARTICLE\n");
+        for (int i = 0; i < areas->nframes; ++i) {
+            fprintf(f, "%d\t%f\t%f\t%f\t%f\n", i, areas->area[i], areas->area2Dbox[i],
+                    areas->area[i] / areas->natoms, areas->area2Dbox[i] / areas->natoms);
+            sum += areas->area[i];
+        }
+    }
+    print_log("Average surface area: %f\n", sum / areas->nframes);
+    print_log("Average area per particle: %f\n", (sum / areas->nframes) / areas->natoms);
+    fclose(f);
+    print_log("Surface areas saved to %s\n", fname);
+}
+
+void free_tri_area(struct tri_area* areas) {
+    free(areas->area); free(areas->area2D); free(areas->area2Dbox);
+    areas->area = areas->area2D = areas->area2Dbox = nullptr;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------ trajectory input
+namespace {
+
+struct Traj {
+    std::vector<rvec*> x; std::vector<double> box;   // box: 9 per frame
+    int natoms = -1;
+    bool add(int n, const std::vector<double>& xyz, const double b[9]) {
+        if (natoms < 0) natoms = n;
+        if (n != natoms) { fprintf(stderr, "read_traj: frame %zu has %d atoms, expected %d\n", x.size(), n, natoms); return false; }
+        rvec* fr = (rvec*)malloc(sizeof(rvec) * (size_t)(n > 0 ? n : 1));
+        memcpy(fr, xyz.data(), sizeof(double) * 3 * (size_t)n);
+        x.push_back(fr);
+        box.insert(box.end(), b, b + 9);
+        return true;
+    }
+};
+
+bool ends_with(const std::string& s, const char* suf) {
+    size_t n = strlen(suf);
+    if (s.size() < n) return false;
+    for (size_t i = 0; i < n; ++i) if (tolower((unsigned char)s[s.size() - n + i]) != suf[i]) return false;
+    return true;
+}
+
+bool read_gro(FILE* f, Traj& t) {
+    char line[512];
+    std::vector<double> xyz;
+    while (fgets(line, sizeof line, f)) {                     // title
+        if (!fgets(line, sizeof line, f)) break;
+        int n = atoi(line);
+        if (n <= 0) return false;
+        xyz.resize(3 * (size_t)n);
+        for (int i = 0; i < n; ++i) {
+            if (!fgets(line, sizeof line, f)) return false;
+            // fixed columns: 20 characters of residue/atom fields, then x y z with a common width that is
+            // inferred from the spacing of the decimal points (the .gro precision is not fixed at 8.3)
+            const char* p = line + 20;
+            const char* d1 = strchr(p, '.');
+            const char* d2 = d1 ? strchr(d1 + 1, '.') : nullptr;
+            int w = (d1 && d2) ? (int)(d2 - d1) : 8;
+            char buf[64];
+            for (int c = 0; c < 3; ++c) {
+                if ((int)strlen(p) < w * (c + 1) - (c == 2 ? w - 1 : 0) && c < 2) return false;
+                int len = w < 63 ? w : 63;
+                strncpy(buf, p + c * w, len); buf[len] = 0;
+                xyz[3 * (size_t)i + c] = atof(buf);
+            }
+        }
+        if (!fgets(line, sizeof line, f)) return false;
+        double v[9] = {0}, b[9] = {0};
+        int k = sscanf(line, "%lf %lf %lf %lf %lf %lf %lf %lf %lf", v, v + 1, v + 2, v + 3, v + 4, v + 5, v + 6, v + 7, v + 8);
+        if (k < 3) return false;
+        // .gro order: v1(x) v2(y) v3(z) v1(y) v1(z) v2(x) v2(z) v3(x) v3(y)
+        b[0] = v[0]; b[4] = v[1]; b[8] = v[2];
+        if (k >= 9) { b[1] = v[3]; b[2] = v[4]; b[3] = v[5]; b[5] = v[6]; b[6] = v[7]; b[7] = v[8]; }
+        if (!t.add(n, xyz, b)) return false;
+    }
+    return !t.x.empty();
+}
+
+bool read_pdb(FILE* f, Traj& t) {
+    char line[512];
+    std::vector<double> xyz; double b[9] = {0};
+    auto flush = [&]() -> bool {
+        if (xyz.empty()) return true;
+        bool ok = t.add((int)(xyz.size() / 3), xyz, b);
+        xyz.clear();
+        return ok;
+    };
+    auto field = [](const char* s, int a, int n) { char buf[32]; int len = (int)strlen(s); if (len < a) return 0.0; strncpy(buf, s + a, n); buf[n] = 0; return atof(buf); };
+    while (fgets(line, sizeof line, f)) {
+        if (!strncmp(line, "CRYST1", 6)) {
+            memset(b, 0, sizeof b);                            // orthogonal part only (the hot path reads [0][0], [1][1])
+            b[0] = field(line, 6, 9) / 10.0; b[4] = field(line, 15, 9) / 10.0; b[8] = field(line, 24, 9) / 10.0;
+        } else if (!strncmp(line, "ATOM", 4) || !strncmp(line, "HETATM", 6)) {
+            xyz.push_back(field(line, 30, 8) / 10.0); xyz.push_back(field(line, 38, 8) / 10.0); xyz.push_back(field(line, 46, 8) / 10.0);
+        } else if (!strncmp(line, "ENDMDL", 6) || (!strncmp(line, "END", 3) && !isalpha((unsigned char)line[3]))) {
+            if (!flush()) return false;
+        }
+    }
+    return flush() && !t.x.empty();
+}
+
+// XDR (big-endian) primitives for .trr
+bool xdr_u32(FILE* f, uint32_t* v) { unsigned char b[4]; if (fread(b, 1, 4, f) != 4) return false; *v = (uint32_t)b[0] << 24 | (uint32_t)b[1] << 16 | (uint32_t)b[2] << 8 | b[3]; return true; }
+bool xdr_i32(FILE* f, int* v) { uint32_t u; if (!xdr_u32(f, &u)) return false; *v = (int)u; return true; }
+bool xdr_real(FILE* f, bool dbl, double* v) {
+    if (dbl) { uint32_t hi, lo; if (!xdr_u32(f, &hi) || !xdr_u32(f, &lo)) return false; uint64_t u = (uint64_t)hi << 32 | lo; memcpy(v, &u, 8); return true; }
+    uint32_t u; if (!xdr_u32(f, &u)) return false; float fl; memcpy(&fl, &u, 4); *v = fl; return true;
+}
+
+bool read_trr(FILE* f, Traj& t) {
+    std::vector<double> xyz;
+    for (;;) {
+        int magic;
+        if (!xdr_i32(f, &magic)) break;                        // clean EOF
+        if (magic != 1993) return false;
+        int slen, slen2;
+        if (!xdr_i32(f, &slen) || !xdr_i32(f, &slen2)) return false;   // xdr_string: length word twice (count, then opaque length)
+        if (slen2 < 0 || slen2 > 256) return false;
+        if (fseek(f, (slen2 + 3) & ~3, SEEK_CUR)) return false;
+        int sz[10], natoms, step, nre;
+        for (int i = 0; i < 10; ++i) if (!xdr_i32(f, &sz[i])) return false;   // ir e box vir pres top sym x v f
+        if (!xdr_i32(f, &natoms) || !xdr_i32(f, &step) || !xdr_i32(f, &nre)) return false;
+        const int box_size = sz[2], x_size = sz[7];
+        bool dbl;
+        if (box_size) dbl = box_size == 9 * 8; else if (natoms > 0 && x_size) dbl = x_size == natoms * 3 * 8; else return false;
+        double tl[2];
+        if (!xdr_real(f, dbl, &tl[0]) || !xdr_real(f, dbl, &tl[1])) return false;
+        double b[9] = {0};
+        if (box_size) for (int i = 0; i < 9; ++i) if (!xdr_real(f, dbl, &b[i])) return false;
+        if (fseek(f, sz[3] + sz[4], SEEK_CUR)) return false;                   // virial, pressure
+        if (!x_size) { if (fseek(f, sz[8] + sz[9], SEEK_CUR)) return false; continue; }   // frame without coordinates
+        xyz.resize(3 * (size_t)natoms);
+        for (size_t i = 0; i < xyz.size(); ++i) if (!xdr_real(f, dbl, &xyz[i])) return false;
+        if (fseek(f, sz[8] + sz[9], SEEK_CUR)) return false;                   // velocities, forces
+        if (!t.add(natoms, xyz, b)) return false;
+    }
+    return !t.x.empty();
+}
+
+}  // namespace
+
+extern "C" {
+
+void read_traj(const char* traj_fname, rvec*** x, matrix** box, int* nframes, int* natoms, output_env_t* oenv) {
+    (void)oenv;
+    *x = nullptr; *box = nullptr; *nframes = 0; *natoms = 0;
+    std::string name(traj_fname ? traj_fname : "");
+    if (ends_with(name, ".xtc")) {
+        fprintf(stderr, "read_traj: %s: .xtc decoding is not implemented in this build; convert to .trr, .gro or .pdb\n", traj_fname);
+        return;
+    }
+    FILE* f = fopen(traj_fname, "rb");
+    if (!f) { fprintf(stderr, "read_traj: cannot open %s\n", traj_fname); return; }
+    Traj t; bool ok;
+    if (ends_with(name, ".gro")) ok = read_gro(f, t);
+    else if (ends_with(name, ".pdb")) ok = read_pdb(f, t);
+    else if (ends_with(name, ".trr")) ok = read_trr(f, t);
+    else { fprintf(stderr, "read_traj: %s: unknown trajectory format (supported: .gro .pdb .trr)\n", traj_fname); fclose(f); return; }
+    fclose(f);
+    if (!ok) {
+        fprintf(stderr, "read_traj: %s: malformed or empty trajectory\n", traj_fname);
+        for (rvec* p : t.x) free(p);
+        return;
+    }
+    const int F = (int)t.x.size();
+    *x = (rvec**)malloc(sizeof(rvec*) * (size_t)F);
+    *box = (matrix*)malloc(sizeof(matrix) * (size_t)F);
+    memcpy(*x, t.x.data(), sizeof(rvec*) * (size_t)F);
+    memcpy(*box, t.box.data(), sizeof(double) * 9 * (size_t)F);
+    *nframes = F; *natoms = t.natoms;
+}
+
+void ndx_filter_traj(const char* ndx_fname, rvec** pre_x, rvec*** new_x, int nframes, int* natoms) {
+    std::vector<int> idx;
+    FILE* f = fopen(ndx_fname, "r");
+    if (!f) { fprintf(stderr, "ndx_filter_traj: cannot open %s\n", ndx_fname); }
+    else {
+        char line[4096]; int groups = 0;
+        while (fgets(line, sizeof line, f)) {
+            const char* p = line; while (isspace((unsigned char)*p)) ++p;
+            if (*p == '[') { if (++groups > 1) break; continue; }
+            if (groups != 1) continue;
+            char* q = (char*)p;
+            for (;;) { char* end; long v = strtol(q, &end, 10); if (end == q) break; idx.push_back((int)v - 1); q = end; }
+        }
+        fclose(f);
+    }
+    const int n_in = *natoms, n = (int)idx.size();
+    *new_x = (rvec**)malloc(sizeof(rvec*) * (size_t)(nframes > 0 ? nframes : 1));
+    for (int fr = 0; fr < nframes; ++fr) {
+        (*new_x)[fr] = (rvec*)malloc(sizeof(rvec) * (size_t)(n > 0 ? n : 1));
+        for (int i = 0; i < n; ++i) {
+            const int a = idx[i];
+            if (a < 0 || a >= n_in) { fprintf(stderr, "ndx_filter_traj: atom %d out of range (1..%d)\n", a + 1, n_in); memset((*new_x)[fr][i], 0, sizeof(rvec)); continue; }
+            memcpy((*new_x)[fr][i], pre_x[fr][a], sizeof(rvec));
+        }
+    }
+    *natoms = n;
+}
+
+}  // extern "C"

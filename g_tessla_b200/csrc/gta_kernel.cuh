@@ -34,7 +34,7 @@ struct KParams {
     double* corr; int corr_cap; int* ncorr;
     unsigned int* work;                        // global frame counter
     unsigned long long* dbg;                   // phase timers (GT_PHASE_TIMING builds), else unused
-    int coop_nodes;                            // levels with at most this many nodes use 16-lane cooperative merges
+    int coop_nodes;                            // levels with at most this many nodes use warp-cooperative merges
 };
 
 __host__ __device__ inline int pool_edges(int cap) { return 3 * cap + 64; }
@@ -312,16 +312,12 @@ __global__ void __launch_bounds__(T, MINB) tessellate_kernel(const KParams p) {
                     const int slot = (tid & 31) * W + (tid >> 5);
                     for (int k = slot; k < nodes; k += T) process_node(f, ln, d, k);
                 } else {
-                    // upper levels: few long merges, 16 lanes each (dt_coop.cuh)
-                    const int gl = tid & (GT_G - 1);
-                    const unsigned gmask = ((1u << GT_G) - 1u) << ((tid & 31) & ~(GT_G - 1));
-                    constexpr int NG = T / GT_G;                   // groups per CTA, dealt to warps round-robin too
-                    const int grp = ((tid >> 4) & 1) * (T / 32) + (tid >> 5);
-                    for (int k = grp; k < nodes; k += NG) {
+                    // upper levels: few long merges, one warp each (dt_coop.cuh)
+                    for (int k = tid >> 5; k < nodes; k += T / 32) {
                         int ia, ib;
                         if (!tree_node(n, d, k, &ia, &ib) || ib - ia < 1) continue;
-                        if (ib - ia < 3) { if (gl == 0) leaf(f, ln, ia, ib); }
-                        else coop_merge(f, ln, (ia + ib) / 2, gmask, gl);
+                        if (ib - ia < 3) { if ((tid & 31) == 0) leaf(f, ln, ia, ib); }
+                        else coop_merge(f, ln, (ia + ib) / 2, p.dbg);
                     }
                 }
                 __syncthreads();

@@ -1,0 +1,214 @@
+// gta_large.cu -- one large frame (BASELINE cfg 4: 10^6 points): the same divide-and-conquer as the
+// batched kernel, run level by level over GLOBAL memory with 32-bit indices.
+//
+// Replaces dtriangulate (reference src/delaunay_tri.c:413-507) for point sets that do not fit the
+// shared-memory kernel. The reference handles such a frame serially (one core, 5.5 s for 10^6 points).
+// Here every level of the reference's recursion tree (:535-539, same split index) is one launch:
+// the lower levels hold up to n/2 independent merges (one thread each, dt_core.cuh::merge -- exactly the
+// code the batched kernel and the host emulation run), the upper levels hold few long merges and give
+// each its own warp so that they do not serialise behind each other. Because it is the reference's own
+// decision sequence, the result is the reference's triangulation on EVERY input, including exactly
+// cocircular point sets where an insert-and-flip triangulator would pick different diagonals; that is
+// why a flip-based kernel was not used for this path.
+//
+// Sorting is two stable cub radix passes (by y, then by x) on order-preserving keys, followed by the
+// reference comparator's near-tie rule (delaunay_tri.c:115-123) on runs of |dx| < 1e-12.
+// Freed edges are recycled only inside the merge that freed them (no shared free stack in this mode):
+// the pool is sized for every edge ever created.
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "dt_core.cuh"
+#include "../../include/gta_b200.h"
+
+namespace gt {
+typedef FrameT<uint32_t> FrameL;
+
+__device__ __forceinline__ unsigned long long okey64(double v) {   // order-preserving bits
+    unsigned long long b = (unsigned long long)__double_as_longlong(v + 0.0);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__global__ void large_keys(const double* pts, int n, unsigned long long* kx, unsigned long long* ky, uint32_t* idx, uint32_t* err) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x = pts[2 * (size_t)i], y = pts[2 * (size_t)i + 1];
+    if (!isfinite(x) || !isfinite(y)) atomicOr(err, 0x100u);
+    kx[i] = okey64(x); ky[i] = okey64(y); idx[i] = (uint32_t)i;
+}
+__global__ void large_gather_key(const unsigned long long* kx, const uint32_t* idx, int n, unsigned long long* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = kx[idx[i]];
+}
+__global__ void large_gather_pts(const double* pts, const uint32_t* perm, int n, Pt* pt, uint32_t* head) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t o = perm[i];
+    pt[i].x = pts[2 * (size_t)o]; pt[i].y = pts[2 * (size_t)o + 1];
+    head[i] = FrameL::NIL;
+}
+// Near-tie runs (see gta_kernel.cuh) and the duplicate check of the reference's contract.
+__global__ void large_fix_ties(Pt* pt, uint32_t* perm, int n, uint32_t* err) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    auto tie = [&](int a, int b) { double d = pt[a].x - pt[b].x; return d < 1e-12 && d > -1e-12; };
+    if ((i == 0 || !tie(i, i - 1)) && i + 1 < n && tie(i + 1, i)) {
+        int e = i + 1; bool inexact = false;
+        while (e < n && tie(e, e - 1)) { inexact |= (pt[e].x != pt[e - 1].x); ++e; }
+        if (inexact) {
+            if (!tie(e - 1, i)) atomicOr(err, 0x200u);
+            for (int a = i + 1; a < e; ++a) {
+                Pt pa = pt[a]; uint32_t oa = perm[a]; int b = a - 1;
+                while (b >= i && pt[b].y > pa.y) { pt[b + 1] = pt[b]; perm[b + 1] = perm[b]; --b; }
+                pt[b + 1] = pa; perm[b + 1] = oa;
+            }
+        }
+    }
+}
+__global__ void large_check_dups(const Pt* pt, int n, uint32_t* err) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 1 || i >= n) return;
+    double dx = pt[i].x - pt[i - 1].x, dy = pt[i].y - pt[i - 1].y;
+    if (dx < 1e-12 && dx > -1e-12 && dy < 1e-12 && dy > -1e-12) atomicOr(err, 0x400u);
+}
+
+// One level of the recursion tree. lanes_per_node = 1: node k is thread k (lower levels, many short merges);
+// lanes_per_node = 32: node k is warp k, lane 0 walks the merge (upper levels: lanes of one warp that walk
+// different merges would serialise).
+__global__ void __launch_bounds__(128) large_level(FrameL f, int depth, int nodes, int lanes_per_node) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long k = t / lanes_per_node;
+    if (k >= nodes || (t % lanes_per_node) != 0) return;
+    Lane ln; ln.free_head = FrameL::NIL;
+    process_node(f, ln, depth, (int)k);
+}
+
+__global__ void large_count(FrameL f, uint32_t* cnt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= f.n) return;
+    cnt[i] = (uint32_t)vertex_triangles(f, i, [](int, int) {});
+}
+__global__ void large_emit(FrameL f, const uint32_t* offs, const uint32_t* perm, int* tri, int tri_cap) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= f.n) return;
+    uint32_t o = offs[i];
+    const int oi = (int)perm[i];
+    vertex_triangles(f, i, [&](int n1, int n2) {
+        if ((int)o < tri_cap) { tri[3 * (size_t)o] = oi; tri[3 * (size_t)o + 1] = (int)perm[n1]; tri[3 * (size_t)o + 2] = (int)perm[n2]; }
+        ++o;
+    });
+}
+}  // namespace gt
+
+namespace {
+thread_local std::string g_lerr;
+thread_local double g_large_ms = 0.0;
+}
+extern "C" const char* gta_b200_large_error(void) { return g_lerr.c_str(); }
+extern "C" double gta_b200_large_last_ms(void) { return g_large_ms; }
+
+#define LCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_lerr = std::string(#call) + ": " + cudaGetErrorString(e_); rc = GTA_B200_E_CUDA; goto done; } } while (0)
+
+extern "C" int gta_b200_triangulate_large(const double* points, int npoints, int device, int* tri, int tri_cap, int* ntri, int* status) {
+    using namespace gt;
+    int rc = GTA_B200_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); g_lerr = "no CUDA device: libgtessla_b200 has no CPU path"; return GTA_B200_E_NO_DEVICE; }
+    if (!points || npoints < 0 || (tri_cap > 0 && !tri)) { g_lerr = "bad argument"; return GTA_B200_E_ARG; }
+    if (status) *status = 0;
+    if (ntri) *ntri = 0;
+    if (npoints < 2) { if (status) *status = GTA_B200_ST_TOO_FEW_POINTS; return GTA_B200_OK; }
+    if (npoints > (1 << 27)) { g_lerr = "too many points for 32-bit half-edge indices"; return GTA_B200_E_TOO_LARGE; }
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { g_lerr = "cudaSetDevice failed"; return GTA_B200_E_CUDA; }
+
+    const int n = npoints;
+    const uint32_t cap_e = (uint32_t)std::min<long long>(8ll * n + 1024, 0x7fffffff / 2);
+    double* d_pts = nullptr; Pt* d_pt = nullptr; unsigned long long *d_k0 = nullptr, *d_k1 = nullptr, *d_ky = nullptr;
+    uint32_t *d_i0 = nullptr, *d_i1 = nullptr, *d_head = nullptr, *d_dst = nullptr, *d_nxt = nullptr, *d_prv = nullptr, *d_ctl = nullptr, *d_cnt = nullptr, *d_off = nullptr;
+    int* d_tri = nullptr; void* d_tmp = nullptr; size_t tmp_bytes = 0, tb2 = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    const int B = 256, G = (n + B - 1) / B;
+    uint32_t hctl[4] = {0, 0, 0, 0};
+    LCK(cudaEventCreate(&ev0)); LCK(cudaEventCreate(&ev1));
+    LCK(cudaMalloc((void**)&d_pts, sizeof(double) * 2 * (size_t)n));
+    LCK(cudaMalloc((void**)&d_pt, sizeof(Pt) * (size_t)n));
+    LCK(cudaMalloc((void**)&d_k0, 8 * (size_t)n)); LCK(cudaMalloc((void**)&d_k1, 8 * (size_t)n)); LCK(cudaMalloc((void**)&d_ky, 8 * (size_t)n));
+    LCK(cudaMalloc((void**)&d_i0, 4 * (size_t)n)); LCK(cudaMalloc((void**)&d_i1, 4 * (size_t)n));
+    LCK(cudaMalloc((void**)&d_head, 4 * (size_t)n));
+    LCK(cudaMalloc((void**)&d_dst, 8 * (size_t)cap_e)); LCK(cudaMalloc((void**)&d_nxt, 8 * (size_t)cap_e)); LCK(cudaMalloc((void**)&d_prv, 8 * (size_t)cap_e));
+    LCK(cudaMalloc((void**)&d_ctl, 16)); LCK(cudaMemset(d_ctl, 0, 16));
+    LCK(cudaMalloc((void**)&d_cnt, 4 * (size_t)n)); LCK(cudaMalloc((void**)&d_off, 4 * (size_t)n));
+    LCK(cudaMemcpy(d_pts, points, sizeof(double) * 2 * (size_t)n, cudaMemcpyHostToDevice));
+    LCK(cudaEventRecord(ev0));
+    {
+        // ---- sort: stable by y, then stable by x  => lexicographic (x, y)
+        large_keys<<<G, B>>>(d_pts, n, d_k0, d_ky, d_i0, d_ctl + 2);
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_ky, d_k1, d_i0, d_i1, n);
+        cub::DeviceScan::ExclusiveSum(nullptr, tb2, d_cnt, d_off, n);
+        tmp_bytes = std::max(tmp_bytes, tb2);
+        LCK(cudaMalloc(&d_tmp, tmp_bytes));
+        cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_ky, d_k1, d_i0, d_i1, n);          // by y: order in d_i1
+        large_gather_key<<<G, B>>>(d_k0, d_i1, n, d_ky);                                       // x keys in y order
+        cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_ky, d_k1, d_i1, d_i0, n);          // by x (stable): perm in d_i0
+        large_gather_pts<<<G, B>>>(d_pts, d_i0, n, d_pt, d_head);
+        large_fix_ties<<<G, B>>>(d_pt, d_i0, n, d_ctl + 2);
+        large_check_dups<<<G, B>>>(d_pt, n, d_ctl + 2);
+        LCK(cudaGetLastError());
+        LCK(cudaMemcpy(hctl, d_ctl, 16, cudaMemcpyDeviceToHost));
+    }
+    if (hctl[2]) {
+        int st = 0;
+        if (hctl[2] & 0x100u) st |= GTA_B200_ST_NONFINITE;
+        if (hctl[2] & 0x200u) st |= GTA_B200_ST_NEAR_TIE_X;
+        if (hctl[2] & 0x400u) st |= GTA_B200_ST_DUPLICATE;
+        if (status) *status = st;
+        goto done;
+    }
+    {
+        FrameL f;
+        f.pt = d_pt; f.head = d_head; f.dst = d_dst; f.nxt = d_nxt; f.prv = d_prv;
+        f.bump = d_ctl; f.stack = nullptr; f.err = d_ctl + 1; f.n = n; f.cap_e = cap_e;
+        const int D = tree_depth(n);
+        for (int d = D; d >= 0; --d) {
+            const int nodes = 1 << d;
+            const int lpn = nodes <= 16384 ? 32 : 1;               // one warp per merge while the GPU has warps to spare
+            const long long threads = (long long)nodes * lpn;
+            large_level<<<(unsigned)((threads + 127) / 128), 128>>>(f, d, nodes, lpn);
+        }
+        LCK(cudaGetLastError());
+        large_count<<<G, B>>>(f, d_cnt);
+        cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_cnt, d_off, n);
+        uint32_t last_off = 0, last_cnt = 0;
+        LCK(cudaMemcpy(&last_off, d_off + (n - 1), 4, cudaMemcpyDeviceToHost));
+        LCK(cudaMemcpy(&last_cnt, d_cnt + (n - 1), 4, cudaMemcpyDeviceToHost));
+        LCK(cudaMemcpy(hctl, d_ctl, 16, cudaMemcpyDeviceToHost));
+        int st = 0;
+        if (hctl[1] & GT_ERR_POOL) st |= GTA_B200_ST_POOL;
+        if (hctl[1] & GT_ERR_RANGE) st |= GTA_B200_ST_PRECISION_RANGE;
+        if (hctl[1] & GT_ERR_RING) st |= GTA_B200_ST_INTERNAL;
+        if (status) *status = st;
+        if (st) goto done;
+        const int total = (int)(last_off + last_cnt);
+        if (ntri) *ntri = total;
+        if (tri && tri_cap > 0) {
+            const int keep = std::min(total, tri_cap);
+            LCK(cudaMalloc((void**)&d_tri, sizeof(int) * 3 * (size_t)std::max(keep, 1)));
+            large_emit<<<G, B>>>(f, d_off, d_i0, d_tri, keep);
+            LCK(cudaGetLastError());
+            LCK(cudaEventRecord(ev1));
+            LCK(cudaMemcpy(tri, d_tri, sizeof(int) * 3 * (size_t)keep, cudaMemcpyDeviceToHost));
+        } else LCK(cudaEventRecord(ev1));
+        LCK(cudaEventSynchronize(ev1));
+        float ms = 0.f; cudaEventElapsedTime(&ms, ev0, ev1); g_large_ms = ms;
+    }
+done:
+    cudaFree(d_pts); cudaFree(d_pt); cudaFree(d_k0); cudaFree(d_k1); cudaFree(d_ky); cudaFree(d_i0); cudaFree(d_i1);
+    cudaFree(d_head); cudaFree(d_dst); cudaFree(d_nxt); cudaFree(d_prv); cudaFree(d_ctl); cudaFree(d_cnt); cudaFree(d_off);
+    cudaFree(d_tri); cudaFree(d_tmp);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    return rc;
+}

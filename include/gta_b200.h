@@ -105,6 +105,15 @@ int gta_b200_tessellate_frames(const double *const *x, const double *box9, int n
                                double espace, unsigned flags, int ngpus, int nthreads,
                                double *area, double *area2d, double *areabox, int *status);
 
+/* ---- one large frame (reference dtriangulate on a point set beyond gta_b200_max_points(), e.g. the
+ * 10^6-point coarse-grained patch): HOST pointers, raw 2-D points [npoints][2], triangles [tri_cap][3] in
+ * the reference's emission order, *ntri their count, *status the GTA_B200_ST_* bits. Runs on one GPU
+ * (a single triangulation does not shard). */
+int gta_b200_triangulate_large(const double *points, int npoints, int device,
+                               int *tri, int tri_cap, int *ntri, int *status);
+/* device milliseconds (sort + all levels + enumeration, without the host copies) of the last call on this thread */
+double gta_b200_large_last_ms(void);
+
 /* Milliseconds the last gta_b200_tessellate_batch call on this thread spent in its kernels
  * (CUDA events on the launching streams), and the number of kernel launches it made. */
 double gta_b200_last_kernel_ms(void);

@@ -18,3 +18,4 @@ tot = v[:21].sum()
 print('coop_nodes', os.environ.get('GTA_B200_COOP_NODES'), 'frames', nf, 'kernel_ms', r['kernel_ms'], 'cycles/frame %.0f' % (tot / nf))
 for i, nm in enumerate(names):
     if v[i]: print('%-10s %9.0f cyc/frame %5.1f%%' % (nm, v[i] / nf, 100 * v[i] / tot))
+if v[26]: print('coop merges %d: tangent+first %.0f cyc/merge, loop %.0f cyc/step, rounds/step %.2f, steps/merge %.1f' % (v[26], v[22]/v[26], v[23]/v[25], v[24]/v[25], v[25]/v[26]))

@@ -8,14 +8,22 @@
 #include <cstring>
 #include <numeric>
 #include <vector>
+#define GT_STATS 1
 #include "../../g_tessla_b200/csrc/dt_core.cuh"
+namespace gt { Stats g_stats; }
 
 extern "C" {
+
+// per-level work counters of the last emu_triangulate call: [level][0..5] = nodes, orient2d, incircle,
+// merge steps, cuts, longest node (steps)
+static long g_level[32][6];
+void emu_level_stats(long* out) { memcpy(out, g_level, sizeof g_level); }
 
 // points [n][2] -> triangles in emission order (indices into the input). Returns ntri or -(err bits).
 int emu_triangulate(const double* points, int n, int* tri_out) {
     using namespace gt;
     if (n < 2) return -1000;
+    memset(g_level, 0, sizeof g_level);
     std::vector<int> perm(n);
     std::iota(perm.begin(), perm.end(), 0);
     std::sort(perm.begin(), perm.end(), [&](int u, int v) {
@@ -48,7 +56,17 @@ int emu_triangulate(const double* points, int n, int* tri_out) {
     for (int d = D; d >= 0; --d) {
         // one "lane" per node, flushed at the end of the level like the kernel does
         std::vector<Lane> lanes(1 << d);
-        for (int k = 0; k < (1 << d); ++k) { lanes[k].free_head = GT_NIL; process_node(f, lanes[k], d, k); }
+        memset(g_level[d], 0, sizeof g_level[d]);
+        for (int k = 0; k < (1 << d); ++k) {
+            lanes[k].free_head = GT_NIL;
+            Stats s0 = g_stats;
+            process_node(f, lanes[k], d, k);
+            int ia, ib;
+            if (tree_node(n, d, k, &ia, &ib) && ib - ia >= 1) g_level[d][0]++;
+            g_level[d][1] += g_stats.o2d - s0.o2d; g_level[d][2] += g_stats.icc - s0.icc;
+            g_level[d][3] += g_stats.steps - s0.steps; g_level[d][4] += g_stats.cuts - s0.cuts;
+            if (g_stats.steps - s0.steps > g_level[d][5]) g_level[d][5] = g_stats.steps - s0.steps;
+        }
         for (int k = 0; k < (1 << d); ++k) flush_lane(f, lanes[k]);
         if (err) return -(int)err;
     }

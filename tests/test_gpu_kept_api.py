@@ -1,0 +1,150 @@
+"""GPU: the reference's own entry points (include/delaunay_tri.h, include/gta_tri.h) and the g_tessla CLI,
+served by libgtessla_b200.so, against the oracle."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from g_tessla_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+
+
+class DTri(C.Structure):
+    _fields_ = [("points", dp), ("npoints", C.c_int), ("triangles", ip), ("ntriangles", C.c_int), ("nverts", C.c_int)]
+
+
+class TriArea(C.Structure):
+    _fields_ = [("area", dp), ("area2D", dp), ("area2Dbox", dp), ("natoms", C.c_int), ("nframes", C.c_int)]
+
+
+def test_dtriangulate_entry_point(gta, checker):
+    L = gta.lib()
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    L.dtinit()
+    for n in (2, 3, 50, 1156, 6000):                        # 6000 > shared-memory capacity: large path
+        p = np.ascontiguousarray(np.random.default_rng(n).random((n, 2)) * 9)
+        t = DTri(p.ctypes.data_as(dp), n, None, -1, -1)
+        L.dtriangulate(C.byref(t))
+        want, _ = checker.triangulate(p)
+        assert t.ntriangles == len(want) and t.nverts == n
+        got = np.ctypeslib.as_array(t.triangles, shape=(t.ntriangles, 3)).copy() if t.ntriangles else np.zeros((0, 3), np.int32)
+        libc.free(t.triangles)                                # caller frees, as with the reference (gta_tri.c:412)
+        assert np.array_equal(got, want)
+    # fewer than two points: message on stderr, struct untouched (reference delaunay_tri.c:416-421)
+    p = np.zeros((1, 2))
+    t = DTri(p.ctypes.data_as(dp), 1, None, -7, -9)
+    L.dtriangulate(C.byref(t))
+    assert t.ntriangles == -7 and t.nverts == -9 and not t.triangles
+    assert L.dt_last_status() & 1
+
+
+def test_delaunay_tessellate_entry_point(gta, checker):
+    L = gta.lib()
+    c = synth.config(2, nframes=50)
+    F, N = c["xyz"].shape[:2]
+    frames = [np.ascontiguousarray(c["xyz"][f]) for f in range(F)]          # one block per frame, like read_traj
+    xptr = (dp * F)(*[fr.ctypes.data_as(dp) for fr in frames])
+    box = np.zeros((F, 3, 3)); box[:, 0, 0] = c["box"][:, 0]; box[:, 1, 1] = c["box"][:, 1]; box[:, 2, 2] = c["box"][:, 2]
+    a = TriArea(None, None, None, N, F)
+    L.delaunay_tessellate.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.POINTER(TriArea), C.c_ubyte]
+    L.delaunay_tessellate(xptr, box.ctypes.data, 0.8, 0, C.byref(a), 3)
+    want = checker.tessellate(c["xyz"], c["box"], 0.8, 3)
+    area = np.ctypeslib.as_array(a.area, shape=(F,)); a2 = np.ctypeslib.as_array(a.area2D, shape=(F,)); ab = np.ctypeslib.as_array(a.area2Dbox, shape=(F,))
+    assert np.allclose(area, want["area"], rtol=1e-12, atol=0)
+    assert np.allclose(a2, want["area2d"], rtol=1e-12, atol=0)
+    assert np.array_equal(ab, want["areabox"])
+    for f in range(F):
+        assert np.array_equal(frames[f], c["xyz"][f])          # the caller's frames are not modified
+    L.free_tri_area(C.byref(a))
+    # one frame, no correction: delaunay_surface_area
+    L.delaunay_surface_area.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_ubyte, dp, dp]
+    a3, a2d = C.c_double(-1), C.c_double(-1)
+    L.delaunay_surface_area(frames[0].ctypes.data, box[0].ctypes.data, N, 0, C.byref(a2d), C.byref(a3))
+    w = checker.tessellate(c["xyz"][:1], c["box"][:1], 0.8, 2)
+    assert abs(a3.value - w["area"][0]) <= 1e-12 * w["area"][0] and abs(a2d.value - w["area2d"][0]) <= 1e-12 * w["area2d"][0]
+
+
+def _write_gro(path, xyz, box, fmt="%8.3f"):
+    with open(path, "w") as f:
+        for fr in range(len(xyz)):
+            f.write("frame t= %d\n%5d\n" % (fr, xyz.shape[1]))
+            for i, (x, y, z) in enumerate(xyz[fr]):
+                f.write("%5d%-5s%5s%5d" % (i + 1, "POPC", "P", i + 1) + (fmt % x) + (fmt % y) + (fmt % z) + "\n")
+            f.write("%10.5f%10.5f%10.5f\n" % tuple(box[fr]))
+
+
+def _expected_dat(area, area2d, areabox, natoms):
+    """The reference's print_areas format (src/gta_tri.c:448-473), restated."""
+    out = []
+    if area2d is not None:
+        out.append('# FRAME\tAREA\t2DAREA\tBOX-AREA\t""/PARTICLE\n')
+        for i in range(len(area)):
+            out.append("%d\t%f\t%f\t%f\t%f\t%f\t%f\n" % (i, area[i], area2d[i], areabox[i], area[i] / natoms, area2d[i] / natoms, areabox[i] / natoms))
+    else:
+        out.append('# FRAME\tAREA\tBOX-AREA\t""/PARTICLE\n')
+        for i in range(len(area)):
+            out.append("%d\t%f\t%f\t%f\t%f\n" % (i, area[i], areabox[i], area[i] / natoms, areabox[i] / natoms))
+    return "".join(out)
+
+
+def test_cli_gro_ndx_dat(gta, checker, tmp_path):
+    exe = os.path.join(ROOT, "g_tessla_b200", "g_tessla")
+    assert os.path.exists(exe), "CLI not built (python -m g_tessla_b200.build)"
+    c = synth.config(1, nframes=12)
+    # trajectory with 80 atoms per frame of which an index group selects the 64 lipid P atoms; .gro keeps 3 decimals
+    rng = np.random.default_rng(3)
+    xyz = np.round(c["xyz"], 3); box = np.round(c["box"], 5)
+    extra = np.round(rng.random((12, 16, 3)) * 6.0, 3)
+    full = np.concatenate([extra[:, :8], xyz, extra[:, 8:]], axis=1)
+    _write_gro(tmp_path / "traj.gro", full, box)
+    with open(tmp_path / "index.ndx", "w") as f:
+        f.write("[ P_atoms ]\n")
+        ids = np.arange(9, 9 + 64)
+        for k in range(0, 64, 15):
+            f.write(" ".join(str(v) for v in ids[k:k + 15]) + "\n")
+        f.write("[ other ]\n1 2 3\n")
+    for flags, extra_args in ((1, ["-corr"]), (3, ["-corr", "-2d"]), (0, [])):
+        r = subprocess.run([exe, "-f", "traj.gro", "-n", "index.ndx", "-o", "out.dat", "-espace", "0.8"] + extra_args,
+                           cwd=tmp_path, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr + r.stdout
+        want = checker.tessellate(xyz, box, 0.8, flags)
+        exp = _expected_dat(want["area"], want["area2d"], want["areabox"], 64)
+        assert open(tmp_path / "out.dat").read() == exp
+        assert "Average surface area: %f" % want["area"].mean() in r.stdout
+        assert "Surface areas saved to out.dat" in r.stdout
+    assert os.path.exists(tmp_path / "gta.log")
+
+
+def test_readers_pdb_trr(gta, checker, tmp_path):
+    import struct
+    exe = os.path.join(ROOT, "g_tessla_b200", "g_tessla")
+    c = synth.config(1, nframes=5)
+    xyz = np.round(c["xyz"], 3); box = np.round(c["box"], 3)
+    # multi-model PDB (Angstrom)
+    with open(tmp_path / "t.pdb", "w") as f:
+        for fr in range(5):
+            f.write("CRYST1%9.3f%9.3f%9.3f  90.00  90.00  90.00 P 1           1\nMODEL %8d\n" % (box[fr, 0] * 10, box[fr, 1] * 10, box[fr, 2] * 10, fr + 1))
+            for i, (x, y, z) in enumerate(xyz[fr]):
+                f.write("ATOM  %5d  P   POP A%4d    %8.3f%8.3f%8.3f  1.00  0.00\n" % (i + 1, i + 1, x * 10, y * 10, z * 10))
+            f.write("TER\nENDMDL\n")
+    # double-precision TRR (XDR, big-endian)
+    with open(tmp_path / "t.trr", "wb") as f:
+        for fr in range(5):
+            n = xyz.shape[1]
+            f.write(struct.pack(">ii", 1993, 13) + struct.pack(">i", 12) + b"GMX_trn_file")
+            f.write(struct.pack(">13i", 0, 0, 72, 0, 0, 0, 0, n * 24, 0, 0, n, fr, 0))
+            f.write(struct.pack(">2d", float(fr), 0.0))
+            b = np.zeros((3, 3)); b[0, 0], b[1, 1], b[2, 2] = c["box"][fr]
+            f.write(b.astype(">f8").tobytes()); f.write(c["xyz"][fr].astype(">f8").tobytes())
+    want_r = checker.tessellate(xyz, box, 0.8, 1)
+    want_f = checker.tessellate(c["xyz"], c["box"], 0.8, 1)
+    for name, want in (("t.pdb", want_r), ("t.trr", want_f)):
+        r = subprocess.run([exe, "-f", name, "-o", name + ".dat", "-corr"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr + r.stdout
+        assert open(tmp_path / (name + ".dat")).read() == _expected_dat(want["area"], None, want["areabox"], 64), name
