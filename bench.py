@@ -247,7 +247,7 @@ def run_native(args):
         ach = ALG_BYTES_PER_FRAME * F / (kern_ms / 1e3) / 1e9                 # GB/s of algorithmic bytes per launch
         fl = ALG_FLOP_PER_FRAME * F / (kern_ms / 1e3) / 1e12
         thr, smem, fps = (g.api.C.c_int(), g.api.C.c_size_t(), g.api.C.c_int())
-        L.gta_b200_launch_shape(max_points, g.api.C.byref(thr), g.api.C.byref(smem), g.api.C.byref(fps))
+        L.gta_b200_launch_shape(max_points, NATOMS, g.api.C.byref(thr), g.api.C.byref(smem), g.api.C.byref(fps))
         line = {
             "metric": "tessellated frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,

@@ -45,7 +45,7 @@ def lib() -> C.CDLL:
     L.gta_b200_last_error.restype = C.c_char_p
     L.gta_b200_last_kernel_ms.restype = C.c_double
     L.gta_b200_max_points_for.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint]
-    L.gta_b200_launch_shape.argtypes = [C.c_int, _ip, C.POINTER(C.c_size_t), _ip]
+    L.gta_b200_launch_shape.argtypes = [C.c_int, C.c_int, _ip, C.POINTER(C.c_size_t), _ip]
     L.gta_b200_tessellate_device.argtypes = [
         C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint,
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,

@@ -21,6 +21,21 @@
 
 namespace gt {
 
+// The merge walks stay inlined in their kernels: an out-of-line merge receives the Frame by reference, which
+// parks its pointers in local memory and costs a local load per ring access (measured: 126k -> 82k frames/s).
+#define GT_MERGE_LINKAGE GT_INLINE
+
+// Filters of the vertex predicates: one shared out-of-line copy (0, default: measured 126k frames/s on cfg 3)
+// or inlined at every call site (1: larger code, more spills, measured 51k frames/s with out-of-line merges).
+#ifndef GT_PRED_INLINE
+#define GT_PRED_INLINE 0
+#endif
+#if GT_PRED_INLINE
+#define GT_PRED_LINKAGE GT_INLINE
+#else
+#define GT_PRED_LINKAGE GT_NOINLINE
+#endif
+
 typedef uint16_t u16;
 #define GT_NIL 0xFFFFu      // empty marker of the 16-bit frame type (FrameT<u16>::NIL)
 
@@ -73,14 +88,14 @@ GT_INLINE void atomic_or_u32(uint32_t* p, uint32_t v) { *p |= v; }
 // Out of line on the device: the merge code calls them from ~20 sites, and one shared copy keeps
 // the kernel's register count and instruction-cache footprint down (the walk is latency bound,
 // a call costs less than the i-cache misses of 20 inlined incircle bodies).
-GT_NOINLINE bool ccw_pts(const Pt* pt, uint32_t* err, int a, int b, int c) {
+GT_PRED_LINKAGE bool ccw_pts(const Pt* pt, uint32_t* err, int a, int b, int c) {
     GT_STAT(o2d);
     Pt pa = pt[a], pb = pt[b], pc = pt[c];
     int s = orient2d_sign(pa.x, pa.y, pb.x, pb.y, pc.x, pc.y);
     if (s == GT_RANGE_ERR) { atomic_or_u32(err, GT_ERR_RANGE); return false; }
     return s > 0;
 }
-GT_NOINLINE bool in_circle_pts(const Pt* pt, uint32_t* err, int a, int b, int c, int d) {
+GT_PRED_LINKAGE bool in_circle_pts(const Pt* pt, uint32_t* err, int a, int b, int c, int d) {
     // incircle with a repeated point is exactly 0 (two equal rows) -- the commonest
     // degenerate call of the merge loop (r2 == li when ri has two neighbours); skip the math.
     if (a == d || b == d || c == d || a == b || a == c || b == c) return false;
@@ -242,7 +257,7 @@ GT_INLINE void leaf(const F& f, Lane& ln, int ia, int ib) {
 // ---------------------------------------------------------------- merge (reference :535-599)
 // Left half = sorted positions ia..mid, right half = mid+1..ib, both already triangulated.
 template <class F>
-GT_INLINE void merge(const F& f, Lane& ln, int mid) {
+GT_MERGE_LINKAGE void merge(const F& f, Lane& ln, int mid) {
     // lower common tangent (reference lct :337-370): walk starts at the rightmost vertex of the
     // left half (position mid) and the leftmost of the right half (mid+1).
     int lx = mid, ly = mid + 1;

@@ -153,8 +153,8 @@ int gta_b200_max_points_for(const double* box, int box_stride, int nframes, int 
     return natoms + best;
 }
 
-int gta_b200_launch_shape(int max_points, int* threads_per_frame, size_t* smem_bytes, int* frames_per_sm) {
-    Shape s = shape_for(max_points);
+int gta_b200_launch_shape(int max_points, int natoms, int* threads_per_frame, size_t* smem_bytes, int* frames_per_sm) {
+    Shape s = shape_for(std::max(max_points, natoms), natoms);
     if (threads_per_frame) *threads_per_frame = s.threads;
     if (smem_bytes) *smem_bytes = s.smem;
     if (frames_per_sm) {

@@ -54,8 +54,9 @@ const char *gta_b200_last_error(void);
 int gta_b200_max_points_for(const double *box, int box_stride, int nframes, int natoms,
                             double espace, unsigned flags);
 
-/* Threads per frame and dynamic shared memory the kernel will use for max_points (for reports). */
-int gta_b200_launch_shape(int max_points, int *threads_per_frame, size_t *smem_bytes, int *frames_per_sm);
+/* Threads per frame, dynamic shared memory and resident frames per SM the kernel will use for frames of
+ * natoms caller points and at most max_points points in total (for reports). */
+int gta_b200_launch_shape(int max_points, int natoms, int *threads_per_frame, size_t *smem_bytes, int *frames_per_sm);
 
 /* ---- device-resident batch: every pointer is DEVICE memory, work is enqueued on `stream`
  * (a cudaStream_t passed as void*, NULL = default stream) and NOT synchronised.

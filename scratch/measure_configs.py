@@ -1,0 +1,29 @@
+"""Throughput of the non-headline BASELINE configs (reported in DESIGN.md; bench.py measures cfg 3)."""
+import json, sys, time
+import numpy as np
+sys.path.insert(0, '.')
+import g_tessla_b200 as g
+from g_tessla_b200 import synth
+from oracle import RefOracle
+ref = RefOracle()
+out = {}
+for cfg, nfr in ((1, 20000), (2, 20000), (5, 5000)):
+    base = synth.config(cfg, nframes=2000)
+    reps = nfr // 2000
+    xyz = np.tile(base['xyz'], (reps, 1, 1)); box = np.tile(base['box'], (reps, 1))
+    g.tessellate(xyz[:2000], box[:2000], 0.8, base['flags'])
+    t0 = time.perf_counter(); r = g.tessellate(xyz, box, 0.8, base['flags']); t1 = time.perf_counter()
+    assert (r['status'] == 0).all()
+    w = ref.tessellate(base['xyz'][:1000], base['box'][:1000], 0.8, base['flags'], nthreads=0)
+    w1 = ref.tessellate(base['xyz'][:200], base['box'][:200], 0.8, base['flags'], nthreads=1)
+    out['cfg%d' % cfg] = dict(frames=nfr, gpu_kernel_fps=nfr / (r['kernel_ms'] / 1e3), gpu_e2e_fps=nfr / (t1 - t0),
+                              cpu_all_threads_fps=1000 / w['seconds'], cpu_1thread_fps=200 / w1['seconds'], cpu_threads=ref.max_threads(),
+                              max_rel=float(np.max(np.abs(r['area'][:1000] - w['area']) / w['area'])))
+p = synth.uniform_patch(1_000_000, seed=4)
+g.triangulate_large(p[:100000])
+tri, st, ms = g.triangulate_large(p)
+t0 = time.perf_counter(); tri, st, ms = g.triangulate_large(p); t1 = time.perf_counter()
+t2 = time.perf_counter(); want, _ = ref.triangulate(p); t3 = time.perf_counter()
+out['cfg4'] = dict(points=len(p), triangles=len(tri), status=st, gpu_device_ms=ms, gpu_e2e_ms=(t1 - t0) * 1e3, cpu_1thread_ms=(t3 - t2) * 1e3,
+                   bit_exact=bool(np.array_equal(tri, want)))
+print(json.dumps(out, indent=1))
