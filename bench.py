@@ -37,6 +37,7 @@ TRI_PER_FRAME = 2178           # 2(n-1) - h with n = 1156, h = 132 (reference de
 ALG_BYTES_PER_FRAME = NATOMS * 24 + 72 + 16      # coordinates + box in, 2 reals out
 ALG_FLOP_PER_FRAME = 203.6e3                      # SURVEY.md §8d implementation-independent lower bound
 FP64_PEAK_TFLOPS_NOMINAL = 37.2                   # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz (not in MEASURED_PEAKS.json)
+NCU_DRAM_BYTES_PER_FRAME = 26254     # dram read+write per frame, ncu --set full capture of 6,000 frames (profiles/r1_tessellate_kernel_ncu.txt)
 WORKLOAD = "cfg3: 2,048-lipid bilayer leaflet, 1,024 atoms/frame, -corr -espace 0.8, 3-D area"
 
 
@@ -262,7 +263,8 @@ def run_native(args):
                     "streams": args.streams},
             "gpu_launches": args.steps + launches_e2e,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                         "traffic": None, "peak_source": pk_src, "kernel": "gt::tessellate_kernel",
+                         "traffic": NCU_DRAM_BYTES_PER_FRAME * F / 1e9, "traffic_unit": "GB per launch (ncu dram bytes per frame x frames per launch)",
+                         "peak_source": pk_src, "kernel": "gt::tessellate_kernel",
                          "kernel_ms_per_launch": kern_ms, "alg_bytes_per_frame": ALG_BYTES_PER_FRAME,
                          "note": "latency/dependency bound (sequential merge walks in shared memory); see DESIGN.md"},
             "roofline_fp64": {"achieved": fl, "peak": FP64_PEAK_TFLOPS_NOMINAL, "unit": "TFLOP/s", "frac": fl / FP64_PEAK_TFLOPS_NOMINAL,
