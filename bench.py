@@ -200,8 +200,11 @@ def run_native(args):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    gathered = [torch.empty_like(T.area) for _ in range(world)] if world > 1 else None
     for a, b in ev:
         a.record(); T.run(xyz_d, box_d, 3); b.record()
+        if world > 1:
+            dist.all_gather(gathered, T.area)          # the path's only exchange: final per-frame area gather (0.8 MB per rank)
     e1.record()
     barrier()
     total_ms = e0.elapsed_time(e1)
