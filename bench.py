@@ -139,14 +139,16 @@ def run_reference(args):
     from oracle import PortOracle, RefOracle, ref_available
     kind = "reference" if ref_available() else "port"
     orc = RefOracle() if kind == "reference" else PortOracle()
-    cores = orc.max_threads()
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: ask for every core this process may run on explicitly
+    # (delaunay_tessellate calls omp_set_num_threads(nthreads) for nthreads > 0, reference gta_tri.c:90-92)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     xyz, box = gen_frames_host(512, seed=3)
-    t = orc.tessellate(xyz, box, ESPACE, FLAGS, nthreads=0)["seconds"]           # calibration (also warms the threads)
+    t = orc.tessellate(xyz, box, ESPACE, FLAGS, nthreads=cores)["seconds"]       # calibration (also warms the threads)
     per_step = max(512, min(20000, int(512 * args.ref_seconds_per_step / max(t, 1e-6))))
     xyz, box = gen_frames_host(per_step, seed=3)
     for _ in range(args.warmup):
-        orc.tessellate(xyz[:max(64, per_step // 8)], box[:max(64, per_step // 8)], ESPACE, FLAGS, nthreads=0)
-    secs = [orc.tessellate(xyz, box, ESPACE, FLAGS, nthreads=0)["seconds"] for _ in range(args.steps)]
+        orc.tessellate(xyz[:max(64, per_step // 8)], box[:max(64, per_step // 8)], ESPACE, FLAGS, nthreads=cores)
+    secs = [orc.tessellate(xyz, box, ESPACE, FLAGS, nthreads=cores)["seconds"] for _ in range(args.steps)]
     tot = sum(secs)
     v = per_step * args.steps / tot
     sample = "%d frames per step (bounded sample of the 100k-frame workload), %d OpenMP threads" % (per_step, cores)
@@ -290,10 +292,10 @@ def cpu_baseline(xyz, box, area_gpu, args):
     from oracle import PortOracle, RefOracle, ref_available
     kind = "reference" if ref_available() else "port"
     orc = RefOracle() if kind == "reference" else PortOracle()
-    cores = orc.max_threads()
-    t = orc.tessellate(xyz[:512], box[:512], ESPACE, FLAGS, nthreads=0)["seconds"]
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    t = orc.tessellate(xyz[:512], box[:512], ESPACE, FLAGS, nthreads=cores)["seconds"]
     n = max(512, min(len(xyz), int(512 * args.cpu_seconds / max(t, 1e-6))))
-    r = orc.tessellate(xyz[:n], box[:n], ESPACE, FLAGS, nthreads=0)
+    r = orc.tessellate(xyz[:n], box[:n], ESPACE, FLAGS, nthreads=cores)
     rel = float(np.max(np.abs(r["area"] - area_gpu[:n]) / np.abs(r["area"])))
     t1 = orc.tessellate(xyz[:256], box[:256], ESPACE, FLAGS, nthreads=1)["seconds"]
     return {"value": n / r["seconds"], "unit": "frames/s", "cores": cores, "kind": kind,

@@ -148,3 +148,33 @@ def test_readers_pdb_trr(gta, checker, tmp_path):
         r = subprocess.run([exe, "-f", name, "-o", name + ".dat", "-corr"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr + r.stdout
         assert open(tmp_path / (name + ".dat")).read() == _expected_dat(want["area"], None, want["areabox"], 64), name
+
+
+def test_print_flag_writes_showme_files(gta, checker, tmp_path):
+    """GTA_PRINT: triangles<k>.node / .ele per frame in the reference's format (src/gta_tri.c:355-360, :475-498)."""
+    L = gta.lib()
+    c = synth.config(1, nframes=3)
+    F, N = c["xyz"].shape[:2]
+    frames = [np.ascontiguousarray(c["xyz"][f]) for f in range(F)]
+    xptr = (dp * F)(*[fr.ctypes.data_as(dp) for fr in frames])
+    box = np.zeros((F, 3, 3)); box[:, 0, 0] = c["box"][:, 0]; box[:, 1, 1] = c["box"][:, 1]
+    a = TriArea(None, None, None, N, F)
+    L.delaunay_tessellate.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.POINTER(TriArea), C.c_ubyte]
+    cwd = os.getcwd(); os.chdir(tmp_path)
+    try:
+        L.delaunay_tessellate(xptr, box.ctypes.data, 0.8, 1, C.byref(a), 1 | 4)
+    finally:
+        os.chdir(cwd)
+    want = checker.tessellate(c["xyz"], c["box"], 0.8, 1, want_corr=True)
+    assert np.allclose(np.ctypeslib.as_array(a.area, shape=(F,)), want["area"], rtol=1e-12, atol=0)
+    nodes = sorted(p for p in os.listdir(tmp_path) if p.endswith(".node"))
+    assert len(nodes) == F
+    k = int(nodes[0][len("triangles"):-len(".node")])
+    p = np.concatenate([c["xyz"][0, :, :2], want["corr"][0, :int(want["ncorr"][0]), :2]])
+    tri, _ = checker.triangulate(p)
+    ele = open(tmp_path / ("triangles%d.ele" % k)).read().splitlines()
+    assert ele[0] == "%d\t3\t0" % len(tri)
+    assert ele[1:] == ["%d\t%d\t%d\t%d" % (i, t[0], t[1], t[2]) for i, t in enumerate(tri)]
+    node = open(tmp_path / nodes[0]).read().splitlines()
+    assert node[0] == "%d\t2\t0\t0" % len(p) and node[1] == "0\t%f\t%f" % (p[0, 0], p[0, 1])
+    L.free_tri_area(C.byref(a))
