@@ -10,6 +10,7 @@
 #include <vector>
 #define GT_STATS 1
 #include "../../g_tessla_b200/csrc/dt_core.cuh"
+#include "../../g_tessla_b200/csrc/lpf_core.cuh"
 namespace gt { Stats g_stats; }
 
 extern "C" {
@@ -73,6 +74,49 @@ int emu_triangulate(const double* points, int n, int* tri_out) {
     int nt = 0;
     for (int i = 0; i < n; ++i)
         vertex_triangles(f, i, [&](int n1, int n2) {
+            tri_out[3 * nt] = perm[i]; tri_out[3 * nt + 1] = perm[n1]; tri_out[3 * nt + 2] = perm[n2];
+            ++nt;
+        });
+    return nt;
+}
+
+// Same input/output as emu_triangulate, through the per-lane state machine (lpf_core.cuh), one lane.
+// iters_out (nullable) receives the number of iterations the lane needed.
+int emu_triangulate_lpf(const double* points, int n, int* tri_out, long* iters_out) {
+    using namespace gt;
+    if (n < 2) return -1000;
+    std::vector<int> perm(n);
+    std::iota(perm.begin(), perm.end(), 0);
+    std::sort(perm.begin(), perm.end(), [&](int u, int v) {
+        double ux = points[2 * u], uy = points[2 * u + 1], vx = points[2 * v], vy = points[2 * v + 1];
+        return ux < vx || (ux == vx && uy < vy);
+    });
+    {
+        auto X = [&](int i) { return points[2 * perm[i]]; };
+        auto tie = [&](int a, int b) { double d = X(a) - X(b); return d < 1e-12 && d > -1e-12; };
+        for (int i = 0; i + 1 < n;) {
+            int e = i + 1; bool inexact = false;
+            while (e < n && tie(e, e - 1)) { inexact |= (X(e) != X(e - 1)); ++e; }
+            if (inexact) {
+                if (!tie(e - 1, i)) return -2000;
+                std::stable_sort(perm.begin() + i, perm.begin() + e, [&](int u, int v) { return points[2 * u + 1] < points[2 * v + 1]; });
+            }
+            i = e;
+        }
+    }
+    std::vector<LPt> pt(n);
+    for (int i = 0; i < n; ++i) { pt[i].x = points[2 * perm[i]]; pt[i].y = points[2 * perm[i] + 1]; pt[i].z = 0; pt[i].w = 0; }
+    const int cap_e = 3 * n + 64;
+    std::vector<LRec> rec(2 * cap_e); std::vector<u16> head(n, (u16)GT_NIL);
+    LFrame f; f.pt = pt.data(); f.rec = rec.data(); f.head = head.data(); f.n = n; f.cap_e = cap_e;
+    LState s; memset(&s, 0, sizeof s); lp_start(s);
+    long iters = 0;
+    while (lpf_step(f, s)) { if (++iters > 400L * n + 10000) return -3000; }
+    if (iters_out) *iters_out = iters;
+    if (s.err) return -(int)s.err;
+    int nt = 0;
+    for (int i = 0; i < n; ++i)
+        lf_vertex_triangles(f, i, [&](int n1, int n2) {
             tri_out[3 * nt] = perm[i]; tri_out[3 * nt + 1] = perm[n1]; tri_out[3 * nt + 2] = perm[n2];
             ++nt;
         });
