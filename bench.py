@@ -234,7 +234,7 @@ def run_native(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clk = clocks.stop() if rank == 0 else None
-    if not np.array_equal(area, area_dev) or status.any() or status_bad:
+    if not np.allclose(area, area_dev, rtol=1e-12, atol=0) or status.any() or status_bad:
         st_dev = T.status.cpu().numpy()
         raise SystemExit("bench.py: device-resident and host-batch results differ or a frame failed: "
                          "status(dev) %s status(host) %s, %d areas differ, first %s vs %s" % (

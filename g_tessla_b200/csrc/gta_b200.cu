@@ -17,6 +17,7 @@
 #include <thread>
 #include <vector>
 #include "gta_kernel.cuh"
+#include "gta_lpf.cuh"
 
 namespace {
 
@@ -110,6 +111,77 @@ int occupancy_for(const Shape& s) {
     return occ;
 }
 
+// ---- lane-per-frame path: workspace cache (one per device, grows on demand) and launcher
+struct LpfCache { gt::LpfWs ws{}; size_t frames = 0; int cap = 0, cap_e = 0; unsigned int* counter = nullptr; };
+LpfCache g_lpf[64];
+std::mutex g_lpf_mu;
+
+int lpf_threshold() {      // batches at least this large use the lane-per-frame path (0 = never); GTA_B200_LPF overrides
+    static int v = -2;
+    if (v == -2) { const char* e = getenv("GTA_B200_LPF"); v = e ? atoi(e) : 0; }
+    return v;
+}
+
+int lpf_ensure(int dev, size_t frames, int cap, int cap_e, LpfCache** out) {
+    std::lock_guard<std::mutex> lk(g_lpf_mu);
+    LpfCache& c = g_lpf[dev];
+    if (c.frames < frames || c.cap < cap || c.cap_e < cap_e) {
+        cudaFree(c.ws.pt); cudaFree(c.ws.z); cudaFree(c.ws.rec); cudaFree(c.ws.head); cudaFree(c.ws.perm);
+        cudaFree(c.ws.n); cudaFree(c.ws.st); cudaFree(c.ws.err); cudaFree(c.counter);
+        c = LpfCache();
+        frames = std::max(frames, c.frames); cap = std::max(cap, c.cap); cap_e = std::max(cap_e, c.cap_e);
+        CK(cudaMalloc((void**)&c.ws.pt, sizeof(gt::Pt) * frames * cap));
+        CK(cudaMalloc((void**)&c.ws.z, sizeof(double) * frames * cap));
+        CK(cudaMalloc((void**)&c.ws.rec, sizeof(gt::LRec) * frames * 2 * (size_t)cap_e));
+        CK(cudaMalloc((void**)&c.ws.head, 2 * frames * cap));
+        CK(cudaMalloc((void**)&c.ws.perm, 2 * frames * cap));
+        CK(cudaMalloc((void**)&c.ws.n, 4 * frames)); CK(cudaMalloc((void**)&c.ws.st, 4 * frames)); CK(cudaMalloc((void**)&c.ws.err, 4 * frames));
+        CK(cudaMalloc((void**)&c.counter, 4));
+        c.ws.cap = cap; c.ws.cap_e = cap_e; c.frames = frames; c.cap = cap; c.cap_e = cap_e;
+    }
+    *out = &c;
+    return GTA_B200_OK;
+}
+
+int launch(const gt::KParams& p, const Shape& s, cudaStream_t st);
+
+int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st) {
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    LpfCache* c = nullptr;
+    int rc = lpf_ensure(dev, (size_t)p.nframes, s.cap, gt::pool_edges(s.cap), &c);
+    if (rc) return rc;
+    // 1. pre-pass (load, -corr, sort) into the workspace
+    p.ws = c->ws;
+    rc = launch(p, s, st);
+    if (rc) return rc;
+    // 2. one lane per frame
+    gt::LpfParams lp; lp.ws = c->ws; lp.nframes = p.nframes; lp.counter = c->counter;
+    CK(cudaMemsetAsync(c->counter, 0, 4, st));
+    static int minb = -1;                                    // experiments: GTA_B200_LPF_BLOCKS = resident 128-thread blocks per SM (2, 4 or 6)
+    if (minb < 0) { const char* e = getenv("GTA_B200_LPF_BLOCKS"); minb = e ? atoi(e) : 2; }
+    auto run = [&](auto kern) -> int {
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, 0));
+        if (occ < 1) return fail(GTA_B200_E_TOO_LARGE, "lpf kernel does not fit");
+        const int lanes = occ * sms * 128;
+        int blocks = occ * sms;
+        if (p.nframes < lanes) blocks = std::max(1, (p.nframes + 127) / 128);
+        kern<<<blocks, 128, 0, st>>>(lp);
+        CK(cudaGetLastError());
+        return GTA_B200_OK;
+    };
+    rc = minb >= 6 ? run(gt::lpf_kernel<4, 6>) : (minb >= 4 ? run(gt::lpf_kernel<4, 4>) : run(gt::lpf_kernel<4, 2>));
+    if (rc) return rc;
+    // 3. areas
+    gt::LpfAreaParams ap; ap.ws = c->ws; ap.nframes = p.nframes; ap.natoms = p.natoms; ap.flags = p.flags;
+    ap.area = p.area; ap.area2d = p.area2d; ap.status = p.status; ap.ntri = p.ntri; ap.tri = p.tri; ap.tri_cap = p.tri_cap;
+    gt::lpf_area_kernel<<<(p.nframes + 3) / 4, 128, 0, st>>>(ap);
+    CK(cudaGetLastError());
+    return GTA_B200_OK;
+}
+
 bool have_device() {
     int n = 0;
     return cudaGetDeviceCount(&n) == cudaSuccess && n > 0;
@@ -193,8 +265,9 @@ int gta_b200_tessellate_device(const double* d_xyz, int in_dim, const double* d_
     p.area = d_area; p.area2d = d_area2d; p.areabox = d_areabox; p.status = d_status;
     p.tri = d_tri; p.tri_cap = tri_cap; p.ntri = d_ntri;
     p.corr = d_corr; p.corr_cap = corr_cap; p.ncorr = d_ncorr;
-    p.work = d_work; p.coop_nodes = coop_nodes_for(s.threads); p.dbg = g_dbg;
+    p.work = d_work; p.coop_nodes = coop_nodes_for(s.threads); p.dbg = g_dbg; p.ws = gt::LpfWs{};
     CK(cudaMemsetAsync(d_work, 0, sizeof(unsigned int), st));
+    if (lpf_threshold() > 0 && nframes >= lpf_threshold() && s.cap < 32000) return launch_lpf(p, s, st);
     return launch(p, s, st);
 }
 
@@ -309,11 +382,11 @@ int submit(Slot& s, const Job& j, const Shape& shp, int f0, int nf, bool src_pin
     p.status = s.d_st; p.ntri = s.d_st + c; p.ncorr = s.d_st + 2 * (size_t)c;
     p.tri = j.tri ? s.d_tri : nullptr; p.tri_cap = j.tri_cap;
     p.corr = j.corr ? s.d_corr : nullptr; p.corr_cap = j.corr_cap;
-    p.work = s.d_work; p.coop_nodes = coop_nodes_for(shp.threads); p.dbg = g_dbg;
+    p.work = s.d_work; p.coop_nodes = coop_nodes_for(shp.threads); p.dbg = g_dbg; p.ws = gt::LpfWs{};
     CK(cudaMemsetAsync(s.d_work, 0, sizeof(unsigned int), s.st));
     CK(cudaMemsetAsync(s.d_st, 0, sizeof(int) * 3 * (size_t)c, s.st));
     CK(cudaEventRecord(s.k0, s.st));
-    int rc = launch(p, shp, s.st);
+    int rc = (lpf_threshold() > 0 && nf >= lpf_threshold() && shp.cap < 32000) ? launch_lpf(p, shp, s.st) : launch(p, shp, s.st);
     if (rc) return rc;
     CK(cudaEventRecord(s.k1, s.st));
     CK(cudaMemcpyAsync(s.h_out, s.d_out, sizeof(double) * 3 * (size_t)c, cudaMemcpyDeviceToHost, s.st));

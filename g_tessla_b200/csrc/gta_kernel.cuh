@@ -11,6 +11,7 @@
 #include <float.h>
 #include "dt_core.cuh"
 #include "dt_coop.cuh"
+#include "lpf_core.cuh"
 #include "../../include/gta_b200.h"
 
 namespace gt {
@@ -22,6 +23,13 @@ namespace gt {
 #else
 #define GT_TICK(slot) do { } while (0)
 #endif
+
+// Global-memory workspace of the lane-per-frame path (gta_lpf.cuh): one slot per frame of the batch.
+struct LpfWs {
+    Pt* pt; double* z; LRec* rec; u16* head; u16* perm;     // strides per frame: cap, cap, 2*cap_e, cap, cap
+    int* n; int* st; uint32_t* err;                          // per frame: point count, status bits of the pre-pass, D&C error bits
+    int cap, cap_e;
+};
 
 struct KParams {
     const double* xyz; int in_dim;            // [nframes][natoms][in_dim]
@@ -35,6 +43,7 @@ struct KParams {
     unsigned int* work;                        // global frame counter
     unsigned long long* dbg;                   // phase timers (GT_PHASE_TIMING builds), else unused
     int coop_nodes;                            // levels with at most this many nodes use warp-cooperative merges
+    LpfWs ws;                                  // ws.pt != nullptr: pre-pass only (load, -corr, sort), frames go to the workspace
 };
 
 __host__ __device__ inline int pool_edges(int cap) { return 3 * cap + 64; }
@@ -295,6 +304,25 @@ __global__ void __launch_bounds__(T, MINB) tessellate_kernel(const KParams p) {
             __syncthreads();
         }
         GT_TICK(3);
+        if (p.ws.pt) {
+            // pre-pass of the lane-per-frame path: sorted points, z, permutation and the status go to the frame's
+            // workspace slot; the triangulation and the area sum are separate launches (gta_lpf.cuh)
+            const size_t slot = (size_t)fr;
+            if (ctl[4] == 0) {
+                Pt* wpt = p.ws.pt + slot * p.ws.cap; double* wz = p.ws.z + slot * p.ws.cap;
+                u16* whead = p.ws.head + slot * p.ws.cap; u16* wperm = p.ws.perm + slot * p.ws.cap;
+                for (int i = tid; i < n; i += T) {
+                    const int o = perm[i];
+                    wpt[i] = pt[i]; wz[i] = o < natoms ? atom_z(o) : zcorr[o - natoms];
+                    whead[i] = (u16)GT_NIL; wperm[i] = (u16)o;
+                }
+            }
+            if (tid == 0) {
+                p.ws.n[slot] = n; p.ws.st[slot] = (int)ctl[4]; p.ws.err[slot] = 0;
+                if (p.areabox) p.areabox[fr] = bx * by;
+            }
+            continue;
+        }
         if (ctl[4] == 0) {
             // -------------------------------------------------------- K1b: bottom-up D&C
             Frame f;

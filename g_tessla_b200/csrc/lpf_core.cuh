@@ -43,7 +43,8 @@ GT_INLINE LPair lf_pair(const LFrame& f, int h) {
     if (h & 1) { p.a = r1; p.b = r0; } else { p.a = r0; p.b = r1; }
     return p;
 }
-GT_INLINE Pt lf_pt(const LFrame& f, int v) { const double2 d = *reinterpret_cast<const double2*>(f.pt + v); Pt p; p.x = d.x; p.y = d.y; return p; }
+// device workspace keeps 16-byte (x, y) points (z apart): f.pt is really a Pt* there
+GT_INLINE Pt lf_pt(const LFrame& f, int v) { const double2 d = *(reinterpret_cast<const double2*>(f.pt) + v); Pt p; p.x = d.x; p.y = d.y; return p; }
 #else
 GT_INLINE LPair lf_pair(const LFrame& f, int h) { LPair p; p.a = f.rec[h]; p.b = f.rec[h ^ 1]; return p; }
 GT_INLINE Pt lf_pt(const LFrame& f, int v) { Pt p; p.x = f.pt[v].x; p.y = f.pt[v].y; return p; }
@@ -55,7 +56,7 @@ GT_INLINE void lf_set_rec(const LFrame& f, int h, int dst, int nxt, int prv) {
 }
 
 enum LPhase : int {
-    LP_NODE = 0,      // pick the next node of the recursion tree (no loads)
+    LP_NODE = 0,      // (unused: the node cursor advances inside the transitions, lp_next_node)
     LP_LEAF0, LP_LEAF1, LP_LEAF2,
     LP_TINIT0, LP_TINIT1, LP_TAN_R, LP_TAN_L,
     LP_INS_T0, LP_INS_SCAN,
@@ -86,6 +87,8 @@ struct LState {
     int go_left, first_edge;
     // leaf scratch
     Pt qa, qb;
+    // fetch / predicate descriptor of the next iteration (lp_prepare)
+    int fa, fb, fc, bA, cB, kind, slot, rp0, rp1, rp2; Pt oX, oA, oB, oY;
 };
 
 GT_INLINE int lp_sign_ccw(Pt x, Pt a, Pt b) { return orient2d_sign(x.x, x.y, a.x, a.y, b.x, b.y); }
@@ -108,108 +111,109 @@ GT_INLINE void lp_queue_inserts(LState& s, int h0, int a, Pt pa, int b, Pt pb, i
     s.phase = LP_INS_T0;
 }
 
+// Advance the post-order cursor over the reference's recursion tree to the next node and enter its first phase.
+GT_INLINE void lp_next_node(const LFrame& f, LState& s) {
+    int d = s.d, k = s.k;
+    if (d < 0) { d = 0; k = 0; }                           // first call: descend from the root
+    else if (d == 0) { s.phase = LP_DONE; return; }
+    else if (k & 1) {                                      // finished a right child: its parent is next, and it is a merge
+        d -= 1; k >>= 1;
+        int ia, ib; tree_node(f.n, d, k, &ia, &ib);
+        s.d = d; s.k = k; s.ia = ia; s.ib = ib;
+        s.phase = LP_TINIT0; s.up = 0; s.tx = (ia + ib) / 2; s.ty = s.tx + 1;
+        return;
+    } else k += 1;                                         // finished a left child: leftmost leaf of the sibling subtree
+    int ia, ib;
+    for (;;) {
+        tree_node(f.n, d, k, &ia, &ib);
+        if (ib - ia < 3) break;
+        d += 1; k <<= 1;
+    }
+    s.d = d; s.k = k; s.ia = ia; s.ib = ib;
+    s.phase = (ib - ia < 1) ? LP_DONE : LP_LEAF0;
+}
+
+// Fill the fetch / predicate descriptor of the phase the lane is now in. Called at the end of a transition, so
+// that the top of the next iteration is one straight-line sequence for every lane whatever its phase
+// (written as per-phase branches up there, the compiler specialises the loads per phase and the warp ends up
+// executing 13 copies of the load-predicate sequence one after another: measured 37k cycles per iteration).
+GT_INLINE void lp_prepare(LState& s) {
+    int fa = -1, fb = -1, fc = -1, bA = 0, cB = 0, kind = 0, slot = 0;
+    Pt oX, oA, oB, oY; oX.x = oX.y = 0.0; oA = oB = oY = oX;
+    int r0 = -2, r1 = -2, r2 = -2;                        // never equal to a vertex or to the 'no point' marker -1
+    const int freeh = (s.free_head != (int)GT_NIL) ? 2 * s.free_head : -1;
+    switch (s.phase) {
+    case LP_LEAF0: fc = s.ia; break;
+    case LP_LEAF1: fc = s.ia + 1; break;
+    case LP_LEAF2: fc = s.ib; fb = freeh; if (s.ib - s.ia == 2) { kind = 3; oX = s.qa; oA = s.qb; slot = 2; } break;
+    case LP_TINIT0: fa = s.tx; bA = 1; fc = s.tx; break;
+    case LP_TINIT1: fa = s.ty; bA = 1; fc = s.ty; break;
+    case LP_TAN_R: case LP_TAN_L:
+        fb = (s.phase == LP_TAN_R) ? s.hr : s.hl; cB = 1; kind = 1; slot = 0;
+        oA = s.up ? s.ptx : s.pty; oB = s.up ? s.pty : s.ptx; break;
+    case LP_INS_T0: fa = s.iP; bA = 1; cB = 1; kind = 1; slot = 1; oX = s.pIN; oB = s.pP; break;
+    case LP_INS_SCAN: fb = s.iCur; cB = 1; kind = 1; slot = 1; oX = s.pIN; oB = s.pP; break;
+    case LP_VR: fb = s.hr1; cB = 1; kind = 1; slot = 0; oA = s.pli; oB = s.pri; break;
+    case LP_VL: fb = s.hl1; cB = 1; kind = 1; slot = 0; oA = s.pli; oB = s.pri; break;
+    case LP_CR: fa = s.r1; fb = s.hr2; cB = 1; kind = 2; slot = 3; oX = s.pr1; oA = s.pli; oB = s.pri; r0 = s.li; r1 = s.ri; r2 = s.r1; break;
+    case LP_CL: fa = s.l1; fb = s.hl2; cB = 1; kind = 2; slot = 3; oX = s.pli; oA = s.pri; oB = s.pl1; r0 = s.li; r1 = s.ri; r2 = s.l1; break;
+    case LP_F: fb = freeh; if (s.vR && s.vL) { kind = 2; slot = 4; oX = s.pli; oA = s.pri; oB = s.pr1; oY = s.pl1; } break;
+    default: break;
+    }
+    s.fa = fa; s.fb = fb; s.fc = fc; s.bA = bA; s.cB = cB; s.kind = kind; s.slot = slot;
+    s.oX = oX; s.oA = oA; s.oB = oB; s.oY = oY; s.rp0 = r0; s.rp1 = r1; s.rp2 = r2;
+}
+
+GT_INLINE void lp_begin(const LFrame& f, LState& s) { lp_start(s); lp_next_node(f, s); lp_prepare(s); }
+
 // One iteration of one lane. Returns false when the lane's tree is finished.
 GT_INLINE bool lpf_step(const LFrame& f, LState& s) {
-    const int ph = s.phase;
-    if (ph == LP_DONE) return false;
+    if (s.phase == LP_DONE) return false;
 
-    // ------------------------------------------------------------------ node cursor (post-order over the reference's tree)
-    if (ph == LP_NODE) {
-        int d = s.d, k = s.k;
-        if (d < 0) { d = 0; k = 0; }                       // first call: descend from the root
-        else if (d == 0) { s.phase = LP_DONE; return false; }
-        else if (k & 1) {                                  // finished a right child: its parent is next, and it is a merge
-            d -= 1; k >>= 1;
-            int ia, ib; tree_node(f.n, d, k, &ia, &ib);
-            s.d = d; s.k = k; s.ia = ia; s.ib = ib;
-            s.phase = LP_TINIT0; s.up = 0; s.tx = (ia + ib) / 2; s.ty = s.tx + 1;
-            return true;
-        } else k += 1;                                     // finished a left child: go to the leftmost leaf of the sibling
-        int ia, ib;
-        for (;;) {
-            tree_node(f.n, d, k, &ia, &ib);
-            if (ib - ia < 3) break;
-            d += 1; k <<= 1;
-        }
-        s.d = d; s.k = k; s.ia = ia; s.ib = ib;
-        if (ib - ia < 1) { s.phase = LP_NODE; return true; }           // single point (n == 1 never reaches here)
-        s.phase = LP_LEAF0;
-        return true;
-    }
-
-    // ------------------------------------------------------------------ addresses and loads (uniform across phases)
-    int va = -1;                                           // A: head[va]
-    if (ph == LP_TINIT0) va = s.tx; else if (ph == LP_TINIT1) va = s.ty;
-    else if (ph == LP_INS_T0) va = s.iP;
-    else if (ph == LP_CR) va = s.r1; else if (ph == LP_CL) va = s.l1;
+    // ------------------------------------------------------------------ uniform part: three dependent loads, one predicate
     int hdA = 0;
-    if (va >= 0) hdA = f.head[va];
-
-    int hb = -1;                                           // B: the edge of half-edge hb
-    if (ph == LP_TINIT0 || ph == LP_TINIT1 || ph == LP_INS_T0) hb = hdA;
-    else if (ph == LP_TAN_R) hb = s.hr; else if (ph == LP_TAN_L) hb = s.hl;
-    else if (ph == LP_INS_SCAN) hb = s.iCur;
-    else if (ph == LP_VR) hb = s.hr1; else if (ph == LP_CR) hb = s.hr2;
-    else if (ph == LP_VL) hb = s.hl1; else if (ph == LP_CL) hb = s.hl2;
-    else if (ph == LP_F && s.free_head != (int)GT_NIL) hb = 2 * s.free_head;
-    else if (ph == LP_LEAF2 && s.free_head != (int)GT_NIL) hb = 2 * s.free_head;
-    LPair pr; pr.a.dst = pr.a.nxt = pr.a.prv = 0; pr.b = pr.a;
+    if (s.fa >= 0) hdA = f.head[s.fa];
+    const int hb = s.bA ? hdA : s.fb;
+    LPair pr; pr.a.dst = pr.a.nxt = pr.a.prv = pr.a.pad = 0; pr.b = pr.a;
     if (hb >= 0) pr = lf_pair(f, hb);
-
-    int vc = -1;                                           // C: pt[vc]
-    if (ph == LP_LEAF0) vc = s.ia; else if (ph == LP_LEAF1) vc = s.ia + 1; else if (ph == LP_LEAF2) vc = s.ib;
-    else if (ph == LP_TINIT0) vc = s.tx; else if (ph == LP_TINIT1) vc = s.ty;
-    else if (ph == LP_TAN_R || ph == LP_TAN_L || ph == LP_INS_T0 || ph == LP_INS_SCAN || ph == LP_VR || ph == LP_CR || ph == LP_VL || ph == LP_CL) vc = pr.a.dst;
+    const int vc = s.cB ? (int)pr.a.dst : s.fc;
     Pt pc; pc.x = pc.y = 0.0;
     if (vc >= 0) pc = lf_pt(f, vc);
-
-    // ------------------------------------------------------------------ the iteration's predicate
-    // kind 1: ccw(X, A, B) > 0     kind 2: incircle(X, A, B, Y) > 0
-    int kind = 0; Pt X = pc, A = pc, B = pc, Y = pc; bool rep = false;
-    if (ph == LP_LEAF2 && s.ib - s.ia == 2) { kind = 3; X = s.qa; A = s.qb; B = pc; }                // orient2d sign of (a, b, c)
-    else if (ph == LP_TAN_R || ph == LP_TAN_L) { kind = 1; X = pc; A = s.up ? s.ptx : s.pty; B = s.up ? s.pty : s.ptx; }
-    else if (ph == LP_INS_T0 || ph == LP_INS_SCAN) { kind = 1; X = s.pIN; A = pc; B = s.pP; }        // rightOf(in, parent, q) = ccw(in, q, parent)
-    else if (ph == LP_VR || ph == LP_VL) { kind = 1; X = pc; A = s.pli; B = s.pri; }                 // leftOf(r1, li, ri) / rightOf(l1, ri, li)
-    else if (ph == LP_CR) { kind = 2; X = s.pr1; A = s.pli; B = s.pri; Y = pc; rep = (vc == s.li) | (vc == s.ri) | (vc == s.r1); }
-    else if (ph == LP_CL) { kind = 2; X = s.pli; A = s.pri; B = s.pl1; Y = pc; rep = (vc == s.li) | (vc == s.ri) | (vc == s.l1); }
-    else if (ph == LP_F && s.vR && s.vL) { kind = 2; X = s.pli; A = s.pri; B = s.pr1; Y = s.pl1; rep = (s.r1 == s.l1); }
+    // kind 1 / 3: orient2d(X, A, B)    kind 2: incircle(X, A, B, Y); the loaded point takes operand `slot`
+    const Pt X = s.slot == 0 ? pc : s.oX, A = s.slot == 1 ? pc : s.oA, B = s.slot == 2 ? pc : s.oB, Y = s.slot == 3 ? pc : s.oY;
+    const bool rep = (vc == s.rp0) | (vc == s.rp1) | (vc == s.rp2);     // incircle with a repeated point is exactly 0
     int sg = 0;
-    if (kind == 1 || kind == 3) {
-        sg = orient2d_sign(X.x, X.y, A.x, A.y, B.x, B.y);
-    } else if (kind == 2 && !rep) {
-        sg = incircle_sign(X.x, X.y, A.x, A.y, B.x, B.y, Y.x, Y.y);
-    }
+    if (s.kind == 2) { if (!rep) sg = incircle_sign(X.x, X.y, A.x, A.y, B.x, B.y, Y.x, Y.y); }
+    else if (s.kind != 0) sg = orient2d_sign(X.x, X.y, A.x, A.y, B.x, B.y);
     if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
     const bool res = sg > 0;
 
-    // ------------------------------------------------------------------ transitions
-    switch (ph) {
+    // ------------------------------------------------------------------ transitions (short, stores only)
+    switch (s.phase) {
     case LP_LEAF0: s.qa = pc; s.phase = LP_LEAF1; break;
     case LP_LEAF1: s.qb = pc; s.phase = LP_LEAF2; break;
     case LP_LEAF2: {
         // reference :516-531 for sorted points a < b (< c); every orientation it asks is the sign of (a, b, c)
         const int a = s.ia, b = s.ia + 1, c = s.ib;
-        LPair fr = pr;
-        int e0 = lp_alloc(f, s, fr);
-        if (e0 < 0) { s.phase = LP_DONE; return false; }
+        const int e0 = lp_alloc(f, s, pr);
+        if (e0 < 0) { s.phase = LP_DONE; break; }
         const int h0 = 2 * e0;
         if (c == b) {                                     // two points: one edge, two single-entry rings
             lf_set_rec(f, h0, b, h0, h0); lf_set_rec(f, h0 ^ 1, a, h0 ^ 1, h0 ^ 1);
             f.head[a] = (u16)h0; f.head[b] = (u16)(h0 ^ 1);
-            s.phase = LP_NODE; break;
+            lp_next_node(f, s); break;
         }
-        // the free list may hold more edges, but their links are not loaded: take the other two from the bump pool
-        // or from the list by reading the records directly (host/device generic path, leaves only)
-        int e1, e2 = -1;
-        { LPair g2; if (s.free_head != (int)GT_NIL) g2 = lf_pair(f, 2 * s.free_head); else g2 = fr; e1 = lp_alloc(f, s, g2); }
-        if (e1 < 0) { s.phase = LP_DONE; return false; }
+        // further edges: the free list's links are read directly here (leaves only)
+        LPair g2 = pr; if (s.free_head != (int)GT_NIL) g2 = lf_pair(f, 2 * s.free_head);
+        const int e1 = lp_alloc(f, s, g2);
+        if (e1 < 0) { s.phase = LP_DONE; break; }
         const int h1 = 2 * e1;
         const bool s1 = sg > 0, s2 = sg < 0;              // ccw(a,b,c), ccw(a,c,b)
         int h2 = -1;
         if (s1 || s2) {
-            LPair g3; if (s.free_head != (int)GT_NIL) g3 = lf_pair(f, 2 * s.free_head); else g3 = fr;
-            e2 = lp_alloc(f, s, g3);
-            if (e2 < 0) { s.phase = LP_DONE; return false; }
+            LPair g3 = pr; if (s.free_head != (int)GT_NIL) g3 = lf_pair(f, 2 * s.free_head);
+            const int e2 = lp_alloc(f, s, g3);
+            if (e2 < 0) { s.phase = LP_DONE; break; }
             h2 = 2 * e2;
         }
         // ring of b: {b->a, b->c}; "first" moves to b->c iff c is right of the ray b->a (= ccw(a,b,c))
@@ -226,17 +230,16 @@ GT_INLINE bool lpf_step(const LFrame& f, LState& s) {
             lf_set_rec(f, h1 ^ 1, b, h2 ^ 1, h2 ^ 1); lf_set_rec(f, h2 ^ 1, a, h1 ^ 1, h1 ^ 1);
             f.head[c] = (u16)(s1 ? (h2 ^ 1) : (h1 ^ 1));
         }
-        s.phase = LP_NODE; break;
+        lp_next_node(f, s); break;
     }
     // -------------------------------------------------------------- tangents (reference lct :337-370, uct :373-406)
     case LP_TINIT0: s.t_hd0 = hdA; s.t_pv0 = pr.a.prv; s.pm0 = pc; s.phase = LP_TINIT1; break;
-    case LP_TINIT1: {
+    case LP_TINIT1:
         s.t_hd1 = hdA; s.t_pv1 = pr.a.prv; s.pm1 = pc;
         s.ptx = s.pm0; s.pty = s.pm1; s.up = 0;
         s.hl = s.t_pv0;            // lower: x -> pred(x, first(x))
         s.hr = s.t_hd1;            //        y -> first(y)
         s.phase = LP_TAN_R; break;
-    }
     case LP_TAN_R:
         if (res) { s.hr = s.up ? pr.b.prv : pr.b.nxt; s.ty = vc; s.pty = pc; }      // pred(rfast, y) / succ(rfast, y)
         else s.phase = LP_TAN_L;
@@ -257,51 +260,36 @@ GT_INLINE bool lpf_step(const LFrame& f, LState& s) {
         }
         break;
     // -------------------------------------------------------------- ring insertion (reference insertNode :210-245)
-    case LP_INS_T0: {
-        const int hd = hdA, last = pr.a.prv;
-        int at = -1, nx = -1; bool newhead = false;
-        if (!res) { if (s.iGap) { at = last; nx = hd; } else { at = s.iAt; nx = s.iNx; } }
-        else if (last == hd) { at = hd; nx = hd; newhead = true; }                 // single-entry ring: right of all
-        else { s.iCur = last; s.iHd = hd; s.iLast = last; s.phase = LP_INS_SCAN; break; }
-        lf_set_nxt(f, at, s.iH); lf_set_prv(f, nx, s.iH); lf_set_rec(f, s.iH, s.iIN, nx, at);
-        if (newhead) f.head[s.iP] = (u16)s.iH;
-        {
-            const int newhd = newhead ? s.iH : hd;
-            if (s.iWhich == 0) {
-                s.at0 = at; s.nx0 = nx;
-                s.headL = newhd;                           // endpoint 0 is always the (new) left vertex li
-                s.iP = s.i1P; s.pP = s.p1P; s.iIN = s.i1IN; s.pIN = s.p1IN; s.iH = s.i1H; s.iAt = s.i1At; s.iNx = s.i1Nx; s.iGap = s.i1Gap; s.iWhich = 1;
-                s.phase = LP_INS_T0;
-            } else {
-                s.headR = newhd;
-                s.e = s.iH ^ 1;                            // li -> ri
-                s.hl1 = s.nx0;                             // succ(li, ri)
-                s.hr1 = at;                                // pred(ri, li)
-                s.phase = (s.li == s.ux && s.ri == s.uy) ? LP_NODE : LP_VR;
-            }
+    case LP_INS_T0: case LP_INS_SCAN: {
+        int at = -1, nx = -1; bool newhead = false, placed = true;
+        int hd;
+        if (s.phase == LP_INS_T0) {
+            hd = hdA; const int last = pr.a.prv;
+            if (!res) { if (s.iGap) { at = last; nx = hd; } else { at = s.iAt; nx = s.iNx; } }
+            else if (last == hd) { at = hd; nx = hd; newhead = true; }             // single-entry ring: right of all
+            else { s.iCur = last; s.iHd = hd; s.iLast = last; s.phase = LP_INS_SCAN; placed = false; }
+        } else {
+            hd = s.iHd;
+            if (res) {
+                const int cur = pr.a.prv;
+                if (cur == hd) { at = s.iLast; nx = hd; newhead = true; }
+                else { s.iCur = cur; placed = false; }
+            } else { at = s.iCur; nx = pr.a.nxt; }
         }
-        break;
-    }
-    case LP_INS_SCAN: {
-        int at = -1, nx = -1; bool newhead = false;
-        if (res) {
-            const int cur = pr.a.prv;
-            if (cur == s.iHd) { at = s.iLast; nx = s.iHd; newhead = true; }
-            else { s.iCur = cur; break; }
-        } else { at = s.iCur; nx = pr.a.nxt; }
+        if (!placed) break;
         lf_set_nxt(f, at, s.iH); lf_set_prv(f, nx, s.iH); lf_set_rec(f, s.iH, s.iIN, nx, at);
         if (newhead) f.head[s.iP] = (u16)s.iH;
-        {
-            const int newhd = newhead ? s.iH : s.iHd;
-            if (s.iWhich == 0) {
-                s.at0 = at; s.nx0 = nx; s.headL = newhd;
-                s.iP = s.i1P; s.pP = s.p1P; s.iIN = s.i1IN; s.pIN = s.p1IN; s.iH = s.i1H; s.iAt = s.i1At; s.iNx = s.i1Nx; s.iGap = s.i1Gap; s.iWhich = 1;
-                s.phase = LP_INS_T0;
-            } else {
-                s.headR = newhd;
-                s.e = s.iH ^ 1; s.hl1 = s.nx0; s.hr1 = at;
-                s.phase = (s.li == s.ux && s.ri == s.uy) ? LP_NODE : LP_VR;
-            }
+        const int newhd = newhead ? s.iH : hd;
+        if (s.iWhich == 0) {
+            s.at0 = at; s.nx0 = nx; s.headL = newhd;       // endpoint 0 is always the (new) left vertex li
+            s.iP = s.i1P; s.pP = s.p1P; s.iIN = s.i1IN; s.pIN = s.p1IN; s.iH = s.i1H; s.iAt = s.i1At; s.iNx = s.i1Nx; s.iGap = s.i1Gap; s.iWhich = 1;
+            s.phase = LP_INS_T0;
+        } else {
+            s.headR = newhd;
+            s.e = s.iH ^ 1;                                // li -> ri
+            s.hl1 = s.nx0;                                 // succ(li, ri)
+            s.hr1 = at;                                    // pred(ri, li)
+            if (s.li == s.ux && s.ri == s.uy) lp_next_node(f, s); else s.phase = LP_VR;
         }
         break;
     }
@@ -339,7 +327,7 @@ GT_INLINE bool lpf_step(const LFrame& f, LState& s) {
         break;
     case LP_F: {
         const int ne = lp_alloc(f, s, pr);
-        if (ne < 0) { s.phase = LP_DONE; return false; }
+        if (ne < 0) { s.phase = LP_DONE; break; }
         const int h0 = 2 * ne;
         if (s.first_edge) {
             s.first_edge = 0;
@@ -362,6 +350,8 @@ GT_INLINE bool lpf_step(const LFrame& f, LState& s) {
     }
     default: break;
     }
+    if (s.phase == LP_DONE) return false;
+    lp_prepare(s);
     return true;
 }
 

@@ -109,7 +109,7 @@ int emu_triangulate_lpf(const double* points, int n, int* tri_out, long* iters_o
     const int cap_e = 3 * n + 64;
     std::vector<LRec> rec(2 * cap_e); std::vector<u16> head(n, (u16)GT_NIL);
     LFrame f; f.pt = pt.data(); f.rec = rec.data(); f.head = head.data(); f.n = n; f.cap_e = cap_e;
-    LState s; memset(&s, 0, sizeof s); lp_start(s);
+    LState s; memset(&s, 0, sizeof s); lp_begin(f, s);
     long iters = 0;
     while (lpf_step(f, s)) { if (++iters > 400L * n + 10000) return -3000; }
     if (iters_out) *iters_out = iters;
