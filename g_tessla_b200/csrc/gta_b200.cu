@@ -159,21 +159,24 @@ int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st) {
     // 2. one lane per frame
     gt::LpfParams lp; lp.ws = c->ws; lp.nframes = p.nframes; lp.counter = c->counter;
     CK(cudaMemsetAsync(c->counter, 0, 4, st));
-    static int minb = -1;                                    // experiments: GTA_B200_LPF_BLOCKS = resident 128-thread blocks per SM (2, 4 or 6)
-    if (minb < 0) { const char* e = getenv("GTA_B200_LPF_BLOCKS"); minb = e ? atoi(e) : 2; }
-    auto run = [&](auto kern) -> int {
-        int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, 0));
-        if (occ < 1) return fail(GTA_B200_E_TOO_LARGE, "lpf kernel does not fit");
-        const int lanes = occ * sms * 128;
-        int blocks = occ * sms;
-        if (p.nframes < lanes) blocks = std::max(1, (p.nframes + 127) / 128);
-        kern<<<blocks, 128, 0, st>>>(lp);
-        CK(cudaGetLastError());
-        return GTA_B200_OK;
-    };
-    rc = minb >= 6 ? run(gt::lpf_kernel<4, 6>) : (minb >= 4 ? run(gt::lpf_kernel<4, 4>) : run(gt::lpf_kernel<4, 2>));
-    if (rc) return rc;
+    static int slots = -1, wthreads = -1;                    // frames in flight per block / threads per block (experiments: GTA_B200_LPF_SLOTS, _THREADS)
+    if (slots < 0) { const char* e = getenv("GTA_B200_LPF_SLOTS"); slots = e ? atoi(e) : 1024; }
+    if (wthreads < 0) { const char* e = getenv("GTA_B200_LPF_THREADS"); wthreads = e ? atoi(e) : 512; }
+    {
+        // spread the batch over every SM: fewer slots per block shorten the round when the batch is small
+        const int blocks = std::max(1, std::min(sms, (p.nframes + 63) / 64));
+        int S = (p.nframes + blocks - 1) / blocks;
+        S = std::max(64, std::min((S + 31) & ~31, std::min(slots, 1152)));
+        const size_t smem = (size_t)gt::LS_WORDS * S * 4 + (size_t)S * 4 + (size_t)S * 2 + ((size_t)gt::LP_DONE * S + 1) * 2 + (32 + 3) * 4 + 64;
+        auto go = [&](auto kern, int threads) -> int {
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<blocks, threads, smem, st>>>(lp, S);
+            CK(cudaGetLastError());
+            return GTA_B200_OK;
+        };
+        rc = wthreads >= 1024 ? go(gt::lpf_wave_kernel<1024>, 1024) : (wthreads >= 768 ? go(gt::lpf_wave_kernel<768>, 768) : (wthreads >= 512 ? go(gt::lpf_wave_kernel<512>, 512) : go(gt::lpf_wave_kernel<256>, 256)));
+        if (rc) return rc;
+    }
     // 3. areas
     gt::LpfAreaParams ap; ap.ws = c->ws; ap.nframes = p.nframes; ap.natoms = p.natoms; ap.flags = p.flags;
     ap.area = p.area; ap.area2d = p.area2d; ap.status = p.status; ap.ntri = p.ntri; ap.tri = p.tri; ap.tri_cap = p.tri_cap;

@@ -20,9 +20,7 @@ struct LpfParams {
 __device__ __forceinline__ LFrame lpf_frame(const LpfWs& ws, int fr) {
     LFrame f;
     const size_t s = (size_t)fr;
-    // LFrame.pt is declared with 32-byte points for the host emulation; on the device the workspace keeps
-    // 16-byte (x, y) points and z apart, and lf_pt is overloaded below through the PT16 flag
-    f.pt = reinterpret_cast<LPt*>(ws.pt + s * ws.cap);
+    f.pt = ws.pt + s * ws.cap;
     f.rec = ws.rec + s * 2 * (size_t)ws.cap_e;
     f.head = ws.head + s * ws.cap;
     f.n = ws.n[s];
@@ -30,35 +28,112 @@ __device__ __forceinline__ LFrame lpf_frame(const LpfWs& ws, int fr) {
     return f;
 }
 
-template <int WARPS, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB) lpf_kernel(const LpfParams p) {
+// One iteration of phase PH for one slot, out of line so that every phase gets a register allocation of its own
+// (inlined into one kernel, the 14 instances share a 128-register budget and spill ~1 KB per thread). The state
+// is unpacked straight from shared memory -- loads of words the phase never reads are dead code -- and only the
+// words the phase may modify (LsDirty<PH>) are written back. Returns the packed phase word's new phase.
+template <int PH>
+__device__ __noinline__ int lpf_wave_phase(uint32_t* st, int SLOTS, int sl, Pt* pt, LRec* rec, u16* head, int n, int cap_e, uint32_t* err_out) {
+    LFrame f; f.pt = pt; f.rec = rec; f.head = head; f.n = n; f.cap_e = cap_e;
     LState s;
-    LFrame f;
-    int fr = -1;
-    bool have = false, out_of_work = false;
-    s.phase = LP_DONE; s.err = 0;
-    for (;;) {
-        if (!have && !out_of_work) {
-            // fetch the next frame that passed the pre-pass
-            for (;;) {
-                fr = (int)atomicAdd(p.counter, 1u);
-                if (fr >= p.nframes) { out_of_work = true; break; }
-                if (p.ws.st[fr] != 0) continue;
-                f = lpf_frame(p.ws, fr);
-                if (f.n < 2) continue;
-                lp_begin(f, s);
-                have = s.phase != LP_DONE;
-                if (!have) continue;
-                break;
+    ls_unpack(s, [&](int w) { return st[w * SLOTS + sl]; });
+    lpf_step_t<PH>(f, s);
+    ls_pack_mask<LsDirty<PH>::mask>(s, [&](int w, uint32_t v) { st[w * SLOTS + sl] = v; });
+    if (s.phase == LP_DONE) *err_out = s.err;
+    return s.phase;
+}
+
+// Phase-sorted ("wavefront") scheduler. A block keeps SLOTS frames in flight; their packed states live in
+// shared memory (word-major: st[w * SLOTS + slot]). Every round the live slots are binned by phase (one pass,
+// one barrier) and the warps take tickets for chunks of up to 32 slots that are in the SAME phase and run that
+// phase's straight-line step for them: no divergence between lanes, 32 independent dependent-load chains in
+// flight per warp. A slot whose frame is finished takes the next frame of the batch from a global counter.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p, const int SLOTS) {
+    extern __shared__ __align__(16) unsigned char lsm[];
+    uint32_t* st = reinterpret_cast<uint32_t*>(lsm);                       // [LS_WORDS][SLOTS]
+    int* slot_fr = reinterpret_cast<int*>(st + (size_t)LS_WORDS * SLOTS);  // [SLOTS] frame of the slot
+    u16* slot_n = reinterpret_cast<u16*>(slot_fr + SLOTS);                 // [SLOTS] its point count
+    u16* bins = slot_n + SLOTS;                                            // [LP_DONE][SLOTS] slots of each phase
+    int* cnt = reinterpret_cast<int*>(bins + (size_t)LP_DONE * SLOTS + ((LP_DONE * SLOTS) & 1));   // [2][16] slots per phase (double buffered)
+    int* ctl = cnt + 32;                                                   // [0] batch exhausted, [1], [2] chunk tickets (double buffered)
+    const int tid = threadIdx.x, lane = tid & 31;
+
+    for (int sl = tid; sl < SLOTS; sl += THREADS) { slot_fr[sl] = -1; st[sl] = LP_DONE; }
+    if (tid < 32) cnt[tid] = 0;
+    if (tid < 3) ctl[tid] = 0;
+    __syncthreads();
+
+    for (int round = 0;; ++round) {
+        int* c_now = cnt + 16 * (round & 1);
+        // ---- refill finished / empty slots; bin every live slot by phase
+        const bool exhausted = ctl[0] != 0;
+        for (int sl = tid; sl < SLOTS; sl += THREADS) {
+            int ph = (int)(st[sl] & 15u);
+            if (ph == LP_DONE && !exhausted) {
+                for (;;) {
+                    const int fr = (int)atomicAdd(p.counter, 1u);
+                    if (fr >= p.nframes) { ctl[0] = 1; break; }
+                    if (p.ws.st[fr] != 0) continue;
+                    LFrame f = lpf_frame(p.ws, fr);
+                    if (f.n < 2) continue;
+                    LState s = {};
+                    lp_begin(f, s);
+                    if (s.phase == LP_DONE) continue;
+                    ls_pack(s, [&](int w, uint32_t v) { st[w * SLOTS + sl] = v; });
+                    slot_fr[sl] = fr; slot_n[sl] = (u16)f.n;
+                    ph = s.phase;
+                    break;
+                }
+            }
+            if (ph != LP_DONE) bins[ph * SLOTS + atomicAdd(&c_now[ph], 1)] = (u16)sl;
+        }
+        if (tid < 16) cnt[16 * ((round + 1) & 1) + tid] = 0;              // next round's counters
+        if (tid == 0) ctl[1 + ((round + 1) & 1)] = 0;                     // and its chunk tickets
+        __syncthreads();
+        // ---- chunk table, computed by every warp for itself: lane q holds phase q's count and first chunk
+        const int myc = lane < LP_DONE ? c_now[lane] : 0;
+        int incl = (myc + 31) >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const int first_chunk = incl - ((myc + 31) >> 5);
+        const int nchunks = __shfl_sync(0xffffffffu, incl, 31);
+        if (nchunks == 0) break;                                          // nothing in flight and nothing left to fetch
+        // ---- one iteration for every live slot: a warp takes the next chunk of <= 32 slots that share a phase
+        int* ticket = &ctl[1 + (round & 1)];
+        for (;;) {
+            int c = 0;
+            if (lane == 0) c = atomicAdd(ticket, 1);
+            c = __shfl_sync(0xffffffffu, c, 0);
+            if (c >= nchunks) break;
+            const int ph = __popc(__ballot_sync(0xffffffffu, lane < LP_DONE && first_chunk <= c)) - 1;    // warp-uniform
+            const int idx = (c - __shfl_sync(0xffffffffu, first_chunk, ph)) * 32 + lane;
+            const int nph = __shfl_sync(0xffffffffu, myc, ph);
+            if (idx < nph) {
+                const int sl = bins[ph * SLOTS + idx];
+                const int fr = slot_fr[sl];
+                Pt* fpt = p.ws.pt + (size_t)fr * p.ws.cap; LRec* frec = p.ws.rec + (size_t)fr * 2 * (size_t)p.ws.cap_e;
+                u16* fhead = p.ws.head + (size_t)fr * p.ws.cap; const int fn = slot_n[sl], fce = p.ws.cap_e;
+                uint32_t* eo = p.ws.err + fr;
+                switch (ph) {                                             // every lane of the chunk is in phase ph
+                case LP_LEAF0: lpf_wave_phase<LP_LEAF0>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                case LP_LEAF1: lpf_wave_phase<LP_LEAF1>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                case LP_LEAF2: lpf_wave_phase<LP_LEAF2>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                case LP_TINIT0: lpf_wave_phase<LP_TINIT0>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                case LP_TINIT1: lpf_wave_phase<LP_TINIT1>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                case LP_TAN_R: lpf_wave_phase<LP_TAN_R>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                case LP_TAN_L: lpf_wave_phase<LP_TAN_L>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                case LP_INS_T0: lpf_wave_phase<LP_INS_T0>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                case LP_INS_SCAN: lpf_wave_phase<LP_INS_SCAN>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                case LP_VR: lpf_wave_phase<LP_VR>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                case LP_CR: lpf_wave_phase<LP_CR>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                case LP_VL: lpf_wave_phase<LP_VL>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                case LP_CL: lpf_wave_phase<LP_CL>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                default: lpf_wave_phase<LP_F>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                }
             }
         }
-        if (__all_sync(0xffffffffu, out_of_work && !have)) break;
-        if (have) {
-            if (!lpf_step(f, s)) {
-                p.ws.err[fr] = s.err;
-                have = false;
-            }
-        }
+        __syncthreads();
     }
 }
 

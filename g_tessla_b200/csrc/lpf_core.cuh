@@ -1,19 +1,25 @@
-// lpf_core.cuh -- the Delaunay divide-and-conquer as a per-lane state machine ("lane per frame").
+// lpf_core.cuh -- the Delaunay divide-and-conquer as a per-frame state machine ("lane per frame").
 //
 // dt_core.cuh::merge is a nest of data-dependent loops: when the lanes of a warp walk different merges
 // they diverge and the warp runs them one after another. Here the same algorithm -- the same predicates
 // on the same operands in the same order, hence the same rings as the reference (src/delaunay_tri.c:
-// 511-601, tangents :337-406, insertNode :210-245, deleteNode :247-268) -- is unrolled into a flat
-// loop of uniform ITERATIONS. One iteration of one lane is:
-//     [address A: ring entry of a vertex] -> [address B: one edge = its two half-edge records]
-//     -> [address C: one point] -> ONE predicate (orient2d or incircle) -> a short transition.
-// Every lane of a warp executes that same sequence whatever phase of whatever merge of whatever frame it
-// is in, so 32 lanes = 32 independent frames advance in lock step, their (uncoalesced) loads in flight
-// together. The per-lane state is a couple of dozen registers; the frame lives in global memory:
-//   point   32 B  {x, y, z, -}          (sorted order)
-//   record   8 B  {dst, nxt, prv, -}    per half-edge, twins adjacent (edge = 16 B, one load)
-//   head     2 B  per vertex
-// Edge pool, free list and the cursor of the recursion tree are private to the lane: no atomics, no barriers.
+// 511-601, tangents :337-406, insertNode :210-245, deleteNode :247-268) -- is cut into ITERATIONS.
+// One iteration of one frame is
+//     [A: ring entry of a vertex] -> [B: one edge = its two half-edge records] -> [C: one point]
+//     -> ONE predicate (orient2d or incircle) -> a short transition that edits the rings and names
+//     the phase of the next iteration.
+// Each phase is a template instance lpf_step_t<PH>: straight-line code. The GPU scheduler
+// (gta_lpf.cuh) sorts the frames in flight by phase every round and lets a warp run ONE phase for 32
+// different frames, so there is no divergence between lanes and their (uncoalesced) loads are in flight
+// together. Per frame the persistent state is 36 words (ls_pack / ls_unpack); the frame itself lives in
+// global memory:
+//   point  16 B {x, y}   record 8 B {dst, nxt, prv, -} per half-edge, twins adjacent (edge = 16 B, one load)
+//   head    2 B per vertex
+// Edge pool, free list and the cursor over the recursion tree are private to the frame: no atomics.
+//
+// The two tangents are computed upper first, then lower (the reference does lower first, :542-543; both are
+// read-only walks over the untouched halves, so the order cannot matter): the lower tangent's end points are
+// then already in the registers that the first merge step needs.
 //
 // Host-compilable: tests/emu drives lpf_step() sequentially and compares with the oracle.
 #pragma once
@@ -23,11 +29,10 @@ namespace gt {
 
 struct LRec { u16 dst, nxt, prv, pad; };                 // one half-edge
 struct LPair { LRec a, b; };                             // a = the half-edge asked for, b = its twin
-struct LPt { double x, y, z, w; };
 
-// Frame storage in global memory (one lane, one frame).
+// Frame storage in global memory.
 struct LFrame {
-    LPt* pt;        // [n]
+    Pt* pt;         // [n] sorted (x, y)
     LRec* rec;      // [2 * cap_e]
     u16* head;      // [n]
     int n;
@@ -43,11 +48,10 @@ GT_INLINE LPair lf_pair(const LFrame& f, int h) {
     if (h & 1) { p.a = r1; p.b = r0; } else { p.a = r0; p.b = r1; }
     return p;
 }
-// device workspace keeps 16-byte (x, y) points (z apart): f.pt is really a Pt* there
-GT_INLINE Pt lf_pt(const LFrame& f, int v) { const double2 d = *(reinterpret_cast<const double2*>(f.pt) + v); Pt p; p.x = d.x; p.y = d.y; return p; }
+GT_INLINE Pt lf_pt(const LFrame& f, int v) { const double2 d = *reinterpret_cast<const double2*>(f.pt + v); Pt p; p.x = d.x; p.y = d.y; return p; }
 #else
 GT_INLINE LPair lf_pair(const LFrame& f, int h) { LPair p; p.a = f.rec[h]; p.b = f.rec[h ^ 1]; return p; }
-GT_INLINE Pt lf_pt(const LFrame& f, int v) { Pt p; p.x = f.pt[v].x; p.y = f.pt[v].y; return p; }
+GT_INLINE Pt lf_pt(const LFrame& f, int v) { return f.pt[v]; }
 #endif
 GT_INLINE void lf_set_nxt(const LFrame& f, int h, int v) { f.rec[h].nxt = (u16)v; }
 GT_INLINE void lf_set_prv(const LFrame& f, int h, int v) { f.rec[h].prv = (u16)v; }
@@ -56,47 +60,108 @@ GT_INLINE void lf_set_rec(const LFrame& f, int h, int dst, int nxt, int prv) {
 }
 
 enum LPhase : int {
-    LP_NODE = 0,      // (unused: the node cursor advances inside the transitions, lp_next_node)
-    LP_LEAF0, LP_LEAF1, LP_LEAF2,
+    LP_LEAF0 = 0, LP_LEAF1, LP_LEAF2,
     LP_TINIT0, LP_TINIT1, LP_TAN_R, LP_TAN_L,
     LP_INS_T0, LP_INS_SCAN,
     LP_VR, LP_CR, LP_VL, LP_CL, LP_F,
-    LP_DONE           // whole tree finished
+    LP_DONE,          // whole tree finished
+    LP_NPHASE
 };
 
-// Per-lane state. Everything a phase needs besides its three loads is kept here (registers on the device).
+// Per-frame state between iterations.
 struct LState {
     int phase;
-    int d, k, ia, ib;                 // current node
+    int d, k, ia, ib;                 // current node of the recursion tree
     uint32_t err;
     int bump, free_head;              // private edge pool
-    // tangents
-    int tx, ty, hl, hr; Pt ptx, pty; int up;
-    int t_hd0, t_pv0, t_hd1, t_pv1; Pt pm0, pm1;     // ring entries at the start vertices, saved for the upper tangent
-    int lx, ly; Pt plx, ply;
-    int ux, uy;
+    int up, first_edge, vR, vL, iGap, i1Gap, iWhich;
+    // tangents: current end points tx / ty (their coordinates are pli / pri), walk positions hl / hr
+    int tx, ty, hl, hr, ux, uy;
     // merge step
-    int li, ri, e; Pt pli, pri; int headL, headR;
-    int hr1, r1, hr2; Pt pr1; int t1_prv, t1_nxt;    // right candidate: ri->r1, its predecessor, twin's links at r1
-    int hl1, l1, hl2; Pt pl1; int u1_prv, u1_nxt;    // left candidate: li->l1, its successor, twin's links at l1
-    int vR, vL;
-    // insertion in flight
-    int iP, iIN, iH, iAt, iNx, iGap, iWhich, iCur, iHd, iLast; Pt pP, pIN;
-    int at0, nx0;                                      // where endpoint 0's half-edge went
-    int i1P, i1IN, i1H, i1At, i1Nx, i1Gap; Pt p1P, p1IN;   // endpoint 1, queued
-    int go_left, first_edge;
-    // leaf scratch
-    Pt qa, qb;
-    // fetch / predicate descriptor of the next iteration (lp_prepare)
-    int fa, fb, fc, bA, cB, kind, slot, rp0, rp1, rp2; Pt oX, oA, oB, oY;
+    int li, ri, e, headL, headR;
+    int hr1, r1, hr2, t1_prv, t1_nxt;    // right candidate ri->r1, its clockwise neighbour, the twin's links at r1
+    int hl1, l1, hl2, u1_prv, u1_nxt;    // left candidate li->l1, its counter-clockwise neighbour, the twin's links at l1
+    // ring insertion in flight (endpoint 0 = the left vertex li, endpoint 1 = the right vertex ri)
+    int iP, iIN, iH, iAt, iNx, iCur, iHd, iLast, at0, nx0;
+    int i1H, i1At, i1Nx;
+    // cached coordinates: pli / pri = li / ri (tangents: tx / ty), pr1 / pl1 = the two candidates (leaves: points a, b)
+    Pt pli, pri, pr1, pl1;
 };
 
-GT_INLINE int lp_sign_ccw(Pt x, Pt a, Pt b) { return orient2d_sign(x.x, x.y, a.x, a.y, b.x, b.y); }
-
-GT_INLINE void lp_start(LState& s) {
-    s.phase = LP_NODE; s.d = -1; s.k = 0; s.err = 0; s.bump = 0; s.free_head = GT_NIL;
+// ---------------------------------------------------------------- persistent form (36 words)
+constexpr int LS_WORDS = 36;
+GT_INLINE uint32_t ls_lo(double v) { return (uint32_t)((uint64_t)dbl_bits(v) & 0xffffffffull); }
+GT_INLINE uint32_t ls_hi(double v) { return (uint32_t)((uint64_t)dbl_bits(v) >> 32); }
+GT_INLINE double ls_dbl(uint32_t lo, uint32_t hi) {
+    const uint64_t b = ((uint64_t)hi << 32) | lo;
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)b);
+#else
+    double v; memcpy(&v, &b, 8); return v;
+#endif
+}
+#define LS_P2(a, b) ((uint32_t)((a) & 0xffff) | ((uint32_t)((b) & 0xffff) << 16))
+template <class Put>
+GT_INLINE void ls_pack(const LState& s, Put&& put) {
+    put(0, (uint32_t)s.phase | ((uint32_t)s.d << 4) | ((uint32_t)s.k << 8) | ((s.err & 15u) << 20) | ((uint32_t)s.up << 24) | ((uint32_t)s.first_edge << 25) |
+           ((uint32_t)s.vR << 26) | ((uint32_t)s.vL << 27) | ((uint32_t)s.iGap << 28) | ((uint32_t)s.i1Gap << 29) | ((uint32_t)s.iWhich << 30));
+    put(1, LS_P2(s.ia, s.ib)); put(2, LS_P2(s.bump, s.free_head));
+    put(3, LS_P2(s.tx, s.ty)); put(4, LS_P2(s.hl, s.hr)); put(5, LS_P2(s.ux, s.uy));
+    put(6, LS_P2(s.li, s.ri)); put(7, LS_P2(s.e, s.headL)); put(8, LS_P2(s.headR, s.hr1)); put(9, LS_P2(s.r1, s.hr2));
+    put(10, LS_P2(s.t1_prv, s.t1_nxt)); put(11, LS_P2(s.hl1, s.l1)); put(12, LS_P2(s.hl2, s.u1_prv)); put(13, LS_P2(s.u1_nxt, s.iP));
+    put(14, LS_P2(s.iIN, s.iH)); put(15, LS_P2(s.iAt, s.iNx)); put(16, LS_P2(s.iCur, s.iHd)); put(17, LS_P2(s.iLast, s.at0));
+    put(18, LS_P2(s.nx0, s.i1H)); put(19, LS_P2(s.i1At, s.i1Nx));
+    put(20, ls_lo(s.pli.x)); put(21, ls_hi(s.pli.x)); put(22, ls_lo(s.pli.y)); put(23, ls_hi(s.pli.y));
+    put(24, ls_lo(s.pri.x)); put(25, ls_hi(s.pri.x)); put(26, ls_lo(s.pri.y)); put(27, ls_hi(s.pri.y));
+    put(28, ls_lo(s.pr1.x)); put(29, ls_hi(s.pr1.x)); put(30, ls_lo(s.pr1.y)); put(31, ls_hi(s.pr1.y));
+    put(32, ls_lo(s.pl1.x)); put(33, ls_hi(s.pl1.x)); put(34, ls_lo(s.pl1.y)); put(35, ls_hi(s.pl1.y));
+}
+template <class Get>
+GT_INLINE void ls_unpack(LState& s, Get&& get) {
+    uint32_t w = get(0);
+    s.phase = w & 15; s.d = (w >> 4) & 15; s.k = (w >> 8) & 0xfff; s.err = (w >> 20) & 15; s.up = (w >> 24) & 1; s.first_edge = (w >> 25) & 1;
+    s.vR = (w >> 26) & 1; s.vL = (w >> 27) & 1; s.iGap = (w >> 28) & 1; s.i1Gap = (w >> 29) & 1; s.iWhich = (w >> 30) & 1;
+#define LS_U2(i, a, b) w = get(i); a = (int)(w & 0xffff); b = (int)(w >> 16)
+    LS_U2(1, s.ia, s.ib); LS_U2(2, s.bump, s.free_head);
+    LS_U2(3, s.tx, s.ty); LS_U2(4, s.hl, s.hr); LS_U2(5, s.ux, s.uy);
+    LS_U2(6, s.li, s.ri); LS_U2(7, s.e, s.headL); LS_U2(8, s.headR, s.hr1); LS_U2(9, s.r1, s.hr2);
+    LS_U2(10, s.t1_prv, s.t1_nxt); LS_U2(11, s.hl1, s.l1); LS_U2(12, s.hl2, s.u1_prv); LS_U2(13, s.u1_nxt, s.iP);
+    LS_U2(14, s.iIN, s.iH); LS_U2(15, s.iAt, s.iNx); LS_U2(16, s.iCur, s.iHd); LS_U2(17, s.iLast, s.at0);
+    LS_U2(18, s.nx0, s.i1H); LS_U2(19, s.i1At, s.i1Nx);
+#undef LS_U2
+    s.pli.x = ls_dbl(get(20), get(21)); s.pli.y = ls_dbl(get(22), get(23));
+    s.pri.x = ls_dbl(get(24), get(25)); s.pri.y = ls_dbl(get(26), get(27));
+    s.pr1.x = ls_dbl(get(28), get(29)); s.pr1.y = ls_dbl(get(30), get(31));
+    s.pl1.x = ls_dbl(get(32), get(33)); s.pl1.y = ls_dbl(get(34), get(35));
 }
 
+// Words a phase may modify (a word is rewritten from the unpacked fields, so a phase that changes one field of
+// a word keeps the other one). tests/emu applies these masks after every iteration: a missing bit shows up
+// as a triangulation mismatch.
+#define LS_W(i) (1ull << (i))
+#define LS_PT(i) (15ull << (i))
+constexpr unsigned long long LS_M_NODE = LS_W(0) | LS_W(1) | LS_W(3);
+template <int PH> struct LsDirty { static constexpr unsigned long long mask = ~0ull; };
+template <> struct LsDirty<LP_LEAF0> { static constexpr unsigned long long mask = LS_W(0) | LS_PT(28); };
+template <> struct LsDirty<LP_LEAF1> { static constexpr unsigned long long mask = LS_W(0) | LS_PT(32); };
+template <> struct LsDirty<LP_LEAF2> { static constexpr unsigned long long mask = LS_W(2) | LS_M_NODE; };
+template <> struct LsDirty<LP_TINIT0> { static constexpr unsigned long long mask = LS_W(0) | LS_W(4) | LS_PT(20); };
+template <> struct LsDirty<LP_TINIT1> { static constexpr unsigned long long mask = LS_W(0) | LS_W(4) | LS_PT(24); };
+template <> struct LsDirty<LP_TAN_R> { static constexpr unsigned long long mask = LS_W(0) | LS_W(3) | LS_W(4) | LS_PT(24); };
+template <> struct LsDirty<LP_TAN_L> { static constexpr unsigned long long mask = LS_W(0) | LS_W(3) | LS_W(4) | LS_W(5) | LS_W(6) | LS_PT(20); };
+template <> struct LsDirty<LP_INS_T0> { static constexpr unsigned long long mask = LS_M_NODE | LS_W(7) | LS_W(8) | LS_W(11) | LS_W(13) | LS_W(14) | LS_W(15) | LS_W(16) | LS_W(17) | LS_W(18); };
+template <> struct LsDirty<LP_INS_SCAN> { static constexpr unsigned long long mask = LsDirty<LP_INS_T0>::mask; };
+template <> struct LsDirty<LP_VR> { static constexpr unsigned long long mask = LS_W(0) | LS_W(9) | LS_W(10) | LS_PT(28); };
+template <> struct LsDirty<LP_CR> { static constexpr unsigned long long mask = LS_W(0) | LS_W(2) | LS_W(8) | LS_W(9) | LS_W(10) | LS_PT(28); };
+template <> struct LsDirty<LP_VL> { static constexpr unsigned long long mask = LS_W(0) | LS_W(11) | LS_W(12) | LS_W(13) | LS_PT(32); };
+template <> struct LsDirty<LP_CL> { static constexpr unsigned long long mask = LS_W(0) | LS_W(2) | LS_W(7) | LS_W(11) | LS_W(12) | LS_W(13) | LS_PT(32); };
+template <> struct LsDirty<LP_F> { static constexpr unsigned long long mask = LS_W(0) | LS_W(2) | LS_W(6) | LS_W(13) | LS_W(14) | LS_W(15) | LS_W(18) | LS_W(19) | LS_PT(20) | LS_PT(24); };
+template <unsigned long long MASK, class Put>
+GT_INLINE void ls_pack_mask(const LState& s, Put&& put) {
+    ls_pack(s, [&](int i, uint32_t v) { if ((MASK >> i) & 1ull) put(i, v); });
+}
+
+// ---------------------------------------------------------------- helpers
 GT_INLINE int lp_alloc(const LFrame& f, LState& s, const LPair& freerec) {
     if (s.free_head != (int)GT_NIL) { int e = s.free_head; s.free_head = freerec.a.nxt; return e; }
     if (s.bump >= f.cap_e) { s.err |= GT_ERR_POOL; return -1; }
@@ -104,10 +169,10 @@ GT_INLINE int lp_alloc(const LFrame& f, LState& s, const LPair& freerec) {
 }
 GT_INLINE void lp_free(const LFrame& f, LState& s, int e) { lf_set_nxt(f, 2 * e, s.free_head); s.free_head = e; }
 
-// queue the two ring insertions of a new edge h0 = a->b (endpoint 0 at a, endpoint 1 at b)
-GT_INLINE void lp_queue_inserts(LState& s, int h0, int a, Pt pa, int b, Pt pb, int at0, int nx0, int gap0, int at1, int nx1, int gap1) {
-    s.iP = a; s.pP = pa; s.iIN = b; s.pIN = pb; s.iH = h0; s.iAt = at0; s.iNx = nx0; s.iGap = gap0; s.iWhich = 0;
-    s.i1P = b; s.p1P = pb; s.i1IN = a; s.p1IN = pa; s.i1H = h0 ^ 1; s.i1At = at1; s.i1Nx = nx1; s.i1Gap = gap1;
+// queue the two ring insertions of the new edge h0 = li -> ri (endpoint 0 at li, endpoint 1 at ri)
+GT_INLINE void lp_queue_inserts(LState& s, int h0, int at0, int nx0, int gap0, int at1, int nx1, int gap1) {
+    s.iP = s.li; s.iIN = s.ri; s.iH = h0; s.iAt = at0; s.iNx = nx0; s.iGap = gap0; s.iWhich = 0;
+    s.i1H = h0 ^ 1; s.i1At = at1; s.i1Nx = nx1; s.i1Gap = gap1;
     s.phase = LP_INS_T0;
 }
 
@@ -120,7 +185,7 @@ GT_INLINE void lp_next_node(const LFrame& f, LState& s) {
         d -= 1; k >>= 1;
         int ia, ib; tree_node(f.n, d, k, &ia, &ib);
         s.d = d; s.k = k; s.ia = ia; s.ib = ib;
-        s.phase = LP_TINIT0; s.up = 0; s.tx = (ia + ib) / 2; s.ty = s.tx + 1;
+        s.phase = LP_TINIT0; s.up = 1; s.tx = (ia + ib) / 2; s.ty = s.tx + 1;
         return;
     } else k += 1;                                         // finished a left child: leftmost leaf of the sibling subtree
     int ia, ib;
@@ -133,87 +198,92 @@ GT_INLINE void lp_next_node(const LFrame& f, LState& s) {
     s.phase = (ib - ia < 1) ? LP_DONE : LP_LEAF0;
 }
 
-// Fill the fetch / predicate descriptor of the phase the lane is now in. Called at the end of a transition, so
-// that the top of the next iteration is one straight-line sequence for every lane whatever its phase
-// (written as per-phase branches up there, the compiler specialises the loads per phase and the warp ends up
-// executing 13 copies of the load-predicate sequence one after another: measured 37k cycles per iteration).
-GT_INLINE void lp_prepare(LState& s) {
-    int fa = -1, fb = -1, fc = -1, bA = 0, cB = 0, kind = 0, slot = 0;
-    Pt oX, oA, oB, oY; oX.x = oX.y = 0.0; oA = oB = oY = oX;
-    int r0 = -2, r1 = -2, r2 = -2;                        // never equal to a vertex or to the 'no point' marker -1
-    const int freeh = (s.free_head != (int)GT_NIL) ? 2 * s.free_head : -1;
-    switch (s.phase) {
-    case LP_LEAF0: fc = s.ia; break;
-    case LP_LEAF1: fc = s.ia + 1; break;
-    case LP_LEAF2: fc = s.ib; fb = freeh; if (s.ib - s.ia == 2) { kind = 3; oX = s.qa; oA = s.qb; slot = 2; } break;
-    case LP_TINIT0: fa = s.tx; bA = 1; fc = s.tx; break;
-    case LP_TINIT1: fa = s.ty; bA = 1; fc = s.ty; break;
-    case LP_TAN_R: case LP_TAN_L:
-        fb = (s.phase == LP_TAN_R) ? s.hr : s.hl; cB = 1; kind = 1; slot = 0;
-        oA = s.up ? s.ptx : s.pty; oB = s.up ? s.pty : s.ptx; break;
-    case LP_INS_T0: fa = s.iP; bA = 1; cB = 1; kind = 1; slot = 1; oX = s.pIN; oB = s.pP; break;
-    case LP_INS_SCAN: fb = s.iCur; cB = 1; kind = 1; slot = 1; oX = s.pIN; oB = s.pP; break;
-    case LP_VR: fb = s.hr1; cB = 1; kind = 1; slot = 0; oA = s.pli; oB = s.pri; break;
-    case LP_VL: fb = s.hl1; cB = 1; kind = 1; slot = 0; oA = s.pli; oB = s.pri; break;
-    case LP_CR: fa = s.r1; fb = s.hr2; cB = 1; kind = 2; slot = 3; oX = s.pr1; oA = s.pli; oB = s.pri; r0 = s.li; r1 = s.ri; r2 = s.r1; break;
-    case LP_CL: fa = s.l1; fb = s.hl2; cB = 1; kind = 2; slot = 3; oX = s.pli; oA = s.pri; oB = s.pl1; r0 = s.li; r1 = s.ri; r2 = s.l1; break;
-    case LP_F: fb = freeh; if (s.vR && s.vL) { kind = 2; slot = 4; oX = s.pli; oA = s.pri; oB = s.pr1; oY = s.pl1; } break;
-    default: break;
-    }
-    s.fa = fa; s.fb = fb; s.fc = fc; s.bA = bA; s.cB = cB; s.kind = kind; s.slot = slot;
-    s.oX = oX; s.oA = oA; s.oB = oB; s.oY = oY; s.rp0 = r0; s.rp1 = r1; s.rp2 = r2;
+GT_INLINE void lp_begin(const LFrame& f, LState& s) {
+    s.d = -1; s.k = 0; s.err = 0; s.bump = 0; s.free_head = GT_NIL; s.first_edge = 0; s.up = 0; s.vR = s.vL = 0;
+    s.iGap = s.i1Gap = s.iWhich = 0;
+    lp_next_node(f, s);
 }
 
-GT_INLINE void lp_begin(const LFrame& f, LState& s) { lp_start(s); lp_next_node(f, s); lp_prepare(s); }
-
-// One iteration of one lane. Returns false when the lane's tree is finished.
-GT_INLINE bool lpf_step(const LFrame& f, LState& s) {
-    if (s.phase == LP_DONE) return false;
-
-    // ------------------------------------------------------------------ uniform part: three dependent loads, one predicate
+// ---------------------------------------------------------------- one iteration of phase PH
+template <int PH>
+GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
+    // ---- what to fetch
+    int fa = -1, fb = -1, fc = -1; bool bA = false, cB = false;
+    const int freeh = (s.free_head != (int)GT_NIL) ? 2 * s.free_head : -1;
+    if (PH == LP_LEAF0) fc = s.ia;
+    else if (PH == LP_LEAF1) fc = s.ia + 1;
+    else if (PH == LP_LEAF2) { fc = s.ib; fb = freeh; }
+    else if (PH == LP_TINIT0) { fa = s.tx; bA = true; fc = s.tx; }
+    else if (PH == LP_TINIT1) { fa = s.ty; bA = true; fc = s.ty; }
+    else if (PH == LP_TAN_R) { fb = s.hr; cB = true; }
+    else if (PH == LP_TAN_L) { fb = s.hl; cB = true; }
+    else if (PH == LP_INS_T0) { fa = s.iP; bA = true; cB = true; }
+    else if (PH == LP_INS_SCAN) { fb = s.iCur; cB = true; }
+    else if (PH == LP_VR) { fb = s.hr1; cB = true; }
+    else if (PH == LP_VL) { fb = s.hl1; cB = true; }
+    else if (PH == LP_CR) { fa = s.r1; fb = s.hr2; cB = true; }
+    else if (PH == LP_CL) { fa = s.l1; fb = s.hl2; cB = true; }
+    else if (PH == LP_F) fb = freeh;
     int hdA = 0;
-    if (s.fa >= 0) hdA = f.head[s.fa];
-    const int hb = s.bA ? hdA : s.fb;
+    if (fa >= 0) hdA = f.head[fa];
+    const int hb = bA ? hdA : fb;
     LPair pr; pr.a.dst = pr.a.nxt = pr.a.prv = pr.a.pad = 0; pr.b = pr.a;
     if (hb >= 0) pr = lf_pair(f, hb);
-    const int vc = s.cB ? (int)pr.a.dst : s.fc;
+    const int vc = cB ? (int)pr.a.dst : fc;
     Pt pc; pc.x = pc.y = 0.0;
     if (vc >= 0) pc = lf_pt(f, vc);
-    // kind 1 / 3: orient2d(X, A, B)    kind 2: incircle(X, A, B, Y); the loaded point takes operand `slot`
-    const Pt X = s.slot == 0 ? pc : s.oX, A = s.slot == 1 ? pc : s.oA, B = s.slot == 2 ? pc : s.oB, Y = s.slot == 3 ? pc : s.oY;
-    const bool rep = (vc == s.rp0) | (vc == s.rp1) | (vc == s.rp2);     // incircle with a repeated point is exactly 0
+
+    // ---- the iteration's predicate
     int sg = 0;
-    if (s.kind == 2) { if (!rep) sg = incircle_sign(X.x, X.y, A.x, A.y, B.x, B.y, Y.x, Y.y); }
-    else if (s.kind != 0) sg = orient2d_sign(X.x, X.y, A.x, A.y, B.x, B.y);
+    if (PH == LP_LEAF2) { if (s.ib - s.ia == 2) sg = orient2d_sign(s.pr1.x, s.pr1.y, s.pl1.x, s.pl1.y, pc.x, pc.y); }
+    else if (PH == LP_TAN_R || PH == LP_TAN_L) {
+        // lower: rightOf(p, x, y) = ccw(p, y, x); upper: leftOf(p, x, y) = ccw(p, x, y)   (x = tx at pli, y = ty at pri)
+        const Pt A = s.up ? s.pli : s.pri, B = s.up ? s.pri : s.pli;
+        sg = orient2d_sign(pc.x, pc.y, A.x, A.y, B.x, B.y);
+    } else if (PH == LP_INS_T0 || PH == LP_INS_SCAN) {
+        // rightOf(in, parent, q) = ccw(in, q, parent); endpoint 0: parent li, in ri; endpoint 1: the other way round
+        const Pt pP = s.iWhich ? s.pri : s.pli, pIN = s.iWhich ? s.pli : s.pri;
+        sg = orient2d_sign(pIN.x, pIN.y, pc.x, pc.y, pP.x, pP.y);
+    } else if (PH == LP_VR || PH == LP_VL) {
+        sg = orient2d_sign(pc.x, pc.y, s.pli.x, s.pli.y, s.pri.x, s.pri.y);       // leftOf(r1, li, ri) / rightOf(l1, ri, li)
+    } else if (PH == LP_CR) {
+        if (!(vc == s.li || vc == s.ri || vc == s.r1))                              // a repeated point: exactly 0
+            sg = incircle_sign(s.pr1.x, s.pr1.y, s.pli.x, s.pli.y, s.pri.x, s.pri.y, pc.x, pc.y);
+    } else if (PH == LP_CL) {
+        if (!(vc == s.li || vc == s.ri || vc == s.l1))
+            sg = incircle_sign(s.pli.x, s.pli.y, s.pri.x, s.pri.y, s.pl1.x, s.pl1.y, pc.x, pc.y);
+    } else if (PH == LP_F) {
+        if (s.vR && s.vL && !s.first_edge && s.r1 != s.l1)
+            sg = incircle_sign(s.pli.x, s.pli.y, s.pri.x, s.pri.y, s.pr1.x, s.pr1.y, s.pl1.x, s.pl1.y);
+    }
     if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
     const bool res = sg > 0;
 
-    // ------------------------------------------------------------------ transitions (short, stores only)
-    switch (s.phase) {
-    case LP_LEAF0: s.qa = pc; s.phase = LP_LEAF1; break;
-    case LP_LEAF1: s.qb = pc; s.phase = LP_LEAF2; break;
-    case LP_LEAF2: {
+    // ---- transition
+    if (PH == LP_LEAF0) { s.pr1 = pc; s.phase = LP_LEAF1; }
+    else if (PH == LP_LEAF1) { s.pl1 = pc; s.phase = LP_LEAF2; }
+    else if (PH == LP_LEAF2) {
         // reference :516-531 for sorted points a < b (< c); every orientation it asks is the sign of (a, b, c)
         const int a = s.ia, b = s.ia + 1, c = s.ib;
         const int e0 = lp_alloc(f, s, pr);
-        if (e0 < 0) { s.phase = LP_DONE; break; }
+        if (e0 < 0) { s.phase = LP_DONE; return; }
         const int h0 = 2 * e0;
         if (c == b) {                                     // two points: one edge, two single-entry rings
             lf_set_rec(f, h0, b, h0, h0); lf_set_rec(f, h0 ^ 1, a, h0 ^ 1, h0 ^ 1);
             f.head[a] = (u16)h0; f.head[b] = (u16)(h0 ^ 1);
-            lp_next_node(f, s); break;
+            lp_next_node(f, s); return;
         }
         // further edges: the free list's links are read directly here (leaves only)
         LPair g2 = pr; if (s.free_head != (int)GT_NIL) g2 = lf_pair(f, 2 * s.free_head);
         const int e1 = lp_alloc(f, s, g2);
-        if (e1 < 0) { s.phase = LP_DONE; break; }
+        if (e1 < 0) { s.phase = LP_DONE; return; }
         const int h1 = 2 * e1;
         const bool s1 = sg > 0, s2 = sg < 0;              // ccw(a,b,c), ccw(a,c,b)
         int h2 = -1;
         if (s1 || s2) {
             LPair g3 = pr; if (s.free_head != (int)GT_NIL) g3 = lf_pair(f, 2 * s.free_head);
             const int e2 = lp_alloc(f, s, g3);
-            if (e2 < 0) { s.phase = LP_DONE; break; }
+            if (e2 < 0) { s.phase = LP_DONE; return; }
             h2 = 2 * e2;
         }
         // ring of b: {b->a, b->c}; "first" moves to b->c iff c is right of the ray b->a (= ccw(a,b,c))
@@ -230,40 +300,29 @@ GT_INLINE bool lpf_step(const LFrame& f, LState& s) {
             lf_set_rec(f, h1 ^ 1, b, h2 ^ 1, h2 ^ 1); lf_set_rec(f, h2 ^ 1, a, h1 ^ 1, h1 ^ 1);
             f.head[c] = (u16)(s1 ? (h2 ^ 1) : (h1 ^ 1));
         }
-        lp_next_node(f, s); break;
+        lp_next_node(f, s);
     }
-    // -------------------------------------------------------------- tangents (reference lct :337-370, uct :373-406)
-    case LP_TINIT0: s.t_hd0 = hdA; s.t_pv0 = pr.a.prv; s.pm0 = pc; s.phase = LP_TINIT1; break;
-    case LP_TINIT1:
-        s.t_hd1 = hdA; s.t_pv1 = pr.a.prv; s.pm1 = pc;
-        s.ptx = s.pm0; s.pty = s.pm1; s.up = 0;
-        s.hl = s.t_pv0;            // lower: x -> pred(x, first(x))
-        s.hr = s.t_hd1;            //        y -> first(y)
-        s.phase = LP_TAN_R; break;
-    case LP_TAN_R:
-        if (res) { s.hr = s.up ? pr.b.prv : pr.b.nxt; s.ty = vc; s.pty = pc; }      // pred(rfast, y) / succ(rfast, y)
+    // -------------------------------------------------------------- tangents (reference uct :373-406, lct :337-370)
+    else if (PH == LP_TINIT0) { s.hl = s.up ? hdA : (int)pr.a.prv; s.pli = pc; s.phase = LP_TINIT1; }     // upper: x -> first(x); lower: x -> pred(x, first(x))
+    else if (PH == LP_TINIT1) { s.hr = s.up ? (int)pr.a.prv : hdA; s.pri = pc; s.phase = LP_TAN_R; }      // upper: y -> pred(y, first(y)); lower: y -> first(y)
+    else if (PH == LP_TAN_R) {
+        if (res) { s.hr = s.up ? pr.b.prv : pr.b.nxt; s.ty = vc; s.pri = pc; }      // pred(rfast, y) / succ(rfast, y)
         else s.phase = LP_TAN_L;
-        break;
-    case LP_TAN_L:
-        if (res) { s.hl = s.up ? pr.b.nxt : pr.b.prv; s.tx = vc; s.ptx = pc; s.phase = LP_TAN_R; }
-        else if (!s.up) {
-            s.lx = s.tx; s.ly = s.ty; s.plx = s.ptx; s.ply = s.pty;
-            s.up = 1; s.tx = (s.ia + s.ib) / 2; s.ty = s.tx + 1; s.ptx = s.pm0; s.pty = s.pm1;
-            s.hl = s.t_hd0;        // upper: x -> first(x)
-            s.hr = s.t_pv1;        //        y -> pred(y, first(y))
-            s.phase = LP_TAN_R;
-        } else {
+    } else if (PH == LP_TAN_L) {
+        if (res) { s.hl = s.up ? pr.b.nxt : pr.b.prv; s.tx = vc; s.pli = pc; s.phase = LP_TAN_R; }
+        else if (s.up) {
             s.ux = s.tx; s.uy = s.ty;
+            s.up = 0; s.tx = (s.ia + s.ib) / 2; s.ty = s.tx + 1; s.phase = LP_TINIT0;
+        } else {
             // first cross edge = lower tangent: both ends take it in their hull gap (before "first")
-            s.li = s.lx; s.ri = s.ly; s.pli = s.plx; s.pri = s.ply; s.first_edge = 1;
-            s.phase = LP_F; s.vR = 0; s.vL = 0;           // LP_F allocates the edge and queues the inserts
+            s.li = s.tx; s.ri = s.ty; s.first_edge = 1; s.vR = 0; s.vL = 0;
+            s.phase = LP_F;                               // LP_F allocates the edge and queues the inserts
         }
-        break;
+    }
     // -------------------------------------------------------------- ring insertion (reference insertNode :210-245)
-    case LP_INS_T0: case LP_INS_SCAN: {
-        int at = -1, nx = -1; bool newhead = false, placed = true;
-        int hd;
-        if (s.phase == LP_INS_T0) {
+    else if (PH == LP_INS_T0 || PH == LP_INS_SCAN) {
+        int at = -1, nx = -1, hd; bool newhead = false, placed = true;
+        if (PH == LP_INS_T0) {
             hd = hdA; const int last = pr.a.prv;
             if (!res) { if (s.iGap) { at = last; nx = hd; } else { at = s.iAt; nx = s.iNx; } }
             else if (last == hd) { at = hd; nx = hd; newhead = true; }             // single-entry ring: right of all
@@ -276,29 +335,28 @@ GT_INLINE bool lpf_step(const LFrame& f, LState& s) {
                 else { s.iCur = cur; placed = false; }
             } else { at = s.iCur; nx = pr.a.nxt; }
         }
-        if (!placed) break;
-        lf_set_nxt(f, at, s.iH); lf_set_prv(f, nx, s.iH); lf_set_rec(f, s.iH, s.iIN, nx, at);
-        if (newhead) f.head[s.iP] = (u16)s.iH;
-        const int newhd = newhead ? s.iH : hd;
-        if (s.iWhich == 0) {
-            s.at0 = at; s.nx0 = nx; s.headL = newhd;       // endpoint 0 is always the (new) left vertex li
-            s.iP = s.i1P; s.pP = s.p1P; s.iIN = s.i1IN; s.pIN = s.p1IN; s.iH = s.i1H; s.iAt = s.i1At; s.iNx = s.i1Nx; s.iGap = s.i1Gap; s.iWhich = 1;
-            s.phase = LP_INS_T0;
-        } else {
-            s.headR = newhd;
-            s.e = s.iH ^ 1;                                // li -> ri
-            s.hl1 = s.nx0;                                 // succ(li, ri)
-            s.hr1 = at;                                    // pred(ri, li)
-            if (s.li == s.ux && s.ri == s.uy) lp_next_node(f, s); else s.phase = LP_VR;
+        if (placed) {
+            lf_set_nxt(f, at, s.iH); lf_set_prv(f, nx, s.iH); lf_set_rec(f, s.iH, s.iIN, nx, at);
+            if (newhead) f.head[s.iP] = (u16)s.iH;
+            const int newhd = newhead ? s.iH : hd;
+            if (s.iWhich == 0) {
+                s.at0 = at; s.nx0 = nx; s.headL = newhd;
+                s.iP = s.ri; s.iIN = s.li; s.iH = s.i1H; s.iAt = s.i1At; s.iNx = s.i1Nx; s.iGap = s.i1Gap; s.iWhich = 1;
+                s.phase = LP_INS_T0;
+            } else {
+                s.headR = newhd;
+                s.e = s.iH ^ 1;                            // li -> ri
+                s.hl1 = s.nx0;                             // succ(li, ri)
+                s.hr1 = at;                                // pred(ri, li)
+                if (s.li == s.ux && s.ri == s.uy) lp_next_node(f, s); else s.phase = LP_VR;
+            }
         }
-        break;
     }
     // -------------------------------------------------------------- merge step (reference :552-594)
-    case LP_VR:
+    else if (PH == LP_VR) {
         s.r1 = vc; s.pr1 = pc; s.hr2 = pr.a.prv; s.t1_prv = pr.b.prv; s.t1_nxt = pr.b.nxt;
         s.vR = res; s.phase = res ? LP_CR : LP_VL;
-        break;
-    case LP_CR:
+    } else if (PH == LP_CR) {
         if (res) {
             // cutVerts(ri, r1): ri's ring loses hr1 (its next is the cross edge), r1's ring loses the twin
             const int h = s.hr1, tw = h ^ 1;
@@ -309,12 +367,10 @@ GT_INLINE bool lpf_step(const LFrame& f, LState& s) {
             lp_free(f, s, h >> 1);
             s.hr1 = s.hr2; s.r1 = vc; s.pr1 = pc; s.hr2 = pr.a.prv; s.t1_prv = pr.b.prv; s.t1_nxt = pr.b.nxt;
         } else s.phase = LP_VL;
-        break;
-    case LP_VL:
+    } else if (PH == LP_VL) {
         s.l1 = vc; s.pl1 = pc; s.hl2 = pr.a.nxt; s.u1_prv = pr.b.prv; s.u1_nxt = pr.b.nxt;
         s.vL = res; s.phase = res ? LP_CL : LP_F;
-        break;
-    case LP_CL:
+    } else if (PH == LP_CL) {
         if (res) {
             const int h = s.hl1, tw = h ^ 1;
             lf_set_nxt(f, s.e, s.hl2); lf_set_prv(f, s.hl2, s.e);
@@ -324,35 +380,50 @@ GT_INLINE bool lpf_step(const LFrame& f, LState& s) {
             lp_free(f, s, h >> 1);
             s.hl1 = s.hl2; s.l1 = vc; s.pl1 = pc; s.hl2 = pr.a.nxt; s.u1_prv = pr.b.prv; s.u1_nxt = pr.b.nxt;
         } else s.phase = LP_F;
-        break;
-    case LP_F: {
+    } else if (PH == LP_F) {
         const int ne = lp_alloc(f, s, pr);
-        if (ne < 0) { s.phase = LP_DONE; break; }
+        if (ne < 0) { s.phase = LP_DONE; return; }
         const int h0 = 2 * ne;
         if (s.first_edge) {
             s.first_edge = 0;
-            lp_queue_inserts(s, h0, s.li, s.pli, s.ri, s.pri, 0, 0, 1, 0, 0, 1);
-            break;
+            lp_queue_inserts(s, h0, 0, 0, 1, 0, 0, 1);
+            return;
         }
         const bool go_left = !s.vR ? true : (!s.vL ? false : res);        // ties prefer the right candidate (:588-593)
         if (go_left) {
             // new edge l1 -> ri: at l1 after the edge back to the old li, at ri before the old cross edge
             const int at0 = s.hl1 ^ 1, nx0 = s.u1_nxt, at1 = s.hr1, nx1 = s.e ^ 1;
             s.li = s.l1; s.pli = s.pl1;
-            lp_queue_inserts(s, h0, s.li, s.pli, s.ri, s.pri, at0, nx0, 0, at1, nx1, 0);
+            lp_queue_inserts(s, h0, at0, nx0, 0, at1, nx1, 0);
         } else {
             // new edge li -> r1: at li after the old cross edge, at r1 before the edge back to the old ri
             const int at0 = s.e, nx0 = s.hl1, at1 = s.t1_prv, nx1 = s.hr1 ^ 1;
             s.ri = s.r1; s.pri = s.pr1;
-            lp_queue_inserts(s, h0, s.li, s.pli, s.ri, s.pri, at0, nx0, 0, at1, nx1, 0);
+            lp_queue_inserts(s, h0, at0, nx0, 0, at1, nx1, 0);
         }
-        break;
     }
-    default: break;
+}
+
+// Generic entry (host emulation): dispatch on the frame's phase. Returns false when the tree is finished.
+GT_INLINE bool lpf_step(const LFrame& f, LState& s) {
+    switch (s.phase) {
+    case LP_LEAF0: lpf_step_t<LP_LEAF0>(f, s); break;
+    case LP_LEAF1: lpf_step_t<LP_LEAF1>(f, s); break;
+    case LP_LEAF2: lpf_step_t<LP_LEAF2>(f, s); break;
+    case LP_TINIT0: lpf_step_t<LP_TINIT0>(f, s); break;
+    case LP_TINIT1: lpf_step_t<LP_TINIT1>(f, s); break;
+    case LP_TAN_R: lpf_step_t<LP_TAN_R>(f, s); break;
+    case LP_TAN_L: lpf_step_t<LP_TAN_L>(f, s); break;
+    case LP_INS_T0: lpf_step_t<LP_INS_T0>(f, s); break;
+    case LP_INS_SCAN: lpf_step_t<LP_INS_SCAN>(f, s); break;
+    case LP_VR: lpf_step_t<LP_VR>(f, s); break;
+    case LP_CR: lpf_step_t<LP_CR>(f, s); break;
+    case LP_VL: lpf_step_t<LP_VL>(f, s); break;
+    case LP_CL: lpf_step_t<LP_CL>(f, s); break;
+    case LP_F: lpf_step_t<LP_F>(f, s); break;
+    default: return false;
     }
-    if (s.phase == LP_DONE) return false;
-    lp_prepare(s);
-    return true;
+    return s.phase != LP_DONE;
 }
 
 // Triangles owned by sorted vertex i, in the reference's emission order (convertTrisFreeAdj :606-635);

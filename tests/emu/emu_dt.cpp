@@ -104,14 +104,33 @@ int emu_triangulate_lpf(const double* points, int n, int* tri_out, long* iters_o
             i = e;
         }
     }
-    std::vector<LPt> pt(n);
-    for (int i = 0; i < n; ++i) { pt[i].x = points[2 * perm[i]]; pt[i].y = points[2 * perm[i] + 1]; pt[i].z = 0; pt[i].w = 0; }
+    std::vector<Pt> pt(n);
+    for (int i = 0; i < n; ++i) { pt[i].x = points[2 * perm[i]]; pt[i].y = points[2 * perm[i] + 1]; }
     const int cap_e = 3 * n + 64;
     std::vector<LRec> rec(2 * cap_e); std::vector<u16> head(n, (u16)GT_NIL);
     LFrame f; f.pt = pt.data(); f.rec = rec.data(); f.head = head.data(); f.n = n; f.cap_e = cap_e;
     LState s; memset(&s, 0, sizeof s); lp_begin(f, s);
     long iters = 0;
-    while (lpf_step(f, s)) { if (++iters > 400L * n + 10000) return -3000; }
+    bool more = s.phase != LP_DONE;
+    uint32_t w[LS_WORDS];
+    ls_pack(s, [&](int i, uint32_t v) { w[i] = v; });
+    while (more) {
+        // the GPU scheduler keeps only the packed form between iterations and rewrites only the words the
+        // phase may modify (LsDirty): go through exactly that here
+        LState t; memset(&t, 0xee, sizeof t);
+        ls_unpack(t, [&](int i) { return w[i]; });
+        auto put = [&](int i, uint32_t v) { w[i] = v; };
+        switch (t.phase) {
+#define EMU_PH(P) case P: lpf_step_t<P>(f, t); ls_pack_mask<LsDirty<P>::mask>(t, put); break;
+        EMU_PH(LP_LEAF0) EMU_PH(LP_LEAF1) EMU_PH(LP_LEAF2) EMU_PH(LP_TINIT0) EMU_PH(LP_TINIT1) EMU_PH(LP_TAN_R) EMU_PH(LP_TAN_L)
+        EMU_PH(LP_INS_T0) EMU_PH(LP_INS_SCAN) EMU_PH(LP_VR) EMU_PH(LP_CR) EMU_PH(LP_VL) EMU_PH(LP_CL) EMU_PH(LP_F)
+#undef EMU_PH
+        default: return -4000;
+        }
+        s = t;
+        more = t.phase != LP_DONE;
+        if (++iters > 400L * n + 10000) return -3000;
+    }
     if (iters_out) *iters_out = iters;
     if (s.err) return -(int)s.err;
     int nt = 0;
