@@ -203,8 +203,10 @@ def run_native(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     gathered = [torch.empty_like(T.area) for _ in range(world)] if world > 1 else None
+    launches_dev = 0
     for a, b in ev:
         a.record(); T.run(xyz_d, box_d, 3); b.record()
+        launches_dev += L.gta_b200_last_launches()
         if world > 1:
             dist.all_gather(gathered, T.area)          # the path's only exchange: final per-frame area gather (0.8 MB per rank)
     e1.record()
@@ -266,7 +268,7 @@ def run_native(args):
             "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": F * (NATOMS * 24 + 24),
                     "d2h_bytes_per_step": F * (3 * 8 + 3 * 4), "timing": "host wall clock around the synchronous C-ABI call",
                     "streams": args.streams},
-            "gpu_launches": args.steps + launches_e2e,
+            "gpu_launches": launches_dev + launches_e2e,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                          "traffic": NCU_DRAM_BYTES_PER_FRAME * F / 1e9, "traffic_unit": "GB per launch (ncu dram bytes per frame x frames per launch)",
                          "peak_source": pk_src, "kernel": "gt::tessellate_kernel",

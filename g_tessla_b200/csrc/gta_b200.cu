@@ -112,15 +112,21 @@ int occupancy_for(const Shape& s) {
 }
 
 // ---- lane-per-frame path: workspace cache (one per device, grows on demand) and launcher
-struct LpfCache { gt::LpfWs ws{}; size_t frames = 0; int cap = 0, cap_e = 0; unsigned int* counter = nullptr; };
+struct LpfCache { gt::LpfWs ws{}; size_t frames = 0; int cap = 0, cap_e = 0; unsigned int* counter = nullptr; cudaEvent_t done = nullptr; };
 LpfCache g_lpf[64];
 std::mutex g_lpf_mu;
 
-int lpf_threshold() {      // batches at least this large use the lane-per-frame path (0 = never); GTA_B200_LPF overrides
-    static int v = -2;
-    if (v == -2) { const char* e = getenv("GTA_B200_LPF"); v = e ? atoi(e) : 0; }
+// Launches of at least this many frames use the lane-per-frame path (its throughput needs tens of thousands of
+// frames in flight; below that the CTA-per-frame kernel wins: measured crossover on cfg 3 at ~25k frames).
+// GTA_B200_LPF overrides (0 = never, 1 = always).
+std::atomic<int> g_lpf_threshold{-2};
+int lpf_threshold() {
+    int v = g_lpf_threshold.load();
+    if (v == -2) { const char* e = getenv("GTA_B200_LPF"); v = e ? atoi(e) : 32768; g_lpf_threshold.store(v); }
     return v;
 }
+// (triangle lists are a parity-test output: they stay on the fused kernel unless the lane-per-frame path is forced)
+bool use_lpf(int nframes, const Shape& s, bool want_tri) { return lpf_threshold() > 0 && nframes >= lpf_threshold() && s.cap < 4000 && (!want_tri || lpf_threshold() == 1); }
 
 int lpf_ensure(int dev, size_t frames, int cap, int cap_e, LpfCache** out) {
     std::lock_guard<std::mutex> lk(g_lpf_mu);
@@ -128,6 +134,7 @@ int lpf_ensure(int dev, size_t frames, int cap, int cap_e, LpfCache** out) {
     if (c.frames < frames || c.cap < cap || c.cap_e < cap_e) {
         cudaFree(c.ws.pt); cudaFree(c.ws.z); cudaFree(c.ws.rec); cudaFree(c.ws.head); cudaFree(c.ws.perm);
         cudaFree(c.ws.n); cudaFree(c.ws.st); cudaFree(c.ws.err); cudaFree(c.counter);
+        if (c.done) { cudaDeviceSynchronize(); cudaEventDestroy(c.done); }
         c = LpfCache();
         frames = std::max(frames, c.frames); cap = std::max(cap, c.cap); cap_e = std::max(cap_e, c.cap_e);
         CK(cudaMalloc((void**)&c.ws.pt, sizeof(gt::Pt) * frames * cap));
@@ -137,6 +144,7 @@ int lpf_ensure(int dev, size_t frames, int cap, int cap_e, LpfCache** out) {
         CK(cudaMalloc((void**)&c.ws.perm, 2 * frames * cap));
         CK(cudaMalloc((void**)&c.ws.n, 4 * frames)); CK(cudaMalloc((void**)&c.ws.st, 4 * frames)); CK(cudaMalloc((void**)&c.ws.err, 4 * frames));
         CK(cudaMalloc((void**)&c.counter, 4));
+        CK(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
         c.ws.cap = cap; c.ws.cap_e = cap_e; c.frames = frames; c.cap = cap; c.cap_e = cap_e;
     }
     *out = &c;
@@ -152,6 +160,9 @@ int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st) {
     LpfCache* c = nullptr;
     int rc = lpf_ensure(dev, (size_t)p.nframes, s.cap, gt::pool_edges(s.cap), &c);
     if (rc) return rc;
+    // the workspace is shared by all streams of this device: launches queue behind each other
+    // (copies of the next chunk still overlap)
+    CK(cudaStreamWaitEvent(st, c->done, 0));
     // 1. pre-pass (load, -corr, sort) into the workspace
     p.ws = c->ws;
     rc = launch(p, s, st);
@@ -161,7 +172,7 @@ int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st) {
     CK(cudaMemsetAsync(c->counter, 0, 4, st));
     static int slots = -1, wthreads = -1;                    // frames in flight per block / threads per block (experiments: GTA_B200_LPF_SLOTS, _THREADS)
     if (slots < 0) { const char* e = getenv("GTA_B200_LPF_SLOTS"); slots = e ? atoi(e) : 1024; }
-    if (wthreads < 0) { const char* e = getenv("GTA_B200_LPF_THREADS"); wthreads = e ? atoi(e) : 512; }
+    if (wthreads < 0) { const char* e = getenv("GTA_B200_LPF_THREADS"); wthreads = e ? atoi(e) : 256; }
     {
         // spread the batch over every SM: fewer slots per block shorten the round when the batch is small
         const int blocks = std::max(1, std::min(sms, (p.nframes + 63) / 64));
@@ -174,7 +185,7 @@ int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st) {
             CK(cudaGetLastError());
             return GTA_B200_OK;
         };
-        rc = wthreads >= 1024 ? go(gt::lpf_wave_kernel<1024>, 1024) : (wthreads >= 768 ? go(gt::lpf_wave_kernel<768>, 768) : (wthreads >= 512 ? go(gt::lpf_wave_kernel<512>, 512) : go(gt::lpf_wave_kernel<256>, 256)));
+        rc = wthreads >= 512 ? go(gt::lpf_wave_kernel<512>, 512) : (wthreads >= 384 ? go(gt::lpf_wave_kernel<384>, 384) : (wthreads >= 320 ? go(gt::lpf_wave_kernel<320>, 320) : go(gt::lpf_wave_kernel<256>, 256)));
         if (rc) return rc;
     }
     // 3. areas
@@ -182,6 +193,7 @@ int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st) {
     ap.area = p.area; ap.area2d = p.area2d; ap.status = p.status; ap.ntri = p.ntri; ap.tri = p.tri; ap.tri_cap = p.tri_cap;
     gt::lpf_area_kernel<<<(p.nframes + 3) / 4, 128, 0, st>>>(ap);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(c->done, st));
     return GTA_B200_OK;
 }
 
@@ -203,6 +215,12 @@ int gta_b200_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
+}
+
+int gta_b200_set_batch_threshold(int min_frames) {
+    int old = lpf_threshold();
+    g_lpf_threshold.store(min_frames < 0 ? 32768 : min_frames);
+    return old;
 }
 
 int gta_b200_max_points(void) {
@@ -270,8 +288,9 @@ int gta_b200_tessellate_device(const double* d_xyz, int in_dim, const double* d_
     p.corr = d_corr; p.corr_cap = corr_cap; p.ncorr = d_ncorr;
     p.work = d_work; p.coop_nodes = coop_nodes_for(s.threads); p.dbg = g_dbg; p.ws = gt::LpfWs{};
     CK(cudaMemsetAsync(d_work, 0, sizeof(unsigned int), st));
-    if (lpf_threshold() > 0 && nframes >= lpf_threshold() && s.cap < 32000) return launch_lpf(p, s, st);
-    return launch(p, s, st);
+    const bool lpf = use_lpf(nframes, s, d_tri != nullptr);
+    g_last_launches = lpf ? 3 : 1;                              // pre-pass + lane-per-frame + area, or the fused kernel
+    return lpf ? launch_lpf(p, s, st) : launch(p, s, st);
 }
 
 }  // extern "C"
@@ -316,14 +335,15 @@ void slot_free(Slot& s) {
     s = Slot();
 }
 
-int slot_ensure(Slot& s, int chunk, size_t frame_bytes, int box_stride, size_t tri_elems, size_t corr_elems) {
+int slot_ensure(Slot& s, int chunk, size_t frame_bytes, int box_stride, size_t tri_elems, size_t corr_elems, bool need_pinned_in) {
     size_t in_bytes = frame_bytes * (size_t)chunk;
-    if (s.st && s.in_bytes >= in_bytes && s.chunk >= chunk && s.box_stride >= box_stride &&
+    if (s.st && s.in_bytes >= in_bytes && (s.h_in || !need_pinned_in) && s.chunk >= chunk && s.box_stride >= box_stride &&
         s.tri_elems >= tri_elems && s.corr_elems >= corr_elems) return GTA_B200_OK;
     slot_free(s);
     CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
     CK(cudaEventCreate(&s.k0)); CK(cudaEventCreate(&s.k1));
-    CK(cudaHostAlloc((void**)&s.h_in, in_bytes, cudaHostAllocDefault)); CK(cudaMalloc((void**)&s.d_in, in_bytes));
+    if (need_pinned_in) CK(cudaHostAlloc((void**)&s.h_in, in_bytes, cudaHostAllocDefault));     // not needed when the caller's buffer is page-locked
+    CK(cudaMalloc((void**)&s.d_in, in_bytes));
     size_t bb = sizeof(double) * (size_t)std::max(box_stride, 1) * chunk;
     CK(cudaHostAlloc((void**)&s.h_box, bb, cudaHostAllocDefault)); CK(cudaMalloc((void**)&s.d_box, bb));
     CK(cudaHostAlloc((void**)&s.h_out, sizeof(double) * 3 * (size_t)chunk, cudaHostAllocDefault));
@@ -389,7 +409,7 @@ int submit(Slot& s, const Job& j, const Shape& shp, int f0, int nf, bool src_pin
     CK(cudaMemsetAsync(s.d_work, 0, sizeof(unsigned int), s.st));
     CK(cudaMemsetAsync(s.d_st, 0, sizeof(int) * 3 * (size_t)c, s.st));
     CK(cudaEventRecord(s.k0, s.st));
-    int rc = (lpf_threshold() > 0 && nf >= lpf_threshold() && shp.cap < 32000) ? launch_lpf(p, shp, s.st) : launch(p, shp, s.st);
+    int rc = use_lpf(nf, shp, j.tri != nullptr) ? launch_lpf(p, shp, s.st) : launch(p, shp, s.st);
     if (rc) return rc;
     CK(cudaEventRecord(s.k1, s.st));
     CK(cudaMemcpyAsync(s.h_out, s.d_out, sizeof(double) * 3 * (size_t)c, cudaMemcpyDeviceToHost, s.st));
@@ -422,6 +442,13 @@ int run_job(Job j, int device, int nstreams) {
     chunk = std::min<long long>(chunk, std::max<long long>(256, (64ll << 20) / (long long)std::max<size_t>(frame_bytes, 1)));
     chunk = std::max<long long>(chunk, 1);
     if (j.tri) chunk = std::min<long long>(chunk, std::max<long long>(1, (256ll << 20) / (12ll * std::max(j.tri_cap, 1))));
+    if (use_lpf(j.nframes, shp, j.tri != nullptr)) {
+        // lane-per-frame path: it wants tens of thousands of frames per launch; two slots so that the copies of one
+        // chunk overlap the kernels of the other
+        const long long nchunks = (j.nframes + 131071) / 131072;
+        chunk = (j.nframes + nchunks - 1) / nchunks;
+        nstreams = (int)std::min<long long>(2, nchunks);
+    }
 
     bool src_pinned = false;
     if (j.xyz) {
@@ -433,7 +460,8 @@ int run_job(Job j, int device, int nstreams) {
     if ((int)g_cache.slots.size() < nstreams) g_cache.slots.resize(nstreams);
     for (int i = 0; i < nstreams; ++i) {
         int rc = slot_ensure(g_cache.slots[i], (int)chunk, frame_bytes, std::max(j.box_stride, 1),
-                             j.tri ? (size_t)chunk * j.tri_cap * 3 : 0, j.corr ? (size_t)chunk * j.corr_cap * 3 : 0);
+                             j.tri ? (size_t)chunk * j.tri_cap * 3 : 0, j.corr ? (size_t)chunk * j.corr_cap * 3 : 0,
+                             !src_pinned || j.frames != nullptr);
         if (rc) return rc;
     }
     double kms = 0.0; int launches = 0, rc = GTA_B200_OK, si = 0;
@@ -444,7 +472,7 @@ int run_job(Job j, int device, int nstreams) {
         if (rc) break;
         int nf = std::min<long long>(chunk, j.nframes - f0);
         rc = submit(s, j, shp, f0, nf, src_pinned);
-        ++launches;
+        launches += use_lpf(nf, shp, j.tri != nullptr) ? 3 : 1;          // pre-pass + lane-per-frame + area, or the fused kernel
     }
     for (int i = 0; i < nstreams; ++i) { int r2 = drain(g_cache.slots[i], j, &kms); if (rc == GTA_B200_OK) rc = r2; }
     g_last_kernel_ms = kms; g_last_launches = launches;

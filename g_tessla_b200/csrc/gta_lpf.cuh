@@ -116,20 +116,13 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
                 u16* fhead = p.ws.head + (size_t)fr * p.ws.cap; const int fn = slot_n[sl], fce = p.ws.cap_e;
                 uint32_t* eo = p.ws.err + fr;
                 switch (ph) {                                             // every lane of the chunk is in phase ph
-                case LP_LEAF0: lpf_wave_phase<LP_LEAF0>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                case LP_LEAF1: lpf_wave_phase<LP_LEAF1>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                case LP_LEAF2: lpf_wave_phase<LP_LEAF2>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                case LP_TINIT0: lpf_wave_phase<LP_TINIT0>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                case LP_TINIT1: lpf_wave_phase<LP_TINIT1>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                case LP_TAN_R: lpf_wave_phase<LP_TAN_R>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                case LP_TAN_L: lpf_wave_phase<LP_TAN_L>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                case LP_INS_T0: lpf_wave_phase<LP_INS_T0>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                case LP_INS_SCAN: lpf_wave_phase<LP_INS_SCAN>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                case LP_VR: lpf_wave_phase<LP_VR>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                case LP_CR: lpf_wave_phase<LP_CR>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                case LP_VL: lpf_wave_phase<LP_VL>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                case LP_CL: lpf_wave_phase<LP_CL>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                default: lpf_wave_phase<LP_F>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                case LP_LEAF: lpf_wave_phase<LP_LEAF>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                case LP_TINIT: lpf_wave_phase<LP_TINIT>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                case LP_TAN: lpf_wave_phase<LP_TAN>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                case LP_INS: lpf_wave_phase<LP_INS>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                case LP_SCAN: lpf_wave_phase<LP_SCAN>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                case LP_V: lpf_wave_phase<LP_V>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                default: lpf_wave_phase<LP_C>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
                 }
             }
         }

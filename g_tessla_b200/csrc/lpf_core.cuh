@@ -2,26 +2,29 @@
 //
 // dt_core.cuh::merge is a nest of data-dependent loops: when the lanes of a warp walk different merges
 // they diverge and the warp runs them one after another. Here the same algorithm -- the same predicates
-// on the same operands in the same order, hence the same rings as the reference (src/delaunay_tri.c:
-// 511-601, tangents :337-406, insertNode :210-245, deleteNode :247-268) -- is cut into ITERATIONS.
-// One iteration of one frame is
-//     [A: ring entry of a vertex] -> [B: one edge = its two half-edge records] -> [C: one point]
-//     -> ONE predicate (orient2d or incircle) -> a short transition that edits the rings and names
-//     the phase of the next iteration.
-// Each phase is a template instance lpf_step_t<PH>: straight-line code. The GPU scheduler
-// (gta_lpf.cuh) sorts the frames in flight by phase every round and lets a warp run ONE phase for 32
-// different frames, so there is no divergence between lanes and their (uncoalesced) loads are in flight
-// together. Per frame the persistent state is 36 words (ls_pack / ls_unpack); the frame itself lives in
+// on the same operands, hence the same rings as the reference (src/delaunay_tri.c:511-601, tangents
+// :337-406, insertNode :210-245, deleteNode :247-268) -- is cut into ITERATIONS. One iteration of one
+// frame runs up to TWO independent chains
+//     [one edge = its two half-edge records] -> [one point (+ the ring entry of that vertex)]
+//     -> one predicate (orient2d or incircle)
+// followed by a short transition that edits the rings and names the phase of the next iteration.
+// The two chains are the two sides of the reference's sequential code that cannot influence each other:
+//   LP_TAN   upper and lower common tangent walk side by side (read-only walks over untouched halves)
+//   LP_V     validity of the right and of the left candidate        (:556, :569)
+//   LP_C     the right and the left incircle deletion chain          (:559-567, :572-580; they edit disjoint rings)
+//   LP_INS   the two ring insertions of a new cross edge            (connectVerts :270-275; two different rings)
+//   LP_SCAN  their clockwise scans, when "right of first" held      (:217-224)
+// The choice between the candidates (:582-593) needs no load and is taken at the end of the LP_V / LP_C
+// iteration that settles both chains. Each phase is a template instance lpf_step_t<PH>: straight-line
+// code. The GPU scheduler (gta_lpf.cuh) bins the frames in flight by phase every round and lets a warp run
+// ONE phase for 32 different frames: no divergence between lanes, and 64 dependent-load chains in flight per
+// warp. Per frame the persistent state is LS_WORDS words (ls_pack / ls_unpack); the frame itself lives in
 // global memory:
 //   point  16 B {x, y}   record 8 B {dst, nxt, prv, -} per half-edge, twins adjacent (edge = 16 B, one load)
 //   head    2 B per vertex
 // Edge pool, free list and the cursor over the recursion tree are private to the frame: no atomics.
 //
-// The two tangents are computed upper first, then lower (the reference does lower first, :542-543; both are
-// read-only walks over the untouched halves, so the order cannot matter): the lower tangent's end points are
-// then already in the registers that the first merge step needs.
-//
-// Host-compilable: tests/emu drives lpf_step() sequentially and compares with the oracle.
+// Host-compilable: tests/emu drives the steps sequentially (through the packed state) and compares with the oracle.
 #pragma once
 #include "dt_core.cuh"
 
@@ -59,14 +62,7 @@ GT_INLINE void lf_set_rec(const LFrame& f, int h, int dst, int nxt, int prv) {
     LRec r; r.dst = (u16)dst; r.nxt = (u16)nxt; r.prv = (u16)prv; r.pad = 0; f.rec[h] = r;
 }
 
-enum LPhase : int {
-    LP_LEAF0 = 0, LP_LEAF1, LP_LEAF2,
-    LP_TINIT0, LP_TINIT1, LP_TAN_R, LP_TAN_L,
-    LP_INS_T0, LP_INS_SCAN,
-    LP_VR, LP_CR, LP_VL, LP_CL, LP_F,
-    LP_DONE,          // whole tree finished
-    LP_NPHASE
-};
+enum LPhase : int { LP_LEAF = 0, LP_TINIT, LP_TAN, LP_INS, LP_SCAN, LP_V, LP_C, LP_DONE, LP_NPHASE };
 
 // Per-frame state between iterations.
 struct LState {
@@ -74,22 +70,24 @@ struct LState {
     int d, k, ia, ib;                 // current node of the recursion tree
     uint32_t err;
     int bump, free_head;              // private edge pool
-    int up, first_edge, vR, vL, iGap, i1Gap, iWhich;
-    // tangents: current end points tx / ty (their coordinates are pli / pri), walk positions hl / hr
-    int tx, ty, hl, hr, ux, uy;
+    int first_edge, vR, vL, actR, actL, scan0, scan1;
+    // tangents: upper (ux, uy) walks with (uHl, uHr), coordinates in pr1 / pl1; lower (li, ri) with (lHl, lHr), coordinates in
+    // pli / pri. xSub: 0 = next test is the right hull's candidate, 1 = the left hull's, 2 = tangent found
+    int ux, uy, uHl, uHr, uSub, lHl, lHr, lSub;
     // merge step
-    int li, ri, e, headL, headR;
-    int hr1, r1, hr2, t1_prv, t1_nxt;    // right candidate ri->r1, its clockwise neighbour, the twin's links at r1
-    int hl1, l1, hl2, u1_prv, u1_nxt;    // left candidate li->l1, its counter-clockwise neighbour, the twin's links at l1
-    // ring insertion in flight (endpoint 0 = the left vertex li, endpoint 1 = the right vertex ri)
-    int iP, iIN, iH, iAt, iNx, iCur, iHd, iLast, at0, nx0;
-    int i1H, i1At, i1Nx;
-    // cached coordinates: pli / pri = li / ri (tangents: tx / ty), pr1 / pl1 = the two candidates (leaves: points a, b)
+    int li, ri, e, headL, headR;              // headL / headR = ring entries ("first") of li / ri
+    int hr1, r1, hr2, t1_prv, t1_nxt, hdR1;   // right candidate ri->r1, its clockwise neighbour, the twin's links at r1, first(r1)
+    int hl1, l1, hl2, u1_prv, u1_nxt, hdL1;   // left candidate li->l1, its counter-clockwise neighbour, the twin's links at l1, first(l1)
+    // the two ring insertions of the new edge h0 = li -> ri (endpoint 0 at li, endpoint 1 at ri)
+    int h0, at0, nx0, at1, nx1;               // slots known from the topology of the merge (unused for the first edge: hull gap)
+    int cur0, hd0, last0, cur1, hd1, last1;   // clockwise scans in flight
+    int plNx0, plAt1;                         // where the half-edges went: succ(li, ri) and pred(ri, li) of the next step
+    // cached coordinates: pli / pri = li / ri, pr1 / pl1 = the two candidates (tangents: upper end points)
     Pt pli, pri, pr1, pl1;
 };
 
-// ---------------------------------------------------------------- persistent form (36 words)
-constexpr int LS_WORDS = 36;
+// ---------------------------------------------------------------- persistent form
+constexpr int LS_WORDS = 37;
 GT_INLINE uint32_t ls_lo(double v) { return (uint32_t)((uint64_t)dbl_bits(v) & 0xffffffffull); }
 GT_INLINE uint32_t ls_hi(double v) { return (uint32_t)((uint64_t)dbl_bits(v) >> 32); }
 GT_INLINE double ls_dbl(uint32_t lo, uint32_t hi) {
@@ -103,36 +101,36 @@ GT_INLINE double ls_dbl(uint32_t lo, uint32_t hi) {
 #define LS_P2(a, b) ((uint32_t)((a) & 0xffff) | ((uint32_t)((b) & 0xffff) << 16))
 template <class Put>
 GT_INLINE void ls_pack(const LState& s, Put&& put) {
-    put(0, (uint32_t)s.phase | ((uint32_t)s.d << 4) | ((uint32_t)s.k << 8) | ((s.err & 15u) << 20) | ((uint32_t)s.up << 24) | ((uint32_t)s.first_edge << 25) |
-           ((uint32_t)s.vR << 26) | ((uint32_t)s.vL << 27) | ((uint32_t)s.iGap << 28) | ((uint32_t)s.i1Gap << 29) | ((uint32_t)s.iWhich << 30));
-    put(1, LS_P2(s.ia, s.ib)); put(2, LS_P2(s.bump, s.free_head));
-    put(3, LS_P2(s.tx, s.ty)); put(4, LS_P2(s.hl, s.hr)); put(5, LS_P2(s.ux, s.uy));
-    put(6, LS_P2(s.li, s.ri)); put(7, LS_P2(s.e, s.headL)); put(8, LS_P2(s.headR, s.hr1)); put(9, LS_P2(s.r1, s.hr2));
-    put(10, LS_P2(s.t1_prv, s.t1_nxt)); put(11, LS_P2(s.hl1, s.l1)); put(12, LS_P2(s.hl2, s.u1_prv)); put(13, LS_P2(s.u1_nxt, s.iP));
-    put(14, LS_P2(s.iIN, s.iH)); put(15, LS_P2(s.iAt, s.iNx)); put(16, LS_P2(s.iCur, s.iHd)); put(17, LS_P2(s.iLast, s.at0));
-    put(18, LS_P2(s.nx0, s.i1H)); put(19, LS_P2(s.i1At, s.i1Nx));
-    put(20, ls_lo(s.pli.x)); put(21, ls_hi(s.pli.x)); put(22, ls_lo(s.pli.y)); put(23, ls_hi(s.pli.y));
-    put(24, ls_lo(s.pri.x)); put(25, ls_hi(s.pri.x)); put(26, ls_lo(s.pri.y)); put(27, ls_hi(s.pri.y));
-    put(28, ls_lo(s.pr1.x)); put(29, ls_hi(s.pr1.x)); put(30, ls_lo(s.pr1.y)); put(31, ls_hi(s.pr1.y));
-    put(32, ls_lo(s.pl1.x)); put(33, ls_hi(s.pl1.x)); put(34, ls_lo(s.pl1.y)); put(35, ls_hi(s.pl1.y));
+    put(0, (uint32_t)s.phase | ((uint32_t)s.d << 4) | ((uint32_t)s.k << 8) | ((s.err & 15u) << 20) | ((uint32_t)s.first_edge << 24) | ((uint32_t)s.vR << 25) |
+           ((uint32_t)s.vL << 26) | ((uint32_t)s.actR << 27) | ((uint32_t)s.actL << 28) | ((uint32_t)s.scan0 << 29) | ((uint32_t)s.scan1 << 30));
+    put(1, (uint32_t)s.ia | ((uint32_t)s.ib << 12) | ((uint32_t)s.uSub << 24) | ((uint32_t)s.lSub << 26));
+    put(2, LS_P2(s.bump, s.free_head)); put(3, LS_P2(s.ux, s.uy)); put(4, LS_P2(s.uHl, s.uHr)); put(5, LS_P2(s.li, s.ri));
+    put(6, LS_P2(s.lHl, s.lHr)); put(7, LS_P2(s.e, s.headL)); put(8, LS_P2(s.headR, s.hr1)); put(9, LS_P2(s.r1, s.hr2));
+    put(10, LS_P2(s.t1_prv, s.t1_nxt)); put(11, LS_P2(s.hdR1, s.hl1)); put(12, LS_P2(s.l1, s.hl2)); put(13, LS_P2(s.u1_prv, s.u1_nxt));
+    put(14, LS_P2(s.hdL1, s.h0)); put(15, LS_P2(s.at0, s.nx0)); put(16, LS_P2(s.at1, s.nx1)); put(17, LS_P2(s.cur0, s.hd0));
+    put(18, LS_P2(s.last0, s.cur1)); put(19, LS_P2(s.hd1, s.last1)); put(20, LS_P2(s.plNx0, s.plAt1));
+    put(21, ls_lo(s.pli.x)); put(22, ls_hi(s.pli.x)); put(23, ls_lo(s.pli.y)); put(24, ls_hi(s.pli.y));
+    put(25, ls_lo(s.pri.x)); put(26, ls_hi(s.pri.x)); put(27, ls_lo(s.pri.y)); put(28, ls_hi(s.pri.y));
+    put(29, ls_lo(s.pr1.x)); put(30, ls_hi(s.pr1.x)); put(31, ls_lo(s.pr1.y)); put(32, ls_hi(s.pr1.y));
+    put(33, ls_lo(s.pl1.x)); put(34, ls_hi(s.pl1.x)); put(35, ls_lo(s.pl1.y)); put(36, ls_hi(s.pl1.y));
 }
 template <class Get>
 GT_INLINE void ls_unpack(LState& s, Get&& get) {
     uint32_t w = get(0);
-    s.phase = w & 15; s.d = (w >> 4) & 15; s.k = (w >> 8) & 0xfff; s.err = (w >> 20) & 15; s.up = (w >> 24) & 1; s.first_edge = (w >> 25) & 1;
-    s.vR = (w >> 26) & 1; s.vL = (w >> 27) & 1; s.iGap = (w >> 28) & 1; s.i1Gap = (w >> 29) & 1; s.iWhich = (w >> 30) & 1;
+    s.phase = w & 15; s.d = (w >> 4) & 15; s.k = (w >> 8) & 0xfff; s.err = (w >> 20) & 15; s.first_edge = (w >> 24) & 1; s.vR = (w >> 25) & 1;
+    s.vL = (w >> 26) & 1; s.actR = (w >> 27) & 1; s.actL = (w >> 28) & 1; s.scan0 = (w >> 29) & 1; s.scan1 = (w >> 30) & 1;
+    w = get(1); s.ia = w & 0xfff; s.ib = (w >> 12) & 0xfff; s.uSub = (w >> 24) & 3; s.lSub = (w >> 26) & 3;
 #define LS_U2(i, a, b) w = get(i); a = (int)(w & 0xffff); b = (int)(w >> 16)
-    LS_U2(1, s.ia, s.ib); LS_U2(2, s.bump, s.free_head);
-    LS_U2(3, s.tx, s.ty); LS_U2(4, s.hl, s.hr); LS_U2(5, s.ux, s.uy);
-    LS_U2(6, s.li, s.ri); LS_U2(7, s.e, s.headL); LS_U2(8, s.headR, s.hr1); LS_U2(9, s.r1, s.hr2);
-    LS_U2(10, s.t1_prv, s.t1_nxt); LS_U2(11, s.hl1, s.l1); LS_U2(12, s.hl2, s.u1_prv); LS_U2(13, s.u1_nxt, s.iP);
-    LS_U2(14, s.iIN, s.iH); LS_U2(15, s.iAt, s.iNx); LS_U2(16, s.iCur, s.iHd); LS_U2(17, s.iLast, s.at0);
-    LS_U2(18, s.nx0, s.i1H); LS_U2(19, s.i1At, s.i1Nx);
+    LS_U2(2, s.bump, s.free_head); LS_U2(3, s.ux, s.uy); LS_U2(4, s.uHl, s.uHr); LS_U2(5, s.li, s.ri);
+    LS_U2(6, s.lHl, s.lHr); LS_U2(7, s.e, s.headL); LS_U2(8, s.headR, s.hr1); LS_U2(9, s.r1, s.hr2);
+    LS_U2(10, s.t1_prv, s.t1_nxt); LS_U2(11, s.hdR1, s.hl1); LS_U2(12, s.l1, s.hl2); LS_U2(13, s.u1_prv, s.u1_nxt);
+    LS_U2(14, s.hdL1, s.h0); LS_U2(15, s.at0, s.nx0); LS_U2(16, s.at1, s.nx1); LS_U2(17, s.cur0, s.hd0);
+    LS_U2(18, s.last0, s.cur1); LS_U2(19, s.hd1, s.last1); LS_U2(20, s.plNx0, s.plAt1);
 #undef LS_U2
-    s.pli.x = ls_dbl(get(20), get(21)); s.pli.y = ls_dbl(get(22), get(23));
-    s.pri.x = ls_dbl(get(24), get(25)); s.pri.y = ls_dbl(get(26), get(27));
-    s.pr1.x = ls_dbl(get(28), get(29)); s.pr1.y = ls_dbl(get(30), get(31));
-    s.pl1.x = ls_dbl(get(32), get(33)); s.pl1.y = ls_dbl(get(34), get(35));
+    s.pli.x = ls_dbl(get(21), get(22)); s.pli.y = ls_dbl(get(23), get(24));
+    s.pri.x = ls_dbl(get(25), get(26)); s.pri.y = ls_dbl(get(27), get(28));
+    s.pr1.x = ls_dbl(get(29), get(30)); s.pr1.y = ls_dbl(get(31), get(32));
+    s.pl1.x = ls_dbl(get(33), get(34)); s.pl1.y = ls_dbl(get(35), get(36));
 }
 
 // Words a phase may modify (a word is rewritten from the unpacked fields, so a phase that changes one field of
@@ -140,41 +138,24 @@ GT_INLINE void ls_unpack(LState& s, Get&& get) {
 // as a triangulation mismatch.
 #define LS_W(i) (1ull << (i))
 #define LS_PT(i) (15ull << (i))
-constexpr unsigned long long LS_M_NODE = LS_W(0) | LS_W(1) | LS_W(3);
+constexpr unsigned long long LS_M_NODE = LS_W(0) | LS_W(1);
+constexpr unsigned long long LS_M_QUEUE = LS_W(0) | LS_W(2) | LS_W(5) | LS_W(7) | LS_W(8) | LS_W(14) | LS_W(15) | LS_W(16) | LS_PT(21) | LS_PT(25);   // lp_decide
+constexpr unsigned long long LS_M_FINISH = LS_M_NODE | LS_W(7) | LS_W(8) | LS_W(11);                                                                  // lp_finish_connect
 template <int PH> struct LsDirty { static constexpr unsigned long long mask = ~0ull; };
-template <> struct LsDirty<LP_LEAF0> { static constexpr unsigned long long mask = LS_W(0) | LS_PT(28); };
-template <> struct LsDirty<LP_LEAF1> { static constexpr unsigned long long mask = LS_W(0) | LS_PT(32); };
-template <> struct LsDirty<LP_LEAF2> { static constexpr unsigned long long mask = LS_W(2) | LS_M_NODE; };
-template <> struct LsDirty<LP_TINIT0> { static constexpr unsigned long long mask = LS_W(0) | LS_W(4) | LS_PT(20); };
-template <> struct LsDirty<LP_TINIT1> { static constexpr unsigned long long mask = LS_W(0) | LS_W(4) | LS_PT(24); };
-template <> struct LsDirty<LP_TAN_R> { static constexpr unsigned long long mask = LS_W(0) | LS_W(3) | LS_W(4) | LS_PT(24); };
-template <> struct LsDirty<LP_TAN_L> { static constexpr unsigned long long mask = LS_W(0) | LS_W(3) | LS_W(4) | LS_W(5) | LS_W(6) | LS_PT(20); };
-template <> struct LsDirty<LP_INS_T0> { static constexpr unsigned long long mask = LS_M_NODE | LS_W(7) | LS_W(8) | LS_W(11) | LS_W(13) | LS_W(14) | LS_W(15) | LS_W(16) | LS_W(17) | LS_W(18); };
-template <> struct LsDirty<LP_INS_SCAN> { static constexpr unsigned long long mask = LsDirty<LP_INS_T0>::mask; };
-template <> struct LsDirty<LP_VR> { static constexpr unsigned long long mask = LS_W(0) | LS_W(9) | LS_W(10) | LS_PT(28); };
-template <> struct LsDirty<LP_CR> { static constexpr unsigned long long mask = LS_W(0) | LS_W(2) | LS_W(8) | LS_W(9) | LS_W(10) | LS_PT(28); };
-template <> struct LsDirty<LP_VL> { static constexpr unsigned long long mask = LS_W(0) | LS_W(11) | LS_W(12) | LS_W(13) | LS_PT(32); };
-template <> struct LsDirty<LP_CL> { static constexpr unsigned long long mask = LS_W(0) | LS_W(2) | LS_W(7) | LS_W(11) | LS_W(12) | LS_W(13) | LS_PT(32); };
-template <> struct LsDirty<LP_F> { static constexpr unsigned long long mask = LS_W(0) | LS_W(2) | LS_W(6) | LS_W(13) | LS_W(14) | LS_W(15) | LS_W(18) | LS_W(19) | LS_PT(20) | LS_PT(24); };
+template <> struct LsDirty<LP_LEAF> { static constexpr unsigned long long mask = LS_W(2) | LS_M_NODE; };
+template <> struct LsDirty<LP_TINIT> { static constexpr unsigned long long mask = LS_W(0) | LS_W(1) | LS_W(3) | LS_W(4) | LS_W(5) | LS_W(6) | LS_W(7) | LS_W(8) | LS_PT(21) | LS_PT(25) | LS_PT(29) | LS_PT(33); };
+template <> struct LsDirty<LP_TAN> { static constexpr unsigned long long mask = LS_W(1) | LS_W(3) | LS_W(4) | LS_W(5) | LS_W(6) | LS_W(7) | LS_W(8) | LS_PT(21) | LS_PT(25) | LS_PT(29) | LS_PT(33) | LS_M_QUEUE; };
+template <> struct LsDirty<LP_INS> { static constexpr unsigned long long mask = LS_W(0) | LS_W(7) | LS_W(8) | LS_W(17) | LS_W(18) | LS_W(19) | LS_W(20) | LS_M_FINISH; };
+template <> struct LsDirty<LP_SCAN> { static constexpr unsigned long long mask = LsDirty<LP_INS>::mask; };
+template <> struct LsDirty<LP_V> { static constexpr unsigned long long mask = LS_W(9) | LS_W(10) | LS_W(11) | LS_W(12) | LS_W(13) | LS_W(14) | LS_PT(29) | LS_PT(33) | LS_M_QUEUE; };
+template <> struct LsDirty<LP_C> { static constexpr unsigned long long mask = LsDirty<LP_V>::mask; };
 template <unsigned long long MASK, class Put>
 GT_INLINE void ls_pack_mask(const LState& s, Put&& put) {
     ls_pack(s, [&](int i, uint32_t v) { if ((MASK >> i) & 1ull) put(i, v); });
 }
 
 // ---------------------------------------------------------------- helpers
-GT_INLINE int lp_alloc(const LFrame& f, LState& s, const LPair& freerec) {
-    if (s.free_head != (int)GT_NIL) { int e = s.free_head; s.free_head = freerec.a.nxt; return e; }
-    if (s.bump >= f.cap_e) { s.err |= GT_ERR_POOL; return -1; }
-    return s.bump++;
-}
 GT_INLINE void lp_free(const LFrame& f, LState& s, int e) { lf_set_nxt(f, 2 * e, s.free_head); s.free_head = e; }
-
-// queue the two ring insertions of the new edge h0 = li -> ri (endpoint 0 at li, endpoint 1 at ri)
-GT_INLINE void lp_queue_inserts(LState& s, int h0, int at0, int nx0, int gap0, int at1, int nx1, int gap1) {
-    s.iP = s.li; s.iIN = s.ri; s.iH = h0; s.iAt = at0; s.iNx = nx0; s.iGap = gap0; s.iWhich = 0;
-    s.i1H = h0 ^ 1; s.i1At = at1; s.i1Nx = nx1; s.i1Gap = gap1;
-    s.phase = LP_INS_T0;
-}
 
 // Advance the post-order cursor over the reference's recursion tree to the next node and enter its first phase.
 GT_INLINE void lp_next_node(const LFrame& f, LState& s) {
@@ -185,7 +166,7 @@ GT_INLINE void lp_next_node(const LFrame& f, LState& s) {
         d -= 1; k >>= 1;
         int ia, ib; tree_node(f.n, d, k, &ia, &ib);
         s.d = d; s.k = k; s.ia = ia; s.ib = ib;
-        s.phase = LP_TINIT0; s.up = 1; s.tx = (ia + ib) / 2; s.ty = s.tx + 1;
+        s.phase = LP_TINIT;
         return;
     } else k += 1;                                         // finished a left child: leftmost leaf of the sibling subtree
     int ia, ib;
@@ -195,77 +176,87 @@ GT_INLINE void lp_next_node(const LFrame& f, LState& s) {
         d += 1; k <<= 1;
     }
     s.d = d; s.k = k; s.ia = ia; s.ib = ib;
-    s.phase = (ib - ia < 1) ? LP_DONE : LP_LEAF0;
+    s.phase = (ib - ia < 1) ? LP_DONE : LP_LEAF;
 }
 
 GT_INLINE void lp_begin(const LFrame& f, LState& s) {
-    s.d = -1; s.k = 0; s.err = 0; s.bump = 0; s.free_head = GT_NIL; s.first_edge = 0; s.up = 0; s.vR = s.vL = 0;
-    s.iGap = s.i1Gap = s.iWhich = 0;
+    s.d = -1; s.k = 0; s.err = 0; s.bump = 0; s.free_head = GT_NIL;
+    s.first_edge = s.vR = s.vL = s.actR = s.actL = s.scan0 = s.scan1 = 0; s.uSub = s.lSub = 0;
     lp_next_node(f, s);
+}
+
+// A new cross edge li -> ri: take an edge from the pool and queue its two ring insertions.
+//   spec    = records of the free list's head as loaded at the start of the iteration
+//   freed   = this iteration pushed an edge on the free list after that load; then the head is that edge and
+//             prev_head (the head before the push) is its successor -- no further load needed
+GT_INLINE void lp_new_edge(const LFrame& f, LState& s, const LPair& spec, bool freed, int prev_head) {
+    int ne;
+    if (s.free_head != (int)GT_NIL) { ne = s.free_head; s.free_head = freed ? prev_head : (int)spec.a.nxt; }
+    else if (s.bump >= f.cap_e) { s.err |= GT_ERR_POOL; s.phase = LP_DONE; return; }
+    else ne = s.bump++;
+    s.h0 = 2 * ne; s.scan0 = s.scan1 = 0;
+    s.phase = LP_INS;
+}
+
+// The choice between the two candidates (reference :582-593; ties prefer the right one) and the new cross edge.
+GT_INLINE void lp_decide(const LFrame& f, LState& s, const LPair& spec, bool freed, int prev_head) {
+    bool go_left = true;
+    if (s.vR) {
+        go_left = false;
+        if (s.vL && s.r1 != s.l1) {
+            int sg = incircle_sign(s.pli.x, s.pli.y, s.pri.x, s.pri.y, s.pr1.x, s.pr1.y, s.pl1.x, s.pl1.y);
+            if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
+            go_left = sg > 0;
+        }
+    }
+    if (go_left) {
+        // new edge l1 -> ri: at l1 after the edge back to the old li, at ri before the old cross edge
+        s.at0 = s.hl1 ^ 1; s.nx0 = s.u1_nxt; s.at1 = s.hr1; s.nx1 = s.e ^ 1;
+        s.li = s.l1; s.pli = s.pl1; s.headL = s.hdL1;
+    } else {
+        // new edge li -> r1: at li after the old cross edge, at r1 before the edge back to the old ri
+        s.at0 = s.e; s.nx0 = s.hl1; s.at1 = s.t1_prv; s.nx1 = s.hr1 ^ 1;
+        s.ri = s.r1; s.pri = s.pr1; s.headR = s.hdR1;
+    }
+    lp_new_edge(f, s, spec, freed, prev_head);
+}
+
+// Both half-edges of the new edge are in their rings: next merge step, or the node is finished.
+GT_INLINE void lp_finish_connect(const LFrame& f, LState& s) {
+    s.e = s.h0;                                            // li -> ri
+    s.hl1 = s.plNx0;                                       // succ(li, ri)
+    s.hr1 = s.plAt1;                                       // pred(ri, li)
+    if (s.li == s.ux && s.ri == s.uy) lp_next_node(f, s); else s.phase = LP_V;
+}
+
+// Put half-edge h (origin P, destination IN) between `at` and `nx` in P's ring (reference insertNodeAfter :202-208).
+GT_INLINE void lp_place(const LFrame& f, LState& s, int which, int P, int IN, int h, int at, int nx, bool newhead, int hd) {
+    lf_set_nxt(f, at, h); lf_set_prv(f, nx, h); lf_set_rec(f, h, IN, nx, at);
+    if (newhead) f.head[P] = (u16)h;
+    const int newhd = newhead ? h : hd;
+    if (which == 0) { s.plNx0 = nx; s.headL = newhd; } else { s.plAt1 = at; s.headR = newhd; }
 }
 
 // ---------------------------------------------------------------- one iteration of phase PH
 template <int PH>
 GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
-    // ---- what to fetch
-    int fa = -1, fb = -1, fc = -1; bool bA = false, cB = false;
-    const int freeh = (s.free_head != (int)GT_NIL) ? 2 * s.free_head : -1;
-    if (PH == LP_LEAF0) fc = s.ia;
-    else if (PH == LP_LEAF1) fc = s.ia + 1;
-    else if (PH == LP_LEAF2) { fc = s.ib; fb = freeh; }
-    else if (PH == LP_TINIT0) { fa = s.tx; bA = true; fc = s.tx; }
-    else if (PH == LP_TINIT1) { fa = s.ty; bA = true; fc = s.ty; }
-    else if (PH == LP_TAN_R) { fb = s.hr; cB = true; }
-    else if (PH == LP_TAN_L) { fb = s.hl; cB = true; }
-    else if (PH == LP_INS_T0) { fa = s.iP; bA = true; cB = true; }
-    else if (PH == LP_INS_SCAN) { fb = s.iCur; cB = true; }
-    else if (PH == LP_VR) { fb = s.hr1; cB = true; }
-    else if (PH == LP_VL) { fb = s.hl1; cB = true; }
-    else if (PH == LP_CR) { fa = s.r1; fb = s.hr2; cB = true; }
-    else if (PH == LP_CL) { fa = s.l1; fb = s.hl2; cB = true; }
-    else if (PH == LP_F) fb = freeh;
-    int hdA = 0;
-    if (fa >= 0) hdA = f.head[fa];
-    const int hb = bA ? hdA : fb;
-    LPair pr; pr.a.dst = pr.a.nxt = pr.a.prv = pr.a.pad = 0; pr.b = pr.a;
-    if (hb >= 0) pr = lf_pair(f, hb);
-    const int vc = cB ? (int)pr.a.dst : fc;
-    Pt pc; pc.x = pc.y = 0.0;
-    if (vc >= 0) pc = lf_pt(f, vc);
+    const LPair zero = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    // the free list's head, for the phases that may need a new edge at the end of the iteration
+    LPair spec = zero;
+    if ((PH == LP_LEAF || PH == LP_TAN || PH == LP_V || PH == LP_C) && s.free_head != (int)GT_NIL) spec = lf_pair(f, 2 * s.free_head);
 
-    // ---- the iteration's predicate
-    int sg = 0;
-    if (PH == LP_LEAF2) { if (s.ib - s.ia == 2) sg = orient2d_sign(s.pr1.x, s.pr1.y, s.pl1.x, s.pl1.y, pc.x, pc.y); }
-    else if (PH == LP_TAN_R || PH == LP_TAN_L) {
-        // lower: rightOf(p, x, y) = ccw(p, y, x); upper: leftOf(p, x, y) = ccw(p, x, y)   (x = tx at pli, y = ty at pri)
-        const Pt A = s.up ? s.pli : s.pri, B = s.up ? s.pri : s.pli;
-        sg = orient2d_sign(pc.x, pc.y, A.x, A.y, B.x, B.y);
-    } else if (PH == LP_INS_T0 || PH == LP_INS_SCAN) {
-        // rightOf(in, parent, q) = ccw(in, q, parent); endpoint 0: parent li, in ri; endpoint 1: the other way round
-        const Pt pP = s.iWhich ? s.pri : s.pli, pIN = s.iWhich ? s.pli : s.pri;
-        sg = orient2d_sign(pIN.x, pIN.y, pc.x, pc.y, pP.x, pP.y);
-    } else if (PH == LP_VR || PH == LP_VL) {
-        sg = orient2d_sign(pc.x, pc.y, s.pli.x, s.pli.y, s.pri.x, s.pri.y);       // leftOf(r1, li, ri) / rightOf(l1, ri, li)
-    } else if (PH == LP_CR) {
-        if (!(vc == s.li || vc == s.ri || vc == s.r1))                              // a repeated point: exactly 0
-            sg = incircle_sign(s.pr1.x, s.pr1.y, s.pli.x, s.pli.y, s.pri.x, s.pri.y, pc.x, pc.y);
-    } else if (PH == LP_CL) {
-        if (!(vc == s.li || vc == s.ri || vc == s.l1))
-            sg = incircle_sign(s.pli.x, s.pli.y, s.pri.x, s.pri.y, s.pl1.x, s.pl1.y, pc.x, pc.y);
-    } else if (PH == LP_F) {
-        if (s.vR && s.vL && !s.first_edge && s.r1 != s.l1)
-            sg = incircle_sign(s.pli.x, s.pli.y, s.pri.x, s.pri.y, s.pr1.x, s.pr1.y, s.pl1.x, s.pl1.y);
-    }
-    if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
-    const bool res = sg > 0;
-
-    // ---- transition
-    if (PH == LP_LEAF0) { s.pr1 = pc; s.phase = LP_LEAF1; }
-    else if (PH == LP_LEAF1) { s.pl1 = pc; s.phase = LP_LEAF2; }
-    else if (PH == LP_LEAF2) {
+    if (PH == LP_LEAF) {
         // reference :516-531 for sorted points a < b (< c); every orientation it asks is the sign of (a, b, c)
         const int a = s.ia, b = s.ia + 1, c = s.ib;
-        const int e0 = lp_alloc(f, s, pr);
+        const Pt pa = lf_pt(f, a), pb = lf_pt(f, b), pc = lf_pt(f, c);
+        int sg = 0;
+        if (c != b) { sg = orient2d_sign(pa.x, pa.y, pb.x, pb.y, pc.x, pc.y); if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; } }
+        auto take = [&](LPair sp) -> int {
+            if (s.free_head != (int)GT_NIL) { const int e = s.free_head; s.free_head = sp.a.nxt; return e; }
+            if (s.bump >= f.cap_e) { s.err |= GT_ERR_POOL; return -1; }
+            return s.bump++;
+        };
+        const int e0 = take(spec);
         if (e0 < 0) { s.phase = LP_DONE; return; }
         const int h0 = 2 * e0;
         if (c == b) {                                     // two points: one edge, two single-entry rings
@@ -274,15 +265,13 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
             lp_next_node(f, s); return;
         }
         // further edges: the free list's links are read directly here (leaves only)
-        LPair g2 = pr; if (s.free_head != (int)GT_NIL) g2 = lf_pair(f, 2 * s.free_head);
-        const int e1 = lp_alloc(f, s, g2);
+        const int e1 = take(s.free_head != (int)GT_NIL ? lf_pair(f, 2 * s.free_head) : zero);
         if (e1 < 0) { s.phase = LP_DONE; return; }
         const int h1 = 2 * e1;
         const bool s1 = sg > 0, s2 = sg < 0;              // ccw(a,b,c), ccw(a,c,b)
         int h2 = -1;
         if (s1 || s2) {
-            LPair g3 = pr; if (s.free_head != (int)GT_NIL) g3 = lf_pair(f, 2 * s.free_head);
-            const int e2 = lp_alloc(f, s, g3);
+            const int e2 = take(s.free_head != (int)GT_NIL ? lf_pair(f, 2 * s.free_head) : zero);
             if (e2 < 0) { s.phase = LP_DONE; return; }
             h2 = 2 * e2;
         }
@@ -301,126 +290,170 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
             f.head[c] = (u16)(s1 ? (h2 ^ 1) : (h1 ^ 1));
         }
         lp_next_node(f, s);
+        return;
     }
-    // -------------------------------------------------------------- tangents (reference uct :373-406, lct :337-370)
-    else if (PH == LP_TINIT0) { s.hl = s.up ? hdA : (int)pr.a.prv; s.pli = pc; s.phase = LP_TINIT1; }     // upper: x -> first(x); lower: x -> pred(x, first(x))
-    else if (PH == LP_TINIT1) { s.hr = s.up ? (int)pr.a.prv : hdA; s.pri = pc; s.phase = LP_TAN_R; }      // upper: y -> pred(y, first(y)); lower: y -> first(y)
-    else if (PH == LP_TAN_R) {
-        if (res) { s.hr = s.up ? pr.b.prv : pr.b.nxt; s.ty = vc; s.pri = pc; }      // pred(rfast, y) / succ(rfast, y)
-        else s.phase = LP_TAN_L;
-    } else if (PH == LP_TAN_L) {
-        if (res) { s.hl = s.up ? pr.b.nxt : pr.b.prv; s.tx = vc; s.pli = pc; s.phase = LP_TAN_R; }
-        else if (s.up) {
-            s.ux = s.tx; s.uy = s.ty;
-            s.up = 0; s.tx = (s.ia + s.ib) / 2; s.ty = s.tx + 1; s.phase = LP_TINIT0;
-        } else {
+
+    if (PH == LP_TINIT) {
+        // both tangents start at the rightmost vertex of the left half and the leftmost of the right half
+        const int x = (s.ia + s.ib) / 2, y = x + 1;
+        const int hdx = f.head[x], hdy = f.head[y];
+        const LPair px = lf_pair(f, hdx), py = lf_pair(f, hdy);
+        const Pt qx = lf_pt(f, x), qy = lf_pt(f, y);
+        s.ux = x; s.uy = y; s.uHl = hdx; s.uHr = py.a.prv; s.pr1 = qx; s.pl1 = qy; s.uSub = 0;      // upper: x -> first(x), y -> pred(y, first(y))   (:378-381)
+        s.li = x; s.ri = y; s.lHl = px.a.prv; s.lHr = hdy; s.pli = qx; s.pri = qy; s.lSub = 0;      // lower: x -> pred(x, first(x)), y -> first(y)   (:342-345)
+        s.headL = hdx; s.headR = hdy;
+        s.phase = LP_TAN;
+        return;
+    }
+
+    if (PH == LP_TAN) {
+        // chain 0: upper tangent (uct :373-406), leftOf(p, x, y) = ccw(p, x, y); chain 1: lower (lct :337-370), rightOf(p, x, y) = ccw(p, y, x)
+        const bool a0 = s.uSub < 2, a1 = s.lSub < 2;
+        LPair p0 = zero, p1 = zero; Pt c0, c1; c0.x = c0.y = 0.0; c1 = c0; int hd1c = 0;
+        if (a0) p0 = lf_pair(f, s.uSub == 0 ? s.uHr : s.uHl);
+        if (a1) p1 = lf_pair(f, s.lSub == 0 ? s.lHr : s.lHl);
+        if (a0) c0 = lf_pt(f, p0.a.dst);
+        if (a1) { c1 = lf_pt(f, p1.a.dst); hd1c = f.head[p1.a.dst]; }
+        if (a0) {
+            int sg = orient2d_sign(c0.x, c0.y, s.pr1.x, s.pr1.y, s.pl1.x, s.pl1.y);
+            if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
+            if (s.uSub == 0) { if (sg > 0) { s.uHr = p0.b.prv; s.uy = p0.a.dst; s.pl1 = c0; } else s.uSub = 1; }        // pred(rfast, y)
+            else if (sg > 0) { s.uHl = p0.b.nxt; s.ux = p0.a.dst; s.pr1 = c0; s.uSub = 0; }                           // succ(lfast, x)
+            else s.uSub = 2;
+        }
+        if (a1) {
+            int sg = orient2d_sign(c1.x, c1.y, s.pri.x, s.pri.y, s.pli.x, s.pli.y);
+            if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
+            if (s.lSub == 0) { if (sg > 0) { s.lHr = p1.b.nxt; s.ri = p1.a.dst; s.pri = c1; s.headR = hd1c; } else s.lSub = 1; }   // succ(rfast, y)
+            else if (sg > 0) { s.lHl = p1.b.prv; s.li = p1.a.dst; s.pli = c1; s.headL = hd1c; s.lSub = 0; }                   // pred(lfast, x)
+            else s.lSub = 2;
+        }
+        if (s.uSub == 2 && s.lSub == 2) {
             // first cross edge = lower tangent: both ends take it in their hull gap (before "first")
-            s.li = s.tx; s.ri = s.ty; s.first_edge = 1; s.vR = 0; s.vL = 0;
-            s.phase = LP_F;                               // LP_F allocates the edge and queues the inserts
+            s.first_edge = 1;
+            lp_new_edge(f, s, spec, false, 0);
         }
+        return;
     }
-    // -------------------------------------------------------------- ring insertion (reference insertNode :210-245)
-    else if (PH == LP_INS_T0 || PH == LP_INS_SCAN) {
-        int at = -1, nx = -1, hd; bool newhead = false, placed = true;
-        if (PH == LP_INS_T0) {
-            hd = hdA; const int last = pr.a.prv;
-            if (!res) { if (s.iGap) { at = last; nx = hd; } else { at = s.iAt; nx = s.iNx; } }
-            else if (last == hd) { at = hd; nx = hd; newhead = true; }             // single-entry ring: right of all
-            else { s.iCur = last; s.iHd = hd; s.iLast = last; s.phase = LP_INS_SCAN; placed = false; }
-        } else {
-            hd = s.iHd;
-            if (res) {
-                const int cur = pr.a.prv;
-                if (cur == hd) { at = s.iLast; nx = hd; newhead = true; }
-                else { s.iCur = cur; placed = false; }
-            } else { at = s.iCur; nx = pr.a.nxt; }
+
+    if (PH == LP_INS || PH == LP_SCAN) {
+        // endpoint 0: parent li, in ri, half-edge h0; endpoint 1: parent ri, in li, half-edge h0^1.
+        // rightOf(in, parent, q) = ccw(in, q, parent)  (insertNode :216-224)
+        const bool a0 = (PH == LP_INS) || s.scan0, a1 = (PH == LP_INS) || s.scan1;
+        LPair p0 = zero, p1 = zero; Pt c0, c1; c0.x = c0.y = 0.0; c1 = c0;
+        if (a0) p0 = lf_pair(f, PH == LP_INS ? s.headL : s.cur0);
+        if (a1) p1 = lf_pair(f, PH == LP_INS ? s.headR : s.cur1);
+        if (a0) c0 = lf_pt(f, p0.a.dst);
+        if (a1) c1 = lf_pt(f, p1.a.dst);
+        if (a0) {
+            int sg = orient2d_sign(s.pri.x, s.pri.y, c0.x, c0.y, s.pli.x, s.pli.y);
+            if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
+            const bool res = sg > 0;
+            if (PH == LP_INS) {
+                const int hd = s.headL, last = p0.a.prv;
+                if (!res) { if (s.first_edge) lp_place(f, s, 0, s.li, s.ri, s.h0, last, hd, false, hd); else lp_place(f, s, 0, s.li, s.ri, s.h0, s.at0, s.nx0, false, hd); }
+                else if (last == hd) lp_place(f, s, 0, s.li, s.ri, s.h0, hd, hd, true, hd);          // single-entry ring: right of all
+                else { s.cur0 = last; s.hd0 = hd; s.last0 = last; s.scan0 = 1; }
+            } else if (res) {
+                const int cur = p0.a.prv;
+                if (cur == s.hd0) { lp_place(f, s, 0, s.li, s.ri, s.h0, s.last0, s.hd0, true, s.hd0); s.scan0 = 0; }
+                else s.cur0 = cur;
+            } else { lp_place(f, s, 0, s.li, s.ri, s.h0, s.cur0, p0.a.nxt, false, s.hd0); s.scan0 = 0; }
         }
-        if (placed) {
-            lf_set_nxt(f, at, s.iH); lf_set_prv(f, nx, s.iH); lf_set_rec(f, s.iH, s.iIN, nx, at);
-            if (newhead) f.head[s.iP] = (u16)s.iH;
-            const int newhd = newhead ? s.iH : hd;
-            if (s.iWhich == 0) {
-                s.at0 = at; s.nx0 = nx; s.headL = newhd;
-                s.iP = s.ri; s.iIN = s.li; s.iH = s.i1H; s.iAt = s.i1At; s.iNx = s.i1Nx; s.iGap = s.i1Gap; s.iWhich = 1;
-                s.phase = LP_INS_T0;
-            } else {
-                s.headR = newhd;
-                s.e = s.iH ^ 1;                            // li -> ri
-                s.hl1 = s.nx0;                             // succ(li, ri)
-                s.hr1 = at;                                // pred(ri, li)
-                if (s.li == s.ux && s.ri == s.uy) lp_next_node(f, s); else s.phase = LP_VR;
-            }
+        if (a1) {
+            int sg = orient2d_sign(s.pli.x, s.pli.y, c1.x, c1.y, s.pri.x, s.pri.y);
+            if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
+            const bool res = sg > 0;
+            const int h1 = s.h0 ^ 1;
+            if (PH == LP_INS) {
+                const int hd = s.headR, last = p1.a.prv;
+                if (!res) { if (s.first_edge) lp_place(f, s, 1, s.ri, s.li, h1, last, hd, false, hd); else lp_place(f, s, 1, s.ri, s.li, h1, s.at1, s.nx1, false, hd); }
+                else if (last == hd) lp_place(f, s, 1, s.ri, s.li, h1, hd, hd, true, hd);
+                else { s.cur1 = last; s.hd1 = hd; s.last1 = last; s.scan1 = 1; }
+            } else if (res) {
+                const int cur = p1.a.prv;
+                if (cur == s.hd1) { lp_place(f, s, 1, s.ri, s.li, h1, s.last1, s.hd1, true, s.hd1); s.scan1 = 0; }
+                else s.cur1 = cur;
+            } else { lp_place(f, s, 1, s.ri, s.li, h1, s.cur1, p1.a.nxt, false, s.hd1); s.scan1 = 0; }
         }
+        if (s.scan0 || s.scan1) s.phase = LP_SCAN;
+        else { s.first_edge = 0; lp_finish_connect(f, s); }
+        return;
     }
-    // -------------------------------------------------------------- merge step (reference :552-594)
-    else if (PH == LP_VR) {
-        s.r1 = vc; s.pr1 = pc; s.hr2 = pr.a.prv; s.t1_prv = pr.b.prv; s.t1_nxt = pr.b.nxt;
-        s.vR = res; s.phase = res ? LP_CR : LP_VL;
-    } else if (PH == LP_CR) {
-        if (res) {
-            // cutVerts(ri, r1): ri's ring loses hr1 (its next is the cross edge), r1's ring loses the twin
-            const int h = s.hr1, tw = h ^ 1;
-            lf_set_nxt(f, s.hr2, s.e ^ 1); lf_set_prv(f, s.e ^ 1, s.hr2);
-            if (s.headR == h) { s.headR = s.e ^ 1; f.head[s.ri] = (u16)(s.e ^ 1); }
-            lf_set_nxt(f, s.t1_prv, s.t1_nxt); lf_set_prv(f, s.t1_nxt, s.t1_prv);
-            if (hdA == tw) f.head[s.r1] = (u16)((s.t1_nxt == tw) ? GT_NIL : s.t1_nxt);
-            lp_free(f, s, h >> 1);
-            s.hr1 = s.hr2; s.r1 = vc; s.pr1 = pc; s.hr2 = pr.a.prv; s.t1_prv = pr.b.prv; s.t1_nxt = pr.b.nxt;
-        } else s.phase = LP_VL;
-    } else if (PH == LP_VL) {
-        s.l1 = vc; s.pl1 = pc; s.hl2 = pr.a.nxt; s.u1_prv = pr.b.prv; s.u1_nxt = pr.b.nxt;
-        s.vL = res; s.phase = res ? LP_CL : LP_F;
-    } else if (PH == LP_CL) {
-        if (res) {
-            const int h = s.hl1, tw = h ^ 1;
-            lf_set_nxt(f, s.e, s.hl2); lf_set_prv(f, s.hl2, s.e);
-            if (s.headL == h) { s.headL = s.hl2; f.head[s.li] = (u16)s.hl2; }
-            lf_set_nxt(f, s.u1_prv, s.u1_nxt); lf_set_prv(f, s.u1_nxt, s.u1_prv);
-            if (hdA == tw) f.head[s.l1] = (u16)((s.u1_nxt == tw) ? GT_NIL : s.u1_nxt);
-            lp_free(f, s, h >> 1);
-            s.hl1 = s.hl2; s.l1 = vc; s.pl1 = pc; s.hl2 = pr.a.nxt; s.u1_prv = pr.b.prv; s.u1_nxt = pr.b.nxt;
-        } else s.phase = LP_F;
-    } else if (PH == LP_F) {
-        const int ne = lp_alloc(f, s, pr);
-        if (ne < 0) { s.phase = LP_DONE; return; }
-        const int h0 = 2 * ne;
-        if (s.first_edge) {
-            s.first_edge = 0;
-            lp_queue_inserts(s, h0, 0, 0, 1, 0, 0, 1);
-            return;
+
+    if (PH == LP_V) {
+        // chain 0: leftOf(r1, li, ri) with r1 = pred(ri, li) (:555-556); chain 1: rightOf(l1, ri, li) with l1 = succ(li, ri) (:568-569)
+        const LPair p0 = lf_pair(f, s.hr1), p1 = lf_pair(f, s.hl1);
+        const Pt c0 = lf_pt(f, p0.a.dst), c1 = lf_pt(f, p1.a.dst);
+        s.hdR1 = f.head[p0.a.dst]; s.hdL1 = f.head[p1.a.dst];
+        int sg0 = orient2d_sign(c0.x, c0.y, s.pli.x, s.pli.y, s.pri.x, s.pri.y);
+        int sg1 = orient2d_sign(c1.x, c1.y, s.pli.x, s.pli.y, s.pri.x, s.pri.y);
+        if (sg0 == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg0 = 0; }
+        if (sg1 == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg1 = 0; }
+        s.r1 = p0.a.dst; s.pr1 = c0; s.hr2 = p0.a.prv; s.t1_prv = p0.b.prv; s.t1_nxt = p0.b.nxt;
+        s.l1 = p1.a.dst; s.pl1 = c1; s.hl2 = p1.a.nxt; s.u1_prv = p1.b.prv; s.u1_nxt = p1.b.nxt;
+        s.vR = sg0 > 0; s.vL = sg1 > 0; s.actR = s.vR; s.actL = s.vL;
+        if (s.actR || s.actL) s.phase = LP_C; else lp_decide(f, s, spec, false, 0);
+        return;
+    }
+
+    if (PH == LP_C) {
+        // chain 0: while incircle(r1, li, ri, r2): cutVerts(ri, r1) (:559-567); chain 1: while incircle(li, ri, l1, l2): cutVerts(li, l1) (:572-580)
+        const bool a0 = s.actR, a1 = s.actL;
+        LPair p0 = zero, p1 = zero; Pt c0, c1; c0.x = c0.y = 0.0; c1 = c0; int hn0 = 0, hn1 = 0;
+        if (a0) p0 = lf_pair(f, s.hr2);
+        if (a1) p1 = lf_pair(f, s.hl2);
+        if (a0) { c0 = lf_pt(f, p0.a.dst); hn0 = f.head[p0.a.dst]; }
+        if (a1) { c1 = lf_pt(f, p1.a.dst); hn1 = f.head[p1.a.dst]; }
+        bool freed = false; int prev_head = 0;
+        if (a0) {
+            const int r2 = p0.a.dst;
+            int sg = 0;
+            if (!(r2 == s.li || r2 == s.ri || r2 == s.r1))                          // a repeated point: exactly 0
+                sg = incircle_sign(s.pr1.x, s.pr1.y, s.pli.x, s.pli.y, s.pri.x, s.pri.y, c0.x, c0.y);
+            if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
+            if (sg > 0) {
+                // ri's ring loses hr1 (its next is the cross edge), r1's ring loses the twin
+                const int h = s.hr1, tw = h ^ 1;
+                lf_set_nxt(f, s.hr2, s.e ^ 1); lf_set_prv(f, s.e ^ 1, s.hr2);
+                if (s.headR == h) { s.headR = s.e ^ 1; f.head[s.ri] = (u16)(s.e ^ 1); }
+                lf_set_nxt(f, s.t1_prv, s.t1_nxt); lf_set_prv(f, s.t1_nxt, s.t1_prv);
+                if (s.hdR1 == tw) f.head[s.r1] = (u16)((s.t1_nxt == tw) ? GT_NIL : s.t1_nxt);
+                prev_head = s.free_head; freed = true; lp_free(f, s, h >> 1);
+                s.hr1 = s.hr2; s.r1 = r2; s.pr1 = c0; s.hr2 = p0.a.prv; s.t1_prv = p0.b.prv; s.t1_nxt = p0.b.nxt; s.hdR1 = hn0;
+            } else s.actR = 0;
         }
-        const bool go_left = !s.vR ? true : (!s.vL ? false : res);        // ties prefer the right candidate (:588-593)
-        if (go_left) {
-            // new edge l1 -> ri: at l1 after the edge back to the old li, at ri before the old cross edge
-            const int at0 = s.hl1 ^ 1, nx0 = s.u1_nxt, at1 = s.hr1, nx1 = s.e ^ 1;
-            s.li = s.l1; s.pli = s.pl1;
-            lp_queue_inserts(s, h0, at0, nx0, 0, at1, nx1, 0);
-        } else {
-            // new edge li -> r1: at li after the old cross edge, at r1 before the edge back to the old ri
-            const int at0 = s.e, nx0 = s.hl1, at1 = s.t1_prv, nx1 = s.hr1 ^ 1;
-            s.ri = s.r1; s.pri = s.pr1;
-            lp_queue_inserts(s, h0, at0, nx0, 0, at1, nx1, 0);
+        if (a1) {
+            const int l2 = p1.a.dst;
+            int sg = 0;
+            if (!(l2 == s.li || l2 == s.ri || l2 == s.l1))
+                sg = incircle_sign(s.pli.x, s.pli.y, s.pri.x, s.pri.y, s.pl1.x, s.pl1.y, c1.x, c1.y);
+            if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
+            if (sg > 0) {
+                const int h = s.hl1, tw = h ^ 1;
+                lf_set_nxt(f, s.e, s.hl2); lf_set_prv(f, s.hl2, s.e);
+                if (s.headL == h) { s.headL = s.hl2; f.head[s.li] = (u16)s.hl2; }
+                lf_set_nxt(f, s.u1_prv, s.u1_nxt); lf_set_prv(f, s.u1_nxt, s.u1_prv);
+                if (s.hdL1 == tw) f.head[s.l1] = (u16)((s.u1_nxt == tw) ? GT_NIL : s.u1_nxt);
+                prev_head = s.free_head; freed = true; lp_free(f, s, h >> 1);
+                s.hl1 = s.hl2; s.l1 = l2; s.pl1 = c1; s.hl2 = p1.a.nxt; s.u1_prv = p1.b.prv; s.u1_nxt = p1.b.nxt; s.hdL1 = hn1;
+            } else s.actL = 0;
         }
+        if (!(s.actR || s.actL)) lp_decide(f, s, spec, freed, prev_head);
+        return;
     }
 }
 
 // Generic entry (host emulation): dispatch on the frame's phase. Returns false when the tree is finished.
 GT_INLINE bool lpf_step(const LFrame& f, LState& s) {
     switch (s.phase) {
-    case LP_LEAF0: lpf_step_t<LP_LEAF0>(f, s); break;
-    case LP_LEAF1: lpf_step_t<LP_LEAF1>(f, s); break;
-    case LP_LEAF2: lpf_step_t<LP_LEAF2>(f, s); break;
-    case LP_TINIT0: lpf_step_t<LP_TINIT0>(f, s); break;
-    case LP_TINIT1: lpf_step_t<LP_TINIT1>(f, s); break;
-    case LP_TAN_R: lpf_step_t<LP_TAN_R>(f, s); break;
-    case LP_TAN_L: lpf_step_t<LP_TAN_L>(f, s); break;
-    case LP_INS_T0: lpf_step_t<LP_INS_T0>(f, s); break;
-    case LP_INS_SCAN: lpf_step_t<LP_INS_SCAN>(f, s); break;
-    case LP_VR: lpf_step_t<LP_VR>(f, s); break;
-    case LP_CR: lpf_step_t<LP_CR>(f, s); break;
-    case LP_VL: lpf_step_t<LP_VL>(f, s); break;
-    case LP_CL: lpf_step_t<LP_CL>(f, s); break;
-    case LP_F: lpf_step_t<LP_F>(f, s); break;
+    case LP_LEAF: lpf_step_t<LP_LEAF>(f, s); break;
+    case LP_TINIT: lpf_step_t<LP_TINIT>(f, s); break;
+    case LP_TAN: lpf_step_t<LP_TAN>(f, s); break;
+    case LP_INS: lpf_step_t<LP_INS>(f, s); break;
+    case LP_SCAN: lpf_step_t<LP_SCAN>(f, s); break;
+    case LP_V: lpf_step_t<LP_V>(f, s); break;
+    case LP_C: lpf_step_t<LP_C>(f, s); break;
     default: return false;
     }
     return s.phase != LP_DONE;

@@ -44,6 +44,13 @@ extern "C" {
 #define GTA_B200_E_ARG          (-3)
 #define GTA_B200_E_TOO_LARGE    (-4)   /* max_points does not fit the shared-memory kernel */
 
+/* Two kernels serve the batched calls: launches of at least `min_frames` frames run the lane-per-frame pipeline
+ * (pre-pass, phase-sorted state machine, area kernel: highest throughput, needs tens of thousands of frames in
+ * flight), smaller ones the fused one-CTA-per-frame kernel (lowest latency). Results are identical triangulations;
+ * areas agree to rounding of the summation tree. Default 32768 (environment GTA_B200_LPF overrides); 0 = never,
+ * 1 = always, negative = restore the default. Returns the previous value. */
+int gta_b200_set_batch_threshold(int min_frames);
+
 /* Largest max_points the batched shared-memory kernel accepts on this device. */
 int gta_b200_max_points(void);
 int gta_b200_device_count(void);
@@ -116,7 +123,7 @@ int gta_b200_triangulate_large(const double *points, int npoints, int device,
 double gta_b200_large_last_ms(void);
 
 /* Milliseconds the last gta_b200_tessellate_batch call on this thread spent in its kernels
- * (CUDA events on the launching streams), and the number of kernel launches it made. */
+ * (CUDA events on the launching streams), and the number of kernel launches the last batch / device call made. */
 double gta_b200_last_kernel_ms(void);
 int gta_b200_last_launches(void);
 

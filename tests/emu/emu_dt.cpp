@@ -122,8 +122,7 @@ int emu_triangulate_lpf(const double* points, int n, int* tri_out, long* iters_o
         auto put = [&](int i, uint32_t v) { w[i] = v; };
         switch (t.phase) {
 #define EMU_PH(P) case P: lpf_step_t<P>(f, t); ls_pack_mask<LsDirty<P>::mask>(t, put); break;
-        EMU_PH(LP_LEAF0) EMU_PH(LP_LEAF1) EMU_PH(LP_LEAF2) EMU_PH(LP_TINIT0) EMU_PH(LP_TINIT1) EMU_PH(LP_TAN_R) EMU_PH(LP_TAN_L)
-        EMU_PH(LP_INS_T0) EMU_PH(LP_INS_SCAN) EMU_PH(LP_VR) EMU_PH(LP_CR) EMU_PH(LP_VL) EMU_PH(LP_CL) EMU_PH(LP_F)
+        EMU_PH(LP_LEAF) EMU_PH(LP_TINIT) EMU_PH(LP_TAN) EMU_PH(LP_INS) EMU_PH(LP_SCAN) EMU_PH(LP_V) EMU_PH(LP_C)
 #undef EMU_PH
         default: return -4000;
         }

@@ -143,3 +143,56 @@ def test_device_resident_entry(gta):
     torch.cuda.synchronize()
     assert np.allclose(T.area.cpu().numpy(), want["area"], rtol=RTOL, atol=0)
     assert (T.status.cpu().numpy() == 0).all()
+
+
+@pytest.fixture()
+def lane_per_frame(gta):
+    """Force every launch through the lane-per-frame pipeline (normally only batches >= 32768 frames)."""
+    L = gta.lib()
+    old = L.gta_b200_set_batch_threshold(1)
+    yield
+    L.gta_b200_set_batch_threshold(old)
+
+
+@pytest.mark.parametrize("cfg,nfr", [(1, 600), (2, 300), (3, 150), (5, 150)])
+def test_lane_per_frame_configs_vs_oracle(gta, checker, lane_per_frame, cfg, nfr):
+    c = synth.config(cfg, nframes=nfr)
+    want = checker.tessellate(c["xyz"], c["box"], c["espace"], c["flags"], nthreads=0, want_corr=True)
+    r = gta.tessellate(c["xyz"], c["box"], c["espace"], c["flags"], want_corr=True, want_tri=True)
+    assert (r["status"] == 0).all()
+    assert _corr_equal(r["corr"], r["ncorr"], want["corr"])
+    assert np.array_equal(r["areabox"], want["areabox"])
+    assert np.allclose(r["area"], want["area"], rtol=RTOL, atol=0)
+    if cfg == 2:
+        assert np.allclose(r["area2d"], want["area2d"], rtol=RTOL, atol=0)
+    for f in range(0, nfr, max(1, nfr // 30)):
+        p = np.concatenate([c["xyz"][f, :, :2], want["corr"][f, :int(want["ncorr"][f]), :2]])
+        tri, _ = checker.triangulate(p)
+        assert np.array_equal(r["tri"][f], tri), (cfg, f)            # the reference's triangles in its emission order
+
+
+def test_lane_per_frame_raw_sets_and_status(gta, checker, lane_per_frame, golden):
+    g = golden["dtriangulate"]
+    for k in g.files:
+        if not k.startswith("pts_") or len(g[k]) < 2:
+            continue
+        tris, st = gta.triangulate(np.stack([g[k]] * 3))
+        assert (st == 0).all(), k
+        for t in tris:
+            assert np.array_equal(t, g["tri_" + k[4:]]), k
+    rng = np.random.default_rng(33)
+    for n in (2, 3, 4, 5, 9, 33, 200, 1156, 3000):
+        p = rng.random((2, n, 2)) * 7
+        tris, st = gta.triangulate(p)
+        assert (st == 0).all(), n
+        for f in range(2):
+            assert np.array_equal(tris[f], checker.triangulate(p[f])[0]), n
+    # rejected frames keep their status and NaN area, the others are unaffected
+    c = synth.config(1, nframes=40)
+    c["xyz"][7, 3] = c["xyz"][7, 9]
+    c["xyz"][11, 5, 0] = -1.0
+    r = gta.tessellate(c["xyz"], c["box"], c["espace"], c["flags"])
+    assert r["status"][7] & 2 and r["status"][11] & 16 and np.isnan(r["area"][7]) and np.isnan(r["area"][11])
+    ok = np.ones(40, bool); ok[[7, 11]] = False
+    want = checker.tessellate(c["xyz"][ok], c["box"][ok], c["espace"], c["flags"])
+    assert np.allclose(r["area"][ok], want["area"], rtol=RTOL, atol=0)
