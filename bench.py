@@ -37,7 +37,11 @@ TRI_PER_FRAME = 2178           # 2(n-1) - h with n = 1156, h = 132 (reference de
 ALG_BYTES_PER_FRAME = NATOMS * 24 + 72 + 16      # coordinates + box in, 2 reals out
 ALG_FLOP_PER_FRAME = 203.6e3                      # SURVEY.md §8d implementation-independent lower bound
 FP64_PEAK_TFLOPS_NOMINAL = 37.2                   # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz (not in MEASURED_PEAKS.json)
-NCU_DRAM_BYTES_PER_FRAME = 26254     # dram read+write per frame, ncu --set full capture of 6,000 frames (profiles/r1_tessellate_kernel_ncu.txt)
+# dram read+write per frame from ncu --set full captures (profiles/): fused CTA-per-frame kernel (6,000 frames) and the
+# lane-per-frame pipeline (pre-pass + lpf_wave_kernel + area kernel, 40,000 frames; its per-frame workspace lives in HBM)
+NCU_DRAM_BYTES_PER_FRAME_FUSED = 26254
+NCU_DRAM_BYTES_PER_FRAME_LPF = 1137000
+LPF_MIN_FRAMES = 32768               # launches at least this large use the lane-per-frame pipeline (gta_b200_set_batch_threshold)
 WORKLOAD = "cfg3: 2,048-lipid bilayer leaflet, 1,024 atoms/frame, -corr -espace 0.8, 3-D area"
 
 
@@ -254,6 +258,7 @@ def run_native(args):
         e2e_v = frames_all / (e2e_ms / 1e3)
         ach = ALG_BYTES_PER_FRAME * F / (kern_ms / 1e3) / 1e9                 # GB/s of algorithmic bytes per launch
         fl = ALG_FLOP_PER_FRAME * F / (kern_ms / 1e3) / 1e12
+        lpf = F >= LPF_MIN_FRAMES
         thr, smem, fps = (g.api.C.c_int(), g.api.C.c_size_t(), g.api.C.c_int())
         L.gta_b200_launch_shape(max_points, NATOMS, g.api.C.byref(thr), g.api.C.byref(smem), g.api.C.byref(fps))
         line = {
@@ -263,17 +268,21 @@ def run_native(args):
             "mtriangles_per_s": value * TRI_PER_FRAME / 1e6,
             "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": F, "natoms": NATOMS, "points_per_frame": 1156,
                        "l2": "inputs larger than L2 (%.2f GB of coordinates per step per GPU)" % (F * NATOMS * 24 / 1e9),
-                       "threads_per_frame": thr.value, "smem_bytes_per_frame": smem.value, "frames_per_sm": fps.value,
+                       "path": ("lane per frame: pre-pass + phase-sorted state machine (one lane = one frame, workspace in HBM) + area kernel"
+                                if lpf else "fused kernel, one CTA per frame in shared memory"),
+                       "fused_kernel_shape": {"threads_per_frame": thr.value, "smem_bytes_per_frame": smem.value, "frames_per_sm": fps.value},
                        "parallelism": "frames sharded over %d GPU(s), no collective" % world},
             "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": F * (NATOMS * 24 + 24),
                     "d2h_bytes_per_step": F * (3 * 8 + 3 * 4), "timing": "host wall clock around the synchronous C-ABI call",
                     "streams": args.streams},
             "gpu_launches": launches_dev + launches_e2e,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                         "traffic": NCU_DRAM_BYTES_PER_FRAME * F / 1e9, "traffic_unit": "GB per launch (ncu dram bytes per frame x frames per launch)",
-                         "peak_source": pk_src, "kernel": "gt::tessellate_kernel",
+                         "traffic": (NCU_DRAM_BYTES_PER_FRAME_LPF if lpf else NCU_DRAM_BYTES_PER_FRAME_FUSED) * F / 1e9,
+                         "traffic_unit": "GB per step (ncu dram bytes per frame x frames per step)",
+                         "peak_source": pk_src,
+                         "kernel": "gt::lpf_wave_kernel (91% of the step; + pre-pass gt::tessellate_kernel 6%, gt::lpf_area_kernel 2%)" if lpf else "gt::tessellate_kernel",
                          "kernel_ms_per_launch": kern_ms, "alg_bytes_per_frame": ALG_BYTES_PER_FRAME,
-                         "note": "latency/dependency bound (sequential merge walks in shared memory); see DESIGN.md"},
+                         "note": "latency / issue bound (dependent pointer-chasing loads, one predicate per iteration); see DESIGN.md section 5"},
             "roofline_fp64": {"achieved": fl, "peak": FP64_PEAK_TFLOPS_NOMINAL, "unit": "TFLOP/s", "frac": fl / FP64_PEAK_TFLOPS_NOMINAL,
                               "peak_source": "nominal", "alg_flop_per_frame": ALG_FLOP_PER_FRAME},
             "clocks": clk,

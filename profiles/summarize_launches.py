@@ -7,8 +7,10 @@ ki, vi, gi, bi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index(
 agg = OrderedDict()
 for r in rows:
     name = re.sub(r"<.*", "", r[ki].replace("void ", ""))[:60]
-    if "tessellate_kernel" in r[ki]:
-        name = "gt::tessellate_kernel" + re.search(r"<[^>]*>", r[ki]).group(0) + " grid" + r[gi] + " block" + r[bi]
+    m = re.search(r"gt::(tessellate_kernel|lpf_wave_kernel|lpf_area_kernel|large_\w+)", r[ki])
+    if m:
+        t = re.search(r"<[^>]*>", r[ki])
+        name = "gt::" + m.group(1) + (t.group(0) if t else "") + " grid" + r[gi] + " block" + r[bi]
     a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += float(r[vi].replace(",", ""))
 tot = sum(a[1] for a in agg.values())
 print("%-90s %6s %14s %7s" % ("kernel", "count", "total_ns", "share"))
