@@ -44,88 +44,100 @@ __device__ __noinline__ int lpf_wave_phase(uint32_t* st, int SLOTS, int sl, Pt* 
 }
 
 // Phase-sorted ("wavefront") scheduler. A block keeps SLOTS frames in flight; their packed states live in
-// shared memory (word-major: st[w * SLOTS + slot]). Every round the live slots are binned by phase (one pass,
-// one barrier) and the warps take tickets for chunks of up to 32 slots that are in the SAME phase and run that
-// phase's straight-line step for them: no divergence between lanes, 32 independent dependent-load chains in
-// flight per warp. A slot whose frame is finished takes the next frame of the batch from a global counter.
+// shared memory (word-major: st[w * SLOTS + slot]) and every slot is filed in the bin of its phase. Every round
+// the warps take tickets for chunks of up to 32 slots that are in the SAME phase, run that phase's straight-line
+// step for them and file each slot under its new phase for the next round (double-buffered bins): no divergence
+// between lanes, 64 dependent-load chains in flight per warp. A slot whose frame is finished goes to the
+// "needs a frame" bin and takes the next frame of the batch from a global counter.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p, const int SLOTS) {
     extern __shared__ __align__(16) unsigned char lsm[];
+    constexpr int NB = LP_DONE + 1;                                        // one bin per phase + one for slots that need a frame
     uint32_t* st = reinterpret_cast<uint32_t*>(lsm);                       // [LS_WORDS][SLOTS]
     int* slot_fr = reinterpret_cast<int*>(st + (size_t)LS_WORDS * SLOTS);  // [SLOTS] frame of the slot
     u16* slot_n = reinterpret_cast<u16*>(slot_fr + SLOTS);                 // [SLOTS] its point count
-    u16* bins = slot_n + SLOTS;                                            // [LP_DONE][SLOTS] slots of each phase
-    int* cnt = reinterpret_cast<int*>(bins + (size_t)LP_DONE * SLOTS + ((LP_DONE * SLOTS) & 1));   // [2][16] slots per phase (double buffered)
+    u16* bins = slot_n + SLOTS;                                            // [2][NB][SLOTS] slots of each phase, this round / next round
+    int* cnt = reinterpret_cast<int*>(bins + 2 * (size_t)NB * SLOTS);      // [2][16]
     int* ctl = cnt + 32;                                                   // [0] batch exhausted, [1], [2] chunk tickets (double buffered)
     const int tid = threadIdx.x, lane = tid & 31;
 
-    for (int sl = tid; sl < SLOTS; sl += THREADS) { slot_fr[sl] = -1; st[sl] = LP_DONE; }
     if (tid < 32) cnt[tid] = 0;
     if (tid < 3) ctl[tid] = 0;
     __syncthreads();
+    // every slot starts in the "needs a frame" bin
+    for (int sl = tid; sl < SLOTS; sl += THREADS) bins[(size_t)LP_DONE * SLOTS + sl] = (u16)sl;
+    if (tid == 0) cnt[LP_DONE] = SLOTS;
+    __syncthreads();
 
     for (int round = 0;; ++round) {
-        int* c_now = cnt + 16 * (round & 1);
-        // ---- refill finished / empty slots; bin every live slot by phase
+        const int b = round & 1;
+        const int* c_now = cnt + 16 * b;
+        int* c_next = cnt + 16 * (b ^ 1);
+        const u16* bin_now = bins + (size_t)b * NB * SLOTS;
+        u16* bin_next = bins + (size_t)(b ^ 1) * NB * SLOTS;
+        // ---- chunk table, computed by every warp for itself: lane q holds bin q's count and first chunk
         const bool exhausted = ctl[0] != 0;
-        for (int sl = tid; sl < SLOTS; sl += THREADS) {
-            int ph = (int)(st[sl] & 15u);
-            if (ph == LP_DONE && !exhausted) {
-                for (;;) {
-                    const int fr = (int)atomicAdd(p.counter, 1u);
-                    if (fr >= p.nframes) { ctl[0] = 1; break; }
-                    if (p.ws.st[fr] != 0) continue;
-                    LFrame f = lpf_frame(p.ws, fr);
-                    if (f.n < 2) continue;
-                    LState s = {};
-                    lp_begin(f, s);
-                    if (s.phase == LP_DONE) continue;
-                    ls_pack(s, [&](int w, uint32_t v) { st[w * SLOTS + sl] = v; });
-                    slot_fr[sl] = fr; slot_n[sl] = (u16)f.n;
-                    ph = s.phase;
-                    break;
-                }
-            }
-            if (ph != LP_DONE) bins[ph * SLOTS + atomicAdd(&c_now[ph], 1)] = (u16)sl;
-        }
-        if (tid < 16) cnt[16 * ((round + 1) & 1) + tid] = 0;              // next round's counters
-        if (tid == 0) ctl[1 + ((round + 1) & 1)] = 0;                     // and its chunk tickets
-        __syncthreads();
-        // ---- chunk table, computed by every warp for itself: lane q holds phase q's count and first chunk
-        const int myc = lane < LP_DONE ? c_now[lane] : 0;
+        int myc = lane < NB ? c_now[lane] : 0;
+        if (lane == LP_DONE && exhausted) myc = 0;                        // nothing left to fetch: empty slots stay empty
         int incl = (myc + 31) >> 5;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
         const int first_chunk = incl - ((myc + 31) >> 5);
         const int nchunks = __shfl_sync(0xffffffffu, incl, 31);
         if (nchunks == 0) break;                                          // nothing in flight and nothing left to fetch
-        // ---- one iteration for every live slot: a warp takes the next chunk of <= 32 slots that share a phase
-        int* ticket = &ctl[1 + (round & 1)];
+        // ---- one iteration for every live slot: a warp takes the next chunk of <= 32 slots that share a phase and files
+        // every slot under its new phase for the next round
+        int* ticket = &ctl[1 + b];
         for (;;) {
             int c = 0;
             if (lane == 0) c = atomicAdd(ticket, 1);
             c = __shfl_sync(0xffffffffu, c, 0);
             if (c >= nchunks) break;
-            const int ph = __popc(__ballot_sync(0xffffffffu, lane < LP_DONE && first_chunk <= c)) - 1;    // warp-uniform
-            const int idx = (c - __shfl_sync(0xffffffffu, first_chunk, ph)) * 32 + lane;
-            const int nph = __shfl_sync(0xffffffffu, myc, ph);
+            // first_chunk is non-decreasing over the bins: the last bin that starts at or before c owns chunk c
+            const int bin = __popc(__ballot_sync(0xffffffffu, lane < NB && first_chunk <= c)) - 1;    // warp-uniform
+            const int idx = (c - __shfl_sync(0xffffffffu, first_chunk, bin)) * 32 + lane;
+            const int nph = __shfl_sync(0xffffffffu, myc, bin);
             if (idx < nph) {
-                const int sl = bins[ph * SLOTS + idx];
-                const int fr = slot_fr[sl];
-                Pt* fpt = p.ws.pt + (size_t)fr * p.ws.cap; LRec* frec = p.ws.rec + (size_t)fr * 2 * (size_t)p.ws.cap_e;
-                u16* fhead = p.ws.head + (size_t)fr * p.ws.cap; const int fn = slot_n[sl], fce = p.ws.cap_e;
-                uint32_t* eo = p.ws.err + fr;
-                switch (ph) {                                             // every lane of the chunk is in phase ph
-                case LP_LEAF: lpf_wave_phase<LP_LEAF>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                case LP_TINIT: lpf_wave_phase<LP_TINIT>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                case LP_TAN: lpf_wave_phase<LP_TAN>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                case LP_INS: lpf_wave_phase<LP_INS>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                case LP_SCAN: lpf_wave_phase<LP_SCAN>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                case LP_V: lpf_wave_phase<LP_V>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                default: lpf_wave_phase<LP_C>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                const int sl = bin_now[(size_t)bin * SLOTS + idx];
+                int next = LP_DONE;
+                if (bin == LP_DONE) {
+                    // the slot's frame is finished (or it never had one): take the next frame of the batch that passed the pre-pass
+                    for (;;) {
+                        const int fr = (int)atomicAdd(p.counter, 1u);
+                        if (fr >= p.nframes) { ctl[0] = 1; break; }
+                        if (p.ws.st[fr] != 0) continue;
+                        LFrame f = lpf_frame(p.ws, fr);
+                        if (f.n < 2) continue;
+                        LState s = {};
+                        lp_begin(f, s);
+                        if (s.phase == LP_DONE) continue;
+                        ls_pack(s, [&](int w, uint32_t v) { st[w * SLOTS + sl] = v; });
+                        slot_fr[sl] = fr; slot_n[sl] = (u16)f.n;
+                        next = s.phase;
+                        break;
+                    }
+                } else {
+                    const int fr = slot_fr[sl];
+                    Pt* fpt = p.ws.pt + (size_t)fr * p.ws.cap; LRec* frec = p.ws.rec + (size_t)fr * 2 * (size_t)p.ws.cap_e;
+                    u16* fhead = p.ws.head + (size_t)fr * p.ws.cap; const int fn = slot_n[sl], fce = p.ws.cap_e;
+                    uint32_t* eo = p.ws.err + fr;
+                    switch (bin) {                                        // every lane of the chunk is in this phase
+                    case LP_LEAF: next = lpf_wave_phase<LP_LEAF>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                    case LP_TINIT: next = lpf_wave_phase<LP_TINIT>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                    case LP_TAN: next = lpf_wave_phase<LP_TAN>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                    case LP_INS: next = lpf_wave_phase<LP_INS>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                    case LP_SCAN: next = lpf_wave_phase<LP_SCAN>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                    case LP_V: next = lpf_wave_phase<LP_V>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                    default: next = lpf_wave_phase<LP_C>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                    }
                 }
+                bin_next[(size_t)next * SLOTS + atomicAdd(&c_next[next], 1)] = (u16)sl;
             }
         }
+        __syncthreads();
+        // this round's counters and tickets become the next-but-one round's
+        if (tid < 16) cnt[16 * b + tid] = 0;
+        if (tid == 0) ctl[1 + b] = 0;
         __syncthreads();
     }
 }
