@@ -57,12 +57,12 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
     int* slot_fr = reinterpret_cast<int*>(st + (size_t)LS_WORDS * SLOTS);  // [SLOTS] frame of the slot
     u16* slot_n = reinterpret_cast<u16*>(slot_fr + SLOTS);                 // [SLOTS] its point count
     u16* bins = slot_n + SLOTS;                                            // [2][NB][SLOTS] slots of each phase, this round / next round
-    int* cnt = reinterpret_cast<int*>(bins + 2 * (size_t)NB * SLOTS);      // [2][16]
-    int* ctl = cnt + 32;                                                   // [0] batch exhausted, [1], [2] chunk tickets (double buffered)
+    int* cnt = reinterpret_cast<int*>(bins + 2 * (size_t)NB * SLOTS);      // [3][16] slots per bin: this round / next round / being cleared
+    int* ctl = cnt + 48;                                                   // [0] batch exhausted, [1..3] chunk tickets (same rotation)
     const int tid = threadIdx.x, lane = tid & 31;
 
-    if (tid < 32) cnt[tid] = 0;
-    if (tid < 3) ctl[tid] = 0;
+    if (tid < 48) cnt[tid] = 0;
+    if (tid < 4) ctl[tid] = 0;
     __syncthreads();
     // every slot starts in the "needs a frame" bin
     for (int sl = tid; sl < SLOTS; sl += THREADS) bins[(size_t)LP_DONE * SLOTS + sl] = (u16)sl;
@@ -70,9 +70,12 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
     __syncthreads();
 
     for (int round = 0;; ++round) {
-        const int b = round & 1;
-        const int* c_now = cnt + 16 * b;
-        int* c_next = cnt + 16 * (b ^ 1);
+        const int b = round & 1, r3 = round % 3, r3n = (round + 1) % 3, r3c = (round + 2) % 3;
+        const int* c_now = cnt + 16 * r3;
+        int* c_next = cnt + 16 * r3n;
+        // the third set of counters / tickets was last read a round ago: clear it for the round after this one
+        if (tid < 16) cnt[16 * r3c + tid] = 0;
+        if (tid == 0) ctl[1 + r3c] = 0;
         const u16* bin_now = bins + (size_t)b * NB * SLOTS;
         u16* bin_next = bins + (size_t)(b ^ 1) * NB * SLOTS;
         // ---- chunk table, computed by every warp for itself: lane q holds bin q's count and first chunk
@@ -87,7 +90,7 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
         if (nchunks == 0) break;                                          // nothing in flight and nothing left to fetch
         // ---- one iteration for every live slot: a warp takes the next chunk of <= 32 slots that share a phase and files
         // every slot under its new phase for the next round
-        int* ticket = &ctl[1 + b];
+        int* ticket = &ctl[1 + r3];
         for (;;) {
             int c = 0;
             if (lane == 0) c = atomicAdd(ticket, 1);
@@ -134,10 +137,6 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
                 bin_next[(size_t)next * SLOTS + atomicAdd(&c_next[next], 1)] = (u16)sl;
             }
         }
-        __syncthreads();
-        // this round's counters and tickets become the next-but-one round's
-        if (tid < 16) cnt[16 * b + tid] = 0;
-        if (tid == 0) ctl[1 + b] = 0;
         __syncthreads();
     }
 }

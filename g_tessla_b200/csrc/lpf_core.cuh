@@ -345,6 +345,15 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
         if (a1) p1 = lf_pair(f, PH == LP_INS ? s.headR : s.cur1);
         if (a0) c0 = lf_pt(f, p0.a.dst);
         if (a1) c1 = lf_pt(f, p1.a.dst);
+        // LP_INS also fetches the ring's LAST entry (prv of first): when the new neighbour is right of "first" the
+        // reference's clockwise scan starts there (:217-219) and usually stops there, so its first test is taken in
+        // the same iteration and LP_SCAN only runs when that test holds too
+        LPair q0 = zero, q1 = zero; Pt d0 = c0, d1 = c1;
+        const bool m0 = PH == LP_INS && (int)p0.a.prv != s.headL, m1 = PH == LP_INS && (int)p1.a.prv != s.headR;
+        if (m0) q0 = lf_pair(f, p0.a.prv);
+        if (m1) q1 = lf_pair(f, p1.a.prv);
+        if (m0) d0 = lf_pt(f, q0.a.dst);
+        if (m1) d1 = lf_pt(f, q1.a.dst);
         if (a0) {
             int sg = orient2d_sign(s.pri.x, s.pri.y, c0.x, c0.y, s.pli.x, s.pli.y);
             if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
@@ -353,7 +362,13 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
                 const int hd = s.headL, last = p0.a.prv;
                 if (!res) { if (s.first_edge) lp_place(f, s, 0, s.li, s.ri, s.h0, last, hd, false, hd); else lp_place(f, s, 0, s.li, s.ri, s.h0, s.at0, s.nx0, false, hd); }
                 else if (last == hd) lp_place(f, s, 0, s.li, s.ri, s.h0, hd, hd, true, hd);          // single-entry ring: right of all
-                else { s.cur0 = last; s.hd0 = hd; s.last0 = last; s.scan0 = 1; }
+                else {
+                    int sl = orient2d_sign(s.pri.x, s.pri.y, d0.x, d0.y, s.pli.x, s.pli.y);
+                    if (sl == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sl = 0; }
+                    if (!(sl > 0)) lp_place(f, s, 0, s.li, s.ri, s.h0, last, hd, false, hd);          // not right of "last": goes after it
+                    else if ((int)q0.a.prv == hd) lp_place(f, s, 0, s.li, s.ri, s.h0, last, hd, true, hd);      // right of all: new "first"
+                    else { s.cur0 = q0.a.prv; s.hd0 = hd; s.last0 = last; s.scan0 = 1; }
+                }
             } else if (res) {
                 const int cur = p0.a.prv;
                 if (cur == s.hd0) { lp_place(f, s, 0, s.li, s.ri, s.h0, s.last0, s.hd0, true, s.hd0); s.scan0 = 0; }
@@ -369,7 +384,13 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
                 const int hd = s.headR, last = p1.a.prv;
                 if (!res) { if (s.first_edge) lp_place(f, s, 1, s.ri, s.li, h1, last, hd, false, hd); else lp_place(f, s, 1, s.ri, s.li, h1, s.at1, s.nx1, false, hd); }
                 else if (last == hd) lp_place(f, s, 1, s.ri, s.li, h1, hd, hd, true, hd);
-                else { s.cur1 = last; s.hd1 = hd; s.last1 = last; s.scan1 = 1; }
+                else {
+                    int sl = orient2d_sign(s.pli.x, s.pli.y, d1.x, d1.y, s.pri.x, s.pri.y);
+                    if (sl == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sl = 0; }
+                    if (!(sl > 0)) lp_place(f, s, 1, s.ri, s.li, h1, last, hd, false, hd);
+                    else if ((int)q1.a.prv == hd) lp_place(f, s, 1, s.ri, s.li, h1, last, hd, true, hd);
+                    else { s.cur1 = q1.a.prv; s.hd1 = hd; s.last1 = last; s.scan1 = 1; }
+                }
             } else if (res) {
                 const int cur = p1.a.prv;
                 if (cur == s.hd1) { lp_place(f, s, 1, s.ri, s.li, h1, s.last1, s.hd1, true, s.hd1); s.scan1 = 0; }
