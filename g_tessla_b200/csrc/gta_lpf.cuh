@@ -38,7 +38,7 @@ __device__ __noinline__ int lpf_wave_phase(uint32_t* st, int SLOTS, int sl, Pt* 
     LState s;
     ls_unpack(s, [&](int w) { return st[w * SLOTS + sl]; });
     lpf_step_t<PH>(f, s);
-    ls_pack_mask<LsDirty<PH>::mask>(s, [&](int w, uint32_t v) { st[w * SLOTS + sl] = v; });
+    ls_writeback<PH>(s, [&](int w, uint32_t v) { st[w * SLOTS + sl] = v; });
     if (s.phase == LP_DONE) *err_out = s.err;
     return s.phase;
 }

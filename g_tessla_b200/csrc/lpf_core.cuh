@@ -141,17 +141,25 @@ GT_INLINE void ls_unpack(LState& s, Get&& get) {
 constexpr unsigned long long LS_M_NODE = LS_W(0) | LS_W(1);
 constexpr unsigned long long LS_M_QUEUE = LS_W(0) | LS_W(2) | LS_W(5) | LS_W(7) | LS_W(8) | LS_W(14) | LS_W(15) | LS_W(16) | LS_PT(21) | LS_PT(25);   // lp_decide
 constexpr unsigned long long LS_M_FINISH = LS_M_NODE | LS_W(7) | LS_W(8) | LS_W(11);                                                                  // lp_finish_connect
-template <int PH> struct LsDirty { static constexpr unsigned long long mask = ~0ull; };
-template <> struct LsDirty<LP_LEAF> { static constexpr unsigned long long mask = LS_W(2) | LS_M_NODE; };
-template <> struct LsDirty<LP_TINIT> { static constexpr unsigned long long mask = LS_W(0) | LS_W(1) | LS_W(3) | LS_W(4) | LS_W(5) | LS_W(6) | LS_W(7) | LS_W(8) | LS_PT(21) | LS_PT(25) | LS_PT(29) | LS_PT(33); };
-template <> struct LsDirty<LP_TAN> { static constexpr unsigned long long mask = LS_W(1) | LS_W(3) | LS_W(4) | LS_W(5) | LS_W(6) | LS_W(7) | LS_W(8) | LS_PT(21) | LS_PT(25) | LS_PT(29) | LS_PT(33) | LS_M_QUEUE; };
-template <> struct LsDirty<LP_INS> { static constexpr unsigned long long mask = LS_W(0) | LS_W(7) | LS_W(8) | LS_W(17) | LS_W(18) | LS_W(19) | LS_W(20) | LS_M_FINISH; };
-template <> struct LsDirty<LP_SCAN> { static constexpr unsigned long long mask = LsDirty<LP_INS>::mask; };
-template <> struct LsDirty<LP_V> { static constexpr unsigned long long mask = LS_W(9) | LS_W(10) | LS_W(11) | LS_W(12) | LS_W(13) | LS_W(14) | LS_PT(29) | LS_PT(33) | LS_M_QUEUE; };
-template <> struct LsDirty<LP_C> { static constexpr unsigned long long mask = LsDirty<LP_V>::mask; };
+// `mask` is written back after every iteration of the phase; `tail` only when the iteration changed the phase (it then
+// also queued a new edge or finished one: more fields move).
+template <int PH> struct LsDirty { static constexpr unsigned long long mask = ~0ull, tail = 0; };
+template <> struct LsDirty<LP_LEAF> { static constexpr unsigned long long mask = LS_W(2) | LS_M_NODE, tail = 0; };
+template <> struct LsDirty<LP_TINIT> { static constexpr unsigned long long mask = LS_W(0) | LS_W(1) | LS_W(3) | LS_W(4) | LS_W(5) | LS_W(6) | LS_W(7) | LS_W(8) | LS_PT(21) | LS_PT(25) | LS_PT(29) | LS_PT(33), tail = 0; };
+template <> struct LsDirty<LP_TAN> { static constexpr unsigned long long mask = LS_W(0) | LS_W(1) | LS_W(3) | LS_W(4) | LS_W(5) | LS_W(6) | LS_W(7) | LS_W(8) | LS_PT(21) | LS_PT(25) | LS_PT(29) | LS_PT(33), tail = LS_M_QUEUE; };
+template <> struct LsDirty<LP_INS> { static constexpr unsigned long long mask = LS_W(0) | LS_W(7) | LS_W(8) | LS_W(17) | LS_W(18) | LS_W(19) | LS_W(20), tail = LS_M_FINISH; };
+template <> struct LsDirty<LP_SCAN> { static constexpr unsigned long long mask = LsDirty<LP_INS>::mask, tail = LS_M_FINISH; };
+template <> struct LsDirty<LP_V> { static constexpr unsigned long long mask = LS_W(0) | LS_W(9) | LS_W(10) | LS_W(11) | LS_W(12) | LS_W(13) | LS_W(14) | LS_PT(29) | LS_PT(33), tail = LS_M_QUEUE; };
+template <> struct LsDirty<LP_C> { static constexpr unsigned long long mask = LS_W(0) | LS_W(2) | LS_W(7) | LS_W(8) | LS_W(9) | LS_W(10) | LS_W(11) | LS_W(12) | LS_W(13) | LS_W(14) | LS_PT(29) | LS_PT(33), tail = LS_M_QUEUE; };
 template <unsigned long long MASK, class Put>
 GT_INLINE void ls_pack_mask(const LState& s, Put&& put) {
     ls_pack(s, [&](int i, uint32_t v) { if ((MASK >> i) & 1ull) put(i, v); });
+}
+// write-back after one iteration of phase PH
+template <int PH, class Put>
+GT_INLINE void ls_writeback(const LState& s, Put&& put) {
+    ls_pack_mask<LsDirty<PH>::mask>(s, put);
+    if (s.phase != PH) ls_pack_mask<LsDirty<PH>::tail & ~LsDirty<PH>::mask>(s, put);
 }
 
 // ---------------------------------------------------------------- helpers

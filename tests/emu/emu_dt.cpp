@@ -121,7 +121,7 @@ int emu_triangulate_lpf(const double* points, int n, int* tri_out, long* iters_o
         ls_unpack(t, [&](int i) { return w[i]; });
         auto put = [&](int i, uint32_t v) { w[i] = v; };
         switch (t.phase) {
-#define EMU_PH(P) case P: lpf_step_t<P>(f, t); ls_pack_mask<LsDirty<P>::mask>(t, put); break;
+#define EMU_PH(P) case P: lpf_step_t<P>(f, t); ls_writeback<P>(t, put); break;
         EMU_PH(LP_LEAF) EMU_PH(LP_TINIT) EMU_PH(LP_TAN) EMU_PH(LP_INS) EMU_PH(LP_SCAN) EMU_PH(LP_V) EMU_PH(LP_C)
 #undef EMU_PH
         default: return -4000;
