@@ -177,8 +177,8 @@ int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st) {
         // spread the batch over every SM: fewer slots per block shorten the round when the batch is small
         const int blocks = std::max(1, std::min(sms, (p.nframes + 63) / 64));
         int S = (p.nframes + blocks - 1) / blocks;
-        S = std::max(64, std::min((S + 31) & ~31, std::min(slots, 1152)));
-        const size_t smem = (size_t)gt::LS_WORDS * S * 4 + (size_t)S * 4 + (size_t)S * 2 + 2 * (size_t)(gt::LP_DONE + 1) * S * 2 + (48 + 4) * 4 + 64;
+        S = std::max(64, std::min((S + 31) & ~31, std::min(slots, gt::LPF_STRIDE)));
+        const size_t smem = (size_t)gt::LS_WORDS * gt::LPF_STRIDE * 4 + (size_t)S * 4 + (size_t)S * 2 + 2 * (size_t)(gt::LP_DONE + 1) * S * 2 + (48 + 4) * 4 + 64;
         auto go = [&](auto kern, int threads) -> int {
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<blocks, threads, smem, st>>>(lp, S);

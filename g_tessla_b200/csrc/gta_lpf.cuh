@@ -32,13 +32,17 @@ __device__ __forceinline__ LFrame lpf_frame(const LpfWs& ws, int fr) {
 // (inlined into one kernel, the 14 instances share a 128-register budget and spill ~1 KB per thread). The state
 // is unpacked straight from shared memory -- loads of words the phase never reads are dead code -- and only the
 // words the phase may modify (LsDirty<PH>) are written back. Returns the packed phase word's new phase.
+constexpr int LPF_STRIDE = 1152;      // slot capacity of a block = stride of the word-major state array (a constant: the state
+                                      // accesses of a step become base + immediate offset)
+
 template <int PH>
-__device__ __noinline__ int lpf_wave_phase(uint32_t* st, int SLOTS, int sl, Pt* pt, LRec* rec, u16* head, int n, int cap_e, uint32_t* err_out) {
+__device__ __noinline__ int lpf_wave_phase(uint32_t* st, int sl, Pt* pt, LRec* rec, u16* head, int n, int cap_e, uint32_t* err_out) {
     LFrame f; f.pt = pt; f.rec = rec; f.head = head; f.n = n; f.cap_e = cap_e;
     LState s;
-    ls_unpack(s, [&](int w) { return st[w * SLOTS + sl]; });
+    uint32_t* mine = st + sl;
+    ls_unpack(s, [&](int w) { return mine[w * LPF_STRIDE]; });
     lpf_step_t<PH>(f, s);
-    ls_writeback<PH>(s, [&](int w, uint32_t v) { st[w * SLOTS + sl] = v; });
+    ls_writeback<PH>(s, [&](int w, uint32_t v) { mine[w * LPF_STRIDE] = v; });
     if (s.phase == LP_DONE) *err_out = s.err;
     return s.phase;
 }
@@ -53,8 +57,8 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p, const int SLOTS) {
     extern __shared__ __align__(16) unsigned char lsm[];
     constexpr int NB = LP_DONE + 1;                                        // one bin per phase + one for slots that need a frame
-    uint32_t* st = reinterpret_cast<uint32_t*>(lsm);                       // [LS_WORDS][SLOTS]
-    int* slot_fr = reinterpret_cast<int*>(st + (size_t)LS_WORDS * SLOTS);  // [SLOTS] frame of the slot
+    uint32_t* st = reinterpret_cast<uint32_t*>(lsm);                       // [LS_WORDS][LPF_STRIDE]
+    int* slot_fr = reinterpret_cast<int*>(st + (size_t)LS_WORDS * LPF_STRIDE);  // [SLOTS] frame of the slot
     u16* slot_n = reinterpret_cast<u16*>(slot_fr + SLOTS);                 // [SLOTS] its point count
     u16* bins = slot_n + SLOTS;                                            // [2][NB][SLOTS] slots of each phase, this round / next round
     int* cnt = reinterpret_cast<int*>(bins + 2 * (size_t)NB * SLOTS);      // [3][16] slots per bin: this round / next round / being cleared
@@ -114,7 +118,7 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
                         LState s = {};
                         lp_begin(f, s);
                         if (s.phase == LP_DONE) continue;
-                        ls_pack(s, [&](int w, uint32_t v) { st[w * SLOTS + sl] = v; });
+                        ls_pack(s, [&](int w, uint32_t v) { st[w * LPF_STRIDE + sl] = v; });
                         slot_fr[sl] = fr; slot_n[sl] = (u16)f.n;
                         next = s.phase;
                         break;
@@ -125,13 +129,13 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
                     u16* fhead = p.ws.head + (size_t)fr * p.ws.cap; const int fn = slot_n[sl], fce = p.ws.cap_e;
                     uint32_t* eo = p.ws.err + fr;
                     switch (bin) {                                        // every lane of the chunk is in this phase
-                    case LP_LEAF: next = lpf_wave_phase<LP_LEAF>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                    case LP_TINIT: next = lpf_wave_phase<LP_TINIT>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                    case LP_TAN: next = lpf_wave_phase<LP_TAN>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                    case LP_INS: next = lpf_wave_phase<LP_INS>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                    case LP_SCAN: next = lpf_wave_phase<LP_SCAN>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                    case LP_V: next = lpf_wave_phase<LP_V>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
-                    default: next = lpf_wave_phase<LP_C>(st, SLOTS, sl, fpt, frec, fhead, fn, fce, eo); break;
+                    case LP_LEAF: next = lpf_wave_phase<LP_LEAF>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
+                    case LP_TINIT: next = lpf_wave_phase<LP_TINIT>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
+                    case LP_TAN: next = lpf_wave_phase<LP_TAN>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
+                    case LP_INS: next = lpf_wave_phase<LP_INS>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
+                    case LP_SCAN: next = lpf_wave_phase<LP_SCAN>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
+                    case LP_V: next = lpf_wave_phase<LP_V>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
+                    default: next = lpf_wave_phase<LP_C>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
                     }
                 }
                 bin_next[(size_t)next * SLOTS + atomicAdd(&c_next[next], 1)] = (u16)sl;
