@@ -219,23 +219,15 @@ GT_NOINLINE int incircle_exact(double ax, double ay, double bx, double by, doubl
 
 // ---------------------------------------------------------------- public predicates
 GT_INLINE int orient2d_sign(double ax, double ay, double bx, double by, double cx, double cy) {
-    // stage A: reference predicates.c:1628-1651
-    double detleft = (ax - cx) * (by - cy);
-    double detright = (ay - cy) * (bx - cx);
-    double det = detleft - detright;
-    double detsum;
-    if (detleft > 0.0) {
-        if (detright <= 0.0) return det > 0.0 ? 1 : (det < 0.0 ? -1 : 0);
-        detsum = detleft + detright;
-    } else if (detleft < 0.0) {
-        if (detright >= 0.0) return det > 0.0 ? 1 : (det < 0.0 ? -1 : 0);
-        detsum = -detleft - detright;
-    } else {
-        return det > 0.0 ? 1 : (det < 0.0 ? -1 : 0);
-    }
-    double errbound = GT_CCW_ERRBOUND_A * detsum;
-    if (det >= errbound) return 1;
-    if (-det >= errbound) return -1;
+    // stage A: reference predicates.c:1628-1651, written without branches (lanes of a warp take this path
+    // together): the sign of det is certain when the two products do not have the same strict sign, or when
+    // |det| reaches the error bound
+    const double detleft = (ax - cx) * (by - cy);
+    const double detright = (ay - cy) * (bx - cx);
+    const double det = detleft - detright;
+    const bool same_sign = (detleft > 0.0 && detright > 0.0) || (detleft < 0.0 && detright < 0.0);
+    const double errbound = GT_CCW_ERRBOUND_A * (fabs(detleft) + fabs(detright));
+    if (!same_sign || fabs(det) >= errbound) return det > 0.0 ? 1 : (det < 0.0 ? -1 : 0);
     return orient2d_exact(ax, ay, bx, by, cx, cy);
 }
 

@@ -178,11 +178,8 @@ GT_INLINE void lp_next_node(const LFrame& f, LState& s) {
         return;
     } else k += 1;                                         // finished a left child: leftmost leaf of the sibling subtree
     int ia, ib;
-    for (;;) {
-        tree_node(f.n, d, k, &ia, &ib);
-        if (ib - ia < 3) break;
-        d += 1; k <<= 1;
-    }
+    tree_node(f.n, d, k, &ia, &ib);
+    while (ib - ia >= 3) { ib = (ia + ib) / 2; d += 1; k <<= 1; }      // left children down to the leaf (:535-538)
     s.d = d; s.k = k; s.ia = ia; s.ib = ib;
     s.phase = (ib - ia < 1) ? LP_DONE : LP_LEAF;
 }
