@@ -10,7 +10,7 @@
 
 static void usage(const char *prog) {
     printf("%s calculates 3-d surface area using Delaunay tessellation (B200-native build).\n"
-           "  -f  <traj>    trajectory: .gro .pdb .trr        (default traj.xtc)\n"
+           "  -f  <traj>    trajectory: .gro .pdb .trr .xtc   (default traj.xtc)\n"
            "  -n  <ndx>     index file; the first group selects the atoms (optional)\n"
            "  -o  <dat>     output table                      (default tessellated_areas.dat)\n"
            "  -nthreads N   host staging streams (default: library choice)\n"

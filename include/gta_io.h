@@ -3,7 +3,8 @@
  * Replaces the reference's gkut_io (extern/gkut/include/gkut_io.h:24-46, src/gkut_io.c:20-97), which
  * wraps GROMACS' read_first_x / read_next_x / rd_index. Same names and argument meaning; the formats
  * are decoded here: .gro (one or many frames), .pdb (CRYST1 + MODEL/ENDMDL, Angstrom -> nm) and .trr
- * (XDR, single or double precision). .xtc is not decoded yet; read_traj reports it.
+ * (XDR, single or double precision) and .xtc (XDR + compressed coordinates; restated from the published
+ * format, see csrc/gta_host.cu).
  */
 #ifndef GTA_IO_H
 #define GTA_IO_H

@@ -42,7 +42,7 @@ struct tri_area {
 };
 
 /* Read a trajectory (and optionally keep only the atoms of the first group of an index file), then
- * delaunay_tessellate it. Formats read without GROMACS: .gro, .g96-free .pdb (MODEL/ENDMDL, CRYST1),
+ * delaunay_tessellate it. Formats read without GROMACS: .gro, .pdb (MODEL/ENDMDL, CRYST1),
  * .trr (single or double precision) and .xtc. oenv is unused and may be NULL. */
 void tessellate_area(const char *traj_fname, const char *ndx_fname, output_env_t *oenv,
                      real espace, int nthreads, struct tri_area *areas, unsigned char flags);
