@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -311,6 +312,7 @@ struct Job {
     double *area = nullptr, *area2d = nullptr, *areabox = nullptr; int* status = nullptr;
     int* tri = nullptr; int tri_cap = 0; int* ntri = nullptr;
     double* corr = nullptr; int corr_cap = 0; int* ncorr = nullptr;
+    int host_threads = 0;                    // staging threads (the meaning -nthreads keeps); <= 0: all cores
 };
 
 // One in-flight chunk: pinned + device buffers, a stream and two events.
@@ -358,13 +360,18 @@ int slot_ensure(Slot& s, int chunk, size_t frame_bytes, int box_stride, size_t t
     return GTA_B200_OK;
 }
 
-// Per host thread and device: a small set of reusable slots (pinned allocations are expensive).
-struct SlotCache { int device = -1; std::vector<Slot> slots; ~SlotCache() { for (auto& s : slots) slot_free(s); } };
-thread_local SlotCache g_cache;
+// Per device: a small set of reusable slots (pinned allocations cost ~1 s per GB, and the sharded entry points
+// run each device from a fresh host thread, so the cache cannot be thread-local). A job holds its device's cache
+// for its duration: concurrent calls on one device queue behind each other.
+struct SlotCache { std::vector<Slot> slots; std::mutex mu; };
+SlotCache g_caches[64];
 
 int drain(Slot& s, const Job& j, double* kernel_ms) {
     if (!s.busy) return GTA_B200_OK;
+    static const bool trace = getenv("GTA_B200_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
     CK(cudaStreamSynchronize(s.st));
+    if (trace) fprintf(stderr, "[gta_b200] chunk %d+%d: waited %.1f ms for copies + kernels\n", s.f0, s.nf, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, s.k0, s.k1) == cudaSuccess) *kernel_ms += ms;
     const int c = s.chunk;
@@ -379,19 +386,32 @@ int drain(Slot& s, const Job& j, double* kernel_ms) {
 }
 
 int submit(Slot& s, const Job& j, const Shape& shp, int f0, int nf, bool src_pinned) {
+    static const bool trace = getenv("GTA_B200_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
     const size_t frame_elems = (size_t)j.natoms * j.in_dim, frame_bytes = frame_elems * sizeof(double);
     s.f0 = f0; s.nf = nf;
     // stage coordinates
     const double* h_src;
     if (j.frames) {
+        // gather of one heap block per frame (the reference's layout, extern/gkut/src/gkut_io.c:37) into the pinned
+        // chunk; at > 200k frames/s per GPU this is several GB/s of memcpy, so it is spread over the host cores
+        const int ht = j.host_threads > 0 ? j.host_threads : std::max(1u, std::thread::hardware_concurrency());
+#pragma omp parallel for schedule(static) num_threads(ht) if (nf >= 256)
         for (int f = 0; f < nf; ++f) memcpy(s.h_in + (size_t)f * frame_elems, j.frames[f0 + f], frame_bytes);
         h_src = s.h_in;
     } else if (src_pinned) {
         h_src = j.xyz + (size_t)f0 * frame_elems;              // caller's buffer is already page-locked
     } else {
-        memcpy(s.h_in, j.xyz + (size_t)f0 * frame_elems, frame_bytes * nf);
+        const int ht = j.host_threads > 0 ? j.host_threads : std::max(1u, std::thread::hardware_concurrency());
+        const long long blocks = std::max(1, std::min(ht, nf / 256));
+#pragma omp parallel for schedule(static) num_threads(ht) if (blocks > 1)
+        for (long long b = 0; b < blocks; ++b) {
+            const size_t lo = (size_t)nf * b / blocks, hi = (size_t)nf * (b + 1) / blocks;
+            memcpy(s.h_in + lo * frame_elems, j.xyz + ((size_t)f0 + lo) * frame_elems, frame_bytes * (hi - lo));
+        }
         h_src = s.h_in;
     }
+    if (trace) fprintf(stderr, "[gta_b200] chunk %d+%d: host staging %.1f ms\n", f0, nf, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
     CK(cudaMemcpyAsync(s.d_in, h_src, frame_bytes * nf, cudaMemcpyHostToDevice, s.st));
     if (j.box) {
         memcpy(s.h_box, j.box + (size_t)f0 * j.box_stride, sizeof(double) * j.box_stride * nf);
@@ -457,7 +477,9 @@ int run_job(Job j, int device, int nstreams) {
         if (cudaPointerGetAttributes(&at, j.xyz) == cudaSuccess) src_pinned = (at.type == cudaMemoryTypeHost);
         else cudaGetLastError();
     }
-    if (g_cache.device != device) { for (auto& s : g_cache.slots) slot_free(s); g_cache.slots.clear(); g_cache.device = device; }
+    if (device < 0 || device >= 64) return fail(GTA_B200_E_ARG, "device index out of range");
+    SlotCache& g_cache = g_caches[device];
+    std::lock_guard<std::mutex> cache_lock(g_cache.mu);
     if ((int)g_cache.slots.size() < nstreams) g_cache.slots.resize(nstreams);
     for (int i = 0; i < nstreams; ++i) {
         int rc = slot_ensure(g_cache.slots[i], (int)chunk, frame_bytes, std::max(j.box_stride, 1),
@@ -512,6 +534,10 @@ static int run_sharded(const Job& base, int ngpus, int nstreams) {
             int f0 = g * per, f1 = std::min(base.nframes, f0 + per);
             if (f0 >= f1) return;
             Job j = base;
+            {   // host staging threads are shared between the per-device threads
+                const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+                j.host_threads = std::max(1, (base.host_threads > 0 ? base.host_threads : hw) / ngpus);
+            }
             const size_t fe = (size_t)j.natoms * j.in_dim;
             if (j.xyz) j.xyz += (size_t)f0 * fe;
             if (j.frames) j.frames += f0;
@@ -548,8 +574,8 @@ int gta_b200_tessellate_frames(const double* const* x, const double* box9, int n
     Job j;
     j.frames = x; j.in_dim = 3; j.box = box9; j.box_stride = 9; j.nframes = nframes; j.natoms = natoms;
     j.espace = espace; j.flags = flags; j.area = area; j.area2d = area2d; j.areabox = areabox; j.status = status;
-    int nstreams = nthreads <= 0 ? 4 : std::max(1, std::min(nthreads, 8));
-    return run_sharded(j, ngpus <= 0 ? 1 : ngpus, nstreams);
+    j.host_threads = nthreads;
+    return run_sharded(j, ngpus <= 0 ? 1 : ngpus, 4);
 }
 
 static int signs_common(const double* pts, int n, int* out, int device, int width) {
