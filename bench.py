@@ -40,7 +40,7 @@ FP64_PEAK_TFLOPS_NOMINAL = 37.2                   # 148 SM x 64 DFMA/clk x 2 x 1
 # dram read+write per frame from ncu --set full captures (profiles/): fused CTA-per-frame kernel (6,000 frames) and the
 # lane-per-frame pipeline (pre-pass + lpf_wave_kernel + area kernel, 40,000 frames; its per-frame workspace lives in HBM)
 NCU_DRAM_BYTES_PER_FRAME_FUSED = 26254
-NCU_DRAM_BYTES_PER_FRAME_LPF = 1137000
+NCU_DRAM_BYTES_PER_FRAME_LPF = 1066000
 LPF_MIN_FRAMES = 32768               # launches at least this large use the lane-per-frame pipeline (gta_b200_set_batch_threshold)
 WORKLOAD = "cfg3: 2,048-lipid bilayer leaflet, 1,024 atoms/frame, -corr -espace 0.8, 3-D area"
 
@@ -282,7 +282,7 @@ def run_native(args):
                          "traffic": (NCU_DRAM_BYTES_PER_FRAME_LPF if lpf else NCU_DRAM_BYTES_PER_FRAME_FUSED) * F / 1e9,
                          "traffic_unit": "GB per step (ncu dram bytes per frame x frames per step)",
                          "peak_source": pk_src,
-                         "kernel": "gt::lpf_wave_kernel (91% of the step; + pre-pass gt::tessellate_kernel 6%, gt::lpf_area_kernel 2%)" if lpf else "gt::tessellate_kernel",
+                         "kernel": "gt::lpf_wave_kernel (89% of the step; + pre-pass gt::tessellate_kernel 8%, gt::lpf_area_kernel 3%)" if lpf else "gt::tessellate_kernel",
                          "kernel_ms_per_launch": kern_ms, "alg_bytes_per_frame": ALG_BYTES_PER_FRAME,
                          "note": "latency / issue bound (dependent pointer-chasing loads, one predicate per iteration); see DESIGN.md section 5"},
             "roofline_fp64": {"achieved": fl, "peak": FP64_PEAK_TFLOPS_NOMINAL, "unit": "TFLOP/s", "frac": fl / FP64_PEAK_TFLOPS_NOMINAL,
