@@ -3,7 +3,8 @@
 // Pipeline for a large batch (>= tens of thousands of frames; smaller batches stay on the CTA-per-frame
 // kernel, whose per-frame latency is 20x lower):
 //   1. tessellate_kernel in pre-pass mode: load, -corr, sort -> workspace          (gta_kernel.cuh)
-//   2. lpf_kernel: every LANE owns a frame and runs the D&C state machine on it     (this file)
+//   2. lpf_wave_kernel: every frame is one slot of a phase-sorted scheduler; a lane runs one iteration of the D&C
+//      state machine (lpf_core.cuh) for one frame at a time                              (this file)
 //   3. lpf_area_kernel: one warp per frame enumerates the triangles and sums areas  (this file)
 // Replaces the same reference loops as the fused kernel (src/gta_tri.c:106-296).
 #pragma once
