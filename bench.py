@@ -164,7 +164,7 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -180,8 +180,6 @@ def run_native(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     L = g.lib()
     F = args.frames
@@ -291,7 +289,7 @@ def run_native(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(xyz_h.numpy(), box_h.numpy(), area_dev, args)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -316,7 +314,26 @@ def cpu_baseline(xyz, box, area_gpu, args):
             "one_thread_frames_per_s": 256 / t1, "max_rel_area_diff_vs_gpu": rel, "parity_ok": bool(rel <= 1e-12)}
 
 
+_REAL_STDOUT = None
+
+
+def own_stdout():
+    """Rank 0 must print exactly ONE line on stdout. Libraries below us write banners to file descriptor 1 (NCCL's version line
+    is one), so point fd 1 at stderr for the whole run and keep the real stdout for the JSON line only."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    own_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
