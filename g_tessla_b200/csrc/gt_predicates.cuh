@@ -15,9 +15,10 @@
 //   X  exact evaluation in multi-word two's-complement integers.  The coordinates of one
 //      call are scaled by a common power of two to integers of W 64-bit words (W = 1, 2, 4
 //      chosen from the bit spread of the operands), the determinant is a degree-2 / degree-4
-//      polynomial evaluated without rounding.  Branch-light, no local-memory expansions;
-//      this replaces Shewchuk's adaptive expansion stages B-D, which are a poor fit for a
-//      GPU (up to 2 x 1152-double scratch per thread, predicates.c:2674).
+//      polynomial evaluated without rounding.  This replaces Shewchuk's adaptive expansion
+//      stages B-D, which are a poor fit for a GPU (up to 2 x 1152-double scratch per thread,
+//      predicates.c:2674); the integers take at most 0.8 KB of local memory and the stage is
+//      out of line and deliberately register-lean (see "multi-word integers" below).
 //      Operands whose bit spread exceeds 251 bits (e.g. 1e-40 next to 1e+20) return
 //      GT_RANGE_ERR instead of a sign (by value: an out-parameter would force a local-memory
 //      round trip on every call); the frame is then flagged GTA_B200_ST_PRECISION_RANGE.
@@ -77,57 +78,51 @@ GT_INLINE uint64_t mulhi64(uint64_t a, uint64_t b) {
 #endif
 }
 
-// ---------------------------------------------------------------- fixed-width integers
-template <int N> struct Big { uint64_t w[N]; };   // two's complement, little-endian words
+// ---------------------------------------------------------------- multi-word integers
+// Little-endian two's-complement integers of n 64-bit words. They live in local memory and the helpers are out of
+// line with run-time loops ON PURPOSE: the exact stage runs for none of the predicates of cfg 1-3 and ~1 % of cfg 5's
+// (tests/emu counters), but a register-resident, fully unrolled version costs every caller up to 140 registers at its
+// call site (measured: the lane-per-frame incircle phase needed 250 registers, 108 without the call) -- and that
+// halves the warps an SM can hold. Slow and small is the right trade for a path this rare.
 
-template <int N> GT_INLINE bool big_neg(const Big<N>& a) { return (int64_t)a.w[N - 1] < 0; }
-template <int N> GT_INLINE bool big_zero(const Big<N>& a) {
-    uint64_t o = 0;
-#pragma unroll
-    for (int i = 0; i < N; ++i) o |= a.w[i];
-    return o == 0;
-}
-template <int N> GT_INLINE Big<N> big_add(const Big<N>& a, const Big<N>& b) {
-    Big<N> r; uint64_t c = 0;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        uint64_t s = a.w[i] + b.w[i]; uint64_t c1 = s < a.w[i];
-        uint64_t t = s + c; uint64_t c2 = t < s;
-        r.w[i] = t; c = c1 | c2;
+// r = a + b  or  a - b  (n words; r may alias a or b)
+GT_NOINLINE void xi_addsub(uint64_t* r, const uint64_t* a, const uint64_t* b, int n, bool sub) {
+    uint64_t c = sub ? 1 : 0;
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+        const uint64_t x = a[i], y = sub ? ~b[i] : b[i];
+        const uint64_t s = x + y; const uint64_t c1 = s < x;
+        const uint64_t t = s + c; const uint64_t c2 = t < s;
+        r[i] = t; c = c1 | c2;
     }
-    return r;
 }
-template <int N> GT_INLINE Big<N> big_negate(const Big<N>& a) {
-    Big<N> r; uint64_t c = 1;
-#pragma unroll
-    for (int i = 0; i < N; ++i) { uint64_t t = ~a.w[i] + c; c = (t < c) ? 1 : 0; r.w[i] = t; }
-    return r;
-}
-template <int N> GT_INLINE Big<N> big_sub(const Big<N>& a, const Big<N>& b) { return big_add(a, big_negate(b)); }
-template <int N> GT_INLINE Big<N> big_abs(const Big<N>& a) { return big_neg(a) ? big_negate(a) : a; }
-
-// signed N x N -> 2N words (schoolbook on magnitudes)
-template <int N> GT_INLINE Big<2 * N> big_mul(const Big<N>& a, const Big<N>& b) {
-    const bool neg = big_neg(a) != big_neg(b);
-    const Big<N> ua = big_abs(a), ub = big_abs(b);
-    Big<2 * N> r;
-#pragma unroll
-    for (int i = 0; i < 2 * N; ++i) r.w[i] = 0;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        uint64_t carry = 0;
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-            uint64_t lo = ua.w[i] * ub.w[j], hi = mulhi64(ua.w[i], ub.w[j]);
-            uint64_t s = r.w[i + j] + lo; hi += (s < lo);
-            uint64_t t = s + carry; hi += (t < s);
-            r.w[i + j] = t; carry = hi;
+// r[0..2n) = a * b, signed (r must not alias a or b). Unsigned schoolbook product, then the two's-complement
+// correction: with ua = a + 2^(64n)[a<0], a*b = ua*ub - 2^(64n) ([a<0] ub + [b<0] ua)  (mod 2^(128n)).
+GT_NOINLINE void xi_mul(uint64_t* r, const uint64_t* a, const uint64_t* b, int n) {
+#pragma unroll 1
+    for (int i = 0; i < 2 * n; ++i) r[i] = 0;
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+        uint64_t carry = 0; const uint64_t ai = a[i];
+#pragma unroll 1
+        for (int j = 0; j < n; ++j) {
+            const uint64_t lo = ai * b[j]; uint64_t hi = mulhi64(ai, b[j]);
+            const uint64_t s = r[i + j] + lo; hi += (s < lo);
+            const uint64_t t = s + carry; hi += (t < s);
+            r[i + j] = t; carry = hi;
         }
-        r.w[i + N] = carry;
+        r[i + n] = carry;
     }
-    return neg ? big_negate(r) : r;
+    if ((int64_t)a[n - 1] < 0) xi_addsub(r + n, r + n, b, n, true);
+    if ((int64_t)b[n - 1] < 0) xi_addsub(r + n, r + n, a, n, true);
 }
-template <int N> GT_INLINE int big_sign(const Big<N>& a) { return big_neg(a) ? -1 : (big_zero(a) ? 0 : 1); }
+GT_NOINLINE int xi_sign(const uint64_t* a, int n) {
+    if ((int64_t)a[n - 1] < 0) return -1;
+    uint64_t o = 0;
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) o |= a[i];
+    return o ? 1 : 0;
+}
 
 // ---------------------------------------------------------------- double -> scaled integer
 // A finite double v != 0 is m * 2^e with integer m (53 bits). lowbit/highbit are the
@@ -144,107 +139,178 @@ GT_INLINE void spread_acc(double v, Spread& s) {
     s.lo = lo < s.lo ? lo : s.lo;
     s.hi = hi > s.hi ? hi : s.hi;
 }
-// v / 2^base as a W-word integer (exact when base <= lowbit(v) and the value fits).
-template <int W> GT_INLINE Big<W> to_big(double v, int base) {
-    Big<W> r;
-#pragma unroll
-    for (int i = 0; i < W; ++i) r.w[i] = 0;
-    int64_t b = dbl_bits(v);
-    uint64_t man = (uint64_t)b & 0x000FFFFFFFFFFFFFull;
-    int ex = (int)((b >> 52) & 0x7FF);
-    if (ex == 0 && man == 0) return r;
+// Device-side count of the predicates the FP filter left undecided (settled by stage A' or by the integers): the host
+// reads it after a launch to learn whether the input is of the degenerate, few-bit kind that stage A' pays for
+// (gta_b200.cu, launch_lpf).
+#if defined(__CUDACC__)
+static __device__ unsigned long long g_xcalls;
+#endif
+#if defined(__CUDA_ARCH__)
+#define GT_XCOUNT() do { if ((threadIdx.x & 7) == 0) atomicAdd(&g_xcalls, 1ull); } while (0)        // a 1-in-8 sample: it is one address
+#else
+#define GT_XCOUNT() ((void)0)
+#endif
+
+// Common scale and word count of one call's operands: base = lowest set bit over all of them, n = 1, 2 or 4 words
+// per coordinate from their bit spread (0: they do not fit, -1: all operands are zero).
+GT_NOINLINE int xi_plan(const double* c, int count, int* base) {
+    GT_XCOUNT();                                           // (here: this function is the first thing both integer stages call)
+    Spread s; s.lo = 1 << 30; s.hi = -(1 << 30);
+#pragma unroll 1
+    for (int i = 0; i < count; ++i) spread_acc(c[i], s);
+    if (s.hi < s.lo) return -1;
+    *base = s.lo;
+    const int span = s.hi - s.lo + 1;
+    return span <= 59 ? 1 : (span <= 123 ? 2 : (span <= 251 ? 4 : 0));
+}
+// r = v / 2^base as an n-word integer (exact when base <= lowbit(v) and the value fits).
+GT_NOINLINE void xi_set(uint64_t* r, int n, double v, int base) {
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) r[i] = 0;
+    const int64_t b = dbl_bits(v);
+    const uint64_t man = (uint64_t)b & 0x000FFFFFFFFFFFFFull;
+    const int ex = (int)((b >> 52) & 0x7FF);
+    if (ex == 0 && man == 0) return;
     uint64_t m = ex ? (man | 0x0010000000000000ull) : man;
     int sh = (ex ? ex - 1075 : -1074) - base;              // may be negative by at most ctz(m)
     if (sh < 0) { m >>= -sh; sh = 0; }
-    int word = sh >> 6, bit = sh & 63;
-#pragma unroll
-    for (int i = 0; i < W; ++i) {
-        if (i == word) r.w[i] = m << bit;
-        if (i == word + 1 && bit) r.w[i] = m >> (64 - bit);
+    const int word = sh >> 6, bit = sh & 63;
+    if (word < n) r[word] = m << bit;
+    if (bit && word + 1 < n) r[word + 1] = m >> (64 - bit);
+    if (b < 0) {                                           // negate: ~r + 1
+        uint64_t c = 1;
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) { const uint64_t t = ~r[i] + c; c = (t < c) ? 1 : 0; r[i] = t; }
     }
-    return (b < 0) ? big_negate(r) : r;
 }
+
+// Host-only counters of the exact stages taken (emulation build, -DGT_STATS): [0..2] orient2d with 1/2/4 words, [3..5] incircle.
+#if defined(GT_STATS) && !defined(__CUDA_ARCH__)
+extern long g_exact_calls[8];
+#define GT_XSTAT(i) (++g_exact_calls[i])
+#else
+#define GT_XSTAT(i) ((void)0)
+#endif
 
 // ---------------------------------------------------------------- exact stages
-template <int W> GT_INLINE int orient2d_big(const double* c, int base) {
-    // c = {ax, ay, bx, by, cx, cy};  det = (ax-cx)(by-cy) - (ay-cy)(bx-cx)
-    Big<W> ax = to_big<W>(c[0], base), ay = to_big<W>(c[1], base), bx = to_big<W>(c[2], base),
-           by = to_big<W>(c[3], base), cx = to_big<W>(c[4], base), cy = to_big<W>(c[5], base);
-    Big<W> acx = big_sub(ax, cx), acy = big_sub(ay, cy), bcx = big_sub(bx, cx), bcy = big_sub(by, cy);
-    return big_sign(big_sub(big_mul(acx, bcy), big_mul(acy, bcx)));
-}
-template <int W> GT_INLINE int incircle_big(const double* c, int base) {
-    // c = {ax, ay, bx, by, cx, cy, dx, dy}
-    Big<W> dx = to_big<W>(c[6], base), dy = to_big<W>(c[7], base);
-    Big<W> adx = big_sub(to_big<W>(c[0], base), dx), ady = big_sub(to_big<W>(c[1], base), dy);
-    Big<W> bdx = big_sub(to_big<W>(c[2], base), dx), bdy = big_sub(to_big<W>(c[3], base), dy);
-    Big<W> cdx = big_sub(to_big<W>(c[4], base), dx), cdy = big_sub(to_big<W>(c[5], base), dy);
-    Big<4 * W> det = big_mul(big_add(big_mul(adx, adx), big_mul(ady, ady)),
-                             big_sub(big_mul(bdx, cdy), big_mul(cdx, bdy)));
-    det = big_add(det, big_mul(big_add(big_mul(bdx, bdx), big_mul(bdy, bdy)),
-                               big_sub(big_mul(cdx, ady), big_mul(adx, cdy))));
-    det = big_add(det, big_mul(big_add(big_mul(cdx, cdx), big_mul(cdy, cdy)),
-                               big_sub(big_mul(adx, bdy), big_mul(bdx, ady))));
-    return big_sign(det);
-}
-
-// Exact sign of orient2d. Word count from the operands' bit spread: every coordinate needs
-// spread+1 bits, differences one more, the degree-2 determinant 2*(spread+2)+1 <= 128*W - 1.
+// Exact sign of orient2d, det = (ax-cx)(by-cy) - (ay-cy)(bx-cx). Word count from the operands' bit spread: every
+// coordinate needs spread+1 bits, differences one more, the degree-2 determinant 2*(spread+2)+1 <= 128*n - 1.
 GT_NOINLINE int orient2d_exact(double ax, double ay, double bx, double by, double cx, double cy) {
     double c[6] = {ax, ay, bx, by, cx, cy};
-    Spread s; s.lo = 1 << 30; s.hi = -(1 << 30);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) spread_acc(c[i], s);
-    if (s.hi < s.lo) return 0;                             // all coordinates are zero
-    int span = s.hi - s.lo + 1;
-    if (span <= 59) return orient2d_big<1>(c, s.lo);
-    if (span <= 123) return orient2d_big<2>(c, s.lo);
-    if (span <= 251) return orient2d_big<4>(c, s.lo);
-    return GT_RANGE_ERR;
+    int base = 0;
+    const int n = xi_plan(c, 6, &base);
+    if (n < 0) return 0;                                   // all coordinates are zero
+    if (n == 0) return GT_RANGE_ERR;
+    GT_XSTAT(n >> 1);
+    uint64_t v[4][4], o[2][4], m1[8], m2[8];               // v = acx, acy, bcx, bcy
+    xi_set(o[0], n, c[4], base); xi_set(o[1], n, c[5], base);
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) { xi_set(v[i], n, c[i], base); xi_addsub(v[i], v[i], o[i & 1], n, true); }
+    xi_mul(m1, v[0], v[3], n); xi_mul(m2, v[1], v[2], n);
+    xi_addsub(m1, m1, m2, 2 * n, true);
+    return xi_sign(m1, 2 * n);
 }
-// Exact sign of incircle: degree 4, 4*(spread+2)+3 <= 256*W - 1.
+// Exact sign of incircle: degree 4, 4*(spread+2)+3 <= 256*n - 1.
+//   det = alift (bdx cdy - cdx bdy) + blift (cdx ady - adx cdy) + clift (adx bdy - bdx ady),  alift = adx^2 + ady^2, ...
 GT_NOINLINE int incircle_exact(double ax, double ay, double bx, double by, double cx, double cy,
                                double dx, double dy) {
     double c[8] = {ax, ay, bx, by, cx, cy, dx, dy};
-    Spread s; s.lo = 1 << 30; s.hi = -(1 << 30);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) spread_acc(c[i], s);
-    if (s.hi < s.lo) return 0;
-    int span = s.hi - s.lo + 1;
-    if (span <= 59) return incircle_big<1>(c, s.lo);
-    if (span <= 123) return incircle_big<2>(c, s.lo);
-    if (span <= 251) return incircle_big<4>(c, s.lo);
-    return GT_RANGE_ERR;
+    int base = 0;
+    const int n = xi_plan(c, 8, &base);
+    if (n < 0) return 0;
+    if (n == 0) return GT_RANGE_ERR;
+    GT_XSTAT(3 + (n >> 1));
+    uint64_t v[6][4], o[2][4];                             // v = adx, ady, bdx, bdy, cdx, cdy
+    uint64_t lift[8], m1[8], m2[8], term[16], det[16];
+    xi_set(o[0], n, c[6], base); xi_set(o[1], n, c[7], base);
+#pragma unroll 1
+    for (int i = 0; i < 6; ++i) { xi_set(v[i], n, c[i], base); xi_addsub(v[i], v[i], o[i & 1], n, true); }
+#pragma unroll 1
+    for (int t = 0; t < 3; ++t) {
+        const int p = (t + 1) % 3, q = (t + 2) % 3;
+        xi_mul(lift, v[2 * t], v[2 * t], n); xi_mul(m1, v[2 * t + 1], v[2 * t + 1], n);
+        xi_addsub(lift, lift, m1, 2 * n, false);
+        xi_mul(m1, v[2 * p], v[2 * q + 1], n); xi_mul(m2, v[2 * q], v[2 * p + 1], n);
+        xi_addsub(m1, m1, m2, 2 * n, true);
+        xi_mul(t == 0 ? det : term, lift, m1, 2 * n);
+        if (t) xi_addsub(det, det, term, 4 * n, false);
+    }
+    return xi_sign(det, 4 * n);
 }
 
 // ---------------------------------------------------------------- public predicates
+// Stage A' (between the filter and the integers): was every operation of the filter exact for these operands? Then the
+// filter's det IS the determinant and its sign -- including 0 -- is final. True for few-bit coordinates, i.e. exactly
+// the inputs that are degenerate on purpose (lattices: cfg 5 has ~320 undecided predicates per frame, all of this
+// kind); costs ~100 flops on the undecided path only, but ~15 registers at every inlined call site, so it is a template
+// switch (AP): the lane-per-frame kernel is built both ways and the host picks (gta_b200.cu, launch_lpf). Error-free
+// transformations as in predicates.c:171-239 (Two_Sum / Two_Diff tails, and the product's tail by one FMA instead of
+// Split + Two_Product).
+GT_INLINE double gt_fma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return fma(a, b, c);
+#endif
+}
+GT_INLINE bool exact_diff(double a, double b, double x) {          // x == fl(a - b)
+    const double bvirt = a - x, avirt = x + bvirt, bround = bvirt - b, around = a - avirt;
+    return (around + bround) == 0.0;
+}
+GT_INLINE bool exact_sum(double a, double b, double x) {           // x == fl(a + b)
+    const double bvirt = x - a, avirt = x - bvirt, bround = b - bvirt, around = a - avirt;
+    return (around + bround) == 0.0;
+}
+GT_INLINE bool exact_prod(double a, double b, double p) {          // p == fl(a * b); tiny products are "not proven": their tail may underflow
+    return (p == 0.0 || fabs(p) > 1e-200) && gt_fma(a, b, -p) == 0.0;
+}
+
+template <bool AP = true>
 GT_INLINE int orient2d_sign(double ax, double ay, double bx, double by, double cx, double cy) {
     // stage A: reference predicates.c:1628-1651, written without branches (lanes of a warp take this path
     // together): the sign of det is certain when the two products do not have the same strict sign, or when
     // |det| reaches the error bound
-    const double detleft = (ax - cx) * (by - cy);
-    const double detright = (ay - cy) * (bx - cx);
+    const double acx = ax - cx, bcy = by - cy, acy = ay - cy, bcx = bx - cx;
+    const double detleft = acx * bcy;
+    const double detright = acy * bcx;
     const double det = detleft - detright;
     const bool same_sign = (detleft > 0.0 && detright > 0.0) || (detleft < 0.0 && detright < 0.0);
     const double errbound = GT_CCW_ERRBOUND_A * (fabs(detleft) + fabs(detright));
     if (!same_sign || fabs(det) >= errbound) return det > 0.0 ? 1 : (det < 0.0 ? -1 : 0);
+    const bool exact = AP & exact_diff(ax, cx, acx) & exact_diff(by, cy, bcy) & exact_diff(ay, cy, acy) & exact_diff(bx, cx, bcx)
+                     & exact_prod(acx, bcy, detleft) & exact_prod(acy, bcx, detright) & exact_diff(detleft, detright, det);
+    if (exact) { GT_XCOUNT(); return det > 0.0 ? 1 : (det < 0.0 ? -1 : 0); }
     return orient2d_exact(ax, ay, bx, by, cx, cy);
 }
 
+template <bool AP = true>
 GT_INLINE int incircle_sign(double ax, double ay, double bx, double by, double cx, double cy,
                             double dx, double dy) {
     // stage A: reference predicates.c:3238-3267
-    double adx = ax - dx, bdx = bx - dx, cdx = cx - dx;
-    double ady = ay - dy, bdy = by - dy, cdy = cy - dy;
-    double bdxcdy = bdx * cdy, cdxbdy = cdx * bdy, alift = adx * adx + ady * ady;
-    double cdxady = cdx * ady, adxcdy = adx * cdy, blift = bdx * bdx + bdy * bdy;
-    double adxbdy = adx * bdy, bdxady = bdx * ady, clift = cdx * cdx + cdy * cdy;
-    double det = alift * (bdxcdy - cdxbdy) + blift * (cdxady - adxcdy) + clift * (adxbdy - bdxady);
-    double permanent = (fabs(bdxcdy) + fabs(cdxbdy)) * alift + (fabs(cdxady) + fabs(adxcdy)) * blift
-                     + (fabs(adxbdy) + fabs(bdxady)) * clift;
-    double errbound = GT_ICC_ERRBOUND_A * permanent;
+    const double adx = ax - dx, bdx = bx - dx, cdx = cx - dx;
+    const double ady = ay - dy, bdy = by - dy, cdy = cy - dy;
+    const double bdxcdy = bdx * cdy, cdxbdy = cdx * bdy, adx2 = adx * adx, ady2 = ady * ady, alift = adx2 + ady2;
+    const double cdxady = cdx * ady, adxcdy = adx * cdy, bdx2 = bdx * bdx, bdy2 = bdy * bdy, blift = bdx2 + bdy2;
+    const double adxbdy = adx * bdy, bdxady = bdx * ady, cdx2 = cdx * cdx, cdy2 = cdy * cdy, clift = cdx2 + cdy2;
+    const double ma = bdxcdy - cdxbdy, mb = cdxady - adxcdy, mc = adxbdy - bdxady;
+    const double ta = alift * ma, tb = blift * mb, tc = clift * mc, tab = ta + tb;
+    const double det = tab + tc;
+    const double permanent = (fabs(bdxcdy) + fabs(cdxbdy)) * alift + (fabs(cdxady) + fabs(adxcdy)) * blift
+                           + (fabs(adxbdy) + fabs(bdxady)) * clift;
+    const double errbound = GT_ICC_ERRBOUND_A * permanent;
     if (det > errbound) return 1;
     if (-det > errbound) return -1;
+    bool exact = AP & exact_diff(ax, dx, adx) & exact_diff(bx, dx, bdx) & exact_diff(cx, dx, cdx)
+               & exact_diff(ay, dy, ady) & exact_diff(by, dy, bdy) & exact_diff(cy, dy, cdy);
+    exact = exact & exact_prod(bdx, cdy, bdxcdy) & exact_prod(cdx, bdy, cdxbdy) & exact_prod(cdx, ady, cdxady)
+          & exact_prod(adx, cdy, adxcdy) & exact_prod(adx, bdy, adxbdy) & exact_prod(bdx, ady, bdxady);
+    exact = exact & exact_prod(adx, adx, adx2) & exact_prod(ady, ady, ady2) & exact_prod(bdx, bdx, bdx2)
+          & exact_prod(bdy, bdy, bdy2) & exact_prod(cdx, cdx, cdx2) & exact_prod(cdy, cdy, cdy2);
+    exact = exact & exact_sum(adx2, ady2, alift) & exact_sum(bdx2, bdy2, blift) & exact_sum(cdx2, cdy2, clift)
+          & exact_diff(bdxcdy, cdxbdy, ma) & exact_diff(cdxady, adxcdy, mb) & exact_diff(adxbdy, bdxady, mc);
+    exact = exact & exact_prod(alift, ma, ta) & exact_prod(blift, mb, tb) & exact_prod(clift, mc, tc)
+          & exact_sum(ta, tb, tab) & exact_sum(tab, tc, det);
+    if (exact) { GT_XCOUNT(); return det > 0.0 ? 1 : (det < 0.0 ? -1 : 0); }
     return incircle_exact(ax, ay, bx, by, cx, cy, dx, dy);
 }
 

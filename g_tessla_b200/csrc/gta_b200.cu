@@ -113,7 +113,12 @@ int occupancy_for(const Shape& s) {
 }
 
 // ---- lane-per-frame path: workspace cache (one per device, grows on demand) and launcher
-struct LpfCache { gt::LpfWs ws{}; size_t frames = 0; int cap = 0, cap_e = 0; unsigned int* counter = nullptr; cudaEvent_t done = nullptr; };
+struct LpfCache {
+    gt::LpfWs ws{}; size_t frames = 0; int cap = 0, cap_e = 0; unsigned int* counter = nullptr; cudaEvent_t done = nullptr;
+    // feedback for the choice of kernel variant (launch_lpf): predicates the FP filter left undecided, as counted on the device
+    unsigned long long* undecided_h = nullptr;      // pinned; the device's running count after the last launch
+    unsigned long long undecided_seen = 0; int last_frames = 0; bool pending = false, degenerate = false;
+};
 LpfCache g_lpf[64];
 std::mutex g_lpf_mu;
 
@@ -136,6 +141,7 @@ int lpf_ensure(int dev, size_t frames, int cap, int cap_e, LpfCache** out) {
         cudaFree(c.ws.pt); cudaFree(c.ws.z); cudaFree(c.ws.rec); cudaFree(c.ws.head); cudaFree(c.ws.perm);
         cudaFree(c.ws.n); cudaFree(c.ws.st); cudaFree(c.ws.err); cudaFree(c.counter);
         if (c.done) { cudaDeviceSynchronize(); cudaEventDestroy(c.done); }
+        if (c.undecided_h) cudaFreeHost(c.undecided_h);
         c = LpfCache();
         frames = std::max(frames, c.frames); cap = std::max(cap, c.cap); cap_e = std::max(cap_e, c.cap_e);
         CK(cudaMalloc((void**)&c.ws.pt, sizeof(gt::Pt) * frames * cap));
@@ -145,6 +151,7 @@ int lpf_ensure(int dev, size_t frames, int cap, int cap_e, LpfCache** out) {
         CK(cudaMalloc((void**)&c.ws.perm, 2 * frames * cap));
         CK(cudaMalloc((void**)&c.ws.n, 4 * frames)); CK(cudaMalloc((void**)&c.ws.st, 4 * frames)); CK(cudaMalloc((void**)&c.ws.err, 4 * frames));
         CK(cudaMalloc((void**)&c.counter, 4));
+        CK(cudaMallocHost((void**)&c.undecided_h, 8)); *c.undecided_h = 0;
         CK(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
         c.ws.cap = cap; c.ws.cap_e = cap_e; c.frames = frames; c.cap = cap; c.cap_e = cap_e;
     }
@@ -172,8 +179,17 @@ int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st) {
     gt::LpfParams lp; lp.ws = c->ws; lp.nframes = p.nframes; lp.counter = c->counter;
     CK(cudaMemsetAsync(c->counter, 0, 4, st));
     static int slots = -1, wthreads = -1;                    // frames in flight per block / threads per block (experiments: GTA_B200_LPF_SLOTS, _THREADS)
-    if (slots < 0) { const char* e = getenv("GTA_B200_LPF_SLOTS"); slots = e ? atoi(e) : 1024; }
-    if (wthreads < 0) { const char* e = getenv("GTA_B200_LPF_THREADS"); wthreads = e ? atoi(e) : 256; }
+    if (slots < 0) { const char* e = getenv("GTA_B200_LPF_SLOTS"); slots = e ? atoi(e) : gt::LPF_STRIDE; }
+    if (wthreads < 0) { const char* e = getenv("GTA_B200_LPF_THREADS"); wthreads = e ? atoi(e) : 0; }
+    // Which build of the kernel? Without stage A' of the predicates (gt_predicates.cuh) the steps fit 128 registers and
+    // 14 warps per SM: best when the FP filter decides everything, as it does on real coordinates (cfg 3: 263 k frames/s
+    // vs 253 k). With stage A', 12 warps: 2x faster on degenerate few-bit input (cfg 5: 290 k vs 136 k). The previous
+    // launch on this device tells which kind of data this is: the device counts the undecided predicates (1 lane in 8).
+    if (c->pending && cudaEventQuery(c->done) == cudaSuccess) {
+        const unsigned long long now = *c->undecided_h;
+        c->degenerate = (now - c->undecided_seen) * 8 >= 16ull * (unsigned long long)c->last_frames;
+        c->undecided_seen = now; c->pending = false;
+    }
     {
         // spread the batch over every SM: fewer slots per block shorten the round when the batch is small
         const int blocks = std::max(1, std::min(sms, (p.nframes + 63) / 64));
@@ -186,8 +202,10 @@ int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st) {
             CK(cudaGetLastError());
             return GTA_B200_OK;
         };
-        // 8 warps per SM measured best on cfg 3 (288 / 320 / 384 / 512 threads: 167 / 172 / 180 / 161 k frames/s vs 231 k)
-        rc = wthreads >= 512 ? go(gt::lpf_wave_kernel<512>, 512) : go(gt::lpf_wave_kernel<256>, 256);
+        if (wthreads == 256) rc = go(gt::lpf_wave_kernel<256, true>, 256);                 // (experiments)
+        else if (wthreads == 512) rc = go(gt::lpf_wave_kernel<512, false>, 512);
+        else if (c->degenerate || wthreads == 384) rc = go(gt::lpf_wave_kernel<384, true>, 384);
+        else rc = go(gt::lpf_wave_kernel<448, false>, 448);
         if (rc) return rc;
     }
     // 3. areas
@@ -195,6 +213,8 @@ int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st) {
     ap.area = p.area; ap.area2d = p.area2d; ap.status = p.status; ap.ntri = p.ntri; ap.tri = p.tri; ap.tri_cap = p.tri_cap;
     gt::lpf_area_kernel<<<(p.nframes + 3) / 4, 128, 0, st>>>(ap);
     CK(cudaGetLastError());
+    CK(cudaMemcpyFromSymbolAsync(c->undecided_h, gt::g_xcalls, 8, 0, cudaMemcpyDeviceToHost, st));
+    c->last_frames = p.nframes; c->pending = true;
     CK(cudaEventRecord(c->done, st));
     return GTA_B200_OK;
 }

@@ -36,13 +36,13 @@ __device__ __forceinline__ LFrame lpf_frame(const LpfWs& ws, int fr) {
 constexpr int LPF_STRIDE = 1152;      // slot capacity of a block = stride of the word-major state array (a constant: the state
                                       // accesses of a step become base + immediate offset)
 
-template <int PH>
+template <int PH, bool AP>
 __device__ __noinline__ int lpf_wave_phase(uint32_t* st, int sl, Pt* pt, LRec* rec, u16* head, int n, int cap_e, uint32_t* err_out) {
     LFrame f; f.pt = pt; f.rec = rec; f.head = head; f.n = n; f.cap_e = cap_e;
     LState s;
     uint32_t* mine = st + sl;
     ls_unpack(s, [&](int w) { return mine[w * LPF_STRIDE]; });
-    lpf_step_t<PH>(f, s);
+    lpf_step_t<PH, AP>(f, s);
     ls_writeback<PH>(s, [&](int w, uint32_t v) { mine[w * LPF_STRIDE] = v; });
     if (s.phase == LP_DONE) *err_out = s.err;
     return s.phase;
@@ -54,7 +54,7 @@ __device__ __noinline__ int lpf_wave_phase(uint32_t* st, int sl, Pt* pt, LRec* r
 // step for them and file each slot under its new phase for the next round (double-buffered bins): no divergence
 // between lanes, 64 dependent-load chains in flight per warp. A slot whose frame is finished goes to the
 // "needs a frame" bin and takes the next frame of the batch from a global counter.
-template <int THREADS>
+template <int THREADS, bool AP>
 __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p, const int SLOTS) {
     extern __shared__ __align__(16) unsigned char lsm[];
     constexpr int NB = LP_DONE + 1;                                        // one bin per phase + one for slots that need a frame
@@ -130,13 +130,13 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
                     u16* fhead = p.ws.head + (size_t)fr * p.ws.cap; const int fn = slot_n[sl], fce = p.ws.cap_e;
                     uint32_t* eo = p.ws.err + fr;
                     switch (bin) {                                        // every lane of the chunk is in this phase
-                    case LP_LEAF: next = lpf_wave_phase<LP_LEAF>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
-                    case LP_TINIT: next = lpf_wave_phase<LP_TINIT>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
-                    case LP_TAN: next = lpf_wave_phase<LP_TAN>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
-                    case LP_INS: next = lpf_wave_phase<LP_INS>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
-                    case LP_SCAN: next = lpf_wave_phase<LP_SCAN>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
-                    case LP_V: next = lpf_wave_phase<LP_V>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
-                    default: next = lpf_wave_phase<LP_C>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
+                    case LP_LEAF: next = lpf_wave_phase<LP_LEAF, AP>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
+                    case LP_TINIT: next = lpf_wave_phase<LP_TINIT, AP>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
+                    case LP_TAN: next = lpf_wave_phase<LP_TAN, AP>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
+                    case LP_INS: next = lpf_wave_phase<LP_INS, AP>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
+                    case LP_SCAN: next = lpf_wave_phase<LP_SCAN, AP>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
+                    case LP_V: next = lpf_wave_phase<LP_V, AP>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
+                    default: next = lpf_wave_phase<LP_C, AP>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
                     }
                 }
                 bin_next[(size_t)next * SLOTS + atomicAdd(&c_next[next], 1)] = (u16)sl;

@@ -204,12 +204,13 @@ GT_INLINE void lp_new_edge(const LFrame& f, LState& s, const LPair& spec, bool f
 }
 
 // The choice between the two candidates (reference :582-593; ties prefer the right one) and the new cross edge.
+template <bool AP>
 GT_INLINE void lp_decide(const LFrame& f, LState& s, const LPair& spec, bool freed, int prev_head) {
     bool go_left = true;
     if (s.vR) {
         go_left = false;
         if (s.vL && s.r1 != s.l1) {
-            int sg = incircle_sign(s.pli.x, s.pli.y, s.pri.x, s.pri.y, s.pr1.x, s.pr1.y, s.pl1.x, s.pl1.y);
+            int sg = incircle_sign<AP>(s.pli.x, s.pli.y, s.pri.x, s.pri.y, s.pr1.x, s.pr1.y, s.pl1.x, s.pl1.y);
             if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
             go_left = sg > 0;
         }
@@ -243,7 +244,7 @@ GT_INLINE void lp_place(const LFrame& f, LState& s, int which, int P, int IN, in
 }
 
 // ---------------------------------------------------------------- one iteration of phase PH
-template <int PH>
+template <int PH, bool AP = true>
 GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
     const LPair zero = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     // the free list's head, for the phases that may need a new edge at the end of the iteration
@@ -255,7 +256,7 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
         const int a = s.ia, b = s.ia + 1, c = s.ib;
         const Pt pa = lf_pt(f, a), pb = lf_pt(f, b), pc = lf_pt(f, c);
         int sg = 0;
-        if (c != b) { sg = orient2d_sign(pa.x, pa.y, pb.x, pb.y, pc.x, pc.y); if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; } }
+        if (c != b) { sg = orient2d_sign<AP>(pa.x, pa.y, pb.x, pb.y, pc.x, pc.y); if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; } }
         auto take = [&](LPair sp) -> int {
             if (s.free_head != (int)GT_NIL) { const int e = s.free_head; s.free_head = sp.a.nxt; return e; }
             if (s.bump >= f.cap_e) { s.err |= GT_ERR_POOL; return -1; }
@@ -320,14 +321,14 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
         if (a0) c0 = lf_pt(f, p0.a.dst);
         if (a1) { c1 = lf_pt(f, p1.a.dst); hd1c = f.head[p1.a.dst]; }
         if (a0) {
-            int sg = orient2d_sign(c0.x, c0.y, s.pr1.x, s.pr1.y, s.pl1.x, s.pl1.y);
+            int sg = orient2d_sign<AP>(c0.x, c0.y, s.pr1.x, s.pr1.y, s.pl1.x, s.pl1.y);
             if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
             if (s.uSub == 0) { if (sg > 0) { s.uHr = p0.b.prv; s.uy = p0.a.dst; s.pl1 = c0; } else s.uSub = 1; }        // pred(rfast, y)
             else if (sg > 0) { s.uHl = p0.b.nxt; s.ux = p0.a.dst; s.pr1 = c0; s.uSub = 0; }                           // succ(lfast, x)
             else s.uSub = 2;
         }
         if (a1) {
-            int sg = orient2d_sign(c1.x, c1.y, s.pri.x, s.pri.y, s.pli.x, s.pli.y);
+            int sg = orient2d_sign<AP>(c1.x, c1.y, s.pri.x, s.pri.y, s.pli.x, s.pli.y);
             if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
             if (s.lSub == 0) { if (sg > 0) { s.lHr = p1.b.nxt; s.ri = p1.a.dst; s.pri = c1; s.headR = hd1c; } else s.lSub = 1; }   // succ(rfast, y)
             else if (sg > 0) { s.lHl = p1.b.prv; s.li = p1.a.dst; s.pli = c1; s.headL = hd1c; s.lSub = 0; }                   // pred(lfast, x)
@@ -360,7 +361,7 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
         if (m0) d0 = lf_pt(f, q0.a.dst);
         if (m1) d1 = lf_pt(f, q1.a.dst);
         if (a0) {
-            int sg = orient2d_sign(s.pri.x, s.pri.y, c0.x, c0.y, s.pli.x, s.pli.y);
+            int sg = orient2d_sign<AP>(s.pri.x, s.pri.y, c0.x, c0.y, s.pli.x, s.pli.y);
             if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
             const bool res = sg > 0;
             if (PH == LP_INS) {
@@ -368,7 +369,7 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
                 if (!res) { if (s.first_edge) lp_place(f, s, 0, s.li, s.ri, s.h0, last, hd, false, hd); else lp_place(f, s, 0, s.li, s.ri, s.h0, s.at0, s.nx0, false, hd); }
                 else if (last == hd) lp_place(f, s, 0, s.li, s.ri, s.h0, hd, hd, true, hd);          // single-entry ring: right of all
                 else {
-                    int sl = orient2d_sign(s.pri.x, s.pri.y, d0.x, d0.y, s.pli.x, s.pli.y);
+                    int sl = orient2d_sign<AP>(s.pri.x, s.pri.y, d0.x, d0.y, s.pli.x, s.pli.y);
                     if (sl == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sl = 0; }
                     if (!(sl > 0)) lp_place(f, s, 0, s.li, s.ri, s.h0, last, hd, false, hd);          // not right of "last": goes after it
                     else if ((int)q0.a.prv == hd) lp_place(f, s, 0, s.li, s.ri, s.h0, last, hd, true, hd);      // right of all: new "first"
@@ -381,7 +382,7 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
             } else { lp_place(f, s, 0, s.li, s.ri, s.h0, s.cur0, p0.a.nxt, false, s.hd0); s.scan0 = 0; }
         }
         if (a1) {
-            int sg = orient2d_sign(s.pli.x, s.pli.y, c1.x, c1.y, s.pri.x, s.pri.y);
+            int sg = orient2d_sign<AP>(s.pli.x, s.pli.y, c1.x, c1.y, s.pri.x, s.pri.y);
             if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
             const bool res = sg > 0;
             const int h1 = s.h0 ^ 1;
@@ -390,7 +391,7 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
                 if (!res) { if (s.first_edge) lp_place(f, s, 1, s.ri, s.li, h1, last, hd, false, hd); else lp_place(f, s, 1, s.ri, s.li, h1, s.at1, s.nx1, false, hd); }
                 else if (last == hd) lp_place(f, s, 1, s.ri, s.li, h1, hd, hd, true, hd);
                 else {
-                    int sl = orient2d_sign(s.pli.x, s.pli.y, d1.x, d1.y, s.pri.x, s.pri.y);
+                    int sl = orient2d_sign<AP>(s.pli.x, s.pli.y, d1.x, d1.y, s.pri.x, s.pri.y);
                     if (sl == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sl = 0; }
                     if (!(sl > 0)) lp_place(f, s, 1, s.ri, s.li, h1, last, hd, false, hd);
                     else if ((int)q1.a.prv == hd) lp_place(f, s, 1, s.ri, s.li, h1, last, hd, true, hd);
@@ -412,14 +413,14 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
         const LPair p0 = lf_pair(f, s.hr1), p1 = lf_pair(f, s.hl1);
         const Pt c0 = lf_pt(f, p0.a.dst), c1 = lf_pt(f, p1.a.dst);
         s.hdR1 = f.head[p0.a.dst]; s.hdL1 = f.head[p1.a.dst];
-        int sg0 = orient2d_sign(c0.x, c0.y, s.pli.x, s.pli.y, s.pri.x, s.pri.y);
-        int sg1 = orient2d_sign(c1.x, c1.y, s.pli.x, s.pli.y, s.pri.x, s.pri.y);
+        int sg0 = orient2d_sign<AP>(c0.x, c0.y, s.pli.x, s.pli.y, s.pri.x, s.pri.y);
+        int sg1 = orient2d_sign<AP>(c1.x, c1.y, s.pli.x, s.pli.y, s.pri.x, s.pri.y);
         if (sg0 == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg0 = 0; }
         if (sg1 == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg1 = 0; }
         s.r1 = p0.a.dst; s.pr1 = c0; s.hr2 = p0.a.prv; s.t1_prv = p0.b.prv; s.t1_nxt = p0.b.nxt;
         s.l1 = p1.a.dst; s.pl1 = c1; s.hl2 = p1.a.nxt; s.u1_prv = p1.b.prv; s.u1_nxt = p1.b.nxt;
         s.vR = sg0 > 0; s.vL = sg1 > 0; s.actR = s.vR; s.actL = s.vL;
-        if (s.actR || s.actL) s.phase = LP_C; else lp_decide(f, s, spec, false, 0);
+        if (s.actR || s.actL) s.phase = LP_C; else lp_decide<AP>(f, s, spec, false, 0);
         return;
     }
 
@@ -436,7 +437,7 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
             const int r2 = p0.a.dst;
             int sg = 0;
             if (!(r2 == s.li || r2 == s.ri || r2 == s.r1))                          // a repeated point: exactly 0
-                sg = incircle_sign(s.pr1.x, s.pr1.y, s.pli.x, s.pli.y, s.pri.x, s.pri.y, c0.x, c0.y);
+                sg = incircle_sign<AP>(s.pr1.x, s.pr1.y, s.pli.x, s.pli.y, s.pri.x, s.pri.y, c0.x, c0.y);
             if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
             if (sg > 0) {
                 // ri's ring loses hr1 (its next is the cross edge), r1's ring loses the twin
@@ -453,7 +454,7 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
             const int l2 = p1.a.dst;
             int sg = 0;
             if (!(l2 == s.li || l2 == s.ri || l2 == s.l1))
-                sg = incircle_sign(s.pli.x, s.pli.y, s.pri.x, s.pri.y, s.pl1.x, s.pl1.y, c1.x, c1.y);
+                sg = incircle_sign<AP>(s.pli.x, s.pli.y, s.pri.x, s.pri.y, s.pl1.x, s.pl1.y, c1.x, c1.y);
             if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
             if (sg > 0) {
                 const int h = s.hl1, tw = h ^ 1;
@@ -465,7 +466,7 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
                 s.hl1 = s.hl2; s.l1 = l2; s.pl1 = c1; s.hl2 = p1.a.nxt; s.u1_prv = p1.b.prv; s.u1_nxt = p1.b.nxt; s.hdL1 = hn1;
             } else s.actL = 0;
         }
-        if (!(s.actR || s.actL)) lp_decide(f, s, spec, freed, prev_head);
+        if (!(s.actR || s.actL)) lp_decide<AP>(f, s, spec, freed, prev_head);
         return;
     }
 }

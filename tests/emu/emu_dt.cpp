@@ -11,7 +11,7 @@
 #define GT_STATS 1
 #include "../../g_tessla_b200/csrc/dt_core.cuh"
 #include "../../g_tessla_b200/csrc/lpf_core.cuh"
-namespace gt { Stats g_stats; }
+namespace gt { Stats g_stats; long g_exact_calls[8]; }
 
 extern "C" {
 
@@ -19,6 +19,12 @@ extern "C" {
 // merge steps, cuts, longest node (steps)
 static long g_level[32][6];
 void emu_level_stats(long* out) { memcpy(out, g_level, sizeof g_level); }
+// exact-stage counters since the last call: orient2d with 1/2/4 words, incircle with 1/2/4 words, total orient2d, total incircle
+void emu_exact_stats(long* out) {
+    memcpy(out, gt::g_exact_calls, sizeof gt::g_exact_calls);
+    out[6] = gt::g_stats.o2d; out[7] = gt::g_stats.icc;
+    memset(gt::g_exact_calls, 0, sizeof gt::g_exact_calls); gt::g_stats.o2d = gt::g_stats.icc = 0;
+}
 
 // points [n][2] -> triangles in emission order (indices into the input). Returns ntri or -(err bits).
 int emu_triangulate(const double* points, int n, int* tri_out) {
