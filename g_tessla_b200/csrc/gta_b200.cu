@@ -134,6 +134,15 @@ int lpf_threshold() {
 // (triangle lists are a parity-test output: they stay on the fused kernel unless the lane-per-frame path is forced)
 bool use_lpf(int nframes, const Shape& s, bool want_tri) { return lpf_threshold() > 0 && nframes >= lpf_threshold() && s.cap < 4000 && (!want_tri || lpf_threshold() == 1); }
 
+// Most frames one lane-per-frame launch should get: one slot per frame and SM-resident block. Beyond that the kernel
+// refills slots as frames finish, and since the frames of a batch finish together the refill runs nearly empty
+// (131,072 frames in one launch: 194 k frames/s; as 2 x 65,536: 298 k). Larger batches are split evenly.
+long long lpf_frames_per_launch(int dev) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    return (long long)sms * gt::LPF_MAX_SLOTS;
+}
+
 int lpf_ensure(int dev, size_t frames, int cap, int cap_e, LpfCache** out) {
     std::lock_guard<std::mutex> lk(g_lpf_mu);
     LpfCache& c = g_lpf[dev];
@@ -176,10 +185,10 @@ int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st) {
     rc = launch(p, s, st);
     if (rc) return rc;
     // 2. one lane per frame
-    gt::LpfParams lp; lp.ws = c->ws; lp.nframes = p.nframes; lp.counter = c->counter;
+    gt::LpfParams lp; lp.ws = c->ws; lp.nframes = p.nframes; lp.counter = c->counter; lp.dbg = p.dbg ? p.dbg + 32 : nullptr;
     CK(cudaMemsetAsync(c->counter, 0, 4, st));
     static int slots = -1, wthreads = -1;                    // frames in flight per block / threads per block (experiments: GTA_B200_LPF_SLOTS, _THREADS)
-    if (slots < 0) { const char* e = getenv("GTA_B200_LPF_SLOTS"); slots = e ? atoi(e) : gt::LPF_STRIDE; }
+    if (slots < 0) { const char* e = getenv("GTA_B200_LPF_SLOTS"); slots = e ? atoi(e) : gt::LPF_MAX_SLOTS; }
     if (wthreads < 0) { const char* e = getenv("GTA_B200_LPF_THREADS"); wthreads = e ? atoi(e) : 0; }
     // Which build of the kernel? Without stage A' of the predicates (gt_predicates.cuh) the steps fit 128 registers and
     // 14 warps per SM: best when the FP filter decides everything, as it does on real coordinates (cfg 3: 263 k frames/s
@@ -194,16 +203,19 @@ int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st) {
         // spread the batch over every SM: fewer slots per block shorten the round when the batch is small
         const int blocks = std::max(1, std::min(sms, (p.nframes + 63) / 64));
         int S = (p.nframes + blocks - 1) / blocks;
-        S = std::max(64, std::min((S + 31) & ~31, std::min(slots, gt::LPF_STRIDE)));
-        const size_t smem = (size_t)gt::LS_WORDS * gt::LPF_STRIDE * 4 + (size_t)S * 4 + (size_t)S * 2 + 2 * (size_t)(gt::LP_DONE + 1) * S * 2 + (48 + 4) * 4 + 64;
+        S = std::max(64, std::min((S + 31) & ~31, std::min(slots, gt::LPF_MAX_SLOTS)));
+        static int xcarve = -1;                                  // (experiments: GTA_B200_LPF_CARVE = carve-out in percent)
+        if (xcarve < 0) { const char* e = getenv("GTA_B200_LPF_CARVE"); xcarve = e ? atoi(e) : 0; }
+        const size_t smem = (size_t)gt::LS_WORDS * gt::LPF_MAX_SLOTS * 4 + (size_t)S * 4 + (size_t)S * 2 + 2 * (size_t)(gt::LP_DONE + 1) * S * 2 + (48 + 8) * 4 + 64;
         auto go = [&](auto kern, int threads) -> int {
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // everything that is not shared memory should be L1: ask for the smallest carve-out that holds the block
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, xcarve ? xcarve : (int)std::min<size_t>(100, (smem + 1024) * 100 / (228 * 1024) + 1)));
             kern<<<blocks, threads, smem, st>>>(lp, S);
             CK(cudaGetLastError());
             return GTA_B200_OK;
         };
-        if (wthreads == 256) rc = go(gt::lpf_wave_kernel<256, true>, 256);                 // (experiments)
-        else if (wthreads == 512) rc = go(gt::lpf_wave_kernel<512, false>, 512);
+        if (wthreads == 512) rc = go(gt::lpf_wave_kernel<512, false>, 512);                 // (experiment)
         else if (c->degenerate || wthreads == 384) rc = go(gt::lpf_wave_kernel<384, true>, 384);
         else rc = go(gt::lpf_wave_kernel<448, false>, 448);
         if (rc) return rc;
@@ -311,8 +323,32 @@ int gta_b200_tessellate_device(const double* d_xyz, int in_dim, const double* d_
     p.work = d_work; p.coop_nodes = coop_nodes_for(s.threads); p.dbg = g_dbg; p.ws = gt::LpfWs{};
     CK(cudaMemsetAsync(d_work, 0, sizeof(unsigned int), st));
     const bool lpf = use_lpf(nframes, s, d_tri != nullptr);
-    g_last_launches = lpf ? 3 : 1;                              // pre-pass + lane-per-frame + area, or the fused kernel
-    return lpf ? launch_lpf(p, s, st) : launch(p, s, st);
+    if (!lpf) { g_last_launches = 1; return launch(p, s, st); }                      // the fused kernel
+    // lane per frame: pre-pass + state machine + area per launch; batches beyond one launch's worth are split evenly
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    const long long per_launch = lpf_frames_per_launch(dev);
+    const long long parts = (nframes + per_launch - 1) / per_launch;
+    g_last_launches = 3 * (int)parts;
+    for (long long k = 0; k < parts; ++k) {
+        const long long f0 = (long long)nframes * k / parts, f1 = (long long)nframes * (k + 1) / parts;
+        gt::KParams q = p;
+        q.nframes = (int)(f1 - f0);
+        q.xyz = d_xyz + (size_t)f0 * natoms * in_dim;
+        if (d_box) q.box = d_box + (size_t)f0 * box_stride;
+        if (d_area) q.area = d_area + f0;
+        if (d_area2d) q.area2d = d_area2d + f0;
+        if (d_areabox) q.areabox = d_areabox + f0;
+        if (d_status) q.status = d_status + f0;
+        if (d_tri) q.tri = d_tri + (size_t)f0 * tri_cap * 3;
+        if (d_ntri) q.ntri = d_ntri + f0;
+        if (d_corr) q.corr = d_corr + (size_t)f0 * corr_cap * 3;
+        if (d_ncorr) q.ncorr = d_ncorr + f0;
+        if (k) CK(cudaMemsetAsync(d_work, 0, sizeof(unsigned int), st));
+        const int rc = launch_lpf(q, s, st);
+        if (rc) return rc;
+    }
+    return GTA_B200_OK;
 }
 
 }  // extern "C"
@@ -486,7 +522,8 @@ int run_job(Job j, int device, int nstreams) {
     if (use_lpf(j.nframes, shp, j.tri != nullptr)) {
         // lane-per-frame path: it wants tens of thousands of frames per launch; two slots so that the copies of one
         // chunk overlap the kernels of the other
-        const long long nchunks = (j.nframes + 131071) / 131072;
+        const long long per_launch = lpf_frames_per_launch(device);
+        const long long nchunks = (j.nframes + per_launch - 1) / per_launch;
         chunk = (j.nframes + nchunks - 1) / nchunks;
         nstreams = (int)std::min<long long>(2, nchunks);
     }
@@ -614,10 +651,10 @@ static int signs_common(const double* pts, int n, int* out, int device, int widt
     return GTA_B200_OK;
 }
 // Debug hook (not in the public header): allocate / read the phase timers of GT_PHASE_TIMING builds.
-int gta_b200_dbg_timers(unsigned long long* out32, int reset) {
-    if (!g_dbg) { if (cudaMalloc((void**)&g_dbg, 32 * 8) != cudaSuccess) return -1; cudaMemset(g_dbg, 0, 32 * 8); }
-    if (out32) cudaMemcpy(out32, g_dbg, 32 * 8, cudaMemcpyDeviceToHost);
-    if (reset) cudaMemset(g_dbg, 0, 32 * 8);
+int gta_b200_dbg_timers(unsigned long long* out64, int reset) {       // [0..31] fused kernel, [32..63] lane-per-frame kernel
+    if (!g_dbg) { if (cudaMalloc((void**)&g_dbg, 64 * 8) != cudaSuccess) return -1; cudaMemset(g_dbg, 0, 64 * 8); }
+    if (out64) cudaMemcpy(out64, g_dbg, 64 * 8, cudaMemcpyDeviceToHost);
+    if (reset) cudaMemset(g_dbg, 0, 64 * 8);
     return 0;
 }
 int gta_b200_orient2d_signs(const double* pts, int n, int* sign_out, int device) { return signs_common(pts, n, sign_out, device, 6); }

@@ -16,6 +16,7 @@ struct LpfParams {
     LpfWs ws;
     int nframes;
     unsigned int* counter;                 // next frame to hand out
+    unsigned long long* dbg;               // -DGT_PHASE_TIMING builds: [3*ph] cycles, [3*ph+1] chunks, [3*ph+2] lanes; [24] barrier wait, [25] rounds x warps
 };
 
 __device__ __forceinline__ LFrame lpf_frame(const LpfWs& ws, int fr) {
@@ -33,17 +34,22 @@ __device__ __forceinline__ LFrame lpf_frame(const LpfWs& ws, int fr) {
 // (inlined into one kernel, the 14 instances share a 128-register budget and spill ~1 KB per thread). The state
 // is unpacked straight from shared memory -- loads of words the phase never reads are dead code -- and only the
 // words the phase may modify (LsDirty<PH>) are written back. Returns the packed phase word's new phase.
-constexpr int LPF_STRIDE = 1152;      // slot capacity of a block = stride of the word-major state array (a constant: the state
-                                      // accesses of a step become base + immediate offset)
+// LPF_MAX_SLOTS = slot capacity of a block = stride of the word-major state array (a constant: the state accesses of a
+// step become base + immediate offset). Deliberately far below what shared memory could hold:
+//  - what is not shared memory is L1, and the steps' loads want it (704 slots in use: 180 k frames/s when the block
+//    needs the 228 KB carve-out and leaves 28 KB of L1, 257 k with 196 KB, 281 k with 164 KB or less);
+//  - a round serves 14 warps; more than ~448 slots per block only queue (66 k frames per launch: 300 k frames/s,
+//    100 k: 281 k) -- the host splits larger batches into even launches instead (gta_b200.cu).
+constexpr int LPF_MAX_SLOTS = 576;
 
 template <int PH, bool AP>
 __device__ __noinline__ int lpf_wave_phase(uint32_t* st, int sl, Pt* pt, LRec* rec, u16* head, int n, int cap_e, uint32_t* err_out) {
     LFrame f; f.pt = pt; f.rec = rec; f.head = head; f.n = n; f.cap_e = cap_e;
     LState s;
     uint32_t* mine = st + sl;
-    ls_unpack(s, [&](int w) { return mine[w * LPF_STRIDE]; });
+    ls_unpack(s, [&](int w) { return mine[w * LPF_MAX_SLOTS]; });
     lpf_step_t<PH, AP>(f, s);
-    ls_writeback<PH>(s, [&](int w, uint32_t v) { mine[w * LPF_STRIDE] = v; });
+    ls_writeback<PH>(s, [&](int w, uint32_t v) { mine[w * LPF_MAX_SLOTS] = v; });
     if (s.phase == LP_DONE) *err_out = s.err;
     return s.phase;
 }
@@ -58,8 +64,8 @@ template <int THREADS, bool AP>
 __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p, const int SLOTS) {
     extern __shared__ __align__(16) unsigned char lsm[];
     constexpr int NB = LP_DONE + 1;                                        // one bin per phase + one for slots that need a frame
-    uint32_t* st = reinterpret_cast<uint32_t*>(lsm);                       // [LS_WORDS][LPF_STRIDE]
-    int* slot_fr = reinterpret_cast<int*>(st + (size_t)LS_WORDS * LPF_STRIDE);  // [SLOTS] frame of the slot
+    uint32_t* st = reinterpret_cast<uint32_t*>(lsm);                       // [LS_WORDS][LPF_MAX_SLOTS]
+    int* slot_fr = reinterpret_cast<int*>(st + (size_t)LS_WORDS * LPF_MAX_SLOTS);  // [SLOTS] frame of the slot
     u16* slot_n = reinterpret_cast<u16*>(slot_fr + SLOTS);                 // [SLOTS] its point count
     u16* bins = slot_n + SLOTS;                                            // [2][NB][SLOTS] slots of each phase, this round / next round
     int* cnt = reinterpret_cast<int*>(bins + 2 * (size_t)NB * SLOTS);      // [3][16] slots per bin: this round / next round / being cleared
@@ -85,8 +91,13 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
         u16* bin_next = bins + (size_t)(b ^ 1) * NB * SLOTS;
         // ---- chunk table, computed by every warp for itself: lane q holds bin q's count and first chunk
         const bool exhausted = ctl[0] != 0;
-        int myc = lane < NB ? c_now[lane] : 0;
-        if (lane == LP_DONE && exhausted) myc = 0;                        // nothing left to fetch: empty slots stay empty
+        // (position q of the table is bin ORDER[q]: the phases with the longest steps first, so that the round's last
+        // chunks are its shortest and the warps reach the barrier closer together)
+        constexpr unsigned ORDER = (unsigned)LP_INS | (unsigned)LP_SCAN << 4 | (unsigned)LP_C << 8 | (unsigned)LP_TAN << 12 | (unsigned)LP_V << 16
+                                 | (unsigned)LP_LEAF << 20 | (unsigned)LP_TINIT << 24 | (unsigned)LP_DONE << 28;
+        const int qbin = (int)((ORDER >> (4 * (lane & 7))) & 15u);
+        int myc = lane < NB ? c_now[qbin] : 0;
+        if (qbin == LP_DONE && exhausted) myc = 0;                        // nothing left to fetch: empty slots stay empty
         int incl = (myc + 31) >> 5;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
@@ -102,9 +113,10 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
             c = __shfl_sync(0xffffffffu, c, 0);
             if (c >= nchunks) break;
             // first_chunk is non-decreasing over the bins: the last bin that starts at or before c owns chunk c
-            const int bin = __popc(__ballot_sync(0xffffffffu, lane < NB && first_chunk <= c)) - 1;    // warp-uniform
-            const int idx = (c - __shfl_sync(0xffffffffu, first_chunk, bin)) * 32 + lane;
-            const int nph = __shfl_sync(0xffffffffu, myc, bin);
+            const int q = __popc(__ballot_sync(0xffffffffu, lane < NB && first_chunk <= c)) - 1;      // warp-uniform
+            const int bin = (int)((ORDER >> (4 * q)) & 15u);
+            const int idx = (c - __shfl_sync(0xffffffffu, first_chunk, q)) * 32 + lane;
+            const int nph = __shfl_sync(0xffffffffu, myc, q);
             if (idx < nph) {
                 const int sl = bin_now[(size_t)bin * SLOTS + idx];
                 int next = LP_DONE;
@@ -119,7 +131,7 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
                         LState s = {};
                         lp_begin(f, s);
                         if (s.phase == LP_DONE) continue;
-                        ls_pack(s, [&](int w, uint32_t v) { st[w * LPF_STRIDE + sl] = v; });
+                        ls_pack(s, [&](int w, uint32_t v) { st[w * LPF_MAX_SLOTS + sl] = v; });
                         slot_fr[sl] = fr; slot_n[sl] = (u16)f.n;
                         next = s.phase;
                         break;
@@ -129,6 +141,9 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
                     Pt* fpt = p.ws.pt + (size_t)fr * p.ws.cap; LRec* frec = p.ws.rec + (size_t)fr * 2 * (size_t)p.ws.cap_e;
                     u16* fhead = p.ws.head + (size_t)fr * p.ws.cap; const int fn = slot_n[sl], fce = p.ws.cap_e;
                     uint32_t* eo = p.ws.err + fr;
+#ifdef GT_PHASE_TIMING
+                    const long long tk0 = clock64();
+#endif
                     switch (bin) {                                        // every lane of the chunk is in this phase
                     case LP_LEAF: next = lpf_wave_phase<LP_LEAF, AP>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
                     case LP_TINIT: next = lpf_wave_phase<LP_TINIT, AP>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
@@ -138,11 +153,23 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
                     case LP_V: next = lpf_wave_phase<LP_V, AP>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
                     default: next = lpf_wave_phase<LP_C, AP>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
                     }
+#ifdef GT_PHASE_TIMING
+                    if (p.dbg) {
+                        const long long tk1 = clock64(); const unsigned am = __activemask();
+                        if (lane == __ffs(am) - 1) { atomicAdd(p.dbg + 3 * bin, (unsigned long long)(tk1 - tk0)); atomicAdd(p.dbg + 3 * bin + 1, 1ull); atomicAdd(p.dbg + 3 * bin + 2, (unsigned long long)__popc(am)); }
+                    }
+#endif
                 }
                 bin_next[(size_t)next * SLOTS + atomicAdd(&c_next[next], 1)] = (u16)sl;
             }
         }
+#ifdef GT_PHASE_TIMING
+        const long long tb0 = clock64();
         __syncthreads();
+        if (p.dbg && lane == 0) { atomicAdd(p.dbg + 24, (unsigned long long)(clock64() - tb0)); atomicAdd(p.dbg + 25, 1ull); }
+#else
+        __syncthreads();
+#endif
     }
 }
 

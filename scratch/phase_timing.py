@@ -5,7 +5,7 @@ import g_tessla_b200.api as api
 api.lib_path = lambda: os.path.abspath('scratch/libdbg.so')
 from g_tessla_b200 import synth
 L = api.lib()
-out = (C.c_ulonglong * 32)()
+out = (C.c_ulonglong * 64)()
 L.gta_b200_dbg_timers(None, 1)
 c = synth.config(3, nframes=3000)
 api.tessellate(c['xyz'], c['box'], c['espace'], c['flags'])

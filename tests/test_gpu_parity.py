@@ -196,3 +196,27 @@ def test_lane_per_frame_raw_sets_and_status(gta, checker, lane_per_frame, golden
     ok = np.ones(40, bool); ok[[7, 11]] = False
     want = checker.tessellate(c["xyz"][ok], c["box"][ok], c["espace"], c["flags"])
     assert np.allclose(r["area"][ok], want["area"], rtol=RTOL, atol=0)
+
+
+def test_lane_per_frame_batch_larger_than_one_launch(gta, checker):
+    """A batch above one launch's worth of slots (148 SMs x 576) is split into even launches by the device call and into
+    even chunks by the host call: every frame must come out exactly as from a small batch (cfg 1 frames, tiled)."""
+    import torch
+    c = synth.config(1, nframes=500)
+    reps = 240                                                  # 120,000 frames > 85,248
+    xyz = np.tile(c["xyz"], (reps, 1, 1)); box = np.tile(c["box"], (reps, 1))
+    want = checker.tessellate(c["xyz"], c["box"], c["espace"], c["flags"], nthreads=0)
+    n = c["xyz"].shape[1]
+    maxp = n + 4 + 4 * int(c["box"][:, :2].max() / c["espace"] + 1)
+    T = gta.Tessellator(len(xyz), n, maxp, c["espace"], c["flags"])
+    T.run(torch.from_numpy(xyz).cuda(), torch.from_numpy(box).cuda(), 3)
+    torch.cuda.synchronize()
+    assert int((T.status != 0).sum()) == 0
+    area = T.area.cpu().numpy().reshape(reps, -1)
+    assert (area == area[0]).all()                              # same frame, same bits, whichever launch it went into
+    assert np.allclose(area[0], want["area"], rtol=RTOL, atol=0)
+    assert np.array_equal(T.areabox.cpu().numpy()[:500], want["areabox"])
+    assert (T.ntri.cpu().numpy().reshape(reps, -1) == T.ntri.cpu().numpy()[:500]).all()
+    r = gta.tessellate(xyz, box, c["espace"], c["flags"])       # host buffers: chunked pipeline
+    assert (r["status"] == 0).all()
+    assert np.array_equal(r["area"].reshape(reps, -1), area)
