@@ -147,17 +147,14 @@ int lpf_ensure(int dev, size_t frames, int cap, int cap_e, LpfCache** out) {
     std::lock_guard<std::mutex> lk(g_lpf_mu);
     LpfCache& c = g_lpf[dev];
     if (c.frames < frames || c.cap < cap || c.cap_e < cap_e) {
-        cudaFree(c.ws.pt); cudaFree(c.ws.z); cudaFree(c.ws.rec); cudaFree(c.ws.head); cudaFree(c.ws.perm);
+        cudaFree(c.ws.pt); cudaFree(c.ws.rec);
         cudaFree(c.ws.n); cudaFree(c.ws.st); cudaFree(c.ws.err); cudaFree(c.counter);
         if (c.done) { cudaDeviceSynchronize(); cudaEventDestroy(c.done); }
         if (c.undecided_h) cudaFreeHost(c.undecided_h);
         c = LpfCache();
         frames = std::max(frames, c.frames); cap = std::max(cap, c.cap); cap_e = std::max(cap_e, c.cap_e);
-        CK(cudaMalloc((void**)&c.ws.pt, sizeof(gt::Pt) * frames * cap));
-        CK(cudaMalloc((void**)&c.ws.z, sizeof(double) * frames * cap));
+        CK(cudaMalloc((void**)&c.ws.pt, sizeof(gt::LPt) * frames * cap));
         CK(cudaMalloc((void**)&c.ws.rec, sizeof(gt::LRec) * frames * 2 * (size_t)cap_e));
-        CK(cudaMalloc((void**)&c.ws.head, 2 * frames * cap));
-        CK(cudaMalloc((void**)&c.ws.perm, 2 * frames * cap));
         CK(cudaMalloc((void**)&c.ws.n, 4 * frames)); CK(cudaMalloc((void**)&c.ws.st, 4 * frames)); CK(cudaMalloc((void**)&c.ws.err, 4 * frames));
         CK(cudaMalloc((void**)&c.counter, 4));
         CK(cudaMallocHost((void**)&c.undecided_h, 8)); *c.undecided_h = 0;

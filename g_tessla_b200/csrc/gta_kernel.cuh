@@ -26,7 +26,7 @@ namespace gt {
 
 // Global-memory workspace of the lane-per-frame path (gta_lpf.cuh): one slot per frame of the batch.
 struct LpfWs {
-    Pt* pt; double* z; LRec* rec; u16* head; u16* perm;     // strides per frame: cap, cap, 2*cap_e, cap, cap
+    LPt* pt; LRec* rec;                                      // strides per frame: cap (x, y, z, ring head, input index), 2*cap_e
     int* n; int* st; uint32_t* err;                          // per frame: point count, status bits of the pre-pass, D&C error bits
     int cap, cap_e;
 };
@@ -309,12 +309,12 @@ __global__ void __launch_bounds__(T, MINB) tessellate_kernel(const KParams p) {
             // workspace slot; the triangulation and the area sum are separate launches (gta_lpf.cuh)
             const size_t slot = (size_t)fr;
             if (ctl[4] == 0) {
-                Pt* wpt = p.ws.pt + slot * p.ws.cap; double* wz = p.ws.z + slot * p.ws.cap;
-                u16* whead = p.ws.head + slot * p.ws.cap; u16* wperm = p.ws.perm + slot * p.ws.cap;
+                LPt* wpt = p.ws.pt + slot * p.ws.cap;
                 for (int i = tid; i < n; i += T) {
                     const int o = perm[i];
-                    wpt[i] = pt[i]; wz[i] = o < natoms ? atom_z(o) : zcorr[o - natoms];
-                    whead[i] = (u16)GT_NIL; wperm[i] = (u16)o;
+                    LPt r; r.x = pt[i].x; r.y = pt[i].y; r.z = o < natoms ? atom_z(o) : zcorr[o - natoms];
+                    r.head = (u16)GT_NIL; r.perm = (u16)o; r.pad = 0;
+                    wpt[i] = r;
                 }
             }
             if (tid == 0) {

@@ -24,7 +24,6 @@ __device__ __forceinline__ LFrame lpf_frame(const LpfWs& ws, int fr) {
     const size_t s = (size_t)fr;
     f.pt = ws.pt + s * ws.cap;
     f.rec = ws.rec + s * 2 * (size_t)ws.cap_e;
-    f.head = ws.head + s * ws.cap;
     f.n = ws.n[s];
     f.cap_e = ws.cap_e;
     return f;
@@ -43,8 +42,8 @@ __device__ __forceinline__ LFrame lpf_frame(const LpfWs& ws, int fr) {
 constexpr int LPF_MAX_SLOTS = 576;
 
 template <int PH, bool AP>
-__device__ __noinline__ int lpf_wave_phase(uint32_t* st, int sl, Pt* pt, LRec* rec, u16* head, int n, int cap_e, uint32_t* err_out) {
-    LFrame f; f.pt = pt; f.rec = rec; f.head = head; f.n = n; f.cap_e = cap_e;
+__device__ __noinline__ int lpf_wave_phase(uint32_t* st, int sl, LPt* pt, LRec* rec, int n, int cap_e, uint32_t* err_out) {
+    LFrame f; f.pt = pt; f.rec = rec; f.n = n; f.cap_e = cap_e;
     LState s;
     uint32_t* mine = st + sl;
     ls_unpack(s, [&](int w) { return mine[w * LPF_MAX_SLOTS]; });
@@ -138,20 +137,20 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
                     }
                 } else {
                     const int fr = slot_fr[sl];
-                    Pt* fpt = p.ws.pt + (size_t)fr * p.ws.cap; LRec* frec = p.ws.rec + (size_t)fr * 2 * (size_t)p.ws.cap_e;
-                    u16* fhead = p.ws.head + (size_t)fr * p.ws.cap; const int fn = slot_n[sl], fce = p.ws.cap_e;
+                    LPt* fpt = p.ws.pt + (size_t)fr * p.ws.cap; LRec* frec = p.ws.rec + (size_t)fr * 2 * (size_t)p.ws.cap_e;
+                    const int fn = slot_n[sl], fce = p.ws.cap_e;
                     uint32_t* eo = p.ws.err + fr;
 #ifdef GT_PHASE_TIMING
                     const long long tk0 = clock64();
 #endif
                     switch (bin) {                                        // every lane of the chunk is in this phase
-                    case LP_LEAF: next = lpf_wave_phase<LP_LEAF, AP>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
-                    case LP_TINIT: next = lpf_wave_phase<LP_TINIT, AP>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
-                    case LP_TAN: next = lpf_wave_phase<LP_TAN, AP>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
-                    case LP_INS: next = lpf_wave_phase<LP_INS, AP>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
-                    case LP_SCAN: next = lpf_wave_phase<LP_SCAN, AP>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
-                    case LP_V: next = lpf_wave_phase<LP_V, AP>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
-                    default: next = lpf_wave_phase<LP_C, AP>(st, sl, fpt, frec, fhead, fn, fce, eo); break;
+                    case LP_LEAF: next = lpf_wave_phase<LP_LEAF, AP>(st, sl, fpt, frec, fn, fce, eo); break;
+                    case LP_TINIT: next = lpf_wave_phase<LP_TINIT, AP>(st, sl, fpt, frec, fn, fce, eo); break;
+                    case LP_TAN: next = lpf_wave_phase<LP_TAN, AP>(st, sl, fpt, frec, fn, fce, eo); break;
+                    case LP_INS: next = lpf_wave_phase<LP_INS, AP>(st, sl, fpt, frec, fn, fce, eo); break;
+                    case LP_SCAN: next = lpf_wave_phase<LP_SCAN, AP>(st, sl, fpt, frec, fn, fce, eo); break;
+                    case LP_V: next = lpf_wave_phase<LP_V, AP>(st, sl, fpt, frec, fn, fce, eo); break;
+                    default: next = lpf_wave_phase<LP_C, AP>(st, sl, fpt, frec, fn, fce, eo); break;
                     }
 #ifdef GT_PHASE_TIMING
                     if (p.dbg) {
@@ -191,8 +190,6 @@ __global__ void __launch_bounds__(128) lpf_area_kernel(const LpfAreaParams p) {
     double a3 = 0.0, a2 = 0.0; unsigned total = 0;
     if (st == 0) {
         const LFrame f = lpf_frame(p.ws, fr);
-        const double* z = p.ws.z + (size_t)fr * p.ws.cap;
-        const u16* perm = p.ws.perm + (size_t)fr * p.ws.cap;
         const bool want2d = (p.flags & GTA_B200_2D) != 0;
         unsigned base = 0;
         for (int i0 = 0; i0 < f.n; i0 += 32) {
@@ -207,13 +204,13 @@ __global__ void __launch_bounds__(128) lpf_area_kernel(const LpfAreaParams p) {
                 base += __shfl_sync(0xffffffffu, inc, 31);
             }
             if (i < f.n) {
-                const Pt pi = lf_pt(f, i); const double zi = z[i];
+                const LPt pi = f.pt[i]; const double zi = pi.z;
                 int* out = p.tri ? p.tri + ((size_t)fr * p.tri_cap) * 3 : nullptr;
                 lf_vertex_triangles(f, i, [&](int n1, int n2) {
-                    const Pt p1 = lf_pt(f, n1), p2 = lf_pt(f, n2);
-                    a3 += tri_area3(pi.x, pi.y, zi, p1.x, p1.y, z[n1], p2.x, p2.y, z[n2]);
+                    const LPt p1 = f.pt[n1], p2 = f.pt[n2];
+                    a3 += tri_area3(pi.x, pi.y, zi, p1.x, p1.y, p1.z, p2.x, p2.y, p2.z);
                     if (want2d) a2 += tri_area3(pi.x, pi.y, 0.0, p1.x, p1.y, 0.0, p2.x, p2.y, 0.0);
-                    if (out && (int)offs < p.tri_cap) { out[3 * offs] = perm[i]; out[3 * offs + 1] = perm[n1]; out[3 * offs + 2] = perm[n2]; }
+                    if (out && (int)offs < p.tri_cap) { out[3 * offs] = pi.perm; out[3 * offs + 1] = p1.perm; out[3 * offs + 2] = p2.perm; }
                     ++offs;
                 });
             }

@@ -21,7 +21,7 @@
 // warp. Per frame the persistent state is LS_WORDS words (ls_pack / ls_unpack); the frame itself lives in
 // global memory:
 //   point  16 B {x, y}   record 8 B {dst, nxt, prv, -} per half-edge, twins adjacent (edge = 16 B, one load)
-//   head    2 B per vertex
+//   (the ring head of a vertex lives in its LPt record)
 // Edge pool, free list and the cursor over the recursion tree are private to the frame: no atomics.
 //
 // Host-compilable: tests/emu drives the steps sequentially (through the packed state) and compares with the oracle.
@@ -33,11 +33,15 @@ namespace gt {
 struct LRec { u16 dst, nxt, prv, pad; };                 // one half-edge
 struct LPair { LRec a, b; };                             // a = the half-edge asked for, b = its twin
 
+// Everything the path keeps per sorted vertex, in ONE 32-byte sector: a step that needs a neighbour's coordinates
+// and its ring head gets both with one load (they were two arrays: 18 % more sector reads, and the kernel is bound
+// by scattered sector reads from HBM).
+struct alignas(32) LPt { double x, y, z; u16 head, perm; uint32_t pad; };
+
 // Frame storage in global memory.
 struct LFrame {
-    Pt* pt;         // [n] sorted (x, y)
+    LPt* pt;        // [n] sorted by (x, y)
     LRec* rec;      // [2 * cap_e]
-    u16* head;      // [n]
     int n;
     int cap_e;
 };
@@ -52,10 +56,21 @@ GT_INLINE LPair lf_pair(const LFrame& f, int h) {
     return p;
 }
 GT_INLINE Pt lf_pt(const LFrame& f, int v) { const double2 d = *reinterpret_cast<const double2*>(f.pt + v); Pt p; p.x = d.x; p.y = d.y; return p; }
+// coordinates and ring head of vertex v with one 256-bit load
+GT_INLINE Pt lf_pth(const LFrame& f, int v, int& head) {
+    unsigned long long a, b, c, d;
+    asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(f.pt + v) : "memory");
+    Pt p; p.x = __longlong_as_double((long long)a); p.y = __longlong_as_double((long long)b);
+    head = (int)(d & 0xffffull);
+    return p;
+}
 #else
 GT_INLINE LPair lf_pair(const LFrame& f, int h) { LPair p; p.a = f.rec[h]; p.b = f.rec[h ^ 1]; return p; }
-GT_INLINE Pt lf_pt(const LFrame& f, int v) { return f.pt[v]; }
+GT_INLINE Pt lf_pt(const LFrame& f, int v) { Pt p; p.x = f.pt[v].x; p.y = f.pt[v].y; return p; }
+GT_INLINE Pt lf_pth(const LFrame& f, int v, int& head) { head = f.pt[v].head; return lf_pt(f, v); }
 #endif
+GT_INLINE int lf_head(const LFrame& f, int v) { return f.pt[v].head; }
+GT_INLINE void lf_set_head(const LFrame& f, int v, int h) { f.pt[v].head = (u16)h; }
 GT_INLINE void lf_set_nxt(const LFrame& f, int h, int v) { f.rec[h].nxt = (u16)v; }
 GT_INLINE void lf_set_prv(const LFrame& f, int h, int v) { f.rec[h].prv = (u16)v; }
 GT_INLINE void lf_set_rec(const LFrame& f, int h, int dst, int nxt, int prv) {
@@ -238,7 +253,7 @@ GT_INLINE void lp_finish_connect(const LFrame& f, LState& s) {
 // Put half-edge h (origin P, destination IN) between `at` and `nx` in P's ring (reference insertNodeAfter :202-208).
 GT_INLINE void lp_place(const LFrame& f, LState& s, int which, int P, int IN, int h, int at, int nx, bool newhead, int hd) {
     lf_set_nxt(f, at, h); lf_set_prv(f, nx, h); lf_set_rec(f, h, IN, nx, at);
-    if (newhead) f.head[P] = (u16)h;
+    if (newhead) lf_set_head(f, P, h);
     const int newhd = newhead ? h : hd;
     if (which == 0) { s.plNx0 = nx; s.headL = newhd; } else { s.plAt1 = at; s.headR = newhd; }
 }
@@ -267,7 +282,7 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
         const int h0 = 2 * e0;
         if (c == b) {                                     // two points: one edge, two single-entry rings
             lf_set_rec(f, h0, b, h0, h0); lf_set_rec(f, h0 ^ 1, a, h0 ^ 1, h0 ^ 1);
-            f.head[a] = (u16)h0; f.head[b] = (u16)(h0 ^ 1);
+            lf_set_head(f, a, h0); lf_set_head(f, b, h0 ^ 1);
             lp_next_node(f, s); return;
         }
         // further edges: the free list's links are read directly here (leaves only)
@@ -283,17 +298,17 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
         }
         // ring of b: {b->a, b->c}; "first" moves to b->c iff c is right of the ray b->a (= ccw(a,b,c))
         lf_set_rec(f, h0 ^ 1, a, h1, h1); lf_set_rec(f, h1, c, h0 ^ 1, h0 ^ 1);
-        f.head[b] = (u16)(s1 ? h1 : (h0 ^ 1));
+        lf_set_head(f, b, s1 ? h1 : (h0 ^ 1));
         if (h2 < 0) {                                     // collinear: a and c keep single-entry rings
-            lf_set_rec(f, h0, b, h0, h0); f.head[a] = (u16)h0;
-            lf_set_rec(f, h1 ^ 1, b, h1 ^ 1, h1 ^ 1); f.head[c] = (u16)(h1 ^ 1);
+            lf_set_rec(f, h0, b, h0, h0); lf_set_head(f, a, h0);
+            lf_set_rec(f, h1 ^ 1, b, h1 ^ 1, h1 ^ 1); lf_set_head(f, c, h1 ^ 1);
         } else {
             // ring of a: {a->b, a->c}; first moves to a->c iff c is right of a->b (= ccw(a,c,b))
             lf_set_rec(f, h0, b, h2, h2); lf_set_rec(f, h2, c, h0, h0);
-            f.head[a] = (u16)(s2 ? h2 : h0);
+            lf_set_head(f, a, s2 ? h2 : h0);
             // ring of c: {c->b, c->a}; first moves to c->a iff a is right of c->b (= ccw(a,b,c))
             lf_set_rec(f, h1 ^ 1, b, h2 ^ 1, h2 ^ 1); lf_set_rec(f, h2 ^ 1, a, h1 ^ 1, h1 ^ 1);
-            f.head[c] = (u16)(s1 ? (h2 ^ 1) : (h1 ^ 1));
+            lf_set_head(f, c, s1 ? (h2 ^ 1) : (h1 ^ 1));
         }
         lp_next_node(f, s);
         return;
@@ -302,9 +317,9 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
     if (PH == LP_TINIT) {
         // both tangents start at the rightmost vertex of the left half and the leftmost of the right half
         const int x = (s.ia + s.ib) / 2, y = x + 1;
-        const int hdx = f.head[x], hdy = f.head[y];
+        int hdx = 0, hdy = 0;
+        const Pt qx = lf_pth(f, x, hdx), qy = lf_pth(f, y, hdy);
         const LPair px = lf_pair(f, hdx), py = lf_pair(f, hdy);
-        const Pt qx = lf_pt(f, x), qy = lf_pt(f, y);
         s.ux = x; s.uy = y; s.uHl = hdx; s.uHr = py.a.prv; s.pr1 = qx; s.pl1 = qy; s.uSub = 0;      // upper: x -> first(x), y -> pred(y, first(y))   (:378-381)
         s.li = x; s.ri = y; s.lHl = px.a.prv; s.lHr = hdy; s.pli = qx; s.pri = qy; s.lSub = 0;      // lower: x -> pred(x, first(x)), y -> first(y)   (:342-345)
         s.headL = hdx; s.headR = hdy;
@@ -319,7 +334,7 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
         if (a0) p0 = lf_pair(f, s.uSub == 0 ? s.uHr : s.uHl);
         if (a1) p1 = lf_pair(f, s.lSub == 0 ? s.lHr : s.lHl);
         if (a0) c0 = lf_pt(f, p0.a.dst);
-        if (a1) { c1 = lf_pt(f, p1.a.dst); hd1c = f.head[p1.a.dst]; }
+        if (a1) c1 = lf_pth(f, p1.a.dst, hd1c);
         if (a0) {
             int sg = orient2d_sign<AP>(c0.x, c0.y, s.pr1.x, s.pr1.y, s.pl1.x, s.pl1.y);
             if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
@@ -411,8 +426,9 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
     if (PH == LP_V) {
         // chain 0: leftOf(r1, li, ri) with r1 = pred(ri, li) (:555-556); chain 1: rightOf(l1, ri, li) with l1 = succ(li, ri) (:568-569)
         const LPair p0 = lf_pair(f, s.hr1), p1 = lf_pair(f, s.hl1);
-        const Pt c0 = lf_pt(f, p0.a.dst), c1 = lf_pt(f, p1.a.dst);
-        s.hdR1 = f.head[p0.a.dst]; s.hdL1 = f.head[p1.a.dst];
+        int hdr = 0, hdl = 0;
+        const Pt c0 = lf_pth(f, p0.a.dst, hdr), c1 = lf_pth(f, p1.a.dst, hdl);
+        s.hdR1 = hdr; s.hdL1 = hdl;
         int sg0 = orient2d_sign<AP>(c0.x, c0.y, s.pli.x, s.pli.y, s.pri.x, s.pri.y);
         int sg1 = orient2d_sign<AP>(c1.x, c1.y, s.pli.x, s.pli.y, s.pri.x, s.pri.y);
         if (sg0 == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg0 = 0; }
@@ -430,8 +446,8 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
         LPair p0 = zero, p1 = zero; Pt c0, c1; c0.x = c0.y = 0.0; c1 = c0; int hn0 = 0, hn1 = 0;
         if (a0) p0 = lf_pair(f, s.hr2);
         if (a1) p1 = lf_pair(f, s.hl2);
-        if (a0) { c0 = lf_pt(f, p0.a.dst); hn0 = f.head[p0.a.dst]; }
-        if (a1) { c1 = lf_pt(f, p1.a.dst); hn1 = f.head[p1.a.dst]; }
+        if (a0) c0 = lf_pth(f, p0.a.dst, hn0);
+        if (a1) c1 = lf_pth(f, p1.a.dst, hn1);
         bool freed = false; int prev_head = 0;
         if (a0) {
             const int r2 = p0.a.dst;
@@ -443,9 +459,9 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
                 // ri's ring loses hr1 (its next is the cross edge), r1's ring loses the twin
                 const int h = s.hr1, tw = h ^ 1;
                 lf_set_nxt(f, s.hr2, s.e ^ 1); lf_set_prv(f, s.e ^ 1, s.hr2);
-                if (s.headR == h) { s.headR = s.e ^ 1; f.head[s.ri] = (u16)(s.e ^ 1); }
+                if (s.headR == h) { s.headR = s.e ^ 1; lf_set_head(f, s.ri, s.e ^ 1); }
                 lf_set_nxt(f, s.t1_prv, s.t1_nxt); lf_set_prv(f, s.t1_nxt, s.t1_prv);
-                if (s.hdR1 == tw) f.head[s.r1] = (u16)((s.t1_nxt == tw) ? GT_NIL : s.t1_nxt);
+                if (s.hdR1 == tw) lf_set_head(f, s.r1, (s.t1_nxt == tw) ? GT_NIL : s.t1_nxt);
                 prev_head = s.free_head; freed = true; lp_free(f, s, h >> 1);
                 s.hr1 = s.hr2; s.r1 = r2; s.pr1 = c0; s.hr2 = p0.a.prv; s.t1_prv = p0.b.prv; s.t1_nxt = p0.b.nxt; s.hdR1 = hn0;
             } else s.actR = 0;
@@ -459,9 +475,9 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
             if (sg > 0) {
                 const int h = s.hl1, tw = h ^ 1;
                 lf_set_nxt(f, s.e, s.hl2); lf_set_prv(f, s.hl2, s.e);
-                if (s.headL == h) { s.headL = s.hl2; f.head[s.li] = (u16)s.hl2; }
+                if (s.headL == h) { s.headL = s.hl2; lf_set_head(f, s.li, s.hl2); }
                 lf_set_nxt(f, s.u1_prv, s.u1_nxt); lf_set_prv(f, s.u1_nxt, s.u1_prv);
-                if (s.hdL1 == tw) f.head[s.l1] = (u16)((s.u1_nxt == tw) ? GT_NIL : s.u1_nxt);
+                if (s.hdL1 == tw) lf_set_head(f, s.l1, (s.u1_nxt == tw) ? GT_NIL : s.u1_nxt);
                 prev_head = s.free_head; freed = true; lp_free(f, s, h >> 1);
                 s.hl1 = s.hl2; s.l1 = l2; s.pl1 = c1; s.hl2 = p1.a.nxt; s.u1_prv = p1.b.prv; s.u1_nxt = p1.b.nxt; s.hdL1 = hn1;
             } else s.actL = 0;
@@ -490,7 +506,7 @@ GT_INLINE bool lpf_step(const LFrame& f, LState& s) {
 // same rule as dt_core.cuh::vertex_triangles on the packed records.
 template <class Visit>
 GT_INLINE int lf_vertex_triangles(const LFrame& f, int i, Visit&& visit) {
-    const int hd = f.head[i];
+    const int hd = lf_head(f, i);
     if (hd == (int)GT_NIL || f.rec[hd].nxt == hd) return 0;
     int cnt = 0, h = hd;
     do {

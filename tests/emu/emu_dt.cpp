@@ -110,11 +110,11 @@ int emu_triangulate_lpf(const double* points, int n, int* tri_out, long* iters_o
             i = e;
         }
     }
-    std::vector<Pt> pt(n);
-    for (int i = 0; i < n; ++i) { pt[i].x = points[2 * perm[i]]; pt[i].y = points[2 * perm[i] + 1]; }
+    std::vector<LPt> pt(n);
+    for (int i = 0; i < n; ++i) { pt[i].x = points[2 * perm[i]]; pt[i].y = points[2 * perm[i] + 1]; pt[i].z = 0.0; pt[i].head = (u16)GT_NIL; pt[i].perm = (u16)perm[i]; pt[i].pad = 0; }
     const int cap_e = 3 * n + 64;
-    std::vector<LRec> rec(2 * cap_e); std::vector<u16> head(n, (u16)GT_NIL);
-    LFrame f; f.pt = pt.data(); f.rec = rec.data(); f.head = head.data(); f.n = n; f.cap_e = cap_e;
+    std::vector<LRec> rec(2 * cap_e);
+    LFrame f; f.pt = pt.data(); f.rec = rec.data(); f.n = n; f.cap_e = cap_e;
     LState s; memset(&s, 0, sizeof s); lp_begin(f, s);
     long iters = 0;
     bool more = s.phase != LP_DONE;
