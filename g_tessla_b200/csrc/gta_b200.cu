@@ -96,6 +96,22 @@ int launch_t(const gt::KParams& p, const Shape& s, cudaStream_t st) {
     return GTA_B200_OK;
 }
 
+// The lane-per-frame path's pre-pass (gta_kernel.cuh, PREPASS): 256 threads per frame, shared memory without the edge pool.
+int launch_prepass(const gt::KParams& p, const Shape& s, cudaStream_t st) {
+    auto kern = gt::tessellate_kernel<256, 4, true>;
+    const size_t smem = gt::smem_bytes_for(s.cap, s.cap_p2, p.natoms, true);
+    int dev = 0, occ = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (occ < 1) return fail(GTA_B200_E_TOO_LARGE, "kernel does not fit on an SM");
+    const int grid = std::max(1, std::min(p.nframes, occ * sms));
+    kern<<<grid, 256, smem, st>>>(p);
+    CK(cudaGetLastError());
+    return GTA_B200_OK;
+}
+
 int launch(const gt::KParams& p, const Shape& s, cudaStream_t st) {
     switch (s.threads) {
         case 32: return launch_t<32, 8>(p, s, st);
@@ -179,7 +195,7 @@ int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st) {
     CK(cudaStreamWaitEvent(st, c->done, 0));
     // 1. pre-pass (load, -corr, sort) into the workspace
     p.ws = c->ws;
-    rc = launch(p, s, st);
+    rc = launch_prepass(p, s, st);
     if (rc) return rc;
     // 2. one lane per frame
     gt::LpfParams lp; lp.ws = c->ws; lp.nframes = p.nframes; lp.counter = c->counter; lp.dbg = p.dbg ? p.dbg + 32 : nullptr;

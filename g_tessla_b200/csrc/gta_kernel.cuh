@@ -49,10 +49,15 @@ struct KParams {
 __host__ __device__ inline int pool_edges(int cap) { return 3 * cap + 64; }
 // dynamic shared memory for a capacity of `cap` points of which `natoms` come from the caller
 // (the other cap - natoms slots can only be -corr points, whose z is generated in the kernel)
-__host__ __device__ inline size_t smem_bytes_for(int cap, int cap_p2, int natoms) {
+// (prepass: the build of the kernel that stops after the sort -- it needs the pool's space only for the points in
+// input order that alias it)
+__host__ __device__ inline size_t pool_bytes_for(int cap, bool prepass) {
+    return prepass ? sizeof(Pt) * (size_t)cap : 12 * (size_t)pool_edges(cap);
+}
+__host__ __device__ inline size_t smem_bytes_for(int cap, int cap_p2, int natoms, bool prepass = false) {
     size_t b = 0;
     b += sizeof(Pt) * (size_t)cap;             // sorted xy
-    b += 12 * (size_t)pool_edges(cap);         // half-edge pool (dst, nxt, prv: u16 x 2 per edge each)
+    b += pool_bytes_for(cap, prepass);         // half-edge pool (dst, nxt, prv: u16 x 2 per edge each)
     b += 2 * (size_t)cap_p2;                   // perm
     b += 2 * (size_t)cap;                      // head
     b = (b + 7) & ~(size_t)7;
@@ -88,7 +93,10 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* s
     }
 }
 
-template <int T, int MINB>
+// PREPASS = true: the lane-per-frame path's first launch -- load, -corr, sort, write the frame to its workspace slot
+// (p.ws) and stop. Its own build: without the D&C it needs a third of the registers and 2/3 of the shared memory, so
+// twice the threads work on the sort.
+template <int T, int MINB, bool PREPASS = false>
 __global__ void __launch_bounds__(T, MINB) tessellate_kernel(const KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
@@ -99,7 +107,7 @@ __global__ void __launch_bounds__(T, MINB) tessellate_kernel(const KParams p) {
     u16* nxt = dst + 2 * cap_e;
     u16* prv = nxt + 2 * cap_e;
     Pt* tmp_xy = reinterpret_cast<Pt*>(pool);                  // setup-time alias of the pool (input order)
-    u16* perm = reinterpret_cast<u16*>(pool + 12 * (size_t)cap_e);
+    u16* perm = reinterpret_cast<u16*>(pool + pool_bytes_for(cap, PREPASS));
     u16* head = perm + p.cap_p2;
     size_t off = (size_t)(reinterpret_cast<unsigned char*>(head + cap) - smem);
     off = (off + 7) & ~(size_t)7;
@@ -304,7 +312,7 @@ __global__ void __launch_bounds__(T, MINB) tessellate_kernel(const KParams p) {
             __syncthreads();
         }
         GT_TICK(3);
-        if (p.ws.pt) {
+        if (PREPASS || p.ws.pt) {
             // pre-pass of the lane-per-frame path: sorted points, z, permutation and the status go to the frame's
             // workspace slot; the triangulation and the area sum are separate launches (gta_lpf.cuh)
             const size_t slot = (size_t)fr;
