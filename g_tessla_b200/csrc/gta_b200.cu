@@ -204,8 +204,9 @@ int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st) {
     if (slots < 0) { const char* e = getenv("GTA_B200_LPF_SLOTS"); slots = e ? atoi(e) : gt::LPF_MAX_SLOTS; }
     if (wthreads < 0) { const char* e = getenv("GTA_B200_LPF_THREADS"); wthreads = e ? atoi(e) : 0; }
     // Which build of the kernel? Without stage A' of the predicates (gt_predicates.cuh) the steps fit 128 registers and
-    // 14 warps per SM: best when the FP filter decides everything, as it does on real coordinates (cfg 3: 263 k frames/s
-    // vs 253 k). With stage A', 12 warps: 2x faster on degenerate few-bit input (cfg 5: 290 k vs 136 k). The previous
+    // 16 warps per SM: best when the FP filter decides everything, as it does on real coordinates (cfg 3: 263 k frames/s
+    // vs 253 k; 16 warps against 14: the same up to 50 k frames per launch, 335 k vs 308 k at 66 k, where a round has
+    // more chunks than 14 warps). With stage A', 12 warps: 2x faster on degenerate few-bit input (cfg 5). The previous
     // launch on this device tells which kind of data this is: the device counts the undecided predicates (1 lane in 8).
     if (c->pending && cudaEventQuery(c->done) == cudaSuccess) {
         const unsigned long long now = *c->undecided_h;
@@ -228,9 +229,9 @@ int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st) {
             CK(cudaGetLastError());
             return GTA_B200_OK;
         };
-        if (wthreads == 512) rc = go(gt::lpf_wave_kernel<512, false>, 512);                 // (experiment)
+        if (wthreads == 448) rc = go(gt::lpf_wave_kernel<448, false>, 448);                 // (experiment)
         else if (c->degenerate || wthreads == 384) rc = go(gt::lpf_wave_kernel<384, true>, 384);
-        else rc = go(gt::lpf_wave_kernel<448, false>, 448);
+        else rc = go(gt::lpf_wave_kernel<512, false>, 512);
         if (rc) return rc;
     }
     // 3. areas
