@@ -137,6 +137,7 @@ struct LpfCache {
 };
 LpfCache g_lpf[64];
 std::mutex g_lpf_mu;
+std::mutex g_lpf_launch_mu[64];          // one launch sequence at a time per device: they share the device's workspace
 
 // Launches of at least this many frames use the lane-per-frame path (its throughput needs tens of thousands of
 // frames in flight; below that the CTA-per-frame kernel wins: measured crossover on cfg 3 at ~25k frames).
@@ -187,11 +188,13 @@ int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st) {
     int dev = 0, sms = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // the workspace is shared by all streams (and host threads) of this device: launches queue behind each other
+    // (copies of the next chunk still overlap). The lock covers grow-workspace, wait-on-previous ... record-done, so
+    // that two host threads cannot both queue behind the same earlier launch and then run side by side in one workspace.
+    std::lock_guard<std::mutex> launch_lock(g_lpf_launch_mu[dev & 63]);
     LpfCache* c = nullptr;
     int rc = lpf_ensure(dev, (size_t)p.nframes, s.cap, gt::pool_edges(s.cap), &c);
     if (rc) return rc;
-    // the workspace is shared by all streams of this device: launches queue behind each other
-    // (copies of the next chunk still overlap)
     CK(cudaStreamWaitEvent(st, c->done, 0));
     // 1. pre-pass (load, -corr, sort) into the workspace
     p.ws = c->ws;

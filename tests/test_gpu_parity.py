@@ -220,3 +220,38 @@ def test_lane_per_frame_batch_larger_than_one_launch(gta, checker):
     r = gta.tessellate(xyz, box, c["espace"], c["flags"])       # host buffers: chunked pipeline
     assert (r["status"] == 0).all()
     assert np.array_equal(r["area"].reshape(reps, -1), area)
+
+
+def test_lane_per_frame_two_host_threads_one_device(gta, checker, lane_per_frame):
+    """Two host threads, two streams, one device: the lane-per-frame launches share the device's workspace and must
+    queue behind each other, not run side by side in it."""
+    import threading
+    import torch
+    cs = [synth.config(1, nframes=400), synth.config(3, nframes=60)]
+    wants = [checker.tessellate(c["xyz"], c["box"], c["espace"], c["flags"], nthreads=0)["area"] for c in cs]
+    got = [None, None]
+    errs = []
+
+    def work(k):
+        try:
+            c = cs[k]
+            n = c["xyz"].shape[1]
+            maxp = n + 4 + 4 * int(c["box"][:, :2].max() / c["espace"] + 1)
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                xyz = torch.from_numpy(c["xyz"]).cuda(); box = torch.from_numpy(c["box"]).cuda()
+                T = gta.Tessellator(len(c["xyz"]), n, maxp, c["espace"], c["flags"])
+                for _ in range(6):
+                    T.run(xyz, box, 3)
+                stream.synchronize()
+                assert int((T.status != 0).sum()) == 0
+                got[k] = T.area.cpu().numpy()
+        except Exception as e:                                  # surfaced in the main thread
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for k in range(2):
+        assert np.allclose(got[k], wants[k], rtol=RTOL, atol=0), k
