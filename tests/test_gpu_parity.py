@@ -255,3 +255,21 @@ def test_lane_per_frame_two_host_threads_one_device(gta, checker, lane_per_frame
     assert not errs, errs
     for k in range(2):
         assert np.allclose(got[k], wants[k], rtol=RTOL, atol=0), k
+
+
+def test_lane_per_frame_both_builds_agree(gta, checker, lane_per_frame):
+    """The lane-per-frame kernel is built with and without the predicates' FP exactness stage and the host picks from
+    the previous launch's count of undecided predicates: a degenerate batch (cfg 5) switches the next launch to the
+    other build, a generic one (cfg 3) switches back. Every launch must give the reference's result, bit for bit the
+    same from both builds."""
+    c5 = synth.config(5, nframes=120); c3 = synth.config(3, nframes=120)
+    w5 = checker.tessellate(c5["xyz"], c5["box"], c5["espace"], c5["flags"], nthreads=0)["area"]
+    w3 = checker.tessellate(c3["xyz"], c3["box"], c3["espace"], c3["flags"], nthreads=0)["area"]
+    runs5, runs3 = [], []
+    for _ in range(3):                                          # 5, 5, 3, 3, 5, 5, ...: each build sees each kind of input
+        for c, runs in ((c5, runs5), (c5, runs5), (c3, runs3), (c3, runs3)):
+            r = gta.tessellate(c["xyz"], c["box"], c["espace"], c["flags"])
+            assert (r["status"] == 0).all()
+            runs.append(r["area"])
+    assert all(np.array_equal(a, runs5[0]) for a in runs5) and all(np.array_equal(a, runs3[0]) for a in runs3)
+    assert np.allclose(runs5[0], w5, rtol=RTOL, atol=0) and np.allclose(runs3[0], w3, rtol=RTOL, atol=0)
