@@ -40,7 +40,8 @@ static __device__ __noinline__ bool inc_slow(uint32_t* err, Pt px, Pt pa, Pt pb,
 // ccw(x, a, b) (reference predicates.c:1628-1651) and incircle(x, a, b, y) (:3238-3267) on its own
 // operands and keeps the one its role asks for (kind 1 / 2, 0 = idle). Lanes with different roles
 // never diverge; only a lane whose filter is inconclusive branches to the exact stage.
-__device__ __forceinline__ bool lane_pred(const Frame& f, int kind, int x, int a, int b, int y) {
+template <class F>
+__device__ __forceinline__ bool lane_pred(const F& f, int kind, int x, int a, int b, int y) {
     const Pt px = f.pt[x], pa = f.pt[a], pb = f.pt[b], py = f.pt[y];
     const double detleft = (px.x - pb.x) * (pa.y - pb.y), detright = (px.y - pb.y) * (pa.x - pb.x);
     const double odet = detleft - detright;
@@ -67,8 +68,9 @@ __device__ __forceinline__ bool lane_pred(const Frame& f, int kind, int x, int a
 // insertNode (reference :210-245) with its first two orientation tests precomputed:
 // t0 = rightOf(in, parent, first), t1 = rightOf(in, parent, last). `after` = the slot known from the
 // topology of the merge, used when t0 is false (see ring_insert_hint).
-__device__ __forceinline__ void coop_insert(const Frame& f, int parent, int in, int h, int after, bool t0, bool t1) {
-    f.dst[h] = (u16)in;
+template <class F>
+__device__ __forceinline__ void coop_insert(const F& f, int parent, int in, int h, int after, bool t0, bool t1) {
+    f.dst[h] = (typename F::idx)in;
     const int hd = f.head[parent];
     if (!t0) { link_after(f, after, h); return; }
     int cur = f.prv[hd];
@@ -76,12 +78,13 @@ __device__ __forceinline__ void coop_insert(const Frame& f, int parent, int in, 
         cur = f.prv[cur];
         while (cur != hd && right_of(f, in, parent, f.dst[cur])) cur = f.prv[cur];
     }
-    if (cur == hd) { f.head[parent] = (u16)h; link_after(f, f.prv[cur], h); }
+    if (cur == hd) { f.head[parent] = (typename F::idx)h; link_after(f, f.prv[cur], h); }
     else link_after(f, cur, h);
 }
 
 // Orientation-only variant for the tangent walks.
-__device__ __forceinline__ bool lane_ccw(const Frame& f, bool active, int x, int a, int b) {
+template <class F>
+__device__ __forceinline__ bool lane_ccw(const F& f, bool active, int x, int a, int b) {
     const Pt px = f.pt[x], pa = f.pt[a], pb = f.pt[b];
     const double detleft = (px.x - pb.x) * (pa.y - pb.y), detright = (px.y - pb.y) * (pa.x - pb.x);
     const double odet = detleft - detright;
@@ -100,7 +103,8 @@ __device__ __forceinline__ bool lane_ccw(const Frame& f, bool active, int x, int
 //   3 L0  4 L1  5 L2   (li's neighbours counter-clockwise from ri: ch = nxt^(j-2)(e))
 //   6 li  7 ri
 // and any lane fetches an operand with one shuffle.
-__device__ __forceinline__ void coop_merge(const Frame& f, Lane& ln, int mid, unsigned long long* dbg = nullptr) {
+template <class F>
+__device__ __forceinline__ void coop_merge(const F& f, Lane& ln, int mid, unsigned long long* dbg = nullptr) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
 #ifdef GT_PHASE_TIMING
@@ -169,7 +173,7 @@ __device__ __forceinline__ void coop_merge(const Frame& f, Lane& ln, int mid, un
     const bool ins_lane = lane >= 10 && lane < 26;
     const bool last_test = lane & 1;
     const int hops = lane < 6 ? (lane < 3 ? lane : lane - 3) + 1 : 0;
-    const u16* const link = lane < 3 ? f.prv : f.nxt;
+    const typename F::idx* const link = lane < 3 ? f.prv : f.nxt;
 
     int li = lx, ri = ly;
     int guard = 8 * f.n + 64;
@@ -214,13 +218,13 @@ __device__ __forceinline__ void coop_merge(const Frame& f, Lane& ln, int mid, un
             const int h0L = __shfl_sync(FULL, ch, 3);
             if (lane < 2 ? lane < nR : (lane >= 3 && lane < 5 && lane - 3 < nL)) ring_unlink(f, cv, ch ^ 1);
             if (lane == 0 && nR > 0) {
-                f.nxt[survR] = (u16)(e ^ 1); f.prv[e ^ 1] = (u16)survR;
+                f.nxt[survR] = (typename F::idx)(e ^ 1); f.prv[e ^ 1] = (typename F::idx)survR;
                 const int hd = f.head[ri];
-                if (hd == ch || (nR > 1 && hd == h1R)) f.head[ri] = (u16)(e ^ 1);
+                if (hd == ch || (nR > 1 && hd == h1R)) f.head[ri] = (typename F::idx)(e ^ 1);
             } else if (lane == 3 && nL > 0) {
-                f.nxt[e] = (u16)survL; f.prv[survL] = (u16)e;
+                f.nxt[e] = (typename F::idx)survL; f.prv[survL] = (typename F::idx)e;
                 const int hd = f.head[li];
-                if (hd == ch || (nL > 1 && hd == h1L)) f.head[li] = (u16)survL;
+                if (hd == ch || (nL > 1 && hd == h1L)) f.head[li] = (typename F::idx)survL;
             }
             __syncwarp();
             if (lane == 0) {

@@ -22,6 +22,7 @@
 #include <string>
 #include <vector>
 #include "dt_core.cuh"
+#include "dt_coop.cuh"
 #include "../../include/gta_b200.h"
 
 namespace gt {
@@ -76,13 +77,23 @@ __global__ void large_check_dups(const Pt* pt, int n, uint32_t* err) {
 }
 
 // One level of the recursion tree. lanes_per_node = 1: node k is thread k (lower levels, many short merges);
-// lanes_per_node = 32: node k is warp k, lane 0 walks the merge (upper levels: lanes of one warp that walk
-// different merges would serialise).
-__global__ void __launch_bounds__(128) large_level(FrameL f, int depth, int nodes, int lanes_per_node) {
+// lanes_per_node = 32: node k is warp k (upper levels: lanes of one warp that walk different merges would
+// serialise) -- with coop, the warp evaluates every predicate a merge step could ask for in one round
+// (dt_coop.cuh::coop_merge, the same code as the top of the tree in the batched kernel); without, lane 0 walks the
+// merge alone.
+__global__ void __launch_bounds__(128) large_level(FrameL f, int depth, int nodes, int lanes_per_node, int coop) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long k = t / lanes_per_node;
-    if (k >= nodes || (t % lanes_per_node) != 0) return;
+    if (k >= nodes) return;
     Lane ln; ln.free_head = FrameL::NIL;
+    if (lanes_per_node == 32 && coop) {
+        int ia, ib;
+        if (!tree_node(f.n, depth, (int)k, &ia, &ib) || ib - ia < 1) return;       // (uniform over the warp)
+        if (ib - ia < 3) { if ((t & 31) == 0) leaf(f, ln, ia, ib); }
+        else coop_merge(f, ln, (ia + ib) / 2);
+        return;
+    }
+    if ((t % lanes_per_node) != 0) return;
     process_node(f, ln, depth, (int)k);
 }
 
@@ -172,11 +183,15 @@ extern "C" int gta_b200_triangulate_large(const double* points, int npoints, int
         f.pt = d_pt; f.head = d_head; f.dst = d_dst; f.nxt = d_nxt; f.prv = d_prv;
         f.bump = d_ctl; f.stack = nullptr; f.err = d_ctl + 1; f.n = n; f.cap_e = cap_e;
         const int D = tree_depth(n);
+        static int coop_nodes = -1;                                // levels with at most this many merges use the warp-cooperative merge
+        if (coop_nodes < 0) { const char* e = getenv("GTA_B200_LARGE_COOP_NODES"); coop_nodes = e ? atoi(e) : 16384; }
+        static int warp_nodes = -1;
+        if (warp_nodes < 0) { const char* e = getenv("GTA_B200_LARGE_WARP_NODES"); warp_nodes = e ? atoi(e) : 16384; }
         for (int d = D; d >= 0; --d) {
             const int nodes = 1 << d;
-            const int lpn = nodes <= 16384 ? 32 : 1;               // one warp per merge while the GPU has warps to spare
+            const int lpn = nodes <= warp_nodes ? 32 : 1;          // one warp per merge while the GPU has warps to spare
             const long long threads = (long long)nodes * lpn;
-            large_level<<<(unsigned)((threads + 127) / 128), 128>>>(f, d, nodes, lpn);
+            large_level<<<(unsigned)((threads + 127) / 128), 128>>>(f, d, nodes, lpn, nodes <= coop_nodes ? 1 : 0);
         }
         LCK(cudaGetLastError());
         large_count<<<G, B>>>(f, d_cnt);
