@@ -99,17 +99,15 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
         if (qbin == LP_DONE && exhausted) myc = 0;                        // nothing left to fetch: empty slots stay empty
         int incl = (myc + 31) >> 5;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        for (int o = 1; o < 8; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }   // (lanes >= 8 hold 0)
         const int first_chunk = incl - ((myc + 31) >> 5);
-        const int nchunks = __shfl_sync(0xffffffffu, incl, 31);
+        const int nchunks = __shfl_sync(0xffffffffu, incl, 7);
         if (nchunks == 0) break;                                          // nothing in flight and nothing left to fetch
         // ---- one iteration for every live slot: a warp takes the next chunk of <= 32 slots that share a phase and files
         // every slot under its new phase for the next round
+        // (a warp's first chunk is the one with its own number; tickets hand out the rest)
         int* ticket = &ctl[1 + r3];
-        for (;;) {
-            int c = 0;
-            if (lane == 0) c = atomicAdd(ticket, 1);
-            c = __shfl_sync(0xffffffffu, c, 0);
+        for (int c = tid >> 5;;) {
             if (c >= nchunks) break;
             // first_chunk is non-decreasing over the bins: the last bin that starts at or before c owns chunk c
             const int q = __popc(__ballot_sync(0xffffffffu, lane < NB && first_chunk <= c)) - 1;      // warp-uniform
@@ -161,6 +159,9 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
                 }
                 bin_next[(size_t)next * SLOTS + atomicAdd(&c_next[next], 1)] = (u16)sl;
             }
+            if (nchunks <= THREADS / 32) break;                            // every chunk had a warp of its own
+            if (lane == 0) c = atomicAdd(ticket, 1) + THREADS / 32;
+            c = __shfl_sync(0xffffffffu, c, 0);
         }
 #ifdef GT_PHASE_TIMING
         const long long tb0 = clock64();
