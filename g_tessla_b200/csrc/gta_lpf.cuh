@@ -16,7 +16,7 @@ struct LpfParams {
     LpfWs ws;
     int nframes;
     unsigned int* counter;                 // next frame to hand out
-    unsigned long long* dbg;               // -DGT_PHASE_TIMING builds: [3*ph] cycles, [3*ph+1] chunks, [3*ph+2] lanes; [24] barrier wait, [25] rounds x warps
+    unsigned long long* dbg;               // -DGT_PHASE_TIMING builds: [3*ph] cycles, [3*ph+1] chunks, [3*ph+2] lanes; [24] barrier wait, [25] rounds x warps, [26..30] rounds of block 0 by chunk count
 };
 
 __device__ __forceinline__ LFrame lpf_frame(const LpfWs& ws, int fr) {
@@ -103,6 +103,9 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
         const int first_chunk = incl - ((myc + 31) >> 5);
         const int nchunks = __shfl_sync(0xffffffffu, incl, 7);
         if (nchunks == 0) break;                                          // nothing in flight and nothing left to fetch
+#ifdef GT_PHASE_TIMING
+        if (p.dbg && tid == 0 && blockIdx.x == 0) atomicAdd(p.dbg + 26 + min(max(nchunks - 16, 0), 4), 1ull);      // rounds with <= 16, 17, 18, 19, >= 20 chunks
+#endif
         // ---- one iteration for every live slot: a warp takes the next chunk of <= 32 slots that share a phase and files
         // every slot under its new phase for the next round
         // (a warp's first chunk is the one with its own number; tickets hand out the rest)

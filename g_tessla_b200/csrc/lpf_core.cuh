@@ -375,48 +375,61 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
         if (m1) q1 = lf_pair(f, p1.a.prv);
         if (m0) d0 = lf_pt(f, q0.a.dst);
         if (m1) d1 = lf_pt(f, q1.a.dst);
+        // Each endpoint: decide (at, nx, newhead) -- or that the scan goes on -- and place once. One copy of the placement
+        // per endpoint and both orientation filters evaluated for every lane keep the step short and its lanes together
+        // (it is the longest step of a round: the round lasts as long as this).
         if (a0) {
             int sg = orient2d_sign<AP>(s.pri.x, s.pri.y, c0.x, c0.y, s.pli.x, s.pli.y);
             if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
             const bool res = sg > 0;
+            bool place = true, newhead = false; int at, nx, hd;
             if (PH == LP_INS) {
-                const int hd = s.headL, last = p0.a.prv;
-                if (!res) { if (s.first_edge) lp_place(f, s, 0, s.li, s.ri, s.h0, last, hd, false, hd); else lp_place(f, s, 0, s.li, s.ri, s.h0, s.at0, s.nx0, false, hd); }
-                else if (last == hd) lp_place(f, s, 0, s.li, s.ri, s.h0, hd, hd, true, hd);          // single-entry ring: right of all
-                else {
-                    int sl = orient2d_sign<AP>(s.pri.x, s.pri.y, d0.x, d0.y, s.pli.x, s.pli.y);
-                    if (sl == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sl = 0; }
-                    if (!(sl > 0)) lp_place(f, s, 0, s.li, s.ri, s.h0, last, hd, false, hd);          // not right of "last": goes after it
-                    else if ((int)q0.a.prv == hd) lp_place(f, s, 0, s.li, s.ri, s.h0, last, hd, true, hd);      // right of all: new "first"
-                    else { s.cur0 = q0.a.prv; s.hd0 = hd; s.last0 = last; s.scan0 = 1; }
+                hd = s.headL; const int last = p0.a.prv;
+                int sl = m0 ? orient2d_sign<AP>(s.pri.x, s.pri.y, d0.x, d0.y, s.pli.x, s.pli.y) : 0;   // right of "last" too?
+                if (sl == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sl = 0; }
+                at = last; nx = hd;                                                  // after "last" (= before "first")
+                if (!res) { if (!s.first_edge) { at = s.at0; nx = s.nx0; } }          // not right of "first": the slot known from the merge
+                else if (last == hd) { at = hd; newhead = true; }                     // single-entry ring: right of all
+                else if (!(sl > 0)) { }                                               // not right of "last": goes after it
+                else if ((int)q0.a.prv == hd) newhead = true;                         // right of all: new "first"
+                else { place = false; s.cur0 = q0.a.prv; s.hd0 = hd; s.last0 = last; s.scan0 = 1; }
+            } else {
+                hd = s.hd0; at = s.cur0; nx = p0.a.nxt;
+                if (res) {
+                    const int cur = p0.a.prv;
+                    if (cur == hd) { at = s.last0; nx = hd; newhead = true; }
+                    else { place = false; s.cur0 = cur; }
                 }
-            } else if (res) {
-                const int cur = p0.a.prv;
-                if (cur == s.hd0) { lp_place(f, s, 0, s.li, s.ri, s.h0, s.last0, s.hd0, true, s.hd0); s.scan0 = 0; }
-                else s.cur0 = cur;
-            } else { lp_place(f, s, 0, s.li, s.ri, s.h0, s.cur0, p0.a.nxt, false, s.hd0); s.scan0 = 0; }
+                if (place) s.scan0 = 0;
+            }
+            if (place) lp_place(f, s, 0, s.li, s.ri, s.h0, at, nx, newhead, hd);
         }
         if (a1) {
             int sg = orient2d_sign<AP>(s.pli.x, s.pli.y, c1.x, c1.y, s.pri.x, s.pri.y);
             if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
             const bool res = sg > 0;
             const int h1 = s.h0 ^ 1;
+            bool place = true, newhead = false; int at, nx, hd;
             if (PH == LP_INS) {
-                const int hd = s.headR, last = p1.a.prv;
-                if (!res) { if (s.first_edge) lp_place(f, s, 1, s.ri, s.li, h1, last, hd, false, hd); else lp_place(f, s, 1, s.ri, s.li, h1, s.at1, s.nx1, false, hd); }
-                else if (last == hd) lp_place(f, s, 1, s.ri, s.li, h1, hd, hd, true, hd);
-                else {
-                    int sl = orient2d_sign<AP>(s.pli.x, s.pli.y, d1.x, d1.y, s.pri.x, s.pri.y);
-                    if (sl == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sl = 0; }
-                    if (!(sl > 0)) lp_place(f, s, 1, s.ri, s.li, h1, last, hd, false, hd);
-                    else if ((int)q1.a.prv == hd) lp_place(f, s, 1, s.ri, s.li, h1, last, hd, true, hd);
-                    else { s.cur1 = q1.a.prv; s.hd1 = hd; s.last1 = last; s.scan1 = 1; }
+                hd = s.headR; const int last = p1.a.prv;
+                int sl = m1 ? orient2d_sign<AP>(s.pli.x, s.pli.y, d1.x, d1.y, s.pri.x, s.pri.y) : 0;
+                if (sl == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sl = 0; }
+                at = last; nx = hd;
+                if (!res) { if (!s.first_edge) { at = s.at1; nx = s.nx1; } }
+                else if (last == hd) { at = hd; newhead = true; }
+                else if (!(sl > 0)) { }
+                else if ((int)q1.a.prv == hd) newhead = true;
+                else { place = false; s.cur1 = q1.a.prv; s.hd1 = hd; s.last1 = last; s.scan1 = 1; }
+            } else {
+                hd = s.hd1; at = s.cur1; nx = p1.a.nxt;
+                if (res) {
+                    const int cur = p1.a.prv;
+                    if (cur == hd) { at = s.last1; nx = hd; newhead = true; }
+                    else { place = false; s.cur1 = cur; }
                 }
-            } else if (res) {
-                const int cur = p1.a.prv;
-                if (cur == s.hd1) { lp_place(f, s, 1, s.ri, s.li, h1, s.last1, s.hd1, true, s.hd1); s.scan1 = 0; }
-                else s.cur1 = cur;
-            } else { lp_place(f, s, 1, s.ri, s.li, h1, s.cur1, p1.a.nxt, false, s.hd1); s.scan1 = 0; }
+                if (place) s.scan1 = 0;
+            }
+            if (place) lp_place(f, s, 1, s.ri, s.li, h1, at, nx, newhead, hd);
         }
         if (s.scan0 || s.scan1) s.phase = LP_SCAN;
         else { s.first_edge = 0; lp_finish_connect(f, s); }

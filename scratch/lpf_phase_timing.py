@@ -24,3 +24,4 @@ print('frames', nf, 'warp-cycles in steps %.3g, barrier wait %.3g (%.0f per warp
 for i, nm in enumerate(names):
     cyc, ch, ln = v[3 * i], v[3 * i + 1], v[3 * i + 2]
     if ch: print('%-6s %5.1f%% of step cycles  %7.0f cycles/chunk  %5.1f lanes/chunk  %8.0f chunks/frame-equivalent %.0f lane-iters/frame' % (nm, 100 * cyc / tot, cyc / ch, ln / ch, ch * 32 / nf, ln / nf))
+print('rounds of block 0 with <=16 / 17 / 18 / 19 / >=20 chunks:', [int(x) for x in v[26:31]])
