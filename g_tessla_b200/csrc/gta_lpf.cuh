@@ -37,8 +37,9 @@ __device__ __forceinline__ LFrame lpf_frame(const LpfWs& ws, int fr) {
 // step become base + immediate offset). Deliberately far below what shared memory could hold:
 //  - what is not shared memory is L1, and the steps' loads want it (704 slots in use: 180 k frames/s when the block
 //    needs the 228 KB carve-out and leaves 28 KB of L1, 257 k with 196 KB, 281 k with 164 KB or less);
-//  - a round serves 14 warps; more than ~448 slots per block only queue (66 k frames per launch: 300 k frames/s,
-//    100 k: 281 k) -- the host splits larger batches into even launches instead (gta_b200.cu).
+//  - a round serves 16 warps; more than ~448 slots per block only queue (measured when 14 warps ran it: 66 k frames per
+//    launch 300 k frames/s, 100 k in one launch 281 k) -- the host splits larger batches into even launches instead
+//    (gta_b200.cu).
 constexpr int LPF_MAX_SLOTS = 576;
 
 template <int PH, bool AP>
