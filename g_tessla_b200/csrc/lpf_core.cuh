@@ -86,6 +86,7 @@ struct LState {
     uint32_t err;
     int bump, free_head;              // private edge pool
     int first_edge, vR, vL, actR, actL, scan0, scan1;
+    int adv;                          // the node is finished: the next LP_TINIT iteration first advances the tree cursor
     // tangents: upper (ux, uy) walks with (uHl, uHr), coordinates in pr1 / pl1; lower (li, ri) with (lHl, lHr), coordinates in
     // pli / pri. xSub: 0 = next test is the right hull's candidate, 1 = the left hull's, 2 = tangent found
     int ux, uy, uHl, uHr, uSub, lHl, lHr, lSub;
@@ -117,7 +118,7 @@ GT_INLINE double ls_dbl(uint32_t lo, uint32_t hi) {
 template <class Put>
 GT_INLINE void ls_pack(const LState& s, Put&& put) {
     put(0, (uint32_t)s.phase | ((uint32_t)s.d << 4) | ((uint32_t)s.k << 8) | ((s.err & 15u) << 20) | ((uint32_t)s.first_edge << 24) | ((uint32_t)s.vR << 25) |
-           ((uint32_t)s.vL << 26) | ((uint32_t)s.actR << 27) | ((uint32_t)s.actL << 28) | ((uint32_t)s.scan0 << 29) | ((uint32_t)s.scan1 << 30));
+           ((uint32_t)s.vL << 26) | ((uint32_t)s.actR << 27) | ((uint32_t)s.actL << 28) | ((uint32_t)s.scan0 << 29) | ((uint32_t)s.scan1 << 30) | ((uint32_t)s.adv << 31));
     put(1, (uint32_t)s.ia | ((uint32_t)s.ib << 12) | ((uint32_t)s.uSub << 24) | ((uint32_t)s.lSub << 26));
     put(2, LS_P2(s.bump, s.free_head)); put(3, LS_P2(s.ux, s.uy)); put(4, LS_P2(s.uHl, s.uHr)); put(5, LS_P2(s.li, s.ri));
     put(6, LS_P2(s.lHl, s.lHr)); put(7, LS_P2(s.e, s.headL)); put(8, LS_P2(s.headR, s.hr1)); put(9, LS_P2(s.r1, s.hr2));
@@ -133,7 +134,7 @@ template <class Get>
 GT_INLINE void ls_unpack(LState& s, Get&& get) {
     uint32_t w = get(0);
     s.phase = w & 15; s.d = (w >> 4) & 15; s.k = (w >> 8) & 0xfff; s.err = (w >> 20) & 15; s.first_edge = (w >> 24) & 1; s.vR = (w >> 25) & 1;
-    s.vL = (w >> 26) & 1; s.actR = (w >> 27) & 1; s.actL = (w >> 28) & 1; s.scan0 = (w >> 29) & 1; s.scan1 = (w >> 30) & 1;
+    s.vL = (w >> 26) & 1; s.actR = (w >> 27) & 1; s.actL = (w >> 28) & 1; s.scan0 = (w >> 29) & 1; s.scan1 = (w >> 30) & 1; s.adv = (w >> 31) & 1;
     w = get(1); s.ia = w & 0xfff; s.ib = (w >> 12) & 0xfff; s.uSub = (w >> 24) & 3; s.lSub = (w >> 26) & 3;
 #define LS_U2(i, a, b) w = get(i); a = (int)(w & 0xffff); b = (int)(w >> 16)
     LS_U2(2, s.bump, s.free_head); LS_U2(3, s.ux, s.uy); LS_U2(4, s.uHl, s.uHr); LS_U2(5, s.li, s.ri);
@@ -200,7 +201,7 @@ GT_INLINE void lp_next_node(const LFrame& f, LState& s) {
 }
 
 GT_INLINE void lp_begin(const LFrame& f, LState& s) {
-    s.d = -1; s.k = 0; s.err = 0; s.bump = 0; s.free_head = GT_NIL;
+    s.d = -1; s.k = 0; s.err = 0; s.bump = 0; s.free_head = GT_NIL; s.adv = 0;
     s.first_edge = s.vR = s.vL = s.actR = s.actL = s.scan0 = s.scan1 = 0; s.uSub = s.lSub = 0;
     lp_next_node(f, s);
 }
@@ -247,7 +248,10 @@ GT_INLINE void lp_finish_connect(const LFrame& f, LState& s) {
     s.e = s.h0;                                            // li -> ri
     s.hl1 = s.plNx0;                                       // succ(li, ri)
     s.hr1 = s.plAt1;                                       // pred(ri, li)
-    if (s.li == s.ux && s.ri == s.uy) lp_next_node(f, s); else s.phase = LP_V;
+    // the merge is complete at the upper tangent. The tree cursor is advanced by the next LP_TINIT iteration, not
+    // here: this is the tail of the insert step, the longest step of a round, and nearly every 32-slot chunk of it
+    // holds a slot that finishes a merge
+    if (s.li == s.ux && s.ri == s.uy) { s.adv = 1; s.phase = LP_TINIT; } else s.phase = LP_V;
 }
 
 // Put half-edge h (origin P, destination IN) between `at` and `nx` in P's ring (reference insertNodeAfter :202-208).
@@ -315,6 +319,7 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
     }
 
     if (PH == LP_TINIT) {
+        if (s.adv) { s.adv = 0; lp_next_node(f, s); if (s.phase != LP_TINIT) return; }      // (see lp_finish_connect)
         // both tangents start at the rightmost vertex of the left half and the leftmost of the right half
         const int x = (s.ia + s.ib) / 2, y = x + 1;
         int hdx = 0, hdy = 0;
