@@ -43,8 +43,8 @@ FP64_PEAK_TFLOPS_NOMINAL = 37.2                   # 148 SM x 64 DFMA/clk x 2 x 1
 NCU_DRAM_BYTES_PER_FRAME_FUSED = 26254
 NCU_DRAM_BYTES_PER_FRAME_LPF = 1984000
 # share of the step's GPU time spent in gt::lpf_wave_kernel, from the ncu launch list of this command
-# (profiles/r1_launches_summary.txt; the rest: pre-pass 8.3 %, area kernel 4.2 %)
-LPF_WAVE_SHARE = 0.872
+# (profiles/r1_launches_summary.txt; the rest: pre-pass 8.6 %, area kernel 4.4 %)
+LPF_WAVE_SHARE = 0.866
 LPF_MIN_FRAMES = 32768               # launches at least this large use the lane-per-frame pipeline (gta_b200_set_batch_threshold)
 WORKLOAD = "cfg3: 2,048-lipid bilayer leaflet, 1,024 atoms/frame, -corr -espace 0.8, 3-D area"
 
@@ -289,7 +289,7 @@ def run_native(args):
                          "traffic": (NCU_DRAM_BYTES_PER_FRAME_LPF if lpf else NCU_DRAM_BYTES_PER_FRAME_FUSED) * frames_per_launch / 1e9,
                          "traffic_unit": "GB per launch (ncu dram bytes per frame x frames per launch)",
                          "peak_source": pk_src,
-                         "kernel": ("gt::lpf_wave_kernel<512,false> (%.1f%% of the step; pre-pass gt::tessellate_kernel<256,4,true> 8.3%%, gt::lpf_area_kernel 4.2%%)" % (100 * LPF_WAVE_SHARE)) if lpf else "gt::tessellate_kernel<128,3>",
+                         "kernel": ("gt::lpf_wave_kernel<512,false> (%.1f%% of the step; pre-pass gt::tessellate_kernel<256,4,true> 8.6%%, gt::lpf_area_kernel 4.4%%)" % (100 * LPF_WAVE_SHARE)) if lpf else "gt::tessellate_kernel<128,3>",
                          "launches_per_step": parts, "frames_per_launch": frames_per_launch,
                          "kernel_ms_per_launch": dom_ms, "pipeline_ms_per_step": kern_ms, "alg_bytes_per_frame": ALG_BYTES_PER_FRAME,
                          "note": "bound by the latency of dependent scattered 32-byte reads (two to three levels per iteration, L2 hit rate ~30 %); algorithmic bytes are 80x below the HBM traffic and the traffic is 11 % of HBM peak; see DESIGN.md section 5"},
