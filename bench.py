@@ -38,10 +38,10 @@ ALG_BYTES_PER_FRAME = NATOMS * 24 + 72 + 16      # coordinates +
 ALG_FLOP_PER_FRAME = 203.6e3                      # SURVEY.md §8d implementation-independent lower bound
 FP64_PEAK_TFLOPS_NOMINAL = 37.2                   # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz (not in MEASURED_PEAKS.json)
 # dram read+write per frame from ncu --set full captures (profiles/): the fused CTA-per-frame kernel (6,000 frames) and the
-# dominant kernel of the lane-per-frame pipeline, gt::lpf_wave_kernel, on one launch of 50,000 frames (77.3 GB read +
-# 21.9 GB written: the frames' workspaces live in HBM and 50,000 of them do not fit in L2)
+# dominant kernel of the lane-per-frame pipeline, gt::lpf_wave_kernel, on one launch of 50,000 frames (76.0 GB read +
+# 21.7 GB written: the frames' workspaces live in HBM and 50,000 of them do not fit in L2)
 NCU_DRAM_BYTES_PER_FRAME_FUSED = 26254
-NCU_DRAM_BYTES_PER_FRAME_LPF = 1984000
+NCU_DRAM_BYTES_PER_FRAME_LPF = 1955000
 # share of the step's GPU time spent in gt::lpf_wave_kernel, from the ncu launch list of this command
 # (profiles/r1_launches_summary.txt; the rest: pre-pass 8.6 %, area kernel 4.4 %)
 LPF_WAVE_SHARE = 0.866
@@ -292,7 +292,7 @@ def run_native(args):
                          "kernel": ("gt::lpf_wave_kernel<512,false> (%.1f%% of the step; pre-pass gt::tessellate_kernel<256,4,true> 8.6%%, gt::lpf_area_kernel 4.4%%)" % (100 * LPF_WAVE_SHARE)) if lpf else "gt::tessellate_kernel<128,3>",
                          "launches_per_step": parts, "frames_per_launch": frames_per_launch,
                          "kernel_ms_per_launch": dom_ms, "pipeline_ms_per_step": kern_ms, "alg_bytes_per_frame": ALG_BYTES_PER_FRAME,
-                         "note": "bound by the latency of dependent scattered 32-byte reads (two to three levels per iteration, L2 hit rate ~30 %); algorithmic bytes are 80x below the HBM traffic and the traffic is 11 % of HBM peak; see DESIGN.md section 5"},
+                         "note": "bound by the latency of dependent scattered 32-byte reads (two to three levels per iteration, L2 hit rate ~30 %); algorithmic bytes are 79x below the HBM traffic and the traffic is 12 % of HBM peak; see DESIGN.md section 5"},
             "roofline_fp64": {"achieved": fl, "peak": FP64_PEAK_TFLOPS_NOMINAL, "unit": "TFLOP/s", "frac": fl / FP64_PEAK_TFLOPS_NOMINAL,
                               "peak_source": "nominal", "alg_flop_per_frame": ALG_FLOP_PER_FRAME},
             "clocks": clk,
