@@ -61,7 +61,8 @@ int main(int argc, char *argv[]) {
     unsigned long flags = ((int)corr * GTA_CORRECT) | ((int)a2D * GTA_2D) | ((int)print * GTA_PRINT);
     tessellate_area(traj, ndx, NULL, espace, nthreads, &areas, (unsigned char)flags);
     int rc = 0;
-    if (areas.nframes > 0 && areas.area) print_areas(out, &areas);
+    if (gta_last_call_rc() != 0) { print_log("g_tessla: the tessellation failed (error %d); no table written.\n", gta_last_call_rc()); rc = 1; }
+    else if (areas.nframes > 0 && areas.area) print_areas(out, &areas);
     else { print_log("No frames were tessellated.\n"); rc = 1; }
     free_tri_area(&areas);
     close_log();

@@ -38,24 +38,27 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 int round_even(int v) { return (v + 1) & ~1; }
 // Levels of the recursion tree with at most this many nodes run as warp-cooperative merges
 // (tunable for experiments: GTA_B200_COOP_NODES).
+// (environment knobs are read once, under std::call_once: the entry points are called from several host threads)
+int env_once(const char* name, int dflt, int* slot, std::once_flag* once) {
+    std::call_once(*once, [&] { const char* e = getenv(name); *slot = e ? atoi(e) : dflt; });
+    return *slot;
+}
 int coop_nodes_for(int threads) {
-    static int env = -2;
-    if (env == -2) { const char* e = getenv("GTA_B200_COOP_NODES"); env = e ? atoi(e) : -1; }
-    if (env >= 0) return env;
-    return threads / 32;
+    static int env; static std::once_flag once;
+    const int v = env_once("GTA_B200_COOP_NODES", -1, &env, &once);
+    return v >= 0 ? v : threads / 32;
 }
 int pow2_ge(int v) { int p = 2; while (p < v) p <<= 1; return p; }
 
 struct Shape { int threads; size_t smem; int cap, cap_p2; };
 
 int smem_limit() {
-    static int lim = -1;
-    if (lim < 0) {
+    static int lim; static std::once_flag once;
+    std::call_once(once, [] {
         int dev = 0, v = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 227 * 1024;
-        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || v <= 0) v = 227 * 1024;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || v <= 0) { cudaGetLastError(); v = 227 * 1024; }
         lim = v;
-    }
+    });
     return lim;
 }
 
@@ -65,8 +68,8 @@ Shape shape_for(int max_points, int natoms = 0) {
     s.cap_p2 = pow2_ge(s.cap);
     s.smem = gt::smem_bytes_for(s.cap, s.cap_p2, natoms);
     s.threads = s.cap <= 192 ? 32 : (s.cap <= 512 ? 64 : 128);
-    static int env_t = -2;                                   // experiments: GTA_B200_THREADS = 32 | 64 | 128
-    if (env_t == -2) { const char* e = getenv("GTA_B200_THREADS"); env_t = e ? atoi(e) : -1; }
+    static int env_slot; static std::once_flag once;        // experiments: GTA_B200_THREADS = 32 | 64 | 128
+    const int env_t = env_once("GTA_B200_THREADS", -1, &env_slot, &once);
     if (env_t == 32 || env_t == 64 || env_t == 128) s.threads = env_t;
     return s;
 }
@@ -128,54 +131,66 @@ int occupancy_for(const Shape& s) {
     return occ;
 }
 
-// ---- lane-per-frame path: workspace cache (one per device, grows on demand) and launcher
+// ---- throughput path (gta_lpf.cuh): workspace cache (one per device, only ever grows) and launcher
 struct LpfCache {
     gt::LpfWs ws{}; size_t frames = 0; int cap = 0, cap_e = 0; unsigned int* counter = nullptr; cudaEvent_t done = nullptr;
     // feedback for the choice of kernel variant (launch_lpf): predicates the FP filter left undecided, as counted on the device
     unsigned long long* undecided_h = nullptr;      // pinned; the device's running count after the last launch
     unsigned long long undecided_seen = 0; int last_frames = 0; bool pending = false, degenerate = false;
+    // stage timers: four events (before pre-pass, before walkers, before areas, end) per launch since gta_b200_stage_reset
+    std::vector<cudaEvent_t> ev; size_t ev_used = 0;
 };
 LpfCache g_lpf[64];
 std::mutex g_lpf_mu;
 std::mutex g_lpf_launch_mu[64];          // one launch sequence at a time per device: they share the device's workspace
 
-// Launches of at least this many frames use the lane-per-frame path (its throughput needs tens of thousands of
-// frames in flight; below that the CTA-per-frame kernel wins: measured crossover on cfg 3 at ~25k frames).
-// GTA_B200_LPF overrides (0 = never, 1 = always).
+// Environment knobs, read once (experiments; the defaults are the measured best).
+struct LpfEnv { int threshold, slots, threads, carve, split, fslots; };
+const LpfEnv& lpf_env() {
+    static LpfEnv e;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        auto geti = [](const char* n, int d) { const char* v = getenv(n); return v ? atoi(v) : d; };
+        e.threshold = geti("GTA_B200_LPF", GTA_B200_DEFAULT_BATCH_THRESHOLD);
+        e.slots = geti("GTA_B200_LPF_SLOTS", gt::LPF_DEFAULT_SLOTS);
+        e.threads = geti("GTA_B200_LPF_THREADS", 0);
+        e.carve = geti("GTA_B200_LPF_CARVE", 0);
+        e.split = geti("GTA_B200_LPF_SPLIT", -1);
+        e.fslots = geti("GTA_B200_LPF_FSLOTS", 0);
+    });
+    return e;
+}
+
+// Launches of at least this many frames use the throughput path; smaller ones the fused CTA-per-frame kernel, whose
+// per-frame latency is lower. GTA_B200_LPF overrides (0 = never, 1 = always).
 std::atomic<int> g_lpf_threshold{-2};
 int lpf_threshold() {
     int v = g_lpf_threshold.load();
-    if (v == -2) { const char* e = getenv("GTA_B200_LPF"); v = e ? atoi(e) : 32768; g_lpf_threshold.store(v); }
+    if (v == -2) { v = lpf_env().threshold; g_lpf_threshold.store(v); }
     return v;
 }
-// (triangle lists are a parity-test output: they stay on the fused kernel unless the lane-per-frame path is forced)
-bool use_lpf(int nframes, const Shape& s, bool want_tri) { return lpf_threshold() > 0 && nframes >= lpf_threshold() && s.cap < 4000 && (!want_tri || lpf_threshold() == 1); }
+bool use_lpf(int nframes, const Shape& s) { return lpf_threshold() > 0 && nframes >= lpf_threshold() && s.cap < 4000; }
 
-// Most frames one lane-per-frame launch should get: one slot per frame and SM-resident block. Beyond that the kernel
-// refills slots as frames finish, and since the frames of a batch finish together the refill runs nearly empty
-// (131,072 frames in one launch: 194 k frames/s; as 2 x 65,536: 298 k). Larger batches are split evenly.
-long long lpf_frames_per_launch(int dev) {
-    int sms = 0;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    return (long long)sms * gt::LPF_MAX_SLOTS;
+// Most frames one launch of the throughput path takes: bounds the workspace (32 B per point + 16 B per edge, per frame).
+long long lpf_frames_per_launch(const Shape& s) {
+    return std::max<long long>(4096, (12ll << 30) / (32ll * std::max(s.cap, 1) + 16ll * gt::pool_edges(s.cap)));
 }
 
 int lpf_ensure(int dev, size_t frames, int cap, int cap_e, LpfCache** out) {
     std::lock_guard<std::mutex> lk(g_lpf_mu);
     LpfCache& c = g_lpf[dev];
     if (c.frames < frames || c.cap < cap || c.cap_e < cap_e) {
-        cudaFree(c.ws.pt); cudaFree(c.ws.rec);
-        cudaFree(c.ws.n); cudaFree(c.ws.st); cudaFree(c.ws.err); cudaFree(c.counter);
-        if (c.done) { cudaDeviceSynchronize(); cudaEventDestroy(c.done); }
-        if (c.undecided_h) cudaFreeHost(c.undecided_h);
-        c = LpfCache();
+        // grow only: keep the larger of the old and the new request in every dimension
         frames = std::max(frames, c.frames); cap = std::max(cap, c.cap); cap_e = std::max(cap_e, c.cap_e);
+        if (c.done) cudaDeviceSynchronize();
+        cudaFree(c.ws.pt); cudaFree(c.ws.rec); cudaFree(c.ws.n); cudaFree(c.ws.st); cudaFree(c.ws.err);
+        c.ws = gt::LpfWs{}; c.frames = 0; c.cap = c.cap_e = 0;
         CK(cudaMalloc((void**)&c.ws.pt, sizeof(gt::LPt) * frames * cap));
-        CK(cudaMalloc((void**)&c.ws.rec, sizeof(gt::LRec) * frames * 2 * (size_t)cap_e));
+        CK(cudaMalloc((void**)&c.ws.rec, sizeof(gt::LRec) * (frames + 1) * 2 * (size_t)cap_e));      // (+1: slack behind the last frame)
         CK(cudaMalloc((void**)&c.ws.n, 4 * frames)); CK(cudaMalloc((void**)&c.ws.st, 4 * frames)); CK(cudaMalloc((void**)&c.ws.err, 4 * frames));
-        CK(cudaMalloc((void**)&c.counter, 4));
-        CK(cudaMallocHost((void**)&c.undecided_h, 8)); *c.undecided_h = 0;
-        CK(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
+        if (!c.counter) CK(cudaMalloc((void**)&c.counter, 4));
+        if (!c.undecided_h) { CK(cudaMallocHost((void**)&c.undecided_h, 8)); *c.undecided_h = 0; }
+        if (!c.done) CK(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
         c.ws.cap = cap; c.ws.cap_e = cap_e; c.frames = frames; c.cap = cap; c.cap_e = cap_e;
     }
     *out = &c;
@@ -188,6 +203,22 @@ int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st) {
     int dev = 0, sms = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const LpfEnv& env = lpf_env();
+    // A frame starts as 2^split subtree walkers. More walkers per frame = fewer frames (ring pools) in flight for the
+    // same number of busy slots, and small batches still fill the GPU.
+    // Measured (cfg 3, n = 1,156): split 2 / 3 / 4 / 5 -> 237 / 250 / 263 / 277 k frames/s at 100k frames; cfg 1 (n = 100): 1 is
+    // best. Default: subtrees of ~32-64 points.
+    int split = env.split;
+    if (split < 0) { split = 1; while (split < gt::LPF_MAX_SPLIT && (s.cap >> (split + 6)) >= 1) ++split; }
+    split = std::max(0, std::min(split, gt::LPF_MAX_SPLIT));
+    // spread the walkers over every SM: fewer slots per block shorten the round when the batch is small
+    const long long walkers = (long long)p.nframes << split;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>(sms, (walkers + 63) / 64));
+    int S = (int)std::min<long long>((walkers + blocks - 1) / blocks, 1 << 20);
+    S = std::max(64, std::min((S + 31) & ~31, std::min(env.slots, gt::LPF_MAX_SLOTS)));
+    // frame slots per block (12 bytes of shared memory each): a frame averages ~0.6 * 2^split live walkers over its life
+    int FS = env.fslots > 0 ? env.fslots : (split == 0 ? S : (5 * S) / (2 << split) + 8);
+    FS = std::max(2, std::min(FS, S));
     // the workspace is shared by all streams (and host threads) of this device: launches queue behind each other
     // (copies of the next chunk still overlap). The lock covers grow-workspace, wait-on-previous ... record-done, so
     // that two host threads cannot both queue behind the same earlier launch and then run side by side in one workspace.
@@ -196,52 +227,52 @@ int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st) {
     int rc = lpf_ensure(dev, (size_t)p.nframes, s.cap, gt::pool_edges(s.cap), &c);
     if (rc) return rc;
     CK(cudaStreamWaitEvent(st, c->done, 0));
+    // stage timers (gta_b200_stage_ms): events on the launching stream around each of the three kernels
+    cudaEvent_t* tev = nullptr;
+    if (c->ev_used + 4 <= 4 * 64) {
+        while (c->ev.size() < c->ev_used + 4) { cudaEvent_t e; CK(cudaEventCreate(&e)); c->ev.push_back(e); }
+        tev = c->ev.data() + c->ev_used; c->ev_used += 4;
+        CK(cudaEventRecord(tev[0], st));
+    }
     // 1. pre-pass (load, -corr, sort) into the workspace
     p.ws = c->ws;
     rc = launch_prepass(p, s, st);
     if (rc) return rc;
-    // 2. one lane per frame
+    if (tev) CK(cudaEventRecord(tev[1], st));
+    // 2. walkers
     gt::LpfParams lp; lp.ws = c->ws; lp.nframes = p.nframes; lp.counter = c->counter; lp.dbg = p.dbg ? p.dbg + 32 : nullptr;
+    lp.split = split; lp.fslots = FS;
     CK(cudaMemsetAsync(c->counter, 0, 4, st));
-    static int slots = -1, wthreads = -1;                    // frames in flight per block / threads per block (experiments: GTA_B200_LPF_SLOTS, _THREADS)
-    if (slots < 0) { const char* e = getenv("GTA_B200_LPF_SLOTS"); slots = e ? atoi(e) : gt::LPF_MAX_SLOTS; }
-    if (wthreads < 0) { const char* e = getenv("GTA_B200_LPF_THREADS"); wthreads = e ? atoi(e) : 0; }
     // Which build of the kernel? Without stage A' of the predicates (gt_predicates.cuh) the steps fit 128 registers and
-    // 16 warps per SM: best when the FP filter decides everything, as it does on real coordinates (cfg 3: 263 k frames/s
-    // vs 253 k; 16 warps against 14: the same up to 50 k frames per launch, 335 k vs 308 k at 66 k, where a round has
-    // more chunks than 14 warps). With stage A', 12 warps: 2x faster on degenerate few-bit input (cfg 5). The previous
-    // launch on this device tells which kind of data this is: the device counts the undecided predicates (1 lane in 8).
+    // 16 warps per SM: best when the FP filter decides everything, as it does on real coordinates (cfg 3). With stage A',
+    // 12 warps: 2x faster on degenerate few-bit input (cfg 5). The previous launch on this device tells which kind of
+    // data this is: the device counts the undecided predicates (1 lane in 8).
     if (c->pending && cudaEventQuery(c->done) == cudaSuccess) {
         const unsigned long long now = *c->undecided_h;
         c->degenerate = (now - c->undecided_seen) * 8 >= 16ull * (unsigned long long)c->last_frames;
         c->undecided_seen = now; c->pending = false;
     }
     {
-        // spread the batch over every SM: fewer slots per block shorten the round when the batch is small
-        const int blocks = std::max(1, std::min(sms, (p.nframes + 63) / 64));
-        int S = (p.nframes + blocks - 1) / blocks;
-        S = std::max(64, std::min((S + 31) & ~31, std::min(slots, gt::LPF_MAX_SLOTS)));
-        static int xcarve = -1;                                  // (experiments: GTA_B200_LPF_CARVE = carve-out in percent)
-        if (xcarve < 0) { const char* e = getenv("GTA_B200_LPF_CARVE"); xcarve = e ? atoi(e) : 0; }
-        const size_t smem = (size_t)gt::LS_WORDS * gt::LPF_MAX_SLOTS * 4 + (size_t)S * 4 + (size_t)S * 2 + 2 * (size_t)(gt::LP_DONE + 1) * S * 2 + (48 + 8) * 4 + 64;
+        const size_t smem = gt::LpfSmem(S, FS).total;
         auto go = [&](auto kern, int threads) -> int {
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             // everything that is not shared memory should be L1: ask for the smallest carve-out that holds the block
-            CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, xcarve ? xcarve : (int)std::min<size_t>(100, (smem + 1024) * 100 / (228 * 1024) + 1)));
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, env.carve ? env.carve : (int)std::min<size_t>(100, (smem + 1024) * 100 / (228 * 1024) + 1)));
             kern<<<blocks, threads, smem, st>>>(lp, S);
             CK(cudaGetLastError());
             return GTA_B200_OK;
         };
-        if (wthreads == 448) rc = go(gt::lpf_wave_kernel<448, false>, 448);                 // (experiment)
-        else if (c->degenerate || wthreads == 384) rc = go(gt::lpf_wave_kernel<384, true>, 384);
+        if (c->degenerate || env.threads == 384) rc = go(gt::lpf_wave_kernel<384, true>, 384);
         else rc = go(gt::lpf_wave_kernel<512, false>, 512);
         if (rc) return rc;
     }
+    if (tev) CK(cudaEventRecord(tev[2], st));
     // 3. areas
     gt::LpfAreaParams ap; ap.ws = c->ws; ap.nframes = p.nframes; ap.natoms = p.natoms; ap.flags = p.flags;
     ap.area = p.area; ap.area2d = p.area2d; ap.status = p.status; ap.ntri = p.ntri; ap.tri = p.tri; ap.tri_cap = p.tri_cap;
     gt::lpf_area_kernel<<<(p.nframes + 3) / 4, 128, 0, st>>>(ap);
     CK(cudaGetLastError());
+    if (tev) CK(cudaEventRecord(tev[3], st));
     CK(cudaMemcpyFromSymbolAsync(c->undecided_h, gt::g_xcalls, 8, 0, cudaMemcpyDeviceToHost, st));
     c->last_frames = p.nframes; c->pending = true;
     CK(cudaEventRecord(c->done, st));
@@ -260,6 +291,32 @@ extern "C" {
 const char* gta_b200_large_error(void);
 const char* gta_b200_last_error(void) { return g_err.empty() ? gta_b200_large_error() : g_err.c_str(); }
 double gta_b200_last_kernel_ms(void) { return g_last_kernel_ms; }
+
+// Stage timers of the throughput path on `device` (< 0: current): forget the launches seen so far / wait for the launches
+// since the last reset and add up their three kernels' durations (CUDA events on the launching streams).
+int gta_b200_stage_reset(int device) {
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return fail(GTA_B200_E_CUDA, "cudaGetDevice");
+    if (device < 0 || device >= 64) return fail(GTA_B200_E_ARG, "device index out of range");
+    std::lock_guard<std::mutex> launch_lock(g_lpf_launch_mu[device]);
+    g_lpf[device].ev_used = 0;
+    return GTA_B200_OK;
+}
+int gta_b200_stage_ms(int device, double* prepass_ms, double* walk_ms, double* area_ms, int* launches) {
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return fail(GTA_B200_E_CUDA, "cudaGetDevice");
+    if (device < 0 || device >= 64) return fail(GTA_B200_E_ARG, "device index out of range");
+    std::lock_guard<std::mutex> launch_lock(g_lpf_launch_mu[device]);
+    LpfCache& c = g_lpf[device];
+    double t[3] = {0.0, 0.0, 0.0};
+    for (size_t i = 0; i + 4 <= c.ev_used; i += 4) {
+        CK(cudaEventSynchronize(c.ev[i + 3]));
+        for (int k = 0; k < 3; ++k) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c.ev[i + k], c.ev[i + k + 1])); t[k] += ms; }
+    }
+    if (prepass_ms) *prepass_ms = t[0];
+    if (walk_ms) *walk_ms = t[1];
+    if (area_ms) *area_ms = t[2];
+    if (launches) *launches = (int)(c.ev_used / 4);
+    return GTA_B200_OK;
+}
 int gta_b200_last_launches(void) { return g_last_launches; }
 
 int gta_b200_device_count(void) {
@@ -270,7 +327,7 @@ int gta_b200_device_count(void) {
 
 int gta_b200_set_batch_threshold(int min_frames) {
     int old = lpf_threshold();
-    g_lpf_threshold.store(min_frames < 0 ? 32768 : min_frames);
+    g_lpf_threshold.store(min_frames < 0 ? GTA_B200_DEFAULT_BATCH_THRESHOLD : min_frames);
     return old;
 }
 
@@ -320,6 +377,7 @@ int gta_b200_tessellate_device(const double* d_xyz, int in_dim, const double* d_
                                int* d_tri, int tri_cap, int* d_ntri,
                                double* d_corr, int corr_cap, int* d_ncorr,
                                unsigned int* d_work, void* stream) {
+    g_err.clear();
     if (!have_device()) return fail(GTA_B200_E_NO_DEVICE, "no CUDA device: libgtessla_b200 has no CPU path");
     if (nframes < 0 || natoms < 0 || (in_dim != 2 && in_dim != 3) || !d_xyz || !d_work)
         return fail(GTA_B200_E_ARG, "bad argument");
@@ -339,12 +397,10 @@ int gta_b200_tessellate_device(const double* d_xyz, int in_dim, const double* d_
     p.corr = d_corr; p.corr_cap = corr_cap; p.ncorr = d_ncorr;
     p.work = d_work; p.coop_nodes = coop_nodes_for(s.threads); p.dbg = g_dbg; p.ws = gt::LpfWs{};
     CK(cudaMemsetAsync(d_work, 0, sizeof(unsigned int), st));
-    const bool lpf = use_lpf(nframes, s, d_tri != nullptr);
+    const bool lpf = use_lpf(nframes, s);
     if (!lpf) { g_last_launches = 1; return launch(p, s, st); }                      // the fused kernel
-    // lane per frame: pre-pass + state machine + area per launch; batches beyond one launch's worth are split evenly
-    int dev = 0;
-    CK(cudaGetDevice(&dev));
-    const long long per_launch = lpf_frames_per_launch(dev);
+    // throughput path: pre-pass + walker kernel + area kernel per launch; batches beyond one launch's worth are split evenly
+    const long long per_launch = lpf_frames_per_launch(s);
     const long long parts = (nframes + per_launch - 1) / per_launch;
     g_last_launches = 3 * (int)parts;
     for (long long k = 0; k < parts; ++k) {
@@ -441,7 +497,8 @@ SlotCache g_caches[64];
 
 int drain(Slot& s, const Job& j, double* kernel_ms) {
     if (!s.busy) return GTA_B200_OK;
-    static const bool trace = getenv("GTA_B200_TRACE") != nullptr;
+    static int trace_slot; static std::once_flag trace_once;
+    const bool trace = env_once("GTA_B200_TRACE", 0, &trace_slot, &trace_once) != 0;
     const auto t_begin = std::chrono::steady_clock::now();
     CK(cudaStreamSynchronize(s.st));
     if (trace) fprintf(stderr, "[gta_b200] chunk %d+%d: waited %.1f ms for copies + kernels\n", s.f0, s.nf, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
@@ -459,7 +516,8 @@ int drain(Slot& s, const Job& j, double* kernel_ms) {
 }
 
 int submit(Slot& s, const Job& j, const Shape& shp, int f0, int nf, bool src_pinned) {
-    static const bool trace = getenv("GTA_B200_TRACE") != nullptr;
+    static int trace_slot; static std::once_flag trace_once;
+    const bool trace = env_once("GTA_B200_TRACE", 0, &trace_slot, &trace_once) != 0;
     const auto t_begin = std::chrono::steady_clock::now();
     const size_t frame_elems = (size_t)j.natoms * j.in_dim, frame_bytes = frame_elems * sizeof(double);
     s.f0 = f0; s.nf = nf;
@@ -503,7 +561,7 @@ int submit(Slot& s, const Job& j, const Shape& shp, int f0, int nf, bool src_pin
     CK(cudaMemsetAsync(s.d_work, 0, sizeof(unsigned int), s.st));
     CK(cudaMemsetAsync(s.d_st, 0, sizeof(int) * 3 * (size_t)c, s.st));
     CK(cudaEventRecord(s.k0, s.st));
-    int rc = use_lpf(nf, shp, j.tri != nullptr) ? launch_lpf(p, shp, s.st) : launch(p, shp, s.st);
+    int rc = use_lpf(nf, shp) ? launch_lpf(p, shp, s.st) : launch(p, shp, s.st);
     if (rc) return rc;
     CK(cudaEventRecord(s.k1, s.st));
     CK(cudaMemcpyAsync(s.h_out, s.d_out, sizeof(double) * 3 * (size_t)c, cudaMemcpyDeviceToHost, s.st));
@@ -515,6 +573,7 @@ int submit(Slot& s, const Job& j, const Shape& shp, int f0, int nf, bool src_pin
 }
 
 int run_job(Job j, int device, int nstreams) {
+    g_err.clear();
     if (!have_device()) return fail(GTA_B200_E_NO_DEVICE, "no CUDA device: libgtessla_b200 has no CPU path");
     if (j.nframes < 0 || j.natoms < 0 || (j.in_dim != 2 && j.in_dim != 3) || (!j.xyz && !j.frames))
         return fail(GTA_B200_E_ARG, "bad argument");
@@ -535,16 +594,18 @@ int run_job(Job j, int device, int nstreams) {
     long long chunk = (j.nframes + nstreams - 1) / nstreams;
     chunk = std::min<long long>(chunk, std::max<long long>(256, (64ll << 20) / (long long)std::max<size_t>(frame_bytes, 1)));
     chunk = std::max<long long>(chunk, 1);
-    if (j.tri) chunk = std::min<long long>(chunk, std::max<long long>(1, (256ll << 20) / (12ll * std::max(j.tri_cap, 1))));
-    if (use_lpf(j.nframes, shp, j.tri != nullptr)) {
-        // lane-per-frame path: it wants tens of thousands of frames per launch; two slots so that the copies of one
-        // chunk overlap the kernels of the other
-        const long long per_launch = lpf_frames_per_launch(device);
-        const long long nchunks = (j.nframes + per_launch - 1) / per_launch;
+    if (use_lpf(j.nframes, shp)) {
+        // throughput path: a launch lasts at least one frame's critical path (~2,800 rounds), so launches want >= 10^4
+        // frames; up to three chunks in flight so that the copies of one overlap the kernels of another
+        const long long target = std::max<long long>(4096, std::min<long long>(25000, (1ll << 30) / (long long)std::max<size_t>(frame_bytes, 1)));
+        const long long nchunks = (j.nframes + target - 1) / target;
         chunk = (j.nframes + nchunks - 1) / nchunks;
-        nstreams = (int)std::min<long long>(2, nchunks);
+        nstreams = (int)std::min<long long>(3, nchunks);
     }
-
+    if (j.tri) {                                              // (parity tests) triangle lists: bound the device buffer of a chunk to 512 MB
+        const long long fit = std::max<long long>(1, (512ll << 20) / (12ll * std::max(j.tri_cap, 1)));
+        if (chunk > fit) { chunk = fit; nstreams = std::min(nstreams, 2); }
+    }
     bool src_pinned = false;
     if (j.xyz) {
         cudaPointerAttributes at;
@@ -569,7 +630,7 @@ int run_job(Job j, int device, int nstreams) {
         if (rc) break;
         int nf = std::min<long long>(chunk, j.nframes - f0);
         rc = submit(s, j, shp, f0, nf, src_pinned);
-        launches += use_lpf(nf, shp, j.tri != nullptr) ? 3 : 1;          // pre-pass + lane-per-frame + area, or the fused kernel
+        launches += use_lpf(nf, shp) ? 3 : 1;                            // pre-pass + walker kernel + area kernel, or the fused kernel
     }
     for (int i = 0; i < nstreams; ++i) { int r2 = drain(g_cache.slots[i], j, &kms); if (rc == GTA_B200_OK) rc = r2; }
     g_last_kernel_ms = kms; g_last_launches = launches;

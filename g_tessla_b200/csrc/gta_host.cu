@@ -28,7 +28,9 @@
 
 namespace {
 thread_local int g_dt_status = 0;
+thread_local int g_call_rc = 0;                 // GTA_B200_* return code behind the last kept (void) entry point on this thread
 thread_local std::vector<int> g_frame_status;
+const double kNaN = __builtin_nan("");
 FILE* g_log = nullptr;
 
 int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
@@ -61,9 +63,9 @@ void dtinit(void) {
 int dt_last_status(void) { return g_dt_status; }
 
 void dtriangulate(struct dTriangulation* tri) {
-    g_dt_status = 0;
+    g_dt_status = 0; g_call_rc = GTA_B200_OK;
     if (tri->npoints < 2) {                                   // reference delaunay_tri.c:416-421
-        fprintf(stderr, "TRIANGULATION ERROR: Only %d point(s)? That's not enough!\n", tri->npoints);
+        fprintf(stderr, "TRIANGULATION ERROR: Only %d points? That's not enough!\n", tri->npoints);   // the reference's text
         g_dt_status = GTA_B200_ST_TOO_FEW_POINTS;
         return;
     }
@@ -78,7 +80,7 @@ void dtriangulate(struct dTriangulation* tri) {
         rc = gta_b200_triangulate_large(tri->points, n, -1, t, cap, &ntri, &status);
     if (rc != GTA_B200_OK) {
         fprintf(stderr, "TRIANGULATION ERROR: %s\n", gta_b200_last_error());
-        g_dt_status = GTA_B200_ST_INTERNAL; free(t); return;
+        g_dt_status = GTA_B200_ST_INTERNAL; g_call_rc = rc; free(t); return;
     }
     g_dt_status = status;
     if (status != 0) {
@@ -95,6 +97,7 @@ void dtriangulate(struct dTriangulation* tri) {
 
 // ------------------------------------------------------------------------------------------ area pipeline
 const int* gta_last_frame_status(void) { return g_frame_status.empty() ? nullptr : g_frame_status.data(); }
+int gta_last_call_rc(void) { return g_call_rc; }
 
 static void write_showme(const char* node, const char* ele, const double* xy, int npts, const int* tri, int ntri) {
     // reference print_dtrifiles, src/gta_tri.c:475-498
@@ -114,6 +117,7 @@ static void write_showme(const char* node, const char* ele, const double* xy, in
 
 void delaunay_tessellate(rvec** x, matrix* box, real espace, int nthreads, struct tri_area* areas, unsigned char flags) {
     const int F = areas->nframes, N = areas->natoms;
+    g_call_rc = GTA_B200_OK;
     if (nthreads > 1 || nthreads <= 0) print_log("Triangulation will be parallelized.\n");   // gta_tri.c:93-94
     dtinit();
     areas->area = (real*)calloc((size_t)(F > 0 ? F : 1), sizeof(real));
@@ -124,11 +128,24 @@ void delaunay_tessellate(rvec** x, matrix* box, real espace, int nthreads, struc
     g_frame_status.assign((size_t)(F > 0 ? F : 1), 0);
     if (F <= 0) return;
     const unsigned fl = flags & (GTA_CORRECT | GTA_2D);
+    const int maxp = gta_b200_max_points_for(&box[0][0][0], 9, F, N, espace, fl);
     int rc;
-    if (flags & GTA_PRINT) {
+    if (maxp > gta_b200_max_points()) {
+        // frames too large for the batched shared-memory kernel (e.g. a whole system without -n): one frame at a time
+        // through the large-frame path, which has no correction-point stage
+        rc = GTA_B200_OK;
+        for (int fr = 0; fr < F && rc == GTA_B200_OK; ++fr) {
+            double a3 = 0.0, a2 = 0.0; int st = 0;
+            rc = gta_b200_surface_area_large(&x[fr][0][0], N, fl, -1, &a3, &a2, nullptr, &st);
+            if (rc != GTA_B200_OK) break;
+            g_frame_status[fr] = st;
+            areas->area[fr] = st ? kNaN : a3;
+            if (areas->area2D) areas->area2D[fr] = st ? kNaN : a2;
+            areas->area2Dbox[fr] = box[fr][XX][XX] * box[fr][YY][YY];
+        }
+    } else if (flags & GTA_PRINT) {
         // one frame at a time (the reference also serialises -print, g_tessla.c:116); files are numbered from 1
         static int iter = 0;
-        const int maxp = gta_b200_max_points_for(&box[0][0][0], 9, F, N, espace, fl);
         std::vector<int> tri(3 * (size_t)(2 * maxp)); std::vector<double> corr(3 * (size_t)(maxp - N + 1)), xy(2 * (size_t)maxp);
         rc = GTA_B200_OK;
         for (int fr = 0; fr < F && rc == GTA_B200_OK; ++fr) {
@@ -149,24 +166,63 @@ void delaunay_tessellate(rvec** x, matrix* box, real espace, int nthreads, struc
         rc = gta_b200_tessellate_frames((const double* const*)x, &box[0][0][0], F, N, espace, fl, ngpus <= 0 ? gta_b200_device_count() : ngpus,
                                         nthreads, areas->area, areas->area2D, areas->area2Dbox, g_frame_status.data());
     }
-    if (rc != GTA_B200_OK) { print_log("TESSELLATION ERROR: %s\n", gta_b200_last_error()); return; }
+    if (rc != GTA_B200_OK) {
+        // every function of this interface is void (reference include/gta_tri.h): the failure is reported on the log, in
+        // gta_last_call_rc(), and as NaN areas with an INTERNAL status on every frame -- never as a table of zeros
+        print_log("TESSELLATION ERROR: %s\n", gta_b200_last_error());
+        g_call_rc = rc;
+        for (int fr = 0; fr < F; ++fr) {
+            areas->area[fr] = kNaN; if (areas->area2D) areas->area2D[fr] = kNaN;
+            g_frame_status[fr] |= GTA_B200_ST_INTERNAL;
+        }
+        return;
+    }
     int bad = 0;
     for (int fr = 0; fr < F; ++fr) bad += g_frame_status[fr] != 0;
     if (bad) print_log("WARNING: %d frame(s) were rejected (NaN area); see gta_last_frame_status().\n", bad);
 }
 
 void delaunay_surface_area(const rvec* x, matrix box, int natoms, unsigned char flags, real* a2D, real* a3D) {
-    (void)box; (void)flags;
-    g_dt_status = 0;
-    if (!a2D && !a3D) return;
-    double a3 = 0.0, a2 = 0.0; int st = 0;
-    int rc = gta_b200_tessellate_batch(&x[0][0], 3, nullptr, 0, 1, natoms, 0.0, a2D ? GTA_B200_2D : 0u, -1, 1,
-                                       &a3, a2D ? &a2 : nullptr, nullptr, &st, nullptr, 0, nullptr, nullptr, 0, nullptr);
-    if (rc != GTA_B200_OK) { fprintf(stderr, "TRIANGULATION ERROR: %s\n", gta_b200_last_error()); g_dt_status = GTA_B200_ST_INTERNAL; return; }
+    (void)box;
+    static int iter = 0;                                       // numbers the -print files, as in the reference (gta_tri.c:338)
+    g_dt_status = 0; g_call_rc = GTA_B200_OK;
+    ++iter;
+    const bool print = (flags & GTA_PRINT) != 0;
+    if (!a2D && !a3D && !print) return;
+    double a3 = 0.0, a2 = 0.0; int st = 0, ntri = 0, rc;
+    std::vector<int> tri;
+    if (natoms > gta_b200_max_points()) {
+        rc = gta_b200_surface_area_large(&x[0][0], natoms, a2D ? GTA_B200_2D : 0u, -1, &a3, &a2, &ntri, &st);
+        if (rc == GTA_B200_OK && print && st == 0) {
+            std::vector<double> xy2(2 * (size_t)natoms);
+            for (int i = 0; i < natoms; ++i) { xy2[2 * i] = x[i][XX]; xy2[2 * i + 1] = x[i][YY]; }
+            tri.resize(3 * (size_t)(ntri > 0 ? ntri : 1));
+            rc = gta_b200_triangulate_large(xy2.data(), natoms, -1, tri.data(), ntri, &ntri, &st);
+        }
+    } else {
+        if (print) tri.resize(3 * (size_t)(2 * (natoms > 1 ? natoms : 1)));
+        rc = gta_b200_tessellate_batch(&x[0][0], 3, nullptr, 0, 1, natoms, 0.0, a2D ? GTA_B200_2D : 0u, -1, 1,
+                                       &a3, a2D ? &a2 : nullptr, nullptr, &st, print ? tri.data() : nullptr, print ? 2 * natoms : 0, &ntri,
+                                       nullptr, 0, nullptr);
+    }
+    if (rc != GTA_B200_OK) {
+        fprintf(stderr, "TRIANGULATION ERROR: %s\n", gta_b200_last_error());
+        g_dt_status = GTA_B200_ST_INTERNAL; g_call_rc = rc;
+        if (a3D) *a3D = kNaN;
+        if (a2D) *a2D = kNaN;
+        return;
+    }
     g_dt_status = st;
-    if (st & GTA_B200_ST_TOO_FEW_POINTS) fprintf(stderr, "TRIANGULATION ERROR: Only %d point(s)? That's not enough!\n", natoms);
-    if (a3D) *a3D = a3;
-    if (a2D) *a2D = a2;
+    if (st & GTA_B200_ST_TOO_FEW_POINTS) fprintf(stderr, "TRIANGULATION ERROR: Only %d points? That's not enough!\n", natoms);
+    if (print && st == 0) {                                    // triangles<iter>.node / .ele (gta_tri.c:355-360)
+        std::vector<double> xy(2 * (size_t)natoms);
+        for (int i = 0; i < natoms; ++i) { xy[2 * i] = x[i][XX]; xy[2 * i + 1] = x[i][YY]; }
+        char n1[64], n2[64];
+        snprintf(n1, sizeof n1, "triangles%d.node", iter); snprintf(n2, sizeof n2, "triangles%d.ele", iter);
+        write_showme(n1, n2, xy.data(), natoms, tri.data(), ntri);
+    }
+    if (a3D) *a3D = (st & ~GTA_B200_ST_TOO_FEW_POINTS) ? kNaN : a3;
+    if (a2D) *a2D = (st & ~GTA_B200_ST_TOO_FEW_POINTS) ? kNaN : a2;
 }
 
 void tessellate_area(const char* traj_fname, const char* ndx_fname, output_env_t* oenv, real espace, int nthreads,
@@ -174,11 +230,14 @@ void tessellate_area(const char* traj_fname, const char* ndx_fname, output_env_t
     rvec **pre_x = nullptr, **x = nullptr;
     matrix* box = nullptr;
     areas->area = areas->area2D = areas->area2Dbox = nullptr;          // gta_tri.c:51-53
+    g_call_rc = GTA_B200_OK;
     read_traj(traj_fname, &pre_x, &box, &areas->nframes, &areas->natoms, oenv);
+    if (!pre_x) { g_call_rc = GTA_B200_E_ARG; areas->nframes = 0; return; }
     if (ndx_fname) {
         ndx_filter_traj(ndx_fname, pre_x, &x, areas->nframes, &areas->natoms);
         for (int i = 0; i < areas->nframes; ++i) free(pre_x[i]);
         free(pre_x);
+        if (!x) { g_call_rc = GTA_B200_E_ARG; free(box); areas->nframes = 0; return; }
     } else x = pre_x;
     delaunay_tessellate(x, box, espace, nthreads, areas, flags);
     for (int i = 0; i < areas->nframes; ++i) free(x[i]);
@@ -251,6 +310,7 @@ bool read_gro(FILE* f, Traj& t) {
         xyz.resize(3 * (size_t)n);
         for (int i = 0; i < n; ++i) {
             if (!fgets(line, sizeof line, f)) return false;
+            if (strlen(line) <= 20) return false;                  // a truncated atom line
             // fixed columns: 20 characters of residue/atom fields, then x y z with a common width that is
             // inferred from the spacing of the decimal points (the .gro precision is not fixed at 8.3)
             const char* p = line + 20;
@@ -322,6 +382,8 @@ bool read_trr(FILE* f, Traj& t) {
         for (int i = 0; i < 10; ++i) if (!xdr_i32(f, &sz[i])) return false;   // ir e box vir pres top sym x v f
         if (!xdr_i32(f, &natoms) || !xdr_i32(f, &step) || !xdr_i32(f, &nre)) return false;
         const int box_size = sz[2], x_size = sz[7];
+        for (int i = 0; i < 10; ++i) if (sz[i] < 0) return false;           // counts come from the file: never seek backwards
+        if (natoms < 0 || natoms > (1 << 28)) return false;
         bool dbl;
         if (box_size) dbl = box_size == 9 * 8; else if (natoms > 0 && x_size) dbl = x_size == natoms * 3 * 8; else return false;
         double tl[2];
@@ -330,6 +392,7 @@ bool read_trr(FILE* f, Traj& t) {
         if (box_size) for (int i = 0; i < 9; ++i) if (!xdr_real(f, dbl, &b[i])) return false;
         if (fseek(f, sz[3] + sz[4], SEEK_CUR)) return false;                   // virial, pressure
         if (!x_size) { if (fseek(f, sz[8] + sz[9], SEEK_CUR)) return false; continue; }   // frame without coordinates
+        if ((long long)x_size != (long long)natoms * 3 * (dbl ? 8 : 4)) return false;
         xyz.resize(3 * (size_t)natoms);
         for (size_t i = 0; i < xyz.size(); ++i) if (!xdr_real(f, dbl, &xyz[i])) return false;
         if (fseek(f, sz[8] + sz[9], SEEK_CUR)) return false;                   // velocities, forces
@@ -397,7 +460,7 @@ bool read_xtc(FILE* f, Traj& t) {
     for (;;) {
         int magic, natoms, step;
         if (!xdr_i32(f, &magic)) break;                        // clean EOF
-        if (magic != 1995 || !xdr_i32(f, &natoms) || !xdr_i32(f, &step) || natoms < 0) return false;
+        if (magic != 1995 || !xdr_i32(f, &natoms) || !xdr_i32(f, &step) || natoms < 0 || natoms > (1 << 28)) return false;
         double tm, b[9];
         if (!xdr_f32(f, &tm)) return false;
         for (int i = 0; i < 9; ++i) if (!xdr_f32(f, &b[i])) return false;
@@ -475,11 +538,13 @@ void read_traj(const char* traj_fname, rvec*** x, matrix** box, int* nframes, in
     FILE* f = fopen(traj_fname, "rb");
     if (!f) { fprintf(stderr, "read_traj: cannot open %s\n", traj_fname); return; }
     Traj t; bool ok;
-    if (ends_with(name, ".gro")) ok = read_gro(f, t);
-    else if (ends_with(name, ".pdb")) ok = read_pdb(f, t);
-    else if (ends_with(name, ".trr")) ok = read_trr(f, t);
-    else if (ends_with(name, ".xtc")) ok = read_xtc(f, t);
-    else { fprintf(stderr, "read_traj: %s: unknown trajectory format (supported: .gro .pdb .trr .xtc)\n", traj_fname); fclose(f); return; }
+    try {                                                      // (nothing may propagate through the C interface)
+        if (ends_with(name, ".gro")) ok = read_gro(f, t);
+        else if (ends_with(name, ".pdb")) ok = read_pdb(f, t);
+        else if (ends_with(name, ".trr")) ok = read_trr(f, t);
+        else if (ends_with(name, ".xtc")) ok = read_xtc(f, t);
+        else { fprintf(stderr, "read_traj: %s: unknown trajectory format (supported: .gro .pdb .trr .xtc)\n", traj_fname); fclose(f); return; }
+    } catch (...) { ok = false; }
     fclose(f);
     if (!ok) {
         fprintf(stderr, "read_traj: %s: malformed or empty trajectory\n", traj_fname);
@@ -510,13 +575,18 @@ void ndx_filter_traj(const char* ndx_fname, rvec** pre_x, rvec*** new_x, int nfr
         fclose(f);
     }
     const int n_in = *natoms, n = (int)idx.size();
+    for (int i = 0; i < n; ++i)
+        if (idx[i] < 0 || idx[i] >= n_in) {
+            // a hard error, as with GROMACS: silently substituting a point would change the tessellation
+            fprintf(stderr, "ndx_filter_traj: %s: atom %d out of range (1..%d)\n", ndx_fname, idx[i] + 1, n_in);
+            *new_x = nullptr; *natoms = 0;
+            return;
+        }
     *new_x = (rvec**)malloc(sizeof(rvec*) * (size_t)(nframes > 0 ? nframes : 1));
     for (int fr = 0; fr < nframes; ++fr) {
         (*new_x)[fr] = (rvec*)malloc(sizeof(rvec) * (size_t)(n > 0 ? n : 1));
         for (int i = 0; i < n; ++i) {
-            const int a = idx[i];
-            if (a < 0 || a >= n_in) { fprintf(stderr, "ndx_filter_traj: atom %d out of range (1..%d)\n", a + 1, n_in); memset((*new_x)[fr][i], 0, sizeof(rvec)); continue; }
-            memcpy((*new_x)[fr][i], pre_x[fr][a], sizeof(rvec));
+            memcpy((*new_x)[fr][i], pre_x[fr][idx[i]], sizeof(rvec));
         }
     }
     *natoms = n;

@@ -24,7 +24,7 @@ namespace gt {
 #define GT_TICK(slot) do { } while (0)
 #endif
 
-// Global-memory workspace of the lane-per-frame path (gta_lpf.cuh): one slot per frame of the batch.
+// Global-memory workspace of the throughput path (gta_lpf.cuh): one slot per frame of the batch.
 struct LpfWs {
     LPt* pt; LRec* rec;                                      // strides per frame: cap (x, y, z, ring head, input index), 2*cap_e
     int* n; int* st; uint32_t* err;                          // per frame: point count, status bits of the pre-pass, D&C error bits
@@ -163,11 +163,14 @@ __global__ void __launch_bounds__(T, MINB) tessellate_kernel(const KParams p) {
         if (corr) {
             const int nx = (int)(bx / p.espace), ny = (int)(by / p.espace);      // gta_tri.c:112-113
             const bool boxok = isfinite(bx) && isfinite(by) && nx >= 0 && ny >= 0 && natoms >= 1;
-            const int ncorr = boxok ? 4 + 2 * nx + 2 * ny : 0;
+            // a tiny espace or a huge box: more edge points than any frame can hold -- and 4 + 2 nx + 2 ny must not wrap
+            // (the same bound as gta_b200_max_points_for on the host)
+            const bool toomany = boxok && (nx > (1 << 20) || ny > (1 << 20));
+            const int ncorr = (boxok && !toomany) ? 4 + 2 * nx + 2 * ny : 0;
             const int K = ncorr + 4;                                             // 4 corners + 2(nx+1) + 2(ny+1) slots
             int* cidx = reinterpret_cast<int*>(ckey + K);
             if (!boxok) { if (tid == 0) atomicOr(&ctl[4], natoms < 1 ? GTA_B200_ST_TOO_FEW_POINTS : GTA_B200_ST_NONFINITE); }
-            else if (natoms + ncorr > cap) { if (tid == 0) atomicOr(&ctl[4], GTA_B200_ST_CAPACITY); }
+            else if (toomany || natoms + ncorr > cap) { if (tid == 0) atomicOr(&ctl[4], GTA_B200_ST_CAPACITY); }
             else {
                 const int oymin = 4, oymax = 4 + (nx + 1), oxmin = 4 + 2 * (nx + 1), oxmax = oxmin + (ny + 1);
                 const unsigned long long kmin0 = okey((double)FLT_MAX), kmax0 = okey((double)FLT_MIN);   // gta_tri.c:119-120,137-144

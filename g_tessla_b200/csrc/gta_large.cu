@@ -112,6 +112,24 @@ __global__ void large_emit(FrameL f, const uint32_t* offs, const uint32_t* perm,
         ++o;
     });
 }
+// Area epilogue of a large frame (reference src/gta_tri.c:368-410): per sorted vertex, the sum over the triangles it owns
+// in emission order; the per-vertex sums are then added up by a fixed-shape reduction (cub).
+__global__ void large_area(FrameL f, const uint32_t* perm, const double* xyz, int want2d, double* a3, double* a2) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= f.n) return;
+    const double* pi = xyz + 3 * (size_t)perm[i];
+    double s3 = 0.0, s2 = 0.0;
+    vertex_triangles(f, i, [&](int n1, int n2) {
+        const double* p1 = xyz + 3 * (size_t)perm[n1]; const double* p2 = xyz + 3 * (size_t)perm[n2];
+        s3 += tri_area3(pi[0], pi[1], pi[2], p1[0], p1[1], p1[2], p2[0], p2[1], p2[2]);
+        if (want2d) s2 += tri_area3(pi[0], pi[1], 0.0, p1[0], p1[1], 0.0, p2[0], p2[1], 0.0);
+    });
+    a3[i] = s3; a2[i] = s2;
+}
+__global__ void large_xy(const double* xyz, int n, double* pts) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { pts[2 * (size_t)i] = xyz[3 * (size_t)i]; pts[2 * (size_t)i + 1] = xyz[3 * (size_t)i + 1]; }
+}
 }  // namespace gt
 
 namespace {
@@ -123,12 +141,14 @@ extern "C" double gta_b200_large_last_ms(void) { return g_large_ms; }
 
 #define LCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_lerr = std::string(#call) + ": " + cudaGetErrorString(e_); rc = GTA_B200_E_CUDA; goto done; } } while (0)
 
-extern "C" int gta_b200_triangulate_large(const double* points, int npoints, int device, int* tri, int tri_cap, int* ntri, int* status) {
+// points: [n][2] raw 2-D points, or (xyz3 != nullptr) ignored and taken from xyz3 [n][3], whose z then enters the areas
+static int large_run(const double* points, const double* xyz3, int npoints, int device, int* tri, int tri_cap, int* ntri, int* status,
+                     unsigned flags, double* area3, double* area2) {
     using namespace gt;
     int rc = GTA_B200_OK;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); g_lerr = "no CUDA device: libgtessla_b200 has no CPU path"; return GTA_B200_E_NO_DEVICE; }
-    if (!points || npoints < 0 || (tri_cap > 0 && !tri)) { g_lerr = "bad argument"; return GTA_B200_E_ARG; }
+    if ((!points && !xyz3) || npoints < 0 || (tri_cap > 0 && !tri)) { g_lerr = "bad argument"; return GTA_B200_E_ARG; }
     if (status) *status = 0;
     if (ntri) *ntri = 0;
     if (npoints < 2) { if (status) *status = GTA_B200_ST_TOO_FEW_POINTS; return GTA_B200_OK; }
@@ -139,7 +159,8 @@ extern "C" int gta_b200_triangulate_large(const double* points, int npoints, int
     const uint32_t cap_e = (uint32_t)std::min<long long>(8ll * n + 1024, 0x7fffffff / 2);
     double* d_pts = nullptr; Pt* d_pt = nullptr; unsigned long long *d_k0 = nullptr, *d_k1 = nullptr, *d_ky = nullptr;
     uint32_t *d_i0 = nullptr, *d_i1 = nullptr, *d_head = nullptr, *d_dst = nullptr, *d_nxt = nullptr, *d_prv = nullptr, *d_ctl = nullptr, *d_cnt = nullptr, *d_off = nullptr;
-    int* d_tri = nullptr; void* d_tmp = nullptr; size_t tmp_bytes = 0, tb2 = 0;
+    int* d_tri = nullptr; void* d_tmp = nullptr; size_t tmp_bytes = 0, tb2 = 0, tb3 = 0;
+    double *d_xyz = nullptr, *d_a3 = nullptr, *d_a2 = nullptr, *d_sum = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     const int B = 256, G = (n + B - 1) / B;
     uint32_t hctl[4] = {0, 0, 0, 0};
@@ -152,14 +173,20 @@ extern "C" int gta_b200_triangulate_large(const double* points, int npoints, int
     LCK(cudaMalloc((void**)&d_dst, 8 * (size_t)cap_e)); LCK(cudaMalloc((void**)&d_nxt, 8 * (size_t)cap_e)); LCK(cudaMalloc((void**)&d_prv, 8 * (size_t)cap_e));
     LCK(cudaMalloc((void**)&d_ctl, 16)); LCK(cudaMemset(d_ctl, 0, 16));
     LCK(cudaMalloc((void**)&d_cnt, 4 * (size_t)n)); LCK(cudaMalloc((void**)&d_off, 4 * (size_t)n));
-    LCK(cudaMemcpy(d_pts, points, sizeof(double) * 2 * (size_t)n, cudaMemcpyHostToDevice));
+    if (xyz3) {
+        LCK(cudaMalloc((void**)&d_xyz, sizeof(double) * 3 * (size_t)n));
+        LCK(cudaMalloc((void**)&d_a3, 8 * (size_t)n)); LCK(cudaMalloc((void**)&d_a2, 8 * (size_t)n)); LCK(cudaMalloc((void**)&d_sum, 16));
+        LCK(cudaMemcpy(d_xyz, xyz3, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice));
+        large_xy<<<G, B>>>(d_xyz, n, d_pts);
+    } else LCK(cudaMemcpy(d_pts, points, sizeof(double) * 2 * (size_t)n, cudaMemcpyHostToDevice));
     LCK(cudaEventRecord(ev0));
     {
         // ---- sort: stable by y, then stable by x  => lexicographic (x, y)
         large_keys<<<G, B>>>(d_pts, n, d_k0, d_ky, d_i0, d_ctl + 2);
         cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_ky, d_k1, d_i0, d_i1, n);
         cub::DeviceScan::ExclusiveSum(nullptr, tb2, d_cnt, d_off, n);
-        tmp_bytes = std::max(tmp_bytes, tb2);
+        cub::DeviceReduce::Sum(nullptr, tb3, d_a3, d_sum, n);
+        tmp_bytes = std::max(tmp_bytes, std::max(tb2, tb3));
         LCK(cudaMalloc(&d_tmp, tmp_bytes));
         cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_ky, d_k1, d_i0, d_i1, n);          // by y: order in d_i1
         large_gather_key<<<G, B>>>(d_k0, d_i1, n, d_ky);                                       // x keys in y order
@@ -183,10 +210,9 @@ extern "C" int gta_b200_triangulate_large(const double* points, int npoints, int
         f.pt = d_pt; f.head = d_head; f.dst = d_dst; f.nxt = d_nxt; f.prv = d_prv;
         f.bump = d_ctl; f.stack = nullptr; f.err = d_ctl + 1; f.n = n; f.cap_e = cap_e;
         const int D = tree_depth(n);
-        static int coop_nodes = -1;                                // levels with at most this many merges use the warp-cooperative merge
-        if (coop_nodes < 0) { const char* e = getenv("GTA_B200_LARGE_COOP_NODES"); coop_nodes = e ? atoi(e) : 16384; }
-        static int warp_nodes = -1;
-        if (warp_nodes < 0) { const char* e = getenv("GTA_B200_LARGE_WARP_NODES"); warp_nodes = e ? atoi(e) : 16384; }
+        // levels with at most this many merges use the warp-cooperative merge / one warp per merge (initialised once, thread-safe)
+        static const int coop_nodes = [] { const char* e = getenv("GTA_B200_LARGE_COOP_NODES"); return e ? atoi(e) : 16384; }();
+        static const int warp_nodes = [] { const char* e = getenv("GTA_B200_LARGE_WARP_NODES"); return e ? atoi(e) : 16384; }();
         for (int d = D; d >= 0; --d) {
             const int nodes = 1 << d;
             const int lpn = nodes <= warp_nodes ? 32 : 1;          // one warp per merge while the GPU has warps to spare
@@ -208,6 +234,16 @@ extern "C" int gta_b200_triangulate_large(const double* points, int npoints, int
         if (st) goto done;
         const int total = (int)(last_off + last_cnt);
         if (ntri) *ntri = total;
+        if (xyz3) {
+            double hs[2] = {0.0, 0.0};
+            large_area<<<G, B>>>(f, d_i0, d_xyz, (flags & GTA_B200_2D) ? 1 : 0, d_a3, d_a2);
+            cub::DeviceReduce::Sum(d_tmp, tmp_bytes, d_a3, d_sum, n);
+            cub::DeviceReduce::Sum(d_tmp, tmp_bytes, d_a2, d_sum + 1, n);
+            LCK(cudaGetLastError());
+            LCK(cudaMemcpy(hs, d_sum, 16, cudaMemcpyDeviceToHost));
+            if (area3) *area3 = hs[0];
+            if (area2) *area2 = hs[1];
+        }
         if (tri && tri_cap > 0) {
             const int keep = std::min(total, tri_cap);
             LCK(cudaMalloc((void**)&d_tri, sizeof(int) * 3 * (size_t)std::max(keep, 1)));
@@ -222,8 +258,18 @@ extern "C" int gta_b200_triangulate_large(const double* points, int npoints, int
 done:
     cudaFree(d_pts); cudaFree(d_pt); cudaFree(d_k0); cudaFree(d_k1); cudaFree(d_ky); cudaFree(d_i0); cudaFree(d_i1);
     cudaFree(d_head); cudaFree(d_dst); cudaFree(d_nxt); cudaFree(d_prv); cudaFree(d_ctl); cudaFree(d_cnt); cudaFree(d_off);
-    cudaFree(d_tri); cudaFree(d_tmp);
+    cudaFree(d_tri); cudaFree(d_tmp); cudaFree(d_xyz); cudaFree(d_a3); cudaFree(d_a2); cudaFree(d_sum);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     return rc;
+}
+
+extern "C" int gta_b200_triangulate_large(const double* points, int npoints, int device, int* tri, int tri_cap, int* ntri, int* status) {
+    return large_run(points, nullptr, npoints, device, tri, tri_cap, ntri, status, 0u, nullptr, nullptr);
+}
+// One large frame of atoms [n][3] without correction points: triangulation of (x, y) + summed 3-D (and, with GTA_B200_2D,
+// projected) triangle areas. Serves delaunay_surface_area / delaunay_tessellate for frames beyond gta_b200_max_points().
+extern "C" int gta_b200_surface_area_large(const double* xyz, int natoms, unsigned flags, int device, double* area3, double* area2, int* ntri, int* status) {
+    if (flags & GTA_B200_CORRECT) { g_lerr = "the correction points (-corr) are generated by the batched kernel only: frame too large"; return GTA_B200_E_TOO_LARGE; }
+    return large_run(nullptr, xyz, natoms, device, nullptr, 0, ntri, status, flags, area3, area2);
 }

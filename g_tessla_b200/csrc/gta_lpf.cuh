@@ -1,11 +1,14 @@
-// gta_lpf.cuh -- lane-per-frame execution of the triangulation (see lpf_core.cuh) and its area epilogue.
+// gta_lpf.cuh -- the throughput path: walkers over (frame, subtree) slots, phase-sorted.
 //
-// Pipeline for a large batch (>= tens of thousands of frames; smaller batches stay on the CTA-per-frame
-// kernel, whose per-frame latency is 20x lower):
-//   1. tessellate_kernel in pre-pass mode: load, -corr, sort -> workspace          (gta_kernel.cuh)
-//   2. lpf_wave_kernel: every frame is one slot of a phase-sorted scheduler; a lane runs one iteration of the D&C
-//      state machine (lpf_core.cuh) for one frame at a time                              (this file)
-//   3. lpf_area_kernel: one warp per frame enumerates the triangles and sums areas  (this file)
+// Pipeline for a batch:
+//   1. tessellate_kernel in pre-pass mode: load, -corr, sort -> workspace                      (gta_kernel.cuh)
+//   2. lpf_wave_kernel: one persistent block per SM; every live walker is one slot of a phase-sorted scheduler, a lane
+//      runs one iteration of the D&C state machine (lpf_core.cuh) for one walker at a time         (this file)
+//   3. lpf_area_kernel: one warp per frame enumerates the triangles and sums areas               (this file)
+// A frame is not one lane for its whole life: its recursion tree is cut at depth `split` into independent subtrees that
+// start in parallel and hand over to their parents pairwise (lp_finish_node), so a frame is in flight for ~2,800 rounds
+// instead of ~28,000, ten times fewer frames are live at any time, and a batch of a few thousand frames already fills
+// the GPU.
 // Replaces the same reference loops as the fused kernel (src/gta_tri.c:106-296).
 #pragma once
 #include "gta_kernel.cuh"
@@ -15,8 +18,11 @@ namespace gt {
 struct LpfParams {
     LpfWs ws;
     int nframes;
-    unsigned int* counter;                 // next frame to hand out
-    unsigned long long* dbg;               // -DGT_PHASE_TIMING builds: [3*ph] cycles, [3*ph+1] chunks, [3*ph+2] lanes; [24] barrier wait, [25] rounds x warps, [26..30] rounds of block 0 by chunk count
+    unsigned int* counter;                 // next frame of the batch to hand out
+    int split;                             // a frame starts as 2^split subtree walkers (fewer if it has too few points)
+    int fslots;                            // frames a block can have in flight
+    unsigned long long* dbg;               // -DGT_PHASE_TIMING builds: [3*ph] cycles, [3*ph+1] chunks, [3*ph+2] lanes; [27] live walkers summed over rounds,
+                                           // [28] rounds, [30] barrier wait, [31] rounds x warps
 };
 
 __device__ __forceinline__ LFrame lpf_frame(const LpfWs& ws, int fr) {
@@ -24,58 +30,148 @@ __device__ __forceinline__ LFrame lpf_frame(const LpfWs& ws, int fr) {
     const size_t s = (size_t)fr;
     f.pt = ws.pt + s * ws.cap;
     f.rec = ws.rec + s * 2 * (size_t)ws.cap_e;
+    f.m = nullptr;
     f.n = ws.n[s];
     f.cap_e = ws.cap_e;
     return f;
 }
 
-// One iteration of phase PH for one slot, out of line so that every phase gets a register allocation of its own
-// (inlined into one kernel, the 14 instances share a 128-register budget and spill ~1 KB per thread). The state
-// is unpacked straight from shared memory -- loads of words the phase never reads are dead code -- and only the
-// words the phase may modify (LsDirty<PH>) are written back. Returns the packed phase word's new phase.
 // LPF_MAX_SLOTS = slot capacity of a block = stride of the word-major state array (a constant: the state accesses of a
-// step become base + immediate offset). Deliberately far below what shared memory could hold:
-//  - what is not shared memory is L1, and the steps' loads want it (704 slots in use: 180 k frames/s when the block
-//    needs the 228 KB carve-out and leaves 28 KB of L1, 257 k with 196 KB, 281 k with 164 KB or less);
-//  - a round serves 16 warps; more than ~448 slots per block only queue (measured when 14 warps ran it: 66 k frames per
-//    launch 300 k frames/s, 100 k in one launch 281 k) -- the host splits larger batches into even launches instead
-//    (gta_b200.cu).
-constexpr int LPF_MAX_SLOTS = 576;
+// step become base + immediate offset). A round gives every warp one chunk of <= 32 same-phase slots; with 16 warps and
+// ~25 slots per chunk more than ~352 slots only add second chunks to a round that already lasts as long as its slowest
+// one (measured on cfg 3, 100k frames: 320 / 352 / 384 / 416 / 480 / 576 slots -> 286 / 277 / 276 / 299 / 290 / 294 ms).
+#ifndef GT_LPF_STRIDE
+#define GT_LPF_STRIDE 384
+#endif
+constexpr int LPF_MAX_SLOTS = GT_LPF_STRIDE;
+constexpr int LPF_DEFAULT_SLOTS = 352;
+constexpr int LPF_MAX_SPLIT = 5;           // the "arrived" bits of a frame's top nodes fit one word (lpf_core.cuh LMeta), and a
+                                           // frame's walkers start from one chunk of free slots (<= 32)
 
+// shared-memory layout of a block, computed identically on the host
+struct LpfSmem {
+    size_t st, meta, fs_frame, fs_n, fs_mask, slot_fs, bins, cnt, ctl, total;
+    __host__ __device__ LpfSmem(int slots, int fslots) {
+        constexpr int NB = LP_DONE + 1;
+        size_t o = 0;
+        st = o; o += (size_t)LS_WORDS * LPF_MAX_SLOTS * 4;
+        meta = o; o += sizeof(LMeta) * (size_t)fslots;
+        fs_frame = o; o += 4 * (size_t)fslots;
+        fs_n = o; o += 4 * (size_t)fslots;
+        fs_mask = o; o += 4 * (size_t)((fslots + 31) / 32);
+        cnt = o; o += 48 * 4;
+        ctl = o; o += 8 * 4;
+        slot_fs = o; o += 2 * (size_t)slots;
+        bins = o; o += 2 * (size_t)2 * NB * slots;
+        total = (o + 15) & ~(size_t)15;
+    }
+};
+
+// One iteration of phase PH for one slot, out of line so that every phase gets a register allocation of its own
+// (inlined into one kernel, the instances share a 128-register budget and spill ~1 KB per thread). The state
+// is unpacked straight from shared memory -- loads of words the phase never reads are dead code -- and only the
+// words the phase may modify (LsDirty<PH>) are written back. Returns the walker's new phase.
 template <int PH, bool AP>
-__device__ __noinline__ int lpf_wave_phase(uint32_t* st, int sl, LPt* pt, LRec* rec, int n, int cap_e, uint32_t* err_out) {
-    LFrame f; f.pt = pt; f.rec = rec; f.n = n; f.cap_e = cap_e;
+__device__ __noinline__ int lpf_wave_phase(uint32_t* st, int sl, LPt* pt, LRec* rec, LMeta* m, int n, int cap_e) {
+    LFrame f; f.pt = pt; f.rec = rec; f.m = m; f.n = n; f.cap_e = cap_e;
     LState s;
     uint32_t* mine = st + sl;
     ls_unpack(s, [&](int w) { return mine[w * LPF_MAX_SLOTS]; });
     lpf_step_t<PH, AP>(f, s);
     ls_writeback<PH>(s, [&](int w, uint32_t v) { mine[w * LPF_MAX_SLOTS] = v; });
-    if (s.phase == LP_DONE) *err_out = s.err;
+    // errors (never on contract input): the scheduler records them for the frame and gives the subtree up after a hard one
+    return s.err ? (s.phase | 16) : s.phase;
+}
+// A walker came back with error bits (they are in its packed state): record them for the frame; after a hard error (pool
+// exhausted, ring inconsistency) give the subtree up -- the frame still completes, its merges above are skipped.
+// One out-of-line copy for all phases.
+__device__ __noinline__ int lpf_wave_error(uint32_t* st, int sl, LMeta* m, int n, int cap_e) {
+    LFrame f; f.pt = nullptr; f.rec = nullptr; f.m = m; f.n = n; f.cap_e = cap_e;
+    LState s;
+    uint32_t* mine = st + sl;
+    ls_unpack(s, [&](int w) { return mine[w * LPF_MAX_SLOTS]; });
+    if (s.phase >= LP_DONE || !(s.err & (GT_ERR_POOL | GT_ERR_RING))) { atomicOr(&m->err, s.err); return s.phase; }
+    lp_abort(f, s);
+    ls_pack(s, [&](int w, uint32_t v) { mine[w * LPF_MAX_SLOTS] = v; });
     return s.phase;
 }
 
-// Phase-sorted ("wavefront") scheduler. A block keeps SLOTS frames in flight; their packed states live in
-// shared memory (word-major: st[w * SLOTS + slot]) and every slot is filed in the bin of its phase. Every round
-// the warps take tickets for chunks of up to 32 slots that are in the SAME phase, run that phase's straight-line
-// step for them and file each slot under its new phase for the next round (double-buffered bins): no divergence
-// between lanes, 64 dependent-load chains in flight per warp. A slot whose frame is finished goes to the
-// "needs a frame" bin and takes the next frame of the batch from a global counter.
+// frame slots of a block (what a frame's walkers share lives there): a bit mask of free ones
+__device__ __forceinline__ int lpf_fs_pop(uint32_t* mask, int words) {
+    for (int w = 0; w < words; ++w) {
+        uint32_t m = *(volatile uint32_t*)&mask[w];
+        while (m) {
+            const uint32_t bit = m & (0u - m);
+            const uint32_t old = atomicAnd(&mask[w], ~bit);
+            if (old & bit) return w * 32 + __ffs(bit) - 1;
+            m = old & ~bit;
+        }
+    }
+    return -1;
+}
+
+// A chunk of free slots admits `nadm` frames: lane a < nadm takes a frame slot and the next frame of the batch that passed
+// the pre-pass, then lanes a * 2^K ... a * 2^K + 2^kk - 1 start the walkers of its subtrees. Returns the lane's new phase.
+__device__ __noinline__ int lpf_admit(const LpfParams& p, uint32_t* st, LMeta* meta, int* fs_frame, int* fs_n, uint32_t* fs_mask, int FSW,
+                                      u16* slot_fs, int* ctl, int nadm, bool live, int sl, int lane) {
+    const int K = p.split;
+    int fs = -1, kk = 0;
+    if (lane < nadm) {
+        fs = lpf_fs_pop(fs_mask, FSW);
+        if (fs >= 0) {
+            for (;;) {
+                const int fr = (int)atomicAdd(p.counter, 1u);
+                if (fr >= p.nframes) { ctl[0] = 1; atomicOr(&fs_mask[fs >> 5], 1u << (fs & 31)); fs = -1; break; }
+                const int n = p.ws.n[fr];
+                if (p.ws.st[fr] != 0 || n < 2) continue;          // rejected by the pre-pass: the area kernel reports it
+                fs_frame[fs] = fr; fs_n[fs] = n;
+                meta[fs].bump = 0; meta[fs].err = 0; meta[fs].ready = 0;
+                kk = lp_split_level(n, K);
+                break;
+            }
+        }
+    }
+    __syncwarp();
+    const int a = lane >> K, k = lane & ((1 << K) - 1);
+    const int fs_a = __shfl_sync(0xffffffffu, fs, a), kk_a = __shfl_sync(0xffffffffu, kk, a);
+    if (!(live && a < nadm && fs_a >= 0 && k < (1 << kk_a))) return LP_DONE;      // (kk < K: a frame with too few points for 2^K subtrees)
+    LFrame f; f.pt = nullptr; f.rec = nullptr; f.m = meta + fs_a; f.n = fs_n[fs_a]; f.cap_e = p.ws.cap_e;
+    LState s = {};
+    lp_begin(f, s, kk_a, k);
+    ls_pack(s, [&](int w, uint32_t v) { st[w * LPF_MAX_SLOTS + sl] = v; });
+    slot_fs[sl] = (u16)fs_a;
+    return s.phase;
+}
+
+// Phase-sorted ("wavefront") scheduler. A block keeps up to SLOTS walkers in flight; their packed states live in
+// shared memory (word-major: st[w * LPF_MAX_SLOTS + slot]) and every slot is filed in the bin of its phase. Every round
+// the warps take tickets for chunks of up to 32 slots that are in the SAME phase, run that phase's straight-line step
+// for them and file each slot under its new phase for the next round (double-buffered bins, one barrier per round): no
+// divergence between lanes, 64 dependent-load chains in flight per warp. A retired walker's slot goes to the "free"
+// bin; a chunk of free slots admits as many whole frames as it can start all subtree walkers of.
 template <int THREADS, bool AP>
 __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p, const int SLOTS) {
     extern __shared__ __align__(16) unsigned char lsm[];
-    constexpr int NB = LP_DONE + 1;                                        // one bin per phase + one for slots that need a frame
-    uint32_t* st = reinterpret_cast<uint32_t*>(lsm);                       // [LS_WORDS][LPF_MAX_SLOTS]
-    int* slot_fr = reinterpret_cast<int*>(st + (size_t)LS_WORDS * LPF_MAX_SLOTS);  // [SLOTS] frame of the slot
-    u16* slot_n = reinterpret_cast<u16*>(slot_fr + SLOTS);                 // [SLOTS] its point count
-    u16* bins = slot_n + SLOTS;                                            // [2][NB][SLOTS] slots of each phase, this round / next round
-    int* cnt = reinterpret_cast<int*>(bins + 2 * (size_t)NB * SLOTS);      // [3][16] slots per bin: this round / next round / being cleared
-    int* ctl = cnt + 48;                                                   // [0] batch exhausted, [1..3] chunk tickets (same rotation)
+    constexpr int NB = LP_DONE + 1;                                        // one bin per phase + one for free slots
+    const int FS = p.fslots, FSW = (FS + 31) / 32;
+    const LpfSmem L(SLOTS, FS);
+    uint32_t* st = reinterpret_cast<uint32_t*>(lsm + L.st);                // [LS_WORDS][LPF_MAX_SLOTS]
+    LMeta* meta = reinterpret_cast<LMeta*>(lsm + L.meta);                  // [FS] what a frame's walkers share
+    int* fs_frame = reinterpret_cast<int*>(lsm + L.fs_frame);              // [FS] frame of the batch
+    int* fs_n = reinterpret_cast<int*>(lsm + L.fs_n);                      // [FS] its point count
+    uint32_t* fs_mask = reinterpret_cast<uint32_t*>(lsm + L.fs_mask);      // free frame slots
+    u16* slot_fs = reinterpret_cast<u16*>(lsm + L.slot_fs);                // [SLOTS] frame slot of the walker
+    u16* bins = reinterpret_cast<u16*>(lsm + L.bins);                      // [2][NB][SLOTS] slots of each phase, this round / next round
+    int* cnt = reinterpret_cast<int*>(lsm + L.cnt);                        // [3][16] slots per bin: this round / next round / being cleared
+    int* ctl = reinterpret_cast<int*>(lsm + L.ctl);                        // [0] batch exhausted, [1..3] chunk tickets (same rotation)
     const int tid = threadIdx.x, lane = tid & 31;
+    const int K = p.split;
 
     if (tid < 48) cnt[tid] = 0;
-    if (tid < 4) ctl[tid] = 0;
+    if (tid < 8) ctl[tid] = 0;
+    for (int w = tid; w < FSW; w += THREADS) fs_mask[w] = (w * 32 + 32 <= FS) ? 0xffffffffu : ((1u << (FS - w * 32)) - 1u);
     __syncthreads();
-    // every slot starts in the "needs a frame" bin
+    // every slot starts in the free bin
     for (int sl = tid; sl < SLOTS; sl += THREADS) bins[(size_t)LP_DONE * SLOTS + sl] = (u16)sl;
     if (tid == 0) cnt[LP_DONE] = SLOTS;
     __syncthreads();
@@ -96,16 +192,16 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
         constexpr unsigned ORDER = (unsigned)LP_INS | (unsigned)LP_SCAN << 4 | (unsigned)LP_C << 8 | (unsigned)LP_TAN << 12 | (unsigned)LP_V << 16
                                  | (unsigned)LP_LEAF << 20 | (unsigned)LP_TINIT << 24 | (unsigned)LP_DONE << 28;
         const int qbin = (int)((ORDER >> (4 * (lane & 7))) & 15u);
-        int myc = lane < NB ? c_now[qbin] : 0;
-        if (qbin == LP_DONE && exhausted) myc = 0;                        // nothing left to fetch: empty slots stay empty
+        int myc = (lane < NB && qbin < NB) ? c_now[qbin] : 0;
+        if (qbin == LP_DONE && exhausted) myc = 0;                        // nothing left to start: free slots stay free
         int incl = (myc + 31) >> 5;
 #pragma unroll
         for (int o = 1; o < 8; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }   // (lanes >= 8 hold 0)
         const int first_chunk = incl - ((myc + 31) >> 5);
         const int nchunks = __shfl_sync(0xffffffffu, incl, 7);
-        if (nchunks == 0) break;                                          // nothing in flight and nothing left to fetch
+        if (nchunks == 0) break;                                          // no walker in flight and nothing left to start
 #ifdef GT_PHASE_TIMING
-        if (p.dbg && tid == 0 && blockIdx.x == 0) atomicAdd(p.dbg + 26 + min(max(nchunks - 16, 0), 4), 1ull);      // rounds with <= 16, 17, 18, 19, >= 20 chunks
+        if (p.dbg && tid == 0) { int lv = 0; for (int q = 0; q < LP_DONE; ++q) lv += c_now[q]; atomicAdd(p.dbg + 27, (unsigned long long)lv); atomicAdd(p.dbg + 28, 1ull); }
 #endif
         // ---- one iteration for every live slot: a warp takes the next chunk of <= 32 slots that share a phase and files
         // every slot under its new phase for the next round
@@ -118,51 +214,49 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
             const int bin = (int)((ORDER >> (4 * q)) & 15u);
             const int idx = (c - __shfl_sync(0xffffffffu, first_chunk, q)) * 32 + lane;
             const int nph = __shfl_sync(0xffffffffu, myc, q);
-            if (idx < nph) {
-                const int sl = bin_now[(size_t)bin * SLOTS + idx];
-                int next = LP_DONE;
-                if (bin == LP_DONE) {
-                    // the slot's frame is finished (or it never had one): take the next frame of the batch that passed the pre-pass
-                    for (;;) {
-                        const int fr = (int)atomicAdd(p.counter, 1u);
-                        if (fr >= p.nframes) { ctl[0] = 1; break; }
-                        if (p.ws.st[fr] != 0) continue;
-                        LFrame f = lpf_frame(p.ws, fr);
-                        if (f.n < 2) continue;
-                        LState s = {};
-                        lp_begin(f, s);
-                        if (s.phase == LP_DONE) continue;
-                        ls_pack(s, [&](int w, uint32_t v) { st[w * LPF_MAX_SLOTS + sl] = v; });
-                        slot_fr[sl] = fr; slot_n[sl] = (u16)f.n;
-                        next = s.phase;
-                        break;
-                    }
-                } else {
-                    const int fr = slot_fr[sl];
-                    LPt* fpt = p.ws.pt + (size_t)fr * p.ws.cap; LRec* frec = p.ws.rec + (size_t)fr * 2 * (size_t)p.ws.cap_e;
-                    const int fn = slot_n[sl], fce = p.ws.cap_e;
-                    uint32_t* eo = p.ws.err + fr;
+            const bool live = idx < nph;
+            const int sl = live ? bin_now[(size_t)bin * SLOTS + idx] : 0;
+            int next = LP_DONE;
+            if (bin == LP_DONE) {
+                // free slots (lanes 0 .. na-1 of the chunk): start as many whole frames as there are slots for all of a
+                // frame's 2^K subtree walkers (out of line: it runs for a few chunks per frame, the loop around it all the time)
+                const int na = __popc(__ballot_sync(0xffffffffu, live));
+                if ((na >> K) > 0) next = lpf_admit(p, st, meta, fs_frame, fs_n, fs_mask, FSW, slot_fs, ctl, na >> K, live, sl, lane);
+            } else if (live) {
+                const int fs = slot_fs[sl];
+                const int fr = fs_frame[fs];
+                LPt* fpt = p.ws.pt + (size_t)fr * p.ws.cap; LRec* frec = p.ws.rec + (size_t)fr * 2 * (size_t)p.ws.cap_e;
+                LMeta* fm = meta + fs;
+                const int fn = fs_n[fs], fce = p.ws.cap_e;
 #ifdef GT_PHASE_TIMING
-                    const long long tk0 = clock64();
+                const long long tk0 = clock64();
 #endif
-                    switch (bin) {                                        // every lane of the chunk is in this phase
-                    case LP_LEAF: next = lpf_wave_phase<LP_LEAF, AP>(st, sl, fpt, frec, fn, fce, eo); break;
-                    case LP_TINIT: next = lpf_wave_phase<LP_TINIT, AP>(st, sl, fpt, frec, fn, fce, eo); break;
-                    case LP_TAN: next = lpf_wave_phase<LP_TAN, AP>(st, sl, fpt, frec, fn, fce, eo); break;
-                    case LP_INS: next = lpf_wave_phase<LP_INS, AP>(st, sl, fpt, frec, fn, fce, eo); break;
-                    case LP_SCAN: next = lpf_wave_phase<LP_SCAN, AP>(st, sl, fpt, frec, fn, fce, eo); break;
-                    case LP_V: next = lpf_wave_phase<LP_V, AP>(st, sl, fpt, frec, fn, fce, eo); break;
-                    default: next = lpf_wave_phase<LP_C, AP>(st, sl, fpt, frec, fn, fce, eo); break;
-                    }
-#ifdef GT_PHASE_TIMING
-                    if (p.dbg) {
-                        const long long tk1 = clock64(); const unsigned am = __activemask();
-                        if (lane == __ffs(am) - 1) { atomicAdd(p.dbg + 3 * bin, (unsigned long long)(tk1 - tk0)); atomicAdd(p.dbg + 3 * bin + 1, 1ull); atomicAdd(p.dbg + 3 * bin + 2, (unsigned long long)__popc(am)); }
-                    }
-#endif
+                switch (bin) {                                            // every lane of the chunk is in this phase
+                case LP_LEAF: next = lpf_wave_phase<LP_LEAF, AP>(st, sl, fpt, frec, fm, fn, fce); break;
+                case LP_TINIT: next = lpf_wave_phase<LP_TINIT, AP>(st, sl, fpt, frec, fm, fn, fce); break;
+                case LP_TAN: next = lpf_wave_phase<LP_TAN, AP>(st, sl, fpt, frec, fm, fn, fce); break;
+                case LP_INS: next = lpf_wave_phase<LP_INS, AP>(st, sl, fpt, frec, fm, fn, fce); break;
+                case LP_SCAN: next = lpf_wave_phase<LP_SCAN, AP>(st, sl, fpt, frec, fm, fn, fce); break;
+                case LP_V: next = lpf_wave_phase<LP_V, AP>(st, sl, fpt, frec, fm, fn, fce); break;
+                default: next = lpf_wave_phase<LP_C, AP>(st, sl, fpt, frec, fm, fn, fce); break;
                 }
-                bin_next[(size_t)next * SLOTS + atomicAdd(&c_next[next], 1)] = (u16)sl;
+                if (next & 16) next = lpf_wave_error(st, sl, fm, fn, fce);
+#ifdef GT_PHASE_TIMING
+                if (p.dbg) {
+                    const long long tk1 = clock64(); const unsigned am = __activemask();
+                    if (lane == __ffs(am) - 1) { atomicAdd(p.dbg + 3 * bin, (unsigned long long)(tk1 - tk0)); atomicAdd(p.dbg + 3 * bin + 1, 1ull); atomicAdd(p.dbg + 3 * bin + 2, (unsigned long long)__popc(am)); }
+                }
+#endif
+                if (next == LP_ROOT) {
+                    // the frame's triangulation is complete (every other walker of it has retired): publish its error bits
+                    // for the area kernel and free the frame slot
+                    p.ws.err[fr] = *(volatile uint32_t*)&fm->err;
+                    __threadfence_block();
+                    atomicOr(&fs_mask[fs >> 5], 1u << (fs & 31));
+                    next = LP_DONE;
+                }
             }
+            if (live) bin_next[(size_t)next * SLOTS + atomicAdd(&c_next[next], 1)] = (u16)sl;
             if (nchunks <= THREADS / 32) break;                            // every chunk had a warp of its own
             if (lane == 0) c = atomicAdd(ticket, 1) + THREADS / 32;
             c = __shfl_sync(0xffffffffu, c, 0);
@@ -170,7 +264,7 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
 #ifdef GT_PHASE_TIMING
         const long long tb0 = clock64();
         __syncthreads();
-        if (p.dbg && lane == 0) { atomicAdd(p.dbg + 24, (unsigned long long)(clock64() - tb0)); atomicAdd(p.dbg + 25, 1ull); }
+        if (p.dbg && lane == 0) { atomicAdd(p.dbg + 30, (unsigned long long)(clock64() - tb0)); atomicAdd(p.dbg + 31, 1ull); }
 #else
         __syncthreads();
 #endif

@@ -30,6 +30,20 @@
 
 namespace gt {
 
+// The predicate filters of the walker phases: inlined at their 15 call sites (default), or ONE out-of-line copy of each
+// (-DGT_LPF_PRED_OL=1: 10 KB less hot code and shorter chunks, but the rounds got longer: 324 ms instead of 308 ms per
+// 100k frames, measured with the merged insert / scan phase).
+#ifndef GT_LPF_PRED_OL
+#define GT_LPF_PRED_OL 0
+#endif
+#if GT_LPF_PRED_OL
+template <bool AP> GT_NOINLINE int lp_orient2d(double ax, double ay, double bx, double by, double cx, double cy) { return orient2d_sign<AP>(ax, ay, bx, by, cx, cy); }
+template <bool AP> GT_NOINLINE int lp_incircle(double ax, double ay, double bx, double by, double cx, double cy, double dx, double dy) { return incircle_sign<AP>(ax, ay, bx, by, cx, cy, dx, dy); }
+#else
+template <bool AP> GT_INLINE int lp_orient2d(double ax, double ay, double bx, double by, double cx, double cy) { return orient2d_sign<AP>(ax, ay, bx, by, cx, cy); }
+template <bool AP> GT_INLINE int lp_incircle(double ax, double ay, double bx, double by, double cx, double cy, double dx, double dy) { return incircle_sign<AP>(ax, ay, bx, by, cx, cy, dx, dy); }
+#endif
+
 struct LRec { u16 dst, nxt, prv, pad; };                 // one half-edge
 struct LPair { LRec a, b; };                             // a = the half-edge asked for, b = its twin
 
@@ -38,14 +52,27 @@ struct LPair { LRec a, b; };                             // a = the half-edge as
 // by scattered sector reads from HBM).
 struct alignas(32) LPt { double x, y, z; u16 head, perm; uint32_t pad; };
 
+// What the walkers of one frame share (shared memory on the device): the edge pool's bump pointer, sticky error
+// bits, and one "arrived" bit per inner node of the top of the recursion tree (heap numbering: node (d, k) is bit
+// (1 << d) + k) -- the first child to arrive at a node sets the bit and retires, the second one runs the merge.
+struct LMeta { uint32_t bump, err, ready; };
+
 // Frame storage in global memory.
 struct LFrame {
     LPt* pt;        // [n] sorted by (x, y)
     LRec* rec;      // [2 * cap_e]
+    LMeta* m;
     int n;
     int cap_e;
 };
 
+#if defined(__CUDA_ARCH__)
+GT_INLINE void lf_fence() { __threadfence_block(); }
+GT_INLINE uint32_t lf_fetch_or(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
+#else
+GT_INLINE void lf_fence() {}
+GT_INLINE uint32_t lf_fetch_or(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p = o | v; return o; }
+#endif
 #if defined(__CUDA_ARCH__)
 GT_INLINE LPair lf_pair(const LFrame& f, int h) {
     const uint4 v = *reinterpret_cast<const uint4*>(f.rec + (h & ~1));
@@ -77,14 +104,16 @@ GT_INLINE void lf_set_rec(const LFrame& f, int h, int dst, int nxt, int prv) {
     LRec r; r.dst = (u16)dst; r.nxt = (u16)nxt; r.prv = (u16)prv; r.pad = 0; f.rec[h] = r;
 }
 
-enum LPhase : int { LP_LEAF = 0, LP_TINIT, LP_TAN, LP_INS, LP_SCAN, LP_V, LP_C, LP_DONE, LP_NPHASE };
+// LP_DONE: the walker retired (its slot is free); LP_ROOT: the walker finished the root merge -- the frame is complete.
+enum LPhase : int { LP_LEAF = 0, LP_TINIT, LP_TAN, LP_INS, LP_SCAN, LP_V, LP_C, LP_DONE, LP_ROOT, LP_NPHASE };
 
-// Per-frame state between iterations.
+// Per-walker state between iterations. A walker owns the subtree rooted at depth `top` that contains its current
+// node (d, k): it walks that subtree in post-order, and when the root is done it arrives at the parent (lp_finish_node).
 struct LState {
     int phase;
     int d, k, ia, ib;                 // current node of the recursion tree
     uint32_t err;
-    int bump, free_head;              // private edge pool
+    int top, free_head;               // depth of the owned subtree's root; private list of freed edges
     int first_edge, vR, vL, actR, actL, scan0, scan1;
     int adv;                          // the node is finished: the next LP_TINIT iteration first advances the tree cursor
     // tangents: upper (ux, uy) walks with (uHl, uHr), coordinates in pr1 / pl1; lower (li, ri) with (lHl, lHr), coordinates in
@@ -120,7 +149,7 @@ GT_INLINE void ls_pack(const LState& s, Put&& put) {
     put(0, (uint32_t)s.phase | ((uint32_t)s.d << 4) | ((uint32_t)s.k << 8) | ((s.err & 15u) << 20) | ((uint32_t)s.first_edge << 24) | ((uint32_t)s.vR << 25) |
            ((uint32_t)s.vL << 26) | ((uint32_t)s.actR << 27) | ((uint32_t)s.actL << 28) | ((uint32_t)s.scan0 << 29) | ((uint32_t)s.scan1 << 30) | ((uint32_t)s.adv << 31));
     put(1, (uint32_t)s.ia | ((uint32_t)s.ib << 12) | ((uint32_t)s.uSub << 24) | ((uint32_t)s.lSub << 26));
-    put(2, LS_P2(s.bump, s.free_head)); put(3, LS_P2(s.ux, s.uy)); put(4, LS_P2(s.uHl, s.uHr)); put(5, LS_P2(s.li, s.ri));
+    put(2, LS_P2(s.top, s.free_head)); put(3, LS_P2(s.ux, s.uy)); put(4, LS_P2(s.uHl, s.uHr)); put(5, LS_P2(s.li, s.ri));
     put(6, LS_P2(s.lHl, s.lHr)); put(7, LS_P2(s.e, s.headL)); put(8, LS_P2(s.headR, s.hr1)); put(9, LS_P2(s.r1, s.hr2));
     put(10, LS_P2(s.t1_prv, s.t1_nxt)); put(11, LS_P2(s.hdR1, s.hl1)); put(12, LS_P2(s.l1, s.hl2)); put(13, LS_P2(s.u1_prv, s.u1_nxt));
     put(14, LS_P2(s.hdL1, s.h0)); put(15, LS_P2(s.at0, s.nx0)); put(16, LS_P2(s.at1, s.nx1)); put(17, LS_P2(s.cur0, s.hd0));
@@ -137,7 +166,7 @@ GT_INLINE void ls_unpack(LState& s, Get&& get) {
     s.vL = (w >> 26) & 1; s.actR = (w >> 27) & 1; s.actL = (w >> 28) & 1; s.scan0 = (w >> 29) & 1; s.scan1 = (w >> 30) & 1; s.adv = (w >> 31) & 1;
     w = get(1); s.ia = w & 0xfff; s.ib = (w >> 12) & 0xfff; s.uSub = (w >> 24) & 3; s.lSub = (w >> 26) & 3;
 #define LS_U2(i, a, b) w = get(i); a = (int)(w & 0xffff); b = (int)(w >> 16)
-    LS_U2(2, s.bump, s.free_head); LS_U2(3, s.ux, s.uy); LS_U2(4, s.uHl, s.uHr); LS_U2(5, s.li, s.ri);
+    LS_U2(2, s.top, s.free_head); LS_U2(3, s.ux, s.uy); LS_U2(4, s.uHl, s.uHr); LS_U2(5, s.li, s.ri);
     LS_U2(6, s.lHl, s.lHr); LS_U2(7, s.e, s.headL); LS_U2(8, s.headR, s.hr1); LS_U2(9, s.r1, s.hr2);
     LS_U2(10, s.t1_prv, s.t1_nxt); LS_U2(11, s.hdR1, s.hl1); LS_U2(12, s.l1, s.hl2); LS_U2(13, s.u1_prv, s.u1_nxt);
     LS_U2(14, s.hdL1, s.h0); LS_U2(15, s.at0, s.nx0); LS_U2(16, s.at1, s.nx1); LS_U2(17, s.cur0, s.hd0);
@@ -161,8 +190,8 @@ constexpr unsigned long long LS_M_FINISH = LS_M_NODE | LS_W(7) | LS_W(8) | LS_W(
 // also queued a new edge or finished one: more fields move).
 template <int PH> struct LsDirty { static constexpr unsigned long long mask = ~0ull, tail = 0; };
 template <> struct LsDirty<LP_LEAF> { static constexpr unsigned long long mask = LS_W(2) | LS_M_NODE, tail = 0; };
-template <> struct LsDirty<LP_TINIT> { static constexpr unsigned long long mask = LS_W(0) | LS_W(1) | LS_W(3) | LS_W(4) | LS_W(5) | LS_W(6) | LS_W(7) | LS_W(8) | LS_PT(21) | LS_PT(25) | LS_PT(29) | LS_PT(33), tail = 0; };
-template <> struct LsDirty<LP_TAN> { static constexpr unsigned long long mask = LS_W(0) | LS_W(1) | LS_W(3) | LS_W(4) | LS_W(5) | LS_W(6) | LS_W(7) | LS_W(8) | LS_PT(21) | LS_PT(25) | LS_PT(29) | LS_PT(33), tail = LS_M_QUEUE; };
+template <> struct LsDirty<LP_TINIT> { static constexpr unsigned long long mask = LS_W(0) | LS_W(1) | LS_W(2) | LS_W(9) | LS_W(3) | LS_W(4) | LS_W(5) | LS_W(6) | LS_W(7) | LS_W(8) | LS_PT(21) | LS_PT(25) | LS_PT(29) | LS_PT(33), tail = 0; };
+template <> struct LsDirty<LP_TAN> { static constexpr unsigned long long mask = LS_W(0) | LS_W(1) | LS_W(9) | LS_W(3) | LS_W(4) | LS_W(5) | LS_W(6) | LS_W(7) | LS_W(8) | LS_PT(21) | LS_PT(25) | LS_PT(29) | LS_PT(33), tail = LS_M_QUEUE; };
 template <> struct LsDirty<LP_INS> { static constexpr unsigned long long mask = LS_W(0) | LS_W(7) | LS_W(8) | LS_W(17) | LS_W(18) | LS_W(19) | LS_W(20), tail = LS_M_FINISH; };
 template <> struct LsDirty<LP_SCAN> { static constexpr unsigned long long mask = LsDirty<LP_INS>::mask, tail = LS_M_FINISH; };
 template <> struct LsDirty<LP_V> { static constexpr unsigned long long mask = LS_W(0) | LS_W(9) | LS_W(10) | LS_W(11) | LS_W(12) | LS_W(13) | LS_W(14) | LS_PT(29) | LS_PT(33), tail = LS_M_QUEUE; };
@@ -181,29 +210,75 @@ GT_INLINE void ls_writeback(const LState& s, Put&& put) {
 // ---------------------------------------------------------------- helpers
 GT_INLINE void lp_free(const LFrame& f, LState& s, int e) { lf_set_nxt(f, 2 * e, s.free_head); s.free_head = e; }
 
-// Advance the post-order cursor over the reference's recursion tree to the next node and enter its first phase.
-GT_INLINE void lp_next_node(const LFrame& f, LState& s) {
-    int d = s.d, k = s.k;
-    if (d < 0) { d = 0; k = 0; }                           // first call: descend from the root
-    else if (d == 0) { s.phase = LP_DONE; return; }
-    else if (k & 1) {                                      // finished a right child: its parent is next, and it is a merge
-        d -= 1; k >>= 1;
-        int ia, ib; tree_node(f.n, d, k, &ia, &ib);
-        s.d = d; s.k = k; s.ia = ia; s.ib = ib;
-        s.phase = LP_TINIT;
-        return;
-    } else k += 1;                                         // finished a left child: leftmost leaf of the sibling subtree
-    int ia, ib;
-    tree_node(f.n, d, k, &ia, &ib);
-    while (ib - ia >= 3) { ib = (ia + ib) / 2; d += 1; k <<= 1; }      // left children down to the leaf (:535-538)
-    s.d = d; s.k = k; s.ia = ia; s.ib = ib;
-    s.phase = (ib - ia < 1) ? LP_DONE : LP_LEAF;
+// The current node (s.d, s.k) is complete: advance the post-order cursor over the reference's recursion tree inside the
+// walker's subtree, or -- at the subtree's root -- arrive at the parent: the first of the two siblings to arrive sets the
+// parent's bit and retires, the second one finds it set and owns the parent from then on (its merge reads both children's
+// rings: the fences order them behind the bit). The root of the tree ends in LP_ROOT. A frame with an error set skips the
+// merges above it (their inputs may be incomplete) but still arrives, so that the frame always completes.
+// (One out-of-line copy, scalars in and a packed word out: the phases that end a node share it, and the walker kernel's
+// code has to stay small -- it already misses the instruction cache.)
+// result: phase | d << 4 | k << 8 | top << 20 | ia << 24 | ib << 36
+GT_NOINLINE uint64_t lp_finish_core(int n, LMeta* m, int d, int k, int top) {
+    int ia = 0, ib = 0, phase;
+    for (;;) {
+        if (d == top) {
+            if (d == 0) { phase = LP_ROOT; break; }
+            const uint32_t bit = 1u << ((1 << (d - 1)) + (k >> 1));
+            lf_fence();
+            const uint32_t old = lf_fetch_or(&m->ready, bit);
+            if (!(old & bit)) { phase = LP_DONE; break; }
+            lf_fence();
+            d -= 1; k >>= 1; top = d;
+            if (*(volatile uint32_t*)&m->err) continue;
+        } else if (k & 1) {                                  // finished a right child: its parent is next, and it is a merge
+            d -= 1; k >>= 1;
+        } else {                                             // finished a left child: leftmost leaf of the sibling subtree
+            k += 1;
+            tree_node(n, d, k, &ia, &ib);
+            while (ib - ia >= 3) { ib = (ia + ib) / 2; d += 1; k <<= 1; }      // left children down to the leaf (:535-538)
+            phase = LP_LEAF;
+            break;
+        }
+        tree_node(n, d, k, &ia, &ib);
+        phase = LP_TINIT;
+        break;
+    }
+    return (uint64_t)phase | (uint64_t)d << 4 | (uint64_t)k << 8 | (uint64_t)top << 20 | (uint64_t)ia << 24 | (uint64_t)ib << 36;
+}
+GT_INLINE void lp_finish_node(const LFrame& f, LState& s) {
+    const uint64_t r = lp_finish_core(f.n, f.m, s.d, s.k, s.top);
+    s.phase = (int)(r & 15u); s.d = (int)((r >> 4) & 15u); s.k = (int)((r >> 8) & 0xfffu); s.top = (int)((r >> 20) & 15u);
+    s.ia = (int)((r >> 24) & 0xfffu); s.ib = (int)((r >> 36) & 0xfffu);
 }
 
-GT_INLINE void lp_begin(const LFrame& f, LState& s) {
-    s.d = -1; s.k = 0; s.err = 0; s.bump = 0; s.free_head = GT_NIL; s.adv = 0;
+// Start a walker on the subtree rooted at node (top_d, top_k); the node must exist and hold at least two points.
+GT_INLINE void lp_begin(const LFrame& f, LState& s, int top_d, int top_k) {
+    s.err = 0; s.free_head = GT_NIL; s.adv = 0; s.top = top_d;
     s.first_edge = s.vR = s.vL = s.actR = s.actL = s.scan0 = s.scan1 = 0; s.uSub = s.lSub = 0;
-    lp_next_node(f, s);
+    int d = top_d, k = top_k, ia, ib;
+    tree_node(f.n, d, k, &ia, &ib);
+    while (ib - ia >= 3) { ib = (ia + ib) / 2; d += 1; k <<= 1; }
+    s.d = d; s.k = k; s.ia = ia; s.ib = ib;
+    s.phase = LP_LEAF;
+}
+// Give up the walker's subtree after a hard error (pool exhausted, ring inconsistency): record it for the frame and arrive
+// at the parent as if the subtree were complete.
+GT_INLINE void lp_abort(const LFrame& f, LState& s) {
+    atomic_or_u32(&f.m->err, s.err);
+    s.k >>= (s.d - s.top); s.d = s.top;
+    lp_finish_node(f, s);
+}
+// Deepest level at which every node of an n-point tree exists and holds at least two points, capped at `want`
+// (a frame is split into 2^level subtrees that start in parallel).
+GT_INLINE int lp_split_level(int n, int want) {
+    int kk = 0;
+    while (kk < want && (n >> (kk + 2)) >= 1) ++kk;          // n >= 2^(kk+1) after the increment
+    return kk;
+}
+// One edge from the frame's shared pool (-1: exhausted).
+GT_INLINE int lp_pool_take(const LFrame& f) {
+    const uint32_t e = atomic_add_u32(&f.m->bump, 1u);
+    return e < (uint32_t)f.cap_e ? (int)e : -1;
 }
 
 // A new cross edge li -> ri: take an edge from the pool and queue its two ring insertions.
@@ -213,8 +288,7 @@ GT_INLINE void lp_begin(const LFrame& f, LState& s) {
 GT_INLINE void lp_new_edge(const LFrame& f, LState& s, const LPair& spec, bool freed, int prev_head) {
     int ne;
     if (s.free_head != (int)GT_NIL) { ne = s.free_head; s.free_head = freed ? prev_head : (int)spec.a.nxt; }
-    else if (s.bump >= f.cap_e) { s.err |= GT_ERR_POOL; s.phase = LP_DONE; return; }
-    else ne = s.bump++;
+    else { ne = lp_pool_take(f); if (ne < 0) { s.err |= GT_ERR_POOL; return; } }
     s.h0 = 2 * ne; s.scan0 = s.scan1 = 0;
     s.phase = LP_INS;
 }
@@ -226,7 +300,7 @@ GT_INLINE void lp_decide(const LFrame& f, LState& s, const LPair& spec, bool fre
     if (s.vR) {
         go_left = false;
         if (s.vL && s.r1 != s.l1) {
-            int sg = incircle_sign<AP>(s.pli.x, s.pli.y, s.pri.x, s.pri.y, s.pr1.x, s.pr1.y, s.pl1.x, s.pl1.y);
+            int sg = lp_incircle<AP>(s.pli.x, s.pli.y, s.pri.x, s.pri.y, s.pr1.x, s.pr1.y, s.pl1.x, s.pl1.y);
             if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
             go_left = sg > 0;
         }
@@ -275,29 +349,29 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
         const int a = s.ia, b = s.ia + 1, c = s.ib;
         const Pt pa = lf_pt(f, a), pb = lf_pt(f, b), pc = lf_pt(f, c);
         int sg = 0;
-        if (c != b) { sg = orient2d_sign<AP>(pa.x, pa.y, pb.x, pb.y, pc.x, pc.y); if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; } }
+        if (c != b) { sg = lp_orient2d<AP>(pa.x, pa.y, pb.x, pb.y, pc.x, pc.y); if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; } }
         auto take = [&](LPair sp) -> int {
             if (s.free_head != (int)GT_NIL) { const int e = s.free_head; s.free_head = sp.a.nxt; return e; }
-            if (s.bump >= f.cap_e) { s.err |= GT_ERR_POOL; return -1; }
-            return s.bump++;
+            const int e = lp_pool_take(f);
+            if (e < 0) s.err |= GT_ERR_POOL;
+            return e;
         };
         const int e0 = take(spec);
-        if (e0 < 0) { s.phase = LP_DONE; return; }
+        if (e0 < 0) return;
         const int h0 = 2 * e0;
         if (c == b) {                                     // two points: one edge, two single-entry rings
             lf_set_rec(f, h0, b, h0, h0); lf_set_rec(f, h0 ^ 1, a, h0 ^ 1, h0 ^ 1);
             lf_set_head(f, a, h0); lf_set_head(f, b, h0 ^ 1);
-            lp_next_node(f, s); return;
-        }
+        } else {
         // further edges: the free list's links are read directly here (leaves only)
         const int e1 = take(s.free_head != (int)GT_NIL ? lf_pair(f, 2 * s.free_head) : zero);
-        if (e1 < 0) { s.phase = LP_DONE; return; }
+        if (e1 < 0) return;
         const int h1 = 2 * e1;
         const bool s1 = sg > 0, s2 = sg < 0;              // ccw(a,b,c), ccw(a,c,b)
         int h2 = -1;
         if (s1 || s2) {
             const int e2 = take(s.free_head != (int)GT_NIL ? lf_pair(f, 2 * s.free_head) : zero);
-            if (e2 < 0) { s.phase = LP_DONE; return; }
+            if (e2 < 0) return;
             h2 = 2 * e2;
         }
         // ring of b: {b->a, b->c}; "first" moves to b->c iff c is right of the ray b->a (= ccw(a,b,c))
@@ -314,12 +388,13 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
             lf_set_rec(f, h1 ^ 1, b, h2 ^ 1, h2 ^ 1); lf_set_rec(f, h2 ^ 1, a, h1 ^ 1, h1 ^ 1);
             lf_set_head(f, c, s1 ? (h2 ^ 1) : (h1 ^ 1));
         }
-        lp_next_node(f, s);
+        }
+        lp_finish_node(f, s);
         return;
     }
 
     if (PH == LP_TINIT) {
-        if (s.adv) { s.adv = 0; lp_next_node(f, s); if (s.phase != LP_TINIT) return; }      // (see lp_finish_connect)
+        if (s.adv) { s.adv = 0; lp_finish_node(f, s); if (s.phase != LP_TINIT) return; }      // (see lp_finish_connect)
         // both tangents start at the rightmost vertex of the left half and the leftmost of the right half
         const int x = (s.ia + s.ib) / 2, y = x + 1;
         int hdx = 0, hdy = 0;
@@ -328,12 +403,16 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
         s.ux = x; s.uy = y; s.uHl = hdx; s.uHr = py.a.prv; s.pr1 = qx; s.pl1 = qy; s.uSub = 0;      // upper: x -> first(x), y -> pred(y, first(y))   (:378-381)
         s.li = x; s.ri = y; s.lHl = px.a.prv; s.lHr = hdy; s.pli = qx; s.pri = qy; s.lSub = 0;      // lower: x -> pred(x, first(x)), y -> first(y)   (:342-345)
         s.headL = hdx; s.headR = hdy;
+        s.hr2 = 0;                                         // (tangent phase: iteration guard, see LP_TAN)
         s.phase = LP_TAN;
         return;
     }
 
     if (PH == LP_TAN) {
         // chain 0: upper tangent (uct :373-406), leftOf(p, x, y) = ccw(p, x, y); chain 1: lower (lct :337-370), rightOf(p, x, y) = ccw(p, y, x)
+        // a hull walk visits every vertex at most once per side: more iterations than that means inconsistent predicate
+        // answers (only after a range error) -- stop instead of circling forever
+        if (++s.hr2 > 2 * f.n + 16) { s.err |= GT_ERR_RING; return; }
         const bool a0 = s.uSub < 2, a1 = s.lSub < 2;
         LPair p0 = zero, p1 = zero; Pt c0, c1; c0.x = c0.y = 0.0; c1 = c0; int hd1c = 0;
         if (a0) p0 = lf_pair(f, s.uSub == 0 ? s.uHr : s.uHl);
@@ -341,14 +420,14 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
         if (a0) c0 = lf_pt(f, p0.a.dst);
         if (a1) c1 = lf_pth(f, p1.a.dst, hd1c);
         if (a0) {
-            int sg = orient2d_sign<AP>(c0.x, c0.y, s.pr1.x, s.pr1.y, s.pl1.x, s.pl1.y);
+            int sg = lp_orient2d<AP>(c0.x, c0.y, s.pr1.x, s.pr1.y, s.pl1.x, s.pl1.y);
             if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
             if (s.uSub == 0) { if (sg > 0) { s.uHr = p0.b.prv; s.uy = p0.a.dst; s.pl1 = c0; } else s.uSub = 1; }        // pred(rfast, y)
             else if (sg > 0) { s.uHl = p0.b.nxt; s.ux = p0.a.dst; s.pr1 = c0; s.uSub = 0; }                           // succ(lfast, x)
             else s.uSub = 2;
         }
         if (a1) {
-            int sg = orient2d_sign<AP>(c1.x, c1.y, s.pri.x, s.pri.y, s.pli.x, s.pli.y);
+            int sg = lp_orient2d<AP>(c1.x, c1.y, s.pri.x, s.pri.y, s.pli.x, s.pli.y);
             if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
             if (s.lSub == 0) { if (sg > 0) { s.lHr = p1.b.nxt; s.ri = p1.a.dst; s.pri = c1; s.headR = hd1c; } else s.lSub = 1; }   // succ(rfast, y)
             else if (sg > 0) { s.lHl = p1.b.prv; s.li = p1.a.dst; s.pli = c1; s.headL = hd1c; s.lSub = 0; }                   // pred(lfast, x)
@@ -363,19 +442,22 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
     }
 
     if (PH == LP_INS || PH == LP_SCAN) {
+        // (the two phases were also tried as one function with a run-time switch -- 5 KB less code, one chunk per round
+        // less: 308 ms instead of 277 ms per 100k frames, the scans ride along at the insertion's three load levels)
+        constexpr bool ins = PH == LP_INS;
         // endpoint 0: parent li, in ri, half-edge h0; endpoint 1: parent ri, in li, half-edge h0^1.
         // rightOf(in, parent, q) = ccw(in, q, parent)  (insertNode :216-224)
-        const bool a0 = (PH == LP_INS) || s.scan0, a1 = (PH == LP_INS) || s.scan1;
+        const bool a0 = ins || s.scan0, a1 = ins || s.scan1;
         LPair p0 = zero, p1 = zero; Pt c0, c1; c0.x = c0.y = 0.0; c1 = c0;
-        if (a0) p0 = lf_pair(f, PH == LP_INS ? s.headL : s.cur0);
-        if (a1) p1 = lf_pair(f, PH == LP_INS ? s.headR : s.cur1);
+        if (a0) p0 = lf_pair(f, ins ? s.headL : s.cur0);
+        if (a1) p1 = lf_pair(f, ins ? s.headR : s.cur1);
         if (a0) c0 = lf_pt(f, p0.a.dst);
         if (a1) c1 = lf_pt(f, p1.a.dst);
         // LP_INS also fetches the ring's LAST entry (prv of first): when the new neighbour is right of "first" the
         // reference's clockwise scan starts there (:217-219) and usually stops there, so its first test is taken in
-        // the same iteration and LP_SCAN only runs when that test holds too
+        // the same iteration and the scan only goes on when that test holds too
         LPair q0 = zero, q1 = zero; Pt d0 = c0, d1 = c1;
-        const bool m0 = PH == LP_INS && (int)p0.a.prv != s.headL, m1 = PH == LP_INS && (int)p1.a.prv != s.headR;
+        const bool m0 = ins && (int)p0.a.prv != s.headL, m1 = ins && (int)p1.a.prv != s.headR;
         if (m0) q0 = lf_pair(f, p0.a.prv);
         if (m1) q1 = lf_pair(f, p1.a.prv);
         if (m0) d0 = lf_pt(f, q0.a.dst);
@@ -384,13 +466,13 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
         // per endpoint and both orientation filters evaluated for every lane keep the step short and its lanes together
         // (it is the longest step of a round: the round lasts as long as this).
         if (a0) {
-            int sg = orient2d_sign<AP>(s.pri.x, s.pri.y, c0.x, c0.y, s.pli.x, s.pli.y);
+            int sg = lp_orient2d<AP>(s.pri.x, s.pri.y, c0.x, c0.y, s.pli.x, s.pli.y);
             if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
             const bool res = sg > 0;
             bool place = true, newhead = false; int at, nx, hd;
-            if (PH == LP_INS) {
+            if (ins) {
                 hd = s.headL; const int last = p0.a.prv;
-                int sl = m0 ? orient2d_sign<AP>(s.pri.x, s.pri.y, d0.x, d0.y, s.pli.x, s.pli.y) : 0;   // right of "last" too?
+                int sl = m0 ? lp_orient2d<AP>(s.pri.x, s.pri.y, d0.x, d0.y, s.pli.x, s.pli.y) : 0;   // right of "last" too?
                 if (sl == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sl = 0; }
                 at = last; nx = hd;                                                  // after "last" (= before "first")
                 if (!res) { if (!s.first_edge) { at = s.at0; nx = s.nx0; } }          // not right of "first": the slot known from the merge
@@ -410,14 +492,14 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
             if (place) lp_place(f, s, 0, s.li, s.ri, s.h0, at, nx, newhead, hd);
         }
         if (a1) {
-            int sg = orient2d_sign<AP>(s.pli.x, s.pli.y, c1.x, c1.y, s.pri.x, s.pri.y);
+            int sg = lp_orient2d<AP>(s.pli.x, s.pli.y, c1.x, c1.y, s.pri.x, s.pri.y);
             if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
             const bool res = sg > 0;
             const int h1 = s.h0 ^ 1;
             bool place = true, newhead = false; int at, nx, hd;
-            if (PH == LP_INS) {
+            if (ins) {
                 hd = s.headR; const int last = p1.a.prv;
-                int sl = m1 ? orient2d_sign<AP>(s.pli.x, s.pli.y, d1.x, d1.y, s.pri.x, s.pri.y) : 0;
+                int sl = m1 ? lp_orient2d<AP>(s.pli.x, s.pli.y, d1.x, d1.y, s.pri.x, s.pri.y) : 0;
                 if (sl == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sl = 0; }
                 at = last; nx = hd;
                 if (!res) { if (!s.first_edge) { at = s.at1; nx = s.nx1; } }
@@ -447,8 +529,8 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
         int hdr = 0, hdl = 0;
         const Pt c0 = lf_pth(f, p0.a.dst, hdr), c1 = lf_pth(f, p1.a.dst, hdl);
         s.hdR1 = hdr; s.hdL1 = hdl;
-        int sg0 = orient2d_sign<AP>(c0.x, c0.y, s.pli.x, s.pli.y, s.pri.x, s.pri.y);
-        int sg1 = orient2d_sign<AP>(c1.x, c1.y, s.pli.x, s.pli.y, s.pri.x, s.pri.y);
+        int sg0 = lp_orient2d<AP>(c0.x, c0.y, s.pli.x, s.pli.y, s.pri.x, s.pri.y);
+        int sg1 = lp_orient2d<AP>(c1.x, c1.y, s.pli.x, s.pli.y, s.pri.x, s.pri.y);
         if (sg0 == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg0 = 0; }
         if (sg1 == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg1 = 0; }
         s.r1 = p0.a.dst; s.pr1 = c0; s.hr2 = p0.a.prv; s.t1_prv = p0.b.prv; s.t1_nxt = p0.b.nxt;
@@ -471,7 +553,7 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
             const int r2 = p0.a.dst;
             int sg = 0;
             if (!(r2 == s.li || r2 == s.ri || r2 == s.r1))                          // a repeated point: exactly 0
-                sg = incircle_sign<AP>(s.pr1.x, s.pr1.y, s.pli.x, s.pli.y, s.pri.x, s.pri.y, c0.x, c0.y);
+                sg = lp_incircle<AP>(s.pr1.x, s.pr1.y, s.pli.x, s.pli.y, s.pri.x, s.pri.y, c0.x, c0.y);
             if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
             if (sg > 0) {
                 // ri's ring loses hr1 (its next is the cross edge), r1's ring loses the twin
@@ -488,7 +570,7 @@ GT_INLINE void lpf_step_t(const LFrame& f, LState& s) {
             const int l2 = p1.a.dst;
             int sg = 0;
             if (!(l2 == s.li || l2 == s.ri || l2 == s.l1))
-                sg = incircle_sign<AP>(s.pli.x, s.pli.y, s.pri.x, s.pri.y, s.pl1.x, s.pl1.y, c1.x, c1.y);
+                sg = lp_incircle<AP>(s.pli.x, s.pli.y, s.pri.x, s.pri.y, s.pl1.x, s.pl1.y, c1.x, c1.y);
             if (sg == GT_RANGE_ERR) { s.err |= GT_ERR_RANGE; sg = 0; }
             if (sg > 0) {
                 const int h = s.hl1, tw = h ^ 1;

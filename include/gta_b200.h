@@ -44,11 +44,11 @@ extern "C" {
 #define GTA_B200_E_ARG          (-3)
 #define GTA_B200_E_TOO_LARGE    (-4)   /* max_points does not fit the shared-memory kernel */
 
-/* Two kernels serve the batched calls: launches of at least `min_frames` frames run the lane-per-frame pipeline
- * (pre-pass, phase-sorted state machine, area kernel: highest throughput, needs tens of thousands of frames in
- * flight), smaller ones the fused one-CTA-per-frame kernel (lowest latency). Results are identical triangulations;
- * areas agree to rounding of the summation tree. Default 32768 (environment GTA_B200_LPF overrides); 0 = never,
- * 1 = always, negative = restore the default. Returns the previous value. */
+/* Two kernels serve the batched calls: launches of at least `min_frames` frames run the throughput path (pre-pass,
+ * a persistent kernel whose phase-sorted scheduler steps (frame, subtree) walkers, area kernel: highest throughput), smaller ones the fused one-CTA-per-frame kernel (lowest latency). Results are identical
+ * triangulations; areas agree to rounding of the summation tree. Environment GTA_B200_LPF overrides the default;
+ * 0 = never, 1 = always, negative = restore the default. Returns the previous value. */
+#define GTA_B200_DEFAULT_BATCH_THRESHOLD 2048
 int gta_b200_set_batch_threshold(int min_frames);
 
 /* Largest max_points the batched shared-memory kernel accepts on this device. */
@@ -119,6 +119,11 @@ int gta_b200_tessellate_frames(const double *const *x, const double *box9, int n
  * (a single triangulation does not shard). */
 int gta_b200_triangulate_large(const double *points, int npoints, int device,
                                int *tri, int tri_cap, int *ntri, int *status);
+/* Same path for one large frame of atoms xyz [natoms][3] WITHOUT correction points: also sums the 3-D triangle areas
+ * (*area3) and, with GTA_B200_2D, the projected ones (*area2). delaunay_surface_area / delaunay_tessellate use it for
+ * frames beyond gta_b200_max_points(). GTA_B200_CORRECT is refused (GTA_B200_E_TOO_LARGE). */
+int gta_b200_surface_area_large(const double *xyz, int natoms, unsigned flags, int device,
+                                double *area3, double *area2, int *ntri, int *status);
 /* device milliseconds (sort + all levels + enumeration, without the host copies) of the last call on this thread */
 double gta_b200_large_last_ms(void);
 
@@ -126,6 +131,11 @@ double gta_b200_large_last_ms(void);
  * (CUDA events on the launching streams), and the number of kernel launches the last batch / device call made. */
 double gta_b200_last_kernel_ms(void);
 int gta_b200_last_launches(void);
+/* Per-kernel device time of the throughput path (pre-pass, walker kernel, area kernel) on `device` (< 0: the current
+ * one): _reset forgets the launches seen so far; _ms waits for the launches made since and adds up each kernel's
+ * duration, measured with CUDA events on the launching streams (at most 64 launches are kept). Any pointer may be NULL. */
+int gta_b200_stage_reset(int device);
+int gta_b200_stage_ms(int device, double *prepass_ms, double *walk_ms, double *area_ms, int *launches);
 
 /* Predicate self-test hooks (device evaluation of the exact-sign predicates on arrays):
  * pts [n][6] -> sign [n] for orient2d, pts [n][8] for incircle; host pointers. */

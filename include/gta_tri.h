@@ -65,6 +65,10 @@ void free_tri_area(struct tri_area *areas);
 /* Per-frame GTA_B200_ST_* bits of the last delaunay_tessellate call on this thread ([nframes], owned by
  * the library, valid until the next call); NULL if none. Frames with a nonzero status have area = NaN. */
 const int *gta_last_frame_status(void);
+/* GTA_B200_* return code (include/gta_b200.h; 0 = ok) behind the last tessellate_area / delaunay_tessellate /
+ * delaunay_surface_area / dtriangulate call on this thread: the kept entry points are void, as in the reference. After a
+ * failure every area of that call is NaN (never 0) and the cause is in gta_b200_last_error(). */
+int gta_last_call_rc(void);
 
 /* stdout + gta.log tee of the reference's gkut_log (extern/gkut/src/gkut_log.c:21-50) */
 void init_log(const char *logfile, int argc, char *argv[]);

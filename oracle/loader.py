@@ -108,6 +108,15 @@ class RefOracle(_TessOracle):
         if wrap:
             self.lib.ref_set_dump.argtypes = [C.c_char_p]
 
+    def print_areas(self, fname, area, area2d, areabox, natoms):
+        """The reference's own print_areas (src/gta_tri.c:448-473) -> fname."""
+        area = np.ascontiguousarray(area, dtype=np.float64); areabox = np.ascontiguousarray(areabox, dtype=np.float64)
+        a2 = None if area2d is None else np.ascontiguousarray(area2d, dtype=np.float64)
+        f = self.lib.ref_print_areas
+        f.restype = None
+        f.argtypes = [C.c_char_p, _dp, _dp, _dp, C.c_int, C.c_int]
+        f(str(fname).encode(), _p(area), _p(a2), _p(areabox), len(area), int(natoms))
+
     def counters(self, reset=True):
         out = (C.c_longlong * 4)()
         self.lib.ref_counters(out, int(reset))

@@ -144,3 +144,11 @@ void ref_incircle_batch(const double *p, int n, double *out) {
     dtinit();
     for (int i = 0; i < n; ++i) out[i] = incircle((double *)p + 8 * i, (double *)p + 8 * i + 2, (double *)p + 8 * i + 4, (double *)p + 8 * i + 6);
 }
+
+/* The reference's own print_areas (src/gta_tri.c:448-473) on caller-supplied arrays: the byte-exact .dat table
+ * the product's print_areas is compared with. area2d may be NULL (then the 4-column table). */
+void ref_print_areas(const char *fname, const real *area, const real *area2d, const real *areabox, int nframes, int natoms) {
+    struct tri_area a;
+    a.area = (real *)area; a.area2D = (real *)area2d; a.area2Dbox = (real *)areabox; a.natoms = natoms; a.nframes = nframes;
+    print_areas(fname, &a);
+}

@@ -6,13 +6,14 @@ ref = RefOracle()
 emu = C.CDLL('/root/repo/tests/emu/libemu_dt.so')
 dp = C.POINTER(C.c_double); ip = C.POINTER(C.c_int)
 emu.emu_triangulate.argtypes = [dp, C.c_int, ip]; emu.emu_triangulate.restype = C.c_int
-emu.emu_triangulate_lpf.argtypes = [dp, C.c_int, ip, C.c_void_p]; emu.emu_triangulate_lpf.restype = C.c_int
+emu.emu_triangulate_lpf2.argtypes = [dp, C.c_int, C.c_int, C.c_uint, ip, C.c_void_p]; emu.emu_triangulate_lpf2.restype = C.c_int
 import os
 LPF = os.environ.get('LPF') == '1'
 def emu_tri(p):
     p = np.ascontiguousarray(p, dtype=np.float64); n = len(p)
     out = np.empty(3*2*n, dtype=np.int32)
-    nt = emu.emu_triangulate_lpf(p.ctypes.data_as(dp), n, out.ctypes.data_as(ip), None) if LPF else emu.emu_triangulate(p.ctypes.data_as(dp), n, out.ctypes.data_as(ip))
+    # LPF=1: the walker state machine, split into 2^K subtrees (K random) stepped in a random interleaving
+    nt = emu.emu_triangulate_lpf2(p.ctypes.data_as(dp), n, int(rng.integers(0, 6)), int(rng.integers(0, 1 << 30)), out.ctypes.data_as(ip), None) if LPF else emu.emu_triangulate(p.ctypes.data_as(dp), n, out.ctypes.data_as(ip))
     return nt if nt < 0 else out[:3*nt].reshape(-1,3).copy()
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 3000

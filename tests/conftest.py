@@ -60,13 +60,15 @@ def emu():
     d = os.path.join(ROOT, "tests", "emu")
     so = os.path.join(d, "libemu_dt.so")
     srcs = [os.path.join(d, "emu_dt.cpp")] + [os.path.join(ROOT, "g_tessla_b200", "csrc", f)
-                                               for f in ("dt_core.cuh", "gt_predicates.cuh")]
+                                               for f in ("dt_core.cuh", "gt_predicates.cuh", "lpf_core.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++",
                                "-o", so, srcs[0]])
     L = C.CDLL(so)
     dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
     L.emu_triangulate.argtypes = [dp, C.c_int, ip]
+    L.emu_triangulate_lpf2.argtypes = [dp, C.c_int, C.c_int, C.c_uint, ip, C.POINTER(C.c_long)]
+    L.emu_exact_stats.argtypes = [C.POINTER(C.c_long)]
     for n in ("emu_orient2d_signs", "emu_incircle_signs", "emu_orient2d_exact", "emu_incircle_exact"):
         getattr(L, n).argtypes = [dp, C.c_int, ip]
 
@@ -77,6 +79,22 @@ def emu():
             nt = L.emu_triangulate(p.ctypes.data_as(dp), len(p), out.ctypes.data_as(ip))
             assert nt >= 0, "emu error %d" % nt
             return out[:3 * nt].reshape(-1, 3).copy()
+
+        def triangulate_walkers(self, p, level, seed):
+            """The walker state machine of the throughput kernel: 2^level subtree walkers stepped one iteration at a time
+            in a pseudo-random interleaving (seed != 0). Returns (triangles, [iterations, pool edges, longest, root])."""
+            p = np.ascontiguousarray(p, dtype=np.float64)
+            out = np.empty(3 * 2 * max(len(p), 1), dtype=np.int32)
+            st = (C.c_long * 4)()
+            nt = L.emu_triangulate_lpf2(p.ctypes.data_as(dp), len(p), int(level), int(seed), out.ctypes.data_as(ip), st)
+            assert nt >= 0, "emu error %d" % nt
+            return out[:3 * nt].reshape(-1, 3).copy(), list(st)
+
+        def exact_stats(self):
+            """[orient2d 1/2/4 words, incircle 1/2/4 words, orient2d total, incircle total] since the last call."""
+            st = (C.c_long * 8)()
+            L.emu_exact_stats(st)
+            return list(st)
 
         def signs(self, fn, p, w):
             p = np.ascontiguousarray(p, dtype=np.float64).reshape(-1, w)

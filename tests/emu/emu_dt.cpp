@@ -86,9 +86,13 @@ int emu_triangulate(const double* points, int n, int* tri_out) {
     return nt;
 }
 
-// Same input/output as emu_triangulate, through the per-lane state machine (lpf_core.cuh), one lane.
-// iters_out (nullable) receives the number of iterations the lane needed.
-int emu_triangulate_lpf(const double* points, int n, int* tri_out, long* iters_out) {
+// Same input/output as emu_triangulate, through the walker state machine (lpf_core.cuh) the way the GPU scheduler drives
+// it: the frame is split into 2^level subtrees (level = min(want_level, what n allows)), every subtree gets a walker,
+// walkers are stepped ONE ITERATION AT A TIME IN A PSEUDO-RANDOM INTERLEAVING (seed), they share the frame's edge pool
+// and arrive at their parents through the "ready" bits. The result must not depend on the interleaving.
+// stats_out (nullable): [0] iterations in total, [1] edges taken from the pool, [2] longest walker (iterations),
+// [3] iterations of the walker that finished the root.
+int emu_triangulate_lpf2(const double* points, int n, int want_level, unsigned seed, int* tri_out, long* stats_out) {
     using namespace gt;
     if (n < 2) return -1000;
     std::vector<int> perm(n);
@@ -114,30 +118,51 @@ int emu_triangulate_lpf(const double* points, int n, int* tri_out, long* iters_o
     for (int i = 0; i < n; ++i) { pt[i].x = points[2 * perm[i]]; pt[i].y = points[2 * perm[i] + 1]; pt[i].z = 0.0; pt[i].head = (u16)GT_NIL; pt[i].perm = (u16)perm[i]; pt[i].pad = 0; }
     const int cap_e = 3 * n + 64;
     std::vector<LRec> rec(2 * cap_e);
-    LFrame f; f.pt = pt.data(); f.rec = rec.data(); f.n = n; f.cap_e = cap_e;
-    LState s; memset(&s, 0, sizeof s); lp_begin(f, s);
-    long iters = 0;
-    bool more = s.phase != LP_DONE;
-    uint32_t w[LS_WORDS];
-    ls_pack(s, [&](int i, uint32_t v) { w[i] = v; });
-    while (more) {
+    LMeta meta = {0, 0, 0};
+    LFrame f; f.pt = pt.data(); f.rec = rec.data(); f.m = &meta; f.n = n; f.cap_e = cap_e;
+    const int level = lp_split_level(n, want_level);
+    struct Walker { uint32_t w[LS_WORDS]; long iters; };
+    std::vector<Walker> live(1 << level);
+    for (int k = 0; k < (1 << level); ++k) {
+        LState s; memset(&s, 0, sizeof s); lp_begin(f, s, level, k);
+        ls_pack(s, [&](int i, uint32_t v) { live[k].w[i] = v; });
+        live[k].iters = 0;
+    }
+    long iters = 0, longest = 0, root_iters = 0;
+    unsigned long long rng = seed * 6364136223846793005ull + 1442695040888963407ull;
+    bool root_done = false;
+    while (!live.empty()) {
+        rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+        const size_t pick = seed ? (size_t)((rng >> 33) % live.size()) : 0;     // seed 0: one walker at a time, to its end
+        Walker& wk = live[pick];
         // the GPU scheduler keeps only the packed form between iterations and rewrites only the words the
         // phase may modify (LsDirty): go through exactly that here
         LState t; memset(&t, 0xee, sizeof t);
-        ls_unpack(t, [&](int i) { return w[i]; });
-        auto put = [&](int i, uint32_t v) { w[i] = v; };
-        switch (t.phase) {
+        ls_unpack(t, [&](int i) { return wk.w[i]; });
+        auto put = [&](int i, uint32_t v) { wk.w[i] = v; };
+        const int ph = t.phase;
+        switch (ph) {
 #define EMU_PH(P) case P: lpf_step_t<P>(f, t); ls_writeback<P>(t, put); break;
         EMU_PH(LP_LEAF) EMU_PH(LP_TINIT) EMU_PH(LP_TAN) EMU_PH(LP_INS) EMU_PH(LP_SCAN) EMU_PH(LP_V) EMU_PH(LP_C)
 #undef EMU_PH
         default: return -4000;
         }
-        s = t;
-        more = t.phase != LP_DONE;
+        ++wk.iters;
+        if (t.err) {                                       // as gta_lpf.cuh::lpf_wave_error does, from the packed state
+            ls_unpack(t, [&](int i) { return wk.w[i]; });
+            if (t.phase >= LP_DONE || !(t.err & (GT_ERR_POOL | GT_ERR_RING))) meta.err |= t.err;
+            else { lp_abort(f, t); ls_pack(t, put); }
+        }
         if (++iters > 400L * n + 10000) return -3000;
+        if (t.phase == LP_DONE || t.phase == LP_ROOT) {
+            if (wk.iters > longest) longest = wk.iters;
+            if (t.phase == LP_ROOT) { if (root_done) return -5000; root_done = true; root_iters = wk.iters; }
+            live[pick] = live.back(); live.pop_back();
+        }
     }
-    if (iters_out) *iters_out = iters;
-    if (s.err) return -(int)s.err;
+    if (!root_done) return -6000;
+    if (stats_out) { stats_out[0] = iters; stats_out[1] = (long)meta.bump; stats_out[2] = longest; stats_out[3] = root_iters; }
+    if (meta.err) return -(int)meta.err;
     int nt = 0;
     for (int i = 0; i < n; ++i)
         lf_vertex_triangles(f, i, [&](int n1, int n2) {
@@ -145,6 +170,13 @@ int emu_triangulate_lpf(const double* points, int n, int* tri_out, long* iters_o
             ++nt;
         });
     return nt;
+}
+// one walker for the whole frame (the tree in post-order)
+int emu_triangulate_lpf(const double* points, int n, int* tri_out, long* iters_out) {
+    long st[4] = {0, 0, 0, 0};
+    const int r = emu_triangulate_lpf2(points, n, 0, 0u, tri_out, st);
+    if (iters_out) *iters_out = st[0];
+    return r;
 }
 
 void emu_orient2d_signs(const double* p, int n, int* out) {
