@@ -10,7 +10,9 @@ A "step" is one pass of the hot path over the whole 100k-frame batch of every ra
          timed with CUDA events on the launching stream, max over ranks.
   e2e    the same metric through the reference-facing C-ABI with HOST buffers
          (gta_b200_tessellate_batch: pinned staging, H2D, kernel, D2H all inside the timed region).
-  roofline / cpu_baseline: see DESIGN.md §5.
+  strong_100k  BASELINE configs[2] literally: ONE 100,000-frame trajectory sharded over the GPUs (strong scaling).
+  kept_api     the drop-in entry point's engine (gta_b200_tessellate_frames) on per-frame heap blocks, all GPUs, from rank 0.
+  roofline / cpu_baseline: see DESIGN.md §5 (kernel times and the FP64 peak are measured by the run that prints them).
 
 --impl reference times the reference's own OpenMP CPU path (oracle/_ref when it was compiled, else
 the oracle port) on this box's host cores, on bounded samples of the same workload.
@@ -36,17 +38,35 @@ FLAGS = 1                      # GTA_CORRECT
 TRI_PER_FRAME = 2178           # 2(n-1) - h with n = 1156, h = 132 (reference delaunay_tri.c:608)
 ALG_BYTES_PER_FRAME = NATOMS * 24 + 72 + 16      # coordinates + box in, 2 reals out
 ALG_FLOP_PER_FRAME = 203.6e3                      # SURVEY.md §8d implementation-independent lower bound
-FP64_PEAK_TFLOPS_NOMINAL = 37.2                   # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz (not in MEASURED_PEAKS.json)
-# dram read+write per frame from ncu --set full captures (profiles/): the fused CTA-per-frame kernel (6,000 frames) and the
-# dominant kernel of the lane-per-frame pipeline, gt::lpf_wave_kernel, on one launch of 50,000 frames (76.0 GB read +
-# 21.7 GB written: the frames' workspaces live in HBM and 50,000 of them do not fit in L2)
-NCU_DRAM_BYTES_PER_FRAME_FUSED = 26254
-NCU_DRAM_BYTES_PER_FRAME_LPF = 1955000
-# share of the step's GPU time spent in gt::lpf_wave_kernel, from the ncu launch list of this command
-# (profiles/r1_launches_summary.txt; the rest: pre-pass 8.6 %, area kernel 4.4 %)
-LPF_WAVE_SHARE = 0.866
-LPF_MIN_FRAMES = 32768               # launches at least this large use the lane-per-frame pipeline (gta_b200_set_batch_threshold)
+FP64_PEAK_TFLOPS_NOMINAL = 37.2                   # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz (fallback if the DFMA micro-benchmark fails)
+STRONG_FRAMES = 100000                            # BASELINE.json configs[2]: ONE 100k-frame trajectory, sharded over the GPUs
+TRAFFIC_JSON = os.path.join("profiles", "r2_walk_traffic.json")   # written by profiles/ncu_keys.py --json from an ncu --set full capture
 WORKLOAD = "cfg3: 2,048-lipid bilayer leaflet, 1,024 atoms/frame, -corr -espace 0.8, 3-D area"
+
+
+def workload_config(frames_per_gpu):
+    """Identical in both arms (the native one and --impl reference), so that the driver's comparison sees one config."""
+    return {"workload": WORKLOAD, "frames_per_gpu_per_step": frames_per_gpu, "natoms": NATOMS, "points_per_frame": 1156,
+            "espace": ESPACE, "flags": "GTA_CORRECT", "headline": "weak scaling: every GPU tessellates its own frames_per_gpu_per_step frames; "
+            "the 100k-frame trajectory of BASELINE configs[2] sharded over the GPUs (strong scaling) is reported beside it as strong_100k"}
+
+
+def git_head():
+    try:
+        return subprocess.run(["git", "-C", ROOT, "rev-parse", "HEAD"], capture_output=True, text=True, timeout=10).stdout.strip()
+    except Exception:
+        return ""
+
+
+def kernel_sources_sha():
+    """Hash of the CUDA sources the captured kernel is built from: the traffic figure is stale when they change."""
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "g_tessla_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()
 
 
 def peaks():
@@ -164,7 +184,7 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "mtriangles_per_s": v * TRI_PER_FRAME / 1e6,
-            "config": {"workload": WORKLOAD, "frames_per_step": per_step, "natoms": NATOMS, "points_per_frame": 1156},
+            "config": workload_config(args.frames),
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -173,18 +193,22 @@ def run_reference(args):
 
 
 def run_native(args):
+    import ctypes as C
     import numpy as np
     import torch
     import g_tessla_b200 as g
+    from g_tessla_b200.dist import frame_range, gather_frames
 
     rank, local_rank, world = dist_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_group = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")          # host-side waits that must not put a spinning kernel on the GPUs
     L = g.lib()
     F = args.frames
     pk, pk_src = peaks()
@@ -193,56 +217,63 @@ def run_native(args):
     xyz_h = torch.empty(xyz_d.shape, dtype=torch.float64, pin_memory=True).copy_(xyz_d)
     box_h = torch.empty(box_d.shape, dtype=torch.float64, pin_memory=True).copy_(box_d)
     max_points = NATOMS + 4 + 4 * int(torch.floor(box_d[:, :2].max() / ESPACE).item())
-    T = g.Tessellator(F, NATOMS, max_points, ESPACE, FLAGS, device=str(dev))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident arm (value, roofline)
-    for _ in range(args.warmup):
-        T.run(xyz_d, box_d, 3)
-    barrier()
+    def resident_arm(nf, gather_total=None):
+        """nf of this rank's frames, already in HBM: (ms per step over the timed region, ms inside the library call, launches, Tessellator)"""
+        T = g.Tessellator(nf, NATOMS, max_points, ESPACE, FLAGS, device=str(dev))
+        x, bx = xyz_d[:nf], box_d[:nf]
+        for _ in range(args.warmup):
+            T.run(x, bx, 3)
+        barrier()
+        g.api.stage_ms(local_rank, reset=True)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches = 0
+        e0.record()
+        for a, b in ev:
+            a.record(); T.run(x, bx, 3); b.record()
+            launches += L.gta_b200_last_launches()
+            if world > 1:                                     # the path's only exchange: the final per-frame area gather
+                gather_frames(T.area, gather_total if gather_total else nf * world)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1), sum(a.elapsed_time(b) for a, b in ev) / args.steps, launches, T
+
+    def e2e_arm(nf):
+        """the same frames through the reference-facing C-ABI with HOST buffers: H2D, kernels, D2H inside the timed region"""
+        area = np.zeros(nf); areabox = np.zeros(nf); status = np.zeros(nf, dtype=np.int32)
+
+        def step():
+            rc = L.gta_b200_tessellate_batch(xyz_h.data_ptr(), 3, box_h.data_ptr(), 3, nf, NATOMS, ESPACE, FLAGS,
+                                             local_rank, args.streams, area.ctypes.data, None, areabox.ctypes.data,
+                                             status.ctypes.data, None, 0, None, None, 0, None)
+            if rc != 0:
+                raise SystemExit("gta_b200_tessellate_batch failed: " + L.gta_b200_last_error().decode())
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        t0 = time.perf_counter()
+        launches = 0
+        for _ in range(args.steps):
+            step()
+            launches += L.gta_b200_last_launches()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3, launches, area, status
+
+    # ---------------- weak arm (the headline): every rank its own F frames
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    gathered = [torch.empty_like(T.area) for _ in range(world)] if world > 1 else None
-    launches_dev = 0
-    for a, b in ev:
-        a.record(); T.run(xyz_d, box_d, 3); b.record()
-        launches_dev += L.gta_b200_last_launches()
-        if world > 1:
-            dist.all_gather(gathered, T.area)          # the path's only exchange: final per-frame area gather (0.8 MB per rank)
-    e1.record()
-    barrier()
-    total_ms = e0.elapsed_time(e1)
-    kern_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    total_ms, kern_ms, launches_dev, T = resident_arm(F)
+    stages = g.api.stage_ms(local_rank)
     status_bad = int((T.status != 0).sum().item())
     area_dev = T.area.cpu().numpy().copy()
-
-    # ---------------- end-to-end arm through the host C-ABI (pinned host buffers in, host results out)
-    area = np.zeros(F); areabox = np.zeros(F); status = np.zeros(F, dtype=np.int32)
-
-    def e2e_step():
-        rc = L.gta_b200_tessellate_batch(xyz_h.data_ptr(), 3, box_h.data_ptr(), 3, F, NATOMS, ESPACE, FLAGS,
-                                         local_rank, args.streams, area.ctypes.data, None, areabox.ctypes.data,
-                                         status.ctypes.data, None, 0, None, None, 0, None)
-        if rc != 0:
-            raise SystemExit("gta_b200_tessellate_batch failed: " + L.gta_b200_last_error().decode())
-    for _ in range(args.warmup):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    launches_e2e = 0
-    for _ in range(args.steps):
-        e2e_step()
-        launches_e2e += L.gta_b200_last_launches()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    e2e_ms, launches_e2e, area, status = e2e_arm(F)
     clk = clocks.stop() if rank == 0 else None
     if not np.allclose(area, area_dev, rtol=1e-12, atol=0) or status.any() or status_bad:
         st_dev = T.status.cpu().numpy()
@@ -250,60 +281,137 @@ def run_native(args):
                          "status(dev) %s status(host) %s, %d areas differ, first %s vs %s" % (
                              np.unique(st_dev, return_counts=True), np.unique(status, return_counts=True),
                              int((area != area_dev).sum()), area[:3], area_dev[:3]))
+    del T
 
-    times = torch.tensor([total_ms, e2e_s * 1e3, kern_ms], dtype=torch.float64, device=dev)
+    # ---------------- strong arm: ONE trajectory of STRONG_FRAMES frames, contiguous ranges per rank (BASELINE configs[2])
+    lo, hi = frame_range(args.strong_frames, rank, world)
+    nf_s = hi - lo
+    if world == 1 and nf_s == F:
+        s_total_ms, s_e2e_ms, s_launches = total_ms, e2e_ms, 0          # the same measurement
+    else:
+        s_total_ms, _, l1, Ts = resident_arm(nf_s, gather_total=args.strong_frames)
+        s_e2e_ms, l2, s_area, s_status = e2e_arm(nf_s)
+        if s_status.any() or not np.allclose(s_area, area_dev[:nf_s], rtol=1e-12, atol=0):
+            raise SystemExit("bench.py: strong-scaling arm disagrees with the weak arm on the same frames")
+        s_launches = l1 + l2
+        del Ts
+
+    times = torch.tensor([total_ms, e2e_ms, kern_ms, s_total_ms, s_e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, kern_ms = [float(x) for x in times.tolist()]
+    total_ms, e2e_ms, kern_ms, s_total_ms, s_e2e_ms = [float(x) for x in times.tolist()]
+
+    # ---------------- the drop-in entry point (delaunay_tessellate -> gta_b200_tessellate_frames) on every GPU of the box:
+    # rank 0 alone, per-frame heap blocks as read_traj leaves them (extern/gkut/src/gkut_io.c:37); the other ranks wait on the host
+    kept = None
+    if rank == 0:
+        kept = kept_api_arm(L, C, np, xyz_h, box_h, area_dev, world, args)
+    if world > 1:
+        dist.barrier(group=host_group)
 
     if rank == 0:
         frames_all = F * world * args.steps
         value = frames_all / (total_ms / 1e3)
         e2e_v = frames_all / (e2e_ms / 1e3)
-        lpf = F >= LPF_MIN_FRAMES
-        # the dominant kernel: one launch of the fused kernel per step, or `parts` launches of gt::lpf_wave_kernel (the
-        # library splits a batch evenly; 3 kernels per part), which take LPF_WAVE_SHARE of the pipeline's time
-        parts = max(1, launches_dev // args.steps // 3) if lpf else 1
-        dom_ms = kern_ms * (LPF_WAVE_SHARE if lpf else 1.0) / parts
-        frames_per_launch = F / parts
-        ach = ALG_BYTES_PER_FRAME * frames_per_launch / (dom_ms / 1e3) / 1e9    # GB/s of algorithmic bytes per launch
-        fl = ALG_FLOP_PER_FRAME * frames_per_launch / (dom_ms / 1e3) / 1e12
-        thr, smem, fps = (g.api.C.c_int(), g.api.C.c_size_t(), g.api.C.c_int())
-        L.gta_b200_launch_shape(max_points, NATOMS, g.api.C.byref(thr), g.api.C.byref(smem), g.api.C.byref(fps))
+        nl = max(1, stages["launches"])
+        walk_ms = stages["walk"] / nl                        # dominant kernel: gt::lpf_wave_kernel, per launch, measured in this run
+        frames_per_launch = F * args.steps / nl
+        ach = ALG_BYTES_PER_FRAME * frames_per_launch / (walk_ms / 1e3) / 1e9    # GB/s of algorithmic bytes per launch
+        stage_sum = max(1e-9, stages["prepass"] + stages["walk"] + stages["area"])
+        # ncu dram bytes per frame of that kernel: from the committed capture summary, flagged when the kernels changed since
+        traffic, traffic_meta = None, {"source": TRAFFIC_JSON, "stale": None}
+        try:
+            tj = json.load(open(os.path.join(ROOT, TRAFFIC_JSON)))
+            traffic = tj["dram_bytes_per_frame"] * frames_per_launch / 1e9
+            traffic_meta.update({"dram_bytes_per_frame": tj["dram_bytes_per_frame"], "captured_frames": tj.get("frames"),
+                                 "capture_git": tj.get("git"), "stale": tj.get("sources_sha") != kernel_sources_sha()})
+        except Exception as e:
+            traffic_meta["error"] = str(e)
+        fp64_peak = L.gta_b200_fp64_peak_tflops(local_rank)
+        fp64_src = "measured (DFMA micro-benchmark, gta_b200_fp64_peak_tflops)"
+        if not fp64_peak > 0:
+            fp64_peak, fp64_src = FP64_PEAK_TFLOPS_NOMINAL, "nominal"
+        fl = ALG_FLOP_PER_FRAME * value / world / 1e12
         line = {
             "metric": "tessellated frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "mtriangles_per_s": value * TRI_PER_FRAME / 1e6,
-            "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": F, "natoms": NATOMS, "points_per_frame": 1156,
-                       "l2": "inputs larger than L2 (%.2f GB of coordinates per step per GPU)" % (F * NATOMS * 24 / 1e9),
-                       "path": ("lane per frame: pre-pass + phase-sorted state machine (one lane = one frame, workspace in HBM) + area kernel"
-                                if lpf else "fused kernel, one CTA per frame in shared memory"),
-                       "fused_kernel_shape": {"threads_per_frame": thr.value, "smem_bytes_per_frame": smem.value, "frames_per_sm": fps.value},
-                       "parallelism": "frames sharded over %d GPU(s), no collective" % world},
+            "config": workload_config(F),
+            "run": {"l2": "inputs larger than L2 (%.2f GB of coordinates per step per GPU)" % (F * NATOMS * 24 / 1e9),
+                    "path": "throughput path: pre-pass (load, -corr, sort) + walker kernel (phase-sorted (frame, subtree) slots) + area kernel",
+                    "parallelism": "frames sharded over %d GPU(s), no collective on the data path (final per-frame area gather only)" % world,
+                    "generator": "device (torch CUDA generator), recipe of g_tessla_b200.synth.jittered_bilayer; seed 3 + 1000 * rank"},
             "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": F * (NATOMS * 24 + 24),
                     "d2h_bytes_per_step": F * (3 * 8 + 3 * 4), "timing": "host wall clock around the synchronous C-ABI call",
                     "streams": args.streams},
-            "gpu_launches": launches_dev + launches_e2e,
+            "strong_100k": {"frames_total": args.strong_frames, "frames_per_gpu": nf_s, "scaling": "strong",
+                            "value": args.strong_frames * args.steps / (s_total_ms / 1e3), "e2e": args.strong_frames * args.steps / (s_e2e_ms / 1e3),
+                            "unit": "frames/s", "ms_per_step": s_total_ms / args.steps,
+                            "note": "one 100k-frame trajectory, contiguous frame ranges per GPU (g_tessla_b200.dist.frame_range), final area gather inside the timed region"},
+            "kept_api": kept,
+            "gpu_launches": launches_dev + launches_e2e + s_launches + (kept or {}).get("launches", 0),
             "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                         "traffic": (NCU_DRAM_BYTES_PER_FRAME_LPF if lpf else NCU_DRAM_BYTES_PER_FRAME_FUSED) * frames_per_launch / 1e9,
-                         "traffic_unit": "GB per launch (ncu dram bytes per frame x frames per launch)",
-                         "peak_source": pk_src,
-                         "kernel": ("gt::lpf_wave_kernel<512,false> (%.1f%% of the step; pre-pass gt::tessellate_kernel<256,4,true> 8.6%%, gt::lpf_area_kernel 4.4%%)" % (100 * LPF_WAVE_SHARE)) if lpf else "gt::tessellate_kernel<128,3>",
-                         "launches_per_step": parts, "frames_per_launch": frames_per_launch,
-                         "kernel_ms_per_launch": dom_ms, "pipeline_ms_per_step": kern_ms, "alg_bytes_per_frame": ALG_BYTES_PER_FRAME,
-                         "note": "bound by the latency of dependent scattered 32-byte reads (two to three levels per iteration, L2 hit rate ~30 %); algorithmic bytes are 79x below the HBM traffic and the traffic is 12 % of HBM peak; see DESIGN.md section 5"},
-            "roofline_fp64": {"achieved": fl, "peak": FP64_PEAK_TFLOPS_NOMINAL, "unit": "TFLOP/s", "frac": fl / FP64_PEAK_TFLOPS_NOMINAL,
-                              "peak_source": "nominal", "alg_flop_per_frame": ALG_FLOP_PER_FRAME},
+                         "traffic": traffic, "traffic_unit": "GB per launch (ncu dram__bytes_read + dram__bytes_write per frame x frames per launch)",
+                         "traffic_meta": traffic_meta, "peak_source": pk_src,
+                         "kernel": "gt::lpf_wave_kernel<512,false>",
+                         "kernel_share_of_step": stages["walk"] / stage_sum,
+                         "stage_ms_per_launch": {"prepass": stages["prepass"] / nl, "walk": walk_ms, "area": stages["area"] / nl},
+                         "launches_per_step": nl / args.steps, "frames_per_launch": frames_per_launch,
+                         "kernel_ms_per_launch": walk_ms, "pipeline_ms_per_step": kern_ms, "alg_bytes_per_frame": ALG_BYTES_PER_FRAME,
+                         "timing": "CUDA events on the launching stream around each kernel, inside the library (gta_b200_stage_ms), over the timed steps",
+                         "note": "latency-bound pointer chasing: the frames' half-edge rings live in an HBM workspace; neither roof is the limiter (DESIGN.md section 5)"},
+            "roofline_fp64": {"achieved": fl, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fl / fp64_peak,
+                              "peak_source": fp64_src, "alg_flop_per_frame": ALG_FLOP_PER_FRAME},
             "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(xyz_h.numpy(), box_h.numpy(), area_dev, args)
+            if kept and line["cpu_baseline"].get("value"):
+                kept["vs_cpu"] = kept["frames_per_s"] / line["cpu_baseline"]["value"]
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def kept_api_arm(L, C, np, xyz_h, box_h, area_dev, ngpus, args):
+    """delaunay_tessellate's own data layout through the kept C entry point's engine: x[fr] = one heap block per frame,
+    box[fr] = 3x3 matrix, results into host arrays; ngpus devices driven from this one process (one host thread each)."""
+    F = xyz_h.shape[0]
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p; libc.malloc.argtypes = [C.c_size_t]; libc.free.argtypes = [C.c_void_p]
+    nbytes = NATOMS * 24
+    base = xyz_h.data_ptr()
+    ptrs = (C.c_void_p * F)()
+    for f in range(F):
+        p = libc.malloc(nbytes)
+        C.memmove(p, base + f * nbytes, nbytes)
+        ptrs[f] = p
+    box9 = np.zeros((F, 3, 3)); bh = box_h.numpy()
+    box9[:, 0, 0] = bh[:, 0]; box9[:, 1, 1] = bh[:, 1]; box9[:, 2, 2] = bh[:, 2]
+    area = np.zeros(F); areabox = np.zeros(F); status = np.zeros(F, dtype=np.int32)
+
+    def step():
+        rc = L.gta_b200_tessellate_frames(ptrs, box9.ctypes.data, F, NATOMS, ESPACE, FLAGS, ngpus, 0,
+                                          area.ctypes.data, None, areabox.ctypes.data, status.ctypes.data)
+        if rc != 0:
+            raise SystemExit("gta_b200_tessellate_frames failed: " + L.gta_b200_last_error().decode())
+    step()                                                     # warm-up: pinned staging buffers, workspaces on every device
+    reps = max(2, min(args.steps, 3))
+    t0 = time.perf_counter()
+    launches = 0
+    for _ in range(reps):
+        step()
+        launches += L.gta_b200_last_launches()
+    dt = time.perf_counter() - t0
+    for f in range(F):
+        libc.free(ptrs[f])
+    rel = float(np.max(np.abs(area - area_dev) / np.abs(area_dev)))
+    return {"entry": "gta_b200_tessellate_frames (engine of delaunay_tessellate), per-frame heap blocks", "frames": F, "ngpus": ngpus,
+            "frames_per_s": F * reps / dt, "ms_per_call": 1e3 * dt / reps, "launches": launches,
+            "max_rel_vs_device_arm": rel, "status_ok": bool(not status.any())}
 
 
 def cpu_baseline(xyz, box, area_gpu, args):
@@ -350,6 +458,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--frames", type=int, default=100000, help="frames per GPU per step")
+    ap.add_argument("--strong-frames", type=int, default=STRONG_FRAMES, help="frames of the ONE trajectory the strong-scaling arm shards over the GPUs")
     ap.add_argument("--streams", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-seconds-per-step", type=float, default=4.0)

@@ -59,6 +59,13 @@ def lib() -> C.CDLL:
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gta_b200_triangulate_large.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, _ip, _ip]
     L.gta_b200_large_last_ms.restype = C.c_double
+    L.gta_b200_fp64_peak_tflops.restype = C.c_double
+    L.gta_b200_fp64_peak_tflops.argtypes = [C.c_int]
+    L.gta_b200_stage_ms.argtypes = [C.c_int, _dp, _dp, _dp, _ip]
+    L.gta_b200_stage_reset.argtypes = [C.c_int]
+    L.gta_b200_tessellate_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_uint, C.c_int, C.c_int,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gta_b200_surface_area_large.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_int, _dp, _dp, _ip, _ip]
     L.gta_b200_orient2d_signs.argtypes = [_dp, C.c_int, _ip, C.c_int]
     L.gta_b200_incircle_signs.argtypes = [_dp, C.c_int, _ip, C.c_int]
     _lib = L
@@ -159,6 +166,17 @@ def incircle_signs(pts, device=-1):
     out = np.zeros(len(p), dtype=np.int32)
     _check(lib().gta_b200_incircle_signs(p.ctypes.data_as(_dp), len(p), out.ctypes.data_as(_ip), device))
     return out
+
+
+def stage_ms(device=-1, reset=False):
+    """Per-kernel device milliseconds of the throughput path since the last reset: dict(prepass, walk, area, launches)."""
+    L = lib()
+    if reset:
+        _check(L.gta_b200_stage_reset(int(device)))
+        return None
+    a, b, c, n = C.c_double(), C.c_double(), C.c_double(), C.c_int()
+    _check(L.gta_b200_stage_ms(int(device), C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
+    return dict(prepass=a.value, walk=b.value, area=c.value, launches=n.value)
 
 
 class Tessellator:

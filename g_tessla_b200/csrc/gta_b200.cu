@@ -19,6 +19,7 @@
 #include <vector>
 #include "gta_kernel.cuh"
 #include "gta_lpf.cuh"
+#include "gta_prepass.cuh"
 
 namespace {
 
@@ -99,12 +100,13 @@ int launch_t(const gt::KParams& p, const Shape& s, cudaStream_t st) {
     return GTA_B200_OK;
 }
 
-// The lane-per-frame path's pre-pass (gta_kernel.cuh, PREPASS): 256 threads per frame, shared memory without the edge pool.
+// The throughput path's first stage (gta_prepass.cuh): bulk-copied coordinate tiles, -corr, bucket sort -> point records.
 int launch_prepass(const gt::KParams& p, const Shape& s, cudaStream_t st) {
-    auto kern = gt::tessellate_kernel<256, 4, true>;
-    const size_t smem = gt::smem_bytes_for(s.cap, s.cap_p2, p.natoms, true);
+    auto kern = gt::prepass_kernel<256>;
+    const size_t smem = gt::PrepassSmem(s.cap, p.natoms, p.in_dim).total;
     int dev = 0, occ = 0, sms = 0;
     CK(cudaGetDevice(&dev));
+    if (smem > (size_t)smem_limit()) return fail(GTA_B200_E_TOO_LARGE, "frame too large for the pre-pass kernel");
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -262,6 +264,8 @@ int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st) {
             CK(cudaGetLastError());
             return GTA_B200_OK;
         };
+        // (18 / 20 warps at the 96 registers they leave per thread, 132 bytes of spills in the incircle step: 336 ms instead of
+        // 270 ms per 100k frames -- the register file, not the warp count, is what this kernel wants)
         if (c->degenerate || env.threads == 384) rc = go(gt::lpf_wave_kernel<384, true>, 384);
         else rc = go(gt::lpf_wave_kernel<512, false>, 512);
         if (rc) return rc;
@@ -728,6 +732,42 @@ static int signs_common(const double* pts, int n, int* out, int device, int widt
     cudaFree(d); cudaFree(o);
     return GTA_B200_OK;
 }
+// FP64 peak of this device, measured: independent DFMA chains in registers (the denominator of the FP64 roofline;
+// MEASURED_PEAKS.json has no FP64 figure). Returns TFLOP/s (2 flops per DFMA), <= 0 on error.
+namespace gt {
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        x0 = __fma_rn(x0, a, b); x1 = __fma_rn(x1, a, b); x2 = __fma_rn(x2, a, b); x3 = __fma_rn(x3, a, b);
+        x4 = __fma_rn(x4, a, b); x5 = __fma_rn(x5, a, b); x6 = __fma_rn(x6, a, b); x7 = __fma_rn(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+}  // namespace gt
+double gta_b200_fp64_peak_tflops(int device) {
+    if (!have_device()) return -1.0;
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return -1.0;
+    int sms = 0, dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1.0;
+    const int blocks = sms * 8, threads = 256, iters = 1 << 15;
+    double* out = nullptr; cudaEvent_t e0, e1;
+    if (cudaMalloc((void**)&out, sizeof(double) * blocks * threads) != cudaSuccess) return -1.0;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {                          // first repetition warms the clocks up
+        cudaEventRecord(e0);
+        gt::dfma_peak_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+        float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    return best;
+}
+
 // Debug hook (not in the public header): allocate / read the phase timers of GT_PHASE_TIMING builds.
 int gta_b200_dbg_timers(unsigned long long* out64, int reset) {       // [0..31] fused kernel, [32..63] lane-per-frame kernel
     if (!g_dbg) { if (cudaMalloc((void**)&g_dbg, 64 * 8) != cudaSuccess) return -1; cudaMemset(g_dbg, 0, 64 * 8); }

@@ -44,13 +44,13 @@ __device__ __forceinline__ LFrame lpf_frame(const LpfWs& ws, int fr) {
 #define GT_LPF_STRIDE 384
 #endif
 constexpr int LPF_MAX_SLOTS = GT_LPF_STRIDE;
-constexpr int LPF_DEFAULT_SLOTS = 352;
+constexpr int LPF_DEFAULT_SLOTS = 384;
 constexpr int LPF_MAX_SPLIT = 5;           // the "arrived" bits of a frame's top nodes fit one word (lpf_core.cuh LMeta), and a
                                            // frame's walkers start from one chunk of free slots (<= 32)
 
 // shared-memory layout of a block, computed identically on the host
 struct LpfSmem {
-    size_t st, meta, fs_frame, fs_n, fs_mask, slot_fs, bins, cnt, ctl, total;
+    size_t st, meta, fs_frame, fs_n, fs_mask, slot_fs, freeq, bins, cnt, ctl, total;
     __host__ __device__ LpfSmem(int slots, int fslots) {
         constexpr int NB = LP_DONE + 1;
         size_t o = 0;
@@ -62,7 +62,8 @@ struct LpfSmem {
         cnt = o; o += 48 * 4;
         ctl = o; o += 8 * 4;
         slot_fs = o; o += 2 * (size_t)slots;
-        bins = o; o += 2 * (size_t)2 * NB * slots;
+        freeq = o; o += 2 * (size_t)slots;
+        bins = o; o += 2 * (size_t)2 * (NB - 1) * slots;
         total = (o + 15) & ~(size_t)15;
     }
 };
@@ -113,7 +114,7 @@ __device__ __forceinline__ int lpf_fs_pop(uint32_t* mask, int words) {
 // A chunk of free slots admits `nadm` frames: lane a < nadm takes a frame slot and the next frame of the batch that passed
 // the pre-pass, then lanes a * 2^K ... a * 2^K + 2^kk - 1 start the walkers of its subtrees. Returns the lane's new phase.
 __device__ __noinline__ int lpf_admit(const LpfParams& p, uint32_t* st, LMeta* meta, int* fs_frame, int* fs_n, uint32_t* fs_mask, int FSW,
-                                      u16* slot_fs, int* ctl, int nadm, bool live, int sl, int lane) {
+                                      u16* slot_fs, int* exhausted_next, int nadm, bool live, int sl, int lane) {
     const int K = p.split;
     int fs = -1, kk = 0;
     if (lane < nadm) {
@@ -121,7 +122,7 @@ __device__ __noinline__ int lpf_admit(const LpfParams& p, uint32_t* st, LMeta* m
         if (fs >= 0) {
             for (;;) {
                 const int fr = (int)atomicAdd(p.counter, 1u);
-                if (fr >= p.nframes) { ctl[0] = 1; atomicOr(&fs_mask[fs >> 5], 1u << (fs & 31)); fs = -1; break; }
+                if (fr >= p.nframes) { *exhausted_next = 1; atomicOr(&fs_mask[fs >> 5], 1u << (fs & 31)); fs = -1; break; }
                 const int n = p.ws.n[fr];
                 if (p.ws.st[fr] != 0 || n < 2) continue;          // rejected by the pre-pass: the area kernel reports it
                 fs_frame[fs] = fr; fs_n[fs] = n;
@@ -161,9 +162,10 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
     int* fs_n = reinterpret_cast<int*>(lsm + L.fs_n);                      // [FS] its point count
     uint32_t* fs_mask = reinterpret_cast<uint32_t*>(lsm + L.fs_mask);      // free frame slots
     u16* slot_fs = reinterpret_cast<u16*>(lsm + L.slot_fs);                // [SLOTS] frame slot of the walker
-    u16* bins = reinterpret_cast<u16*>(lsm + L.bins);                      // [2][NB][SLOTS] slots of each phase, this round / next round
-    int* cnt = reinterpret_cast<int*>(lsm + L.cnt);                        // [3][16] slots per bin: this round / next round / being cleared
-    int* ctl = reinterpret_cast<int*>(lsm + L.ctl);                        // [0] batch exhausted, [1..3] chunk tickets (same rotation)
+    u16* freeq = reinterpret_cast<u16*>(lsm + L.freeq);                    // [SLOTS] ring of free slots (retired walkers), see below
+    u16* bins = reinterpret_cast<u16*>(lsm + L.bins);                      // [2][NB - 1][SLOTS] slots of each phase, this round / next round
+    int* cnt = reinterpret_cast<int*>(lsm + L.cnt);                        // [3][16] slots per bin ([15]: batch exhausted): this round / next round / being cleared
+    int* ctl = reinterpret_cast<int*>(lsm + L.ctl);                        // [1..3] chunk tickets (same rotation as cnt)
     const int tid = threadIdx.x, lane = tid & 31;
     const int K = p.split;
 
@@ -171,9 +173,13 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
     if (tid < 8) ctl[tid] = 0;
     for (int w = tid; w < FSW; w += THREADS) fs_mask[w] = (w * 32 + 32 <= FS) ? 0xffffffffu : ((1u << (FS - w * 32)) - 1u);
     __syncthreads();
-    // every slot starts in the free bin
-    for (int sl = tid; sl < SLOTS; sl += THREADS) bins[(size_t)LP_DONE * SLOTS + sl] = (u16)sl;
-    if (tid == 0) cnt[LP_DONE] = SLOTS;
+    // Free slots wait in a ring, not in a bin: a bin costs a chunk (a warp) every round, and with 2^K slots needed per
+    // admission there nearly always are a few free ones waiting. Retiring walkers append behind q_tail (their count is
+    // this round's c_next[LP_DONE]); the round's one admission chunk takes from q_head. Both cursors are advanced by every
+    // warp for itself from values that are stable across the round barrier, so all warps see the same chunk table.
+    for (int sl = tid; sl < SLOTS; sl += THREADS) freeq[sl] = (u16)sl;
+    int q_head = 0, q_tail = SLOTS;
+    bool exhausted = false;                                                // the batch has no frame left to admit
     __syncthreads();
 
     for (int round = 0;; ++round) {
@@ -183,17 +189,21 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
         // the third set of counters / tickets was last read a round ago: clear it for the round after this one
         if (tid < 16) cnt[16 * r3c + tid] = 0;
         if (tid == 0) ctl[1 + r3c] = 0;
-        const u16* bin_now = bins + (size_t)b * NB * SLOTS;
-        u16* bin_next = bins + (size_t)(b ^ 1) * NB * SLOTS;
+        const u16* bin_now = bins + (size_t)b * (NB - 1) * SLOTS;
+        u16* bin_next = bins + (size_t)(b ^ 1) * (NB - 1) * SLOTS;
+        q_tail += c_now[LP_DONE];                                         // walkers that retired in the previous round
+        // this round's admission: up to 32 free slots, whole frames (2^K slots each) only
+        exhausted |= c_now[15] != 0;                                      // (raised through the round's counters: stable while the round runs)
+        const int take = exhausted ? 0 : (min(32, q_tail - q_head) & ~((1 << K) - 1));
+        const int q_take0 = q_head;
+        q_head += take;
         // ---- chunk table, computed by every warp for itself: lane q holds bin q's count and first chunk
-        const bool exhausted = ctl[0] != 0;
         // (position q of the table is bin ORDER[q]: the phases with the longest steps first, so that the round's last
         // chunks are its shortest and the warps reach the barrier closer together)
         constexpr unsigned ORDER = (unsigned)LP_INS | (unsigned)LP_SCAN << 4 | (unsigned)LP_C << 8 | (unsigned)LP_TAN << 12 | (unsigned)LP_V << 16
                                  | (unsigned)LP_LEAF << 20 | (unsigned)LP_TINIT << 24 | (unsigned)LP_DONE << 28;
         const int qbin = (int)((ORDER >> (4 * (lane & 7))) & 15u);
-        int myc = (lane < NB && qbin < NB) ? c_now[qbin] : 0;
-        if (qbin == LP_DONE && exhausted) myc = 0;                        // nothing left to start: free slots stay free
+        int myc = (lane < NB && qbin < NB) ? (qbin == LP_DONE ? take : c_now[qbin]) : 0;
         int incl = (myc + 31) >> 5;
 #pragma unroll
         for (int o = 1; o < 8; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }   // (lanes >= 8 hold 0)
@@ -215,13 +225,12 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
             const int idx = (c - __shfl_sync(0xffffffffu, first_chunk, q)) * 32 + lane;
             const int nph = __shfl_sync(0xffffffffu, myc, q);
             const bool live = idx < nph;
-            const int sl = live ? bin_now[(size_t)bin * SLOTS + idx] : 0;
+            const int sl = !live ? 0 : (bin == LP_DONE ? freeq[(q_take0 + idx) % SLOTS] : bin_now[(size_t)bin * SLOTS + idx]);
             int next = LP_DONE;
             if (bin == LP_DONE) {
                 // free slots (lanes 0 .. na-1 of the chunk): start as many whole frames as there are slots for all of a
                 // frame's 2^K subtree walkers (out of line: it runs for a few chunks per frame, the loop around it all the time)
-                const int na = __popc(__ballot_sync(0xffffffffu, live));
-                if ((na >> K) > 0) next = lpf_admit(p, st, meta, fs_frame, fs_n, fs_mask, FSW, slot_fs, ctl, na >> K, live, sl, lane);
+                next = lpf_admit(p, st, meta, fs_frame, fs_n, fs_mask, FSW, slot_fs, c_next + 15, take >> K, live, sl, lane);
             } else if (live) {
                 const int fs = slot_fs[sl];
                 const int fr = fs_frame[fs];
@@ -256,7 +265,11 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
                     next = LP_DONE;
                 }
             }
-            if (live) bin_next[(size_t)next * SLOTS + atomicAdd(&c_next[next], 1)] = (u16)sl;
+            if (live) {
+                const int pos = atomicAdd(&c_next[next], 1);
+                if (next == LP_DONE) freeq[(q_tail + pos) % SLOTS] = (u16)sl;         // retired (or not started): behind this round's tail
+                else bin_next[(size_t)next * SLOTS + pos] = (u16)sl;
+            }
             if (nchunks <= THREADS / 32) break;                            // every chunk had a warp of its own
             if (lane == 0) c = atomicAdd(ticket, 1) + THREADS / 32;
             c = __shfl_sync(0xffffffffu, c, 0);
@@ -290,12 +303,12 @@ __global__ void __launch_bounds__(128) lpf_area_kernel(const LpfAreaParams p) {
     if (st == 0) {
         const LFrame f = lpf_frame(p.ws, fr);
         const bool want2d = (p.flags & GTA_B200_2D) != 0;
-        unsigned base = 0;
+        unsigned base = 0, mine = 0;
         for (int i0 = 0; i0 < f.n; i0 += 32) {
             const int i = i0 + lane;
-            unsigned offs = 0, cnt = 0;
-            if (p.tri || p.ntri) {
-                cnt = (i < f.n) ? (unsigned)lf_vertex_triangles(f, i, [](int, int) {}) : 0u;
+            unsigned offs = 0;
+            if (p.tri) {                                                   // (parity tests) positions in the frame's triangle list: a count pass first
+                const unsigned cnt = (i < f.n) ? (unsigned)lf_vertex_triangles(f, i, [](int, int) {}) : 0u;
                 unsigned inc = cnt;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
@@ -305,8 +318,7 @@ __global__ void __launch_bounds__(128) lpf_area_kernel(const LpfAreaParams p) {
             if (i < f.n) {
                 const LPt pi = f.pt[i]; const double zi = pi.z;
                 int* out = p.tri ? p.tri + ((size_t)fr * p.tri_cap) * 3 : nullptr;
-                lf_vertex_triangles(f, i, [&](int n1, int n2) {
-                    const LPt p1 = f.pt[n1], p2 = f.pt[n2];
+                mine += (unsigned)lf_vertex_triangles_pts(f, i, pi, [&](int, int, const LPt& p1, const LPt& p2) {
                     a3 += tri_area3(pi.x, pi.y, zi, p1.x, p1.y, p1.z, p2.x, p2.y, p2.z);
                     if (want2d) a2 += tri_area3(pi.x, pi.y, 0.0, p1.x, p1.y, 0.0, p2.x, p2.y, 0.0);
                     if (out && (int)offs < p.tri_cap) { out[3 * offs] = pi.perm; out[3 * offs + 1] = p1.perm; out[3 * offs + 2] = p2.perm; }
@@ -314,6 +326,9 @@ __global__ void __launch_bounds__(128) lpf_area_kernel(const LpfAreaParams p) {
                 });
             }
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+        base = __shfl_sync(0xffffffffu, mine, 0);
         total = base;
     }
 #pragma unroll

@@ -625,4 +625,32 @@ GT_INLINE int lf_vertex_triangles(const LFrame& f, int i, Visit&& visit) {
     return cnt;
 }
 
+// The same enumeration for the area pass, arranged for memory-level parallelism: the ring is one chain of dependent
+// 8-byte record loads (the record of the next entry is fetched before the current triangle is evaluated), every
+// neighbour's point record is loaded once and handed from one triangle to the next. pi = the vertex's own record
+// (coordinates + ring head). visit(n1, n2, p1, p2) in emission order; returns the count.
+template <class Visit>
+GT_INLINE int lf_vertex_triangles_pts(const LFrame& f, int i, const LPt& pi, Visit&& visit) {
+    const int hd = pi.head;
+    if (hd == (int)GT_NIL) return 0;
+    LRec cur = f.rec[hd];
+    if (cur.nxt == hd) return 0;
+    LPt none; none.x = none.y = none.z = 0.0; none.head = none.perm = 0; none.pad = 0;
+    LPt p1 = (int)cur.dst > i ? f.pt[cur.dst] : none;
+    int cnt = 0, h = hd;
+    do {
+        const int hn = cur.nxt;
+        const LRec nx = f.rec[hn];
+        const int n1 = cur.dst, n2 = nx.dst;
+        const LPt p2 = n2 > i ? f.pt[n2] : none;
+        if (n1 > i && n2 > i) {
+            if (hn == hd && !(orient2d_sign(p1.x, p1.y, p2.x, p2.y, pi.x, pi.y) > 0)) break;      // the hull gap (:619-621): !rightOf(n1, i, n2)
+            visit(n1, n2, p1, p2);
+            ++cnt;
+        }
+        h = hn; cur = nx; p1 = p2;
+    } while (h != hd);
+    return cnt;
+}
+
 }  // namespace gt

@@ -15,6 +15,20 @@ def frame_range(nframes: int, rank: int, world: int) -> tuple[int, int]:
     return lo, min(nframes, lo + per)
 
 
+def gather_frames(local, nframes: int, group=None):
+    """The path's only exchange: every rank holds the per-frame values of its own frame_range (a 1-D torch tensor, on
+    the device with NCCL, on the host with gloo) and receives the full [nframes] tensor."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    per = (nframes + world - 1) // world
+    loc = torch.zeros(per, dtype=local.dtype, device=local.device)
+    loc[:len(local)] = local
+    parts = [torch.zeros_like(loc) for _ in range(world)]
+    dist.all_gather(parts, loc, group=group)
+    return torch.cat(parts)[:nframes]
+
+
 def tessellate_sharded(xyz, box, espace, flags, compute=None, group=None, device=None):
     """Every rank passes the same full arrays (or at least its own slice filled in); returns the full per-frame
     result dict on every rank. `compute(xyz, box, espace, flags) -> dict(area, areabox[, area2d], status)` defaults
@@ -28,15 +42,12 @@ def tessellate_sharded(xyz, box, espace, flags, compute=None, group=None, device
     F = len(xyz)
     lo, hi = frame_range(F, rank, world)
     r = compute(xyz[lo:hi], None if box is None else box[lo:hi], espace, flags) if hi > lo else None
-    per = (F + world - 1) // world
     keys = ["area", "areabox", "status"] + (["area2d"] if (flags & 2) else [])
     out = {}
     for k in keys:
-        loc = torch.zeros(per, dtype=torch.float64, device=device)
+        loc = torch.zeros(hi - lo, dtype=torch.float64, device=device)
         if r is not None:
-            loc[:hi - lo] = torch.as_tensor(np.asarray(r[k], dtype=np.float64), device=device)
-        parts = [torch.zeros_like(loc) for _ in range(world)]
-        dist.all_gather(parts, loc, group=group)
-        full = torch.cat(parts)[:F].cpu().numpy()
+            loc[:] = torch.as_tensor(np.asarray(r[k], dtype=np.float64), device=device)
+        full = gather_frames(loc, F, group=group).cpu().numpy()
         out[k] = full.astype(np.int32) if k == "status" else full
     return out

@@ -137,6 +137,10 @@ int gta_b200_last_launches(void);
 int gta_b200_stage_reset(int device);
 int gta_b200_stage_ms(int device, double *prepass_ms, double *walk_ms, double *area_ms, int *launches);
 
+/* FP64 peak of the device in TFLOP/s, measured with independent DFMA chains (2 flops each): the denominator of the
+ * FP64 roofline bench.py reports (MEASURED_PEAKS.json holds no FP64 figure). <= 0 on error. device < 0: current. */
+double gta_b200_fp64_peak_tflops(int device);
+
 /* Predicate self-test hooks (device evaluation of the exact-sign predicates on arrays):
  * pts [n][6] -> sign [n] for orient2d, pts [n][8] for incircle; host pointers. */
 int gta_b200_orient2d_signs(const double *pts, int n, int *sign_out, int device);

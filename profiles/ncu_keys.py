@@ -1,5 +1,11 @@
-"""Print the handful of ncu raw-page metrics the DESIGN/roofline notes quote (per captured launch)."""
-import csv, subprocess, sys
+"""Print the handful of ncu raw-page metrics the DESIGN/roofline notes quote (per captured launch).
+
+  python profiles/ncu_keys.py REPORT.ncu-rep                         print the metrics
+  python profiles/ncu_keys.py REPORT.ncu-rep --json OUT.json FRAMES  also write the DRAM traffic per frame of the first captured
+      launch (FRAMES = frames that launch processed) with the hash of the CUDA sources and the git commit it was taken on:
+      bench.py reads it for roofline.traffic and flags it stale when the sources have changed since.
+"""
+import csv, hashlib, json, os, subprocess, sys
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(l for l in raw.splitlines() if l.startswith('"')))
@@ -23,3 +29,23 @@ for r in rows[2:]:
     for v, h in top:
         print("  stall %-45s %.3f" % (h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")], v))
     print("-" * 40)
+
+if "--json" in sys.argv:
+    k = sys.argv.index("--json")
+    out, frames = sys.argv[k + 1], int(sys.argv[k + 2])
+    d = dict(zip(hdr, rows[2]))
+    def gb(name):
+        v = float(d[name].replace(",", "")); u = units[hdr.index(name)].lower()
+        return v * {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0, "tbyte": 1e12}[u]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    h = hashlib.sha1()
+    src = os.path.join(root, "g_tessla_b200", "csrc")
+    for f in sorted(os.listdir(src)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(src, f), "rb").read())
+    rd, wr = gb("dram__bytes_read.sum"), gb("dram__bytes_write.sum")
+    git = subprocess.run(["git", "-C", root, "rev-parse", "HEAD"], capture_output=True, text=True).stdout.strip()
+    json.dump({"report": os.path.basename(rep), "kernel": d.get("Kernel Name", ""), "frames": frames, "dram_bytes_read": rd, "dram_bytes_write": wr,
+               "dram_bytes_per_frame": (rd + wr) / frames, "gpu_time_ms": float(d["gpu__time_duration.sum"].replace(",", "")),
+               "sources_sha": h.hexdigest(), "git": git}, open(out, "w"), indent=1)
+    print("wrote", out)
