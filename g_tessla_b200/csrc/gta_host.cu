@@ -225,25 +225,6 @@ void delaunay_surface_area(const rvec* x, matrix box, int natoms, unsigned char 
     if (a2D) *a2D = (st & ~GTA_B200_ST_TOO_FEW_POINTS) ? kNaN : a2;
 }
 
-void tessellate_area(const char* traj_fname, const char* ndx_fname, output_env_t* oenv, real espace, int nthreads,
-                     struct tri_area* areas, unsigned char flags) {
-    rvec **pre_x = nullptr, **x = nullptr;
-    matrix* box = nullptr;
-    areas->area = areas->area2D = areas->area2Dbox = nullptr;          // gta_tri.c:51-53
-    g_call_rc = GTA_B200_OK;
-    read_traj(traj_fname, &pre_x, &box, &areas->nframes, &areas->natoms, oenv);
-    if (!pre_x) { g_call_rc = GTA_B200_E_ARG; areas->nframes = 0; return; }
-    if (ndx_fname) {
-        ndx_filter_traj(ndx_fname, pre_x, &x, areas->nframes, &areas->natoms);
-        for (int i = 0; i < areas->nframes; ++i) free(pre_x[i]);
-        free(pre_x);
-        if (!x) { g_call_rc = GTA_B200_E_ARG; free(box); areas->nframes = 0; return; }
-    } else x = pre_x;
-    delaunay_tessellate(x, box, espace, nthreads, areas, flags);
-    for (int i = 0; i < areas->nframes; ++i) free(x[i]);
-    free(x); free(box);
-}
-
 void print_areas(const char* fname, const struct tri_area* areas) {
     FILE* f = fopen(fname, "w");
     if (!f) { print_log("Could not open %s for writing.\n", fname); return; }
@@ -279,16 +260,24 @@ void free_tri_area(struct tri_area* areas) {
 // ------------------------------------------------------------------------------------------ trajectory input
 namespace {
 
+// A trajectory as the readers deliver it: ONE contiguous [nframes][nkeep][3] array (what the batch entry points want;
+// the reference's layout -- one heap block per frame, extern/gkut/src/gkut_io.c:37 -- is made from it only for the kept
+// read_traj). `keep` (optional) is the index group: the filter is applied while reading, so the atoms that are not
+// selected are never stored.
 struct Traj {
-    std::vector<rvec*> x; std::vector<double> box;   // box: 9 per frame
-    int natoms = -1;
-    bool add(int n, const std::vector<double>& xyz, const double b[9]) {
-        if (natoms < 0) natoms = n;
-        if (n != natoms) { fprintf(stderr, "read_traj: frame %zu has %d atoms, expected %d\n", x.size(), n, natoms); return false; }
-        rvec* fr = (rvec*)malloc(sizeof(rvec) * (size_t)(n > 0 ? n : 1));
-        memcpy(fr, xyz.data(), sizeof(double) * 3 * (size_t)n);
-        x.push_back(fr);
+    std::vector<double> xyz, box;                    // box: 9 per frame
+    const std::vector<int>* keep = nullptr;
+    int natoms = -1, nkeep = -1, nframes = 0;
+    bool add(int n, const std::vector<double>& fr, const double b[9]) {
+        if (natoms < 0) {
+            natoms = n; nkeep = keep ? (int)keep->size() : n;
+            if (keep) for (int a : *keep) if (a < 0 || a >= n) { fprintf(stderr, "index group: atom %d out of range (1..%d)\n", a + 1, n); return false; }
+        }
+        if (n != natoms) { fprintf(stderr, "read_traj: frame %d has %d atoms, expected %d\n", nframes, n, natoms); return false; }
+        if (keep) for (int a : *keep) xyz.insert(xyz.end(), fr.begin() + 3 * (size_t)a, fr.begin() + 3 * (size_t)a + 3);
+        else xyz.insert(xyz.end(), fr.begin(), fr.begin() + 3 * (size_t)n);
         box.insert(box.end(), b, b + 9);
+        ++nframes;
         return true;
     }
 };
@@ -334,7 +323,7 @@ bool read_gro(FILE* f, Traj& t) {
         if (k >= 9) { b[1] = v[3]; b[2] = v[4]; b[3] = v[5]; b[5] = v[6]; b[6] = v[7]; b[7] = v[8]; }
         if (!t.add(n, xyz, b)) return false;
     }
-    return !t.x.empty();
+    return t.nframes > 0;
 }
 
 bool read_pdb(FILE* f, Traj& t) {
@@ -357,7 +346,7 @@ bool read_pdb(FILE* f, Traj& t) {
             if (!flush()) return false;
         }
     }
-    return flush() && !t.x.empty();
+    return flush() && t.nframes > 0;
 }
 
 // XDR (big-endian) primitives for .trr
@@ -398,7 +387,7 @@ bool read_trr(FILE* f, Traj& t) {
         if (fseek(f, sz[8] + sz[9], SEEK_CUR)) return false;                   // velocities, forces
         if (!t.add(natoms, xyz, b)) return false;
     }
-    return !t.x.empty();
+    return t.nframes > 0;
 }
 
 
@@ -524,7 +513,40 @@ bool read_xtc(FILE* f, Traj& t) {
         if (o != xyz.size()) return false;
         if (!t.add(natoms, xyz, b)) return false;
     }
-    return !t.x.empty();
+    return t.nframes > 0;
+}
+
+bool read_any(const char* traj_fname, Traj& t) {
+    std::string name(traj_fname ? traj_fname : "");
+    FILE* f = fopen(traj_fname, "rb");
+    if (!f) { fprintf(stderr, "read_traj: cannot open %s\n", traj_fname); return false; }
+    bool ok;
+    try {                                                      // (nothing may propagate through the C interface)
+        if (ends_with(name, ".gro")) ok = read_gro(f, t);
+        else if (ends_with(name, ".pdb")) ok = read_pdb(f, t);
+        else if (ends_with(name, ".trr")) ok = read_trr(f, t);
+        else if (ends_with(name, ".xtc")) ok = read_xtc(f, t);
+        else { fprintf(stderr, "read_traj: %s: unknown trajectory format (supported: .gro .pdb .trr .xtc)\n", traj_fname); fclose(f); return false; }
+    } catch (...) { ok = false; }
+    fclose(f);
+    if (!ok) fprintf(stderr, "read_traj: %s: malformed or empty trajectory\n", traj_fname);
+    return ok;
+}
+
+// first group of an index file, 0-based
+bool read_ndx(const char* ndx_fname, std::vector<int>& idx) {
+    FILE* f = fopen(ndx_fname, "r");
+    if (!f) { fprintf(stderr, "ndx_filter_traj: cannot open %s\n", ndx_fname); return false; }
+    char line[4096]; int groups = 0;
+    while (fgets(line, sizeof line, f)) {
+        const char* p = line; while (isspace((unsigned char)*p)) ++p;
+        if (*p == '[') { if (++groups > 1) break; continue; }
+        if (groups != 1) continue;
+        char* q = (char*)p;
+        for (;;) { char* end; long v = strtol(q, &end, 10); if (end == q) break; idx.push_back((int)v - 1); q = end; }
+    }
+    fclose(f);
+    return true;
 }
 
 }  // namespace
@@ -534,46 +556,23 @@ extern "C" {
 void read_traj(const char* traj_fname, rvec*** x, matrix** box, int* nframes, int* natoms, output_env_t* oenv) {
     (void)oenv;
     *x = nullptr; *box = nullptr; *nframes = 0; *natoms = 0;
-    std::string name(traj_fname ? traj_fname : "");
-    FILE* f = fopen(traj_fname, "rb");
-    if (!f) { fprintf(stderr, "read_traj: cannot open %s\n", traj_fname); return; }
-    Traj t; bool ok;
-    try {                                                      // (nothing may propagate through the C interface)
-        if (ends_with(name, ".gro")) ok = read_gro(f, t);
-        else if (ends_with(name, ".pdb")) ok = read_pdb(f, t);
-        else if (ends_with(name, ".trr")) ok = read_trr(f, t);
-        else if (ends_with(name, ".xtc")) ok = read_xtc(f, t);
-        else { fprintf(stderr, "read_traj: %s: unknown trajectory format (supported: .gro .pdb .trr .xtc)\n", traj_fname); fclose(f); return; }
-    } catch (...) { ok = false; }
-    fclose(f);
-    if (!ok) {
-        fprintf(stderr, "read_traj: %s: malformed or empty trajectory\n", traj_fname);
-        for (rvec* p : t.x) free(p);
-        return;
-    }
-    const int F = (int)t.x.size();
+    Traj t;
+    if (!read_any(traj_fname, t)) return;
+    // the reference's layout: one heap block per frame (extern/gkut/src/gkut_io.c:37)
+    const int F = t.nframes, N = t.natoms;
     *x = (rvec**)malloc(sizeof(rvec*) * (size_t)F);
     *box = (matrix*)malloc(sizeof(matrix) * (size_t)F);
-    memcpy(*x, t.x.data(), sizeof(rvec*) * (size_t)F);
+    for (int fr = 0; fr < F; ++fr) {
+        (*x)[fr] = (rvec*)malloc(sizeof(rvec) * (size_t)(N > 0 ? N : 1));
+        memcpy((*x)[fr], t.xyz.data() + 3 * (size_t)N * fr, sizeof(double) * 3 * (size_t)N);
+    }
     memcpy(*box, t.box.data(), sizeof(double) * 9 * (size_t)F);
-    *nframes = F; *natoms = t.natoms;
+    *nframes = F; *natoms = N;
 }
 
 void ndx_filter_traj(const char* ndx_fname, rvec** pre_x, rvec*** new_x, int nframes, int* natoms) {
     std::vector<int> idx;
-    FILE* f = fopen(ndx_fname, "r");
-    if (!f) { fprintf(stderr, "ndx_filter_traj: cannot open %s\n", ndx_fname); }
-    else {
-        char line[4096]; int groups = 0;
-        while (fgets(line, sizeof line, f)) {
-            const char* p = line; while (isspace((unsigned char)*p)) ++p;
-            if (*p == '[') { if (++groups > 1) break; continue; }
-            if (groups != 1) continue;
-            char* q = (char*)p;
-            for (;;) { char* end; long v = strtol(q, &end, 10); if (end == q) break; idx.push_back((int)v - 1); q = end; }
-        }
-        fclose(f);
-    }
+    read_ndx(ndx_fname, idx);
     const int n_in = *natoms, n = (int)idx.size();
     for (int i = 0; i < n; ++i)
         if (idx[i] < 0 || idx[i] >= n_in) {
@@ -590,6 +589,52 @@ void ndx_filter_traj(const char* ndx_fname, rvec** pre_x, rvec*** new_x, int nfr
         }
     }
     *natoms = n;
+}
+
+void tessellate_area(const char* traj_fname, const char* ndx_fname, output_env_t* oenv, real espace, int nthreads,
+                     struct tri_area* areas, unsigned char flags) {
+    (void)oenv;
+    areas->area = areas->area2D = areas->area2Dbox = nullptr;          // gta_tri.c:51-53
+    areas->nframes = 0; areas->natoms = 0;
+    g_call_rc = GTA_B200_OK;
+    // The reference reads one heap block per frame, filters them into new blocks and hands the pointers on (gta_tri.c:55-70).
+    // Here the reader streams the selected atoms of every frame into ONE contiguous array, which is what the batch entry
+    // point wants: no per-frame allocation, no filter copy, no gather into the staging buffers.
+    std::vector<int> idx;
+    Traj t;
+    if (ndx_fname) { if (!read_ndx(ndx_fname, idx)) { g_call_rc = GTA_B200_E_ARG; return; } t.keep = &idx; }
+    if (!read_any(traj_fname, t)) { g_call_rc = GTA_B200_E_ARG; return; }
+    const int F = t.nframes, N = t.nkeep;
+    areas->nframes = F; areas->natoms = N;
+    const unsigned fl = flags & (GTA_CORRECT | GTA_2D);
+    const int maxp = gta_b200_max_points_for(t.box.data(), 9, F, N, espace, fl);
+    if ((flags & GTA_PRINT) || maxp > gta_b200_max_points()) {
+        // -print (one frame at a time) and frames beyond the batched kernel: through delaunay_tessellate on per-frame views
+        std::vector<rvec*> x((size_t)F);
+        for (int fr = 0; fr < F; ++fr) x[fr] = (rvec*)(t.xyz.data() + 3 * (size_t)N * fr);
+        delaunay_tessellate(x.data(), (matrix*)t.box.data(), espace, nthreads, areas, flags);
+        return;
+    }
+    if (nthreads > 1 || nthreads <= 0) print_log("Triangulation will be parallelized.\n");   // gta_tri.c:93-94
+    dtinit();
+    areas->area = (real*)calloc((size_t)(F > 0 ? F : 1), sizeof(real));
+    areas->area2Dbox = (real*)calloc((size_t)(F > 0 ? F : 1), sizeof(real));
+    if (flags & GTA_2D) areas->area2D = (real*)calloc((size_t)(F > 0 ? F : 1), sizeof(real));
+    if (flags & GTA_CORRECT) print_log("Triangulating and correcting %d frames...\n", F);  // gta_tri.c:104
+    else print_log("Triangulating %d frames...\n", F);                                        // gta_tri.c:299
+    g_frame_status.assign((size_t)(F > 0 ? F : 1), 0);
+    const int ngpus = env_int("GTA_B200_NGPUS", 0);
+    const int rc = gta_b200_tessellate_multi(t.xyz.data(), 3, t.box.data(), 9, F, N, espace, fl, ngpus <= 0 ? gta_b200_device_count() : ngpus,
+                                             nthreads > 0 ? nthreads : 0, areas->area, areas->area2D, areas->area2Dbox, g_frame_status.data());
+    if (rc != GTA_B200_OK) {
+        print_log("TESSELLATION ERROR: %s\n", gta_b200_last_error());
+        g_call_rc = rc;
+        for (int fr = 0; fr < F; ++fr) { areas->area[fr] = kNaN; if (areas->area2D) areas->area2D[fr] = kNaN; g_frame_status[fr] |= GTA_B200_ST_INTERNAL; }
+        return;
+    }
+    int bad = 0;
+    for (int fr = 0; fr < F; ++fr) bad += g_frame_status[fr] != 0;
+    if (bad) print_log("WARNING: %d frame(s) were rejected (NaN area); see gta_last_frame_status().\n", bad);
 }
 
 }  // extern "C"
