@@ -600,353 +600,36 @@ int run_job(Job j, int device, int nstreams) {
     if (shp.smem > (size_t)smem_limit() || gt::pool_edges(shp.cap) >= 32760)
         return fail(GTA_B200_E_TOO_LARGE, "frame too large for the shared-memory kernel (see gta_b200_max_points)");
 
-    nstreams = std::max(1, std::min(nstreams <= 0 ? 3 : nstreams, 8));
-    const size_t frame_bytes = (size_t)j.natoms * j.in_dim * sizeof(double);
-    // chunk: enough frames for several waves of persistent CTAs, bounded to ~64 MB of coordinates
-    long long chunk = (j.nframes + nstreams - 1) / nstreams;
-    chunk = std::min<long long>(chunk, std::max<long long>(256, (64ll << 20) / (long long)std::max<size_t>(frame_bytes, 1)));
-    chunk = std::max<long long>(chunk, 1);
-    if (use_lpf(j.nframes, shp)) {
-        // throughput path: a launch lasts at least one frame's critical path (~2,800 rounds), so launches want >= 10^4
-        // frames; up to three chunks in flight so that the copies of one overlap the kernels of another
-        const long long target = std::max<long long>(4096, std::min<long long>(25000, (1ll << 30) / (long long)std::max<size_t>(frame_bytes, 1)));
-        long long nchunks = (j.nframes + target - 1) / target;
-        // a batch of one or two launches' worth that has to be staged by the host first (per-frame blocks, pageable memory):
-        // cut it in pieces of >= chunk_min frames, so that the staging of the second piece runs under the kernels of the first
-        // (measured on one GPU, 12,500 / 25,000 frames in per-frame blocks: 227 -> 238 k and 242 -> 264 k frames/s; from a pinned
-        // buffer, where only the copy can overlap, one launch is as fast or faster: 268 k against 260 k)
-        static int cm_slot; static std::once_flag cm_once;
-        const long long chunk_min = std::max(1024, env_once("GTA_B200_CHUNK_MIN", 6000, &cm_slot, &cm_once));
-        if (j.frames || !src_pinned) nchunks = std::max(nchunks, std::min<long long>(3, j.nframes / chunk_min));
-        chunk = (j.nframes + nchunks - 1) / nchunks;
-        nstreams = (int)std::min<long long>(3, nchunks);
-    }
-    if (j.tri) {                                              // (parity tests) triangle lists: bound the device buffer of a chunk to 512 MB
-        const long long fit = std::max<long long>(1, (512ll << 20) / (12ll * std::max(j.tri_cap, 1)));
-        if (chunk > fit) { chunk = fit; nstreams = std::min(nstreams, 2); }
-    }
-    if (device < 0 || device >= 64) return fail(GTA_B200_E_ARG, "device index out of range");
-    std::lock_guard<std::mutex> launch_lock(g_lpf_launch_mu[device]);
-    g_lpf[device].ev_used = 0;
-    return GTA_B200_OK;
-}
-int gta_b200_stage_ms(int device, double* prepass_ms, double* walk_ms, double* area_ms, int* launches) {
-    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return fail(GTA_B200_E_CUDA, "cudaGetDevice");
-    if (device < 0 || device >= 64) return fail(GTA_B200_E_ARG, "device index out of range");
-    std::lock_guard<std::mutex> launch_lock(g_lpf_launch_mu[device]);
-    LpfCache& c = g_lpf[device];
-    double t[3] = {0.0, 0.0, 0.0};
-    for (size_t i = 0; i + 4 <= c.ev_used; i += 4) {
-        CK(cudaEventSynchronize(c.ev[i + 3]));
-        for (int k = 0; k < 3; ++k) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c.ev[i + k], c.ev[i + k + 1])); t[k] += ms; }
-    }
-    if (prepass_ms) *prepass_ms = t[0];
-    if (walk_ms) *walk_ms = t[1];
-    if (area_ms) *area_ms = t[2];
-    if (launches) *launches = (int)(c.ev_used / 4);
-    return GTA_B200_OK;
-}
-int gta_b200_last_launches(void) { return g_last_launches; }
-
-int gta_b200_device_count(void) {
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
-    return n;
-}
-
-int gta_b200_set_batch_threshold(int min_frames) {
-    int old = lpf_threshold();
-    g_lpf_threshold.store(min_frames < 0 ? GTA_B200_DEFAULT_BATCH_THRESHOLD : min_frames);
-    return old;
-}
-
-int gta_b200_max_points(void) {
-    // ~64 bytes of shared memory per point (see smem_bytes_for)
-    int lim = have_device() ? smem_limit() : 227 * 1024;
-    int lo = 4, hi = 8192;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) / 2;
-        Shape s = shape_for(mid);
-        if (s.smem <= (size_t)lim && gt::pool_edges(s.cap) < 32760) lo = mid; else hi = mid - 1;
-    }
-    return lo & ~1;
-}
-
-int gta_b200_max_points_for(const double* box, int box_stride, int nframes, int natoms, double espace, unsigned flags) {
-    if (!(flags & GTA_B200_CORRECT) || !box) return natoms;
-    int by_off = box_stride == 9 ? 4 : 1, best = 0;
-    for (int f = 0; f < nframes; ++f) {
-        int nx = (int)(box[(size_t)f * box_stride] / espace), ny = (int)(box[(size_t)f * box_stride + by_off] / espace);
-        if (nx < 0 || ny < 0 || nx > (1 << 20) || ny > (1 << 20)) continue;
-        best = std::max(best, 4 + 2 * nx + 2 * ny);
-    }
-    return natoms + best;
-}
-
-int gta_b200_launch_shape(int max_points, int natoms, int* threads_per_frame, size_t* smem_bytes, int* frames_per_sm) {
-    Shape s = shape_for(std::max(max_points, natoms), natoms);
-    if (threads_per_frame) *threads_per_frame = s.threads;
-    if (smem_bytes) *smem_bytes = s.smem;
-    if (frames_per_sm) {
-        *frames_per_sm = 0;
-        if (have_device() && s.smem <= (size_t)smem_limit()) {
-            // the attribute must be raised before the occupancy query sees > 48 KB
-            if (s.threads == 32) cudaFuncSetAttribute(gt::tessellate_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem);
-            else if (s.threads == 64) cudaFuncSetAttribute(gt::tessellate_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem);
-            else cudaFuncSetAttribute(gt::tessellate_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem);
-            *frames_per_sm = occupancy_for(s);
-        }
-    }
-    return GTA_B200_OK;
-}
-
-int gta_b200_tessellate_device(const double* d_xyz, int in_dim, const double* d_box, int box_stride,
-                               int nframes, int natoms, int max_points, double espace, unsigned flags,
-                               double* d_area, double* d_area2d, double* d_areabox, int* d_status,
-                               int* d_tri, int tri_cap, int* d_ntri,
-                               double* d_corr, int corr_cap, int* d_ncorr,
-                               unsigned int* d_work, void* stream) {
-    g_err.clear();
-    if (!have_device()) return fail(GTA_B200_E_NO_DEVICE, "no CUDA device: libgtessla_b200 has no CPU path");
-    if (nframes < 0 || natoms < 0 || (in_dim != 2 && in_dim != 3) || !d_xyz || !d_work)
-        return fail(GTA_B200_E_ARG, "bad argument");
-    if ((flags & GTA_B200_CORRECT) && (!d_box || !(espace > 0.0)))
-        return fail(GTA_B200_E_ARG, "-corr needs the box and espace > 0");
-    if (nframes == 0) return GTA_B200_OK;
-    Shape s = shape_for(std::max(max_points, natoms), natoms);
-    if (s.smem > (size_t)smem_limit() || gt::pool_edges(s.cap) >= 32760)
-        return fail(GTA_B200_E_TOO_LARGE, "max_points exceeds the shared-memory kernel (see gta_b200_max_points)");
-    cudaStream_t st = (cudaStream_t)stream;
-    gt::KParams p;
-    p.xyz = d_xyz; p.in_dim = in_dim; p.box = d_box; p.box_stride = box_stride; p.by_off = (box_stride == 9) ? 4 : 1;
-    p.nframes = nframes; p.natoms = natoms; p.cap = s.cap; p.cap_p2 = s.cap_p2;
-    p.espace = espace; p.flags = flags;
-    p.area = d_area; p.area2d = d_area2d; p.areabox = d_areabox; p.status = d_status;
-    p.tri = d_tri; p.tri_cap = tri_cap; p.ntri = d_ntri;
-    p.corr = d_corr; p.corr_cap = corr_cap; p.ncorr = d_ncorr;
-    p.work = d_work; p.coop_nodes = coop_nodes_for(s.threads); p.dbg = g_dbg; p.ws = gt::LpfWs{};
-    CK(cudaMemsetAsync(d_work, 0, sizeof(unsigned int), st));
-    const bool lpf = use_lpf(nframes, s);
-    if (!lpf) { g_last_launches = 1; return launch(p, s, st); }                      // the fused kernel
-    // throughput path: pre-pass + walker kernel + area kernel per launch; batches beyond one launch's worth are split evenly
-    const long long per_launch = lpf_frames_per_launch(s);
-    const long long parts = (nframes + per_launch - 1) / per_launch;
-    g_last_launches = 3 * (int)parts;
-    for (long long k = 0; k < parts; ++k) {
-        const long long f0 = (long long)nframes * k / parts, f1 = (long long)nframes * (k + 1) / parts;
-        gt::KParams q = p;
-        q.nframes = (int)(f1 - f0);
-        q.xyz = d_xyz + (size_t)f0 * natoms * in_dim;
-        if (d_box) q.box = d_box + (size_t)f0 * box_stride;
-        if (d_area) q.area = d_area + f0;
-        if (d_area2d) q.area2d = d_area2d + f0;
-        if (d_areabox) q.areabox = d_areabox + f0;
-        if (d_status) q.status = d_status + f0;
-        if (d_tri) q.tri = d_tri + (size_t)f0 * tri_cap * 3;
-        if (d_ntri) q.ntri = d_ntri + f0;
-        if (d_corr) q.corr = d_corr + (size_t)f0 * corr_cap * 3;
-        if (d_ncorr) q.ncorr = d_ncorr + f0;
-        if (k) CK(cudaMemsetAsync(d_work, 0, sizeof(unsigned int), st));
-        const int rc = launch_lpf(q, s, st);
-        if (rc) return rc;
-    }
-    return GTA_B200_OK;
-}
-
-}  // extern "C"
-
-// ------------------------------------------------------------------------------------------
-// Host-buffer pipeline
-// ------------------------------------------------------------------------------------------
-namespace {
-
-struct Job {
-    const double* xyz = nullptr;             // flat [nframes][natoms][in_dim] or
-    const double* const* frames = nullptr;   // one pointer per frame (reference layout)
-    int in_dim = 3;
-    const double* box = nullptr; int box_stride = 0;
-    int nframes = 0, natoms = 0; double espace = 0.8; unsigned flags = 0;
-    int max_points = 0;
-    double *area = nullptr, *area2d = nullptr, *areabox = nullptr; int* status = nullptr;
-    int* tri = nullptr; int tri_cap = 0; int* ntri = nullptr;
-    double* corr = nullptr; int corr_cap = 0; int* ncorr = nullptr;
-    int host_threads = 0;                    // staging threads (the meaning -nthreads keeps); <= 0: all cores
-};
-
-// One in-flight chunk: pinned + device buffers, a stream and two events.
-struct Slot {
-    cudaStream_t st = nullptr; cudaEvent_t k0 = nullptr, k1 = nullptr;
-    double *h_in = nullptr, *d_in = nullptr;           // coords
-    double *h_box = nullptr, *d_box = nullptr;
-    double *h_out = nullptr, *d_out = nullptr;         // area | area2d | areabox  (3 * chunk)
-    int *h_st = nullptr, *d_st = nullptr;              // status | ntri | ncorr    (3 * chunk)
-    int* d_tri = nullptr; double* d_corr = nullptr;    // optional, copied straight to the caller
-    unsigned int* d_work = nullptr;
-    size_t in_bytes = 0; int chunk = 0, box_stride = 0; size_t tri_elems = 0, corr_elems = 0;
-    int f0 = 0, nf = 0; bool busy = false;
-};
-
-void slot_free(Slot& s) {
-    if (s.st) cudaStreamDestroy(s.st);
-    if (s.k0) cudaEventDestroy(s.k0);
-    if (s.k1) cudaEventDestroy(s.k1);
-    cudaFreeHost(s.h_in); cudaFree(s.d_in); cudaFreeHost(s.h_box); cudaFree(s.d_box);
-    cudaFreeHost(s.h_out); cudaFree(s.d_out); cudaFreeHost(s.h_st); cudaFree(s.d_st);
-    cudaFree(s.d_tri); cudaFree(s.d_corr); cudaFree(s.d_work);
-    s = Slot();
-}
-
-int slot_ensure(Slot& s, int chunk, size_t frame_bytes, int box_stride, size_t tri_elems, size_t corr_elems, bool need_pinned_in) {
-    size_t in_bytes = frame_bytes * (size_t)chunk;
-    if (s.st && s.in_bytes >= in_bytes && (s.h_in || !need_pinned_in) && s.chunk >= chunk && s.box_stride >= box_stride &&
-        s.tri_elems >= tri_elems && s.corr_elems >= corr_elems) return GTA_B200_OK;
-    slot_free(s);
-    CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
-    CK(cudaEventCreate(&s.k0)); CK(cudaEventCreate(&s.k1));
-    if (need_pinned_in) CK(cudaHostAlloc((void**)&s.h_in, in_bytes, cudaHostAllocDefault));     // not needed when the caller's buffer is page-locked
-    CK(cudaMalloc((void**)&s.d_in, in_bytes));
-    size_t bb = sizeof(double) * (size_t)std::max(box_stride, 1) * chunk;
-    CK(cudaHostAlloc((void**)&s.h_box, bb, cudaHostAllocDefault)); CK(cudaMalloc((void**)&s.d_box, bb));
-    CK(cudaHostAlloc((void**)&s.h_out, sizeof(double) * 3 * (size_t)chunk, cudaHostAllocDefault));
-    CK(cudaMalloc((void**)&s.d_out, sizeof(double) * 3 * (size_t)chunk));
-    CK(cudaHostAlloc((void**)&s.h_st, sizeof(int) * 3 * (size_t)chunk, cudaHostAllocDefault));
-    CK(cudaMalloc((void**)&s.d_st, sizeof(int) * 3 * (size_t)chunk));
-    if (tri_elems) CK(cudaMalloc((void**)&s.d_tri, sizeof(int) * tri_elems));
-    if (corr_elems) CK(cudaMalloc((void**)&s.d_corr, sizeof(double) * corr_elems));
-    CK(cudaMalloc((void**)&s.d_work, sizeof(unsigned int)));
-    s.in_bytes = in_bytes; s.chunk = chunk; s.box_stride = box_stride; s.tri_elems = tri_elems; s.corr_elems = corr_elems;
-    return GTA_B200_OK;
-}
-
-// Per device: a small set of reusable slots (pinned allocations cost ~1 s per GB, and the sharded entry points
-// run each device from a fresh host thread, so the cache cannot be thread-local). A job holds its device's cache
-// for its duration: concurrent calls on one device queue behind each other.
-struct SlotCache { std::vector<Slot> slots; std::mutex mu; };
-SlotCache g_caches[64];
-
-int drain(Slot& s, const Job& j, double* kernel_ms) {
-    if (!s.busy) return GTA_B200_OK;
-    static int trace_slot; static std::once_flag trace_once;
-    const bool trace = env_once("GTA_B200_TRACE", 0, &trace_slot, &trace_once) != 0;
-    const auto t_begin = std::chrono::steady_clock::now();
-    CK(cudaStreamSynchronize(s.st));
-    if (trace) fprintf(stderr, "[gta_b200] chunk %d+%d: waited %.1f ms for copies + kernels\n", s.f0, s.nf, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, s.k0, s.k1) == cudaSuccess) *kernel_ms += ms;
-    const int c = s.chunk;
-    if (j.area) memcpy(j.area + s.f0, s.h_out, sizeof(double) * s.nf);
-    if (j.area2d && (j.flags & GTA_B200_2D)) memcpy(j.area2d + s.f0, s.h_out + c, sizeof(double) * s.nf);
-    if (j.areabox) memcpy(j.areabox + s.f0, s.h_out + 2 * (size_t)c, sizeof(double) * s.nf);
-    if (j.status) memcpy(j.status + s.f0, s.h_st, sizeof(int) * s.nf);
-    if (j.ntri) memcpy(j.ntri + s.f0, s.h_st + c, sizeof(int) * s.nf);
-    if (j.ncorr) memcpy(j.ncorr + s.f0, s.h_st + 2 * (size_t)c, sizeof(int) * s.nf);
-    s.busy = false;
-    return GTA_B200_OK;
-}
-
-int submit(Slot& s, const Job& j, const Shape& shp, int f0, int nf, bool src_pinned) {
-    static int trace_slot; static std::once_flag trace_once;
-    const bool trace = env_once("GTA_B200_TRACE", 0, &trace_slot, &trace_once) != 0;
-    const auto t_begin = std::chrono::steady_clock::now();
-    const size_t frame_elems = (size_t)j.natoms * j.in_dim, frame_bytes = frame_elems * sizeof(double);
-    s.f0 = f0; s.nf = nf;
-    // stage coordinates
-    const double* h_src;
-    if (j.frames) {
-        // gather of one heap block per frame (the reference's layout, extern/gkut/src/gkut_io.c:37) into the pinned
-        // chunk; at > 200k frames/s per GPU this is several GB/s of memcpy, so it is spread over the host cores
-        const int ht = j.host_threads > 0 ? j.host_threads : std::max(1u, std::thread::hardware_concurrency());
-#pragma omp parallel for schedule(static) num_threads(ht) if (nf >= 256)
-        for (int f = 0; f < nf; ++f) memcpy(s.h_in + (size_t)f * frame_elems, j.frames[f0 + f], frame_bytes);
-        h_src = s.h_in;
-    } else if (src_pinned) {
-        h_src = j.xyz + (size_t)f0 * frame_elems;              // caller's buffer is already page-locked
-    } else {
-        const int ht = j.host_threads > 0 ? j.host_threads : std::max(1u, std::thread::hardware_concurrency());
-        const long long blocks = std::max(1, std::min(ht, nf / 256));
-#pragma omp parallel for schedule(static) num_threads(ht) if (blocks > 1)
-        for (long long b = 0; b < blocks; ++b) {
-            const size_t lo = (size_t)nf * b / blocks, hi = (size_t)nf * (b + 1) / blocks;
-            memcpy(s.h_in + lo * frame_elems, j.xyz + ((size_t)f0 + lo) * frame_elems, frame_bytes * (hi - lo));
-        }
-        h_src = s.h_in;
-    }
-    if (trace) fprintf(stderr, "[gta_b200] chunk %d+%d: host staging %.1f ms\n", f0, nf, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
-    CK(cudaMemcpyAsync(s.d_in, h_src, frame_bytes * nf, cudaMemcpyHostToDevice, s.st));
-    if (j.box) {
-        memcpy(s.h_box, j.box + (size_t)f0 * j.box_stride, sizeof(double) * j.box_stride * nf);
-        CK(cudaMemcpyAsync(s.d_box, s.h_box, sizeof(double) * j.box_stride * nf, cudaMemcpyHostToDevice, s.st));
-    }
-    const int c = s.chunk;
-    gt::KParams p;
-    p.xyz = s.d_in; p.in_dim = j.in_dim; p.box = j.box ? s.d_box : nullptr; p.box_stride = j.box_stride;
-    p.by_off = (j.box_stride == 9) ? 4 : 1;
-    p.nframes = nf; p.natoms = j.natoms; p.cap = shp.cap; p.cap_p2 = shp.cap_p2; p.espace = j.espace; p.flags = j.flags;
-    p.area = s.d_out; p.area2d = s.d_out + c; p.areabox = s.d_out + 2 * (size_t)c;
-    p.status = s.d_st; p.ntri = s.d_st + c; p.ncorr = s.d_st + 2 * (size_t)c;
-    p.tri = j.tri ? s.d_tri : nullptr; p.tri_cap = j.tri_cap;
-    p.corr = j.corr ? s.d_corr : nullptr; p.corr_cap = j.corr_cap;
-    p.work = s.d_work; p.coop_nodes = coop_nodes_for(shp.threads); p.dbg = g_dbg; p.ws = gt::LpfWs{};
-    CK(cudaMemsetAsync(s.d_work, 0, sizeof(unsigned int), s.st));
-    CK(cudaMemsetAsync(s.d_st, 0, sizeof(int) * 3 * (size_t)c, s.st));
-    CK(cudaEventRecord(s.k0, s.st));
-    int rc = use_lpf(nf, shp) ? launch_lpf(p, shp, s.st) : launch(p, shp, s.st);
-    if (rc) return rc;
-    CK(cudaEventRecord(s.k1, s.st));
-    CK(cudaMemcpyAsync(s.h_out, s.d_out, sizeof(double) * 3 * (size_t)c, cudaMemcpyDeviceToHost, s.st));
-    CK(cudaMemcpyAsync(s.h_st, s.d_st, sizeof(int) * 3 * (size_t)c, cudaMemcpyDeviceToHost, s.st));
-    if (j.tri) CK(cudaMemcpyAsync(j.tri + (size_t)f0 * j.tri_cap * 3, s.d_tri, sizeof(int) * 3 * (size_t)j.tri_cap * nf, cudaMemcpyDeviceToHost, s.st));
-    if (j.corr) CK(cudaMemcpyAsync(j.corr + (size_t)f0 * j.corr_cap * 3, s.d_corr, sizeof(double) * 3 * (size_t)j.corr_cap * nf, cudaMemcpyDeviceToHost, s.st));
-    s.busy = true;
-    return GTA_B200_OK;
-}
-
-int run_job(Job j, int device, int nstreams) {
-    g_err.clear();
-    if (!have_device()) return fail(GTA_B200_E_NO_DEVICE, "no CUDA device: libgtessla_b200 has no CPU path");
-    if (j.nframes < 0 || j.natoms < 0 || (j.in_dim != 2 && j.in_dim != 3) || (!j.xyz && !j.frames))
-        return fail(GTA_B200_E_ARG, "bad argument");
-    if ((j.flags & GTA_B200_CORRECT) && (!j.box || !(j.espace > 0.0)))
-        return fail(GTA_B200_E_ARG, "-corr needs the box and espace > 0");
-    g_last_kernel_ms = 0.0; g_last_launches = 0;
-    if (j.nframes == 0) return GTA_B200_OK;
-    if (device >= 0) CK(cudaSetDevice(device));
-    CK(cudaGetDevice(&device));
-    j.max_points = gta_b200_max_points_for(j.box, j.box_stride, j.nframes, j.natoms, j.espace, j.flags);
-    Shape shp = shape_for(j.max_points, j.natoms);
-    if (shp.smem > (size_t)smem_limit() || gt::pool_edges(shp.cap) >= 32760)
-        return fail(GTA_B200_E_TOO_LARGE, "frame too large for the shared-memory kernel (see gta_b200_max_points)");
-
-    nstreams = std::max(1, std::min(nstreams <= 0 ? 3 : nstreams, 8));
-    const size_t frame_bytes = (size_t)j.natoms * j.in_dim * sizeof(double);
-    // chunk: enough frames for several waves of persistent CTAs, bounded to ~64 MB of coordinates
-    long long chunk = (j.nframes + nstreams - 1) / nstreams;
-    chunk = std::min<long long>(chunk, std::max<long long>(256, (64ll << 20) / (long long)std::max<size_t>(frame_bytes, 1)));
-    chunk = std::max<long long>(chunk, 1);
-    if (use_lpf(j.nframes, shp)) {
-        // throughput path: a launch lasts at least one frame's critical path (~2,800 rounds), so launches want >= 10^4
-        // frames; up to three chunks in flight so that the copies of one overlap the kernels of another
-        const long long target = std::max<long long>(4096, std::min<long long>(25000, (1ll << 30) / (long long)std::max<size_t>(frame_bytes, 1)));
-        long long nchunks = (j.nframes + target - 1) / target;
-        // a batch of one or two launches' worth that has to be staged by the host first (per-frame blocks, pageable memory):
-        // cut it in pieces of >= chunk_min frames, so that the staging of the second piece runs under the kernels of the first
-        // (measured on one GPU, 12,500 / 25,000 frames in per-frame blocks: 227 -> 238 k and 242 -> 264 k frames/s; from a pinned
-        // buffer, where only the copy can overlap, one launch is as fast or faster: 268 k against 260 k)
-        static int cm_slot; static std::once_flag cm_once;
-        const long long chunk_min = std::max(1024, env_once("GTA_B200_CHUNK_MIN", 6000, &cm_slot, &cm_once));
-        if (j.frames || !src_pinned) nchunks = std::max(nchunks, std::min<long long>(3, j.nframes / chunk_min));
-        chunk = (j.nframes + nchunks - 1) / nchunks;
-        nstreams = (int)std::min<long long>(3, nchunks);
-    }
-    if (j.tri) {                                              // (parity tests) triangle lists: bound the device buffer of a chunk to 512 MB
-        const long long fit = std::max<long long>(1, (512ll << 20) / (12ll * std::max(j.tri_cap, 1)));
-        if (chunk > fit) { chunk = fit; nstreams = std::min(nstreams, 2); }
-    }
     bool src_pinned = false;
     if (j.xyz) {
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, j.xyz) == cudaSuccess) src_pinned = (at.type == cudaMemoryTypeHost);
         else cudaGetLastError();
+    }
+    nstreams = std::max(1, std::min(nstreams <= 0 ? 3 : nstreams, 8));
+    const size_t frame_bytes = (size_t)j.natoms * j.in_dim * sizeof(double);
+    // chunk: enough frames for several waves of persistent CTAs, bounded to ~64 MB of coordinates
+    long long chunk = (j.nframes + nstreams - 1) / nstreams;
+    chunk = std::min<long long>(chunk, std::max<long long>(256, (64ll << 20) / (long long)std::max<size_t>(frame_bytes, 1)));
+    chunk = std::max<long long>(chunk, 1);
+    if (use_lpf(j.nframes, shp)) {
+        // throughput path: a launch lasts at least one frame's critical path (~2,800 rounds), so launches want >= 10^4
+        // frames; up to three chunks in flight so that the copies of one overlap the kernels of another
+        const long long target = std::max<long long>(4096, std::min<long long>(25000, (1ll << 30) / (long long)std::max<size_t>(frame_bytes, 1)));
+        long long nchunks = (j.nframes + target - 1) / target;
+        // a batch of one or two launches' worth that has to be staged by the host first (per-frame blocks, pageable memory):
+        // cut it in pieces of >= chunk_min frames, so that the staging of the second piece runs under the kernels of the first
+        // (measured on one GPU, 12,500 / 25,000 frames in per-frame blocks: 227 -> 238 k and 242 -> 264 k frames/s; from a pinned
+        // buffer, where only the copy can overlap, one launch is as fast or faster: 268 k against 260 k)
+        static int cm_slot; static std::once_flag cm_once;
+        const long long chunk_min = std::max(1024, env_once("GTA_B200_CHUNK_MIN", 6000, &cm_slot, &cm_once));
+        if (j.frames || !src_pinned) nchunks = std::max(nchunks, std::min<long long>(3, j.nframes / chunk_min));
+        chunk = (j.nframes + nchunks - 1) / nchunks;
+        nstreams = (int)std::min<long long>(3, nchunks);
+    }
+    if (j.tri) {                                              // (parity tests) triangle lists: bound the device buffer of a chunk to 512 MB
+        const long long fit = std::max<long long>(1, (512ll << 20) / (12ll * std::max(j.tri_cap, 1)));
+        if (chunk > fit) { chunk = fit; nstreams = std::min(nstreams, 2); }
     }
     if (device < 0 || device >= 64) return fail(GTA_B200_E_ARG, "device index out of range");
     SlotCache& g_cache = g_caches[device];
