@@ -151,7 +151,7 @@ std::mutex g_lpf_mu;
 std::mutex g_lpf_launch_mu[64];          // one launch sequence at a time per device: they share the device's workspace
 
 // Environment knobs, read once (experiments; the defaults are the measured best).
-struct LpfEnv { int threshold, slots, threads, carve, split, fslots; };
+struct LpfEnv { int threshold, slots, threads, carve, split, fslots, defer, defer_phases, defer_rounds; };
 const LpfEnv& lpf_env() {
     static LpfEnv e;
     static std::once_flag once;
@@ -163,6 +163,9 @@ const LpfEnv& lpf_env() {
         e.carve = geti("GTA_B200_LPF_CARVE", 0);
         e.split = geti("GTA_B200_LPF_SPLIT", -1);
         e.fslots = geti("GTA_B200_LPF_FSLOTS", 0);
+        e.defer = geti("GTA_B200_LPF_DEFER", 14);
+        e.defer_phases = geti("GTA_B200_LPF_DEFER_PHASES", (1 << gt::LP_LEAF) | (1 << gt::LP_TINIT));
+        e.defer_rounds = geti("GTA_B200_LPF_DEFER_ROUNDS", 3);
     });
     return e;
 }
@@ -250,7 +253,7 @@ int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st) {
     if (tev) CK(cudaEventRecord(tev[1], st));
     // 2. walkers
     gt::LpfParams lp; lp.ws = ws.ws; lp.nframes = p.nframes; lp.counter = ws.counter; lp.dbg = p.dbg ? p.dbg + 32 : nullptr;
-    lp.split = split; lp.fslots = FS;
+    lp.split = split; lp.fslots = FS; lp.defer_below = env.defer; lp.defer_phases = env.defer_phases; lp.defer_rounds = env.defer_rounds;
     CK(cudaMemsetAsync(ws.counter, 0, 4, st));
     // Which build of the kernel? Without stage A' of the predicates (gt_predicates.cuh) the steps fit 128 registers and
     // 16 warps per SM: best when the FP filter decides everything, as it does on real coordinates (cfg 3). With stage A',
