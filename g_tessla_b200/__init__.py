@@ -5,5 +5,6 @@ include/delaunay_tri.h) built from g_tessla_b200/csrc/ for sm_100a.  This packag
 Python binding used by tests/ and bench.py; it never imports oracle/ and has no CPU path.
 """
 from .api import (  # noqa: F401
-    GTA_CORRECT, GTA_2D, Tessellator, lib, lib_path, tessellate, triangulate, triangulate_large, GtaError,
+    GTA_CORRECT, GTA_2D, PATH_AUTO, PATH_DC, PATH_STAR, Tessellator, lib, lib_path, tessellate, triangulate, triangulate_large, GtaError,
+    set_path, last_fallback_frames, stage_ms, star_counters,
 )

@@ -63,6 +63,11 @@ def lib() -> C.CDLL:
     L.gta_b200_fp64_peak_tflops.argtypes = [C.c_int]
     L.gta_b200_stage_ms.argtypes = [C.c_int, _dp, _dp, _dp, _ip]
     L.gta_b200_stage_reset.argtypes = [C.c_int]
+    L.gta_b200_stage_ms4.argtypes = [C.c_int, _dp, _ip]
+    L.gta_b200_last_fallback_frames.argtypes = [C.c_int]
+    L.gta_b200_last_fallback_frames.restype = C.c_longlong
+    L.gta_b200_set_path.argtypes = [C.c_int]
+    L.gta_b200_star_counters.argtypes = [C.c_int, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.c_int]
     L.gta_b200_tessellate_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_uint, C.c_int, C.c_int,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gta_b200_surface_area_large.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_int, _dp, _dp, _ip, _ip]
@@ -169,14 +174,35 @@ def incircle_signs(pts, device=-1):
 
 
 def stage_ms(device=-1, reset=False):
-    """Per-kernel device milliseconds of the throughput path since the last reset: dict(prepass, walk, area, launches)."""
+    """Per-kernel device milliseconds of the batched path since the last reset: dict(star, prepass, walk, area, launches)."""
     L = lib()
     if reset:
         _check(L.gta_b200_stage_reset(int(device)))
         return None
-    a, b, c, n = C.c_double(), C.c_double(), C.c_double(), C.c_int()
-    _check(L.gta_b200_stage_ms(int(device), C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
-    return dict(prepass=a.value, walk=b.value, area=c.value, launches=n.value)
+    t, n = (C.c_double * 4)(), C.c_int()
+    _check(L.gta_b200_stage_ms4(int(device), t, C.byref(n)))
+    return dict(star=t[0], prepass=t[1], walk=t[2], area=t[3], launches=n.value)
+
+
+PATH_AUTO, PATH_DC, PATH_STAR = 0, 1, 2
+
+
+def set_path(mode):
+    """Engine of the batched calls (include/gta_b200.h): PATH_AUTO, PATH_DC (divide and conquer only), PATH_STAR (stars also
+    when triangle lists are asked for). Returns the previous mode."""
+    return lib().gta_b200_set_path(int(mode))
+
+
+def star_counters(device=-1, reset=False):
+    """(frames certified by their stars, frames handed to the divide-and-conquer engine) on `device` since the last reset."""
+    a, b = C.c_ulonglong(), C.c_ulonglong()
+    _check(lib().gta_b200_star_counters(int(device), C.byref(a), C.byref(b), 1 if reset else 0))
+    return a.value, b.value
+
+
+def last_fallback_frames(device=-1):
+    """Frames the most recent sampled star launch handed to the divide-and-conquer engine (-1: no star launch yet)."""
+    return int(lib().gta_b200_last_fallback_frames(int(device)))
 
 
 class Tessellator:

@@ -20,6 +20,7 @@
 #include "gta_kernel.cuh"
 #include "gta_lpf.cuh"
 #include "gta_prepass.cuh"
+#include "gta_star.cuh"
 
 namespace {
 
@@ -136,14 +137,20 @@ int occupancy_for(const Shape& s) {
 // ---- throughput path (gta_lpf.cuh): workspace cache (one per device, only ever grows) and launcher
 // One of the device's two workspaces: consecutive launches (on different streams) alternate between them, so that the
 // pre-pass of launch k+1 fills the SMs the tail of launch k's walker kernel leaves idle.
-struct LpfSet { gt::LpfWs ws{}; size_t frames = 0; int cap = 0, cap_e = 0; unsigned int* counter = nullptr; cudaEvent_t done = nullptr; };
+struct LpfSet {
+    gt::LpfWs ws{}; size_t frames = 0; int cap = 0, cap_e = 0; unsigned int* counter = nullptr; cudaEvent_t done = nullptr;
+    int* fb_list = nullptr; unsigned int* fb_count = nullptr;        // star path: the frames of the launch that need this workspace
+};
 struct LpfCache {
     LpfSet set[2]; unsigned turn = 0;
     cudaEvent_t last_done = nullptr;
     // feedback for the choice of kernel variant (launch_lpf): predicates the FP filter left undecided, as counted on the device
     unsigned long long* undecided_h = nullptr;      // pinned; the device's running count after the last launch
     unsigned long long undecided_seen = 0; int last_frames = 0; bool pending = false, degenerate = false;
-    // stage timers: four events (before pre-pass, before walkers, before areas, end) per launch since gta_b200_stage_reset
+    // feedback for the star path: how many frames of the last star launch fell back to the divide-and-conquer pipeline
+    unsigned int* fb_h = nullptr; bool fb_pending = false; int fb_frames = 0, star_skip = 0, skip_natoms = -1, skip_cap = -1; cudaEvent_t fb_done = nullptr;
+    unsigned long long* star_counters = nullptr;     // device: [0] frames certified by their stars, [1] frames handed to the divide-and-conquer pipeline
+    // stage timers: five events (start, after stars, after pre-pass, after walkers, after areas) per launch since gta_b200_stage_reset
     std::vector<cudaEvent_t> ev; size_t ev_used = 0;
 };
 LpfCache g_lpf[64];
@@ -178,6 +185,19 @@ int lpf_threshold() {
     if (v == -2) { v = lpf_env().threshold; g_lpf_threshold.store(v); }
     return v;
 }
+// Which engine serves the batched calls: 0 = automatic (star path unless triangle lists are wanted: their emission order is
+// the divide and conquer's), 1 = divide and conquer only, 2 = star path always. GTA_B200_PATH overrides the default.
+std::atomic<int> g_path{-1};
+int path_mode() {
+    int v = g_path.load();
+    if (v < 0) { static int env; static std::once_flag once; v = env_once("GTA_B200_PATH", 0, &env, &once); v = (v < 0 || v > 2) ? 0 : v; g_path.store(v); }
+    return v;
+}
+bool use_star(const gt::KParams& p, const Shape& s) {
+    const int m = path_mode();
+    if (m == 1 || s.cap > 4000 || gt::StarSmem(s.cap, p.natoms, p.in_dim).total > (size_t)smem_limit()) return false;
+    return m == 2 || p.tri == nullptr;
+}
 bool use_lpf(int nframes, const Shape& s) { return lpf_threshold() > 0 && nframes >= lpf_threshold() && s.cap < 4000; }
 
 // Most frames one launch of the throughput path takes: bounds the workspace (32 B per point + 16 B per edge, per frame).
@@ -193,23 +213,56 @@ int lpf_ensure(int dev, int which, size_t frames, int cap, int cap_e, LpfCache**
         // grow only: keep the larger of the old and the new request in every dimension
         frames = std::max(frames, c.frames); cap = std::max(cap, c.cap); cap_e = std::max(cap_e, c.cap_e);
         if (c.done) cudaEventSynchronize(c.done);
-        cudaFree(c.ws.pt); cudaFree(c.ws.rec); cudaFree(c.ws.n); cudaFree(c.ws.st); cudaFree(c.ws.err);
-        c.ws = gt::LpfWs{}; c.frames = 0; c.cap = c.cap_e = 0;
+        cudaFree(c.ws.pt); cudaFree(c.ws.rec); cudaFree(c.ws.n); cudaFree(c.ws.st); cudaFree(c.ws.err); cudaFree(c.fb_list);
+        c.ws = gt::LpfWs{}; c.frames = 0; c.cap = c.cap_e = 0; c.fb_list = nullptr;
         CK(cudaMalloc((void**)&c.ws.pt, sizeof(gt::LPt) * frames * cap));
         CK(cudaMalloc((void**)&c.ws.rec, sizeof(gt::LRec) * (frames + 1) * 2 * (size_t)cap_e));      // (+1: slack behind the last frame)
         CK(cudaMalloc((void**)&c.ws.n, 4 * frames)); CK(cudaMalloc((void**)&c.ws.st, 4 * frames)); CK(cudaMalloc((void**)&c.ws.err, 4 * frames));
+        CK(cudaMalloc((void**)&c.fb_list, 4 * frames));
         if (!c.counter) CK(cudaMalloc((void**)&c.counter, 4));
+        if (!c.fb_count) CK(cudaMalloc((void**)&c.fb_count, 4));
         if (!c.done) CK(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
         c.ws.cap = cap; c.ws.cap_e = cap_e; c.frames = frames; c.cap = cap; c.cap_e = cap_e;
     }
     if (!cc.undecided_h) { CK(cudaMallocHost((void**)&cc.undecided_h, 8)); *cc.undecided_h = 0; }
+    if (!cc.fb_h) { CK(cudaMallocHost((void**)&cc.fb_h, 4)); *cc.fb_h = 0; CK(cudaEventCreateWithFlags(&cc.fb_done, cudaEventDisableTiming)); }
+    if (!cc.star_counters) { CK(cudaMalloc((void**)&cc.star_counters, 32)); CK(cudaMemset(cc.star_counters, 0, 32)); }
     *out = &cc;
     return GTA_B200_OK;
 }
 
 int launch(const gt::KParams& p, const Shape& s, cudaStream_t st);
 
-int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st) {
+// The star kernel (gta_star.cuh): one CTA per frame, a thread per point. Frames it does not certify go to ws.fb_list.
+int launch_star(const gt::KParams& p, const Shape& s, int* fb_list, unsigned int* fb_count, unsigned long long* counters, cudaStream_t st) {
+    gt::StarParams sp; sp.k = p; sp.fb_list = fb_list; sp.fb_count = fb_count; sp.counters = counters;
+    const size_t smem = gt::StarSmem(s.cap, p.natoms, p.in_dim).total;
+    if (smem > (size_t)smem_limit()) return fail(GTA_B200_E_TOO_LARGE, "frame too large for the star kernel");
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    auto go = [&](auto kern, int threads) -> int {
+        int occ = 0;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+        if (occ < 1) return fail(GTA_B200_E_TOO_LARGE, "star kernel does not fit on an SM");
+        const int grid = std::max(1, std::min(p.nframes, occ * sms));
+        kern<<<grid, threads, smem, st>>>(sp);
+        CK(cudaGetLastError());
+        return GTA_B200_OK;
+    };
+    static int env_t; static std::once_flag once;            // experiments: GTA_B200_STAR_THREADS = 64 | 128 | 256 | 384
+    const int t = env_once("GTA_B200_STAR_THREADS", 0, &env_t, &once);
+    const int threads = t ? t : (s.cap <= 160 ? 64 : (s.cap <= 512 ? 128 : 256));
+    switch (threads) {
+        case 64: return go(gt::star_kernel<64, 8>, 64);
+        case 128: return go(gt::star_kernel<128, 4>, 128);
+        case 384: return go(gt::star_kernel<384, 1>, 384);
+        default: return go(gt::star_kernel<256, 2>, 256);
+    }
+}
+
+int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st, bool star = false) {
     int dev = 0, sms = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -241,18 +294,39 @@ int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st) {
     CK(cudaStreamWaitEvent(st, ws.done, 0));
     // stage timers (gta_b200_stage_ms): events on the launching stream around each of the three kernels
     cudaEvent_t* tev = nullptr;
-    if (c->ev_used + 4 <= 4 * 64) {
-        while (c->ev.size() < c->ev_used + 4) { cudaEvent_t e; CK(cudaEventCreate(&e)); c->ev.push_back(e); }
-        tev = c->ev.data() + c->ev_used; c->ev_used += 4;
+    if (c->ev_used + 5 <= 5 * 64) {
+        while (c->ev.size() < c->ev_used + 5) { cudaEvent_t e; CK(cudaEventCreate(&e)); c->ev.push_back(e); }
+        tev = c->ev.data() + c->ev_used; c->ev_used += 5;
         CK(cudaEventRecord(tev[0], st));
     }
+    // 0. star path: every frame it certifies is finished by this launch; the others are listed for the three kernels below.
+    // Input that keeps falling back (lattices: every frame has cocircular ties) skips the stars for a while.
+    // (automatic mode only, and only for the trajectory shape that fell back)
+    if (star && c->fb_pending && cudaEventQuery(c->fb_done) == cudaSuccess) {
+        c->fb_pending = false;
+        if ((long long)*c->fb_h * 2 > (long long)c->fb_frames) { c->star_skip = 16; c->skip_natoms = p.natoms; c->skip_cap = s.cap; }
+    }
+    if (star && path_mode() == 0 && c->star_skip > 0 && c->skip_natoms == p.natoms && c->skip_cap == s.cap) { --c->star_skip; star = false; }
+    if (star) {
+        CK(cudaMemsetAsync(ws.fb_count, 0, 4, st));
+        p.ws = gt::LpfWs{};
+        rc = launch_star(p, s, ws.fb_list, ws.fb_count, c->star_counters, st);
+        if (rc) return rc;
+        if (!c->fb_pending) {
+            CK(cudaMemcpyAsync(c->fb_h, ws.fb_count, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(c->fb_done, st));
+            c->fb_pending = true; c->fb_frames = p.nframes;
+        }
+        p.list = ws.fb_list; p.list_count = ws.fb_count;
+    }
+    if (tev) CK(cudaEventRecord(tev[1], st));
     // 1. pre-pass (load, -corr, sort) into the workspace
     p.ws = ws.ws;
     rc = launch_prepass(p, s, st);
     if (rc) return rc;
-    if (tev) CK(cudaEventRecord(tev[1], st));
+    if (tev) CK(cudaEventRecord(tev[2], st));
     // 2. walkers
-    gt::LpfParams lp; lp.ws = ws.ws; lp.nframes = p.nframes; lp.counter = ws.counter; lp.dbg = p.dbg ? p.dbg + 32 : nullptr;
+    gt::LpfParams lp; lp.ws = ws.ws; lp.nframes = p.nframes; lp.nframes_dev = p.list_count; lp.counter = ws.counter; lp.dbg = p.dbg ? p.dbg + 32 : nullptr;
     lp.split = split; lp.fslots = FS; lp.defer_below = env.defer; lp.defer_phases = env.defer_phases; lp.defer_rounds = env.defer_rounds;
     CK(cudaMemsetAsync(ws.counter, 0, 4, st));
     // Which build of the kernel? Without stage A' of the predicates (gt_predicates.cuh) the steps fit 128 registers and
@@ -280,13 +354,13 @@ int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st) {
         else rc = go(gt::lpf_wave_kernel<512, false>, 512);
         if (rc) return rc;
     }
-    if (tev) CK(cudaEventRecord(tev[2], st));
+    if (tev) CK(cudaEventRecord(tev[3], st));
     // 3. areas
-    gt::LpfAreaParams ap; ap.ws = ws.ws; ap.nframes = p.nframes; ap.natoms = p.natoms; ap.flags = p.flags;
+    gt::LpfAreaParams ap; ap.ws = ws.ws; ap.nframes = p.nframes; ap.natoms = p.natoms; ap.flags = p.flags; ap.list = p.list; ap.list_count = p.list_count;
     ap.area = p.area; ap.area2d = p.area2d; ap.status = p.status; ap.ntri = p.ntri; ap.tri = p.tri; ap.tri_cap = p.tri_cap;
     gt::lpf_area_kernel<<<(p.nframes + 3) / 4, 128, 0, st>>>(ap);
     CK(cudaGetLastError());
-    if (tev) CK(cudaEventRecord(tev[3], st));
+    if (tev) CK(cudaEventRecord(tev[4], st));
     CK(cudaMemcpyFromSymbolAsync(c->undecided_h, gt::g_xcalls, 8, 0, cudaMemcpyDeviceToHost, st));
     c->last_frames = p.nframes; c->pending = true;
     CK(cudaEventRecord(ws.done, st));
@@ -316,21 +390,64 @@ int gta_b200_stage_reset(int device) {
     g_lpf[device].ev_used = 0;
     return GTA_B200_OK;
 }
-int gta_b200_stage_ms(int device, double* prepass_ms, double* walk_ms, double* area_ms, int* launches) {
+static int stage_sum(int device, double t[4], int* launches) {
     if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return fail(GTA_B200_E_CUDA, "cudaGetDevice");
     if (device < 0 || device >= 64) return fail(GTA_B200_E_ARG, "device index out of range");
     std::lock_guard<std::mutex> launch_lock(g_lpf_launch_mu[device]);
     LpfCache& c = g_lpf[device];
-    double t[3] = {0.0, 0.0, 0.0};
-    for (size_t i = 0; i + 4 <= c.ev_used; i += 4) {
-        CK(cudaEventSynchronize(c.ev[i + 3]));
-        for (int k = 0; k < 3; ++k) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c.ev[i + k], c.ev[i + k + 1])); t[k] += ms; }
+    t[0] = t[1] = t[2] = t[3] = 0.0;
+    for (size_t i = 0; i + 5 <= c.ev_used; i += 5) {
+        CK(cudaEventSynchronize(c.ev[i + 4]));
+        for (int k = 0; k < 4; ++k) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c.ev[i + k], c.ev[i + k + 1])); t[k] += ms; }
     }
-    if (prepass_ms) *prepass_ms = t[0];
-    if (walk_ms) *walk_ms = t[1];
-    if (area_ms) *area_ms = t[2];
-    if (launches) *launches = (int)(c.ev_used / 4);
+    if (launches) *launches = (int)(c.ev_used / 5);
     return GTA_B200_OK;
+}
+int gta_b200_stage_ms(int device, double* prepass_ms, double* walk_ms, double* area_ms, int* launches) {
+    double t[4];
+    const int rc = stage_sum(device, t, launches);
+    if (rc) return rc;
+    if (prepass_ms) *prepass_ms = t[1];
+    if (walk_ms) *walk_ms = t[2];
+    if (area_ms) *area_ms = t[3];
+    return GTA_B200_OK;
+}
+// the same with the star kernel's time in front: out4 = {stars, pre-pass, walkers, areas} in ms
+int gta_b200_stage_ms4(int device, double* out4, int* launches) {
+    double t[4];
+    const int rc = stage_sum(device, t, launches);
+    if (rc) return rc;
+    if (out4) for (int k = 0; k < 4; ++k) out4[k] = t[k];
+    return GTA_B200_OK;
+}
+// running totals of the star kernel on `device` since the last reset (waits for the device): frames certified / handed over
+int gta_b200_star_counters(int device, unsigned long long* certified, unsigned long long* fallback, int reset) {
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return fail(GTA_B200_E_CUDA, "cudaGetDevice");
+    if (device < 0 || device >= 64) return fail(GTA_B200_E_ARG, "device index out of range");
+    std::lock_guard<std::mutex> launch_lock(g_lpf_launch_mu[device]);
+    LpfCache& c = g_lpf[device];
+    unsigned long long v[2] = {0, 0};
+    if (c.star_counters) {
+        int cur = 0; CK(cudaGetDevice(&cur));
+        CK(cudaSetDevice(device));
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(v, c.star_counters, 16, cudaMemcpyDeviceToHost));
+        if (reset) CK(cudaMemset(c.star_counters, 0, 16));
+        CK(cudaSetDevice(cur));
+    }
+    if (certified) *certified = v[0];
+    if (fallback) *fallback = v[1];
+    return GTA_B200_OK;
+}
+// frames the last star launch on `device` handed to the divide-and-conquer pipeline (waits for that launch), < 0: none seen
+long long gta_b200_last_fallback_frames(int device) {
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return -1;
+    if (device < 0 || device >= 64) return -1;
+    std::lock_guard<std::mutex> launch_lock(g_lpf_launch_mu[device]);
+    LpfCache& c = g_lpf[device];
+    if (!c.fb_h || !c.fb_done) return -1;
+    if (cudaEventSynchronize(c.fb_done) != cudaSuccess) return -1;
+    return (long long)*c.fb_h;
 }
 int gta_b200_last_launches(void) { return g_last_launches; }
 
@@ -338,6 +455,12 @@ int gta_b200_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
+}
+
+int gta_b200_set_path(int mode) {
+    const int old = path_mode();
+    g_path.store(mode < 0 || mode > 2 ? 0 : mode);
+    return old;
 }
 
 int gta_b200_set_batch_threshold(int min_frames) {
@@ -412,12 +535,13 @@ int gta_b200_tessellate_device(const double* d_xyz, int in_dim, const double* d_
     p.corr = d_corr; p.corr_cap = corr_cap; p.ncorr = d_ncorr;
     p.work = d_work; p.coop_nodes = coop_nodes_for(s.threads); p.dbg = g_dbg; p.ws = gt::LpfWs{};
     CK(cudaMemsetAsync(d_work, 0, sizeof(unsigned int), st));
-    const bool lpf = use_lpf(nframes, s);
+    const bool star = use_star(p, s);
+    const bool lpf = star || use_lpf(nframes, s);
     if (!lpf) { g_last_launches = 1; return launch(p, s, st); }                      // the fused kernel
     // throughput path: pre-pass + walker kernel + area kernel per launch; batches beyond one launch's worth are split evenly
     const long long per_launch = lpf_frames_per_launch(s);
     const long long parts = (nframes + per_launch - 1) / per_launch;
-    g_last_launches = 3 * (int)parts;
+    g_last_launches = (star ? 4 : 3) * (int)parts;
     for (long long k = 0; k < parts; ++k) {
         const long long f0 = (long long)nframes * k / parts, f1 = (long long)nframes * (k + 1) / parts;
         gt::KParams q = p;
@@ -433,7 +557,7 @@ int gta_b200_tessellate_device(const double* d_xyz, int in_dim, const double* d_
         if (d_corr) q.corr = d_corr + (size_t)f0 * corr_cap * 3;
         if (d_ncorr) q.ncorr = d_ncorr + f0;
         if (k) CK(cudaMemsetAsync(d_work, 0, sizeof(unsigned int), st));
-        const int rc = launch_lpf(q, s, st);
+        const int rc = launch_lpf(q, s, st, star);
         if (rc) return rc;
     }
     return GTA_B200_OK;
@@ -576,7 +700,8 @@ int submit(Slot& s, const Job& j, const Shape& shp, int f0, int nf, bool src_pin
     CK(cudaMemsetAsync(s.d_work, 0, sizeof(unsigned int), s.st));
     CK(cudaMemsetAsync(s.d_st, 0, sizeof(int) * 3 * (size_t)c, s.st));
     CK(cudaEventRecord(s.k0, s.st));
-    int rc = use_lpf(nf, shp) ? launch_lpf(p, shp, s.st) : launch(p, shp, s.st);
+    const bool star = use_star(p, shp);
+    int rc = (star || use_lpf(nf, shp)) ? launch_lpf(p, shp, s.st, star) : launch(p, shp, s.st);
     if (rc) return rc;
     CK(cudaEventRecord(s.k1, s.st));
     CK(cudaMemcpyAsync(s.h_out, s.d_out, sizeof(double) * 3 * (size_t)c, cudaMemcpyDeviceToHost, s.st));
@@ -615,7 +740,17 @@ int run_job(Job j, int device, int nstreams) {
     long long chunk = (j.nframes + nstreams - 1) / nstreams;
     chunk = std::min<long long>(chunk, std::max<long long>(256, (64ll << 20) / (long long)std::max<size_t>(frame_bytes, 1)));
     chunk = std::max<long long>(chunk, 1);
-    if (use_lpf(j.nframes, shp)) {
+    gt::KParams probe; probe.natoms = j.natoms; probe.in_dim = j.in_dim; probe.tri = j.tri;
+    const bool star = use_star(probe, shp);
+    if (star) {
+        // star path: a launch has no long critical path (a frame is a CTA for ~0.1 ms), so the chunks are sized for the overlap
+        // of the copies with the kernels: several chunks of a few thousand frames in flight on three streams
+        static int sc_slot; static std::once_flag sc_once;
+        const long long target = std::max(256, env_once("GTA_B200_STAR_CHUNK", 8192, &sc_slot, &sc_once));
+        const long long nchunks = std::max<long long>(1, (j.nframes + target - 1) / target);
+        chunk = (j.nframes + nchunks - 1) / nchunks;
+        nstreams = (int)std::min<long long>(3, nchunks);
+    } else if (use_lpf(j.nframes, shp)) {
         // throughput path: a launch lasts at least one frame's critical path (~2,800 rounds), so launches want >= 10^4
         // frames; up to three chunks in flight so that the copies of one overlap the kernels of another
         const long long target = std::max<long long>(4096, std::min<long long>(25000, (1ll << 30) / (long long)std::max<size_t>(frame_bytes, 1)));
@@ -652,7 +787,7 @@ int run_job(Job j, int device, int nstreams) {
         if (rc) break;
         int nf = std::min<long long>(chunk, j.nframes - f0);
         rc = submit(s, j, shp, f0, nf, src_pinned);
-        launches += use_lpf(nf, shp) ? 3 : 1;                            // pre-pass + walker kernel + area kernel, or the fused kernel
+        launches += star ? 4 : (use_lpf(nf, shp) ? 3 : 1);                // (stars +) pre-pass + walker kernel + area kernel, or the fused kernel
     }
     for (int i = 0; i < nstreams; ++i) { int r2 = drain(g_cache.slots[i], j, &kms); if (rc == GTA_B200_OK) rc = r2; }
     g_last_kernel_ms = kms; g_last_launches = launches;

@@ -44,6 +44,9 @@ struct KParams {
     unsigned long long* dbg;                   // phase timers (GT_PHASE_TIMING builds), else unused
     int coop_nodes;                            // levels with at most this many nodes use warp-cooperative merges
     LpfWs ws;                                  // ws.pt != nullptr: pre-pass only (load, -corr, sort), frames go to the workspace
+    // Divide-and-conquer pipeline as the fallback of the star path (gta_star.cuh): work on the frames list[0 .. *list_count)
+    // of the batch instead of all of them; workspace slot i holds frame list[i], results go to the frame's own index.
+    const int* list = nullptr; const unsigned int* list_count = nullptr;
 };
 
 __host__ __device__ inline int pool_edges(int cap) { return 3 * cap + 64; }

@@ -18,6 +18,7 @@ namespace gt {
 struct LpfParams {
     LpfWs ws;
     int nframes;
+    const unsigned int* nframes_dev;       // != nullptr: the number of frames in the workspace is read from the device (fallback of the star path)
     unsigned int* counter;                 // next frame of the batch to hand out
     int split;                             // a frame starts as 2^split subtree walkers (fewer if it has too few points)
     int fslots;                            // frames a block can have in flight
@@ -124,7 +125,7 @@ __device__ __noinline__ int lpf_admit(const LpfParams& p, uint32_t* st, LMeta* m
         if (fs >= 0) {
             for (;;) {
                 const int fr = (int)atomicAdd(p.counter, 1u);
-                if (fr >= p.nframes) { *exhausted_next = 1; atomicOr(&fs_mask[fs >> 5], 1u << (fs & 31)); fs = -1; break; }
+                if (fr >= (p.nframes_dev ? (int)*p.nframes_dev : p.nframes)) { *exhausted_next = 1; atomicOr(&fs_mask[fs >> 5], 1u << (fs & 31)); fs = -1; break; }
                 const int n = p.ws.n[fr];
                 if (p.ws.st[fr] != 0 || n < 2) continue;          // rejected by the pre-pass: the area kernel reports it
                 fs_frame[fs] = fr; fs_n[fs] = n;
@@ -296,12 +297,14 @@ __global__ void __launch_bounds__(THREADS, 1) lpf_wave_kernel(const LpfParams p,
 // include/gta_tri.h:91-99), fixed-order warp reduction.
 struct LpfAreaParams {
     LpfWs ws; int nframes; int natoms; unsigned flags;
+    const int* list; const unsigned int* list_count;      // fallback of the star path: workspace slot i = frame list[i] of the batch
     double* area; double* area2d; int* status; int* ntri; int* tri; int tri_cap;
 };
 __global__ void __launch_bounds__(128) lpf_area_kernel(const LpfAreaParams p) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= p.nframes) return;
-    const int fr = warp;
+    if (warp >= (p.list ? (int)*p.list_count : p.nframes)) return;
+    const int fr = warp;                                                   // workspace slot
+    const int ofr = p.list ? p.list[warp] : warp;                          // frame of the batch the results belong to
     int st = p.ws.st[fr];
     const uint32_t e = p.ws.err[fr];
     if (e & GT_ERR_POOL) st |= GTA_B200_ST_POOL;
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__(128) lpf_area_kernel(const LpfAreaParams p) {
             }
             if (i < f.n) {
                 const LPt pi = f.pt[i]; const double zi = pi.z;
-                int* out = p.tri ? p.tri + ((size_t)fr * p.tri_cap) * 3 : nullptr;
+                int* out = p.tri ? p.tri + ((size_t)ofr * p.tri_cap) * 3 : nullptr;
                 mine += (unsigned)lf_vertex_triangles_pts(f, i, pi, [&](int, int, const LPt& p1, const LPt& p2) {
                     a3 += tri_area3(pi.x, pi.y, zi, p1.x, p1.y, p1.z, p2.x, p2.y, p2.z);
                     if (want2d) a2 += tri_area3(pi.x, pi.y, 0.0, p1.x, p1.y, 0.0, p2.x, p2.y, 0.0);
@@ -343,10 +346,10 @@ __global__ void __launch_bounds__(128) lpf_area_kernel(const LpfAreaParams p) {
     for (int o = 16; o > 0; o >>= 1) { a3 += __shfl_down_sync(0xffffffffu, a3, o); a2 += __shfl_down_sync(0xffffffffu, a2, o); }
     if (lane == 0) {
         if (st & ~GTA_B200_ST_TOO_FEW_POINTS) { a3 = __longlong_as_double(0x7ff8000000000000ll); a2 = a3; }
-        if (p.area) p.area[fr] = a3;
-        if (p.area2d && (p.flags & GTA_B200_2D)) p.area2d[fr] = a2;
-        if (p.status) p.status[fr] = st;
-        if (p.ntri) p.ntri[fr] = st ? 0 : (int)total;
+        if (p.area) p.area[ofr] = a3;
+        if (p.area2d && (p.flags & GTA_B200_2D)) p.area2d[ofr] = a2;
+        if (p.status) p.status[ofr] = st;
+        if (p.ntri) p.ntri[ofr] = st ? 0 : (int)total;
     }
 }
 

@@ -15,6 +15,7 @@
 //     up in one bucket falls back to the bitonic network (same result).
 #pragma once
 #include "gta_kernel.cuh"
+#include "gta_corr.cuh"
 
 namespace gt {
 
@@ -92,18 +93,22 @@ __global__ void __launch_bounds__(T) prepass_kernel(const KParams p) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     const int first = blockIdx.x, stride = gridDim.x;
-    if (bulk && tid == 0 && first < p.nframes)
-        pp_bulk_load(psm + L.tile, p.xyz + (size_t)first * natoms * in_dim, frame_bytes, &mbar[0]);
+    // (fallback of the star path: the frames list[0 .. *list_count) of the batch; workspace slot = position in the list)
+    const int nwork = p.list ? (int)*p.list_count : p.nframes;
+    auto frame_of = [&](int i) -> int { return p.list ? p.list[i] : i; };
+    if (bulk && tid == 0 && first < nwork)
+        pp_bulk_load(psm + L.tile, p.xyz + (size_t)frame_of(first) * natoms * in_dim, frame_bytes, &mbar[0]);
 
     int it = 0;
-    for (int fr = first; fr < p.nframes; fr += stride, ++it) {
+    for (int wi = first; wi < nwork; wi += stride, ++it) {
+        const int fr = frame_of(wi);
         const int buf = it & 1;
         const double* tile = reinterpret_cast<const double*>(psm + L.tile + (size_t)buf * tile_bytes);
         // ---- the next frame's tile starts loading now (its buffer was last read two frames ago, before a barrier)
-        const int nxt = fr + stride;
-        if (bulk && tid == 0 && nxt < p.nframes) {
+        const int nxt = wi + stride;
+        if (bulk && tid == 0 && nxt < nwork) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            pp_bulk_load(psm + L.tile + (size_t)(buf ^ 1) * tile_bytes, p.xyz + (size_t)nxt * natoms * in_dim, frame_bytes, &mbar[buf ^ 1]);
+            pp_bulk_load(psm + L.tile + (size_t)(buf ^ 1) * tile_bytes, p.xyz + (size_t)frame_of(nxt) * natoms * in_dim, frame_bytes, &mbar[buf ^ 1]);
         }
 #ifdef GT_PHASE_TIMING
         long long tick_ = clock64();
@@ -129,144 +134,9 @@ __global__ void __launch_bounds__(T) prepass_kernel(const KParams p) {
         __syncthreads();
         PP_TICK(1);
 
-        // ------------------------------------------------------------ K0: -corr points (gta_tri.c:112-272; as gta_kernel.cuh)
+        // ------------------------------------------------------------ K0: -corr points (gta_tri.c:112-272; gta_corr.cuh)
         if (corr) {
-            const int nx = (int)(bx / p.espace), ny = (int)(by / p.espace);      // gta_tri.c:112-113
-            const bool boxok = isfinite(bx) && isfinite(by) && nx >= 0 && ny >= 0 && natoms >= 1;
-            const bool toomany = boxok && (nx > (1 << 20) || ny > (1 << 20));
-            const int ncorr = (boxok && !toomany) ? 4 + 2 * nx + 2 * ny : 0;
-            ncorr_out = ncorr;
-            const int K = ncorr + 4;                                             // 4 corners + 2(nx+1) + 2(ny+1) slots
-            if (!boxok) { if (tid == 0) atomicOr(&ctl[0], natoms < 1 ? GTA_B200_ST_TOO_FEW_POINTS : GTA_B200_ST_NONFINITE); }
-            else if (toomany || natoms + ncorr > cap) { if (tid == 0) atomicOr(&ctl[0], GTA_B200_ST_CAPACITY); }
-            else {
-                const int oymin = 4, oymax = 4 + (nx + 1), oxmin = 4 + 2 * (nx + 1), oxmax = oxmin + (ny + 1);
-                const unsigned long long kmin0 = okey((double)FLT_MAX), kmax0 = okey((double)FLT_MIN);   // gta_tri.c:119-120,137-144
-                // Per-interval extremes on order-preserving 64-bit keys, found with NATIVE 32-bit shared atomics in two steps (high
-                // word, then low word among the atoms that tie on the high word): 64-bit shared atomicMin / atomicMax are
-                // compare-and-swap loops and were a quarter of the pre-pass. khi / klo / cidx: K words each.
-                uint32_t* khi = reinterpret_cast<uint32_t*>(ckey);
-                uint32_t* klo = khi + K;
-                int* cidx = reinterpret_cast<int*>(klo + K);
-                auto is_min = [&](int s) -> bool { return (s == 0 || s == 2) || (s >= oymin && s < oymax) || (s >= oxmin && s < oxmax); };
-                for (int s = tid; s < K; s += T) { khi[s] = (uint32_t)((is_min(s) ? kmin0 : kmax0) >> 32); cidx[s] = 0x7fffffff; }
-                __syncthreads();
-                // pass 1: extreme values per slot (gta_tri.c:153-202). The four corner slots see every atom: they are reduced in
-                // registers and by shuffles; the per-interval slots (a few dozen atoms each) use the atomics.
-                const int NONE = 0x7fffffff;
-                double bv[4] = {(double)FLT_MAX, (double)FLT_MIN, (double)FLT_MAX, (double)FLT_MIN};      // running extremes, initial values of the reference
-                int bi[4] = {NONE, NONE, NONE, NONE};
-                for (int j = tid; j < natoms; j += T) {                       // ascending j: the strict comparisons keep the first atom
-                    const double X = ax(j), Y = ay(j);
-                    const double d0 = X * X + Y * Y, dY = by - Y, d1 = X * X + dY * dY;
-                    const double fx = (X / bx) * nx, fy = (Y / by) * ny;
-                    if (!(fx > -1.0 && fx < (double)(nx + 1) && fy > -1.0 && fy < (double)(ny + 1))) { atomicOr(&ctl[0], GTA_B200_ST_OUT_OF_BOX); continue; }
-                    const int xi = (int)fx, yi = (int)fy;
-                    if (d0 < bv[0]) { bv[0] = d0; bi[0] = j; }
-                    if (d0 > bv[1]) { bv[1] = d0; bi[1] = j; }
-                    if (d1 < bv[2]) { bv[2] = d1; bi[2] = j; }
-                    if (d1 > bv[3]) { bv[3] = d1; bi[3] = j; }
-                    const uint32_t yh = (uint32_t)(okey(Y) >> 32), xh = (uint32_t)(okey(X) >> 32);
-                    atomicMin(&khi[oymin + xi], yh); atomicMax(&khi[oymax + xi], yh);
-                    atomicMin(&khi[oxmin + yi], xh); atomicMax(&khi[oxmax + yi], xh);
-                }
-                {
-                    // is candidate b better than a for corner slot c? better value wins (c odd: a maximum), equal values keep the
-                    // lower index, "no candidate" loses -- the same atom the reference's sequential scan ends with
-                    auto better = [NONE](int c, double va, int ia, double vb, int ib) -> bool {
-                        if (ib == NONE) return false;
-                        if (ia == NONE) return true;
-                        if (vb != va) return (c & 1) ? vb > va : vb < va;
-                        return ib < ia;
-                    };
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            const double vo = __shfl_xor_sync(0xffffffffu, bv[c], o); const int io = __shfl_xor_sync(0xffffffffu, bi[c], o);
-                            if (better(c, bv[c], bi[c], vo, io)) { bv[c] = vo; bi[c] = io; }
-                        }
-                    }
-                    double* rv = red;                                         // (reduction scratch: 4 x 8 doubles + 4 x 8 ints)
-                    int* ri = reinterpret_cast<int*>(rv + 4 * (T / 32));
-                    if (lane == 0) {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) { rv[4 * warp + c] = bv[c]; ri[4 * warp + c] = bi[c]; }
-                    }
-                    __syncthreads();
-                    if (tid < 4) {
-                        double v = rv[tid]; int ix = ri[tid];
-                        for (int w = 1; w < T / 32; ++w) if (better(tid, v, ix, rv[4 * w + tid], ri[4 * w + tid])) { v = rv[4 * w + tid]; ix = ri[4 * w + tid]; }
-                        cidx[tid] = ix;
-                    }
-                    // low words start from the initial value's when the high word still is the initial value's, else from the neutral element
-                    for (int s = 4 + tid; s < K; s += T) {
-                        const unsigned long long k0 = is_min(s) ? kmin0 : kmax0;
-                        klo[s] = khi[s] == (uint32_t)(k0 >> 32) ? (uint32_t)k0 : (is_min(s) ? 0xffffffffu : 0u);
-                    }
-                }
-                __syncthreads();
-                const bool inbox = !(ctl[0] & GTA_B200_ST_OUT_OF_BOX);
-                // pass 1b: low words, among the atoms whose high word is the slot's extreme
-                if (inbox) {
-                    for (int j = tid; j < natoms; j += T) {
-                        const double X = ax(j), Y = ay(j);
-                        const int xi = (int)((X / bx) * nx), yi = (int)((Y / by) * ny);
-                        const unsigned long long ky = okey(Y), kx = okey(X);
-                        const uint32_t yh = (uint32_t)(ky >> 32), xh = (uint32_t)(kx >> 32);
-                        if (yh == khi[oymin + xi]) atomicMin(&klo[oymin + xi], (uint32_t)ky);
-                        if (yh == khi[oymax + xi]) atomicMax(&klo[oymax + xi], (uint32_t)ky);
-                        if (xh == khi[oxmin + yi]) atomicMin(&klo[oxmin + yi], (uint32_t)kx);
-                        if (xh == khi[oxmax + yi]) atomicMax(&klo[oxmax + yi], (uint32_t)kx);
-                    }
-                }
-                __syncthreads();
-                // pass 2: lowest atom index attaining the extreme of its intervals (strict < / > keeps the first one)
-                if (inbox) {
-                    for (int j = tid; j < natoms; j += T) {
-                        const double X = ax(j), Y = ay(j);
-                        const int xi = (int)((X / bx) * nx), yi = (int)((Y / by) * ny);
-                        const double fmx = (double)FLT_MAX, fmn = (double)FLT_MIN;
-                        const unsigned long long ky = okey(Y), kx = okey(X);
-                        auto slot_key = [&](int s) -> unsigned long long { return ((unsigned long long)khi[s] << 32) | klo[s]; };
-                        if (Y < fmx && ky == slot_key(oymin + xi)) atomicMin(&cidx[oymin + xi], j);
-                        if (Y > fmn && ky == slot_key(oymax + xi)) atomicMin(&cidx[oymax + xi], j);
-                        if (X < fmx && kx == slot_key(oxmin + yi)) atomicMin(&cidx[oxmin + yi], j);
-                        if (X > fmn && kx == slot_key(oxmax + yi)) atomicMin(&cidx[oxmax + yi], j);
-                    }
-                }
-                __syncthreads();
-                for (int s = tid; s < K; s += T) if (cidx[s] == 0x7fffffff) cidx[s] = 0;      // index arrays start at 0 (gta_tri.c:146-149)
-                __syncthreads();
-                // corner z (gta_tri.c:209-212) and the appended points in the reference's order (:220-272)
-                const double zc = (az(cidx[0]) + az(cidx[1]) + az(cidx[2]) + az(cidx[3])) / 4.0;
-                for (int s = tid; s < ncorr; s += T) {
-                    double X, Y, Z;
-                    if (s < 4) {
-                        X = (s == 1 || s == 2) ? bx : 0.0; Y = (s >= 2) ? by : 0.0; Z = zc;
-                    } else if (s < 4 + 2 * nx) {
-                        const int j = (s - 4) >> 1;
-                        const int imin = cidx[oymin + j], imax = cidx[oymax + j];
-                        const double dist1 = ay(imin), dist2 = by - ay(imax), dist = dist1 + dist2;
-                        const double zmin = az(imin), zmax = az(imax);
-                        Z = zmin - (dist1 / dist) * zmin + zmax - (dist2 / dist) * zmax;
-                        X = j * p.espace + p.espace / 2; Y = ((s - 4) & 1) ? by : 0.0;
-                    } else {
-                        const int j = (s - 4 - 2 * nx) >> 1;
-                        const int imin = cidx[oxmin + j], imax = cidx[oxmax + j];
-                        const double dist1 = ax(imin), dist2 = bx - ax(imax), dist = dist1 + dist2;
-                        const double zmin = az(imin), zmax = az(imax);
-                        Z = zmin - (dist1 / dist) * zmin + zmax - (dist2 / dist) * zmax;
-                        Y = j * p.espace + p.espace / 2; X = ((s - 4 - 2 * nx) & 1) ? bx : 0.0;
-                    }
-                    corr3[3 * s] = X; corr3[3 * s + 1] = Y; corr3[3 * s + 2] = Z;
-                    if (p.corr && s < p.corr_cap) {
-                        double* o = p.corr + ((size_t)fr * p.corr_cap + s) * 3;
-                        o[0] = X; o[1] = Y; o[2] = Z;
-                    }
-                }
-                n = natoms + ncorr;
-            }
+            n = corr_points<T>(tile, in_dim, natoms, cap, bx, by, p.espace, ckey, red, ctl, corr3, p.corr, p.corr_cap, fr, &ncorr_out);
         } else if (natoms > cap) {
             if (tid == 0) atomicOr(&ctl[0], GTA_B200_ST_CAPACITY);
         }
@@ -400,7 +270,7 @@ __global__ void __launch_bounds__(T) prepass_kernel(const KParams p) {
         }
         PP_TICK(7);
         // ------------------------------------------------------------ the frame's records
-        const size_t slot = (size_t)fr;
+        const size_t slot = (size_t)wi;
         if (ctl[0] == 0) {
             LPt* wpt = p.ws.pt + slot * p.ws.cap;
             for (int i = tid; i < n; i += T) {

@@ -44,7 +44,19 @@ extern "C" {
 #define GTA_B200_E_ARG          (-3)
 #define GTA_B200_E_TOO_LARGE    (-4)   /* max_points does not fit the shared-memory kernel */
 
-/* Two kernels serve the batched calls: launches of at least `min_frames` frames run the throughput path (pre-pass,
+/* Engines behind the batched calls (every one returns the reference's triangulation; areas agree to the rounding of the
+ * summation order, |rel| ~ 1e-16):
+ *   star path (default when no triangle list is asked for): one fused launch, a CTA per frame, a thread per point builds
+ *     that point's Delaunay star from a uniform grid with exact predicates and certifies it (csrc/star_core.cuh). Frames
+ *     whose Delaunay triangulation is not unique (cocircular ties), duplicates and refused frames are handed, inside the
+ *     same call, to the divide-and-conquer engine, which keeps the reference's tie-breaking (delaunay_tri.c:582-593).
+ *   divide and conquer (always when d_tri / tri is given: its list is in the reference's emission order,
+ *     delaunay_tri.c:613-629): the two kernels described below.
+ * gta_b200_set_path: 0 = automatic (above), 1 = divide and conquer only, 2 = star path also for triangle lists (the list
+ * then holds the same triangles in another order). Environment GTA_B200_PATH sets the default. Returns the previous mode. */
+int gta_b200_set_path(int mode);
+
+/* Two kernels serve the divide-and-conquer engine: launches of at least `min_frames` frames run the throughput path (pre-pass,
  * a persistent kernel whose phase-sorted scheduler steps (frame, subtree) walkers, area kernel: highest throughput), smaller ones the fused one-CTA-per-frame kernel (lowest latency). Results are identical
  * triangulations; areas agree to rounding of the summation tree. Environment GTA_B200_LPF overrides the default;
  * 0 = never, 1 = always, negative = restore the default. Returns the previous value. */
@@ -136,6 +148,13 @@ int gta_b200_last_launches(void);
  * duration, measured with CUDA events on the launching streams (at most 64 launches are kept). Any pointer may be NULL. */
 int gta_b200_stage_reset(int device);
 int gta_b200_stage_ms(int device, double *prepass_ms, double *walk_ms, double *area_ms, int *launches);
+/* The same with the star kernel in front: out4 = {star kernel, pre-pass, walker kernel, area kernel} in ms. */
+int gta_b200_stage_ms4(int device, double *out4, int *launches);
+/* Frames the most recent sampled star launch on `device` handed to the divide-and-conquer engine (waits for it); < 0: none yet. */
+long long gta_b200_last_fallback_frames(int device);
+/* Running totals of the star engine on `device` since the last reset (synchronises the device): frames certified by their
+ * stars and frames handed to the divide-and-conquer engine. Either pointer may be NULL; reset != 0 zeroes the totals. */
+int gta_b200_star_counters(int device, unsigned long long *certified, unsigned long long *fallback, int reset);
 
 /* FP64 peak of the device in TFLOP/s, measured with independent DFMA chains (2 flops each): the denominator of the
  * FP64 roofline bench.py reports (MEASURED_PEAKS.json holds no FP64 figure). <= 0 on error. device < 0: current. */

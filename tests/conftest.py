@@ -60,7 +60,7 @@ def emu():
     d = os.path.join(ROOT, "tests", "emu")
     so = os.path.join(d, "libemu_dt.so")
     srcs = [os.path.join(d, "emu_dt.cpp")] + [os.path.join(ROOT, "g_tessla_b200", "csrc", f)
-                                               for f in ("dt_core.cuh", "gt_predicates.cuh", "lpf_core.cuh")]
+                                               for f in ("dt_core.cuh", "gt_predicates.cuh", "lpf_core.cuh", "star_core.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++",
                                "-o", so, srcs[0]])
@@ -69,6 +69,7 @@ def emu():
     L.emu_triangulate.argtypes = [dp, C.c_int, ip]
     L.emu_triangulate_lpf2.argtypes = [dp, C.c_int, C.c_int, C.c_uint, ip, C.POINTER(C.c_long)]
     L.emu_exact_stats.argtypes = [C.POINTER(C.c_long)]
+    L.emu_star.argtypes = [dp, C.c_int, C.c_int, C.c_double, ip, C.POINTER(C.c_long)]
     for n in ("emu_orient2d_signs", "emu_incircle_signs", "emu_orient2d_exact", "emu_incircle_exact"):
         getattr(L, n).argtypes = [dp, C.c_int, ip]
 
@@ -89,6 +90,16 @@ def emu():
             nt = L.emu_triangulate_lpf2(p.ctypes.data_as(dp), len(p), int(level), int(seed), out.ctypes.data_as(ip), st)
             assert nt >= 0, "emu error %d" % nt
             return out[:3 * nt].reshape(-1, 3).copy(), list(st)
+
+        def star(self, p, w0=2, dens=1.0):
+            """The star path (star_core.cuh): (triangles in any order or None when the frame is not certified, status, counters)."""
+            p = np.ascontiguousarray(p, dtype=np.float64)
+            out = np.empty(3 * 2 * max(len(p), 1), dtype=np.int32)
+            st = (C.c_long * 11)()
+            nt = L.emu_star(p.ctypes.data_as(dp), len(p), int(w0), float(dens), out.ctypes.data_as(ip), st)
+            if nt < 0:
+                return None, -nt, list(st)
+            return out[:3 * nt].reshape(-1, 3).copy(), 0, list(st)
 
         def exact_stats(self):
             """[orient2d 1/2/4 words, incircle 1/2/4 words, orient2d total, incircle total] since the last call."""
@@ -116,3 +127,19 @@ def gta():
     L = g.lib()
     assert L.gta_b200_device_count() > 0, "no CUDA device visible to libgtessla_b200.so"
     return g
+
+
+@pytest.fixture()
+def dc_path(gta):
+    """Batched calls through the divide-and-conquer engine only (tests of that engine's own kernels)."""
+    old = gta.set_path(gta.PATH_DC)
+    yield
+    gta.set_path(old)
+
+
+@pytest.fixture()
+def star_path(gta):
+    """Batched calls through the star engine even when triangle lists are asked for (they then come in any order)."""
+    old = gta.set_path(gta.PATH_STAR)
+    yield
+    gta.set_path(old)

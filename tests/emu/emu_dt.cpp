@@ -11,7 +11,8 @@
 #define GT_STATS 1
 #include "../../g_tessla_b200/csrc/dt_core.cuh"
 #include "../../g_tessla_b200/csrc/lpf_core.cuh"
-namespace gt { Stats g_stats; long g_exact_calls[8]; }
+#include "../../g_tessla_b200/csrc/star_core.cuh"
+namespace gt { Stats g_stats; long g_exact_calls[8]; StarStats g_star; }
 
 extern "C" {
 
@@ -177,6 +178,53 @@ int emu_triangulate_lpf(const double* points, int n, int* tri_out, long* iters_o
     const int r = emu_triangulate_lpf2(points, n, 0, 0u, tri_out, st);
     if (iters_out) *iters_out = st[0];
     return r;
+}
+
+// The star path (star_core.cuh) the way the GPU kernel drives it: bin the points into the grid (cell order, input order
+// inside a cell), one star per point, owned triangles out (indices into the input, any order). Returns ntri, or
+// -(STAR_* bits) when the frame is not certified (ties, duplicates), or -64 when the triangle count is not 2(n-1)-h.
+// stats_out (nullable): [0] candidates visited, [1] left of the edge, [2] incircle filters, [3] exact-stage calls,
+// [4] window expansions, [5] walk steps, [6] points, [7] hull certificates, [8] hull vertices, [9] gx, [10] gy
+int emu_star(const double* points, int n, int w0, double dens, int* tri_out, long* stats_out) {
+    using namespace gt;
+    if (n < 2) return -1000;
+    memset(&g_star, 0, sizeof g_star);
+    double xmin = points[0], xmax = points[0], ymin = points[1], ymax = points[1];
+    for (int i = 1; i < n; ++i) {
+        xmin = std::min(xmin, points[2 * i]); xmax = std::max(xmax, points[2 * i]);
+        ymin = std::min(ymin, points[2 * i + 1]); ymax = std::max(ymax, points[2 * i + 1]);
+    }
+    const StarDims d = star_dims(n, xmin, xmax, ymin, ymax, std::max(n, 1), dens);
+    const int nc = d.gx * d.gy;
+    std::vector<int> cell(n), cstart(nc + 1, 0), id(n);
+    for (int i = 0; i < n; ++i) {
+        cell[i] = star_cell(points[2 * i + 1], ymin, d.sy, d.gy) * d.gx + star_cell(points[2 * i], xmin, d.sx, d.gx);
+        cstart[cell[i] + 1]++;
+    }
+    for (int c = 0; c < nc; ++c) cstart[c + 1] += cstart[c];
+    std::vector<int> cur(cstart.begin(), cstart.end() - 1);
+    std::vector<SPt> pt(n);
+    for (int i = 0; i < n; ++i) { const int pos = cur[cell[i]]++; pt[pos].x = points[2 * i]; pt[pos].y = points[2 * i + 1]; id[pos] = i; }
+    StarGrid<int> g;
+    g.pt = pt.data(); g.cstart = cstart.data(); g.n = n; g.gx = d.gx; g.gy = d.gy;
+    g.x0 = xmin; g.y0 = ymin; g.sx = d.sx; g.sy = d.sy; g.xmin = xmin; g.xmax = xmax; g.ymin = ymin; g.ymax = ymax;
+    int nt = 0, st = 0, nh = 0;
+    for (int ip = 0; ip < n; ++ip) {
+        bool hull = false;
+        st |= star_point(g, ip, true, w0, &hull, [&](int n1, int n2) {
+            tri_out[3 * nt] = id[ip]; tri_out[3 * nt + 1] = id[n1]; tri_out[3 * nt + 2] = id[n2];
+            ++nt;
+        });
+        nh += hull;
+    }
+    if (stats_out) {
+        stats_out[0] = g_star.cand; stats_out[1] = g_star.left; stats_out[2] = g_star.icc; stats_out[3] = g_star.exact;
+        stats_out[4] = g_star.expand; stats_out[5] = g_star.steps; stats_out[6] = g_star.points; stats_out[7] = g_star.hullcert;
+        stats_out[8] = nh; stats_out[9] = d.gx; stats_out[10] = d.gy;
+    }
+    if (st) return -st;
+    if (nt != 2 * (n - 1) - nh) return -64;
+    return nt;
 }
 
 void emu_orient2d_signs(const double* p, int n, int* out) {

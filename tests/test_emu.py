@@ -132,3 +132,65 @@ def test_cfg5_census_live(ref, tmp_path):
     assert cnt5["orient2d_zero"] >= 8000 and cnt5["incircle_zero"] >= 1200, cnt5
     assert cocirc5 >= 200, cocirc5            # >= 50 exactly cocircular decisions per frame: the tie-break rule decides them
     assert cocirc3 == 0, cocirc3              # generic positions: none
+
+
+def _canon(t):
+    return synth.canonical_triangles(t)
+
+
+def test_star_path_matches_oracle_on_configs(emu, checker):
+    """star_core.cuh on the host: for frames whose Delaunay triangulation is unique the stars deliver the reference's
+    triangle set (canonical order); the lattice of cfg 5 (cocircular ties everywhere) must NOT be certified."""
+    for cfg, nfr in ((1, 30), (2, 10), (3, 6)):
+        c = synth.config(cfg, nframes=nfr)
+        r = checker.tessellate(c["xyz"], c["box"], c["espace"], c["flags"], want_corr=True)
+        for f in range(nfr):
+            p = np.concatenate([c["xyz"][f, :, :2], r["corr"][f, :int(r["ncorr"][f]), :2]])
+            want, _ = checker.triangulate(p)
+            tri, st, _ = emu.star(p)
+            assert st == 0 and np.array_equal(_canon(tri), _canon(want)), (cfg, f, st)
+    c = synth.config(5, nframes=3)
+    r = checker.tessellate(c["xyz"], c["box"], c["espace"], c["flags"], want_corr=True)
+    for f in range(3):
+        p = np.concatenate([c["xyz"][f, :, :2], r["corr"][f, :int(r["ncorr"][f]), :2]])
+        tri, st, _ = emu.star(p)
+        assert tri is None and st & 1
+
+
+def test_star_path_random_sizes_and_windows(emu, checker):
+    """No -corr points: the hull is irregular, hull vertices scan the whole grid. Any first window and any cell density must
+    give the same triangles (the window only has to be grown more or less often)."""
+    rng = np.random.default_rng(5)
+    for n in list(range(2, 30)) + [64, 65, 129, 500, 1157, 3000]:
+        p = rng.random((n, 2)) * np.array([3.0, 7.0])
+        want, _ = checker.triangulate(p)
+        for w0, dens in ((2, 1.0), (0, 1.0), (1, 4.0), (3, 0.5)):
+            tri, st, _ = emu.star(p, w0, dens)
+            assert st == 0 and np.array_equal(_canon(tri), _canon(want)), (n, w0, dens, st)
+    # clustered points: windows must grow a lot, the result stays exact
+    p = np.concatenate([rng.normal(0, 0.01, (300, 2)), rng.normal(5, 2.0, (300, 2)), rng.random((50, 2)) * 40])
+    want, _ = checker.triangulate(p)
+    tri, st, cnt = emu.star(p)
+    assert st == 0 and cnt[4] > 0 and np.array_equal(_canon(tri), _canon(want))
+
+
+def test_star_path_refuses_what_it_cannot_certify(emu, golden):
+    """Cocircular lattices, collinear sets and duplicates are left to the divide-and-conquer path (status bits, no triangles);
+    the golden near-degenerate sets it does certify must equal the reference's triangles."""
+    gx, gy = np.meshgrid(np.arange(9.0), np.arange(7.0))
+    tri, st, _ = emu.star(np.stack([gx.ravel(), gy.ravel()], 1))
+    assert tri is None and st & 1                                        # squares: four cocircular points on empty circles
+    tri, st, _ = emu.star(np.stack([np.arange(10.0), 2 * np.arange(10.0)], 1))
+    assert tri is None                                                   # all collinear: the triangle count rule fails
+    p = np.random.default_rng(2).random((40, 2)); p[17] = p[3]
+    tri, st, _ = emu.star(p)
+    assert tri is None and st & 2
+    g = golden["dtriangulate"]
+    seen = 0
+    for k in g.files:
+        if k.startswith("pts_") and len(g[k]) >= 3:
+            tri, st, _ = emu.star(g[k])
+            if tri is not None:
+                seen += 1
+                assert np.array_equal(_canon(tri), _canon(g["tri_" + k[4:]])), k
+    assert seen >= 3

@@ -150,7 +150,9 @@ def lane_per_frame(gta):
     """Force every launch through the lane-per-frame pipeline (normally only batches >= 32768 frames)."""
     L = gta.lib()
     old = L.gta_b200_set_batch_threshold(1)
+    oldp = gta.set_path(gta.PATH_DC)
     yield
+    gta.set_path(oldp)
     L.gta_b200_set_batch_threshold(old)
 
 

@@ -47,7 +47,7 @@ def test_baseline_frame_counts_vs_reference(gta, checker, cfg, nfr):
 
 
 @pytest.mark.parametrize("cfg,nfr", [(3, 6000), (5, 6000)])
-def test_throughput_path_unforced_triangles(gta, checker, cfg, nfr):
+def test_throughput_path_unforced_triangles(gta, checker, dc_path, cfg, nfr):
     """A batch above the default threshold takes the throughput path (pre-pass, walker kernel, area kernel) without any
     forcing, and hands back triangle lists from it: compared with the reference in emission order on a sample, areas
     against the fused kernel on every frame (the two paths must agree to the rounding of the summation tree)."""
@@ -223,7 +223,7 @@ def test_corr_point_count_cannot_overflow(gta):
     assert (r["status"] == 0).all()
 
 
-def test_stage_timers(gta):
+def test_stage_timers(gta, dc_path):
     """gta_b200_stage_ms: per-kernel device time of the throughput path since the last reset."""
     L = gta.lib()
     L.gta_b200_stage_ms.argtypes = [C.c_int, dp, dp, dp, ip]
