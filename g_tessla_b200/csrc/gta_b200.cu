@@ -193,9 +193,13 @@ int path_mode() {
     if (v < 0) { static int env; static std::once_flag once; v = env_once("GTA_B200_PATH", 0, &env, &once); v = (v < 0 || v > 2) ? 0 : v; g_path.store(v); }
     return v;
 }
+int star_threads(int cap, int forced) {
+    if (forced == 64 || forced == 128 || forced == 256 || forced == 384) return forced;
+    return cap <= 160 ? 64 : (cap <= 512 ? 128 : 256);
+}
 bool use_star(const gt::KParams& p, const Shape& s) {
     const int m = path_mode();
-    if (m == 1 || s.cap > 4000 || gt::StarSmem(s.cap, p.natoms, p.in_dim).total > (size_t)smem_limit()) return false;
+    if (m == 1 || s.cap > 4000 || gt::StarSmem(s.cap, p.natoms, p.in_dim, 384).total > (size_t)smem_limit()) return false;
     return m == 2 || p.tri == nullptr;
 }
 bool use_lpf(int nframes, const Shape& s) { return lpf_threshold() > 0 && nframes >= lpf_threshold() && s.cap < 4000; }
@@ -236,7 +240,10 @@ int launch(const gt::KParams& p, const Shape& s, cudaStream_t st);
 // The star kernel (gta_star.cuh): one CTA per frame, a thread per point. Frames it does not certify go to ws.fb_list.
 int launch_star(const gt::KParams& p, const Shape& s, int* fb_list, unsigned int* fb_count, unsigned long long* counters, cudaStream_t st) {
     gt::StarParams sp; sp.k = p; sp.fb_list = fb_list; sp.fb_count = fb_count; sp.counters = counters;
-    const size_t smem = gt::StarSmem(s.cap, p.natoms, p.in_dim).total;
+    static int env_t; static std::once_flag once;            // experiments: GTA_B200_STAR_THREADS = 64 | 128 | 256 | 384
+    const int t = env_once("GTA_B200_STAR_THREADS", 0, &env_t, &once);
+    const int threads = star_threads(s.cap, t);
+    const size_t smem = gt::StarSmem(s.cap, p.natoms, p.in_dim, threads).total;
     if (smem > (size_t)smem_limit()) return fail(GTA_B200_E_TOO_LARGE, "frame too large for the star kernel");
     int dev = 0, sms = 0;
     CK(cudaGetDevice(&dev));
@@ -251,14 +258,12 @@ int launch_star(const gt::KParams& p, const Shape& s, int* fb_list, unsigned int
         CK(cudaGetLastError());
         return GTA_B200_OK;
     };
-    static int env_t; static std::once_flag once;            // experiments: GTA_B200_STAR_THREADS = 64 | 128 | 256 | 384
-    const int t = env_once("GTA_B200_STAR_THREADS", 0, &env_t, &once);
-    const int threads = t ? t : (s.cap <= 160 ? 64 : (s.cap <= 512 ? 128 : 256));
+    const bool full = !(p.flags & GTA_B200_CORRECT);          // without -corr points the hull is not the box: whole stars
     switch (threads) {
-        case 64: return go(gt::star_kernel<64, 8>, 64);
-        case 128: return go(gt::star_kernel<128, 4>, 128);
-        case 384: return go(gt::star_kernel<384, 1>, 384);
-        default: return go(gt::star_kernel<256, 2>, 256);
+        case 64: return full ? go(gt::star_kernel<64, 8, true>, 64) : go(gt::star_kernel<64, 8, false>, 64);
+        case 128: return full ? go(gt::star_kernel<128, 4, true>, 128) : go(gt::star_kernel<128, 4, false>, 128);
+        case 384: return full ? go(gt::star_kernel<384, 1, true>, 384) : go(gt::star_kernel<384, 1, false>, 384);
+        default: return full ? go(gt::star_kernel<256, 2, true>, 256) : go(gt::star_kernel<256, 2, false>, 256);
     }
 }
 

@@ -31,6 +31,8 @@ namespace gt {
 #define GT_STAR_DENS 1.0      // points per cell
 #endif
 
+constexpr int STAR_LCAP = 24;                  // left candidates a lane keeps per round of a walk step (star_core.cuh)
+
 struct StarParams {
     KParams k;
     int* fb_list; unsigned int* fb_count;      // frames that need the divide-and-conquer path
@@ -38,9 +40,9 @@ struct StarParams {
 };
 
 struct StarSmem {
-    size_t tile, corr, spt, sz, sid, tmp, cell, cstart, ctl, total;
+    size_t tile, corr, spt, sz, sid, tmp, cell, cstart, csum, lists, ctl, total;
     int ncell_max;
-    __host__ __device__ StarSmem(int cap, int natoms, int in_dim) {
+    __host__ __device__ StarSmem(int cap, int natoms, int in_dim, int threads) {
         size_t o = 0;
         tile = o; o += (((size_t)natoms * in_dim * 8) + 15) & ~(size_t)15;       // bulk-copy destination
         corr = o; o += 24 * (size_t)(cap > natoms ? cap - natoms : 0); o = (o + 15) & ~(size_t)15;
@@ -52,19 +54,23 @@ struct StarSmem {
         tmp = o; o += 2 * (size_t)cap;                                          // scatter order
         cell = o; o += 2 * (size_t)cap;                                         // cell of each input point
         o = (o + 15) & ~(size_t)15;
+        csum = o; o += 16 * (size_t)((cap + 31) / 32 + 1);                      // area sums of every chunk of 32 points
+        lists = o; o += 2 * (size_t)STAR_LCAP * threads;                        // every thread's list of left candidates
         ctl = o; o += 16 * 4 + 8 * 32 * 8 + 8;                                  // status / counters, reduction scratch, one mbarrier
         total = (o + 15) & ~(size_t)15;
     }
 };
 
-template <int T, int MINB>
+// FULL = false (frames with -corr points: the hull is the box, every star is closed or ends on it): a point walks only the
+// arc of its star that holds the triangles it owns (star_core.cuh); FULL = true: whole stars.
+template <int T, int MINB, bool FULL>
 __global__ void __launch_bounds__(T, MINB) star_kernel(const StarParams sp) {
     extern __shared__ __align__(128) unsigned char ssm[];
     const KParams& p = sp.k;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = T / 32;
     const int cap = p.cap, natoms = p.natoms, in_dim = p.in_dim;
-    const StarSmem L(cap, natoms, in_dim);
+    const StarSmem L(cap, natoms, in_dim, T);
     double* tile = reinterpret_cast<double*>(ssm + L.tile);
     double* corr3 = reinterpret_cast<double*>(ssm + L.corr);
     SPt* spt = reinterpret_cast<SPt*>(ssm + L.spt);
@@ -73,7 +79,9 @@ __global__ void __launch_bounds__(T, MINB) star_kernel(const StarParams sp) {
     u16* sid = reinterpret_cast<u16*>(ssm + L.sid);
     u16* tmp = reinterpret_cast<u16*>(ssm + L.tmp);
     u16* cell = reinterpret_cast<u16*>(ssm + L.cell);
-    uint32_t* ctl = reinterpret_cast<uint32_t*>(ssm + L.ctl);              // [0] status, [1] triangles written, [2] scan carry
+    double* csum = reinterpret_cast<double*>(ssm + L.csum);
+    u16* lists = reinterpret_cast<u16*>(ssm + L.lists);                     // [STAR_LCAP][T]
+    uint32_t* ctl = reinterpret_cast<uint32_t*>(ssm + L.ctl);              // [0] status, [1] triangles written, [3] next chunk of points
     double* red = reinterpret_cast<double*>(ctl + 16);                      // [8][32]
     uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 8 * 32);
     unsigned long long* ckey = reinterpret_cast<unsigned long long*>(ssm + L.spt);
@@ -91,7 +99,7 @@ __global__ void __launch_bounds__(T, MINB) star_kernel(const StarParams sp) {
 
     int it = 0;
     for (int fr = first; fr < p.nframes; fr += stride, ++it) {
-        if (tid == 0) { ctl[0] = 0; ctl[1] = 0; }
+        if (tid == 0) { ctl[0] = 0; ctl[1] = 0; ctl[3] = NW; ctl[4] = 0; ctl[5] = 0; }
         if (bulk) pp_mbar_wait(mbar, (uint32_t)(it & 1));
         else {
             const double* src = p.xyz + (size_t)fr * natoms * in_dim;
@@ -114,7 +122,7 @@ __global__ void __launch_bounds__(T, MINB) star_kernel(const StarParams sp) {
         auto pz = [&](int i) -> double { return i < natoms ? (in_dim == 3 ? tile[(size_t)i * 3 + 2] : 0.0) : corr3[3 * (i - natoms) + 2]; };
         const bool ok = ctl[0] == 0;                                       // (block-uniform: read after the barrier)
 
-        double a3 = 0.0, a2 = 0.0; int ntri = 0, nhull = 0, st = 0;
+        int ntri = 0, nhull = 0, st = 0;
         if (ok) {
             // ---------------------------------------------------------------- bounding box of the points
             double xlo = 1.7976931348623157e308, xhi = -xlo, ylo = xlo, yhi = -xlo;
@@ -159,6 +167,12 @@ __global__ void __launch_bounds__(T, MINB) star_kernel(const StarParams sp) {
                 for (int q = s; q < e; ++q) rank += tmp[q] < i;
                 SPt v; v.x = px(i); v.y = py(i);
                 spt[s + rank] = v; sz[s + rank] = pz(i); sid[s + rank] = (u16)i;
+                if (!FULL) {
+                    // points on the bounding box: when its four corners are points, they are the hull vertices (triangle count rule)
+                    const bool ex = v.x == xlo || v.x == xhi, ey = v.y == ylo || v.y == yhi;
+                    if (ex || ey) atomicAdd(&ctl[5], 1u);
+                    if (ex && ey) atomicAdd(&ctl[4], 1u);
+                }
             }
             __syncthreads();
             // the tile is dead from here on: the next frame's coordinates arrive while this frame's stars are built
@@ -171,16 +185,22 @@ __global__ void __launch_bounds__(T, MINB) star_kernel(const StarParams sp) {
             g.pt = spt; g.cstart = cbase; g.n = n; g.gx = dm.gx; g.gy = dm.gy;
             g.x0 = xlo; g.y0 = ylo; g.sx = dm.sx; g.sy = dm.sy; g.xmin = xlo; g.xmax = xhi; g.ymin = ylo; g.ymax = yhi;
             int* tri_out = p.tri ? p.tri + (size_t)fr * p.tri_cap * 3 : nullptr;
-            // (a warp's 32 lanes build 32 stars in lockstep: all of them call star_point, lanes beyond n without a point)
-            for (int ip0 = warp * 32; ip0 < n; ip0 += T) {
-                const int ip = ip0 + lane;
+            // A warp's 32 lanes build the stars of 32 consecutive positions in lockstep (all of them call star_point, lanes
+            // beyond n without a point). Chunks of 32 are handed out by a shared counter (a warp's first one is static), so
+            // the warps finish together whatever their chunks cost; every chunk's area sums are kept apart and added in
+            // chunk order below, so the frame's sum does not depend on which warp took which chunk.
+            for (int ch = warp; ch * 32 < n;) {
+                const int ip = ch * 32 + lane;
                 const bool active = ip < n;
                 const SPt P = spt[active ? ip : 0]; const double zp = sz[active ? ip : 0];
+                double c3 = 0.0, c2 = 0.0;
                 bool hull = false;
-                st |= star_point(g, ip, active, GT_STAR_W0, &hull, [&](int n1, int n2) {
+                struct { u16* base; __device__ void put(int k, int pos) { base[k * T] = (u16)pos; } __device__ int get(int k) const { return base[k * T]; } } lst;
+                lst.base = lists + tid;
+                st |= star_point<STAR_LCAP, FULL>(g, ip, active, GT_STAR_W0, lst, &hull, [&](int n1, int n2) {
                     const SPt A = spt[n1], B = spt[n2];
-                    a3 += tri_area3(P.x, P.y, zp, A.x, A.y, sz[n1], B.x, B.y, sz[n2]);
-                    if (want2d) a2 += tri_area3(P.x, P.y, 0.0, A.x, A.y, 0.0, B.x, B.y, 0.0);
+                    c3 += tri_area3(P.x, P.y, zp, A.x, A.y, sz[n1], B.x, B.y, sz[n2]);
+                    if (want2d) c2 += tri_area3(P.x, P.y, 0.0, A.x, A.y, 0.0, B.x, B.y, 0.0);
                     if (tri_out) {
                         const int o = (int)atomicAdd(&ctl[1], 1u);
                         if (o < p.tri_cap) { tri_out[3 * o] = sid[ip]; tri_out[3 * o + 1] = sid[n1]; tri_out[3 * o + 2] = sid[n2]; }
@@ -188,6 +208,11 @@ __global__ void __launch_bounds__(T, MINB) star_kernel(const StarParams sp) {
                     ++ntri;
                 });
                 nhull += hull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { c3 += __shfl_down_sync(0xffffffffu, c3, o); c2 += __shfl_down_sync(0xffffffffu, c2, o); }
+                int nextch = 0;
+                if (lane == 0) { csum[2 * ch] = c3; csum[2 * ch + 1] = c2; nextch = (int)atomicAdd(&ctl[3], 1u); }
+                ch = __shfl_sync(0xffffffffu, nextch, 0);
             }
         } else if (bulk && tid == 0 && fr + stride < p.nframes) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -196,18 +221,20 @@ __global__ void __launch_bounds__(T, MINB) star_kernel(const StarParams sp) {
         // ---------------------------------------------------------------- the frame's sums (fixed order) and its verdict
         unsigned packed = ((unsigned)ntri << 12) | (unsigned)nhull;          // (n <= 4,094 points here: 2n triangles fit 20 bits)
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            a3 += __shfl_down_sync(0xffffffffu, a3, o); a2 += __shfl_down_sync(0xffffffffu, a2, o);
-            packed += __shfl_down_sync(0xffffffffu, packed, o); st |= __shfl_down_sync(0xffffffffu, st, o);
-        }
+        for (int o = 16; o > 0; o >>= 1) { packed += __shfl_down_sync(0xffffffffu, packed, o); st |= __shfl_down_sync(0xffffffffu, st, o); }
         __syncthreads();                                                   // (red was the scan's scratch)
-        if (lane == 0) { red[4 * warp] = a3; red[4 * warp + 1] = a2; red[4 * warp + 2] = __hiloint2double((int)packed, st); }
+        if (lane == 0) red[warp] = __hiloint2double((int)packed, st);
         __syncthreads();
         if (tid == 0) {
             double s3 = 0.0, s2 = 0.0; unsigned pk = 0; int sst = 0;
-            for (int w = 0; w < NW; ++w) { s3 += red[4 * w]; s2 += red[4 * w + 1]; pk += (unsigned)__double2hiint(red[4 * w + 2]); sst |= __double2loint(red[4 * w + 2]); }
-            const int tris = (int)(pk >> 12), hulls = (int)(pk & 0xfffu);
-            const bool certified = ok && sst == 0 && tris == 2 * (n - 1) - hulls && (!p.tri || tris <= p.tri_cap);
+            for (int w = 0; w < NW; ++w) { pk += (unsigned)__double2hiint(red[w]); sst |= __double2loint(red[w]); }
+            if (ok) for (int ch = 0; ch * 32 < n; ++ch) { s3 += csum[2 * ch]; s2 += csum[2 * ch + 1]; }
+            const int tris = (int)(pk >> 12);
+            // triangle count rule (delaunay_tri.c:608): hull vertices = open stars, or (arcs only) the points on the bounding
+            // box when its corners are points -- otherwise the hull size is not known here and the rule is not applied
+            const int hulls = FULL ? (int)(pk & 0xfffu) : (int)ctl[5];
+            const bool count_ok = (!FULL && ctl[4] < 4u) || tris == 2 * (n - 1) - hulls;
+            const bool certified = ok && sst == 0 && count_ok && (!p.tri || tris <= p.tri_cap);
             if (certified) {
                 if (p.area) p.area[fr] = s3;
                 if (p.area2d && want2d) p.area2d[fr] = s2;

@@ -81,33 +81,51 @@ GT_INLINE bool star_covers(const StarGrid<Idx>& g, const StarWin& w, double xa, 
     return star_cell(xa, g.x0, g.sx, g.gx) >= w.c0 && star_cell(xb, g.x0, g.sx, g.gx) <= w.c1 &&
            star_cell(ya, g.y0, g.sy, g.gy) >= w.r0 && star_cell(yb, g.y0, g.sy, g.gy) <= w.r1;
 }
-// Cursor over the positions of window `w` that are not in window `in` (in.c0 > in.c1: no inner window), one contiguous
-// run of cell-sorted positions ("segment") at a time.
-struct StarCursor { int pos, end, s, ns, ring; StarWin w, in; };
+// Cursor over the cell-sorted positions of a window, or of a window without an inner window (the ring a grown window adds):
+// a queue of at most four rectangles of cells, walked row by row -- a row of a rectangle is one contiguous run of
+// positions. The per-candidate cost is one increment and one compare; a new row costs two shared-memory loads.
+struct StarCursor { int pos, end, ci, rows, width, part; };
 template <class Idx>
-GT_INLINE bool star_cur_next(const StarGrid<Idx>& g, StarCursor& c) {        // next non-empty segment; false: window exhausted
-    while (c.s < c.ns) {
-        int row, ca, cb;
-        if (!c.ring) { row = c.w.r0 + c.s; ca = c.w.c0; cb = c.w.c1; }
-        else {
-            row = c.w.r0 + (c.s >> 1);
-            const bool half = (c.s & 1) != 0, split = row >= c.in.r0 && row <= c.in.r1;
-            if (!split) { ca = c.w.c0; cb = half ? -1 : c.w.c1; }
-            else if (!half) { ca = c.w.c0; cb = c.in.c0 - 1; }
-            else { ca = c.in.c1 + 1; cb = c.w.c1; }
-        }
-        ++c.s;
-        if (ca > cb) continue;
-        const int base = row * g.gx;
-        c.pos = (int)g.cstart[base + ca]; c.end = (int)g.cstart[base + cb + 1];
-        if (c.pos < c.end) return true;
+GT_INLINE bool star_cur_row(const StarGrid<Idx>& g, StarCursor& c) {
+    while (c.rows > 0) {
+        const int a = (int)g.cstart[c.ci], b = (int)g.cstart[c.ci + c.width];
+        c.ci += g.gx; --c.rows;
+        if (a < b) { c.pos = a; c.end = b; return true; }
     }
     return false;
 }
 template <class Idx>
+GT_INLINE bool star_cur_next(const StarGrid<Idx>& g, StarCursor& c, const StarWin& w, const StarWin& in) {
+    if (star_cur_row(g, c)) return true;
+    while (c.part < 4) {
+        // the ring w \ in: rows above, rows below, columns left, columns right of the inner window
+        int r0, r1, c0, c1;
+        const int k = c.part++;
+        if (k == 0) { r0 = w.r0; r1 = in.r0 - 1; c0 = w.c0; c1 = w.c1; }
+        else if (k == 1) { r0 = in.r1 + 1; r1 = w.r1; c0 = w.c0; c1 = w.c1; }
+        else if (k == 2) { r0 = in.r0; r1 = in.r1; c0 = w.c0; c1 = in.c0 - 1; }
+        else { r0 = in.r0; r1 = in.r1; c0 = in.c1 + 1; c1 = w.c1; }
+        if (r0 > r1 || c0 > c1) continue;
+        c.ci = r0 * g.gx + c0; c.rows = r1 - r0 + 1; c.width = c1 - c0 + 1;
+        if (star_cur_row(g, c)) return true;
+    }
+    return false;
+}
+// start on the whole window w (in.c0 > in.c1) or on the ring w \ in
+template <class Idx>
 GT_INLINE bool star_cur_begin(const StarGrid<Idx>& g, StarCursor& c, const StarWin& w, const StarWin& in) {
-    c.w = w; c.in = in; c.ring = in.c0 <= in.c1; c.s = 0; c.ns = (w.r1 - w.r0 + 1) << (c.ring ? 1 : 0); c.pos = c.end = 0;
-    return star_cur_next(g, c);
+    c.pos = c.end = 0;
+    if (in.c0 > in.c1) { c.part = 4; c.ci = w.r0 * g.gx + w.c0; c.rows = w.r1 - w.r0 + 1; c.width = w.c1 - w.c0 + 1; }
+    else { c.part = 0; c.rows = 0; c.ci = 0; c.width = 0; }
+    return star_cur_next(g, c, w, in);
+}
+// v or -v (m = 0 or the sign bit of the high word): mirrors a coordinate without a trip through the FP64 pipe
+GT_INLINE double star_flip(double v, uint32_t m) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(__double2hiint(v) ^ (int)m, __double2loint(v));
+#else
+    return m ? -v : v;
+#endif
 }
 
 // The exact stages behind the two inlined filters, out of line (rare; registers of the hot loop matter more).
@@ -132,8 +150,9 @@ GT_NOINLINE int star_incircle_exact(double ax, double ay, double bx, double by, 
 
 // Star of the point at position `ip`. emit(n1_pos, n2_pos) for every triangle (ip, n1, n2) it owns; *hull = the star is
 // open (ip is a hull vertex). `w0` = half-width of the first window in cells. Returns STAR_* bits (0: certified).
-template <class Idx, class Emit>
-GT_INLINE int star_point(const StarGrid<Idx>& g, int ip, bool active, int w0, bool* hull, Emit&& emit) {
+// `lst` = the lane's list of LCAP candidate positions (put(k, pos) / get(k)): shared memory on the device.
+template <int LCAP, bool FULL, class Idx, class List, class Emit>
+GT_INLINE int star_point(const StarGrid<Idx>& g, int ip, bool active, int w0, List&& lst, bool* hull, Emit&& emit) {
     *hull = false;
     if (g.n < 3) { *hull = active; return 0; }                // (uniform: n is the frame's)
     if (!active) ip = 0;
@@ -141,14 +160,15 @@ GT_INLINE int star_point(const StarGrid<Idx>& g, int ip, bool active, int w0, bo
     const double px = P.x, py = P.y;
     if (active) STAR_STAT(points, 1);
     StarWin none; none.c0 = 1; none.c1 = 0; none.r0 = 1; none.r1 = 0;
-    StarWin win;
+    StarWin win, in = none;
     win.c0 = win.c1 = star_cell(px, g.x0, g.sx, g.gx); win.r0 = win.r1 = star_cell(py, g.y0, g.sy, g.gy);
     win = star_win_grow(g, win, w0);
     int err = 0;
     StarCursor cu;
 
-    // ---------------------------------------------------------------- nearest neighbour
-    int q0 = -1; double l1 = 1.7976931348623157e308, l2 = l1, q0dx = 0.0, q0dy = 0.0;
+    // ---------------------------------------------------------------- nearest neighbour (and the two runners-up)
+    const double BIG = 1.7976931348623157e308;
+    int q0 = -1, b2 = -1; double l1 = BIG, l2 = BIG, l3 = BIG, q0dx = 0.0, q0dy = 0.0;
     {
         bool searching = active;
         bool busy = searching && star_cur_begin(g, cu, win, none);
@@ -159,10 +179,11 @@ GT_INLINE int star_point(const StarGrid<Idx>& g, int ip, bool active, int w0, bo
                     const SPt S = g.pt[pos];
                     const double dx = S.x - px, dy = S.y - py, l = dx * dx + dy * dy;
                     if (pos != ip) {
-                        if (l < l1) { l2 = l1; l1 = l; q0 = pos; q0dx = dx; q0dy = dy; }
-                        else if (l < l2) l2 = l;
+                        if (l < l1) { l3 = l2; l2 = l1; b2 = q0; l1 = l; q0 = pos; q0dx = dx; q0dy = dy; }
+                        else if (l < l2) { l3 = l2; l2 = l; b2 = pos; }
+                        else if (l < l3) l3 = l;
                     }
-                    if (++cu.pos >= cu.end) busy = star_cur_next(g, cu);
+                    if (++cu.pos >= cu.end) busy = star_cur_next(g, cu, win, in);
                 }
             }
             if (searching) {
@@ -173,7 +194,7 @@ GT_INLINE int star_point(const StarGrid<Idx>& g, int ip, bool active, int w0, bo
                 }
                 if (done) searching = false;
                 else {
-                    const StarWin in = win; win = star_win_grow(g, win, 1);
+                    in = win; win = star_win_grow(g, win, 1);
                     STAR_STAT(expand, 1);
                     busy = star_cur_begin(g, cu, win, in);
                 }
@@ -184,69 +205,104 @@ GT_INLINE int star_point(const StarGrid<Idx>& g, int ip, bool active, int w0, bo
     bool walking = active;
     if (walking && q0 < 0) { *hull = true; walking = false; }                 // (n >= 3 and no other point: cannot happen)
     if (walking && l1 < 4e-24) { err |= STAR_DUP; walking = false; }          // within 1e-12 in x and y: the reference's duplicate rule (delaunay_tri.c:440-452)
-    // The rounded distances may not decide which point is nearest (the -corr points of a box edge are equidistant from
-    // their two neighbours): then the start edge p -> q0 is verified instead -- it is Delaunay iff the best point on its
-    // right is not inside the circle through the best point on its left (modes 0 and 1 below; a hull edge is Delaunay).
-    const bool ambiguous = !(l2 > l1 * (1.0 + 16.0 * GT_EPS));
+    if (walking && !(l2 > l1 * (1.0 + 16.0 * GT_EPS))) {
+        // The rounded distances do not decide which of q0 and b2 is nearer (the -corr points of a box edge are equidistant
+        // from their two neighbours). p -> q0 is still a Delaunay (Gabriel) edge if b2 is outside the circle with diameter
+        // p q0 -- every other point is strictly farther from p than q0 and therefore outside it: (b2 - p).(b2 - q0) > 0.
+        bool okay = l3 > l1 * (1.0 + 16.0 * GT_EPS);
+        if (okay) {
+            const SPt B = g.pt[b2], Q0 = g.pt[q0];
+            const double t1 = (B.x - px) * (B.x - Q0.x), t2 = (B.y - py) * (B.y - Q0.y);
+            okay = t1 + t2 > 1e-12 * (fabs(t1) + fabs(t2));
+        }
+        if (!okay) { err |= STAR_TIE; walking = false; }
+    }
 
     // ---------------------------------------------------------------- the walks
-    // mode 0 / 1: one step from q0 to its left / right (verification of an ambiguous start edge, nothing is emitted)
-    // mode 2: counter-clockwise walk from q0 until the star closes or reaches the hull
-    // mode 3: clockwise walk from q0 (open stars only) = the same code on mirrored y
+    // mir = 0: counter-clockwise, mir = 1: clockwise = the same code on mirrored y.
+    // FULL: the whole star -- counter-clockwise from q0 until it closes or reaches the hull, then (open stars) clockwise from
+    //   q0; *hull says whether the star is open.
+    // !FULL: only the arc of neighbours that are lexicographically greater than p -- a triangle is owned by its smallest
+    //   vertex, so that arc holds every triangle p has to report (2 of the ~6 around an interior point). From a greater
+    //   q0: counter-clockwise while the neighbours stay greater, then clockwise from q0 likewise. From another q0: towards
+    //   the arc by the shorter way (q0 above p: clockwise), through it, and if the hull came first, the other way round.
     const int guard_max = 4 * g.n + 64;
-    int guard = 0;
-    int mode = ambiguous ? 0 : 2;
-    int vl = -1;                                              // best left point of the start edge (mode 0)
+    int guard = 0, mir = 0;
+    uint32_t ym = 0;                                              // sign-bit mask of the mirrored walk
     if (q0 < 0) q0 = 0;
-    int cur = q0; double yd = 1.0, qdx = q0dx, qdy = q0dy, ql = l1;
+    const bool q0_greater = q0dx > 0.0 || (q0dx == 0.0 && q0dy > 0.0);
+    bool in_arc = q0_greater, second = false;                     // (!FULL) cur is in the arc; this is the second direction
+    if (!FULL && !q0_greater && q0dy > 0.0) { mir = 1; ym = 0x80000000u; }
+    int cur = q0; double qdx = q0dx, qdy = star_flip(q0dy, ym), ql = l1;
     while (STAR_ANY(walking)) {
         // ---- one step for every walking lane: best left candidate of p -> cur; ties against the best so far are remembered
         int r = -1; double rdx = 0.0, rdy = 0.0, rl = 0.0, mc = 0.0, mcp = 0.0; bool tie = false;
-        const SPt Q = g.pt[cur];
         bool scanning = walking;
         bool found = false;
-        bool busy = scanning && star_cur_begin(g, cu, win, none);
+        in = none;
+        bool busy = scanning && star_cur_begin(g, cu, win, in);
         if (walking) { STAR_STAT(steps, 1); if (++guard > guard_max) { err |= STAR_GUARD; walking = scanning = busy = false; } }
         for (;;) {
-            while (STAR_ANY(busy)) {
-                if (busy) {
+            // ---- pass 1: which candidates are left of p -> cur? They go to the lane's list. (Two passes instead of one loop that
+            // does everything for a candidate: a candidate is left for half the lanes and beats the best so far for a tenth, and
+            // a warp pays for every branch any of its lanes takes -- the one-loop version ran its incircle part at 9 lanes and
+            // its update at 4. A full list ends the pass for the lane; it resumes after pass 2.)
+            int cnt = 0;
+            while (STAR_ANY(busy && cnt < LCAP)) {
+                if (busy && cnt < LCAP) {
                     const int pos = cu.pos;
                     const SPt S = g.pt[pos];
-                    const double sdx = S.x - px, sdy = yd * (S.y - py);
-                    // left of p -> cur?  orient2d(cur, s, p): detleft = qdx * sdy, detright = qdy * sdx (predicates.c:1628-1651).
-                    // One comparison decides: when the two products do not have the same strict sign, |det| = |dl| + |dr| = dsum.
+                    const double sdx = S.x - px, sdy = star_flip(S.y - py, ym);
+                    // orient2d(cur, s, p): detleft = qdx * sdy, detright = qdy * sdx (predicates.c:1628-1651). One comparison
+                    // decides: when the two products do not have the same strict sign, |det| = |dl| + |dr| = dsum.
                     const double dl = qdx * sdy, dr = qdy * sdx, det = dl - dr, dsum = fabs(dl) + fabs(dr);
-                    int sg = (det > 0.0 && pos != cur) ? 1 : 0;                     // (s = cur: det is exactly 0; s = p: all zero)
+                    bool left = det > 0.0 && pos != cur;                             // (s = cur: det is exactly 0; s = p: all zero)
                     if (!(fabs(det) >= GT_CCW_ERRBOUND_A * dsum) && pos != cur) {
-                        sg = star_orient_exact(Q.x, yd * Q.y, S.x, yd * S.y, px, yd * py);
-                        if (sg == GT_RANGE_ERR) { err |= STAR_RANGE; sg = 0; }
+                        const SPt Q = g.pt[cur];
+                        const int sg = star_orient_exact(Q.x, star_flip(Q.y, ym), S.x, star_flip(S.y, ym), px, star_flip(py, ym));
+                        if (sg == GT_RANGE_ERR) err |= STAR_RANGE;
+                        left = sg == 1;
                     }
                     STAR_STAT(cand, 1);
-                    if (sg > 0) {
-                        STAR_STAT(left, 1);
-                        const double sl = sdx * sdx + sdy * sdy;
-                        int ig = 1;
-                        if (r >= 0) {
-                            // s inside circle(p, cur, r)?  incircle(a = r, b = cur, c = s, d = p), predicates.c:3238-3267
-                            STAR_STAT(icc, 1);
-                            const double cdxady = sdx * rdy, adxcdy = rdx * sdy;
-                            const double ta = rl * det, tb = ql * (cdxady - adxcdy), tc = sl * mc;
-                            const double idet = (ta + tb) + tc;
-                            const double perm = dsum * rl + (fabs(cdxady) + fabs(adxcdy)) * ql + mcp * sl;
-                            const double eb = GT_ICC_ERRBOUND_A * perm;
-                            ig = idet > eb ? 1 : -1;
-                            if (!(fabs(idet) > eb)) {
-                                const SPt R = g.pt[r];
-                                ig = star_incircle_exact(R.x, yd * R.y, Q.x, yd * Q.y, S.x, yd * S.y, px, yd * py);
-                                if (ig == GT_RANGE_ERR) { err |= STAR_RANGE; ig = -1; }
-                            }
-                        }
-                        if (ig > 0) { r = pos; rdx = sdx; rdy = sdy; rl = sl; mc = dr - dl; mcp = dsum; tie = false; }
-                        else if (ig == 0) tie = true;
-                    }
-                    if (++cu.pos >= cu.end) busy = star_cur_next(g, cu);
+                    if (left) { lst.put(cnt, pos); ++cnt; STAR_STAT(left, 1); }
+                    if (++cu.pos >= cu.end) busy = star_cur_next(g, cu, win, in);
                 }
             }
+            // ---- pass 2: the best of the list (and of what earlier rounds of this step found): s beats r when it is inside
+            // circle(p, cur, r) = incircle(a = r, b = cur, c = s, d = p) > 0, predicates.c:3238-3267
+            int k = 0;
+            if (cnt > 0 && r < 0) {                                                  // the first left candidate of the step
+                const int pos = lst.get(0);
+                const SPt S = g.pt[pos];
+                const double sdx = S.x - px, sdy = star_flip(S.y - py, ym);
+                const double dl = qdx * sdy, dr = qdy * sdx;
+                r = pos; rdx = sdx; rdy = sdy; rl = sdx * sdx + sdy * sdy; mc = dr - dl; mcp = fabs(dl) + fabs(dr); tie = false;
+                k = 1;
+            }
+            while (STAR_ANY(k < cnt)) {
+                if (k < cnt) {
+                    const int pos = lst.get(k); ++k;
+                    const SPt S = g.pt[pos];
+                    const double sdx = S.x - px, sdy = star_flip(S.y - py, ym);
+                    const double dl = qdx * sdy, dr = qdy * sdx, det = dl - dr, dsum = fabs(dl) + fabs(dr);
+                    const double sl = sdx * sdx + sdy * sdy;
+                    STAR_STAT(icc, 1);
+                    const double cdxady = sdx * rdy, adxcdy = rdx * sdy;
+                    const double ta = rl * det, tb = ql * (cdxady - adxcdy), tc = sl * mc;
+                    const double idet = (ta + tb) + tc;
+                    const double perm = dsum * rl + (fabs(cdxady) + fabs(adxcdy)) * ql + mcp * sl;
+                    const double eb = GT_ICC_ERRBOUND_A * perm;
+                    int ig = idet > eb ? 1 : -1;
+                    if (!(fabs(idet) > eb)) {
+                        const SPt R = g.pt[r], Q = g.pt[cur];
+                        ig = star_incircle_exact(R.x, star_flip(R.y, ym), Q.x, star_flip(Q.y, ym), S.x, star_flip(S.y, ym), px, star_flip(py, ym));
+                        if (ig == GT_RANGE_ERR) { err |= STAR_RANGE; ig = -1; }
+                    }
+                    if (ig > 0) { r = pos; rdx = sdx; rdy = sdy; rl = sl; mc = dr - dl; mcp = dsum; tie = false; }
+                    else if (ig == 0) tie = true;
+                }
+            }
+            if (STAR_ANY(busy)) continue;                                            // a lane's list was full: it goes on scanning
             // ---- the scan of the window (or of its newest ring) is over: is the answer final?
             if (scanning) {
                 bool done = false;
@@ -262,17 +318,18 @@ GT_INLINE int star_point(const StarGrid<Idx>& g, int ip, bool active, int w0, bo
                         const double ex = 4.0 * GT_EPS * (fabs(ax) + fabs(bx)) * fabs(iD) + fabs(ux) * relD;
                         const double ey = 4.0 * GT_EPS * (fabs(ay) + fabs(by)) * fabs(iD) + fabs(uy) * relD;
                         const double m = 2.0 * (ex + ey) + 1e-12 * R + 8.0 * GT_EPS * (fabs(px) + fabs(py) + R + fabs(ux) + fabs(uy));
-                        const double cy = py + yd * uy;
+                        const double cy = py + star_flip(uy, ym);
                         if (star_covers(g, win, (px + ux) - R - m, (px + ux) + R + m, cy - R - m, cy + R + m)) { found = true; done = true; }
                     }
                 } else {
                     // no point on the left inside the window: p -> cur is a hull edge if the whole bounding box is on its right
                     STAR_STAT(hullcert, 1);
+                    const SPt Q = g.pt[cur];
                     bool right = true;
 #pragma unroll 1
                     for (int c = 0; c < 4 && right; ++c) {
                         const double bx = (c & 1) ? g.xmax : g.xmin, by = (c & 2) ? g.ymax : g.ymin;
-                        const int sg = star_orient_exact(Q.x, yd * Q.y, bx, yd * by, px, yd * py);
+                        const int sg = star_orient_exact(Q.x, star_flip(Q.y, ym), bx, star_flip(by, ym), px, star_flip(py, ym));
                         if (sg == GT_RANGE_ERR) { err |= STAR_RANGE; right = false; }
                         else if (sg > 0) right = false;
                     }
@@ -280,7 +337,7 @@ GT_INLINE int star_point(const StarGrid<Idx>& g, int ip, bool active, int w0, bo
                 }
                 if (done) scanning = false;
                 else {
-                    const StarWin in = win; win = star_win_grow(g, win, 1);
+                    in = win; win = star_win_grow(g, win, 1);
                     STAR_STAT(expand, 1);
                     busy = star_cur_begin(g, cu, win, in);
                 }
@@ -289,36 +346,37 @@ GT_INLINE int star_point(const StarGrid<Idx>& g, int ip, bool active, int w0, bo
         }
         // ---- transition
         if (walking) {
-            bool next_mode = false;
+            // triangle (p, cur, r) is counter-clockwise in walk coordinates; p owns it when cur and r are greater than p
+            const bool own_q = qdx > 0.0 || (qdx == 0.0 && star_flip(qdy, ym) > 0.0), own_r = rdx > 0.0 || (rdx == 0.0 && star_flip(rdy, ym) > 0.0);
+            bool turn = false;                                     // this direction is over
             if (err) walking = false;
             else if (found && tie) { err |= STAR_TIE; walking = false; }
-            else if (mode < 2) {
-                // verification of the start edge (hull edges are Delaunay)
-                if (mode == 0) vl = found ? r : -1;
-                else if (found && vl >= 0) {
-                    const SPt L = g.pt[vl], R = g.pt[r];
-                    const int ig = star_incircle_exact(px, py, Q.x, Q.y, L.x, L.y, R.x, R.y);     // (p, q0, left) is counter-clockwise
-                    if (ig == GT_RANGE_ERR) { err |= STAR_RANGE; walking = false; }
-                    else if (ig >= 0) { err |= STAR_TIE; walking = false; }     // cocircular, or q0 is not a neighbour after all: not decided here
-                }
-                next_mode = true;
-            } else if (!found) {
-                *hull = true;                                     // hull edge: this walk is over
-                if (mode == 3) walking = false; else next_mode = true;
-            } else {
-                // triangle (p, cur, r), counter-clockwise in walk coordinates
-                const bool own_q = qdx > 0.0 || (qdx == 0.0 && yd * qdy > 0.0), own_r = rdx > 0.0 || (rdx == 0.0 && yd * rdy > 0.0);
-                if (own_q && own_r) { if (mode == 3) emit(r, cur); else emit(cur, r); }
+            else if (!found) { *hull = true; turn = true; }        // hull edge
+            else if (FULL) {
+                if (own_q && own_r) { if (mir) emit(r, cur); else emit(cur, r); }
                 cur = r; qdx = rdx; qdy = rdy; ql = rl;
                 if (r == q0) {
-                    if (mode == 3) err |= STAR_GUARD;              // an open star cannot come back to its start
+                    if (mir) err |= STAR_GUARD;                    // an open star cannot come back to its start
                     walking = false;                               // closed
                 }
+            } else {
+                if (in_arc && !own_r) turn = true;                 // left the arc: nothing owned beyond
+                else {
+                    if (in_arc) { if (mir) emit(r, cur); else emit(cur, r); }
+                    in_arc = own_r;
+                    cur = r; qdx = rdx; qdy = rdy; ql = rl;
+                    if (r == q0) { err |= STAR_GUARD; walking = false; }      // (a closed star has neighbours on both sides of p)
+                }
             }
-            if (next_mode && walking) {
-                ++mode;
-                yd = (mode & 1) ? -1.0 : 1.0;
-                cur = q0; qdx = q0dx; qdy = yd * q0dy; ql = l1;
+            if (turn && walking) {
+                // the other direction from q0 -- unless this was it, or (!FULL) the arc has been walked through already
+                // (a walk leaves the arc the moment it steps out of it: in_arc == false here means it never got in)
+                const bool again = !second && (FULL || q0_greater || !in_arc);
+                if (!again) walking = false;
+                else {
+                    second = true; mir ^= 1; ym ^= 0x80000000u; in_arc = q0_greater;
+                    cur = q0; qdx = q0dx; qdy = star_flip(q0dy, ym); ql = l1;
+                }
             }
         }
     }

@@ -8,6 +8,7 @@ emu = conftest.emu.__wrapped__()
 chk = RefOracle() if ref_available() else PortOracle()
 w0 = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 dens = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+full = (sys.argv[3] != '0') if len(sys.argv) > 3 else True
 names = "cand left icc exact expand steps points hullcert nhull gx gy".split()
 for cfg, nfr in ((1, 20), (3, 20), (5, 4)):
     c = synth.config(cfg, nframes=nfr)
@@ -17,7 +18,7 @@ for cfg, nfr in ((1, 20), (3, 20), (5, 4)):
         nc = int(r["ncorr"][f])
         p = np.concatenate([c["xyz"][f, :, :2], r["corr"][f, :nc, :2]])
         want, _ = chk.triangulate(p)
-        tri, st, cnt = emu.star(p, w0, dens)
+        tri, st, cnt = emu.star(p, w0, dens, full)
         tot += np.array(cnt)
         if tri is None:
             continue

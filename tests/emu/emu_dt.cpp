@@ -185,7 +185,7 @@ int emu_triangulate_lpf(const double* points, int n, int* tri_out, long* iters_o
 // -(STAR_* bits) when the frame is not certified (ties, duplicates), or -64 when the triangle count is not 2(n-1)-h.
 // stats_out (nullable): [0] candidates visited, [1] left of the edge, [2] incircle filters, [3] exact-stage calls,
 // [4] window expansions, [5] walk steps, [6] points, [7] hull certificates, [8] hull vertices, [9] gx, [10] gy
-int emu_star(const double* points, int n, int w0, double dens, int* tri_out, long* stats_out) {
+int emu_star(const double* points, int n, int w0, double dens, int full, int* tri_out, long* stats_out) {
     using namespace gt;
     if (n < 2) return -1000;
     memset(&g_star, 0, sizeof g_star);
@@ -211,10 +211,13 @@ int emu_star(const double* points, int n, int w0, double dens, int* tri_out, lon
     int nt = 0, st = 0, nh = 0;
     for (int ip = 0; ip < n; ++ip) {
         bool hull = false;
-        st |= star_point(g, ip, true, w0, &hull, [&](int n1, int n2) {
+        struct { int v[8]; void put(int k, int pos) { v[k] = pos; } int get(int k) const { return v[k]; } } lst;      // (a short list: the refill path is exercised)
+        auto emit = [&](int n1, int n2) {
             tri_out[3 * nt] = id[ip]; tri_out[3 * nt + 1] = id[n1]; tri_out[3 * nt + 2] = id[n2];
             ++nt;
-        });
+        };
+        if (full) st |= star_point<8, true>(g, ip, true, w0, lst, &hull, emit);
+        else st |= star_point<8, false>(g, ip, true, w0, lst, &hull, emit);
         nh += hull;
     }
     if (stats_out) {
@@ -223,6 +226,17 @@ int emu_star(const double* points, int n, int w0, double dens, int* tri_out, lon
         stats_out[8] = nh; stats_out[9] = d.gx; stats_out[10] = d.gy;
     }
     if (st) return -st;
+    if (!full) {
+        // arcs only: the hull size is not known from the walks. When the four corners of the bounding box are points, the hull
+        // is that rectangle and its vertices are the points on it (the -corr case); otherwise the count is not checked here.
+        int corners = 0; nh = 0;
+        for (int i = 0; i < n; ++i) {
+            const double x = points[2 * i], y = points[2 * i + 1];
+            const bool bx = x == xmin || x == xmax, by = y == ymin || y == ymax;
+            nh += bx || by; corners += bx && by;
+        }
+        if (corners < 4) return nt;
+    }
     if (nt != 2 * (n - 1) - nh) return -64;
     return nt;
 }

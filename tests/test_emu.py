@@ -147,8 +147,9 @@ def test_star_path_matches_oracle_on_configs(emu, checker):
         for f in range(nfr):
             p = np.concatenate([c["xyz"][f, :, :2], r["corr"][f, :int(r["ncorr"][f]), :2]])
             want, _ = checker.triangulate(p)
-            tri, st, _ = emu.star(p)
-            assert st == 0 and np.array_equal(_canon(tri), _canon(want)), (cfg, f, st)
+            for full in (True, False):
+                tri, st, _ = emu.star(p, full=full)
+                assert st == 0 and np.array_equal(_canon(tri), _canon(want)), (cfg, f, st, full)
     c = synth.config(5, nframes=3)
     r = checker.tessellate(c["xyz"], c["box"], c["espace"], c["flags"], want_corr=True)
     for f in range(3):
@@ -164,14 +165,15 @@ def test_star_path_random_sizes_and_windows(emu, checker):
     for n in list(range(2, 30)) + [64, 65, 129, 500, 1157, 3000]:
         p = rng.random((n, 2)) * np.array([3.0, 7.0])
         want, _ = checker.triangulate(p)
-        for w0, dens in ((2, 1.0), (0, 1.0), (1, 4.0), (3, 0.5)):
-            tri, st, _ = emu.star(p, w0, dens)
-            assert st == 0 and np.array_equal(_canon(tri), _canon(want)), (n, w0, dens, st)
+        for w0, dens, full in ((2, 1.0, True), (0, 1.0, True), (1, 4.0, False), (3, 0.5, False), (2, 1.0, False)):
+            tri, st, _ = emu.star(p, w0, dens, full)
+            assert st == 0 and np.array_equal(_canon(tri), _canon(want)), (n, w0, dens, full, st)
     # clustered points: windows must grow a lot, the result stays exact
     p = np.concatenate([rng.normal(0, 0.01, (300, 2)), rng.normal(5, 2.0, (300, 2)), rng.random((50, 2)) * 40])
     want, _ = checker.triangulate(p)
-    tri, st, cnt = emu.star(p)
-    assert st == 0 and cnt[4] > 0 and np.array_equal(_canon(tri), _canon(want))
+    for full in (True, False):
+        tri, st, cnt = emu.star(p, full=full)
+        assert st == 0 and cnt[4] > 0 and np.array_equal(_canon(tri), _canon(want))
 
 
 def test_star_path_refuses_what_it_cannot_certify(emu, golden):
