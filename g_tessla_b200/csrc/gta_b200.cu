@@ -194,7 +194,7 @@ int path_mode() {
     return v;
 }
 int star_threads(int cap, int forced) {
-    if (forced == 64 || forced == 128 || forced == 256 || forced == 384) return forced;
+    if (forced == 64 || forced == 128 || forced == 256 || forced == 320 || forced == 384) return forced;
     return cap <= 160 ? 64 : (cap <= 512 ? 128 : 256);
 }
 bool use_star(const gt::KParams& p, const Shape& s) {
@@ -262,7 +262,8 @@ int launch_star(const gt::KParams& p, const Shape& s, int* fb_list, unsigned int
     switch (threads) {
         case 64: return full ? go(gt::star_kernel<64, 8, true>, 64) : go(gt::star_kernel<64, 8, false>, 64);
         case 128: return full ? go(gt::star_kernel<128, 4, true>, 128) : go(gt::star_kernel<128, 4, false>, 128);
-        case 384: return full ? go(gt::star_kernel<384, 1, true>, 384) : go(gt::star_kernel<384, 1, false>, 384);
+        case 320: return full ? go(gt::star_kernel<320, 2, true>, 320) : go(gt::star_kernel<320, 2, false>, 320);
+        case 384: return full ? go(gt::star_kernel<384, 2, true>, 384) : go(gt::star_kernel<384, 2, false>, 384);
         default: return full ? go(gt::star_kernel<256, 2, true>, 256) : go(gt::star_kernel<256, 2, false>, 256);
     }
 }

@@ -32,6 +32,7 @@ namespace gt {
 #endif
 
 constexpr int STAR_LCAP = 24;                  // left candidates a lane keeps per round of a walk step (star_core.cuh)
+constexpr int STAR_CCAP = 40;                  // candidates a lane keeps (the points of its window); more: it walks the grid
 
 struct StarParams {
     KParams k;
@@ -40,23 +41,32 @@ struct StarParams {
 };
 
 struct StarSmem {
-    size_t tile, corr, spt, sz, sid, tmp, cell, cstart, csum, lists, ctl, total;
+    // persistent over a frame: cell-sorted points (double, float, z, input index), cell starts, chunk sums, control words.
+    // setup (tile, -corr points, scatter scratch) and star phase (the threads' candidate / left lists) share one region.
+    size_t spt, sptf, sz, cstart, sid, csum, ctl, tile, corr, tmp, cell, clist, lists, total;
     int ncell_max;
     __host__ __device__ StarSmem(int cap, int natoms, int in_dim, int threads) {
         size_t o = 0;
-        tile = o; o += (((size_t)natoms * in_dim * 8) + 15) & ~(size_t)15;       // bulk-copy destination
-        corr = o; o += 24 * (size_t)(cap > natoms ? cap - natoms : 0); o = (o + 15) & ~(size_t)15;
         spt = o; o += sizeof(SPt) * (size_t)cap;                                // cell-sorted (x, y); -corr scratch before that
         sz = o; o += 8 * (size_t)cap;                                           // cell-sorted z
+        sptf = o; o += sizeof(SPtF) * (size_t)cap;                              // cell-sorted (x, y) in float
         ncell_max = cap;
         cstart = o; o += 4 * (size_t)(ncell_max + 2);
         sid = o; o += 2 * (size_t)cap;                                          // cell-sorted input index
-        tmp = o; o += 2 * (size_t)cap;                                          // scatter order
-        cell = o; o += 2 * (size_t)cap;                                         // cell of each input point
         o = (o + 15) & ~(size_t)15;
         csum = o; o += 16 * (size_t)((cap + 31) / 32 + 1);                      // area sums of every chunk of 32 points
-        lists = o; o += 2 * (size_t)STAR_LCAP * threads;                        // every thread's list of left candidates
         ctl = o; o += 16 * 4 + 8 * 32 * 8 + 8;                                  // status / counters, reduction scratch, one mbarrier
+        o = (o + 127) & ~(size_t)127;
+        const size_t shared0 = o;
+        tile = o; o += (((size_t)natoms * in_dim * 8) + 15) & ~(size_t)15;       // bulk-copy destination
+        corr = o; o += 24 * (size_t)(cap > natoms ? cap - natoms : 0); o = (o + 15) & ~(size_t)15;
+        tmp = o; o += 2 * (size_t)cap;                                          // scatter order
+        cell = o; o += 2 * (size_t)cap;                                         // cell of each input point
+        const size_t setup_end = o;
+        o = shared0;
+        clist = o; o += 2 * (size_t)STAR_CCAP * threads;                        // every thread's candidates (its window's points)
+        lists = o; o += 2 * (size_t)STAR_LCAP * threads;                        // every thread's left candidates of the current step
+        o = o > setup_end ? o : setup_end;
         total = (o + 15) & ~(size_t)15;
     }
 };
@@ -74,6 +84,8 @@ __global__ void __launch_bounds__(T, MINB) star_kernel(const StarParams sp) {
     double* tile = reinterpret_cast<double*>(ssm + L.tile);
     double* corr3 = reinterpret_cast<double*>(ssm + L.corr);
     SPt* spt = reinterpret_cast<SPt*>(ssm + L.spt);
+    SPtF* sptf = reinterpret_cast<SPtF*>(ssm + L.sptf);
+    u16* clist = reinterpret_cast<u16*>(ssm + L.clist);                     // [STAR_CCAP][T]
     double* sz = reinterpret_cast<double*>(ssm + L.sz);
     uint32_t* cbase = reinterpret_cast<uint32_t*>(ssm + L.cstart);         // cstart[0 .. ncell]
     u16* sid = reinterpret_cast<u16*>(ssm + L.sid);
@@ -167,6 +179,7 @@ __global__ void __launch_bounds__(T, MINB) star_kernel(const StarParams sp) {
                 for (int q = s; q < e; ++q) rank += tmp[q] < i;
                 SPt v; v.x = px(i); v.y = py(i);
                 spt[s + rank] = v; sz[s + rank] = pz(i); sid[s + rank] = (u16)i;
+                SPtF vf; vf.x = (float)v.x; vf.y = (float)v.y; sptf[s + rank] = vf;
                 if (!FULL) {
                     // points on the bounding box: when its four corners are points, they are the hull vertices (triangle count rule)
                     const bool ex = v.x == xlo || v.x == xhi, ey = v.y == ylo || v.y == yhi;
@@ -175,14 +188,14 @@ __global__ void __launch_bounds__(T, MINB) star_kernel(const StarParams sp) {
                 }
             }
             __syncthreads();
-            // the tile is dead from here on: the next frame's coordinates arrive while this frame's stars are built
-            if (bulk && tid == 0 && fr + stride < p.nframes) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                pp_bulk_load(tile, p.xyz + (size_t)(fr + stride) * natoms * in_dim, frame_bytes, mbar);
-            }
+            // the next frame's coordinates are pulled into L2 while this frame's stars are built (the tile's shared memory holds
+            // the threads' lists during the star phase, so the copy itself starts when the frame is done)
+            if (bulk && tid == 0 && fr + stride < p.nframes)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p.xyz + (size_t)(fr + stride) * natoms * in_dim), "r"(frame_bytes) : "memory");
             // ---------------------------------------------------------------- stars + areas
             StarGrid<uint32_t> g;
-            g.pt = spt; g.cstart = cbase; g.n = n; g.gx = dm.gx; g.gy = dm.gy;
+            g.pt = spt; g.ptf = sptf; g.cstart = cbase;
+            g.kf = (float)(2.5 * 5.9604644775390625e-08 * fmax(fmax(fabs(xlo), fabs(xhi)), fmax(fabs(ylo), fabs(yhi)))) * 1.0001f; g.n = n; g.gx = dm.gx; g.gy = dm.gy;
             g.x0 = xlo; g.y0 = ylo; g.sx = dm.sx; g.sy = dm.sy; g.xmin = xlo; g.xmax = xhi; g.ymin = ylo; g.ymax = yhi;
             int* tri_out = p.tri ? p.tri + (size_t)fr * p.tri_cap * 3 : nullptr;
             // A warp's 32 lanes build the stars of 32 consecutive positions in lockstep (all of them call star_point, lanes
@@ -195,9 +208,11 @@ __global__ void __launch_bounds__(T, MINB) star_kernel(const StarParams sp) {
                 const SPt P = spt[active ? ip : 0]; const double zp = sz[active ? ip : 0];
                 double c3 = 0.0, c2 = 0.0;
                 bool hull = false;
-                struct { u16* base; __device__ void put(int k, int pos) { base[k * T] = (u16)pos; } __device__ int get(int k) const { return base[k * T]; } } lst;
-                lst.base = lists + tid;
-                st |= star_point<STAR_LCAP, FULL>(g, ip, active, GT_STAR_W0, lst, &hull, [&](int n1, int n2) {
+                struct { u16* base; u16* cbase;
+                         __device__ void put(int k, int pos) { base[k * T] = (u16)pos; } __device__ int get(int k) const { return base[k * T]; }
+                         __device__ void cput(int k, int pos) { cbase[k * T] = (u16)pos; } __device__ int cget(int k) const { return cbase[k * T]; } } lst;
+                lst.base = lists + tid; lst.cbase = clist + tid;
+                st |= star_point<STAR_LCAP, STAR_CCAP, FULL>(g, ip, active, GT_STAR_W0, lst, &hull, [&](int n1, int n2) {
                     const SPt A = spt[n1], B = spt[n2];
                     c3 += tri_area3(P.x, P.y, zp, A.x, A.y, sz[n1], B.x, B.y, sz[n2]);
                     if (want2d) c2 += tri_area3(P.x, P.y, 0.0, A.x, A.y, 0.0, B.x, B.y, 0.0);
@@ -214,9 +229,6 @@ __global__ void __launch_bounds__(T, MINB) star_kernel(const StarParams sp) {
                 if (lane == 0) { csum[2 * ch] = c3; csum[2 * ch + 1] = c2; nextch = (int)atomicAdd(&ctl[3], 1u); }
                 ch = __shfl_sync(0xffffffffu, nextch, 0);
             }
-        } else if (bulk && tid == 0 && fr + stride < p.nframes) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            pp_bulk_load(tile, p.xyz + (size_t)(fr + stride) * natoms * in_dim, frame_bytes, mbar);
         }
         // ---------------------------------------------------------------- the frame's sums (fixed order) and its verdict
         unsigned packed = ((unsigned)ntri << 12) | (unsigned)nhull;          // (n <= 4,094 points here: 2n triangles fit 20 bits)
@@ -248,6 +260,10 @@ __global__ void __launch_bounds__(T, MINB) star_kernel(const StarParams sp) {
             if (sp.counters) atomicAdd(&sp.counters[certified ? 0 : 1], 1ull);
         }
         __syncthreads();
+        if (bulk && tid == 0 && fr + stride < p.nframes) {                  // (the lists are dead: the tile's memory takes the next frame)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            pp_bulk_load(tile, p.xyz + (size_t)(fr + stride) * natoms * in_dim, frame_bytes, mbar);
+        }
     }
 }
 

@@ -32,6 +32,7 @@
 namespace gt {
 
 struct alignas(16) SPt { double x, y; };
+struct alignas(8) SPtF { float x, y; };                       // the same point rounded to float (screening only)
 
 enum { STAR_TIE = 1, STAR_DUP = 2, STAR_GUARD = 4, STAR_RANGE = 8 };
 
@@ -39,6 +40,8 @@ enum { STAR_TIE = 1, STAR_DUP = 2, STAR_GUARD = 4, STAR_RANGE = 8 };
 template <class Idx>
 struct StarGrid {
     const SPt* pt;             // [n] cell-sorted coordinates
+    const SPtF* ptf;           // [n] the same, rounded to float
+    float kf;                  // 2.5 * 2^-24 * (largest |coordinate| of the frame): what the rounding to float can move a coordinate difference by, with slack
     const Idx* cstart;         // [gx * gy + 1]
     int n, gx, gy;
     double x0, y0, sx, sy;     // col = trunc((x - x0) * sx) clamped to [0, gx-1]; row likewise: monotone in x / y
@@ -120,6 +123,13 @@ GT_INLINE bool star_cur_begin(const StarGrid<Idx>& g, StarCursor& c, const StarW
     return star_cur_next(g, c, w, in);
 }
 // v or -v (m = 0 or the sign bit of the high word): mirrors a coordinate without a trip through the FP64 pipe
+GT_INLINE float star_flipf(float v, uint32_t m) {
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(__float_as_int(v) ^ (int)m);
+#else
+    return m ? -v : v;
+#endif
+}
 GT_INLINE double star_flip(double v, uint32_t m) {
 #if defined(__CUDA_ARCH__)
     return __hiloint2double(__double2hiint(v) ^ (int)m, __double2loint(v));
@@ -148,74 +158,262 @@ GT_NOINLINE int star_incircle_exact(double ax, double ay, double bx, double by, 
 #define STAR_ANY(x) (x)
 #endif
 
-// Star of the point at position `ip`. emit(n1_pos, n2_pos) for every triangle (ip, n1, n2) it owns; *hull = the star is
-// open (ip is a hull vertex). `w0` = half-width of the first window in cells. Returns STAR_* bits (0: certified).
-// `lst` = the lane's list of LCAP candidate positions (put(k, pos) / get(k)): shared memory on the device.
-template <int LCAP, bool FULL, class Idx, class List, class Emit>
-GT_INLINE int star_point(const StarGrid<Idx>& g, int ip, bool active, int w0, List&& lst, bool* hull, Emit&& emit) {
-    *hull = false;
-    if (g.n < 3) { *hull = active; return 0; }                // (uniform: n is the frame's)
-    if (!active) ip = 0;
-    const SPt P = g.pt[ip];
-    const double px = P.x, py = P.y;
-    if (active) STAR_STAT(points, 1);
+// One lane's state. It lives in local memory between the passes of a step; every pass is its own out-of-line function
+// that loads what it needs into registers and writes back what it changed. (Written as one function, the compiler kept
+// some fifty values live across the two hot loops and spilled in the middle of them: 10 % of all instructions were local
+// loads and stores. This way the loops run in a small register set and the state moves once per pass.)
+struct StarLane {
+    double px, py;                              // the point
+    float pxf, pyf; int ip;
+    StarWin win;                                // the window its candidates come from
+    int m, overflow;                            // candidates in the lane's list; the window holds more than the list
+    int q0, b2; double l1, l2, l3, q0dx, q0dy;  // nearest neighbour, runner-up, the three smallest squared distances
+    int cur; double qdx, qdy, ql; uint32_t ym;  // current edge p -> cur (coordinates relative to p, y mirrored on clockwise walks)
+    int r, tie; double rdx, rdy, rl, mc, mcp;   // best left candidate of the step so far, and whether something tied with it
+    int err;
+};
+
+// Nearest neighbour of the lane's point (and the two runners-up); the window's points become the lane's candidate list.
+template <int CCAP, class Idx, class List>
+GT_NOINLINE void star_nn(const StarGrid<Idx>& g, List lst, StarLane& L, bool active, int w0) {
+    const int ip = L.ip;
+    const double px = L.px, py = L.py;
     StarWin none; none.c0 = 1; none.c1 = 0; none.r0 = 1; none.r1 = 0;
     StarWin win, in = none;
     win.c0 = win.c1 = star_cell(px, g.x0, g.sx, g.gx); win.r0 = win.r1 = star_cell(py, g.y0, g.sy, g.gy);
     win = star_win_grow(g, win, w0);
-    int err = 0;
-    StarCursor cu;
-
-    // ---------------------------------------------------------------- nearest neighbour (and the two runners-up)
     const double BIG = 1.7976931348623157e308;
     int q0 = -1, b2 = -1; double l1 = BIG, l2 = BIG, l3 = BIG, q0dx = 0.0, q0dy = 0.0;
-    {
-        bool searching = active;
-        bool busy = searching && star_cur_begin(g, cu, win, none);
-        for (;;) {
-            while (STAR_ANY(busy)) {
-                if (busy) {
-                    const int pos = cu.pos;
-                    const SPt S = g.pt[pos];
-                    const double dx = S.x - px, dy = S.y - py, l = dx * dx + dy * dy;
-                    if (pos != ip) {
-                        if (l < l1) { l3 = l2; l2 = l1; b2 = q0; l1 = l; q0 = pos; q0dx = dx; q0dy = dy; }
-                        else if (l < l2) { l3 = l2; l2 = l; b2 = pos; }
-                        else if (l < l3) l3 = l;
-                    }
-                    if (++cu.pos >= cu.end) busy = star_cur_next(g, cu, win, in);
+    int m = 0; bool overflow = false;
+    StarCursor cu;
+    bool searching = active;
+    bool busy = searching && star_cur_begin(g, cu, win, none);
+    for (;;) {
+        while (STAR_ANY(busy)) {
+            if (busy) {
+                const int pos = cu.pos;
+                const SPt S = g.pt[pos];
+                const double dx = S.x - px, dy = S.y - py, l = dx * dx + dy * dy;
+                if (pos != ip) {
+                    if (l < l1) { l3 = l2; l2 = l1; b2 = q0; l1 = l; q0 = pos; q0dx = dx; q0dy = dy; }
+                    else if (l < l2) { l3 = l2; l2 = l; b2 = pos; }
+                    else if (l < l3) l3 = l;
+                    if (m < CCAP) { lst.cput(m, pos); ++m; } else overflow = true;
+                }
+                if (++cu.pos >= cu.end) busy = star_cur_next(g, cu, win, in);
+            }
+        }
+        if (searching) {
+            bool done = star_win_all(g, win);
+            if (!done && q0 >= 0) {
+                const double d = sqrt(l1) * (1.0 + 1e-9), mg = 8.0 * GT_EPS * (fabs(px) + fabs(py) + d);
+                done = star_covers(g, win, px - d - mg, px + d + mg, py - d - mg, py + d + mg);
+            }
+            if (done) searching = false;
+            else {
+                in = win; win = star_win_grow(g, win, 1);
+                STAR_STAT(expand, 1);
+                busy = star_cur_begin(g, cu, win, in);
+            }
+        }
+        if (!STAR_ANY(searching)) break;
+    }
+    L.win = win; L.m = m; L.overflow = overflow ? 1 : 0;
+    L.q0 = q0; L.b2 = b2; L.l1 = l1; L.l2 = l2; L.l3 = l3; L.q0dx = q0dx; L.q0dy = q0dy;
+}
+
+// Pass 1 of a walk step, from the lane's candidate list: which candidates are left of p -> cur? They go to the lane's list
+// of left candidates. Screened in float: orient2d(cur, s, p) = a d - b c on float coordinates is off by at most
+// kf (|a| + |b|) + 5 2^-24 (|a d| + |b c|) from the real determinant; beyond that its sign is the real one. Closer to the
+// line: the reference's own filter in double (predicates.c:1628-1651), then the exact stage.
+// kk = next entry of the candidate list; returns kk | cnt << 16 (cnt = entries of the left list).
+template <int LCAP, class Idx, class List>
+GT_NOINLINE int star_pass1_list(const StarGrid<Idx>& g, List lst, StarLane& L, int kk) {
+    const int m = L.m, cur = L.cur;
+    const uint32_t ym = L.ym;
+    const float pxf = L.pxf, pyf = L.pyf;
+    const float af = (float)L.qdx, bf = (float)L.qdy, kfab = g.kf * (fabsf(af) + fabsf(bf));
+    int cnt = 0;
+    while (STAR_ANY(kk < m && cnt < LCAP)) {
+        if (kk < m && cnt < LCAP) {
+            const int pos = lst.cget(kk); ++kk;
+            const SPtF F = g.ptf[pos];
+            const float c = F.x - pxf, d = star_flipf(F.y - pyf, ym);
+            const float dlf = af * d, drf = bf * c, detf = dlf - drf;
+            bool left = detf > 0.0f;
+            if (!(fabsf(detf) > kfab + 6e-7f * (fabsf(dlf) + fabsf(drf))) && pos != cur) {
+                const SPt S = g.pt[pos];
+                const double px = L.px, py = L.py, qdx = L.qdx, qdy = L.qdy;
+                const double sdx = S.x - px, sdy = star_flip(S.y - py, ym);
+                const double dl = qdx * sdy, dr = qdy * sdx, det = dl - dr, dsum = fabs(dl) + fabs(dr);
+                left = det > 0.0;
+                if (!(fabs(det) >= GT_CCW_ERRBOUND_A * dsum)) {
+                    const SPt Q = g.pt[cur];
+                    const int sg = star_orient_exact(Q.x, star_flip(Q.y, ym), S.x, star_flip(S.y, ym), px, star_flip(py, ym));
+                    if (sg == GT_RANGE_ERR) L.err |= STAR_RANGE;
+                    left = sg == 1;
                 }
             }
-            if (searching) {
-                bool done = star_win_all(g, win);
-                if (!done && q0 >= 0) {
-                    const double d = sqrt(l1) * (1.0 + 1e-9), m = 8.0 * GT_EPS * (fabs(px) + fabs(py) + d);
-                    done = star_covers(g, win, px - d - m, px + d + m, py - d - m, py + d + m);
-                }
-                if (done) searching = false;
-                else {
-                    in = win; win = star_win_grow(g, win, 1);
-                    STAR_STAT(expand, 1);
-                    busy = star_cur_begin(g, cu, win, in);
-                }
-            }
-            if (!STAR_ANY(searching)) break;
+            STAR_STAT(cand, 1);
+            if (left && pos != cur) { lst.put(cnt, pos); ++cnt; STAR_STAT(left, 1); }
         }
     }
+    return kk | (cnt << 16);
+}
+
+// Pass 1 from the grid (a window with more points than the candidate list holds, or the ring a grown window adds; rare).
+// Ring points also join the candidate list, so that later steps find them there. Returns cnt.
+template <int LCAP, int CCAP, class Idx, class List>
+GT_NOINLINE int star_pass1_grid(const StarGrid<Idx>& g, List lst, StarLane& L, StarCursor& cu, const StarWin& in, bool* busy_io, int cnt) {
+    const int cur = L.cur, ip = L.ip;
+    const uint32_t ym = L.ym;
+    const double px = L.px, py = L.py, qdx = L.qdx, qdy = L.qdy;
+    const StarWin win = L.win;
+    int m = L.m; bool overflow = L.overflow != 0;
+    bool busy = *busy_io;
+    while (STAR_ANY(busy && cnt < LCAP)) {
+        if (busy && cnt < LCAP) {
+            const int pos = cu.pos;
+            const SPt S = g.pt[pos];
+            const double sdx = S.x - px, sdy = star_flip(S.y - py, ym);
+            // orient2d(cur, s, p): detleft = qdx * sdy, detright = qdy * sdx. One comparison decides: when the two products do
+            // not have the same strict sign, |det| = |dl| + |dr| = dsum.
+            const double dl = qdx * sdy, dr = qdy * sdx, det = dl - dr, dsum = fabs(dl) + fabs(dr);
+            bool left = det > 0.0 && pos != cur;                             // (s = cur: det is exactly 0; s = p: all zero)
+            if (!(fabs(det) >= GT_CCW_ERRBOUND_A * dsum) && pos != cur) {
+                const SPt Q = g.pt[cur];
+                const int sg = star_orient_exact(Q.x, star_flip(Q.y, ym), S.x, star_flip(S.y, ym), px, star_flip(py, ym));
+                if (sg == GT_RANGE_ERR) L.err |= STAR_RANGE;
+                left = sg == 1;
+            }
+            STAR_STAT(cand, 1);
+            if (left) { lst.put(cnt, pos); ++cnt; STAR_STAT(left, 1); }
+            if (!overflow && pos != ip) { if (m < CCAP) { lst.cput(m, pos); ++m; } else overflow = true; }
+            if (++cu.pos >= cu.end) busy = star_cur_next(g, cu, win, in);
+        }
+    }
+    L.m = m; L.overflow = overflow ? 1 : 0;
+    *busy_io = busy;
+    return cnt;
+}
+
+// Pass 2: the best of the left list (and of what earlier rounds of this step found): s beats r when it is inside
+// circle(p, cur, r) = incircle(a = r, b = cur, c = s, d = p) > 0: the reference's filter (predicates.c:3238-3267), then exact.
+template <class Idx, class List>
+GT_NOINLINE void star_pass2(const StarGrid<Idx>& g, List lst, StarLane& L, int cnt) {
+    const uint32_t ym = L.ym;
+    const double px = L.px, py = L.py, qdx = L.qdx, qdy = L.qdy, ql = L.ql;
+    int r = L.r; double rdx = L.rdx, rdy = L.rdy, rl = L.rl, mc = L.mc, mcp = L.mcp; bool tie = L.tie != 0;
+    int k = 0;
+    if (cnt > 0 && r < 0) {                                                  // the first left candidate of the step
+        const int pos = lst.get(0);
+        const SPt S = g.pt[pos];
+        const double sdx = S.x - px, sdy = star_flip(S.y - py, ym);
+        const double dl = qdx * sdy, dr = qdy * sdx;
+        r = pos; rdx = sdx; rdy = sdy; rl = sdx * sdx + sdy * sdy; mc = dr - dl; mcp = fabs(dl) + fabs(dr); tie = false;
+        k = 1;
+    }
+    while (STAR_ANY(k < cnt)) {
+        if (k < cnt) {
+            const int pos = lst.get(k); ++k;
+            const SPt S = g.pt[pos];
+            const double sdx = S.x - px, sdy = star_flip(S.y - py, ym);
+            const double dl = qdx * sdy, dr = qdy * sdx, det = dl - dr, dsum = fabs(dl) + fabs(dr);
+            const double sl = sdx * sdx + sdy * sdy;
+            STAR_STAT(icc, 1);
+            const double cdxady = sdx * rdy, adxcdy = rdx * sdy;
+            const double ta = rl * det, tb = ql * (cdxady - adxcdy), tc = sl * mc;
+            const double idet = (ta + tb) + tc;
+            const double perm = dsum * rl + (fabs(cdxady) + fabs(adxcdy)) * ql + mcp * sl;
+            const double eb = GT_ICC_ERRBOUND_A * perm;
+            int ig = idet > eb ? 1 : -1;
+            if (!(fabs(idet) > eb)) {
+                const SPt R = g.pt[r], Q = g.pt[L.cur];
+                ig = star_incircle_exact(R.x, star_flip(R.y, ym), Q.x, star_flip(Q.y, ym), S.x, star_flip(S.y, ym), px, star_flip(py, ym));
+                if (ig == GT_RANGE_ERR) { L.err |= STAR_RANGE; ig = -1; }
+            }
+            if (ig > 0) { r = pos; rdx = sdx; rdy = sdy; rl = sl; mc = dr - dl; mcp = dsum; tie = false; }
+            else if (ig == 0) tie = true;
+        }
+    }
+    L.r = r; L.rdx = rdx; L.rdy = rdy; L.rl = rl; L.mc = mc; L.mcp = mcp; L.tie = tie ? 1 : 0;
+}
+
+// The scan of the window (or of its newest ring) is over: is the answer final? 1: yes, r is the next neighbour; 2: yes, p -> cur
+// is a hull edge; 0: no -- the window has been grown by one ring and the cursor stands on it (*busy: the ring is not empty).
+template <class Idx>
+GT_NOINLINE int star_certify(const StarGrid<Idx>& g, StarLane& L, StarCursor& cu, StarWin& in, bool* busy) {
+    const StarWin win = L.win;
+    const double px = L.px, py = L.py;
+    const uint32_t ym = L.ym;
+    const int r = L.r;
+    if (star_win_all(g, win)) return r >= 0 ? 1 : 2;
+    if (r >= 0) {
+        // circumdisc of (0, q', r') inside the window?  D = 2 cross(q', r') = -2 mc > 0
+        const double mc = L.mc, mcp = L.mcp;
+        if (fabs(mc) * 1048576.0 >= mcp) {
+            const double qdx = L.qdx, qdy = L.qdy, ql = L.ql, rdx = L.rdx, rdy = L.rdy, rl = L.rl;
+            const double D = -2.0 * mc, iD = 1.0 / D;
+            const double ax = rdy * ql, bx = qdy * rl, ay = qdx * rl, by = rdx * ql;
+            const double ux = (ax - bx) * iD, uy = (ay - by) * iD;
+            const double R = sqrt(ux * ux + uy * uy);
+            const double relD = 4.0 * GT_EPS * mcp / fabs(mc) + 8.0 * GT_EPS;
+            const double ex = 4.0 * GT_EPS * (fabs(ax) + fabs(bx)) * fabs(iD) + fabs(ux) * relD;
+            const double ey = 4.0 * GT_EPS * (fabs(ay) + fabs(by)) * fabs(iD) + fabs(uy) * relD;
+            const double mg = 2.0 * (ex + ey) + 1e-12 * R + 8.0 * GT_EPS * (fabs(px) + fabs(py) + R + fabs(ux) + fabs(uy));
+            const double cy = py + star_flip(uy, ym);
+            if (star_covers(g, win, (px + ux) - R - mg, (px + ux) + R + mg, cy - R - mg, cy + R + mg)) return 1;
+        }
+    } else {
+        // no point on the left inside the window: p -> cur is a hull edge if the whole bounding box is on its right
+        STAR_STAT(hullcert, 1);
+        const SPt Q = g.pt[L.cur];
+        bool right = true;
+#pragma unroll 1
+        for (int c = 0; c < 4 && right; ++c) {
+            const double bx = (c & 1) ? g.xmax : g.xmin, by = (c & 2) ? g.ymax : g.ymin;
+            const int sg = star_orient_exact(Q.x, star_flip(Q.y, ym), bx, star_flip(by, ym), px, star_flip(py, ym));
+            if (sg == GT_RANGE_ERR) { L.err |= STAR_RANGE; right = false; }
+            else if (sg > 0) right = false;
+        }
+        if (right) return 2;
+    }
+    in = win; L.win = star_win_grow(g, win, 1);
+    STAR_STAT(expand, 1);
+    *busy = star_cur_begin(g, cu, L.win, in);
+    return 0;
+}
+
+// Star of the point at position `ip`. emit(n1_pos, n2_pos) for every triangle (ip, n1, n2) it owns; *hull = the star is
+// open (ip is a hull vertex; FULL only). `w0` = half-width of the first window in cells. Returns STAR_* bits (0: certified).
+// `lst` = the lane's two lists of positions in shared memory: its candidates (cput / cget, CCAP entries) and the left
+// candidates of the current step (put / get, LCAP entries).
+template <int LCAP, int CCAP, bool FULL, class Idx, class List, class Emit>
+GT_INLINE int star_point(const StarGrid<Idx>& g, int ip, bool active, int w0, List lst, bool* hull, Emit&& emit) {
+    *hull = false;
+    if (g.n < 3) { *hull = active; return 0; }                // (uniform: n is the frame's)
+    if (!active) ip = 0;
+    StarLane L;
+    {
+        const SPt P = g.pt[ip]; const SPtF PF = g.ptf[ip];
+        L.px = P.x; L.py = P.y; L.pxf = PF.x; L.pyf = PF.y; L.ip = ip; L.err = 0;
+    }
+    if (active) STAR_STAT(points, 1);
+    star_nn<CCAP>(g, lst, L, active, w0);
     bool walking = active;
-    if (walking && q0 < 0) { *hull = true; walking = false; }                 // (n >= 3 and no other point: cannot happen)
-    if (walking && l1 < 4e-24) { err |= STAR_DUP; walking = false; }          // within 1e-12 in x and y: the reference's duplicate rule (delaunay_tri.c:440-452)
-    if (walking && !(l2 > l1 * (1.0 + 16.0 * GT_EPS))) {
+    if (walking && L.q0 < 0) { *hull = true; walking = false; }               // (n >= 3 and no other point: cannot happen)
+    if (walking && L.l1 < 4e-24) { L.err |= STAR_DUP; walking = false; }      // within 1e-12 in x and y: the reference's duplicate rule (delaunay_tri.c:440-452)
+    if (walking && !(L.l2 > L.l1 * (1.0 + 16.0 * GT_EPS))) {
         // The rounded distances do not decide which of q0 and b2 is nearer (the -corr points of a box edge are equidistant
         // from their two neighbours). p -> q0 is still a Delaunay (Gabriel) edge if b2 is outside the circle with diameter
         // p q0 -- every other point is strictly farther from p than q0 and therefore outside it: (b2 - p).(b2 - q0) > 0.
-        bool okay = l3 > l1 * (1.0 + 16.0 * GT_EPS);
+        bool okay = L.l3 > L.l1 * (1.0 + 16.0 * GT_EPS);
         if (okay) {
-            const SPt B = g.pt[b2], Q0 = g.pt[q0];
-            const double t1 = (B.x - px) * (B.x - Q0.x), t2 = (B.y - py) * (B.y - Q0.y);
+            const SPt B = g.pt[L.b2], Q0 = g.pt[L.q0];
+            const double t1 = (B.x - L.px) * (B.x - Q0.x), t2 = (B.y - L.py) * (B.y - Q0.y);
             okay = t1 + t2 > 1e-12 * (fabs(t1) + fabs(t2));
         }
-        if (!okay) { err |= STAR_TIE; walking = false; }
+        if (!okay) { L.err |= STAR_TIE; walking = false; }
     }
 
     // ---------------------------------------------------------------- the walks
@@ -228,135 +426,61 @@ GT_INLINE int star_point(const StarGrid<Idx>& g, int ip, bool active, int w0, Li
     //   the arc by the shorter way (q0 above p: clockwise), through it, and if the hull came first, the other way round.
     const int guard_max = 4 * g.n + 64;
     int guard = 0, mir = 0;
-    uint32_t ym = 0;                                              // sign-bit mask of the mirrored walk
-    if (q0 < 0) q0 = 0;
-    const bool q0_greater = q0dx > 0.0 || (q0dx == 0.0 && q0dy > 0.0);
+    if (L.q0 < 0) L.q0 = 0;
+    const int q0 = L.q0;
+    const bool q0_greater = L.q0dx > 0.0 || (L.q0dx == 0.0 && L.q0dy > 0.0);
     bool in_arc = q0_greater, second = false;                     // (!FULL) cur is in the arc; this is the second direction
-    if (!FULL && !q0_greater && q0dy > 0.0) { mir = 1; ym = 0x80000000u; }
-    int cur = q0; double qdx = q0dx, qdy = star_flip(q0dy, ym), ql = l1;
+    if (!FULL && !q0_greater && L.q0dy > 0.0) mir = 1;
+    L.ym = mir ? 0x80000000u : 0u;
+    L.cur = q0; L.qdx = L.q0dx; L.qdy = star_flip(L.q0dy, L.ym); L.ql = L.l1;
+    StarWin none; none.c0 = 1; none.c1 = 0; none.r0 = 1; none.r1 = 0;
+    StarCursor cu;
     while (STAR_ANY(walking)) {
         // ---- one step for every walking lane: best left candidate of p -> cur; ties against the best so far are remembered
-        int r = -1; double rdx = 0.0, rdy = 0.0, rl = 0.0, mc = 0.0, mcp = 0.0; bool tie = false;
+        L.r = -1; L.tie = 0;
         bool scanning = walking;
-        bool found = false;
-        in = none;
-        bool busy = scanning && star_cur_begin(g, cu, win, in);
-        if (walking) { STAR_STAT(steps, 1); if (++guard > guard_max) { err |= STAR_GUARD; walking = scanning = busy = false; } }
+        if (walking) { STAR_STAT(steps, 1); if (++guard > guard_max) { L.err |= STAR_GUARD; walking = scanning = false; } }
+        // the candidates come from the lane's list; a lane whose window holds more than the list walks the grid instead
+        StarWin in = none;
+        int kk = (scanning && !L.overflow) ? 0 : L.m;
+        bool busy = scanning && L.overflow && star_cur_begin(g, cu, L.win, in);
+        int found = 0;
         for (;;) {
-            // ---- pass 1: which candidates are left of p -> cur? They go to the lane's list. (Two passes instead of one loop that
-            // does everything for a candidate: a candidate is left for half the lanes and beats the best so far for a tenth, and
-            // a warp pays for every branch any of its lanes takes -- the one-loop version ran its incircle part at 9 lanes and
-            // its update at 4. A full list ends the pass for the lane; it resumes after pass 2.)
-            int cnt = 0;
-            while (STAR_ANY(busy && cnt < LCAP)) {
-                if (busy && cnt < LCAP) {
-                    const int pos = cu.pos;
-                    const SPt S = g.pt[pos];
-                    const double sdx = S.x - px, sdy = star_flip(S.y - py, ym);
-                    // orient2d(cur, s, p): detleft = qdx * sdy, detright = qdy * sdx (predicates.c:1628-1651). One comparison
-                    // decides: when the two products do not have the same strict sign, |det| = |dl| + |dr| = dsum.
-                    const double dl = qdx * sdy, dr = qdy * sdx, det = dl - dr, dsum = fabs(dl) + fabs(dr);
-                    bool left = det > 0.0 && pos != cur;                             // (s = cur: det is exactly 0; s = p: all zero)
-                    if (!(fabs(det) >= GT_CCW_ERRBOUND_A * dsum) && pos != cur) {
-                        const SPt Q = g.pt[cur];
-                        const int sg = star_orient_exact(Q.x, star_flip(Q.y, ym), S.x, star_flip(S.y, ym), px, star_flip(py, ym));
-                        if (sg == GT_RANGE_ERR) err |= STAR_RANGE;
-                        left = sg == 1;
-                    }
-                    STAR_STAT(cand, 1);
-                    if (left) { lst.put(cnt, pos); ++cnt; STAR_STAT(left, 1); }
-                    if (++cu.pos >= cu.end) busy = star_cur_next(g, cu, win, in);
-                }
+            // Two passes instead of one loop that does everything for a candidate: a candidate is left for half the lanes and
+            // beats the best so far for a tenth, and a warp pays for every branch any of its lanes takes -- the one-loop version
+            // ran its incircle part at 9 lanes and its update at 4. A full left list ends pass 1 for the lane; it resumes after pass 2.
+            const int pc = star_pass1_list<LCAP>(g, lst, L, kk);
+            kk = pc & 0xffff;
+            int cnt = pc >> 16;
+            if (STAR_ANY(busy)) {
+                const bool grid = busy;
+                cnt = star_pass1_grid<LCAP, CCAP>(g, lst, L, cu, in, &busy, cnt);
+                if (grid) kk = L.m;                                // (what a ring added to the candidate list has been seen)
             }
-            // ---- pass 2: the best of the list (and of what earlier rounds of this step found): s beats r when it is inside
-            // circle(p, cur, r) = incircle(a = r, b = cur, c = s, d = p) > 0, predicates.c:3238-3267
-            int k = 0;
-            if (cnt > 0 && r < 0) {                                                  // the first left candidate of the step
-                const int pos = lst.get(0);
-                const SPt S = g.pt[pos];
-                const double sdx = S.x - px, sdy = star_flip(S.y - py, ym);
-                const double dl = qdx * sdy, dr = qdy * sdx;
-                r = pos; rdx = sdx; rdy = sdy; rl = sdx * sdx + sdy * sdy; mc = dr - dl; mcp = fabs(dl) + fabs(dr); tie = false;
-                k = 1;
-            }
-            while (STAR_ANY(k < cnt)) {
-                if (k < cnt) {
-                    const int pos = lst.get(k); ++k;
-                    const SPt S = g.pt[pos];
-                    const double sdx = S.x - px, sdy = star_flip(S.y - py, ym);
-                    const double dl = qdx * sdy, dr = qdy * sdx, det = dl - dr, dsum = fabs(dl) + fabs(dr);
-                    const double sl = sdx * sdx + sdy * sdy;
-                    STAR_STAT(icc, 1);
-                    const double cdxady = sdx * rdy, adxcdy = rdx * sdy;
-                    const double ta = rl * det, tb = ql * (cdxady - adxcdy), tc = sl * mc;
-                    const double idet = (ta + tb) + tc;
-                    const double perm = dsum * rl + (fabs(cdxady) + fabs(adxcdy)) * ql + mcp * sl;
-                    const double eb = GT_ICC_ERRBOUND_A * perm;
-                    int ig = idet > eb ? 1 : -1;
-                    if (!(fabs(idet) > eb)) {
-                        const SPt R = g.pt[r], Q = g.pt[cur];
-                        ig = star_incircle_exact(R.x, star_flip(R.y, ym), Q.x, star_flip(Q.y, ym), S.x, star_flip(S.y, ym), px, star_flip(py, ym));
-                        if (ig == GT_RANGE_ERR) { err |= STAR_RANGE; ig = -1; }
-                    }
-                    if (ig > 0) { r = pos; rdx = sdx; rdy = sdy; rl = sl; mc = dr - dl; mcp = dsum; tie = false; }
-                    else if (ig == 0) tie = true;
-                }
-            }
-            if (STAR_ANY(busy)) continue;                                            // a lane's list was full: it goes on scanning
-            // ---- the scan of the window (or of its newest ring) is over: is the answer final?
+            star_pass2(g, lst, L, cnt);
+            if (STAR_ANY(busy || kk < L.m)) continue;                                // a lane's left list was full: it goes on
             if (scanning) {
-                bool done = false;
-                if (star_win_all(g, win)) { found = r >= 0; done = true; }
-                else if (r >= 0) {
-                    // circumdisc of (0, q', r') inside the window?  D = 2 cross(q', r') = -2 mc > 0
-                    if (fabs(mc) * 1048576.0 >= mcp) {
-                        const double D = -2.0 * mc, iD = 1.0 / D;
-                        const double ax = rdy * ql, bx = qdy * rl, ay = qdx * rl, by = rdx * ql;
-                        const double ux = (ax - bx) * iD, uy = (ay - by) * iD;
-                        const double R = sqrt(ux * ux + uy * uy);
-                        const double relD = 4.0 * GT_EPS * mcp / fabs(mc) + 8.0 * GT_EPS;
-                        const double ex = 4.0 * GT_EPS * (fabs(ax) + fabs(bx)) * fabs(iD) + fabs(ux) * relD;
-                        const double ey = 4.0 * GT_EPS * (fabs(ay) + fabs(by)) * fabs(iD) + fabs(uy) * relD;
-                        const double m = 2.0 * (ex + ey) + 1e-12 * R + 8.0 * GT_EPS * (fabs(px) + fabs(py) + R + fabs(ux) + fabs(uy));
-                        const double cy = py + star_flip(uy, ym);
-                        if (star_covers(g, win, (px + ux) - R - m, (px + ux) + R + m, cy - R - m, cy + R + m)) { found = true; done = true; }
-                    }
-                } else {
-                    // no point on the left inside the window: p -> cur is a hull edge if the whole bounding box is on its right
-                    STAR_STAT(hullcert, 1);
-                    const SPt Q = g.pt[cur];
-                    bool right = true;
-#pragma unroll 1
-                    for (int c = 0; c < 4 && right; ++c) {
-                        const double bx = (c & 1) ? g.xmax : g.xmin, by = (c & 2) ? g.ymax : g.ymin;
-                        const int sg = star_orient_exact(Q.x, star_flip(Q.y, ym), bx, star_flip(by, ym), px, star_flip(py, ym));
-                        if (sg == GT_RANGE_ERR) { err |= STAR_RANGE; right = false; }
-                        else if (sg > 0) right = false;
-                    }
-                    if (right) { found = false; done = true; }
-                }
-                if (done) scanning = false;
-                else {
-                    in = win; win = star_win_grow(g, win, 1);
-                    STAR_STAT(expand, 1);
-                    busy = star_cur_begin(g, cu, win, in);
-                }
+                found = star_certify(g, L, cu, in, &busy);
+                if (found) scanning = false; else kk = L.m;       // (the ring is read from the grid; pass 1 appends it to the list)
             }
             if (!STAR_ANY(scanning)) break;
         }
         // ---- transition
         if (walking) {
+            const uint32_t ym = L.ym;
+            const int r = L.r, cur = L.cur;
+            const double qdx = L.qdx, qdy = L.qdy, rdx = L.rdx, rdy = L.rdy;
             // triangle (p, cur, r) is counter-clockwise in walk coordinates; p owns it when cur and r are greater than p
             const bool own_q = qdx > 0.0 || (qdx == 0.0 && star_flip(qdy, ym) > 0.0), own_r = rdx > 0.0 || (rdx == 0.0 && star_flip(rdy, ym) > 0.0);
             bool turn = false;                                     // this direction is over
-            if (err) walking = false;
-            else if (found && tie) { err |= STAR_TIE; walking = false; }
-            else if (!found) { *hull = true; turn = true; }        // hull edge
+            if (L.err) walking = false;
+            else if (found == 1 && L.tie) { L.err |= STAR_TIE; walking = false; }
+            else if (found != 1) { *hull = true; turn = true; }    // hull edge
             else if (FULL) {
                 if (own_q && own_r) { if (mir) emit(r, cur); else emit(cur, r); }
-                cur = r; qdx = rdx; qdy = rdy; ql = rl;
+                L.cur = r; L.qdx = rdx; L.qdy = rdy; L.ql = L.rl;
                 if (r == q0) {
-                    if (mir) err |= STAR_GUARD;                    // an open star cannot come back to its start
+                    if (mir) L.err |= STAR_GUARD;                  // an open star cannot come back to its start
                     walking = false;                               // closed
                 }
             } else {
@@ -364,8 +488,8 @@ GT_INLINE int star_point(const StarGrid<Idx>& g, int ip, bool active, int w0, Li
                 else {
                     if (in_arc) { if (mir) emit(r, cur); else emit(cur, r); }
                     in_arc = own_r;
-                    cur = r; qdx = rdx; qdy = rdy; ql = rl;
-                    if (r == q0) { err |= STAR_GUARD; walking = false; }      // (a closed star has neighbours on both sides of p)
+                    L.cur = r; L.qdx = rdx; L.qdy = rdy; L.ql = L.rl;
+                    if (r == q0) { L.err |= STAR_GUARD; walking = false; }    // (a closed star has neighbours on both sides of p)
                 }
             }
             if (turn && walking) {
@@ -374,13 +498,13 @@ GT_INLINE int star_point(const StarGrid<Idx>& g, int ip, bool active, int w0, Li
                 const bool again = !second && (FULL || q0_greater || !in_arc);
                 if (!again) walking = false;
                 else {
-                    second = true; mir ^= 1; ym ^= 0x80000000u; in_arc = q0_greater;
-                    cur = q0; qdx = q0dx; qdy = star_flip(q0dy, ym); ql = l1;
+                    second = true; mir ^= 1; L.ym ^= 0x80000000u; in_arc = q0_greater;
+                    L.cur = q0; L.qdx = L.q0dx; L.qdy = star_flip(L.q0dy, L.ym); L.ql = L.l1;
                 }
             }
         }
     }
-    return err;
+    return L.err;
 }
 
 // Grid dimensions for n points in the bounding box [xmin, xmax] x [ymin, ymax]: about `dens` points per cell, cells about

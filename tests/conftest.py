@@ -69,7 +69,7 @@ def emu():
     L.emu_triangulate.argtypes = [dp, C.c_int, ip]
     L.emu_triangulate_lpf2.argtypes = [dp, C.c_int, C.c_int, C.c_uint, ip, C.POINTER(C.c_long)]
     L.emu_exact_stats.argtypes = [C.POINTER(C.c_long)]
-    L.emu_star.argtypes = [dp, C.c_int, C.c_int, C.c_double, C.c_int, ip, C.POINTER(C.c_long)]
+    L.emu_star.argtypes = [dp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, ip, C.POINTER(C.c_long)]
     for n in ("emu_orient2d_signs", "emu_incircle_signs", "emu_orient2d_exact", "emu_incircle_exact"):
         getattr(L, n).argtypes = [dp, C.c_int, ip]
 
@@ -91,12 +91,12 @@ def emu():
             assert nt >= 0, "emu error %d" % nt
             return out[:3 * nt].reshape(-1, 3).copy(), list(st)
 
-        def star(self, p, w0=2, dens=1.0, full=True):
+        def star(self, p, w0=2, dens=1.0, full=True, ccap=64):
             """The star path (star_core.cuh): (triangles in any order or None when the frame is not certified, status, counters)."""
             p = np.ascontiguousarray(p, dtype=np.float64)
             out = np.empty(3 * 2 * max(len(p), 1), dtype=np.int32)
             st = (C.c_long * 11)()
-            nt = L.emu_star(p.ctypes.data_as(dp), len(p), int(w0), float(dens), 1 if full else 0, out.ctypes.data_as(ip), st)
+            nt = L.emu_star(p.ctypes.data_as(dp), len(p), int(w0), float(dens), 1 if full else 0, int(ccap), out.ctypes.data_as(ip), st)
             if nt < 0:
                 return None, -nt, list(st)
             return out[:3 * nt].reshape(-1, 3).copy(), 0, list(st)

@@ -185,7 +185,7 @@ int emu_triangulate_lpf(const double* points, int n, int* tri_out, long* iters_o
 // -(STAR_* bits) when the frame is not certified (ties, duplicates), or -64 when the triangle count is not 2(n-1)-h.
 // stats_out (nullable): [0] candidates visited, [1] left of the edge, [2] incircle filters, [3] exact-stage calls,
 // [4] window expansions, [5] walk steps, [6] points, [7] hull certificates, [8] hull vertices, [9] gx, [10] gy
-int emu_star(const double* points, int n, int w0, double dens, int full, int* tri_out, long* stats_out) {
+int emu_star(const double* points, int n, int w0, double dens, int full, int ccap, int* tri_out, long* stats_out) {
     using namespace gt;
     if (n < 2) return -1000;
     memset(&g_star, 0, sizeof g_star);
@@ -205,19 +205,33 @@ int emu_star(const double* points, int n, int w0, double dens, int full, int* tr
     std::vector<int> cur(cstart.begin(), cstart.end() - 1);
     std::vector<SPt> pt(n);
     for (int i = 0; i < n; ++i) { const int pos = cur[cell[i]]++; pt[pos].x = points[2 * i]; pt[pos].y = points[2 * i + 1]; id[pos] = i; }
+    std::vector<SPtF> ptf(n);
+    double M = 0.0;
+    for (int i = 0; i < n; ++i) { ptf[i].x = (float)pt[i].x; ptf[i].y = (float)pt[i].y; M = std::max(M, std::max(fabs(pt[i].x), fabs(pt[i].y))); }
     StarGrid<int> g;
+    g.ptf = ptf.data(); g.kf = (float)(2.5 * 5.9604644775390625e-08 * M) * 1.0001f;
     g.pt = pt.data(); g.cstart = cstart.data(); g.n = n; g.gx = d.gx; g.gy = d.gy;
     g.x0 = xmin; g.y0 = ymin; g.sx = d.sx; g.sy = d.sy; g.xmin = xmin; g.xmax = xmax; g.ymin = ymin; g.ymax = ymax;
     int nt = 0, st = 0, nh = 0;
     for (int ip = 0; ip < n; ++ip) {
         bool hull = false;
-        struct { int v[8]; void put(int k, int pos) { v[k] = pos; } int get(int k) const { return v[k]; } } lst;      // (a short list: the refill path is exercised)
+        // (short lists: the refill of the left list and the overflow of the candidate list are exercised)
+        // (passed by value to the passes, like the device's pair of shared-memory pointers)
+        int lv[8], lc[64];
+        struct { int *v, *c; void put(int k, int pos) { v[k] = pos; } int get(int k) const { return v[k]; }
+                 void cput(int k, int pos) { c[k] = pos; } int cget(int k) const { return c[k]; } } lst;
+        lst.v = lv; lst.c = lc;
         auto emit = [&](int n1, int n2) {
             tri_out[3 * nt] = id[ip]; tri_out[3 * nt + 1] = id[n1]; tri_out[3 * nt + 2] = id[n2];
             ++nt;
         };
-        if (full) st |= star_point<8, true>(g, ip, true, w0, lst, &hull, emit);
-        else st |= star_point<8, false>(g, ip, true, w0, lst, &hull, emit);
+        if (ccap <= 12) {
+            if (full) st |= star_point<8, 12, true>(g, ip, true, w0, lst, &hull, emit);
+            else st |= star_point<8, 12, false>(g, ip, true, w0, lst, &hull, emit);
+        } else {
+            if (full) st |= star_point<8, 64, true>(g, ip, true, w0, lst, &hull, emit);
+            else st |= star_point<8, 64, false>(g, ip, true, w0, lst, &hull, emit);
+        }
         nh += hull;
     }
     if (stats_out) {

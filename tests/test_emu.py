@@ -147,9 +147,9 @@ def test_star_path_matches_oracle_on_configs(emu, checker):
         for f in range(nfr):
             p = np.concatenate([c["xyz"][f, :, :2], r["corr"][f, :int(r["ncorr"][f]), :2]])
             want, _ = checker.triangulate(p)
-            for full in (True, False):
-                tri, st, _ = emu.star(p, full=full)
-                assert st == 0 and np.array_equal(_canon(tri), _canon(want)), (cfg, f, st, full)
+            for full, ccap in ((True, 64), (False, 64), (False, 12)):
+                tri, st, _ = emu.star(p, full=full, ccap=ccap)
+                assert st == 0 and np.array_equal(_canon(tri), _canon(want)), (cfg, f, st, full, ccap)
     c = synth.config(5, nframes=3)
     r = checker.tessellate(c["xyz"], c["box"], c["espace"], c["flags"], want_corr=True)
     for f in range(3):
@@ -165,9 +165,9 @@ def test_star_path_random_sizes_and_windows(emu, checker):
     for n in list(range(2, 30)) + [64, 65, 129, 500, 1157, 3000]:
         p = rng.random((n, 2)) * np.array([3.0, 7.0])
         want, _ = checker.triangulate(p)
-        for w0, dens, full in ((2, 1.0, True), (0, 1.0, True), (1, 4.0, False), (3, 0.5, False), (2, 1.0, False)):
-            tri, st, _ = emu.star(p, w0, dens, full)
-            assert st == 0 and np.array_equal(_canon(tri), _canon(want)), (n, w0, dens, full, st)
+        for w0, dens, full, ccap in ((2, 1.0, True, 64), (0, 1.0, True, 12), (1, 4.0, False, 64), (3, 0.5, False, 12), (2, 1.0, False, 12)):
+            tri, st, _ = emu.star(p, w0, dens, full, ccap)
+            assert st == 0 and np.array_equal(_canon(tri), _canon(want)), (n, w0, dens, full, ccap, st)
     # clustered points: windows must grow a lot, the result stays exact
     p = np.concatenate([rng.normal(0, 0.01, (300, 2)), rng.normal(5, 2.0, (300, 2)), rng.random((50, 2)) * 40])
     want, _ = checker.triangulate(p)
