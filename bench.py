@@ -40,7 +40,7 @@ ALG_BYTES_PER_FRAME = NATOMS * 24 + 72 + 16      # coordinates +
 ALG_FLOP_PER_FRAME = 203.6e3                      # SURVEY.md §8d implementation-independent lower bound
 FP64_PEAK_TFLOPS_NOMINAL = 37.2                   # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz (fallback if the DFMA micro-benchmark fails)
 STRONG_FRAMES = 100000                            # BASELINE.json configs[2]: ONE 100k-frame trajectory, sharded over the GPUs
-TRAFFIC_JSON = os.path.join("profiles", "r2_walk_traffic.json")   # written by profiles/ncu_keys.py --json from an ncu --set full capture
+TRAFFIC_JSON = os.path.join("profiles", "r2_star_traffic.json")   # written by profiles/ncu_keys.py --json from an ncu --set full capture
 WORKLOAD = "cfg3: 2,048-lipid bilayer leaflet, 1,024 atoms/frame, -corr -espace 0.8, 3-D area"
 
 
@@ -231,6 +231,7 @@ def run_native(args):
             T.run(x, bx, 3)
         barrier()
         g.api.stage_ms(local_rank, reset=True)
+        g.api.star_counters(local_rank, reset=True)
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches = 0
@@ -271,6 +272,7 @@ def run_native(args):
         clocks.start()
     total_ms, kern_ms, launches_dev, T = resident_arm(F)
     stages = g.api.stage_ms(local_rank)
+    certified, fallback = g.api.star_counters(local_rank)
     status_bad = int((T.status != 0).sum().item())
     area_dev = T.area.cpu().numpy().copy()
     e2e_ms, launches_e2e, area, status = e2e_arm(F)
@@ -314,10 +316,12 @@ def run_native(args):
         value = frames_all / (total_ms / 1e3)
         e2e_v = frames_all / (e2e_ms / 1e3)
         nl = max(1, stages["launches"])
-        walk_ms = stages["walk"] / nl                        # dominant kernel: gt::lpf_wave_kernel, per launch, measured in this run
+        # dominant kernel of the step, per launch, measured in this run: the star kernel (or the walker kernel when the stars were skipped)
+        dom = "star" if stages["star"] >= stages["walk"] else "walk"
+        dom_ms = stages[dom] / nl
         frames_per_launch = F * args.steps / nl
-        ach = ALG_BYTES_PER_FRAME * frames_per_launch / (walk_ms / 1e3) / 1e9    # GB/s of algorithmic bytes per launch
-        stage_sum = max(1e-9, stages["prepass"] + stages["walk"] + stages["area"])
+        ach = ALG_BYTES_PER_FRAME * frames_per_launch / (dom_ms / 1e3) / 1e9     # GB/s of algorithmic bytes per launch
+        stage_sum = max(1e-9, stages["star"] + stages["prepass"] + stages["walk"] + stages["area"])
         # ncu dram bytes per frame of that kernel: from the committed capture summary, flagged when the kernels changed since
         traffic, traffic_meta = None, {"source": TRAFFIC_JSON, "stale": None}
         try:
@@ -339,7 +343,9 @@ def run_native(args):
             "mtriangles_per_s": value * TRI_PER_FRAME / 1e6,
             "config": workload_config(F),
             "run": {"l2": "inputs larger than L2 (%.2f GB of coordinates per step per GPU)" % (F * NATOMS * 24 / 1e9),
-                    "path": "throughput path: pre-pass (load, -corr, sort) + walker kernel (phase-sorted (frame, subtree) slots) + area kernel",
+                    "path": "star engine: one fused launch per chunk (load, -corr, grid binning, per-point Delaunay stars with exact predicates, areas); "
+                            "frames it does not certify (cocircular ties) go through pre-pass + walker kernel + area kernel inside the same call",
+                    "frames_certified_by_stars": certified, "frames_through_divide_and_conquer": fallback,
                     "parallelism": "frames sharded over %d GPU(s), no collective on the data path (final per-frame area gather only)" % world,
                     "generator": "device (torch CUDA generator), recipe of g_tessla_b200.synth.jittered_bilayer; seed 3 + 1000 * rank"},
             "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": F * (NATOMS * 24 + 24),
@@ -354,13 +360,14 @@ def run_native(args):
             "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                          "traffic": traffic, "traffic_unit": "GB per launch (ncu dram__bytes_read + dram__bytes_write per frame x frames per launch)",
                          "traffic_meta": traffic_meta, "peak_source": pk_src,
-                         "kernel": "gt::lpf_wave_kernel<512,false>",
-                         "kernel_share_of_step": stages["walk"] / stage_sum,
-                         "stage_ms_per_launch": {"prepass": stages["prepass"] / nl, "walk": walk_ms, "area": stages["area"] / nl},
+                         "kernel": "gt::star_kernel<256,2,false>" if dom == "star" else "gt::lpf_wave_kernel<512,false>",
+                         "kernel_share_of_step": stages[dom] / stage_sum,
+                         "stage_ms_per_launch": {"star": stages["star"] / nl, "prepass": stages["prepass"] / nl, "walk": stages["walk"] / nl, "area": stages["area"] / nl},
                          "launches_per_step": nl / args.steps, "frames_per_launch": frames_per_launch,
-                         "kernel_ms_per_launch": walk_ms, "pipeline_ms_per_step": kern_ms, "alg_bytes_per_frame": ALG_BYTES_PER_FRAME,
-                         "timing": "CUDA events on the launching stream around each kernel, inside the library (gta_b200_stage_ms), over the timed steps",
-                         "note": "latency-bound pointer chasing: the frames' half-edge rings live in an HBM workspace; neither roof is the limiter (DESIGN.md section 5)"},
+                         "kernel_ms_per_launch": dom_ms, "pipeline_ms_per_step": kern_ms, "alg_bytes_per_frame": ALG_BYTES_PER_FRAME,
+                         "timing": "CUDA events on the launching stream around each kernel, inside the library (gta_b200_stage_ms4), over the timed steps",
+                         "note": "the star kernel reads each coordinate once (DRAM traffic ~ the algorithmic bytes) and is bound by instruction issue and the FP64 pipe, "
+                                 "not by HBM: ~2,300 double-precision predicate operations per point against 24 bytes of input (DESIGN.md section 5)"},
             "roofline_fp64": {"achieved": fl, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fl / fp64_peak,
                               "peak_source": fp64_src, "alg_flop_per_frame": ALG_FLOP_PER_FRAME},
             "clocks": clk,

@@ -148,7 +148,7 @@ struct LpfCache {
     unsigned long long* undecided_h = nullptr;      // pinned; the device's running count after the last launch
     unsigned long long undecided_seen = 0; int last_frames = 0; bool pending = false, degenerate = false;
     // feedback for the star path: how many frames of the last star launch fell back to the divide-and-conquer pipeline
-    unsigned int* fb_h = nullptr; bool fb_pending = false; int fb_frames = 0, star_skip = 0, skip_natoms = -1, skip_cap = -1; cudaEvent_t fb_done = nullptr;
+    unsigned int* fb_h = nullptr; bool fb_pending = false; int fb_frames = 0, fb_natoms = -1, fb_cap = -1, star_skip = 0, skip_natoms = -1, skip_cap = -1; cudaEvent_t fb_done = nullptr;
     unsigned long long* star_counters = nullptr;     // device: [0] frames certified by their stars, [1] frames handed to the divide-and-conquer pipeline
     // stage timers: five events (start, after stars, after pre-pass, after walkers, after areas) per launch since gta_b200_stage_reset
     std::vector<cudaEvent_t> ev; size_t ev_used = 0;
@@ -310,7 +310,7 @@ int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st, bool star = false
     // (automatic mode only, and only for the trajectory shape that fell back)
     if (star && c->fb_pending && cudaEventQuery(c->fb_done) == cudaSuccess) {
         c->fb_pending = false;
-        if ((long long)*c->fb_h * 2 > (long long)c->fb_frames) { c->star_skip = 16; c->skip_natoms = p.natoms; c->skip_cap = s.cap; }
+        if ((long long)*c->fb_h * 2 > (long long)c->fb_frames) { c->star_skip = 16; c->skip_natoms = c->fb_natoms; c->skip_cap = c->fb_cap; }
     }
     if (star && path_mode() == 0 && c->star_skip > 0 && c->skip_natoms == p.natoms && c->skip_cap == s.cap) { --c->star_skip; star = false; }
     if (star) {
@@ -321,7 +321,7 @@ int launch_lpf(gt::KParams p, const Shape& s, cudaStream_t st, bool star = false
         if (!c->fb_pending) {
             CK(cudaMemcpyAsync(c->fb_h, ws.fb_count, 4, cudaMemcpyDeviceToHost, st));
             CK(cudaEventRecord(c->fb_done, st));
-            c->fb_pending = true; c->fb_frames = p.nframes;
+            c->fb_pending = true; c->fb_frames = p.nframes; c->fb_natoms = p.natoms; c->fb_cap = s.cap;
         }
         p.list = ws.fb_list; p.list_count = ws.fb_count;
     }

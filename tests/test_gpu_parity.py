@@ -219,9 +219,11 @@ def test_lane_per_frame_batch_larger_than_one_launch(gta, checker):
     assert np.allclose(area[0], want["area"], rtol=RTOL, atol=0)
     assert np.array_equal(T.areabox.cpu().numpy()[:500], want["areabox"])
     assert (T.ntri.cpu().numpy().reshape(reps, -1) == T.ntri.cpu().numpy()[:500]).all()
+    gta.star_counters(reset=True)
     r = gta.tessellate(xyz, box, c["espace"], c["flags"])       # host buffers: chunked pipeline
     assert (r["status"] == 0).all()
-    assert np.array_equal(r["area"].reshape(reps, -1), area)
+    d = r["area"].reshape(reps, -1) != area
+    assert not d.any(), (int(d.sum()), gta.star_counters(), np.unique(np.nonzero(d)[0])[:8], np.unique(np.nonzero(d)[1])[:8])
 
 
 def test_lane_per_frame_two_host_threads_one_device(gta, checker, lane_per_frame):
