@@ -29,7 +29,8 @@ class GtaError(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libgtessla_b200.so")
+    # (GTA_B200_LIB: an experiment build of the same sources, see scratch/README.md)
+    return os.environ.get("GTA_B200_LIB") or os.path.join(_HERE, "libgtessla_b200.so")
 
 
 def lib() -> C.CDLL:

@@ -25,19 +25,23 @@ def _stale(target: str, srcs: list[str]) -> bool:
     return any(os.path.getmtime(s) > t for s in srcs)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, out: str | None = None) -> str:
     """Compile every CUDA source for sm_100a. -fmad=false: the FP64 predicate filter and the area
     arithmetic must round every operation individually (reference predicates.c:123-133)."""
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h", ".c"))]
     srcs += [os.path.join(HERE, "..", "include", f) for f in sorted(os.listdir(os.path.join(HERE, "..", "include")))]
-    if force or _stale(LIB, srcs):
+    lib = out or LIB
+    if force or _stale(lib, srcs):
         cu = [s for s in srcs if s.endswith(".cu")]
         cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-               "-fmad=false", "-Xcompiler", "-fPIC,-O2,-fopenmp", "-shared", "-o", LIB, *cu,
+               "-fmad=false", "-Xcompiler", "-fPIC,-O2,-fopenmp", "-shared", "-o", lib, *cu,
                "-I" + os.path.join(HERE, "..", "include"), "-lgomp"]
+        cmd += os.environ.get("GTA_B200_NVCC_FLAGS", "").split()      # experiments: extra -D switches (scratch/README.md)
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.check_call(cmd, cwd=CSRC)
+    if out:
+        return lib
     cli_src = os.path.join(HERE, "cli", "g_tessla.c")
     if os.path.exists(cli_src) and (force or _stale(CLI, [cli_src, LIB])):
         subprocess.check_call(["gcc", "-std=c99", "-O2", "-Wall", "-o", CLI, cli_src,

@@ -251,6 +251,9 @@ int launch_star(const gt::KParams& p, const Shape& s, int* fb_list, unsigned int
     auto go = [&](auto kern, int threads) -> int {
         int occ = 0;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static int env_c; static std::once_flag once_c;      // experiments: GTA_B200_STAR_CARVE = shared-memory carve-out in percent
+        const int carve = env_once("GTA_B200_STAR_CARVE", 0, &env_c, &once_c);
+        if (carve > 0) CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
         if (occ < 1) return fail(GTA_B200_E_TOO_LARGE, "star kernel does not fit on an SM");
         const int grid = std::max(1, std::min(p.nframes, occ * sms));
@@ -264,7 +267,7 @@ int launch_star(const gt::KParams& p, const Shape& s, int* fb_list, unsigned int
         case 128: return full ? go(gt::star_kernel<128, 4, true>, 128) : go(gt::star_kernel<128, 4, false>, 128);
         case 320: return full ? go(gt::star_kernel<320, 2, true>, 320) : go(gt::star_kernel<320, 2, false>, 320);
         case 384: return full ? go(gt::star_kernel<384, 2, true>, 384) : go(gt::star_kernel<384, 2, false>, 384);
-        default: return full ? go(gt::star_kernel<256, 2, true>, 256) : go(gt::star_kernel<256, 2, false>, 256);
+        default: return full ? go(gt::star_kernel<256, GT_STAR_MINB, true>, 256) : go(gt::star_kernel<256, GT_STAR_MINB, false>, 256);
     }
 }
 

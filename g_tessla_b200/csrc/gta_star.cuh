@@ -27,12 +27,21 @@ namespace gt {
 #ifndef GT_STAR_W0
 #define GT_STAR_W0 2          // half-width of a point's first window, in cells
 #endif
+#ifndef GT_STAR_LCAP
+#define GT_STAR_LCAP 24
+#endif
+#ifndef GT_STAR_CCAP
+#define GT_STAR_CCAP 40
+#endif
+#ifndef GT_STAR_MINB
+#define GT_STAR_MINB 2        // CTAs of 256 threads per SM the kernel is compiled for (3: 80 registers per thread)
+#endif
 #ifndef GT_STAR_DENS
 #define GT_STAR_DENS 1.0      // points per cell
 #endif
 
-constexpr int STAR_LCAP = 24;                  // left candidates a lane keeps per round of a walk step (star_core.cuh)
-constexpr int STAR_CCAP = 40;                  // candidates a lane keeps (the points of its window); more: it walks the grid
+constexpr int STAR_LCAP = GT_STAR_LCAP;                  // left candidates a lane keeps per round of a walk step (star_core.cuh)
+constexpr int STAR_CCAP = GT_STAR_CCAP;                  // candidates a lane keeps (the points of its window); more: it walks the grid
 
 struct StarParams {
     KParams k;
@@ -49,7 +58,6 @@ struct StarSmem {
         size_t o = 0;
         spt = o; o += sizeof(SPt) * (size_t)cap;                                // cell-sorted (x, y); -corr scratch before that
         sz = o; o += 8 * (size_t)cap;                                           // cell-sorted z
-        sptf = o; o += sizeof(SPtF) * (size_t)cap;                              // cell-sorted (x, y) in float
         ncell_max = cap;
         cstart = o; o += 4 * (size_t)(ncell_max + 2);
         sid = o; o += 2 * (size_t)cap;                                          // cell-sorted input index
@@ -66,6 +74,8 @@ struct StarSmem {
         o = shared0;
         clist = o; o += 2 * (size_t)STAR_CCAP * threads;                        // every thread's candidates (its window's points)
         lists = o; o += 2 * (size_t)STAR_LCAP * threads;                        // every thread's left candidates of the current step
+        o = (o + 15) & ~(size_t)15;
+        sptf = o; o += sizeof(SPtF) * (size_t)cap;                              // cell-sorted (x, y) in float (screening), written when the star phase starts
         o = o > setup_end ? o : setup_end;
         total = (o + 15) & ~(size_t)15;
     }
@@ -179,7 +189,6 @@ __global__ void __launch_bounds__(T, MINB) star_kernel(const StarParams sp) {
                 for (int q = s; q < e; ++q) rank += tmp[q] < i;
                 SPt v; v.x = px(i); v.y = py(i);
                 spt[s + rank] = v; sz[s + rank] = pz(i); sid[s + rank] = (u16)i;
-                SPtF vf; vf.x = (float)v.x; vf.y = (float)v.y; sptf[s + rank] = vf;
                 if (!FULL) {
                     // points on the bounding box: when its four corners are points, they are the hull vertices (triangle count rule)
                     const bool ex = v.x == xlo || v.x == xhi, ey = v.y == ylo || v.y == yhi;
@@ -188,6 +197,8 @@ __global__ void __launch_bounds__(T, MINB) star_kernel(const StarParams sp) {
                 }
             }
             __syncthreads();
+            for (int i = tid; i < n; i += T) { const SPt v = spt[i]; SPtF vf; vf.x = (float)v.x; vf.y = (float)v.y; sptf[i] = vf; }     // (over the dead tile)
+            __syncthreads();
             // the next frame's coordinates are pulled into L2 while this frame's stars are built (the tile's shared memory holds
             // the threads' lists during the star phase, so the copy itself starts when the frame is done)
             if (bulk && tid == 0 && fr + stride < p.nframes)
@@ -195,6 +206,7 @@ __global__ void __launch_bounds__(T, MINB) star_kernel(const StarParams sp) {
             // ---------------------------------------------------------------- stars + areas
             StarGrid<uint32_t> g;
             g.pt = spt; g.ptf = sptf; g.cstart = cbase;
+            g.pt_s = pp_smem_addr(spt); g.ptf_s = pp_smem_addr(sptf); g.cstart_s = pp_smem_addr(cbase);
             g.kf = (float)(2.5 * 5.9604644775390625e-08 * fmax(fmax(fabs(xlo), fabs(xhi)), fmax(fabs(ylo), fabs(yhi)))) * 1.0001f; g.n = n; g.gx = dm.gx; g.gy = dm.gy;
             g.x0 = xlo; g.y0 = ylo; g.sx = dm.sx; g.sy = dm.sy; g.xmin = xlo; g.xmax = xhi; g.ymin = ylo; g.ymax = yhi;
             int* tri_out = p.tri ? p.tri + (size_t)fr * p.tri_cap * 3 : nullptr;
@@ -208,10 +220,13 @@ __global__ void __launch_bounds__(T, MINB) star_kernel(const StarParams sp) {
                 const SPt P = spt[active ? ip : 0]; const double zp = sz[active ? ip : 0];
                 double c3 = 0.0, c2 = 0.0;
                 bool hull = false;
-                struct { u16* base; u16* cbase;
-                         __device__ void put(int k, int pos) { base[k * T] = (u16)pos; } __device__ int get(int k) const { return base[k * T]; }
-                         __device__ void cput(int k, int pos) { cbase[k * T] = (u16)pos; } __device__ int cget(int k) const { return cbase[k * T]; } } lst;
-                lst.base = lists + tid; lst.cbase = clist + tid;
+                // (the thread's two lists, addressed in the shared window: entry k of T-interleaved 16-bit positions)
+                struct { uint32_t base, cbase;
+                         __device__ void put(int k, int pos) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(base + 2u * T * (uint32_t)k), "h"((unsigned short)pos) : "memory"); }
+                         __device__ int get(int k) const { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(base + 2u * T * (uint32_t)k) : "memory"); return v; }
+                         __device__ void cput(int k, int pos) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(cbase + 2u * T * (uint32_t)k), "h"((unsigned short)pos) : "memory"); }
+                         __device__ int cget(int k) const { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(cbase + 2u * T * (uint32_t)k) : "memory"); return v; } } lst;
+                lst.base = pp_smem_addr(lists + tid); lst.cbase = pp_smem_addr(clist + tid);
                 st |= star_point<STAR_LCAP, STAR_CCAP, FULL>(g, ip, active, GT_STAR_W0, lst, &hull, [&](int n1, int n2) {
                     const SPt A = spt[n1], B = spt[n2];
                     c3 += tri_area3(P.x, P.y, zp, A.x, A.y, sz[n1], B.x, B.y, sz[n2]);

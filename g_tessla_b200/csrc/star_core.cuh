@@ -43,10 +43,29 @@ struct StarGrid {
     const SPtF* ptf;           // [n] the same, rounded to float
     float kf;                  // 2.5 * 2^-24 * (largest |coordinate| of the frame): what the rounding to float can move a coordinate difference by, with slack
     const Idx* cstart;         // [gx * gy + 1]
+    uint32_t pt_s, ptf_s, cstart_s;   // device, frame in shared memory: the three arrays' addresses in the shared window (ld.shared, not generic loads)
     int n, gx, gy;
     double x0, y0, sx, sy;     // col = trunc((x - x0) * sx) clamped to [0, gx-1]; row likewise: monotone in x / y
     double xmin, xmax, ymin, ymax;   // exact extremes of the point set (its bounding box)
 };
+
+// Reads of the frame's arrays. On the device they are shared memory and the loads say so (the passes are out-of-line
+// functions: behind a generic pointer the compiler issues generic loads, which wait on the long scoreboard).
+#if defined(__CUDA_ARCH__)
+template <class Idx> GT_INLINE SPt star_pt(const StarGrid<Idx>& g, int pos) {
+    SPt v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(g.pt_s + 16u * (uint32_t)pos)); return v;
+}
+template <class Idx> GT_INLINE SPtF star_ptf(const StarGrid<Idx>& g, int pos) {
+    SPtF v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(g.ptf_s + 8u * (uint32_t)pos)); return v;
+}
+template <class Idx> GT_INLINE int star_cstart(const StarGrid<Idx>& g, int c) {
+    uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(g.cstart_s + 4u * (uint32_t)c)); return (int)v;
+}
+#else
+template <class Idx> GT_INLINE SPt star_pt(const StarGrid<Idx>& g, int pos) { return g.pt[pos]; }
+template <class Idx> GT_INLINE SPtF star_ptf(const StarGrid<Idx>& g, int pos) { return g.ptf[pos]; }
+template <class Idx> GT_INLINE int star_cstart(const StarGrid<Idx>& g, int c) { return (int)g.cstart[c]; }
+#endif
 
 // work counters of the emulation build
 #if defined(GT_STATS) && !defined(__CUDA_ARCH__)
@@ -91,7 +110,7 @@ struct StarCursor { int pos, end, ci, rows, width, part; };
 template <class Idx>
 GT_INLINE bool star_cur_row(const StarGrid<Idx>& g, StarCursor& c) {
     while (c.rows > 0) {
-        const int a = (int)g.cstart[c.ci], b = (int)g.cstart[c.ci + c.width];
+        const int a = star_cstart(g, c.ci), b = star_cstart(g, c.ci + c.width);
         c.ci += g.gx; --c.rows;
         if (a < b) { c.pos = a; c.end = b; return true; }
     }
@@ -192,7 +211,7 @@ GT_NOINLINE void star_nn(const StarGrid<Idx>& g, List lst, StarLane& L, bool act
         while (STAR_ANY(busy)) {
             if (busy) {
                 const int pos = cu.pos;
-                const SPt S = g.pt[pos];
+                const SPt S = star_pt(g, pos);
                 const double dx = S.x - px, dy = S.y - py, l = dx * dx + dy * dy;
                 if (pos != ip) {
                     if (l < l1) { l3 = l2; l2 = l1; b2 = q0; l1 = l; q0 = pos; q0dx = dx; q0dy = dy; }
@@ -237,18 +256,18 @@ GT_NOINLINE int star_pass1_list(const StarGrid<Idx>& g, List lst, StarLane& L, i
     while (STAR_ANY(kk < m && cnt < LCAP)) {
         if (kk < m && cnt < LCAP) {
             const int pos = lst.cget(kk); ++kk;
-            const SPtF F = g.ptf[pos];
+            const SPtF F = star_ptf(g, pos);
             const float c = F.x - pxf, d = star_flipf(F.y - pyf, ym);
             const float dlf = af * d, drf = bf * c, detf = dlf - drf;
             bool left = detf > 0.0f;
             if (!(fabsf(detf) > kfab + 6e-7f * (fabsf(dlf) + fabsf(drf))) && pos != cur) {
-                const SPt S = g.pt[pos];
+                const SPt S = star_pt(g, pos);
                 const double px = L.px, py = L.py, qdx = L.qdx, qdy = L.qdy;
                 const double sdx = S.x - px, sdy = star_flip(S.y - py, ym);
                 const double dl = qdx * sdy, dr = qdy * sdx, det = dl - dr, dsum = fabs(dl) + fabs(dr);
                 left = det > 0.0;
                 if (!(fabs(det) >= GT_CCW_ERRBOUND_A * dsum)) {
-                    const SPt Q = g.pt[cur];
+                    const SPt Q = star_pt(g, cur);
                     const int sg = star_orient_exact(Q.x, star_flip(Q.y, ym), S.x, star_flip(S.y, ym), px, star_flip(py, ym));
                     if (sg == GT_RANGE_ERR) L.err |= STAR_RANGE;
                     left = sg == 1;
@@ -274,14 +293,14 @@ GT_NOINLINE int star_pass1_grid(const StarGrid<Idx>& g, List lst, StarLane& L, S
     while (STAR_ANY(busy && cnt < LCAP)) {
         if (busy && cnt < LCAP) {
             const int pos = cu.pos;
-            const SPt S = g.pt[pos];
+            const SPt S = star_pt(g, pos);
             const double sdx = S.x - px, sdy = star_flip(S.y - py, ym);
             // orient2d(cur, s, p): detleft = qdx * sdy, detright = qdy * sdx. One comparison decides: when the two products do
             // not have the same strict sign, |det| = |dl| + |dr| = dsum.
             const double dl = qdx * sdy, dr = qdy * sdx, det = dl - dr, dsum = fabs(dl) + fabs(dr);
             bool left = det > 0.0 && pos != cur;                             // (s = cur: det is exactly 0; s = p: all zero)
             if (!(fabs(det) >= GT_CCW_ERRBOUND_A * dsum) && pos != cur) {
-                const SPt Q = g.pt[cur];
+                const SPt Q = star_pt(g, cur);
                 const int sg = star_orient_exact(Q.x, star_flip(Q.y, ym), S.x, star_flip(S.y, ym), px, star_flip(py, ym));
                 if (sg == GT_RANGE_ERR) L.err |= STAR_RANGE;
                 left = sg == 1;
@@ -307,7 +326,7 @@ GT_NOINLINE void star_pass2(const StarGrid<Idx>& g, List lst, StarLane& L, int c
     int k = 0;
     if (cnt > 0 && r < 0) {                                                  // the first left candidate of the step
         const int pos = lst.get(0);
-        const SPt S = g.pt[pos];
+        const SPt S = star_pt(g, pos);
         const double sdx = S.x - px, sdy = star_flip(S.y - py, ym);
         const double dl = qdx * sdy, dr = qdy * sdx;
         r = pos; rdx = sdx; rdy = sdy; rl = sdx * sdx + sdy * sdy; mc = dr - dl; mcp = fabs(dl) + fabs(dr); tie = false;
@@ -316,7 +335,7 @@ GT_NOINLINE void star_pass2(const StarGrid<Idx>& g, List lst, StarLane& L, int c
     while (STAR_ANY(k < cnt)) {
         if (k < cnt) {
             const int pos = lst.get(k); ++k;
-            const SPt S = g.pt[pos];
+            const SPt S = star_pt(g, pos);
             const double sdx = S.x - px, sdy = star_flip(S.y - py, ym);
             const double dl = qdx * sdy, dr = qdy * sdx, det = dl - dr, dsum = fabs(dl) + fabs(dr);
             const double sl = sdx * sdx + sdy * sdy;
@@ -328,7 +347,7 @@ GT_NOINLINE void star_pass2(const StarGrid<Idx>& g, List lst, StarLane& L, int c
             const double eb = GT_ICC_ERRBOUND_A * perm;
             int ig = idet > eb ? 1 : -1;
             if (!(fabs(idet) > eb)) {
-                const SPt R = g.pt[r], Q = g.pt[L.cur];
+                const SPt R = star_pt(g, r), Q = star_pt(g, L.cur);
                 ig = star_incircle_exact(R.x, star_flip(R.y, ym), Q.x, star_flip(Q.y, ym), S.x, star_flip(S.y, ym), px, star_flip(py, ym));
                 if (ig == GT_RANGE_ERR) { L.err |= STAR_RANGE; ig = -1; }
             }
@@ -367,7 +386,7 @@ GT_NOINLINE int star_certify(const StarGrid<Idx>& g, StarLane& L, StarCursor& cu
     } else {
         // no point on the left inside the window: p -> cur is a hull edge if the whole bounding box is on its right
         STAR_STAT(hullcert, 1);
-        const SPt Q = g.pt[L.cur];
+        const SPt Q = star_pt(g, L.cur);
         bool right = true;
 #pragma unroll 1
         for (int c = 0; c < 4 && right; ++c) {
@@ -395,7 +414,7 @@ GT_INLINE int star_point(const StarGrid<Idx>& g, int ip, bool active, int w0, Li
     if (!active) ip = 0;
     StarLane L;
     {
-        const SPt P = g.pt[ip]; const SPtF PF = g.ptf[ip];
+        const SPt P = star_pt(g, ip); const SPtF PF = star_ptf(g, ip);
         L.px = P.x; L.py = P.y; L.pxf = PF.x; L.pyf = PF.y; L.ip = ip; L.err = 0;
     }
     if (active) STAR_STAT(points, 1);
@@ -409,7 +428,7 @@ GT_INLINE int star_point(const StarGrid<Idx>& g, int ip, bool active, int w0, Li
         // p q0 -- every other point is strictly farther from p than q0 and therefore outside it: (b2 - p).(b2 - q0) > 0.
         bool okay = L.l3 > L.l1 * (1.0 + 16.0 * GT_EPS);
         if (okay) {
-            const SPt B = g.pt[L.b2], Q0 = g.pt[L.q0];
+            const SPt B = star_pt(g, L.b2), Q0 = star_pt(g, L.q0);
             const double t1 = (B.x - L.px) * (B.x - Q0.x), t2 = (B.y - L.py) * (B.y - Q0.y);
             okay = t1 + t2 > 1e-12 * (fabs(t1) + fabs(t2));
         }
