@@ -182,21 +182,46 @@ GT_NOINLINE int star_incircle_exact(double ax, double ay, double bx, double by, 
 // some fifty values live across the two hot loops and spilled in the middle of them: 10 % of all instructions were local
 // loads and stores. This way the loops run in a small register set and the state moves once per pass.)
 struct StarLane {
-    double px, py;                              // the point
-    float pxf, pyf; int ip;
+    int ip;                                     // the point (position in cell order)
     StarWin win;                                // the window its candidates come from
     int m, overflow;                            // candidates in the lane's list; the window holds more than the list
-    int q0, b2; double l1, l2, l3, q0dx, q0dy;  // nearest neighbour, runner-up, the three smallest squared distances
-    int cur; double qdx, qdy, ql; uint32_t ym;  // current edge p -> cur (coordinates relative to p, y mirrored on clockwise walks)
-    int r, tie; double rdx, rdy, rl, mc, mcp;   // best left candidate of the step so far, and whether something tied with it
+    int q0;                                     // nearest neighbour: the walks start at p -> q0
+    int cur; uint32_t ym;                       // current edge p -> cur; sign-bit mask of the walk (clockwise walks run on mirrored y)
+    int r, tie;                                 // best left candidate of the step so far, and whether something tied with it
     int err;
 };
+// Everything else a pass needs is a function of these positions and is recomputed from the shared-memory arrays when the
+// pass starts (a few loads and FP64 operations per pass, instead of keeping ~25 more words per lane in local memory: the
+// lanes' state has to stay in the part of L1 the shared memory leaves).
+struct StarEdge { double px, py, qdx, qdy, ql; };
+template <class Idx>
+GT_INLINE StarEdge star_edge(const StarGrid<Idx>& g, const StarLane& L) {
+    StarEdge e;
+    const SPt P = star_pt(g, L.ip), Q = star_pt(g, L.cur);
+    e.px = P.x; e.py = P.y;
+    e.qdx = Q.x - P.x; e.qdy = star_flip(Q.y - P.y, L.ym);
+    e.ql = e.qdx * e.qdx + e.qdy * e.qdy;
+    return e;
+}
+struct StarBest { double rdx, rdy, rl, mc, mcp; };           // r relative to p, |r - p|^2, cross(r', q') and the sum of its two products' magnitudes
+template <class Idx>
+GT_INLINE StarBest star_best(const StarGrid<Idx>& g, const StarLane& L, const StarEdge& e) {
+    StarBest b;
+    const SPt R = star_pt(g, L.r >= 0 ? L.r : L.cur);
+    b.rdx = R.x - e.px; b.rdy = star_flip(R.y - e.py, L.ym);
+    b.rl = b.rdx * b.rdx + b.rdy * b.rdy;
+    const double dl = e.qdx * b.rdy, dr = e.qdy * b.rdx;
+    b.mc = dr - dl; b.mcp = fabs(dl) + fabs(dr);
+    return b;
+}
+
 
 // Nearest neighbour of the lane's point (and the two runners-up); the window's points become the lane's candidate list.
 template <int CCAP, class Idx, class List>
 GT_NOINLINE void star_nn(const StarGrid<Idx>& g, List lst, StarLane& L, bool active, int w0) {
     const int ip = L.ip;
-    const double px = L.px, py = L.py;
+    const SPt P = star_pt(g, ip);
+    const double px = P.x, py = P.y;
     StarWin none; none.c0 = 1; none.c1 = 0; none.r0 = 1; none.r1 = 0;
     StarWin win, in = none;
     win.c0 = win.c1 = star_cell(px, g.x0, g.sx, g.gx); win.r0 = win.r1 = star_cell(py, g.y0, g.sy, g.gy);
@@ -238,7 +263,22 @@ GT_NOINLINE void star_nn(const StarGrid<Idx>& g, List lst, StarLane& L, bool act
         if (!STAR_ANY(searching)) break;
     }
     L.win = win; L.m = m; L.overflow = overflow ? 1 : 0;
-    L.q0 = q0; L.b2 = b2; L.l1 = l1; L.l2 = l2; L.l3 = l3; L.q0dx = q0dx; L.q0dy = q0dy;
+    L.q0 = q0;
+    if (!active || q0 < 0) return;
+    if (l1 < 4e-24) { L.err |= STAR_DUP; return; }            // within 1e-12 in x and y: the reference's duplicate rule (delaunay_tri.c:440-452)
+    if (!(l2 > l1 * (1.0 + 16.0 * GT_EPS))) {
+        // The rounded distances do not decide which of q0 and b2 is nearer (the -corr points of a box edge are equidistant
+        // from their two neighbours). p -> q0 is still a Delaunay (Gabriel) edge if b2 is outside the circle with diameter
+        // p q0 -- every other point is strictly farther from p than q0 and therefore outside it: (b2 - p).(b2 - q0) > 0.
+        bool okay = l3 > l1 * (1.0 + 16.0 * GT_EPS);
+        if (okay) {
+            const SPt B = star_pt(g, b2), Q0 = star_pt(g, q0);
+            const double t1 = (B.x - px) * (B.x - Q0.x), t2 = (B.y - py) * (B.y - Q0.y);
+            okay = t1 + t2 > 1e-12 * (fabs(t1) + fabs(t2));
+        }
+        if (!okay) L.err |= STAR_TIE;
+    }
+    (void)q0dx; (void)q0dy;
 }
 
 // Pass 1 of a walk step, from the lane's candidate list: which candidates are left of p -> cur? They go to the lane's list
@@ -250,8 +290,10 @@ template <int LCAP, class Idx, class List>
 GT_NOINLINE int star_pass1_list(const StarGrid<Idx>& g, List lst, StarLane& L, int kk) {
     const int m = L.m, cur = L.cur;
     const uint32_t ym = L.ym;
-    const float pxf = L.pxf, pyf = L.pyf;
-    const float af = (float)L.qdx, bf = (float)L.qdy, kfab = g.kf * (fabsf(af) + fabsf(bf));
+    const StarEdge e = star_edge(g, L);
+    const SPtF PF = star_ptf(g, L.ip);
+    const float pxf = PF.x, pyf = PF.y;
+    const float af = (float)e.qdx, bf = (float)e.qdy, kfab = g.kf * (fabsf(af) + fabsf(bf));
     int cnt = 0;
     while (STAR_ANY(kk < m && cnt < LCAP)) {
         if (kk < m && cnt < LCAP) {
@@ -262,7 +304,7 @@ GT_NOINLINE int star_pass1_list(const StarGrid<Idx>& g, List lst, StarLane& L, i
             bool left = detf > 0.0f;
             if (!(fabsf(detf) > kfab + 6e-7f * (fabsf(dlf) + fabsf(drf))) && pos != cur) {
                 const SPt S = star_pt(g, pos);
-                const double px = L.px, py = L.py, qdx = L.qdx, qdy = L.qdy;
+                const double px = e.px, py = e.py, qdx = e.qdx, qdy = e.qdy;
                 const double sdx = S.x - px, sdy = star_flip(S.y - py, ym);
                 const double dl = qdx * sdy, dr = qdy * sdx, det = dl - dr, dsum = fabs(dl) + fabs(dr);
                 left = det > 0.0;
@@ -286,7 +328,8 @@ template <int LCAP, int CCAP, class Idx, class List>
 GT_NOINLINE int star_pass1_grid(const StarGrid<Idx>& g, List lst, StarLane& L, StarCursor& cu, const StarWin& in, bool* busy_io, int cnt) {
     const int cur = L.cur, ip = L.ip;
     const uint32_t ym = L.ym;
-    const double px = L.px, py = L.py, qdx = L.qdx, qdy = L.qdy;
+    const StarEdge e = star_edge(g, L);
+    const double px = e.px, py = e.py, qdx = e.qdx, qdy = e.qdy;
     const StarWin win = L.win;
     int m = L.m; bool overflow = L.overflow != 0;
     bool busy = *busy_io;
@@ -321,8 +364,10 @@ GT_NOINLINE int star_pass1_grid(const StarGrid<Idx>& g, List lst, StarLane& L, S
 template <class Idx, class List>
 GT_NOINLINE void star_pass2(const StarGrid<Idx>& g, List lst, StarLane& L, int cnt) {
     const uint32_t ym = L.ym;
-    const double px = L.px, py = L.py, qdx = L.qdx, qdy = L.qdy, ql = L.ql;
-    int r = L.r; double rdx = L.rdx, rdy = L.rdy, rl = L.rl, mc = L.mc, mcp = L.mcp; bool tie = L.tie != 0;
+    const StarEdge e = star_edge(g, L);
+    const double px = e.px, py = e.py, qdx = e.qdx, qdy = e.qdy, ql = e.ql;
+    const StarBest b0 = star_best(g, L, e);                   // (what an earlier round of this step found; unused while r < 0)
+    int r = L.r; double rdx = b0.rdx, rdy = b0.rdy, rl = b0.rl, mc = b0.mc, mcp = b0.mcp; bool tie = L.tie != 0;
     int k = 0;
     if (cnt > 0 && r < 0) {                                                  // the first left candidate of the step
         const int pos = lst.get(0);
@@ -355,7 +400,7 @@ GT_NOINLINE void star_pass2(const StarGrid<Idx>& g, List lst, StarLane& L, int c
             else if (ig == 0) tie = true;
         }
     }
-    L.r = r; L.rdx = rdx; L.rdy = rdy; L.rl = rl; L.mc = mc; L.mcp = mcp; L.tie = tie ? 1 : 0;
+    L.r = r; L.tie = tie ? 1 : 0;
 }
 
 // The scan of the window (or of its newest ring) is over: is the answer final? 1: yes, r is the next neighbour; 2: yes, p -> cur
@@ -363,15 +408,17 @@ GT_NOINLINE void star_pass2(const StarGrid<Idx>& g, List lst, StarLane& L, int c
 template <class Idx>
 GT_NOINLINE int star_certify(const StarGrid<Idx>& g, StarLane& L, StarCursor& cu, StarWin& in, bool* busy) {
     const StarWin win = L.win;
-    const double px = L.px, py = L.py;
     const uint32_t ym = L.ym;
     const int r = L.r;
     if (star_win_all(g, win)) return r >= 0 ? 1 : 2;
+    const StarEdge e = star_edge(g, L);
+    const double px = e.px, py = e.py;
     if (r >= 0) {
         // circumdisc of (0, q', r') inside the window?  D = 2 cross(q', r') = -2 mc > 0
-        const double mc = L.mc, mcp = L.mcp;
+        const StarBest b = star_best(g, L, e);
+        const double mc = b.mc, mcp = b.mcp;
         if (fabs(mc) * 1048576.0 >= mcp) {
-            const double qdx = L.qdx, qdy = L.qdy, ql = L.ql, rdx = L.rdx, rdy = L.rdy, rl = L.rl;
+            const double qdx = e.qdx, qdy = e.qdy, ql = e.ql, rdx = b.rdx, rdy = b.rdy, rl = b.rl;
             const double D = -2.0 * mc, iD = 1.0 / D;
             const double ax = rdy * ql, bx = qdy * rl, ay = qdx * rl, by = rdx * ql;
             const double ux = (ax - bx) * iD, uy = (ay - by) * iD;
@@ -413,27 +460,11 @@ GT_INLINE int star_point(const StarGrid<Idx>& g, int ip, bool active, int w0, Li
     if (g.n < 3) { *hull = active; return 0; }                // (uniform: n is the frame's)
     if (!active) ip = 0;
     StarLane L;
-    {
-        const SPt P = star_pt(g, ip); const SPtF PF = star_ptf(g, ip);
-        L.px = P.x; L.py = P.y; L.pxf = PF.x; L.pyf = PF.y; L.ip = ip; L.err = 0;
-    }
+    L.ip = ip; L.err = 0; L.cur = 0; L.r = -1; L.tie = 0; L.ym = 0u;
     if (active) STAR_STAT(points, 1);
-    star_nn<CCAP>(g, lst, L, active, w0);
-    bool walking = active;
+    star_nn<CCAP>(g, lst, L, active, w0);                       // (also: duplicates and an undecided nearest neighbour -> L.err)
+    bool walking = active && L.err == 0;
     if (walking && L.q0 < 0) { *hull = true; walking = false; }               // (n >= 3 and no other point: cannot happen)
-    if (walking && L.l1 < 4e-24) { L.err |= STAR_DUP; walking = false; }      // within 1e-12 in x and y: the reference's duplicate rule (delaunay_tri.c:440-452)
-    if (walking && !(L.l2 > L.l1 * (1.0 + 16.0 * GT_EPS))) {
-        // The rounded distances do not decide which of q0 and b2 is nearer (the -corr points of a box edge are equidistant
-        // from their two neighbours). p -> q0 is still a Delaunay (Gabriel) edge if b2 is outside the circle with diameter
-        // p q0 -- every other point is strictly farther from p than q0 and therefore outside it: (b2 - p).(b2 - q0) > 0.
-        bool okay = L.l3 > L.l1 * (1.0 + 16.0 * GT_EPS);
-        if (okay) {
-            const SPt B = star_pt(g, L.b2), Q0 = star_pt(g, L.q0);
-            const double t1 = (B.x - L.px) * (B.x - Q0.x), t2 = (B.y - L.py) * (B.y - Q0.y);
-            okay = t1 + t2 > 1e-12 * (fabs(t1) + fabs(t2));
-        }
-        if (!okay) { L.err |= STAR_TIE; walking = false; }
-    }
 
     // ---------------------------------------------------------------- the walks
     // mir = 0: counter-clockwise, mir = 1: clockwise = the same code on mirrored y.
@@ -447,11 +478,16 @@ GT_INLINE int star_point(const StarGrid<Idx>& g, int ip, bool active, int w0, Li
     int guard = 0, mir = 0;
     if (L.q0 < 0) L.q0 = 0;
     const int q0 = L.q0;
-    const bool q0_greater = L.q0dx > 0.0 || (L.q0dx == 0.0 && L.q0dy > 0.0);
+    bool q0_greater, q0_above;
+    {
+        const SPt P = star_pt(g, ip), Q0 = star_pt(g, q0);
+        const double dx = Q0.x - P.x, dy = Q0.y - P.y;
+        q0_greater = dx > 0.0 || (dx == 0.0 && dy > 0.0); q0_above = dy > 0.0;
+    }
     bool in_arc = q0_greater, second = false;                     // (!FULL) cur is in the arc; this is the second direction
-    if (!FULL && !q0_greater && L.q0dy > 0.0) mir = 1;
+    if (!FULL && !q0_greater && q0_above) mir = 1;
     L.ym = mir ? 0x80000000u : 0u;
-    L.cur = q0; L.qdx = L.q0dx; L.qdy = star_flip(L.q0dy, L.ym); L.ql = L.l1;
+    L.cur = q0;
     StarWin none; none.c0 = 1; none.c1 = 0; none.r0 = 1; none.r1 = 0;
     StarCursor cu;
     while (STAR_ANY(walking)) {
@@ -486,18 +522,21 @@ GT_INLINE int star_point(const StarGrid<Idx>& g, int ip, bool active, int w0, Li
         }
         // ---- transition
         if (walking) {
-            const uint32_t ym = L.ym;
             const int r = L.r, cur = L.cur;
-            const double qdx = L.qdx, qdy = L.qdy, rdx = L.rdx, rdy = L.rdy;
             // triangle (p, cur, r) is counter-clockwise in walk coordinates; p owns it when cur and r are greater than p
-            const bool own_q = qdx > 0.0 || (qdx == 0.0 && star_flip(qdy, ym) > 0.0), own_r = rdx > 0.0 || (rdx == 0.0 && star_flip(rdy, ym) > 0.0);
+            bool own_q, own_r;
+            {
+                const SPt P = star_pt(g, ip), Q = star_pt(g, cur), R = star_pt(g, r >= 0 ? r : cur);
+                const double qx = Q.x - P.x, qy = Q.y - P.y, rx = R.x - P.x, ry = R.y - P.y;
+                own_q = qx > 0.0 || (qx == 0.0 && qy > 0.0); own_r = rx > 0.0 || (rx == 0.0 && ry > 0.0);
+            }
             bool turn = false;                                     // this direction is over
             if (L.err) walking = false;
             else if (found == 1 && L.tie) { L.err |= STAR_TIE; walking = false; }
             else if (found != 1) { *hull = true; turn = true; }    // hull edge
             else if (FULL) {
                 if (own_q && own_r) { if (mir) emit(r, cur); else emit(cur, r); }
-                L.cur = r; L.qdx = rdx; L.qdy = rdy; L.ql = L.rl;
+                L.cur = r;
                 if (r == q0) {
                     if (mir) L.err |= STAR_GUARD;                  // an open star cannot come back to its start
                     walking = false;                               // closed
@@ -507,7 +546,7 @@ GT_INLINE int star_point(const StarGrid<Idx>& g, int ip, bool active, int w0, Li
                 else {
                     if (in_arc) { if (mir) emit(r, cur); else emit(cur, r); }
                     in_arc = own_r;
-                    L.cur = r; L.qdx = rdx; L.qdy = rdy; L.ql = L.rl;
+                    L.cur = r;
                     if (r == q0) { L.err |= STAR_GUARD; walking = false; }    // (a closed star has neighbours on both sides of p)
                 }
             }
@@ -518,7 +557,7 @@ GT_INLINE int star_point(const StarGrid<Idx>& g, int ip, bool active, int w0, Li
                 if (!again) walking = false;
                 else {
                     second = true; mir ^= 1; L.ym ^= 0x80000000u; in_arc = q0_greater;
-                    L.cur = q0; L.qdx = L.q0dx; L.qdy = star_flip(L.q0dy, L.ym); L.ql = L.l1;
+                    L.cur = q0;
                 }
             }
         }
