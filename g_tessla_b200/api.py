@@ -160,6 +160,17 @@ def triangulate_large(points, device=-1):
     return tri[:nt.value].copy(), st.value, lib().gta_b200_large_last_ms()
 
 
+def surface_area_large(xyz, flags=0, device=-1):
+    """delaunay_surface_area on one large frame of atoms [n,3] without correction points (any n >= 2).
+
+    Returns dict(area, area2d, ntri, status, device_ms, engine): engine 1 = star engine, 0 = level-by-level divide and conquer."""
+    p = np.ascontiguousarray(xyz, dtype=np.float64)
+    a3, a2, nt, st = C.c_double(0.0), C.c_double(0.0), C.c_int(0), C.c_int(0)
+    _check(lib().gta_b200_surface_area_large(_vp(p), len(p), int(flags), int(device), C.byref(a3), C.byref(a2), C.byref(nt), C.byref(st)))
+    return dict(area=a3.value, area2d=a2.value, ntri=nt.value, status=st.value, device_ms=lib().gta_b200_large_last_ms(),
+                engine=lib().gta_b200_large_last_engine())
+
+
 def orient2d_signs(pts, device=-1):
     p = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 6)
     out = np.zeros(len(p), dtype=np.int32)

@@ -466,6 +466,8 @@ int gta_b200_device_count(void) {
     return n;
 }
 
+int gta_b200_get_path(void) { return path_mode(); }
+
 int gta_b200_set_path(int mode) {
     const int old = path_mode();
     g_path.store(mode < 0 || mode > 2 ? 0 : mode);

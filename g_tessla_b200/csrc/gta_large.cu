@@ -23,6 +23,7 @@
 #include <vector>
 #include "dt_core.cuh"
 #include "dt_coop.cuh"
+#include "gta_large_star.cuh"
 #include "../../include/gta_b200.h"
 
 namespace gt {
@@ -135,9 +136,127 @@ __global__ void large_xy(const double* xyz, int n, double* pts) {
 namespace {
 thread_local std::string g_lerr;
 thread_local double g_large_ms = 0.0;
+thread_local int g_large_star = 0;
 }
+extern "C" int gta_b200_large_last_engine(void) { return g_large_star; }
 extern "C" const char* gta_b200_large_error(void) { return g_lerr.c_str(); }
 extern "C" double gta_b200_large_last_ms(void) { return g_large_ms; }
+
+extern "C" int gta_b200_get_path(void);
+
+// One large frame through the star engine (gta_large_star.cuh). d_pts: device [n][2]; d_xyz: device [n][3] or null.
+// Returns 0: certified, results written (triangles in cell order); 1: not certified (a tie, duplicates, count rule) -- the
+// caller runs the level-by-level path; < 0: error (g_lerr set).
+static int large_star(const double* d_pts, const double* d_xyz, int n, unsigned flags, int* tri, int tri_cap, int* ntri, double* area3, double* area2) {
+    using namespace gt;
+#define SCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_lerr = std::string(#call) + ": " + cudaGetErrorString(e_); rc = GTA_B200_E_CUDA; goto out; } } while (0)
+    int rc = 1;
+    unsigned long long* d_key = nullptr; uint32_t *d_ctl = nullptr, *d_cell = nullptr, *d_cell2 = nullptr, *d_idx = nullptr, *d_idx2 = nullptr, *d_cstart = nullptr;
+    uint32_t *d_ll = nullptr, *d_cl = nullptr, *d_cnt = nullptr, *d_off = nullptr, *d_pairs = nullptr, *d_ovf = nullptr;
+    SPt* d_spt = nullptr; SPtF* d_sptf = nullptr; double *d_sz = nullptr, *d_a3 = nullptr, *d_a2 = nullptr, *d_sum = nullptr; int* d_tri = nullptr;
+    void* d_tmp = nullptr; size_t tb = 0, tb2 = 0, tb3 = 0;
+    const int B = 256, G = (n + B - 1) / B;
+    const bool want_area = d_xyz != nullptr && area3 != nullptr, want_tri = tri != nullptr && tri_cap > 0;
+    unsigned long long hkey[4] = {~0ull, 0ull, ~0ull, 0ull};
+    uint32_t hctl[4] = {0, 0, 0, 0};
+    int dev = 0, sms = 0;
+    SCK(cudaGetDevice(&dev));
+    SCK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    {
+        SCK(cudaMalloc((void**)&d_key, 32)); SCK(cudaMalloc((void**)&d_ctl, 16));
+        SCK(cudaMemcpy(d_key, hkey, 32, cudaMemcpyHostToDevice)); SCK(cudaMemset(d_ctl, 0, 16));
+        ls_bbox<<<sms * 4, 256>>>(d_pts, n, d_key, d_ctl);
+        SCK(cudaMemcpy(hkey, d_key, 32, cudaMemcpyDeviceToHost));
+        SCK(cudaMemcpy(hctl, d_ctl, 16, cudaMemcpyDeviceToHost));
+        if (hctl[0]) { rc = 1; goto out; }                                   // non-finite input: the other path reports it
+        const double xmin = ls_unkey(hkey[0]), xmax = ls_unkey(hkey[1]), ymin = ls_unkey(hkey[2]), ymax = ls_unkey(hkey[3]);
+        const StarDims dm = star_dims(n, xmin, xmax, ymin, ymax, std::max(n, 1), 1.0);
+        const int ncell = dm.gx * dm.gy;
+        SCK(cudaMalloc((void**)&d_cell, 4 * (size_t)n)); SCK(cudaMalloc((void**)&d_cell2, 4 * (size_t)n));
+        SCK(cudaMalloc((void**)&d_idx, 4 * (size_t)n)); SCK(cudaMalloc((void**)&d_idx2, 4 * (size_t)n));
+        SCK(cudaMalloc((void**)&d_cstart, 4 * (size_t)(ncell + 2))); SCK(cudaMemset(d_cstart, 0, 4 * (size_t)(ncell + 2)));
+        SCK(cudaMalloc((void**)&d_spt, sizeof(SPt) * (size_t)n)); SCK(cudaMalloc((void**)&d_sptf, sizeof(SPtF) * (size_t)n));
+        if (want_area) { SCK(cudaMalloc((void**)&d_sz, 8 * (size_t)n)); SCK(cudaMalloc((void**)&d_a3, 8 * (size_t)n)); SCK(cudaMalloc((void**)&d_a2, 8 * (size_t)n)); SCK(cudaMalloc((void**)&d_sum, 16)); }
+        SCK(cudaMalloc((void**)&d_cnt, 4 * (size_t)n)); SCK(cudaMalloc((void**)&d_off, 4 * (size_t)n));
+        const uint32_t ovf_cap = (uint32_t)std::max(n / 4, 4096);
+        if (want_tri) { SCK(cudaMalloc((void**)&d_pairs, 8 * (size_t)LS_MAXOWN * n)); SCK(cudaMalloc((void**)&d_ovf, 12 * (size_t)ovf_cap)); }
+        // cells, stable sort by cell (order inside a cell = input order), cell starts
+        ls_cells<<<G, B>>>(d_pts, n, xmin, ymin, dm.sx, dm.sy, dm.gx, dm.gy, d_cell, d_idx, d_cstart + 1);
+        int bits = 1; while ((1ll << bits) < ncell && bits < 32) ++bits;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, d_cell, d_cell2, d_idx, d_idx2, n, 0, bits);
+        cub::DeviceScan::InclusiveSum(nullptr, tb2, d_cstart + 1, d_cstart + 1, ncell);
+        cub::DeviceScan::ExclusiveSum(nullptr, tb3, d_cnt, d_off, n);
+        tb = std::max(tb, std::max(tb2, tb3));
+        if (want_area) { size_t t4 = 0; cub::DeviceReduce::Sum(nullptr, t4, d_a3, d_sum, n); tb = std::max(tb, t4); }
+        SCK(cudaMalloc(&d_tmp, tb));
+        cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_cell, d_cell2, d_idx, d_idx2, n, 0, bits);
+        cub::DeviceScan::InclusiveSum(d_tmp, tb, d_cstart + 1, d_cstart + 1, ncell);          // cstart[c + 1] = end of cell c
+        ls_gather<<<G, B>>>(d_pts, d_xyz, d_idx2, n, d_spt, d_sptf, d_sz);
+        // stars
+        StarGrid<uint32_t, true> g;
+        g.pt = d_spt; g.ptf = d_sptf; g.cstart = d_cstart; g.pt_s = g.ptf_s = g.cstart_s = 0;
+        g.kf = (float)(2.5 * 5.9604644775390625e-08 * std::max(std::max(fabs(xmin), fabs(xmax)), std::max(fabs(ymin), fabs(ymax)))) * 1.0001f;
+        g.n = n; g.gx = dm.gx; g.gy = dm.gy; g.x0 = xmin; g.y0 = ymin; g.sx = dm.sx; g.sy = dm.sy;
+        g.xmin = xmin; g.xmax = xmax; g.ymin = ymin; g.ymax = ymax;
+        int occ = 0;
+        SCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ls_star_kernel, 128, 0));
+        const int blocks = std::max(1, std::min((n + 127) / 128, std::max(1, occ) * sms));
+        const size_t nt = (size_t)blocks * 128;
+        SCK(cudaMalloc((void**)&d_ll, 4 * (size_t)LS_LCAP * nt)); SCK(cudaMalloc((void**)&d_cl, 4 * (size_t)LS_CCAP * nt));
+        SCK(cudaMemset(d_ctl, 0, 16));
+        static const bool trace = getenv("GTA_B200_TRACE") != nullptr;
+        cudaEvent_t t0 = nullptr, t1 = nullptr;
+        if (trace) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0); }
+        ls_star_kernel<<<blocks, 128>>>(g, d_ll, d_cl, d_sz, (flags & GTA_B200_2D) ? 1 : 0, d_cnt, d_pairs, d_ovf, ovf_cap, d_a3, d_a2, d_ctl);
+        SCK(cudaGetLastError());
+        if (trace) {
+            cudaEventRecord(t1); cudaEventSynchronize(t1); float ms = 0.f; cudaEventElapsedTime(&ms, t0, t1);
+            uint32_t c2[4]; cudaMemcpy(c2, d_ctl, 16, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[gta_b200] large star: n %d grid %d x %d, %d blocks, star kernel %.2f ms, status bits 0x%x, open stars %u\n", n, dm.gx, dm.gy, blocks, ms, c2[0], c2[1]);
+            cudaEventDestroy(t0); cudaEventDestroy(t1);
+        }
+        cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_cnt, d_off, n);
+        uint32_t last_off = 0, last_cnt = 0;
+        SCK(cudaMemcpy(&last_off, d_off + (n - 1), 4, cudaMemcpyDeviceToHost));
+        SCK(cudaMemcpy(&last_cnt, d_cnt + (n - 1), 4, cudaMemcpyDeviceToHost));
+        SCK(cudaMemcpy(hctl, d_ctl, 16, cudaMemcpyDeviceToHost));
+        const long long in_slots = (long long)last_off + last_cnt, novf = want_tri ? (long long)hctl[2] : 0;
+        const long long total = in_slots + novf;
+        // certified: no tie / duplicate / guard / list overflow anywhere, and the triangle count rule (delaunay_tri.c:608)
+        if (hctl[0] != 0 || total != 2ll * (n - 1) - (long long)hctl[1]) { rc = 1; goto out; }
+        if (ntri) *ntri = (int)total;
+        if (want_area) {
+            double hs[2] = {0.0, 0.0};
+            cub::DeviceReduce::Sum(d_tmp, tb, d_a3, d_sum, n);
+            cub::DeviceReduce::Sum(d_tmp, tb, d_a2, d_sum + 1, n);
+            SCK(cudaMemcpy(hs, d_sum, 16, cudaMemcpyDeviceToHost));
+            *area3 = hs[0];
+            if (area2) *area2 = hs[1];
+        }
+        if (want_tri) {
+            const int keep = (int)std::min<long long>(total, tri_cap);
+            SCK(cudaMalloc((void**)&d_tri, sizeof(int) * 3 * (size_t)std::max(keep, 1)));
+            ls_emit<<<G, B>>>(d_cnt, d_off, d_pairs, d_idx2, n, d_tri, keep);
+            if (novf > 0) ls_emit_overflow<<<(unsigned)((novf + 255) / 256), 256>>>(d_ovf, (int)novf, d_idx2, d_tri, (int)in_slots, keep);
+            SCK(cudaGetLastError());
+            SCK(cudaMemcpy(tri, d_tri, sizeof(int) * 3 * (size_t)keep, cudaMemcpyDeviceToHost));
+            if (novf > 0 && in_slots < keep) {
+                // the overflow list was filled through an atomic counter: put its triangles in a fixed order
+                struct T3 { int a, b, c; };
+                T3* t = reinterpret_cast<T3*>(tri) + in_slots;
+                std::sort(t, t + (keep - in_slots), [](const T3& x, const T3& y) { return x.a != y.a ? x.a < y.a : (x.b != y.b ? x.b < y.b : x.c < y.c); });
+            }
+        }
+        SCK(cudaDeviceSynchronize());
+        rc = 0;
+    }
+out:
+    cudaFree(d_key); cudaFree(d_ctl); cudaFree(d_cell); cudaFree(d_cell2); cudaFree(d_idx); cudaFree(d_idx2); cudaFree(d_cstart);
+    cudaFree(d_ll); cudaFree(d_cl); cudaFree(d_cnt); cudaFree(d_off); cudaFree(d_pairs); cudaFree(d_ovf); cudaFree(d_spt); cudaFree(d_sptf);
+    cudaFree(d_sz); cudaFree(d_a3); cudaFree(d_a2); cudaFree(d_sum); cudaFree(d_tri); cudaFree(d_tmp);
+    return rc;
+#undef SCK
+}
 
 #define LCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_lerr = std::string(#call) + ": " + cudaGetErrorString(e_); rc = GTA_B200_E_CUDA; goto done; } } while (0)
 
@@ -180,6 +299,22 @@ static int large_run(const double* points, const double* xyz3, int npoints, int 
         large_xy<<<G, B>>>(d_xyz, n, d_pts);
     } else LCK(cudaMemcpy(d_pts, points, sizeof(double) * 2 * (size_t)n, cudaMemcpyHostToDevice));
     LCK(cudaEventRecord(ev0));
+    {
+        // The star engine first, when its output contract allows it: areas always; triangle lists only under GTA_B200_PATH=2
+        // (they come in cell order, the kept dtriangulate promises the reference's emission order). Not certified -> below.
+        const int mode = gta_b200_get_path();
+        if (mode == 2 || (mode == 0 && !(tri && tri_cap > 0) && xyz3)) {
+            const int sr = large_star(d_pts, d_xyz, n, flags, tri, tri_cap, ntri, area3, area2);
+            if (sr < 0) { rc = sr; goto done; }
+            if (sr == 0) {
+                LCK(cudaEventRecord(ev1)); LCK(cudaEventSynchronize(ev1));
+                float ms = 0.f; cudaEventElapsedTime(&ms, ev0, ev1); g_large_ms = ms;
+                g_large_star = 1;
+                goto done;
+            }
+        }
+        g_large_star = 0;
+    }
     {
         // ---- sort: stable by y, then stable by x  => lexicographic (x, y)
         large_keys<<<G, B>>>(d_pts, n, d_k0, d_ky, d_i0, d_ctl + 2);

@@ -37,7 +37,8 @@ struct alignas(8) SPtF { float x, y; };                       // the same point 
 enum { STAR_TIE = 1, STAR_DUP = 2, STAR_GUARD = 4, STAR_RANGE = 8 };
 
 // The grid of one frame: points in cell order (cell = row * gx + col), cell c holds positions cstart[c] .. cstart[c+1]-1.
-template <class Idx>
+// GL = false: the frame's arrays are shared memory (the batched kernel); GL = true: global memory (one large frame).
+template <class Idx, bool GL = false>
 struct StarGrid {
     const SPt* pt;             // [n] cell-sorted coordinates
     const SPtF* ptf;           // [n] the same, rounded to float
@@ -52,24 +53,27 @@ struct StarGrid {
 // Reads of the frame's arrays. On the device they are shared memory and the loads say so (the passes are out-of-line
 // functions: behind a generic pointer the compiler issues generic loads, which wait on the long scoreboard).
 #if defined(__CUDA_ARCH__)
-template <class Idx> GT_INLINE SPt star_pt(const StarGrid<Idx>& g, int pos) {
+template <class Idx, bool GL> GT_INLINE SPt star_pt(const StarGrid<Idx, GL>& g, int pos) {
+    if (GL) return g.pt[pos];
     SPt v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(g.pt_s + 16u * (uint32_t)pos)); return v;
 }
-template <class Idx> GT_INLINE SPtF star_ptf(const StarGrid<Idx>& g, int pos) {
+template <class Idx, bool GL> GT_INLINE SPtF star_ptf(const StarGrid<Idx, GL>& g, int pos) {
+    if (GL) return g.ptf[pos];
     SPtF v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(g.ptf_s + 8u * (uint32_t)pos)); return v;
 }
-template <class Idx> GT_INLINE int star_cstart(const StarGrid<Idx>& g, int c) {
+template <class Idx, bool GL> GT_INLINE int star_cstart(const StarGrid<Idx, GL>& g, int c) {
+    if (GL) return (int)g.cstart[c];
     uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(g.cstart_s + 4u * (uint32_t)c)); return (int)v;
 }
 #else
-template <class Idx> GT_INLINE SPt star_pt(const StarGrid<Idx>& g, int pos) { return g.pt[pos]; }
-template <class Idx> GT_INLINE SPtF star_ptf(const StarGrid<Idx>& g, int pos) { return g.ptf[pos]; }
-template <class Idx> GT_INLINE int star_cstart(const StarGrid<Idx>& g, int c) { return (int)g.cstart[c]; }
+template <class Idx, bool GL> GT_INLINE SPt star_pt(const StarGrid<Idx, GL>& g, int pos) { return g.pt[pos]; }
+template <class Idx, bool GL> GT_INLINE SPtF star_ptf(const StarGrid<Idx, GL>& g, int pos) { return g.ptf[pos]; }
+template <class Idx, bool GL> GT_INLINE int star_cstart(const StarGrid<Idx, GL>& g, int c) { return (int)g.cstart[c]; }
 #endif
 
 // work counters of the emulation build
 #if defined(GT_STATS) && !defined(__CUDA_ARCH__)
-struct StarStats { long cand, left, icc, exact, expand, steps, points, hullcert; };
+struct StarStats { long cand, left, icc, exact, expand, steps, points, hullcert, gridcand, rows; };
 extern StarStats g_star;
 #define STAR_STAT(x, v) (g_star.x += (v))
 #else
@@ -86,10 +90,10 @@ GT_INLINE int star_cell(double v, double o, double s, int g) {
 
 // window of cells [c0, c1] x [r0, r1] (inclusive)
 struct StarWin { int c0, c1, r0, r1; };
-template <class Idx>
-GT_INLINE bool star_win_all(const StarGrid<Idx>& g, const StarWin& w) { return w.c0 == 0 && w.r0 == 0 && w.c1 == g.gx - 1 && w.r1 == g.gy - 1; }
-template <class Idx>
-GT_INLINE StarWin star_win_grow(const StarGrid<Idx>& g, const StarWin& w, int by) {
+template <class Idx, bool GL>
+GT_INLINE bool star_win_all(const StarGrid<Idx, GL>& g, const StarWin& w) { return w.c0 == 0 && w.r0 == 0 && w.c1 == g.gx - 1 && w.r1 == g.gy - 1; }
+template <class Idx, bool GL>
+GT_INLINE StarWin star_win_grow(const StarGrid<Idx, GL>& g, const StarWin& w, int by) {
     StarWin o;
     o.c0 = w.c0 - by > 0 ? w.c0 - by : 0; o.r0 = w.r0 - by > 0 ? w.r0 - by : 0;
     o.c1 = w.c1 + by < g.gx - 1 ? w.c1 + by : g.gx - 1; o.r1 = w.r1 + by < g.gy - 1 ? w.r1 + by : g.gy - 1;
@@ -97,8 +101,8 @@ GT_INLINE StarWin star_win_grow(const StarGrid<Idx>& g, const StarWin& w, int by
 }
 // is the axis-parallel box [xa, xb] x [ya, yb] inside the window? (a bound beyond the point set's extent clamps to the
 // outermost cell, which is what makes the window's outer edges "infinite")
-template <class Idx>
-GT_INLINE bool star_covers(const StarGrid<Idx>& g, const StarWin& w, double xa, double xb, double ya, double yb) {
+template <class Idx, bool GL>
+GT_INLINE bool star_covers(const StarGrid<Idx, GL>& g, const StarWin& w, double xa, double xb, double ya, double yb) {
     if (!(xa <= xb && ya <= yb)) return false;               // NaN
     return star_cell(xa, g.x0, g.sx, g.gx) >= w.c0 && star_cell(xb, g.x0, g.sx, g.gx) <= w.c1 &&
            star_cell(ya, g.y0, g.sy, g.gy) >= w.r0 && star_cell(yb, g.y0, g.sy, g.gy) <= w.r1;
@@ -106,9 +110,97 @@ GT_INLINE bool star_covers(const StarGrid<Idx>& g, const StarWin& w, double xa, 
 // Cursor over the cell-sorted positions of a window, or of a window without an inner window (the ring a grown window adds):
 // a queue of at most four rectangles of cells, walked row by row -- a row of a rectangle is one contiguous run of
 // positions. The per-candidate cost is one increment and one compare; a new row costs two shared-memory loads.
-struct StarCursor { int pos, end, ci, rows, width, part; };
-template <class Idx>
-GT_INLINE bool star_cur_row(const StarGrid<Idx>& g, StarCursor& c) {
+struct StarCursor { int pos, end, ci, rows, width, part; int region; };   // region != 0: rows come from the lane's StarRegion instead
+
+// What has to be scanned when a step's answer cannot be certified from the window: a part of the half-plane on the walk's
+// left of p -> cur, scan-converted against the rows of the grid -- per row one run of cells, minus cells scanned before --
+// so that the cost follows the region's area, not the distance it reaches to. star_certify picks the regions:
+//   no left candidate yet   the half-plane inside a box around p that doubles until one is found (or the box is everything:
+//                           a hull edge); the hull side of a point near the hull is empty for a long way
+//   a long edge p - cur     first a band of cells along the segment: its apex lies in the circumdisc of the first guess, and
+//                           that disc holds ~|p cur|^2 points; a point near the segment subtends a wide angle, so the disc
+//                           through it has a thin cap on the left
+//   finally                 the left part of the circumdisc of (p, cur, r): whatever beats r lies in it, and the disc of a
+//                           better r lies inside it -- this scan settles the step
+struct StarRegion {
+    int disc, band;               // clip to the circumdisc / to a band around the segment p - cur
+    double px, py, A, B;          // left of p -> cur in real coordinates: B (x - px) < A (y - py)
+    double cx, cy, R;             // the disc, centre and (conservative) radius in real coordinates
+    double bw, bx0, bx1;          // the band: |x - X(y)| <= bw on the line's x at height y, and bx0 <= x <= bx1
+    int row, row_end, seg, sb0, sb1;
+    StarWin lim, skip;            // only cells of `lim`; the cells of `skip` have been scanned before
+};
+// cells [ca, cb] of `row` that may hold points of the region (false: none). Conservative: the bounds are widened by far
+// more than their rounding, and the cell map is monotone.
+template <class Idx, bool GL>
+GT_INLINE bool star_region_cols(const StarGrid<Idx, GL>& g, const StarRegion& rg, int row, int* ca, int* cb) {
+    double y0 = g.ymin, y1 = g.ymax;
+    if (g.sy > 0.0) {
+        const double h = 1.0 / g.sy;
+        y0 = g.y0 + row * h; y1 = g.y0 + (row + 1) * h;
+        const double my = 1e-9 * (fabs(y0) + fabs(y1) + h);
+        y0 -= my; y1 += my;
+        if (row == 0) y0 = fmin(y0, g.ymin);
+        if (row == g.gy - 1) y1 = fmax(y1, g.ymax);
+    }
+    double xa = g.xmin, xb = g.xmax;
+    const double A = rg.A, B = rg.B, t0 = y0 - rg.py, t1 = y1 - rg.py;
+    if (B != 0.0) {
+        const double sl = A / B, X0 = rg.px + sl * t0, X1 = rg.px + sl * t1;
+        const double mx = 1e-9 * (fabs(rg.px) + fabs(sl * t0) + fabs(sl * t1));
+        if (X0 == X0 && X1 == X1 && mx == mx) {                   // (an overflowing slope bounds nothing)
+            if (B > 0.0) xb = fmin(xb, fmax(X0, X1) + mx); else xa = fmax(xa, fmin(X0, X1) - mx);
+            if (rg.band) { xa = fmax(xa, fmin(X0, X1) - mx - rg.bw); xb = fmin(xb, fmax(X0, X1) + mx + rg.bw); }
+        }
+    } else if (A > 0.0) { if (!(t1 > 0.0)) return false; }
+    else if (A < 0.0) { if (!(t0 < 0.0)) return false; }
+    if (rg.band) { xa = fmax(xa, rg.bx0); xb = fmin(xb, rg.bx1); }
+    if (rg.disc) {
+        const double cy = rg.cy, R = rg.R;
+        if (y1 < cy - R || y0 > cy + R) return false;
+        const double dy = (cy >= y0 && cy <= y1) ? 0.0 : fmin(fabs(y0 - cy), fabs(y1 - cy));
+        const double w2 = R * R - dy * dy;
+        const double w = (w2 > 0.0 ? sqrt(w2) : 0.0) * (1.0 + 1e-9) + 1e-9 * R;
+        xa = fmax(xa, rg.cx - w); xb = fmin(xb, rg.cx + w);
+    }
+    if (!(xa <= xb)) return false;
+    int a = star_cell(xa, g.x0, g.sx, g.gx), b = star_cell(xb, g.x0, g.sx, g.gx);
+    a = a > rg.lim.c0 ? a : rg.lim.c0; b = b < rg.lim.c1 ? b : rg.lim.c1;
+    if (a > b) return false;
+    *ca = a; *cb = b;
+    return true;
+}
+template <class Idx, bool GL>
+GT_INLINE bool star_region_next(const StarGrid<Idx, GL>& g, StarCursor& c, StarRegion& rg) {
+    for (;;) {
+        int ca, cb;
+        if (rg.seg == 0) {
+            if (rg.row > rg.row_end) return false;
+            STAR_STAT(rows, 1);
+            if (!star_region_cols(g, rg, rg.row, &ca, &cb)) { ++rg.row; continue; }
+            rg.sb0 = 1; rg.sb1 = 0;                                // second run of the row: none
+            if (rg.row >= rg.skip.r0 && rg.row <= rg.skip.r1) {    // cells scanned before are skipped
+                rg.sb0 = ca > rg.skip.c1 + 1 ? ca : rg.skip.c1 + 1; rg.sb1 = cb;
+                cb = cb < rg.skip.c0 - 1 ? cb : rg.skip.c0 - 1;
+            }
+            rg.seg = 1;
+        } else {
+            ca = rg.sb0; cb = rg.sb1;
+            rg.seg = 0; ++rg.row;
+            if (ca > cb) continue;
+            const int base = (rg.row - 1) * g.gx;
+            c.pos = star_cstart(g, base + ca); c.end = star_cstart(g, base + cb + 1);
+            if (c.pos < c.end) return true;
+            continue;
+        }
+        if (ca > cb) continue;
+        const int base = rg.row * g.gx;
+        c.pos = star_cstart(g, base + ca); c.end = star_cstart(g, base + cb + 1);
+        if (c.pos < c.end) return true;
+    }
+}
+template <class Idx, bool GL>
+GT_INLINE bool star_cur_row(const StarGrid<Idx, GL>& g, StarCursor& c) {
     while (c.rows > 0) {
         const int a = star_cstart(g, c.ci), b = star_cstart(g, c.ci + c.width);
         c.ci += g.gx; --c.rows;
@@ -116,8 +208,8 @@ GT_INLINE bool star_cur_row(const StarGrid<Idx>& g, StarCursor& c) {
     }
     return false;
 }
-template <class Idx>
-GT_INLINE bool star_cur_next(const StarGrid<Idx>& g, StarCursor& c, const StarWin& w, const StarWin& in) {
+template <class Idx, bool GL>
+GT_INLINE bool star_cur_next(const StarGrid<Idx, GL>& g, StarCursor& c, const StarWin& w, const StarWin& in) {
     if (star_cur_row(g, c)) return true;
     while (c.part < 4) {
         // the ring w \ in: rows above, rows below, columns left, columns right of the inner window
@@ -134,9 +226,9 @@ GT_INLINE bool star_cur_next(const StarGrid<Idx>& g, StarCursor& c, const StarWi
     return false;
 }
 // start on the whole window w (in.c0 > in.c1) or on the ring w \ in
-template <class Idx>
-GT_INLINE bool star_cur_begin(const StarGrid<Idx>& g, StarCursor& c, const StarWin& w, const StarWin& in) {
-    c.pos = c.end = 0;
+template <class Idx, bool GL>
+GT_INLINE bool star_cur_begin(const StarGrid<Idx, GL>& g, StarCursor& c, const StarWin& w, const StarWin& in) {
+    c.pos = c.end = 0; c.region = 0;
     if (in.c0 > in.c1) { c.part = 4; c.ci = w.r0 * g.gx + w.c0; c.rows = w.r1 - w.r0 + 1; c.width = w.c1 - w.c0 + 1; }
     else { c.part = 0; c.rows = 0; c.ci = 0; c.width = 0; }
     return star_cur_next(g, c, w, in);
@@ -194,8 +286,8 @@ struct StarLane {
 // pass starts (a few loads and FP64 operations per pass, instead of keeping ~25 more words per lane in local memory: the
 // lanes' state has to stay in the part of L1 the shared memory leaves).
 struct StarEdge { double px, py, qdx, qdy, ql; };
-template <class Idx>
-GT_INLINE StarEdge star_edge(const StarGrid<Idx>& g, const StarLane& L) {
+template <class Idx, bool GL>
+GT_INLINE StarEdge star_edge(const StarGrid<Idx, GL>& g, const StarLane& L) {
     StarEdge e;
     const SPt P = star_pt(g, L.ip), Q = star_pt(g, L.cur);
     e.px = P.x; e.py = P.y;
@@ -204,8 +296,8 @@ GT_INLINE StarEdge star_edge(const StarGrid<Idx>& g, const StarLane& L) {
     return e;
 }
 struct StarBest { double rdx, rdy, rl, mc, mcp; };           // r relative to p, |r - p|^2, cross(r', q') and the sum of its two products' magnitudes
-template <class Idx>
-GT_INLINE StarBest star_best(const StarGrid<Idx>& g, const StarLane& L, const StarEdge& e) {
+template <class Idx, bool GL>
+GT_INLINE StarBest star_best(const StarGrid<Idx, GL>& g, const StarLane& L, const StarEdge& e) {
     StarBest b;
     const SPt R = star_pt(g, L.r >= 0 ? L.r : L.cur);
     b.rdx = R.x - e.px; b.rdy = star_flip(R.y - e.py, L.ym);
@@ -217,8 +309,8 @@ GT_INLINE StarBest star_best(const StarGrid<Idx>& g, const StarLane& L, const St
 
 
 // Nearest neighbour of the lane's point (and the two runners-up); the window's points become the lane's candidate list.
-template <int CCAP, class Idx, class List>
-GT_NOINLINE void star_nn(const StarGrid<Idx>& g, List lst, StarLane& L, bool active, int w0) {
+template <int CCAP, class Idx, bool GL, class List>
+GT_NOINLINE void star_nn(const StarGrid<Idx, GL>& g, List lst, StarLane& L, bool active, int w0) {
     const int ip = L.ip;
     const SPt P = star_pt(g, ip);
     const double px = P.x, py = P.y;
@@ -286,8 +378,8 @@ GT_NOINLINE void star_nn(const StarGrid<Idx>& g, List lst, StarLane& L, bool act
 // kf (|a| + |b|) + 5 2^-24 (|a d| + |b c|) from the real determinant; beyond that its sign is the real one. Closer to the
 // line: the reference's own filter in double (predicates.c:1628-1651), then the exact stage.
 // kk = next entry of the candidate list; returns kk | cnt << 16 (cnt = entries of the left list).
-template <int LCAP, class Idx, class List>
-GT_NOINLINE int star_pass1_list(const StarGrid<Idx>& g, List lst, StarLane& L, int kk) {
+template <int LCAP, class Idx, bool GL, class List>
+GT_NOINLINE int star_pass1_list(const StarGrid<Idx, GL>& g, List lst, StarLane& L, int kk) {
     const int m = L.m, cur = L.cur;
     const uint32_t ym = L.ym;
     const StarEdge e = star_edge(g, L);
@@ -330,16 +422,16 @@ GT_NOINLINE int star_pass1_list(const StarGrid<Idx>& g, List lst, StarLane& L, i
     return kk | (cnt << 16);
 }
 
-// Pass 1 from the grid (a window with more points than the candidate list holds, or the ring a grown window adds; rare).
-// Ring points also join the candidate list, so that later steps find them there. Returns cnt.
-template <int LCAP, int CCAP, class Idx, class List>
-GT_NOINLINE int star_pass1_grid(const StarGrid<Idx>& g, List lst, StarLane& L, StarCursor& cu, const StarWin& in, bool* busy_io, int cnt) {
-    const int cur = L.cur, ip = L.ip;
+// Pass 1 from the grid: a window with more points than the candidate list holds, or the region a failed certificate
+// asks for (star_certify). Rare. Returns cnt.
+template <int LCAP, class Idx, bool GL, class List>
+GT_NOINLINE int star_pass1_grid(const StarGrid<Idx, GL>& g, List lst, StarLane& L, StarCursor& cu, StarRegion& rg, bool* busy_io, int cnt) {
+    const int cur = L.cur, ip = L.ip, rbest = L.r;                 // (regions may overlap: r met again would tie with itself)
     const uint32_t ym = L.ym;
     const StarEdge e = star_edge(g, L);
     const double px = e.px, py = e.py, qdx = e.qdx, qdy = e.qdy;
     const StarWin win = L.win;
-    int m = L.m; bool overflow = L.overflow != 0;
+    StarWin none; none.c0 = 1; none.c1 = 0; none.r0 = 1; none.r1 = 0;
     bool busy = *busy_io;
     while (STAR_ANY(busy && cnt < LCAP)) {
         if (busy && cnt < LCAP) {
@@ -349,28 +441,27 @@ GT_NOINLINE int star_pass1_grid(const StarGrid<Idx>& g, List lst, StarLane& L, S
             // orient2d(cur, s, p): detleft = qdx * sdy, detright = qdy * sdx. One comparison decides: when the two products do
             // not have the same strict sign, |det| = |dl| + |dr| = dsum.
             const double dl = qdx * sdy, dr = qdy * sdx, det = dl - dr, dsum = fabs(dl) + fabs(dr);
-            bool left = det > 0.0 && pos != cur;                             // (s = cur: det is exactly 0; s = p: all zero)
-            if (!(fabs(det) >= GT_CCW_ERRBOUND_A * dsum) && pos != cur) {
+            const bool skip = pos == cur || pos == ip || pos == rbest;      // (s = cur: det is exactly 0; s = p: all zero)
+            bool left = det > 0.0 && !skip;
+            if (!(fabs(det) >= GT_CCW_ERRBOUND_A * dsum) && !skip) {
                 const SPt Q = star_pt(g, cur);
                 const int sg = star_orient_exact(Q.x, star_flip(Q.y, ym), S.x, star_flip(S.y, ym), px, star_flip(py, ym));
                 if (sg == GT_RANGE_ERR) L.err |= STAR_RANGE;
                 left = sg == 1;
             }
-            STAR_STAT(cand, 1);
+            STAR_STAT(cand, 1); STAR_STAT(gridcand, 1);
             if (left) { lst.put(cnt, pos); ++cnt; STAR_STAT(left, 1); }
-            if (!overflow && pos != ip) { if (m < CCAP) { lst.cput(m, pos); ++m; } else overflow = true; }
-            if (++cu.pos >= cu.end) busy = star_cur_next(g, cu, win, in);
+            if (++cu.pos >= cu.end) busy = cu.region ? star_region_next(g, cu, rg) : star_cur_next(g, cu, win, none);
         }
     }
-    L.m = m; L.overflow = overflow ? 1 : 0;
     *busy_io = busy;
     return cnt;
 }
 
 // Pass 2: the best of the left list (and of what earlier rounds of this step found): s beats r when it is inside
 // circle(p, cur, r) = incircle(a = r, b = cur, c = s, d = p) > 0: the reference's filter (predicates.c:3238-3267), then exact.
-template <class Idx, class List>
-GT_NOINLINE void star_pass2(const StarGrid<Idx>& g, List lst, StarLane& L, int cnt) {
+template <class Idx, bool GL, class List>
+GT_NOINLINE void star_pass2(const StarGrid<Idx, GL>& g, List lst, StarLane& L, int cnt) {
     const uint32_t ym = L.ym;
     const StarEdge e = star_edge(g, L);
     const double px = e.px, py = e.py, qdx = e.qdx, qdy = e.qdy, ql = e.ql;
@@ -416,18 +507,29 @@ GT_NOINLINE void star_pass2(const StarGrid<Idx>& g, List lst, StarLane& L, int c
     L.r = r; L.tie = tie ? 1 : 0;
 }
 
-// The scan of the window (or of its newest ring) is over: is the answer final? 1: yes, r is the next neighbour; 2: yes, p -> cur
-// is a hull edge; 0: no -- the window has been grown by one ring and the cursor stands on it (*busy: the ring is not empty).
-template <class Idx>
-GT_NOINLINE int star_certify(const StarGrid<Idx>& g, StarLane& L, StarCursor& cu, StarWin& in, bool* busy) {
+// A scan is over (the window's, or a region's): is the answer final? 1: yes, r is the next neighbour; 2: yes, p -> cur
+// is a hull edge; 0: not yet -- `rg` describes the next region to scan and the cursor stands on it (*busy: it is not empty).
+// The search goes outwards from p in boxes that double (window, +4 cells, +8, +16, ...), always clipped to the half-plane on
+// the left of p -> cur and, once there is a candidate r, to the circumdisc of (p, cur, r) -- whatever beats r lies in that
+// disc, and the disc of a better r lies inside it. It ends when the disc fits into what has been scanned, or everything
+// has been. A long edge first gets a band of cells along its segment: the disc of a first guess near p holds ~|p cur|^2
+// points, while a point near the segment subtends a wide angle and leaves a thin cap.
+// *rs = the step's progress: bits 0-7 the box level, STAR_RS_BAND the band has been scanned.
+enum { STAR_RS_BAND = 0x100 };
+template <class Idx, bool GL>
+GT_NOINLINE int star_certify(const StarGrid<Idx, GL>& g, StarLane& L, StarCursor& cu, StarRegion& rg, int* rs, bool* busy) {
     const StarWin win = L.win;
     const uint32_t ym = L.ym;
     const int r = L.r;
-    if (star_win_all(g, win)) return r >= 0 ? 1 : 2;
+    const int level = *rs & 0xff;
+    const StarWin seen = level == 0 ? win : star_win_grow(g, win, level < 24 ? (2 << level) : (1 << 26));      // scanned so far
+    if (star_win_all(g, seen)) return r >= 0 ? 1 : 2;
     const StarEdge e = star_edge(g, L);
     const double px = e.px, py = e.py;
+    // (the region's description is only written once the common case -- the disc fits into the window -- is out of the way)
+    int disc = 0; double dcx = 0.0, dcy = 0.0, dR = 0.0;
     if (r >= 0) {
-        // circumdisc of (0, q', r') inside the window?  D = 2 cross(q', r') = -2 mc > 0
+        // circumdisc of (0, q', r') inside what has been scanned?  D = 2 cross(q', r') = -2 mc > 0
         const StarBest b = star_best(g, L, e);
         const double mc = b.mc, mcp = b.mcp;
         if (fabs(mc) * 1048576.0 >= mcp) {
@@ -440,11 +542,34 @@ GT_NOINLINE int star_certify(const StarGrid<Idx>& g, StarLane& L, StarCursor& cu
             const double ex = 4.0 * GT_EPS * (fabs(ax) + fabs(bx)) * fabs(iD) + fabs(ux) * relD;
             const double ey = 4.0 * GT_EPS * (fabs(ay) + fabs(by)) * fabs(iD) + fabs(uy) * relD;
             const double mg = 2.0 * (ex + ey) + 1e-12 * R + 8.0 * GT_EPS * (fabs(px) + fabs(py) + R + fabs(ux) + fabs(uy));
-            const double cy = py + star_flip(uy, ym);
-            if (star_covers(g, win, (px + ux) - R - mg, (px + ux) + R + mg, cy - R - mg, cy + R + mg)) return 1;
+            const double cx = px + ux, cy = py + star_flip(uy, ym);
+            if (star_covers(g, seen, cx - R - mg, cx + R + mg, cy - R - mg, cy + R + mg)) return 1;
+            if (R + mg < 1.7976931348623157e308) { disc = 1; dcx = cx; dcy = cy; dR = R + mg; }
         }
-    } else {
-        // no point on the left inside the window: p -> cur is a hull edge if the whole bounding box is on its right
+    }
+    StarWin all; all.c0 = 0; all.r0 = 0; all.c1 = g.gx - 1; all.r1 = g.gy - 1;
+    // left of p -> cur in real coordinates (a clockwise walk's left is the real right)
+    const double sgn = ym ? -1.0 : 1.0;
+    rg.px = px; rg.py = py; rg.A = sgn * e.qdx; rg.B = sgn * star_flip(e.qdy, ym);
+    rg.disc = disc; rg.cx = dcx; rg.cy = dcy; rg.R = dR;
+    rg.band = 0; rg.bw = rg.bx0 = rg.bx1 = 0.0;
+    rg.lim = all; rg.skip = seen; rg.seg = 0; rg.sb0 = 1; rg.sb1 = 0;
+    if (r >= 0) {
+        // (a sliver too flat for a trustworthy centre: no disc, the half-plane alone bounds the search)
+        const double qx = e.qdx, qy = star_flip(e.qdy, ym);                   // cur - p, real coordinates
+        const double cell = (g.sx > 0.0 && g.sy > 0.0) ? fmax(1.0 / g.sx, 1.0 / g.sy) : 0.0;
+        if (!(*rs & STAR_RS_BAND) && cell > 0.0 && (!rg.disc || rg.R > 6.0 * cell) && e.ql > 36.0 * cell * cell) {
+            STAR_STAT(expand, 1);
+            *rs |= STAR_RS_BAND;
+            rg.band = 1; rg.bw = 1.5 * cell;
+            rg.bx0 = fmin(px, px + qx) - rg.bw; rg.bx1 = fmax(px, px + qx) + rg.bw;
+            rg.row = star_cell(fmin(py, py + qy) - rg.bw, g.y0, g.sy, g.gy); rg.row_end = star_cell(fmax(py, py + qy) + rg.bw, g.y0, g.sy, g.gy);
+            cu.region = 1; cu.pos = cu.end = 0;
+            *busy = star_region_next(g, cu, rg);
+            return 0;
+        }
+    } else if (level == 0) {
+        // no point on the left in the window: p -> cur is a hull edge if the whole bounding box is on its right (exact)
         STAR_STAT(hullcert, 1);
         const SPt Q = star_pt(g, L.cur);
         bool right = true;
@@ -457,9 +582,17 @@ GT_NOINLINE int star_certify(const StarGrid<Idx>& g, StarLane& L, StarCursor& cu
         }
         if (right) return 2;
     }
-    in = win; L.win = star_win_grow(g, win, 1);
+    // the next box
     STAR_STAT(expand, 1);
-    *busy = star_cur_begin(g, cu, L.win, in);
+    rg.lim = star_win_grow(g, win, level < 23 ? (4 << level) : (1 << 26));
+    rg.row = rg.lim.r0; rg.row_end = rg.lim.r1;
+    if (rg.disc) {
+        const int d0 = star_cell(rg.cy - rg.R, g.y0, g.sy, g.gy), d1 = star_cell(rg.cy + rg.R, g.y0, g.sy, g.gy);
+        rg.row = rg.row > d0 ? rg.row : d0; rg.row_end = rg.row_end < d1 ? rg.row_end : d1;
+    }
+    *rs = (*rs & ~0xff) | (level + 1);
+    cu.region = 1; cu.pos = cu.end = 0;
+    *busy = star_region_next(g, cu, rg);
     return 0;
 }
 
@@ -467,8 +600,8 @@ GT_NOINLINE int star_certify(const StarGrid<Idx>& g, StarLane& L, StarCursor& cu
 // open (ip is a hull vertex; FULL only). `w0` = half-width of the first window in cells. Returns STAR_* bits (0: certified).
 // `lst` = the lane's two lists of positions in shared memory: its candidates (cput / cget, CCAP entries) and the left
 // candidates of the current step (put / get, LCAP entries).
-template <int LCAP, int CCAP, bool FULL, class Idx, class List, class Emit>
-GT_INLINE int star_point(const StarGrid<Idx>& g, int ip, bool active, int w0, List lst, bool* hull, Emit&& emit) {
+template <int LCAP, int CCAP, bool FULL, class Idx, bool GL, class List, class Emit>
+GT_INLINE int star_point(const StarGrid<Idx, GL>& g, int ip, bool active, int w0, List lst, bool* hull, Emit&& emit) {
     *hull = false;
     if (g.n < 3) { *hull = active; return 0; }                // (uniform: n is the frame's)
     if (!active) ip = 0;
@@ -503,15 +636,16 @@ GT_INLINE int star_point(const StarGrid<Idx>& g, int ip, bool active, int w0, Li
     L.cur = q0;
     StarWin none; none.c0 = 1; none.c1 = 0; none.r0 = 1; none.r1 = 0;
     StarCursor cu;
+    StarRegion rg;
     while (STAR_ANY(walking)) {
         // ---- one step for every walking lane: best left candidate of p -> cur; ties against the best so far are remembered
         L.r = -1; L.tie = 0;
         bool scanning = walking;
         if (walking) { STAR_STAT(steps, 1); if (++guard > guard_max) { L.err |= STAR_GUARD; walking = scanning = false; } }
         // the candidates come from the lane's list; a lane whose window holds more than the list walks the grid instead
-        StarWin in = none;
         int kk = (scanning && !L.overflow) ? 0 : L.m;
-        bool busy = scanning && L.overflow && star_cur_begin(g, cu, L.win, in);
+        bool busy = scanning && L.overflow && star_cur_begin(g, cu, L.win, none);
+        int rs = 0;                                                  // progress through the step's regions (star_certify)
         int found = 0;
         for (;;) {
             // Two passes instead of one loop that does everything for a candidate: a candidate is left for half the lanes and
@@ -520,16 +654,12 @@ GT_INLINE int star_point(const StarGrid<Idx>& g, int ip, bool active, int w0, Li
             const int pc = star_pass1_list<LCAP>(g, lst, L, kk);
             kk = pc & 0xffff;
             int cnt = pc >> 16;
-            if (STAR_ANY(busy)) {
-                const bool grid = busy;
-                cnt = star_pass1_grid<LCAP, CCAP>(g, lst, L, cu, in, &busy, cnt);
-                if (grid) kk = L.m;                                // (what a ring added to the candidate list has been seen)
-            }
+            if (STAR_ANY(busy)) cnt = star_pass1_grid<LCAP>(g, lst, L, cu, rg, &busy, cnt);
             star_pass2(g, lst, L, cnt);
             if (STAR_ANY(busy || kk < L.m)) continue;                                // a lane's left list was full: it goes on
             if (scanning) {
-                found = star_certify(g, L, cu, in, &busy);
-                if (found) scanning = false; else kk = L.m;       // (the ring is read from the grid; pass 1 appends it to the list)
+                found = star_certify(g, L, cu, rg, &rs, &busy);
+                if (found) scanning = false;
             }
             if (!STAR_ANY(scanning)) break;
         }

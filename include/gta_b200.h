@@ -55,6 +55,7 @@ extern "C" {
  * gta_b200_set_path: 0 = automatic (above), 1 = divide and conquer only, 2 = star path also for triangle lists (the list
  * then holds the same triangles in another order). Environment GTA_B200_PATH sets the default. Returns the previous mode. */
 int gta_b200_set_path(int mode);
+int gta_b200_get_path(void);
 
 /* Two kernels serve the divide-and-conquer engine: launches of at least `min_frames` frames run the throughput path (pre-pass,
  * a persistent kernel whose phase-sorted scheduler steps (frame, subtree) walkers, area kernel: highest throughput), smaller ones the fused one-CTA-per-frame kernel (lowest latency). Results are identical
@@ -138,6 +139,9 @@ int gta_b200_surface_area_large(const double *xyz, int natoms, unsigned flags, i
                                 double *area3, double *area2, int *ntri, int *status);
 /* device milliseconds (sort + all levels + enumeration, without the host copies) of the last call on this thread */
 double gta_b200_large_last_ms(void);
+/* engine of the last large-frame call on this thread: 1 = star engine (csrc/gta_large_star.cuh: areas by default,
+ * triangle lists -- in cell order -- under gta_b200_set_path(2)), 0 = level-by-level divide and conquer */
+int gta_b200_large_last_engine(void);
 
 /* Milliseconds the last gta_b200_tessellate_batch call on this thread spent in its kernels
  * (CUDA events on the launching streams), and the number of kernel launches the last batch / device call made. */

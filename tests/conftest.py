@@ -95,7 +95,7 @@ def emu():
             """The star path (star_core.cuh): (triangles in any order or None when the frame is not certified, status, counters)."""
             p = np.ascontiguousarray(p, dtype=np.float64)
             out = np.empty(3 * 2 * max(len(p), 1), dtype=np.int32)
-            st = (C.c_long * 11)()
+            st = (C.c_long * 17)()
             nt = L.emu_star(p.ctypes.data_as(dp), len(p), int(w0), float(dens), 1 if full else 0, int(ccap), out.ctypes.data_as(ip), st)
             if nt < 0:
                 return None, -nt, list(st)

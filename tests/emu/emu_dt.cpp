@@ -4,6 +4,7 @@
 // logic and the exact predicates can be checked against the oracle without a GPU.
 // Never linked into libgtessla_b200.so; the product has no CPU path.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -237,7 +238,7 @@ int emu_star(const double* points, int n, int w0, double dens, int full, int cca
     if (stats_out) {
         stats_out[0] = g_star.cand; stats_out[1] = g_star.left; stats_out[2] = g_star.icc; stats_out[3] = g_star.exact;
         stats_out[4] = g_star.expand; stats_out[5] = g_star.steps; stats_out[6] = g_star.points; stats_out[7] = g_star.hullcert;
-        stats_out[8] = nh; stats_out[9] = d.gx; stats_out[10] = d.gy;
+        stats_out[8] = nh; stats_out[9] = d.gx; stats_out[10] = d.gy; stats_out[11] = g_star.gridcand; stats_out[12] = g_star.rows;
     }
     if (st) return -st;
     if (!full) {

@@ -67,3 +67,48 @@ def test_cfg4_vs_oracle(gta, checker):
     assert st == 0
     assert np.array_equal(synth.canonical_triangles(tri), synth.canonical_triangles(want))
     assert np.array_equal(tri, want)
+
+
+def test_large_star_engine_vs_oracle(gta, checker, star_path):
+    """The star engine on one large frame (csrc/gta_large_star.cuh; triangle lists only under PATH_STAR: they come in cell
+    order): the reference's triangle set after canonical sorting, for point sets with irregular hulls of any size."""
+    L = gta.lib()
+    rng = np.random.default_rng(4)
+    for n in (3, 7, 100, 1156, 5000, 40000, 300000):
+        p = rng.random((n, 2)) * np.array([50.0, 20.0])
+        tri, st, _ = gta.triangulate_large(p)
+        assert st == 0 and L.gta_b200_large_last_engine() == 1, (n, st)
+        want, _ = checker.triangulate(p)
+        assert np.array_equal(synth.canonical_triangles(tri), synth.canonical_triangles(want)), n
+    # a lattice is all ties: not certified, the level-by-level path answers in the reference's emission order
+    gx, gy = np.meshgrid(np.arange(60) * 0.25, np.arange(40) * 0.25)
+    p = np.stack([gx.ravel(), gy.ravel()], 1)
+    tri, st, _ = gta.triangulate_large(p)
+    want, _ = checker.triangulate(p)
+    assert st == 0 and L.gta_b200_large_last_engine() == 0 and np.array_equal(tri, want)
+
+
+def test_cfg4_star_engine(gta, checker, star_path):
+    """cfg 4 through the stars: 10^6 points, the reference's triangle set bit-exact after canonical sorting (north_star)."""
+    p = synth.uniform_patch(1_000_000, seed=4)
+    tri, st, ms = gta.triangulate_large(p)
+    assert st == 0 and gta.lib().gta_b200_large_last_engine() == 1
+    want, _ = checker.triangulate(p)
+    assert np.array_equal(synth.canonical_triangles(tri), synth.canonical_triangles(want))
+    print("cfg 4, star engine: %.1f ms on the device" % ms)
+
+
+def test_large_surface_area_both_engines(gta):
+    """delaunay_surface_area's engine for frames beyond the shared-memory kernels: the star engine by default (areas have no
+    order contract), the level-by-level path under PATH_DC; same count, areas equal to the rounding of the sum order."""
+    rng = np.random.default_rng(9)
+    xyz = np.concatenate([rng.random((200000, 2)) * 300.0, 4.0 + 0.2 * rng.standard_normal((200000, 1))], 1)
+    a = gta.surface_area_large(xyz, flags=synth.GTA_2D)
+    old = gta.set_path(gta.PATH_DC)
+    try:
+        b = gta.surface_area_large(xyz, flags=synth.GTA_2D)
+    finally:
+        gta.set_path(old)
+    assert a["status"] == 0 and b["status"] == 0 and a["engine"] == 1 and b["engine"] == 0
+    assert a["ntri"] == b["ntri"]
+    assert abs(a["area"] - b["area"]) <= 1e-12 * b["area"] and abs(a["area2d"] - b["area2d"]) <= 1e-12 * b["area2d"]
