@@ -19,6 +19,7 @@
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <cstdio>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "dt_core.cuh"
@@ -147,6 +148,19 @@ extern "C" int gta_b200_get_path(void);
 // One large frame through the star engine (gta_large_star.cuh). d_pts: device [n][2]; d_xyz: device [n][3] or null.
 // Returns 0: certified, results written (triangles in cell order); 1: not certified (a tie, duplicates, count rule) -- the
 // caller runs the level-by-level path; < 0: error (g_lerr set).
+// Buffers of the large-frame star path come from the device's stream-ordered pool with a release threshold that keeps
+// them between calls: the ~20 cudaMalloc / cudaFree of a call were 10 ms of its 44.
+static cudaError_t ls_alloc(void** p, size_t bytes) {
+    static std::once_flag once[64];
+    int dev = 0; cudaGetDevice(&dev);
+    std::call_once(once[dev & 63], [dev] {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) { unsigned long long keep = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); }
+    });
+    return cudaMallocAsync(p, bytes ? bytes : 1, 0);
+}
+static void ls_free(void* p) { if (p) cudaFreeAsync(p, 0); }
+
 static int large_star(const double* d_pts, const double* d_xyz, int n, unsigned flags, int* tri, int tri_cap, int* ntri, double* area3, double* area2) {
     using namespace gt;
 #define SCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_lerr = std::string(#call) + ": " + cudaGetErrorString(e_); rc = GTA_B200_E_CUDA; goto out; } } while (0)
@@ -163,7 +177,7 @@ static int large_star(const double* d_pts, const double* d_xyz, int n, unsigned 
     SCK(cudaGetDevice(&dev));
     SCK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     {
-        SCK(cudaMalloc((void**)&d_key, 32)); SCK(cudaMalloc((void**)&d_ctl, 16));
+        SCK(ls_alloc((void**)&d_key, 32)); SCK(ls_alloc((void**)&d_ctl, 16));
         SCK(cudaMemcpy(d_key, hkey, 32, cudaMemcpyHostToDevice)); SCK(cudaMemset(d_ctl, 0, 16));
         ls_bbox<<<sms * 4, 256>>>(d_pts, n, d_key, d_ctl);
         SCK(cudaMemcpy(hkey, d_key, 32, cudaMemcpyDeviceToHost));
@@ -172,14 +186,14 @@ static int large_star(const double* d_pts, const double* d_xyz, int n, unsigned 
         const double xmin = ls_unkey(hkey[0]), xmax = ls_unkey(hkey[1]), ymin = ls_unkey(hkey[2]), ymax = ls_unkey(hkey[3]);
         const StarDims dm = star_dims(n, xmin, xmax, ymin, ymax, std::max(n, 1), 1.0);
         const int ncell = dm.gx * dm.gy;
-        SCK(cudaMalloc((void**)&d_cell, 4 * (size_t)n)); SCK(cudaMalloc((void**)&d_cell2, 4 * (size_t)n));
-        SCK(cudaMalloc((void**)&d_idx, 4 * (size_t)n)); SCK(cudaMalloc((void**)&d_idx2, 4 * (size_t)n));
-        SCK(cudaMalloc((void**)&d_cstart, 4 * (size_t)(ncell + 2))); SCK(cudaMemset(d_cstart, 0, 4 * (size_t)(ncell + 2)));
-        SCK(cudaMalloc((void**)&d_spt, sizeof(SPt) * (size_t)n)); SCK(cudaMalloc((void**)&d_sptf, sizeof(SPtF) * (size_t)n));
-        if (want_area) { SCK(cudaMalloc((void**)&d_sz, 8 * (size_t)n)); SCK(cudaMalloc((void**)&d_a3, 8 * (size_t)n)); SCK(cudaMalloc((void**)&d_a2, 8 * (size_t)n)); SCK(cudaMalloc((void**)&d_sum, 16)); }
-        SCK(cudaMalloc((void**)&d_cnt, 4 * (size_t)n)); SCK(cudaMalloc((void**)&d_off, 4 * (size_t)n));
+        SCK(ls_alloc((void**)&d_cell, 4 * (size_t)n)); SCK(ls_alloc((void**)&d_cell2, 4 * (size_t)n));
+        SCK(ls_alloc((void**)&d_idx, 4 * (size_t)n)); SCK(ls_alloc((void**)&d_idx2, 4 * (size_t)n));
+        SCK(ls_alloc((void**)&d_cstart, 4 * (size_t)(ncell + 2))); SCK(cudaMemset(d_cstart, 0, 4 * (size_t)(ncell + 2)));
+        SCK(ls_alloc((void**)&d_spt, sizeof(SPt) * (size_t)n)); SCK(ls_alloc((void**)&d_sptf, sizeof(SPtF) * (size_t)n));
+        if (want_area) { SCK(ls_alloc((void**)&d_sz, 8 * (size_t)n)); SCK(ls_alloc((void**)&d_a3, 8 * (size_t)n)); SCK(ls_alloc((void**)&d_a2, 8 * (size_t)n)); SCK(ls_alloc((void**)&d_sum, 16)); }
+        SCK(ls_alloc((void**)&d_cnt, 4 * (size_t)n)); SCK(ls_alloc((void**)&d_off, 4 * (size_t)n));
         const uint32_t ovf_cap = (uint32_t)std::max(n / 4, 4096);
-        if (want_tri) { SCK(cudaMalloc((void**)&d_pairs, 8 * (size_t)LS_MAXOWN * n)); SCK(cudaMalloc((void**)&d_ovf, 12 * (size_t)ovf_cap)); }
+        if (want_tri) { SCK(ls_alloc((void**)&d_pairs, 8 * (size_t)LS_MAXOWN * n)); SCK(ls_alloc((void**)&d_ovf, 12 * (size_t)ovf_cap)); }
         // cells, stable sort by cell (order inside a cell = input order), cell starts
         ls_cells<<<G, B>>>(d_pts, n, xmin, ymin, dm.sx, dm.sy, dm.gx, dm.gy, d_cell, d_idx, d_cstart + 1);
         int bits = 1; while ((1ll << bits) < ncell && bits < 32) ++bits;
@@ -188,7 +202,7 @@ static int large_star(const double* d_pts, const double* d_xyz, int n, unsigned 
         cub::DeviceScan::ExclusiveSum(nullptr, tb3, d_cnt, d_off, n);
         tb = std::max(tb, std::max(tb2, tb3));
         if (want_area) { size_t t4 = 0; cub::DeviceReduce::Sum(nullptr, t4, d_a3, d_sum, n); tb = std::max(tb, t4); }
-        SCK(cudaMalloc(&d_tmp, tb));
+        SCK(ls_alloc(&d_tmp, tb));
         cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_cell, d_cell2, d_idx, d_idx2, n, 0, bits);
         cub::DeviceScan::InclusiveSum(d_tmp, tb, d_cstart + 1, d_cstart + 1, ncell);          // cstart[c + 1] = end of cell c
         ls_gather<<<G, B>>>(d_pts, d_xyz, d_idx2, n, d_spt, d_sptf, d_sz);
@@ -202,18 +216,31 @@ static int large_star(const double* d_pts, const double* d_xyz, int n, unsigned 
         SCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ls_star_kernel, 128, 0));
         const int blocks = std::max(1, std::min((n + 127) / 128, std::max(1, occ) * sms));
         const size_t nt = (size_t)blocks * 128;
-        SCK(cudaMalloc((void**)&d_ll, 4 * (size_t)LS_LCAP * nt)); SCK(cudaMalloc((void**)&d_cl, 4 * (size_t)LS_CCAP * nt));
+        SCK(ls_alloc((void**)&d_ll, 4 * (size_t)LS_LCAP * nt)); SCK(ls_alloc((void**)&d_cl, 4 * (size_t)LS_CCAP * nt));
         SCK(cudaMemset(d_ctl, 0, 16));
         static const bool trace = getenv("GTA_B200_TRACE") != nullptr;
+        unsigned long long* d_clk = nullptr;
+        if (trace) { ls_alloc((void**)&d_clk, 8 * (size_t)((n + 31) / 32)); cudaMemset(d_clk, 0, 8 * (size_t)((n + 31) / 32)); }
         cudaEvent_t t0 = nullptr, t1 = nullptr;
         if (trace) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0); }
-        ls_star_kernel<<<blocks, 128>>>(g, d_ll, d_cl, d_sz, (flags & GTA_B200_2D) ? 1 : 0, d_cnt, d_pairs, d_ovf, ovf_cap, d_a3, d_a2, d_ctl);
+        ls_star_kernel<<<blocks, 128>>>(g, d_ll, d_cl, d_sz, (flags & GTA_B200_2D) ? 1 : 0, d_cnt, d_pairs, d_ovf, ovf_cap, d_a3, d_a2, d_ctl, d_clk);
         SCK(cudaGetLastError());
+        if (trace && d_clk) {
+            const int nch = (n + 31) / 32;
+            std::vector<unsigned long long> hc(nch);
+            cudaMemcpy(hc.data(), d_clk, 8 * (size_t)nch, cudaMemcpyDeviceToHost);
+            std::vector<int> order(nch); for (int i = 0; i < nch; ++i) order[i] = i;
+            std::sort(order.begin(), order.end(), [&](int a, int b) { return hc[a] > hc[b]; });
+            unsigned long long sum = 0; for (auto v : hc) sum += v;
+            fprintf(stderr, "[gta_b200] chunk cycles: sum %.3g, median %llu, top:", (double)sum, hc[order[nch / 2]]);
+            for (int i = 0; i < 8 && i < nch; ++i) fprintf(stderr, " ch %d (row %d): %.3g;", order[i], (order[i] * 32) / std::max(dm.gx, 1), (double)hc[order[i]]);
+            fprintf(stderr, "\n");
+        }
         if (trace) {
             cudaEventRecord(t1); cudaEventSynchronize(t1); float ms = 0.f; cudaEventElapsedTime(&ms, t0, t1);
             uint32_t c2[4]; cudaMemcpy(c2, d_ctl, 16, cudaMemcpyDeviceToHost);
             fprintf(stderr, "[gta_b200] large star: n %d grid %d x %d, %d blocks, star kernel %.2f ms, status bits 0x%x, open stars %u\n", n, dm.gx, dm.gy, blocks, ms, c2[0], c2[1]);
-            cudaEventDestroy(t0); cudaEventDestroy(t1);
+            cudaEventDestroy(t0); cudaEventDestroy(t1); ls_free(d_clk);
         }
         cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_cnt, d_off, n);
         uint32_t last_off = 0, last_cnt = 0;
@@ -235,7 +262,7 @@ static int large_star(const double* d_pts, const double* d_xyz, int n, unsigned 
         }
         if (want_tri) {
             const int keep = (int)std::min<long long>(total, tri_cap);
-            SCK(cudaMalloc((void**)&d_tri, sizeof(int) * 3 * (size_t)std::max(keep, 1)));
+            SCK(ls_alloc((void**)&d_tri, sizeof(int) * 3 * (size_t)std::max(keep, 1)));
             ls_emit<<<G, B>>>(d_cnt, d_off, d_pairs, d_idx2, n, d_tri, keep);
             if (novf > 0) ls_emit_overflow<<<(unsigned)((novf + 255) / 256), 256>>>(d_ovf, (int)novf, d_idx2, d_tri, (int)in_slots, keep);
             SCK(cudaGetLastError());
@@ -251,9 +278,9 @@ static int large_star(const double* d_pts, const double* d_xyz, int n, unsigned 
         rc = 0;
     }
 out:
-    cudaFree(d_key); cudaFree(d_ctl); cudaFree(d_cell); cudaFree(d_cell2); cudaFree(d_idx); cudaFree(d_idx2); cudaFree(d_cstart);
-    cudaFree(d_ll); cudaFree(d_cl); cudaFree(d_cnt); cudaFree(d_off); cudaFree(d_pairs); cudaFree(d_ovf); cudaFree(d_spt); cudaFree(d_sptf);
-    cudaFree(d_sz); cudaFree(d_a3); cudaFree(d_a2); cudaFree(d_sum); cudaFree(d_tri); cudaFree(d_tmp);
+    ls_free(d_key); ls_free(d_ctl); ls_free(d_cell); ls_free(d_cell2); ls_free(d_idx); ls_free(d_idx2); ls_free(d_cstart);
+    ls_free(d_ll); ls_free(d_cl); ls_free(d_cnt); ls_free(d_off); ls_free(d_pairs); ls_free(d_ovf); ls_free(d_spt); ls_free(d_sptf);
+    ls_free(d_sz); ls_free(d_a3); ls_free(d_a2); ls_free(d_sum); ls_free(d_tri); ls_free(d_tmp);
     return rc;
 #undef SCK
 }
@@ -285,16 +312,8 @@ static int large_run(const double* points, const double* xyz3, int npoints, int 
     uint32_t hctl[4] = {0, 0, 0, 0};
     LCK(cudaEventCreate(&ev0)); LCK(cudaEventCreate(&ev1));
     LCK(cudaMalloc((void**)&d_pts, sizeof(double) * 2 * (size_t)n));
-    LCK(cudaMalloc((void**)&d_pt, sizeof(Pt) * (size_t)n));
-    LCK(cudaMalloc((void**)&d_k0, 8 * (size_t)n)); LCK(cudaMalloc((void**)&d_k1, 8 * (size_t)n)); LCK(cudaMalloc((void**)&d_ky, 8 * (size_t)n));
-    LCK(cudaMalloc((void**)&d_i0, 4 * (size_t)n)); LCK(cudaMalloc((void**)&d_i1, 4 * (size_t)n));
-    LCK(cudaMalloc((void**)&d_head, 4 * (size_t)n));
-    LCK(cudaMalloc((void**)&d_dst, 8 * (size_t)cap_e)); LCK(cudaMalloc((void**)&d_nxt, 8 * (size_t)cap_e)); LCK(cudaMalloc((void**)&d_prv, 8 * (size_t)cap_e));
-    LCK(cudaMalloc((void**)&d_ctl, 16)); LCK(cudaMemset(d_ctl, 0, 16));
-    LCK(cudaMalloc((void**)&d_cnt, 4 * (size_t)n)); LCK(cudaMalloc((void**)&d_off, 4 * (size_t)n));
     if (xyz3) {
         LCK(cudaMalloc((void**)&d_xyz, sizeof(double) * 3 * (size_t)n));
-        LCK(cudaMalloc((void**)&d_a3, 8 * (size_t)n)); LCK(cudaMalloc((void**)&d_a2, 8 * (size_t)n)); LCK(cudaMalloc((void**)&d_sum, 16));
         LCK(cudaMemcpy(d_xyz, xyz3, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice));
         large_xy<<<G, B>>>(d_xyz, n, d_pts);
     } else LCK(cudaMemcpy(d_pts, points, sizeof(double) * 2 * (size_t)n, cudaMemcpyHostToDevice));
@@ -315,6 +334,15 @@ static int large_run(const double* points, const double* xyz3, int npoints, int 
         }
         g_large_star = 0;
     }
+    // the level-by-level path's buffers (only now: a frame the stars certified never needs them)
+    LCK(cudaMalloc((void**)&d_pt, sizeof(Pt) * (size_t)n));
+    LCK(cudaMalloc((void**)&d_k0, 8 * (size_t)n)); LCK(cudaMalloc((void**)&d_k1, 8 * (size_t)n)); LCK(cudaMalloc((void**)&d_ky, 8 * (size_t)n));
+    LCK(cudaMalloc((void**)&d_i0, 4 * (size_t)n)); LCK(cudaMalloc((void**)&d_i1, 4 * (size_t)n));
+    LCK(cudaMalloc((void**)&d_head, 4 * (size_t)n));
+    LCK(cudaMalloc((void**)&d_dst, 8 * (size_t)cap_e)); LCK(cudaMalloc((void**)&d_nxt, 8 * (size_t)cap_e)); LCK(cudaMalloc((void**)&d_prv, 8 * (size_t)cap_e));
+    LCK(cudaMalloc((void**)&d_ctl, 16)); LCK(cudaMemset(d_ctl, 0, 16));
+    LCK(cudaMalloc((void**)&d_cnt, 4 * (size_t)n)); LCK(cudaMalloc((void**)&d_off, 4 * (size_t)n));
+    if (xyz3) { LCK(cudaMalloc((void**)&d_a3, 8 * (size_t)n)); LCK(cudaMalloc((void**)&d_a2, 8 * (size_t)n)); LCK(cudaMalloc((void**)&d_sum, 16)); }
     {
         // ---- sort: stable by y, then stable by x  => lexicographic (x, y)
         large_keys<<<G, B>>>(d_pts, n, d_k0, d_ky, d_i0, d_ctl + 2);

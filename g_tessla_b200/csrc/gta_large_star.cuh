@@ -78,15 +78,19 @@ struct LsList {
 // ctl: [0] STAR_* bits of any point | 0x1000 when the overflow list is full, [1] open stars (hull vertices),
 // [2] entries of the overflow list: triangles beyond the LS_MAXOWN a point keeps in its own slots (hull vertices own long fans)
 __global__ void __launch_bounds__(128) ls_star_kernel(StarGrid<uint32_t, true> g, uint32_t* llist, uint32_t* clist, const double* sz, int want2d,
-                                                      uint32_t* own_cnt, uint32_t* own_pairs, uint32_t* ovf, uint32_t ovf_cap, double* a3, double* a2, uint32_t* ctl) {
+                                                      uint32_t* own_cnt, uint32_t* own_pairs, uint32_t* ovf, uint32_t ovf_cap, double* a3, double* a2, uint32_t* ctl,
+                                                      unsigned long long* chunk_clk) {
     const size_t nt = (size_t)gridDim.x * blockDim.x, gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int nwarps = (int)(nt >> 5), gwarp = (int)(gtid >> 5);
     LsList lst; lst.l = llist + gtid; lst.c = clist + gtid; lst.nt = nt;
     const int n = g.n;
-    for (int ch = gwarp; (long long)ch * 32 < n; ch += nwarps) {
+    // chunks of 32 consecutive positions; a warp's first chunk is its own number, the rest come from a counter, so that the
+    // chunks along the hull -- whose searches reach far -- do not pile up on the warps they would statically fall to
+    for (int ch = gwarp; (long long)ch * 32 < n;) {
         const int ip = ch * 32 + lane;
         const bool active = ip < n;
+        const long long clk0 = chunk_clk ? clock64() : 0;
         const SPt P = g.pt[active ? ip : 0];
         const double zp = sz ? sz[active ? ip : 0] : 0.0;
         double s3 = 0.0, s2 = 0.0; int cnt = 0;
@@ -114,6 +118,10 @@ __global__ void __launch_bounds__(128) ls_star_kernel(StarGrid<uint32_t, true> g
             if (st) atomicOr(&ctl[0], (uint32_t)st);
             if (hull) atomicAdd(&ctl[1], 1u);
         }
+        if (chunk_clk && lane == 0) chunk_clk[ch] = (unsigned long long)(clock64() - clk0);
+        int nextch = 0;
+        if (lane == 0) nextch = nwarps + (int)atomicAdd(&ctl[3], 1u);
+        ch = __shfl_sync(0xffffffffu, nextch, 0);
     }
 }
 __global__ void ls_emit(const uint32_t* own_cnt, const uint32_t* offs, const uint32_t* own_pairs, const uint32_t* idx, int n, int* tri, int tri_cap) {

@@ -125,6 +125,7 @@ struct StarCursor { int pos, end, ci, rows, width, part; int region; };   // reg
 struct StarRegion {
     int disc, band;               // clip to the circumdisc / to a band around the segment p - cur
     double px, py, A, B;          // left of p -> cur in real coordinates: B (x - px) < A (y - py)
+    double slope, hrow;           // A / B (B != 0) and the height of a row of cells, computed once per region
     double cx, cy, R;             // the disc, centre and (conservative) radius in real coordinates
     double bw, bx0, bx1;          // the band: |x - X(y)| <= bw on the line's x at height y, and bx0 <= x <= bx1
     int row, row_end, seg, sb0, sb1;
@@ -136,7 +137,7 @@ template <class Idx, bool GL>
 GT_INLINE bool star_region_cols(const StarGrid<Idx, GL>& g, const StarRegion& rg, int row, int* ca, int* cb) {
     double y0 = g.ymin, y1 = g.ymax;
     if (g.sy > 0.0) {
-        const double h = 1.0 / g.sy;
+        const double h = rg.hrow;
         y0 = g.y0 + row * h; y1 = g.y0 + (row + 1) * h;
         const double my = 1e-9 * (fabs(y0) + fabs(y1) + h);
         y0 -= my; y1 += my;
@@ -146,7 +147,7 @@ GT_INLINE bool star_region_cols(const StarGrid<Idx, GL>& g, const StarRegion& rg
     double xa = g.xmin, xb = g.xmax;
     const double A = rg.A, B = rg.B, t0 = y0 - rg.py, t1 = y1 - rg.py;
     if (B != 0.0) {
-        const double sl = A / B, X0 = rg.px + sl * t0, X1 = rg.px + sl * t1;
+        const double sl = rg.slope, X0 = rg.px + sl * t0, X1 = rg.px + sl * t1;
         const double mx = 1e-9 * (fabs(rg.px) + fabs(sl * t0) + fabs(sl * t1));
         if (X0 == X0 && X1 == X1 && mx == mx) {                   // (an overflowing slope bounds nothing)
             if (B > 0.0) xb = fmin(xb, fmax(X0, X1) + mx); else xa = fmax(xa, fmin(X0, X1) - mx);
@@ -551,6 +552,7 @@ GT_NOINLINE int star_certify(const StarGrid<Idx, GL>& g, StarLane& L, StarCursor
     // left of p -> cur in real coordinates (a clockwise walk's left is the real right)
     const double sgn = ym ? -1.0 : 1.0;
     rg.px = px; rg.py = py; rg.A = sgn * e.qdx; rg.B = sgn * star_flip(e.qdy, ym);
+    rg.slope = rg.B != 0.0 ? rg.A / rg.B : 0.0; rg.hrow = g.sy > 0.0 ? 1.0 / g.sy : 0.0;
     rg.disc = disc; rg.cx = dcx; rg.cy = dcy; rg.R = dR;
     rg.band = 0; rg.bw = rg.bx0 = rg.bx1 = 0.0;
     rg.lim = all; rg.skip = seen; rg.seg = 0; rg.sb0 = 1; rg.sb1 = 0;

@@ -226,6 +226,7 @@ int emu_star(const double* points, int n, int w0, double dens, int full, int cca
             tri_out[3 * nt] = id[ip]; tri_out[3 * nt + 1] = id[n1]; tri_out[3 * nt + 2] = id[n2];
             ++nt;
         };
+        const long rows0 = g_star.rows, gc0 = g_star.gridcand, ex0 = g_star.expand;
         if (ccap <= 12) {
             if (full) st |= star_point<8, 12, true>(g, ip, true, w0, lst, &hull, emit);
             else st |= star_point<8, 12, false>(g, ip, true, w0, lst, &hull, emit);
@@ -233,6 +234,9 @@ int emu_star(const double* points, int n, int w0, double dens, int full, int cca
             if (full) st |= star_point<8, 64, true>(g, ip, true, w0, lst, &hull, emit);
             else st |= star_point<8, 64, false>(g, ip, true, w0, lst, &hull, emit);
         }
+        if (getenv("STAR_DEBUG") && (g_star.rows - rows0 > 20000 || g_star.gridcand - gc0 > 20000))
+            fprintf(stderr, "heavy point pos %d (%.4f, %.4f) cell (%d, %d): region rows %ld, candidates %ld, scans %ld, hull %d\n", ip, pt[ip].x, pt[ip].y,
+                    star_cell(pt[ip].x, xmin, d.sx, d.gx), star_cell(pt[ip].y, ymin, d.sy, d.gy), g_star.rows - rows0, g_star.gridcand - gc0, g_star.expand - ex0, (int)hull);
         nh += hull;
     }
     if (stats_out) {
