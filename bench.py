@@ -323,10 +323,11 @@ def run_native(args):
         ach = ALG_BYTES_PER_FRAME * frames_per_launch / (dom_ms / 1e3) / 1e9     # GB/s of algorithmic bytes per launch
         stage_sum = max(1e-9, stages["star"] + stages["prepass"] + stages["walk"] + stages["area"])
         # ncu dram bytes per frame of that kernel: from the committed capture summary, flagged when the kernels changed since
-        traffic, traffic_meta = None, {"source": TRAFFIC_JSON, "stale": None}
+        traffic, traffic_meta, ncu_extra = None, {"source": TRAFFIC_JSON, "stale": None}, None
         try:
             tj = json.load(open(os.path.join(ROOT, TRAFFIC_JSON)))
             traffic = tj["dram_bytes_per_frame"] * frames_per_launch / 1e9
+            ncu_extra = {k: tj.get(k) for k in ("fp64_pipe_active_pct", "issue_active_pct", "active_lanes_per_instruction", "warp_instructions_per_frame", "registers_per_thread")}
             traffic_meta.update({"dram_bytes_per_frame": tj["dram_bytes_per_frame"], "captured_frames": tj.get("frames"),
                                  "capture_git": tj.get("git"), "stale": tj.get("sources_sha") != kernel_sources_sha()})
         except Exception as e:
@@ -369,7 +370,8 @@ def run_native(args):
                          "note": "the star kernel reads each coordinate once (DRAM traffic ~ the algorithmic bytes) and is bound by instruction issue and the FP64 pipe, "
                                  "not by HBM: ~2,300 double-precision predicate operations per point against 24 bytes of input (DESIGN.md section 5)"},
             "roofline_fp64": {"achieved": fl, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fl / fp64_peak,
-                              "peak_source": fp64_src, "alg_flop_per_frame": ALG_FLOP_PER_FRAME},
+                              "peak_source": fp64_src, "alg_flop_per_frame": ALG_FLOP_PER_FRAME,
+                              "ncu_capture_of_the_kernel": ncu_extra},
             "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -45,7 +45,17 @@ if "--json" in sys.argv:
             h.update(open(os.path.join(src, f), "rb").read())
     rd, wr = gb("dram__bytes_read.sum"), gb("dram__bytes_write.sum")
     git = subprocess.run(["git", "-C", root, "rev-parse", "HEAD"], capture_output=True, text=True).stdout.strip()
+    def num(name):
+        try:
+            return float(d[name].replace(",", ""))
+        except Exception:
+            return None
     json.dump({"report": os.path.basename(rep), "kernel": d.get("Kernel Name", ""), "frames": frames, "dram_bytes_read": rd, "dram_bytes_write": wr,
                "dram_bytes_per_frame": (rd + wr) / frames, "gpu_time_ms": float(d["gpu__time_duration.sum"].replace(",", "")),
+               "fp64_pipe_active_pct": num("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+               "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+               "active_lanes_per_instruction": num("smsp__thread_inst_executed_per_inst_executed.ratio"),
+               "warp_instructions_per_frame": (num("smsp__inst_executed.sum") or 0.0) / frames,
+               "registers_per_thread": num("launch__registers_per_thread"),
                "sources_sha": h.hexdigest(), "git": git}, open(out, "w"), indent=1)
     print("wrote", out)

@@ -7,7 +7,7 @@ ki, vi, gi, bi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index(
 agg = OrderedDict()
 for r in rows:
     name = re.sub(r"<.*", "", r[ki].replace("void ", ""))[:60]
-    m = re.search(r"gt::(star_kernel|tessellate_kernel|prepass_kernel|lpf_wave_kernel|lpf_area_kernel|dfma_peak_kernel|large_\w+)", r[ki])
+    m = re.search(r"gt::(star_kernel|ls_\w+|tessellate_kernel|prepass_kernel|lpf_wave_kernel|lpf_area_kernel|dfma_peak_kernel|large_\w+)", r[ki])
     if m:
         t = re.search(r"<[^>]*>", r[ki])
         name = "gt::" + m.group(1) + (t.group(0) if t else "") + " grid" + r[gi] + " block" + r[bi]

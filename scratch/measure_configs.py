@@ -29,13 +29,20 @@ for cfg, nfr in ((1, 1000), (2, 1000), (1, 100000), (2, 100000), (3, 3000), (3, 
     for it in range(4):
         torch.cuda.synchronize(); t0 = time.perf_counter(); T.run(xyz, box, 3); torch.cuda.synchronize(); best = min(best, time.perf_counter() - t0)
     assert int((T.status != 0).sum()) == 0
+    cert, fb = g.star_counters(reset=True)
     out['cfg%d_resident_%d' % (cfg, len(xyz))] = dict(frames=len(xyz), ms=best * 1e3, fps=len(xyz) / best,
-                                                      path='throughput path (walkers)' if len(xyz) >= 2048 else 'fused kernel')
+                                                      engine='star engine' if fb == 0 and cert > 0 else ('divide and conquer (tied frames handed over / stars skipped)'))
 p = synth.uniform_patch(1_000_000, seed=4)
 g.triangulate_large(p[:100000])
 tri, st, ms = g.triangulate_large(p)
 t0 = time.perf_counter(); tri, st, ms = g.triangulate_large(p); t1 = time.perf_counter()
 t2 = time.perf_counter(); want, _ = ref.triangulate(p); t3 = time.perf_counter()
-out['cfg4'] = dict(points=len(p), triangles=len(tri), status=st, gpu_device_ms=ms, gpu_e2e_ms=(t1 - t0) * 1e3, cpu_1thread_ms=(t3 - t2) * 1e3,
-                   bit_exact=bool(np.array_equal(tri, want)))
+out['cfg4_divide_and_conquer'] = dict(points=len(p), triangles=len(tri), status=st, gpu_device_ms=ms, gpu_e2e_ms=(t1 - t0) * 1e3, cpu_1thread_ms=(t3 - t2) * 1e3,
+                                      bit_exact_in_emission_order=bool(np.array_equal(tri, want)))
+g.set_path(g.PATH_STAR)
+tri, st, ms = g.triangulate_large(p)
+t0 = time.perf_counter(); tri, st, ms = g.triangulate_large(p); t1 = time.perf_counter()
+out['cfg4_star_engine'] = dict(points=len(p), triangles=len(tri), status=st, engine=int(g.lib().gta_b200_large_last_engine()), gpu_device_ms=ms, gpu_e2e_ms=(t1 - t0) * 1e3,
+                               set_equal_after_canonical_sorting=bool(np.array_equal(synth.canonical_triangles(tri), synth.canonical_triangles(want))))
+g.set_path(g.PATH_AUTO)
 print(json.dumps(out, indent=1))
