@@ -1,4 +1,6 @@
 set -x
 mkdir -p gpurun_out; rm -f gpurun_out/ab.log
-GTA_B200_TRACE=1 timeout 500 python scratch/large_star.py 100000 1000000 2>&1 | grep -v chunk | tee -a gpurun_out/ab.log
-timeout 900 python -m pytest tests/test_gpu_large.py -x -q 2>&1 | tail -2 | tee -a gpurun_out/ab.log
+for t in 64 128 256; do
+  GTA_B200_STAR_THREADS=$t timeout 300 python scratch/star_time.py 100000 1 2>&1 | tail -1 | cut -c1-110 | sed "s/^/T=$t cfg1 /" | tee -a gpurun_out/ab.log
+done
+GTA_B200_PATH=1 timeout 300 python scratch/star_time.py 100000 1 2>&1 | tail -1 | cut -c1-110 | sed "s/^/DC cfg1 /" | tee -a gpurun_out/ab.log
