@@ -110,7 +110,7 @@ GT_INLINE bool star_covers(const StarGrid<Idx, GL>& g, const StarWin& w, double 
 // Cursor over the cell-sorted positions of a window, or of a window without an inner window (the ring a grown window adds):
 // a queue of at most four rectangles of cells, walked row by row -- a row of a rectangle is one contiguous run of
 // positions. The per-candidate cost is one increment and one compare; a new row costs two shared-memory loads.
-struct StarCursor { int pos, end, ci, rows, width, part; int region; };   // region != 0: rows come from the lane's StarRegion instead
+struct StarCursor { int pos, end, ci, rows, width, part; };
 
 // What has to be scanned when a step's answer cannot be certified from the window: a part of the half-plane on the walk's
 // left of p -> cur, scan-converted against the rows of the grid -- per row one run of cells, minus cells scanned before --
@@ -229,7 +229,7 @@ GT_INLINE bool star_cur_next(const StarGrid<Idx, GL>& g, StarCursor& c, const St
 // start on the whole window w (in.c0 > in.c1) or on the ring w \ in
 template <class Idx, bool GL>
 GT_INLINE bool star_cur_begin(const StarGrid<Idx, GL>& g, StarCursor& c, const StarWin& w, const StarWin& in) {
-    c.pos = c.end = 0; c.region = 0;
+    c.pos = c.end = 0;
     if (in.c0 > in.c1) { c.part = 4; c.ci = w.r0 * g.gx + w.c0; c.rows = w.r1 - w.r0 + 1; c.width = w.c1 - w.c0 + 1; }
     else { c.part = 0; c.rows = 0; c.ci = 0; c.width = 0; }
     return star_cur_next(g, c, w, in);
@@ -452,7 +452,7 @@ GT_NOINLINE int star_pass1_grid(const StarGrid<Idx, GL>& g, List lst, StarLane& 
             }
             STAR_STAT(cand, 1); STAR_STAT(gridcand, 1);
             if (left) { lst.put(cnt, pos); ++cnt; STAR_STAT(left, 1); }
-            if (++cu.pos >= cu.end) busy = cu.region ? star_region_next(g, cu, rg) : star_cur_next(g, cu, win, none);
+            if (++cu.pos >= cu.end) busy = cu.part == 5 ? star_region_next(g, cu, rg) : star_cur_next(g, cu, win, none);
         }
     }
     *busy_io = busy;
@@ -517,37 +517,17 @@ GT_NOINLINE void star_pass2(const StarGrid<Idx, GL>& g, List lst, StarLane& L, i
 // points, while a point near the segment subtends a wide angle and leaves a thin cap.
 // *rs = the step's progress: bits 0-7 the box level, STAR_RS_BAND the band has been scanned.
 enum { STAR_RS_BAND = 0x100 };
+// the rare part of star_certify: describe the next region. Returns 1 / 2 (final after all) or 0, | the step's new progress << 4.
 template <class Idx, bool GL>
-GT_NOINLINE int star_certify(const StarGrid<Idx, GL>& g, StarLane& L, StarCursor& cu, StarRegion& rg, int* rs, bool* busy) {
+GT_NOINLINE int star_certify_region(const StarGrid<Idx, GL>& g, StarLane& L, StarCursor& cu, StarRegion& rg, int rs, bool* busy,
+                                    int disc, double dcx, double dcy, double dR) {
     const StarWin win = L.win;
     const uint32_t ym = L.ym;
     const int r = L.r;
-    const int level = *rs & 0xff;
+    const int level = rs & 0xff;
     const StarWin seen = level == 0 ? win : star_win_grow(g, win, level < 24 ? (2 << level) : (1 << 26));      // scanned so far
-    if (star_win_all(g, seen)) return r >= 0 ? 1 : 2;
     const StarEdge e = star_edge(g, L);
     const double px = e.px, py = e.py;
-    // (the region's description is only written once the common case -- the disc fits into the window -- is out of the way)
-    int disc = 0; double dcx = 0.0, dcy = 0.0, dR = 0.0;
-    if (r >= 0) {
-        // circumdisc of (0, q', r') inside what has been scanned?  D = 2 cross(q', r') = -2 mc > 0
-        const StarBest b = star_best(g, L, e);
-        const double mc = b.mc, mcp = b.mcp;
-        if (fabs(mc) * 1048576.0 >= mcp) {
-            const double qdx = e.qdx, qdy = e.qdy, ql = e.ql, rdx = b.rdx, rdy = b.rdy, rl = b.rl;
-            const double D = -2.0 * mc, iD = 1.0 / D;
-            const double ax = rdy * ql, bx = qdy * rl, ay = qdx * rl, by = rdx * ql;
-            const double ux = (ax - bx) * iD, uy = (ay - by) * iD;
-            const double R = sqrt(ux * ux + uy * uy);
-            const double relD = 4.0 * GT_EPS * mcp / fabs(mc) + 8.0 * GT_EPS;
-            const double ex = 4.0 * GT_EPS * (fabs(ax) + fabs(bx)) * fabs(iD) + fabs(ux) * relD;
-            const double ey = 4.0 * GT_EPS * (fabs(ay) + fabs(by)) * fabs(iD) + fabs(uy) * relD;
-            const double mg = 2.0 * (ex + ey) + 1e-12 * R + 8.0 * GT_EPS * (fabs(px) + fabs(py) + R + fabs(ux) + fabs(uy));
-            const double cx = px + ux, cy = py + star_flip(uy, ym);
-            if (star_covers(g, seen, cx - R - mg, cx + R + mg, cy - R - mg, cy + R + mg)) return 1;
-            if (R + mg < 1.7976931348623157e308) { disc = 1; dcx = cx; dcy = cy; dR = R + mg; }
-        }
-    }
     StarWin all; all.c0 = 0; all.r0 = 0; all.c1 = g.gx - 1; all.r1 = g.gy - 1;
     // left of p -> cur in real coordinates (a clockwise walk's left is the real right)
     const double sgn = ym ? -1.0 : 1.0;
@@ -560,15 +540,15 @@ GT_NOINLINE int star_certify(const StarGrid<Idx, GL>& g, StarLane& L, StarCursor
         // (a sliver too flat for a trustworthy centre: no disc, the half-plane alone bounds the search)
         const double qx = e.qdx, qy = star_flip(e.qdy, ym);                   // cur - p, real coordinates
         const double cell = (g.sx > 0.0 && g.sy > 0.0) ? fmax(1.0 / g.sx, 1.0 / g.sy) : 0.0;
-        if (!(*rs & STAR_RS_BAND) && cell > 0.0 && (!rg.disc || rg.R > 6.0 * cell) && e.ql > 36.0 * cell * cell) {
+        if (!(rs & STAR_RS_BAND) && cell > 0.0 && (!rg.disc || rg.R > 6.0 * cell) && e.ql > 36.0 * cell * cell) {
             STAR_STAT(expand, 1);
-            *rs |= STAR_RS_BAND;
+            rs |= STAR_RS_BAND;
             rg.band = 1; rg.bw = 1.5 * cell;
             rg.bx0 = fmin(px, px + qx) - rg.bw; rg.bx1 = fmax(px, px + qx) + rg.bw;
             rg.row = star_cell(fmin(py, py + qy) - rg.bw, g.y0, g.sy, g.gy); rg.row_end = star_cell(fmax(py, py + qy) + rg.bw, g.y0, g.sy, g.gy);
-            cu.region = 1; cu.pos = cu.end = 0;
+            cu.part = 5; cu.pos = cu.end = 0;                        // (part 5: the rows come from the lane's StarRegion)
             *busy = star_region_next(g, cu, rg);
-            return 0;
+            return rs << 4;
         }
     } else if (level == 0) {
         // no point on the left in the window: p -> cur is a hull edge if the whole bounding box is on its right (exact)
@@ -582,7 +562,7 @@ GT_NOINLINE int star_certify(const StarGrid<Idx, GL>& g, StarLane& L, StarCursor
             if (sg == GT_RANGE_ERR) { L.err |= STAR_RANGE; right = false; }
             else if (sg > 0) right = false;
         }
-        if (right) return 2;
+        if (right) return 2 | (rs << 4);
     }
     // the next box
     STAR_STAT(expand, 1);
@@ -592,10 +572,43 @@ GT_NOINLINE int star_certify(const StarGrid<Idx, GL>& g, StarLane& L, StarCursor
         const int d0 = star_cell(rg.cy - rg.R, g.y0, g.sy, g.gy), d1 = star_cell(rg.cy + rg.R, g.y0, g.sy, g.gy);
         rg.row = rg.row > d0 ? rg.row : d0; rg.row_end = rg.row_end < d1 ? rg.row_end : d1;
     }
-    *rs = (*rs & ~0xff) | (level + 1);
-    cu.region = 1; cu.pos = cu.end = 0;
+    rs = (rs & ~0xff) | (level + 1);
+    cu.part = 5; cu.pos = cu.end = 0;                        // (part 5: the rows come from the lane's StarRegion)
     *busy = star_region_next(g, cu, rg);
-    return 0;
+    return rs << 4;
+}
+// Returns the answer (0 / 1 / 2) | the step's new progress << 4.
+template <class Idx, bool GL>
+GT_NOINLINE int star_certify(const StarGrid<Idx, GL>& g, StarLane& L, StarCursor& cu, StarRegion& rg, int rs, bool* busy) {
+    const StarWin win = L.win;
+    const uint32_t ym = L.ym;
+    const int r = L.r;
+    const int level = rs & 0xff;
+    const StarWin seen = level == 0 ? win : star_win_grow(g, win, level < 24 ? (2 << level) : (1 << 26));      // scanned so far
+    if (star_win_all(g, seen)) return (r >= 0 ? 1 : 2) | (rs << 4);
+    int disc = 0; double dcx = 0.0, dcy = 0.0, dR = 0.0;
+    if (r >= 0) {
+        // circumdisc of (0, q', r') inside what has been scanned?  D = 2 cross(q', r') = -2 mc > 0
+        const StarEdge e = star_edge(g, L);
+        const double px = e.px, py = e.py;
+        const StarBest b = star_best(g, L, e);
+        const double mc = b.mc, mcp = b.mcp;
+        if (fabs(mc) * 1048576.0 >= mcp) {
+            const double qdx = e.qdx, qdy = e.qdy, ql = e.ql, rdx = b.rdx, rdy = b.rdy, rl = b.rl;
+            const double D = -2.0 * mc, iD = 1.0 / D;
+            const double ax = rdy * ql, bx = qdy * rl, ay = qdx * rl, by = rdx * ql;
+            const double ux = (ax - bx) * iD, uy = (ay - by) * iD;
+            const double R = sqrt(ux * ux + uy * uy);
+            const double relD = 4.0 * GT_EPS * mcp / fabs(mc) + 8.0 * GT_EPS;
+            const double ex = 4.0 * GT_EPS * (fabs(ax) + fabs(bx)) * fabs(iD) + fabs(ux) * relD;
+            const double ey = 4.0 * GT_EPS * (fabs(ay) + fabs(by)) * fabs(iD) + fabs(uy) * relD;
+            const double mg = 2.0 * (ex + ey) + 1e-12 * R + 8.0 * GT_EPS * (fabs(px) + fabs(py) + R + fabs(ux) + fabs(uy));
+            const double cx = px + ux, cy = py + star_flip(uy, ym);
+            if (star_covers(g, seen, cx - R - mg, cx + R + mg, cy - R - mg, cy + R + mg)) return 1 | (rs << 4);
+            if (R + mg < 1.7976931348623157e308) { disc = 1; dcx = cx; dcy = cy; dR = R + mg; }
+        }
+    }
+    return star_certify_region(g, L, cu, rg, rs, busy, disc, dcx, dcy, dR);
 }
 
 // Star of the point at position `ip`. emit(n1_pos, n2_pos) for every triangle (ip, n1, n2) it owns; *hull = the star is
@@ -660,7 +673,8 @@ GT_INLINE int star_point(const StarGrid<Idx, GL>& g, int ip, bool active, int w0
             star_pass2(g, lst, L, cnt);
             if (STAR_ANY(busy || kk < L.m)) continue;                                // a lane's left list was full: it goes on
             if (scanning) {
-                found = star_certify(g, L, cu, rg, &rs, &busy);
+                const int cr = star_certify(g, L, cu, rg, rs, &busy);
+                found = cr & 15; rs = cr >> 4;
                 if (found) scanning = false;
             }
             if (!STAR_ANY(scanning)) break;
