@@ -86,15 +86,16 @@ __device__ __noinline__ int lpf_wave_phase(uint32_t* st, int sl, LPt* pt, LRec* 
     // errors (never on contract input): the scheduler records them for the frame and gives the subtree up after a hard one
     return s.err ? (s.phase | 16) : s.phase;
 }
-// A walker came back with error bits (they are in its packed state): record them for the frame; after a hard error (pool
-// exhausted, ring inconsistency) give the subtree up -- the frame still completes, its merges above are skipped.
+// A walker came back with error bits (they are in its packed state): record them for the frame and give the subtree up
+// -- the frame still completes, its merges above are skipped. (A range error is hard too: its predicate's sign was forced
+// to 0, and a ring scan over inconsistent signs need not end.)
 // One out-of-line copy for all phases.
 __device__ __noinline__ int lpf_wave_error(uint32_t* st, int sl, LMeta* m, int n, int cap_e) {
     LFrame f; f.pt = nullptr; f.rec = nullptr; f.m = m; f.n = n; f.cap_e = cap_e;
     LState s;
     uint32_t* mine = st + sl;
     ls_unpack(s, [&](int w) { return mine[w * LPF_MAX_SLOTS]; });
-    if (s.phase >= LP_DONE || !(s.err & (GT_ERR_POOL | GT_ERR_RING))) { atomicOr(&m->err, s.err); return s.phase; }
+    if (s.phase >= LP_DONE || !(s.err & (GT_ERR_POOL | GT_ERR_RING | GT_ERR_RANGE))) { atomicOr(&m->err, s.err); return s.phase; }
     lp_abort(f, s);
     ls_pack(s, [&](int w, uint32_t v) { mine[w * LPF_MAX_SLOTS] = v; });
     return s.phase;

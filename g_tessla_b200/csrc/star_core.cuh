@@ -320,7 +320,7 @@ GT_NOINLINE void star_nn(const StarGrid<Idx, GL>& g, List lst, StarLane& L, bool
     win.c0 = win.c1 = star_cell(px, g.x0, g.sx, g.gx); win.r0 = win.r1 = star_cell(py, g.y0, g.sy, g.gy);
     win = star_win_grow(g, win, w0);
     const double BIG = 1.7976931348623157e308;
-    int q0 = -1, b2 = -1; double l1 = BIG, l2 = BIG, l3 = BIG, q0dx = 0.0, q0dy = 0.0;
+    int q0 = -1, b2 = -1; double l1 = BIG, l2 = BIG, l3 = BIG;
     int m = 0; bool overflow = false;
     StarCursor cu;
     bool searching = active;
@@ -331,12 +331,16 @@ GT_NOINLINE void star_nn(const StarGrid<Idx, GL>& g, List lst, StarLane& L, bool
                 const int pos = cu.pos;
                 const SPt S = star_pt(g, pos);
                 const double dx = S.x - px, dy = S.y - py, l = dx * dx + dy * dy;
-                if (pos != ip) {
-                    if (l < l1) { l3 = l2; l2 = l1; b2 = q0; l1 = l; q0 = pos; q0dx = dx; q0dy = dy; }
-                    else if (l < l2) { l3 = l2; l2 = l; b2 = pos; }
-                    else if (l < l3) l3 = l;
-                    if (m < CCAP) { lst.cput(m, pos); ++m; } else overflow = true;
-                }
+                // the three smallest distances, without branches (as an if / else-if chain the compiler shuffled ~40 registers
+                // per candidate): l1 <= l2 <= l3 always, so l < l1 implies l < l2
+                const bool other = pos != ip;
+                const double lx = other ? l : BIG;
+                const bool c1 = lx < l1, c2 = lx < l2, c3 = lx < l3;
+                l3 = c2 ? l2 : (c3 ? lx : l3);
+                l2 = c1 ? l1 : (c2 ? lx : l2);
+                b2 = c1 ? q0 : (c2 ? pos : b2);
+                l1 = c1 ? lx : l1; q0 = c1 ? pos : q0;
+                if (other) { if (m < CCAP) { lst.cput(m, pos); ++m; } else overflow = true; }
                 if (++cu.pos >= cu.end) busy = star_cur_next(g, cu, win, in);
             }
         }
@@ -371,7 +375,6 @@ GT_NOINLINE void star_nn(const StarGrid<Idx, GL>& g, List lst, StarLane& L, bool
         }
         if (!okay) L.err |= STAR_TIE;
     }
-    (void)q0dx; (void)q0dy;
 }
 
 // Pass 1 of a walk step, from the lane's candidate list: which candidates are left of p -> cur? They go to the lane's list

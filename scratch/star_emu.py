@@ -13,7 +13,7 @@ names = "cand left icc exact expand steps points hullcert nhull gx gy".split()
 for cfg, nfr in ((1, 20), (3, 20), (5, 4)):
     c = synth.config(cfg, nframes=nfr)
     r = chk.tessellate(c["xyz"], c["box"], c["espace"], c["flags"], want_corr=True)
-    tot = np.zeros(11); bad = 0; cert = 0
+    tot = np.zeros(17); bad = 0; cert = 0
     for f in range(nfr):
         nc = int(r["ncorr"][f])
         p = np.concatenate([c["xyz"][f, :, :2], r["corr"][f, :nc, :2]])
