@@ -196,3 +196,33 @@ def test_star_path_refuses_what_it_cannot_certify(emu, golden):
                 seen += 1
                 assert np.array_equal(_canon(tri), _canon(g["tri_" + k[4:]])), k
     assert seen >= 3
+
+
+def test_star_path_scales_offsets_and_near_ties(emu, checker):
+    """The float screening inside the star path must never change a result: point sets at small and huge scales, far from
+    the origin (where the float copies of the coordinates cannot tell neighbours apart and the screen has to stand back),
+    and lattices jittered by less than float resolution (every square nearly cocircular: double / exact stages decide).
+    A certified result equals the reference's triangles; exact lattices are still refused."""
+    rng = np.random.default_rng(11)
+    for n in (40, 300):
+        base = rng.random((n, 2)) * np.array([5.0, 3.0])
+        for scale in (1e-8, 1e-3, 1.0, 1e6, 1e20):       # (below ~1e-10 the reference calls neighbours duplicates: 1e-12 absolute)
+            for off in (0.0, 1e3, 3e7):
+                p = (base + off) * scale
+                want, _ = checker.triangulate(p)
+                for full in (True, False):
+                    tri, st, cnt = emu.star(p, full=full)
+                    assert st == 0 and np.array_equal(_canon(tri), _canon(want)), (n, scale, off, full, st)
+    gx, gy = np.meshgrid(np.arange(12.0), np.arange(10.0))
+    lat = np.stack([gx.ravel(), gy.ravel()], 1)
+    for jit in (1e-3, 1e-7, 1e-9, 1e-13):
+        for off in (0.0, 1000.0):
+            p = lat + off + rng.uniform(-jit, jit, lat.shape)
+            want, _ = checker.triangulate(p)
+            tri, st, _ = emu.star(p)
+            if tri is None:
+                assert st & 1                                            # (a jitter that rounds away leaves exact ties)
+            else:
+                assert np.array_equal(_canon(tri), _canon(want)), (jit, off)
+    tri, st, _ = emu.star(lat * 0.1 + 7.0)
+    assert tri is None and st & 1
