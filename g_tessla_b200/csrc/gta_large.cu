@@ -166,19 +166,19 @@ static int large_star(const double* d_pts, const double* d_xyz, int n, unsigned 
 #define SCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_lerr = std::string(#call) + ": " + cudaGetErrorString(e_); rc = GTA_B200_E_CUDA; goto out; } } while (0)
     int rc = 1;
     unsigned long long* d_key = nullptr; uint32_t *d_ctl = nullptr, *d_cell = nullptr, *d_cell2 = nullptr, *d_idx = nullptr, *d_idx2 = nullptr, *d_cstart = nullptr;
-    uint32_t *d_ll = nullptr, *d_cl = nullptr, *d_cnt = nullptr, *d_off = nullptr, *d_pairs = nullptr, *d_ovf = nullptr;
-    SPt* d_spt = nullptr; SPtF* d_sptf = nullptr; double *d_sz = nullptr, *d_a3 = nullptr, *d_a2 = nullptr, *d_sum = nullptr; int* d_tri = nullptr;
+    uint32_t *d_ll = nullptr, *d_cl = nullptr, *d_cnt = nullptr, *d_off = nullptr, *d_pairs = nullptr, *d_ovf = nullptr, *d_def = nullptr;
+    SPt* d_spt = nullptr; SPtF* d_sptf = nullptr; double *d_sz = nullptr, *d_a3 = nullptr, *d_a2 = nullptr, *d_sum = nullptr, *d_rowx = nullptr; int* d_tri = nullptr;
     void* d_tmp = nullptr; size_t tb = 0, tb2 = 0, tb3 = 0;
     const int B = 256, G = (n + B - 1) / B;
     const bool want_area = d_xyz != nullptr && area3 != nullptr, want_tri = tri != nullptr && tri_cap > 0;
     unsigned long long hkey[4] = {~0ull, 0ull, ~0ull, 0ull};
-    uint32_t hctl[4] = {0, 0, 0, 0};
+    uint32_t hctl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int dev = 0, sms = 0;
     SCK(cudaGetDevice(&dev));
     SCK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     {
-        SCK(ls_alloc((void**)&d_key, 32)); SCK(ls_alloc((void**)&d_ctl, 16));
-        SCK(cudaMemcpy(d_key, hkey, 32, cudaMemcpyHostToDevice)); SCK(cudaMemset(d_ctl, 0, 16));
+        SCK(ls_alloc((void**)&d_key, 32)); SCK(ls_alloc((void**)&d_ctl, 32));
+        SCK(cudaMemcpy(d_key, hkey, 32, cudaMemcpyHostToDevice)); SCK(cudaMemset(d_ctl, 0, 32));
         ls_bbox<<<sms * 4, 256>>>(d_pts, n, d_key, d_ctl);
         SCK(cudaMemcpy(hkey, d_key, 32, cudaMemcpyDeviceToHost));
         SCK(cudaMemcpy(hctl, d_ctl, 16, cudaMemcpyDeviceToHost));
@@ -206,27 +206,45 @@ static int large_star(const double* d_pts, const double* d_xyz, int n, unsigned 
         cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_cell, d_cell2, d_idx, d_idx2, n, 0, bits);
         cub::DeviceScan::InclusiveSum(d_tmp, tb, d_cstart + 1, d_cstart + 1, ncell);          // cstart[c + 1] = end of cell c
         ls_gather<<<G, B>>>(d_pts, d_xyz, d_idx2, n, d_spt, d_sptf, d_sz);
+        SCK(ls_alloc((void**)&d_rowx, 16 * (size_t)dm.gy));
+        ls_rowx<<<(unsigned)((32 * (size_t)dm.gy + 255) / 256), 256>>>(d_spt, d_cstart, dm.gx, dm.gy, d_rowx);
         // stars
         StarGrid<uint32_t, true> g;
         g.pt = d_spt; g.ptf = d_sptf; g.cstart = d_cstart; g.pt_s = g.ptf_s = g.cstart_s = 0;
         g.kf = (float)(2.5 * 5.9604644775390625e-08 * std::max(std::max(fabs(xmin), fabs(xmax)), std::max(fabs(ymin), fabs(ymax)))) * 1.0001f;
         g.n = n; g.gx = dm.gx; g.gy = dm.gy; g.x0 = xmin; g.y0 = ymin; g.sx = dm.sx; g.sy = dm.sy;
         g.xmin = xmin; g.xmax = xmax; g.ymin = ymin; g.ymax = ymax;
+        g.cx0 = g.cy0 = 0; g.ggx = dm.gx; g.ggy = dm.gy; g.open = 0; g.rowx = d_rowx;
         int occ = 0;
         SCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ls_star_kernel, 128, 0));
         const int blocks = std::max(1, std::min((n + 127) / 128, std::max(1, occ) * sms));
         const size_t nt = (size_t)blocks * 128;
         SCK(ls_alloc((void**)&d_ll, 4 * (size_t)LS_LCAP * nt)); SCK(ls_alloc((void**)&d_cl, 4 * (size_t)LS_CCAP * nt));
-        SCK(cudaMemset(d_ctl, 0, 16));
+        SCK(cudaMemset(d_ctl, 0, 32));
         static const bool trace = getenv("GTA_B200_TRACE") != nullptr;
+        static const int defer_per = getenv("GTA_B200_DEFER_PER") ? std::max(1, std::min(32, atoi(getenv("GTA_B200_DEFER_PER")))) : 1;   // deferred points per warp
+        static const bool tiles = !getenv("GTA_B200_LARGE_TILES") || atoi(getenv("GTA_B200_LARGE_TILES")) != 0;     // experiments: 0 = every point from global memory
         unsigned long long* d_clk = nullptr;
-        if (trace) { ls_alloc((void**)&d_clk, 8 * (size_t)((n + 31) / 32)); cudaMemset(d_clk, 0, 8 * (size_t)((n + 31) / 32)); }
+        if (trace) { ls_alloc((void**)&d_clk, 8 * (size_t)n); cudaMemset(d_clk, 0, 8 * (size_t)n); }      // (a chunk may be one deferred point)
         cudaEvent_t t0 = nullptr, t1 = nullptr;
         if (trace) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0); }
-        ls_star_kernel<<<blocks, 128>>>(g, d_ll, d_cl, d_sz, (flags & GTA_B200_2D) ? 1 : 0, d_cnt, d_pairs, d_ovf, ovf_cap, d_a3, d_a2, d_ctl, d_clk);
+        if (tiles) {
+            // tiles of the grid staged in shared memory; what they defer goes through ls_star_kernel afterwards
+            const int tiles_x = (dm.gx + LT_TW - 1) / LT_TW, tiles_y = (dm.gy + LT_TH - 1) / LT_TH, ntiles = tiles_x * tiles_y;
+            const size_t smem = LtSmem().total;
+            int tocc = 0;
+            SCK(ls_alloc((void**)&d_def, 4 * (size_t)n));
+            SCK(cudaFuncSetAttribute(ls_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tocc, ls_tile_kernel, LT_T, smem));
+            ls_tile_kernel<<<std::max(1, std::min(ntiles, std::max(1, tocc) * sms)), LT_T, smem>>>(g, tiles_x, ntiles, d_sz, (flags & GTA_B200_2D) ? 1 : 0, d_cnt, d_pairs, d_a3, d_a2, d_ctl, d_def);
+            SCK(cudaGetLastError());
+            if (trace) { cudaEvent_t tm; cudaEventCreate(&tm); cudaEventRecord(tm); cudaEventSynchronize(tm); float ms = 0.f; cudaEventElapsedTime(&ms, t0, tm); fprintf(stderr, "[gta_b200] tile kernel %.2f ms (%d tiles)\n", ms, ntiles); cudaEventDestroy(tm); }
+            ls_star_kernel<<<blocks, 128>>>(g, d_ll, d_cl, d_sz, (flags & GTA_B200_2D) ? 1 : 0, d_cnt, d_pairs, d_ovf, ovf_cap, d_a3, d_a2, d_ctl, d_clk, d_def, d_ctl + 4, defer_per);
+        } else
+        ls_star_kernel<<<blocks, 128>>>(g, d_ll, d_cl, d_sz, (flags & GTA_B200_2D) ? 1 : 0, d_cnt, d_pairs, d_ovf, ovf_cap, d_a3, d_a2, d_ctl, d_clk, nullptr, nullptr, 32);
         SCK(cudaGetLastError());
         if (trace && d_clk) {
-            const int nch = (n + 31) / 32;
+            const int nch = tiles ? std::min(n, 4096) : (n + 31) / 32;
             std::vector<unsigned long long> hc(nch);
             cudaMemcpy(hc.data(), d_clk, 8 * (size_t)nch, cudaMemcpyDeviceToHost);
             std::vector<int> order(nch); for (int i = 0; i < nch; ++i) order[i] = i;
@@ -238,8 +256,8 @@ static int large_star(const double* d_pts, const double* d_xyz, int n, unsigned 
         }
         if (trace) {
             cudaEventRecord(t1); cudaEventSynchronize(t1); float ms = 0.f; cudaEventElapsedTime(&ms, t0, t1);
-            uint32_t c2[4]; cudaMemcpy(c2, d_ctl, 16, cudaMemcpyDeviceToHost);
-            fprintf(stderr, "[gta_b200] large star: n %d grid %d x %d, %d blocks, star kernel %.2f ms, status bits 0x%x, open stars %u\n", n, dm.gx, dm.gy, blocks, ms, c2[0], c2[1]);
+            uint32_t c2[8]; cudaMemcpy(c2, d_ctl, 32, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[gta_b200] large star: n %d grid %d x %d, %d blocks, star kernels %.2f ms, status bits 0x%x, open stars %u, deferred by the tiles %u\n", n, dm.gx, dm.gy, blocks, ms, c2[0], c2[1], c2[4]);
             cudaEventDestroy(t0); cudaEventDestroy(t1); ls_free(d_clk);
         }
         cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_cnt, d_off, n);
@@ -280,7 +298,7 @@ static int large_star(const double* d_pts, const double* d_xyz, int n, unsigned 
 out:
     ls_free(d_key); ls_free(d_ctl); ls_free(d_cell); ls_free(d_cell2); ls_free(d_idx); ls_free(d_idx2); ls_free(d_cstart);
     ls_free(d_ll); ls_free(d_cl); ls_free(d_cnt); ls_free(d_off); ls_free(d_pairs); ls_free(d_ovf); ls_free(d_spt); ls_free(d_sptf);
-    ls_free(d_sz); ls_free(d_a3); ls_free(d_a2); ls_free(d_sum); ls_free(d_tri); ls_free(d_tmp);
+    ls_free(d_sz); ls_free(d_a3); ls_free(d_a2); ls_free(d_sum); ls_free(d_tri); ls_free(d_tmp); ls_free(d_def); ls_free(d_rowx);
     return rc;
 #undef SCK
 }

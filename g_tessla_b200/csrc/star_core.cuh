@@ -34,11 +34,16 @@ namespace gt {
 struct alignas(16) SPt { double x, y; };
 struct alignas(8) SPtF { float x, y; };                       // the same point rounded to float (screening only)
 
-enum { STAR_TIE = 1, STAR_DUP = 2, STAR_GUARD = 4, STAR_RANGE = 8 };
+enum { STAR_TIE = 1, STAR_DUP = 2, STAR_GUARD = 4, STAR_RANGE = 8, STAR_DEFER = 16 };
 
 // The grid of one frame: points in cell order (cell = row * gx + col), cell c holds positions cstart[c] .. cstart[c+1]-1.
-// GL = false: the frame's arrays are shared memory (the batched kernel); GL = true: global memory (one large frame).
-template <class Idx, bool GL = false>
+// GL = 0: the frame's arrays are shared memory (the batched kernel); GL = 1: global memory (one large frame);
+// GL = 2: a TILE of a large frame's grid staged in shared memory (gta_large_star.cuh): gx x gy are the staged cells, the
+// staged cell (0, 0) is cell (cx0, cy0) of the frame's ggx x ggy grid, and a side of the tile that is not a side of the
+// frame's grid is OPEN: there are points beyond it. A search that would have to look beyond an open side gives up with
+// STAR_DEFER (the point goes to the kernel that reads the whole frame from global memory); nothing is ever concluded
+// from having scanned "everything" unless everything really was staged.
+template <class Idx, int GL = 0>
 struct StarGrid {
     const SPt* pt;             // [n] cell-sorted coordinates
     const SPtF* ptf;           // [n] the same, rounded to float
@@ -48,27 +53,29 @@ struct StarGrid {
     int n, gx, gy;
     double x0, y0, sx, sy;     // col = trunc((x - x0) * sx) clamped to [0, gx-1]; row likewise: monotone in x / y
     double xmin, xmax, ymin, ymax;   // exact extremes of the point set (its bounding box)
+    const double* rowx;              // GL = 1 only (nullable): [2 r], [2 r + 1] = smallest and largest x of the points in grid row r (+inf, -inf: none)
+    int cx0, cy0, ggx, ggy, open;    // GL = 2 only: the tile's place in the frame's grid; open = 1 left | 2 right | 4 bottom | 8 top
 };
 
 // Reads of the frame's arrays. On the device they are shared memory and the loads say so (the passes are out-of-line
 // functions: behind a generic pointer the compiler issues generic loads, which wait on the long scoreboard).
 #if defined(__CUDA_ARCH__)
-template <class Idx, bool GL> GT_INLINE SPt star_pt(const StarGrid<Idx, GL>& g, int pos) {
-    if (GL) return g.pt[pos];
+template <class Idx, int GL> GT_INLINE SPt star_pt(const StarGrid<Idx, GL>& g, int pos) {
+    if (GL == 1) return g.pt[pos];
     SPt v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(g.pt_s + 16u * (uint32_t)pos)); return v;
 }
-template <class Idx, bool GL> GT_INLINE SPtF star_ptf(const StarGrid<Idx, GL>& g, int pos) {
-    if (GL) return g.ptf[pos];
+template <class Idx, int GL> GT_INLINE SPtF star_ptf(const StarGrid<Idx, GL>& g, int pos) {
+    if (GL == 1) return g.ptf[pos];
     SPtF v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(g.ptf_s + 8u * (uint32_t)pos)); return v;
 }
-template <class Idx, bool GL> GT_INLINE int star_cstart(const StarGrid<Idx, GL>& g, int c) {
-    if (GL) return (int)g.cstart[c];
+template <class Idx, int GL> GT_INLINE int star_cstart(const StarGrid<Idx, GL>& g, int c) {
+    if (GL == 1) return (int)g.cstart[c];
     uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(g.cstart_s + 4u * (uint32_t)c)); return (int)v;
 }
 #else
-template <class Idx, bool GL> GT_INLINE SPt star_pt(const StarGrid<Idx, GL>& g, int pos) { return g.pt[pos]; }
-template <class Idx, bool GL> GT_INLINE SPtF star_ptf(const StarGrid<Idx, GL>& g, int pos) { return g.ptf[pos]; }
-template <class Idx, bool GL> GT_INLINE int star_cstart(const StarGrid<Idx, GL>& g, int c) { return (int)g.cstart[c]; }
+template <class Idx, int GL> GT_INLINE SPt star_pt(const StarGrid<Idx, GL>& g, int pos) { return g.pt[pos]; }
+template <class Idx, int GL> GT_INLINE SPtF star_ptf(const StarGrid<Idx, GL>& g, int pos) { return g.ptf[pos]; }
+template <class Idx, int GL> GT_INLINE int star_cstart(const StarGrid<Idx, GL>& g, int c) { return (int)g.cstart[c]; }
 #endif
 
 // work counters of the emulation build
@@ -90,9 +97,20 @@ GT_INLINE int star_cell(double v, double o, double s, int g) {
 
 // window of cells [c0, c1] x [r0, r1] (inclusive)
 struct StarWin { int c0, c1, r0, r1; };
-template <class Idx, bool GL>
-GT_INLINE bool star_win_all(const StarGrid<Idx, GL>& g, const StarWin& w) { return w.c0 == 0 && w.r0 == 0 && w.c1 == g.gx - 1 && w.r1 == g.gy - 1; }
-template <class Idx, bool GL>
+// column / row of a coordinate in the grid's own numbering. A tile (GL = 2) bins exactly like the frame's grid (same map,
+// shifted by whole cells); the _u forms may lie outside the tile -- that is how "beyond the staged cells" shows.
+template <class Idx, int GL> GT_INLINE int star_col_u(const StarGrid<Idx, GL>& g, double x) { return GL == 2 ? star_cell(x, g.x0, g.sx, g.ggx) - g.cx0 : star_cell(x, g.x0, g.sx, g.gx); }
+template <class Idx, int GL> GT_INLINE int star_row_u(const StarGrid<Idx, GL>& g, double y) { return GL == 2 ? star_cell(y, g.y0, g.sy, g.ggy) - g.cy0 : star_cell(y, g.y0, g.sy, g.gy); }
+template <class Idx, int GL> GT_INLINE int star_col(const StarGrid<Idx, GL>& g, double x) { int c = star_col_u(g, x); if (GL == 2) { c = c > 0 ? c : 0; c = c < g.gx - 1 ? c : g.gx - 1; } return c; }
+template <class Idx, int GL> GT_INLINE int star_row(const StarGrid<Idx, GL>& g, double y) { int r = star_row_u(g, y); if (GL == 2) { r = r > 0 ? r : 0; r = r < g.gy - 1 ? r : g.gy - 1; } return r; }
+// does the window reach an open side of a tile? (its cells end there, the points do not)
+template <class Idx, int GL> GT_INLINE bool star_win_open(const StarGrid<Idx, GL>& g, const StarWin& w) {
+    if (GL != 2) return false;
+    return ((g.open & 1) && w.c0 <= 0) || ((g.open & 2) && w.c1 >= g.gx - 1) || ((g.open & 4) && w.r0 <= 0) || ((g.open & 8) && w.r1 >= g.gy - 1);
+}
+template <class Idx, int GL>
+GT_INLINE bool star_win_all(const StarGrid<Idx, GL>& g, const StarWin& w) { return w.c0 == 0 && w.r0 == 0 && w.c1 == g.gx - 1 && w.r1 == g.gy - 1 && (GL != 2 || g.open == 0); }
+template <class Idx, int GL>
 GT_INLINE StarWin star_win_grow(const StarGrid<Idx, GL>& g, const StarWin& w, int by) {
     StarWin o;
     o.c0 = w.c0 - by > 0 ? w.c0 - by : 0; o.r0 = w.r0 - by > 0 ? w.r0 - by : 0;
@@ -101,11 +119,10 @@ GT_INLINE StarWin star_win_grow(const StarGrid<Idx, GL>& g, const StarWin& w, in
 }
 // is the axis-parallel box [xa, xb] x [ya, yb] inside the window? (a bound beyond the point set's extent clamps to the
 // outermost cell, which is what makes the window's outer edges "infinite")
-template <class Idx, bool GL>
+template <class Idx, int GL>
 GT_INLINE bool star_covers(const StarGrid<Idx, GL>& g, const StarWin& w, double xa, double xb, double ya, double yb) {
     if (!(xa <= xb && ya <= yb)) return false;               // NaN
-    return star_cell(xa, g.x0, g.sx, g.gx) >= w.c0 && star_cell(xb, g.x0, g.sx, g.gx) <= w.c1 &&
-           star_cell(ya, g.y0, g.sy, g.gy) >= w.r0 && star_cell(yb, g.y0, g.sy, g.gy) <= w.r1;
+    return star_col_u(g, xa) >= w.c0 && star_col_u(g, xb) <= w.c1 && star_row_u(g, ya) >= w.r0 && star_row_u(g, yb) <= w.r1;
 }
 // Cursor over the cell-sorted positions of a window, or of a window without an inner window (the ring a grown window adds):
 // a queue of at most four rectangles of cells, walked row by row -- a row of a rectangle is one contiguous run of
@@ -133,16 +150,17 @@ struct StarRegion {
 };
 // cells [ca, cb] of `row` that may hold points of the region (false: none). Conservative: the bounds are widened by far
 // more than their rounding, and the cell map is monotone.
-template <class Idx, bool GL>
+template <class Idx, int GL>
 GT_INLINE bool star_region_cols(const StarGrid<Idx, GL>& g, const StarRegion& rg, int row, int* ca, int* cb) {
     double y0 = g.ymin, y1 = g.ymax;
     if (g.sy > 0.0) {
         const double h = rg.hrow;
-        y0 = g.y0 + row * h; y1 = g.y0 + (row + 1) * h;
+        const int grow = GL == 2 ? row + g.cy0 : row;                   // (the row's number in the frame's grid)
+        y0 = g.y0 + grow * h; y1 = g.y0 + (grow + 1) * h;
         const double my = 1e-9 * (fabs(y0) + fabs(y1) + h);
         y0 -= my; y1 += my;
-        if (row == 0) y0 = fmin(y0, g.ymin);
-        if (row == g.gy - 1) y1 = fmax(y1, g.ymax);
+        if (grow == 0) y0 = fmin(y0, g.ymin);
+        if (grow == (GL == 2 ? g.ggy : g.gy) - 1) y1 = fmax(y1, g.ymax);
     }
     double xa = g.xmin, xb = g.xmax;
     const double A = rg.A, B = rg.B, t0 = y0 - rg.py, t1 = y1 - rg.py;
@@ -156,6 +174,14 @@ GT_INLINE bool star_region_cols(const StarGrid<Idx, GL>& g, const StarRegion& rg
     } else if (A > 0.0) { if (!(t1 > 0.0)) return false; }
     else if (A < 0.0) { if (!(t0 < 0.0)) return false; }
     if (rg.band) { xa = fmax(xa, rg.bx0); xb = fmin(xb, rg.bx1); }
+    if (GL == 1 && g.rowx) {
+        // One large frame: the far searches -- a hull edge, the disc of a skinny triangle along the hull -- walk thousands of
+        // rows along a side of the point set, between the set and its bounding box, where a row holds a cell or two of the
+        // region and no point of it. The row's own extent in x says so before the disc's square root, the cell map and the
+        // two loads of cell starts a whole grid row apart are paid.
+        xa = fmax(xa, g.rowx[2 * (size_t)row]); xb = fmin(xb, g.rowx[2 * (size_t)row + 1]);
+        if (!(xa <= xb)) return false;
+    }
     if (rg.disc) {
         const double cy = rg.cy, R = rg.R;
         if (y1 < cy - R || y0 > cy + R) return false;
@@ -165,13 +191,13 @@ GT_INLINE bool star_region_cols(const StarGrid<Idx, GL>& g, const StarRegion& rg
         xa = fmax(xa, rg.cx - w); xb = fmin(xb, rg.cx + w);
     }
     if (!(xa <= xb)) return false;
-    int a = star_cell(xa, g.x0, g.sx, g.gx), b = star_cell(xb, g.x0, g.sx, g.gx);
+    int a = star_col(g, xa), b = star_col(g, xb);
     a = a > rg.lim.c0 ? a : rg.lim.c0; b = b < rg.lim.c1 ? b : rg.lim.c1;
     if (a > b) return false;
     *ca = a; *cb = b;
     return true;
 }
-template <class Idx, bool GL>
+template <class Idx, int GL>
 GT_INLINE bool star_region_next(const StarGrid<Idx, GL>& g, StarCursor& c, StarRegion& rg) {
     for (;;) {
         int ca, cb;
@@ -200,7 +226,7 @@ GT_INLINE bool star_region_next(const StarGrid<Idx, GL>& g, StarCursor& c, StarR
         if (c.pos < c.end) return true;
     }
 }
-template <class Idx, bool GL>
+template <class Idx, int GL>
 GT_INLINE bool star_cur_row(const StarGrid<Idx, GL>& g, StarCursor& c) {
     while (c.rows > 0) {
         const int a = star_cstart(g, c.ci), b = star_cstart(g, c.ci + c.width);
@@ -209,7 +235,7 @@ GT_INLINE bool star_cur_row(const StarGrid<Idx, GL>& g, StarCursor& c) {
     }
     return false;
 }
-template <class Idx, bool GL>
+template <class Idx, int GL>
 GT_INLINE bool star_cur_next(const StarGrid<Idx, GL>& g, StarCursor& c, const StarWin& w, const StarWin& in) {
     if (star_cur_row(g, c)) return true;
     while (c.part < 4) {
@@ -227,7 +253,7 @@ GT_INLINE bool star_cur_next(const StarGrid<Idx, GL>& g, StarCursor& c, const St
     return false;
 }
 // start on the whole window w (in.c0 > in.c1) or on the ring w \ in
-template <class Idx, bool GL>
+template <class Idx, int GL>
 GT_INLINE bool star_cur_begin(const StarGrid<Idx, GL>& g, StarCursor& c, const StarWin& w, const StarWin& in) {
     c.pos = c.end = 0;
     if (in.c0 > in.c1) { c.part = 4; c.ci = w.r0 * g.gx + w.c0; c.rows = w.r1 - w.r0 + 1; c.width = w.c1 - w.c0 + 1; }
@@ -287,7 +313,7 @@ struct StarLane {
 // pass starts (a few loads and FP64 operations per pass, instead of keeping ~25 more words per lane in local memory: the
 // lanes' state has to stay in the part of L1 the shared memory leaves).
 struct StarEdge { double px, py, qdx, qdy, ql; };
-template <class Idx, bool GL>
+template <class Idx, int GL>
 GT_INLINE StarEdge star_edge(const StarGrid<Idx, GL>& g, const StarLane& L) {
     StarEdge e;
     const SPt P = star_pt(g, L.ip), Q = star_pt(g, L.cur);
@@ -297,7 +323,7 @@ GT_INLINE StarEdge star_edge(const StarGrid<Idx, GL>& g, const StarLane& L) {
     return e;
 }
 struct StarBest { double rdx, rdy, rl, mc, mcp; };           // r relative to p, |r - p|^2, cross(r', q') and the sum of its two products' magnitudes
-template <class Idx, bool GL>
+template <class Idx, int GL>
 GT_INLINE StarBest star_best(const StarGrid<Idx, GL>& g, const StarLane& L, const StarEdge& e) {
     StarBest b;
     const SPt R = star_pt(g, L.r >= 0 ? L.r : L.cur);
@@ -310,14 +336,14 @@ GT_INLINE StarBest star_best(const StarGrid<Idx, GL>& g, const StarLane& L, cons
 
 
 // Nearest neighbour of the lane's point (and the two runners-up); the window's points become the lane's candidate list.
-template <int CCAP, class Idx, bool GL, class List>
+template <int CCAP, class Idx, int GL, class List>
 GT_NOINLINE void star_nn(const StarGrid<Idx, GL>& g, List lst, StarLane& L, bool active, int w0) {
     const int ip = L.ip;
     const SPt P = star_pt(g, ip);
     const double px = P.x, py = P.y;
     StarWin none; none.c0 = 1; none.c1 = 0; none.r0 = 1; none.r1 = 0;
     StarWin win, in = none;
-    win.c0 = win.c1 = star_cell(px, g.x0, g.sx, g.gx); win.r0 = win.r1 = star_cell(py, g.y0, g.sy, g.gy);
+    win.c0 = win.c1 = star_col(g, px); win.r0 = win.r1 = star_row(g, py);
     win = star_win_grow(g, win, w0);
     const double BIG = 1.7976931348623157e308;
     int q0 = -1, b2 = -1; double l1 = BIG, l2 = BIG, l3 = BIG;
@@ -351,6 +377,7 @@ GT_NOINLINE void star_nn(const StarGrid<Idx, GL>& g, List lst, StarLane& L, bool
                 done = star_covers(g, win, px - d - mg, px + d + mg, py - d - mg, py + d + mg);
             }
             if (done) searching = false;
+            else if (star_win_open(g, win)) { L.err |= STAR_DEFER; searching = false; }     // (a tile: the next ring is not staged)
             else {
                 in = win; win = star_win_grow(g, win, 1);
                 STAR_STAT(expand, 1);
@@ -382,7 +409,7 @@ GT_NOINLINE void star_nn(const StarGrid<Idx, GL>& g, List lst, StarLane& L, bool
 // kf (|a| + |b|) + 5 2^-24 (|a d| + |b c|) from the real determinant; beyond that its sign is the real one. Closer to the
 // line: the reference's own filter in double (predicates.c:1628-1651), then the exact stage.
 // kk = next entry of the candidate list; returns kk | cnt << 16 (cnt = entries of the left list).
-template <int LCAP, class Idx, bool GL, class List>
+template <int LCAP, class Idx, int GL, class List>
 GT_NOINLINE int star_pass1_list(const StarGrid<Idx, GL>& g, List lst, StarLane& L, int kk) {
     const int m = L.m, cur = L.cur;
     const uint32_t ym = L.ym;
@@ -428,7 +455,7 @@ GT_NOINLINE int star_pass1_list(const StarGrid<Idx, GL>& g, List lst, StarLane& 
 
 // Pass 1 from the grid: a window with more points than the candidate list holds, or the region a failed certificate
 // asks for (star_certify). Rare. Returns cnt.
-template <int LCAP, class Idx, bool GL, class List>
+template <int LCAP, class Idx, int GL, class List>
 GT_NOINLINE int star_pass1_grid(const StarGrid<Idx, GL>& g, List lst, StarLane& L, StarCursor& cu, StarRegion& rg, bool* busy_io, int cnt) {
     const int cur = L.cur, ip = L.ip, rbest = L.r;                 // (regions may overlap: r met again would tie with itself)
     const uint32_t ym = L.ym;
@@ -464,7 +491,7 @@ GT_NOINLINE int star_pass1_grid(const StarGrid<Idx, GL>& g, List lst, StarLane& 
 
 // Pass 2: the best of the left list (and of what earlier rounds of this step found): s beats r when it is inside
 // circle(p, cur, r) = incircle(a = r, b = cur, c = s, d = p) > 0: the reference's filter (predicates.c:3238-3267), then exact.
-template <class Idx, bool GL, class List>
+template <class Idx, int GL, class List>
 GT_NOINLINE void star_pass2(const StarGrid<Idx, GL>& g, List lst, StarLane& L, int cnt) {
     const uint32_t ym = L.ym;
     const StarEdge e = star_edge(g, L);
@@ -521,7 +548,7 @@ GT_NOINLINE void star_pass2(const StarGrid<Idx, GL>& g, List lst, StarLane& L, i
 // *rs = the step's progress: bits 0-7 the box level, STAR_RS_BAND the band has been scanned.
 enum { STAR_RS_BAND = 0x100 };
 // the rare part of star_certify: describe the next region. Returns 1 / 2 (final after all) or 0, | the step's new progress << 4.
-template <class Idx, bool GL>
+template <class Idx, int GL>
 GT_NOINLINE int star_certify_region(const StarGrid<Idx, GL>& g, StarLane& L, StarCursor& cu, StarRegion& rg, int rs, bool* busy,
                                     int disc, double dcx, double dcy, double dR) {
     const StarWin win = L.win;
@@ -548,7 +575,14 @@ GT_NOINLINE int star_certify_region(const StarGrid<Idx, GL>& g, StarLane& L, Sta
             rs |= STAR_RS_BAND;
             rg.band = 1; rg.bw = 1.5 * cell;
             rg.bx0 = fmin(px, px + qx) - rg.bw; rg.bx1 = fmax(px, px + qx) + rg.bw;
-            rg.row = star_cell(fmin(py, py + qy) - rg.bw, g.y0, g.sy, g.gy); rg.row_end = star_cell(fmax(py, py + qy) + rg.bw, g.y0, g.sy, g.gy);
+            rg.row = star_row(g, fmin(py, py + qy) - rg.bw); rg.row_end = star_row(g, fmax(py, py + qy) + rg.bw);
+            if (GL == 2) {                                           // a tile: the band must lie inside the staged cells
+                StarWin bb; bb.c0 = star_col_u(g, rg.bx0); bb.c1 = star_col_u(g, rg.bx1);
+                bb.r0 = star_row_u(g, fmin(py, py + qy) - rg.bw); bb.r1 = star_row_u(g, fmax(py, py + qy) + rg.bw);
+                if (((g.open & 1) && bb.c0 < 0) || ((g.open & 2) && bb.c1 > g.gx - 1) || ((g.open & 4) && bb.r0 < 0) || ((g.open & 8) && bb.r1 > g.gy - 1)) {
+                    L.err |= STAR_DEFER; *busy = false; return 1 | (rs << 4);
+                }
+            }
             cu.part = 5; cu.pos = cu.end = 0;                        // (part 5: the rows come from the lane's StarRegion)
             *busy = star_region_next(g, cu, rg);
             return rs << 4;
@@ -569,10 +603,16 @@ GT_NOINLINE int star_certify_region(const StarGrid<Idx, GL>& g, StarLane& L, Sta
     }
     // the next box
     STAR_STAT(expand, 1);
+    if (GL == 2) {                                                   // a tile: the box must lie inside the staged cells
+        const int by = level < 23 ? (4 << level) : (1 << 26);
+        if (((g.open & 1) && win.c0 - by < 0) || ((g.open & 2) && win.c1 + by > g.gx - 1) || ((g.open & 4) && win.r0 - by < 0) || ((g.open & 8) && win.r1 + by > g.gy - 1)) {
+            L.err |= STAR_DEFER; *busy = false; return 1 | (rs << 4);
+        }
+    }
     rg.lim = star_win_grow(g, win, level < 23 ? (4 << level) : (1 << 26));
     rg.row = rg.lim.r0; rg.row_end = rg.lim.r1;
     if (rg.disc) {
-        const int d0 = star_cell(rg.cy - rg.R, g.y0, g.sy, g.gy), d1 = star_cell(rg.cy + rg.R, g.y0, g.sy, g.gy);
+        const int d0 = star_row(g, rg.cy - rg.R), d1 = star_row(g, rg.cy + rg.R);
         rg.row = rg.row > d0 ? rg.row : d0; rg.row_end = rg.row_end < d1 ? rg.row_end : d1;
     }
     rs = (rs & ~0xff) | (level + 1);
@@ -581,7 +621,7 @@ GT_NOINLINE int star_certify_region(const StarGrid<Idx, GL>& g, StarLane& L, Sta
     return rs << 4;
 }
 // Returns the answer (0 / 1 / 2) | the step's new progress << 4.
-template <class Idx, bool GL>
+template <class Idx, int GL>
 GT_NOINLINE int star_certify(const StarGrid<Idx, GL>& g, StarLane& L, StarCursor& cu, StarRegion& rg, int rs, bool* busy) {
     const StarWin win = L.win;
     const uint32_t ym = L.ym;
@@ -618,7 +658,7 @@ GT_NOINLINE int star_certify(const StarGrid<Idx, GL>& g, StarLane& L, StarCursor
 // open (ip is a hull vertex; FULL only). `w0` = half-width of the first window in cells. Returns STAR_* bits (0: certified).
 // `lst` = the lane's two lists of positions in shared memory: its candidates (cput / cget, CCAP entries) and the left
 // candidates of the current step (put / get, LCAP entries).
-template <int LCAP, int CCAP, bool FULL, class Idx, bool GL, class List, class Emit>
+template <int LCAP, int CCAP, bool FULL, class Idx, int GL, class List, class Emit>
 GT_INLINE int star_point(const StarGrid<Idx, GL>& g, int ip, bool active, int w0, List lst, bool* hull, Emit&& emit) {
     *hull = false;
     if (g.n < 3) { *hull = active; return 0; }                // (uniform: n is the frame's)

@@ -1,0 +1,6 @@
+# large frame through staged tiles: GPU tests of the large path, then timing with and without the tiles
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_large.py -x -q -m gpu 2>&1 | tail -8 | tee gpurun_out/pytest_large.log
+GTA_B200_TRACE=1 timeout 300 python scratch/large_star.py 100000 1000000 4000000 2>&1 | grep -v "chunk cycles" | tee gpurun_out/large_tiles.log
+GTA_B200_LARGE_TILES=0 GTA_B200_TRACE=1 timeout 300 python scratch/large_star.py 1000000 2>&1 | grep -v "chunk cycles" | tee -a gpurun_out/large_tiles.log

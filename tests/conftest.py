@@ -70,6 +70,7 @@ def emu():
     L.emu_triangulate_lpf2.argtypes = [dp, C.c_int, C.c_int, C.c_uint, ip, C.POINTER(C.c_long)]
     L.emu_exact_stats.argtypes = [C.POINTER(C.c_long)]
     L.emu_star.argtypes = [dp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, ip, C.POINTER(C.c_long)]
+    L.emu_star_tiles.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_double, ip, C.POINTER(C.c_long)]
     for n in ("emu_orient2d_signs", "emu_incircle_signs", "emu_orient2d_exact", "emu_incircle_exact"):
         getattr(L, n).argtypes = [dp, C.c_int, ip]
 
@@ -97,6 +98,16 @@ def emu():
             out = np.empty(3 * 2 * max(len(p), 1), dtype=np.int32)
             st = (C.c_long * 17)()
             nt = L.emu_star(p.ctypes.data_as(dp), len(p), int(w0), float(dens), 1 if full else 0, int(ccap), out.ctypes.data_as(ip), st)
+            if nt < 0:
+                return None, -nt, list(st)
+            return out[:3 * nt].reshape(-1, 3).copy(), 0, list(st)
+
+        def star_tiles(self, p, tw=32, halo=6, dens=1.0):
+            """The star path over staged tiles of the grid (ls_tile_kernel's logic): (triangles or None, status, [deferred, tiles, hull])."""
+            p = np.ascontiguousarray(p, dtype=np.float64)
+            out = np.empty(3 * 2 * max(len(p), 1), dtype=np.int32)
+            st = (C.c_long * 4)()
+            nt = L.emu_star_tiles(p.ctypes.data_as(dp), len(p), int(tw), int(halo), float(dens), out.ctypes.data_as(ip), st)
             if nt < 0:
                 return None, -nt, list(st)
             return out[:3 * nt].reshape(-1, 3).copy(), 0, list(st)

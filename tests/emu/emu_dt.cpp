@@ -213,6 +213,7 @@ int emu_star(const double* points, int n, int w0, double dens, int full, int cca
     g.ptf = ptf.data(); g.kf = (float)(2.5 * 5.9604644775390625e-08 * M) * 1.0001f;
     g.pt = pt.data(); g.cstart = cstart.data(); g.n = n; g.gx = d.gx; g.gy = d.gy;
     g.x0 = xmin; g.y0 = ymin; g.sx = d.sx; g.sy = d.sy; g.xmin = xmin; g.xmax = xmax; g.ymin = ymin; g.ymax = ymax;
+    g.cx0 = g.cy0 = 0; g.ggx = d.gx; g.ggy = d.gy; g.open = 0; g.rowx = nullptr;
     int nt = 0, st = 0, nh = 0;
     for (int ip = 0; ip < n; ++ip) {
         bool hull = false;
@@ -256,6 +257,97 @@ int emu_star(const double* points, int n, int w0, double dens, int full, int cca
         }
         if (corners < 4) return nt;
     }
+    if (nt != 2 * (n - 1) - nh) return -64;
+    return nt;
+}
+
+// The star path over TILES of the grid, the way ls_tile_kernel (gta_large_star.cuh) drives it: every tile of tw x tw cells is
+// staged with a halo of `halo` cells (StarGrid GL = 2), its own points build their whole stars from the staged cells, and a
+// point whose search would leave the staged cells on an open side is deferred and done over the whole grid afterwards.
+// Returns ntri (or -(STAR_* bits), -64 count rule); stats_out[0] = deferred points, [1] = tiles.
+int emu_star_tiles(const double* points, int n, int tw, int halo, double dens, int* tri_out, long* stats_out) {
+    using namespace gt;
+    if (n < 3) return -1000;
+    memset(&g_star, 0, sizeof g_star);
+    double xmin = points[0], xmax = points[0], ymin = points[1], ymax = points[1];
+    for (int i = 1; i < n; ++i) {
+        xmin = std::min(xmin, points[2 * i]); xmax = std::max(xmax, points[2 * i]);
+        ymin = std::min(ymin, points[2 * i + 1]); ymax = std::max(ymax, points[2 * i + 1]);
+    }
+    const StarDims d = star_dims(n, xmin, xmax, ymin, ymax, std::max(n, 1), dens);
+    const int nc = d.gx * d.gy, gx = d.gx, gy = d.gy;
+    std::vector<int> cell(n), cstart(nc + 1, 0), id(n);
+    for (int i = 0; i < n; ++i) {
+        cell[i] = star_cell(points[2 * i + 1], ymin, d.sy, d.gy) * d.gx + star_cell(points[2 * i], xmin, d.sx, d.gx);
+        cstart[cell[i] + 1]++;
+    }
+    for (int c = 0; c < nc; ++c) cstart[c + 1] += cstart[c];
+    std::vector<int> cur(cstart.begin(), cstart.end() - 1);
+    std::vector<SPt> pt(n);
+    for (int i = 0; i < n; ++i) { const int pos = cur[cell[i]]++; pt[pos].x = points[2 * i]; pt[pos].y = points[2 * i + 1]; id[pos] = i; }
+    std::vector<SPtF> ptf(n);
+    double M = 0.0;
+    for (int i = 0; i < n; ++i) { ptf[i].x = (float)pt[i].x; ptf[i].y = (float)pt[i].y; M = std::max(M, std::max(fabs(pt[i].x), fabs(pt[i].y))); }
+    const float kf = (float)(2.5 * 5.9604644775390625e-08 * M) * 1.0001f;
+    int nt = 0, st = 0, nh = 0;
+    int lv[8], lc[64];
+    struct { int *v, *c; void put(int k, int pos) { v[k] = pos; } int get(int k) const { return v[k]; }
+             void cput(int k, int pos) { c[k] = pos; } int cget(int k) const { return c[k]; } } lst;
+    lst.v = lv; lst.c = lc;
+    std::vector<int> deferred;
+    long ntiles = 0;
+    for (int ty = 0; ty * tw < gy; ++ty) for (int tx = 0; tx * tw < gx; ++tx) {
+        ++ntiles;
+        const int cc0 = tx * tw, cc1 = std::min(gx, cc0 + tw) - 1, cr0 = ty * tw, cr1 = std::min(gy, cr0 + tw) - 1;
+        const int C0 = std::max(0, cc0 - halo), C1 = std::min(gx - 1, cc1 + halo), R0 = std::max(0, cr0 - halo), R1 = std::min(gy - 1, cr1 + halo);
+        const int W = C1 - C0 + 1, Hh = R1 - R0 + 1;
+        std::vector<int> rowg0(Hh), rowbase(Hh + 1, 0), lcs(W * Hh + 1);
+        for (int r = 0; r < Hh; ++r) { rowg0[r] = cstart[(R0 + r) * gx + C0]; rowbase[r + 1] = rowbase[r] + cstart[(R0 + r) * gx + C1 + 1] - rowg0[r]; }
+        const int nloc = rowbase[Hh];
+        for (int r = 0; r < Hh; ++r) for (int c = 0; c < W; ++c) lcs[r * W + c] = cstart[(R0 + r) * gx + C0 + c] - rowg0[r] + rowbase[r];
+        lcs[W * Hh] = nloc;
+        std::vector<SPt> lpt(std::max(nloc, 1)); std::vector<SPtF> lptf(std::max(nloc, 1));
+        for (int r = 0; r < Hh; ++r) for (int j = 0; j < rowbase[r + 1] - rowbase[r]; ++j) { lpt[rowbase[r] + j] = pt[rowg0[r] + j]; lptf[rowbase[r] + j] = ptf[rowg0[r] + j]; }
+        StarGrid<int, 2> g;
+        g.pt = lpt.data(); g.ptf = lptf.data(); g.cstart = lcs.data(); g.kf = kf; g.n = nloc; g.gx = W; g.gy = Hh;
+        g.x0 = xmin; g.y0 = ymin; g.sx = d.sx; g.sy = d.sy; g.xmin = xmin; g.xmax = xmax; g.ymin = ymin; g.ymax = ymax;
+        g.cx0 = C0; g.cy0 = R0; g.ggx = gx; g.ggy = gy;
+        g.open = (C0 > 0 ? 1 : 0) | (C1 < gx - 1 ? 2 : 0) | (R0 > 0 ? 4 : 0) | (R1 < gy - 1 ? 8 : 0);
+        auto gpos = [&](int lp) { const int r = star_row(g, lpt[lp].y); return rowg0[r] + lp - rowbase[r]; };
+        for (int r = cr0 - R0; r <= cr1 - R0; ++r) for (int lp = lcs[r * W + (cc0 - C0)]; lp < lcs[r * W + (cc1 - C0) + 1]; ++lp) {
+            const int gip = gpos(lp);
+            if (nloc < 3) { deferred.push_back(gip); continue; }
+            bool hull = false;
+            const int nt0 = nt;
+            const int s1 = star_point<8, 12, true>(g, lp, true, 2, lst, &hull, [&](int n1, int n2) {
+                tri_out[3 * nt] = id[gip]; tri_out[3 * nt + 1] = id[gpos(n1)]; tri_out[3 * nt + 2] = id[gpos(n2)];
+                ++nt;
+            });
+            if (s1 & STAR_DEFER) { nt = nt0; deferred.push_back(gip); }
+            else { st |= s1; nh += hull; }
+        }
+    }
+    StarGrid<int, 1> g;                                       // (GL = 1, as on the device: the region walk that queues four rows)
+    g.ptf = ptf.data(); g.kf = kf; g.pt = pt.data(); g.cstart = cstart.data(); g.n = n; g.gx = gx; g.gy = gy;
+    g.x0 = xmin; g.y0 = ymin; g.sx = d.sx; g.sy = d.sy; g.xmin = xmin; g.xmax = xmax; g.ymin = ymin; g.ymax = ymax;
+    g.cx0 = g.cy0 = 0; g.ggx = gx; g.ggy = gy; g.open = 0;
+    std::vector<double> rowx(2 * (size_t)gy);
+    for (int r = 0; r < gy; ++r) {
+        double lo = INFINITY, hi = -INFINITY;
+        for (int i = cstart[r * gx]; i < cstart[(r + 1) * gx]; ++i) { lo = std::min(lo, pt[i].x); hi = std::max(hi, pt[i].x); }
+        rowx[2 * r] = lo; rowx[2 * r + 1] = hi;
+    }
+    g.rowx = rowx.data();
+    for (int ip : deferred) {
+        bool hull = false;
+        st |= star_point<8, 12, true>(g, ip, true, 2, lst, &hull, [&](int n1, int n2) {
+            tri_out[3 * nt] = id[ip]; tri_out[3 * nt + 1] = id[n1]; tri_out[3 * nt + 2] = id[n2];
+            ++nt;
+        });
+        nh += hull;
+    }
+    if (stats_out) { stats_out[0] = (long)deferred.size(); stats_out[1] = ntiles; stats_out[2] = nh; }
+    if (st) return -st;
     if (nt != 2 * (n - 1) - nh) return -64;
     return nt;
 }

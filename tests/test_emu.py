@@ -226,3 +226,26 @@ def test_star_path_scales_offsets_and_near_ties(emu, checker):
                 assert np.array_equal(_canon(tri), _canon(want)), (jit, off)
     tri, st, _ = emu.star(lat * 0.1 + 7.0)
     assert tri is None and st & 1
+
+
+def test_star_tiles_defer_what_they_cannot_see(emu, checker):
+    """Tiles of the grid with a halo (StarGrid GL = 2, the large frame's shared-memory kernel): a tile's own points build their
+    stars from the staged cells and DEFER whenever a search would leave them on an open side; tiles + deferred points together
+    must give exactly the reference's triangles, for any tile size and halo (small ones defer nearly everything along their
+    borders), on uniform, clustered and anisotropic sets."""
+    rng = np.random.default_rng(21)
+    sets = [rng.random((n, 2)) * np.array([4.0, 3.0]) for n in (50, 700, 3000)]
+    sets.append(np.concatenate([rng.normal(0, 0.02, (400, 2)), rng.normal(3, 1.0, (400, 2)), rng.random((60, 2)) * 20]))
+    sets.append(rng.random((1500, 2)) * np.array([30.0, 1.0]))
+    deferred = tiles = 0
+    for p in sets:
+        want, _ = checker.triangulate(p)
+        for tw, halo, dens in ((32, 6, 1.0), (8, 6, 1.0), (4, 2, 1.0), (5, 3, 0.5), (16, 4, 2.0), (3, 0, 1.0)):
+            tri, st, cnt = emu.star_tiles(p, tw, halo, dens)
+            assert st == 0 and np.array_equal(_canon(tri), _canon(want)), (len(p), tw, halo, dens, st)
+            deferred += cnt[0]; tiles += cnt[1]
+    assert deferred > 0 and tiles > len(sets) * 6                        # (both ways were taken)
+    # a lattice is refused whichever way its points are done
+    gx, gy = np.meshgrid(np.arange(20.0), np.arange(17.0))
+    tri, st, _ = emu.star_tiles(np.stack([gx.ravel(), gy.ravel()], 1), 6, 3)
+    assert tri is None and st & 1
