@@ -80,7 +80,7 @@ template <class Idx, int GL> GT_INLINE int star_cstart(const StarGrid<Idx, GL>& 
 
 // work counters of the emulation build
 #if defined(GT_STATS) && !defined(__CUDA_ARCH__)
-struct StarStats { long cand, left, icc, exact, expand, steps, points, hullcert, gridcand, rows; };
+struct StarStats { long cand, left, icc, exact, expand, steps, points, hullcert, gridcand, rows, screened; };
 extern StarStats g_star;
 #define STAR_STAT(x, v) (g_star.x += (v))
 #else
@@ -180,7 +180,7 @@ GT_INLINE bool star_region_cols(const StarGrid<Idx, GL>& g, const StarRegion& rg
         // region and no point of it. The row's own extent in x says so before the disc's square root, the cell map and the
         // two loads of cell starts a whole grid row apart are paid.
         xa = fmax(xa, g.rowx[2 * (size_t)row]); xb = fmin(xb, g.rowx[2 * (size_t)row + 1]);
-        if (!(xa <= xb)) return false;
+        if (!(xa <= xb)) { STAR_STAT(screened, 1); return false; }
     }
     if (rg.disc) {
         const double cy = rg.cy, R = rg.R;

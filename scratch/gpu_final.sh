@@ -1,7 +1,9 @@
 #!/bin/bash
-# final single-GPU round: bench (both arms), other configs, launch list, full capture of the star kernel
+# final single-GPU round: all GPU tests, bench (both arms), other configs, launch list, full capture of the star kernel
 set -x
 mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -5 | tee gpurun_out/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2 | tee -a gpurun_out/pytest_gpu.log
 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 python scratch/measure_configs.py > gpurun_out/other_configs.json 2> gpurun_out/other_configs.err; tail -2 gpurun_out/other_configs.err

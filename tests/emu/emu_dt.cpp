@@ -337,7 +337,8 @@ int emu_star_tiles(const double* points, int n, int tw, int halo, double dens, i
         for (int i = cstart[r * gx]; i < cstart[(r + 1) * gx]; ++i) { lo = std::min(lo, pt[i].x); hi = std::max(hi, pt[i].x); }
         rowx[2 * r] = lo; rowx[2 * r + 1] = hi;
     }
-    g.rowx = rowx.data();
+    g.rowx = getenv("STAR_NOROWX") ? nullptr : rowx.data();
+    const long rows_t = g_star.rows, gc_t = g_star.gridcand, ex_t = g_star.expand, exact_t = g_star.exact, icc_t = g_star.icc;
     for (int ip : deferred) {
         bool hull = false;
         st |= star_point<8, 12, true>(g, ip, true, 2, lst, &hull, [&](int n1, int n2) {
@@ -346,7 +347,8 @@ int emu_star_tiles(const double* points, int n, int tw, int halo, double dens, i
         });
         nh += hull;
     }
-    if (stats_out) { stats_out[0] = (long)deferred.size(); stats_out[1] = ntiles; stats_out[2] = nh; }
+    if (stats_out) { stats_out[0] = (long)deferred.size(); stats_out[1] = ntiles; stats_out[2] = nh; stats_out[3] = g_star.rows; }
+    if (getenv("STAR_DEBUG")) fprintf(stderr, "deferred pass: rows %ld, rejected by the row extents %ld, grid candidates %ld, scans %ld, exact %ld, icc %ld\n", g_star.rows - rows_t, g_star.screened, g_star.gridcand - gc_t, g_star.expand - ex_t, g_star.exact - exact_t, g_star.icc - icc_t);
     if (st) return -st;
     if (nt != 2 * (n - 1) - nh) return -64;
     return nt;
