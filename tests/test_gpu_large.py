@@ -88,6 +88,29 @@ def test_large_star_engine_vs_oracle(gta, checker, star_path):
     assert st == 0 and L.gta_b200_large_last_engine() == 0 and np.array_equal(tri, want)
 
 
+def test_large_star_tiles_clusters_strips_and_box_hulls(gta, checker, star_path):
+    """The tiles of the large frame's grid (ls_tile_kernel) on what they handle least gracefully: clusters that overflow a
+    tile's arrays or leave tiles nearly empty (whole tiles deferred), long thin strips (tiles cut by the grid's sides, hull
+    everywhere), and a hull that is the bounding box with points along it (what -corr makes of a frame). Tiles and deferred
+    points together must give the reference's triangle set."""
+    L = gta.lib()
+    rng = np.random.default_rng(17)
+    sets = [
+        np.concatenate([rng.normal(0, 0.01, (8000, 2)), rng.normal(40, 3.0, (30000, 2)), rng.random((2000, 2)) * 100]),
+        rng.random((50000, 2)) * np.array([2000.0, 3.0]),
+        rng.random((50000, 2)) * np.array([2.0, 900.0]),
+    ]
+    q = rng.random((90000, 2)) * np.array([30.0, 30.0])
+    t = np.linspace(0.0, 30.0, 301)
+    sets.append(np.concatenate([q[(q > 0).all(1) & (q < 30).all(1)], np.stack([t, 0 * t], 1), np.stack([t, 0 * t + 30.0], 1),
+                                np.stack([0 * t[1:-1], t[1:-1]], 1), np.stack([0 * t[1:-1] + 30.0, t[1:-1]], 1)]))
+    for k, p in enumerate(sets):
+        tri, st, _ = gta.triangulate_large(p)
+        assert st == 0 and L.gta_b200_large_last_engine() == 1, (k, st)
+        want, _ = checker.triangulate(p)
+        assert np.array_equal(synth.canonical_triangles(tri), synth.canonical_triangles(want)), k
+
+
 def test_cfg4_star_engine(gta, checker, star_path):
     """cfg 4 through the stars: 10^6 points, the reference's triangle set bit-exact after canonical sorting (north_star)."""
     p = synth.uniform_patch(1_000_000, seed=4)
