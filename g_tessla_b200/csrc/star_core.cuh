@@ -87,6 +87,30 @@ extern StarStats g_star;
 #define STAR_STAT(x, v) ((void)0)
 #endif
 
+// On the device the 32 lanes of a warp build 32 stars in LOCKSTEP: every loop below runs until no lane of the warp has
+// work left in it (a vote), so that the lanes meet again after every candidate, every scan and every walk step instead of
+// drifting apart through the nest of data-dependent loops (the first version, written as plain nested loops, ran at 4.4
+// active lanes of 32). All 32 lanes must call star_point together; lanes without a point pass active = false.
+#if defined(__CUDA_ARCH__)
+#define STAR_ANY(x) (__any_sync(0xffffffffu, (x)) != 0)
+#define STAR_BALLOT(x) __ballot_sync(0xffffffffu, (x))
+#define STAR_FFS(m) (__ffs((int)(m)) - 1)
+#define STAR_LANES 32
+__device__ __forceinline__ int star_lane_id() { uint32_t v; asm("mov.u32 %0, %%laneid;" : "=r"(v)); return (int)v; }
+__device__ __forceinline__ int star_bcast(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double star_bcast(double v, int src) {
+    return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src), __shfl_sync(0xffffffffu, __double2loint(v), src));
+}
+#else
+#define STAR_ANY(x) (x)
+#define STAR_BALLOT(x) ((x) ? 1u : 0u)
+#define STAR_FFS(m) 0
+#define STAR_LANES 1
+inline int star_lane_id() { return 0; }
+inline int star_bcast(int v, int) { return v; }
+inline double star_bcast(double v, int) { return v; }
+#endif
+
 GT_INLINE int star_cell(double v, double o, double s, int g) {
     double t = (v - o) * s;
     const double hi = (double)(g - 1);
@@ -226,6 +250,56 @@ GT_INLINE bool star_region_next(const StarGrid<Idx, GL>& g, StarCursor& c, StarR
         if (c.pos < c.end) return true;
     }
 }
+// One large frame in global memory (GL = 1): the far searches -- a hull edge, the disc of a skinny triangle along the hull
+// -- walk thousands of rows that hold a cell or two of the region and nothing in it, and a row is a chain of ~40 dependent
+// FP64 operations and two loads a whole grid row apart: ~1,000 cycles for the one lane that walks. So the walk from one
+// non-empty row to the next is done by the WARP: the lanes take the region of the lane that needs a row (`leader`) and
+// look at 32 consecutive rows at once. The leader then stands on the first row that holds a candidate (and goes through it
+// with star_region_next, which finds it non-empty at once), or the region is exhausted.
+// All 32 lanes call this together; returns the row (all lanes) or -1.
+template <class Idx, int GL>
+GT_INLINE int star_region_find_row(const StarGrid<Idx, GL>& g, const StarRegion& mine, int leader) {
+    StarRegion R;
+    R.disc = star_bcast(mine.disc, leader); R.band = star_bcast(mine.band, leader);
+    R.px = star_bcast(mine.px, leader); R.py = star_bcast(mine.py, leader); R.A = star_bcast(mine.A, leader); R.B = star_bcast(mine.B, leader);
+    R.slope = star_bcast(mine.slope, leader); R.hrow = star_bcast(mine.hrow, leader);
+    R.cx = star_bcast(mine.cx, leader); R.cy = star_bcast(mine.cy, leader); R.R = star_bcast(mine.R, leader);
+    R.bw = star_bcast(mine.bw, leader); R.bx0 = star_bcast(mine.bx0, leader); R.bx1 = star_bcast(mine.bx1, leader);
+    R.row = star_bcast(mine.row, leader); R.row_end = star_bcast(mine.row_end, leader);
+    R.lim.c0 = star_bcast(mine.lim.c0, leader); R.lim.c1 = star_bcast(mine.lim.c1, leader); R.lim.r0 = star_bcast(mine.lim.r0, leader); R.lim.r1 = star_bcast(mine.lim.r1, leader);
+    R.skip.c0 = star_bcast(mine.skip.c0, leader); R.skip.c1 = star_bcast(mine.skip.c1, leader); R.skip.r0 = star_bcast(mine.skip.r0, leader); R.skip.r1 = star_bcast(mine.skip.r1, leader);
+    R.seg = 0; R.sb0 = 1; R.sb1 = 0;
+    const int lane = star_lane_id();
+    for (int row0 = R.row; row0 <= R.row_end; row0 += STAR_LANES) {
+        const int row = row0 + lane;
+        bool has = false;
+        int ca, cb;
+        if (row <= R.row_end && star_region_cols(g, R, row, &ca, &cb)) {
+            STAR_STAT(rows, 1);
+            const int base = row * g.gx;
+            int a1 = 1, b1 = 0;
+            if (row >= R.skip.r0 && row <= R.skip.r1) {               // cells scanned before are skipped (as in star_region_next)
+                a1 = ca > R.skip.c1 + 1 ? ca : R.skip.c1 + 1; b1 = cb;
+                cb = cb < R.skip.c0 - 1 ? cb : R.skip.c0 - 1;
+            }
+            if (ca <= cb) has = star_cstart(g, base + ca) < star_cstart(g, base + cb + 1);
+            if (!has && a1 <= b1) has = star_cstart(g, base + a1) < star_cstart(g, base + b1 + 1);
+        }
+        const uint32_t m = STAR_BALLOT(has);
+        if (m) return row0 + STAR_FFS(m);
+    }
+    return -1;
+}
+// the second run of the row the cursor has just finished (seg == 1), if it has one and it is not empty
+template <class Idx, int GL>
+GT_INLINE bool star_region_second(const StarGrid<Idx, GL>& g, StarCursor& c, StarRegion& rg) {
+    const int ca = rg.sb0, cb = rg.sb1;
+    rg.seg = 0; ++rg.row;
+    if (ca > cb) return false;
+    const int base = (rg.row - 1) * g.gx;
+    c.pos = star_cstart(g, base + ca); c.end = star_cstart(g, base + cb + 1);
+    return c.pos < c.end;
+}
 template <class Idx, int GL>
 GT_INLINE bool star_cur_row(const StarGrid<Idx, GL>& g, StarCursor& c) {
     while (c.rows > 0) {
@@ -285,16 +359,6 @@ GT_NOINLINE int star_incircle_exact(double ax, double ay, double bx, double by, 
     STAR_STAT(exact, 1);
     return incircle_sign<true>(ax, ay, bx, by, cx, cy, dx, dy);
 }
-
-// On the device the 32 lanes of a warp build 32 stars in LOCKSTEP: every loop below runs until no lane of the warp has
-// work left in it (a vote), so that the lanes meet again after every candidate, every scan and every walk step instead of
-// drifting apart through the nest of data-dependent loops (the first version, written as plain nested loops, ran at 4.4
-// active lanes of 32). All 32 lanes must call star_point together; lanes without a point pass active = false.
-#if defined(__CUDA_ARCH__)
-#define STAR_ANY(x) (__any_sync(0xffffffffu, (x)) != 0)
-#else
-#define STAR_ANY(x) (x)
-#endif
 
 // One lane's state. It lives in local memory between the passes of a step; every pass is its own out-of-line function
 // that loads what it needs into registers and writes back what it changed. (Written as one function, the compiler kept
@@ -464,8 +528,11 @@ GT_NOINLINE int star_pass1_grid(const StarGrid<Idx, GL>& g, List lst, StarLane& 
     const StarWin win = L.win;
     StarWin none; none.c0 = 1; none.c1 = 0; none.r0 = 1; none.r1 = 0;
     bool busy = *busy_io;
-    while (STAR_ANY(busy && cnt < LCAP)) {
-        if (busy && cnt < LCAP) {
+    // (GL = 1) a region that has just been set up, or whose cursor ran out while the left list was full: the lane is busy but
+    // stands on nothing -- it needs the next non-empty row, which the warp finds (star_region_find_row)
+    bool need_row = GL == 1 && busy && cu.part == 5 && cu.pos >= cu.end;
+    while (STAR_ANY(busy && (cnt < LCAP || need_row))) {
+        if (busy && cnt < LCAP && !need_row) {
             const int pos = cu.pos;
             const SPt S = star_pt(g, pos);
             const double sdx = S.x - px, sdy = star_flip(S.y - py, ym);
@@ -482,7 +549,22 @@ GT_NOINLINE int star_pass1_grid(const StarGrid<Idx, GL>& g, List lst, StarLane& 
             }
             STAR_STAT(cand, 1); STAR_STAT(gridcand, 1);
             if (left) { lst.put(cnt, pos); ++cnt; STAR_STAT(left, 1); }
-            if (++cu.pos >= cu.end) busy = cu.part == 5 ? star_region_next(g, cu, rg) : star_cur_next(g, cu, win, none);
+            if (++cu.pos >= cu.end) {
+                if (cu.part != 5) busy = star_cur_next(g, cu, win, none);
+                else if (GL != 1) busy = star_region_next(g, cu, rg);
+                else if (rg.seg == 0 || !star_region_second(g, cu, rg)) need_row = true;      // (the warp finds the next row, below)
+            }
+        }
+        if (GL == 1) {
+            for (uint32_t m = STAR_BALLOT(need_row); m != 0u; m = STAR_BALLOT(need_row)) {
+                const int leader = STAR_FFS(m);
+                const int row = star_region_find_row(g, rg, leader);
+                if (star_lane_id() == leader) {
+                    need_row = false;
+                    if (row < 0) { busy = false; rg.row = rg.row_end + 1; }
+                    else { rg.row = row; rg.seg = 0; busy = star_region_next(g, cu, rg); }
+                }
+            }
         }
     }
     *busy_io = busy;
@@ -584,7 +666,7 @@ GT_NOINLINE int star_certify_region(const StarGrid<Idx, GL>& g, StarLane& L, Sta
                 }
             }
             cu.part = 5; cu.pos = cu.end = 0;                        // (part 5: the rows come from the lane's StarRegion)
-            *busy = star_region_next(g, cu, rg);
+            *busy = GL == 1 ? true : star_region_next(g, cu, rg);    // (GL = 1: the warp finds the first row, star_pass1_grid)
             return rs << 4;
         }
     } else if (level == 0) {
@@ -617,7 +699,7 @@ GT_NOINLINE int star_certify_region(const StarGrid<Idx, GL>& g, StarLane& L, Sta
     }
     rs = (rs & ~0xff) | (level + 1);
     cu.part = 5; cu.pos = cu.end = 0;                        // (part 5: the rows come from the lane's StarRegion)
-    *busy = star_region_next(g, cu, rg);
+    *busy = GL == 1 ? true : star_region_next(g, cu, rg);    // (GL = 1: the warp finds the first row, star_pass1_grid)
     return rs << 4;
 }
 // Returns the answer (0 / 1 / 2) | the step's new progress << 4.
