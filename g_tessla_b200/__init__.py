@@ -6,5 +6,5 @@ Python binding used by tests/ and bench.py; it never imports oracle/ and has no 
 """
 from .api import (  # noqa: F401
     GTA_CORRECT, GTA_2D, PATH_AUTO, PATH_DC, PATH_STAR, Tessellator, lib, lib_path, tessellate, triangulate, triangulate_large, GtaError,
-    set_path, last_fallback_frames, stage_ms, star_counters, surface_area_large,
+    set_path, last_fallback_frames, stage_ms, star_counters, surface_area_large, tessellate_large,
 )

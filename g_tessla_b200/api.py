@@ -72,6 +72,7 @@ def lib() -> C.CDLL:
     L.gta_b200_tessellate_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_uint, C.c_int, C.c_int,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gta_b200_surface_area_large.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_int, _dp, _dp, _ip, _ip]
+    L.gta_b200_tessellate_large.argtypes = [C.c_void_p, C.c_int, _dp, C.c_double, C.c_uint, C.c_int, _dp, _dp, _dp, _ip, _ip, _ip]
     L.gta_b200_orient2d_signs.argtypes = [_dp, C.c_int, _ip, C.c_int]
     L.gta_b200_incircle_signs.argtypes = [_dp, C.c_int, _ip, C.c_int]
     _lib = L
@@ -168,6 +169,18 @@ def surface_area_large(xyz, flags=0, device=-1):
     a3, a2, nt, st = C.c_double(0.0), C.c_double(0.0), C.c_int(0), C.c_int(0)
     _check(lib().gta_b200_surface_area_large(_vp(p), len(p), int(flags), int(device), C.byref(a3), C.byref(a2), C.byref(nt), C.byref(st)))
     return dict(area=a3.value, area2d=a2.value, ntri=nt.value, status=st.value, device_ms=lib().gta_b200_large_last_ms(),
+                engine=lib().gta_b200_large_last_engine())
+
+
+def tessellate_large(xyz, box, espace, flags=0, device=-1):
+    """One large frame the way delaunay_tessellate treats a frame: -corr points generated on the device (flags & CORRECT),
+    then the large-frame path. xyz [n,3], box [3,3] or [9]. Returns dict(area, area2d, areabox, ntri, ncorr, status, engine)."""
+    p = np.ascontiguousarray(xyz, dtype=np.float64)
+    b = np.ascontiguousarray(box, dtype=np.float64).reshape(-1)
+    a3, a2, ab, nt, nc, st = C.c_double(0.0), C.c_double(0.0), C.c_double(0.0), C.c_int(0), C.c_int(0), C.c_int(0)
+    _check(lib().gta_b200_tessellate_large(_vp(p), len(p), b.ctypes.data_as(_dp), float(espace), int(flags), int(device),
+                                           C.byref(a3), C.byref(a2), C.byref(ab), C.byref(nt), C.byref(nc), C.byref(st)))
+    return dict(area=a3.value, area2d=a2.value, areabox=ab.value, ntri=nt.value, ncorr=nc.value, status=st.value,
                 engine=lib().gta_b200_large_last_engine())
 
 

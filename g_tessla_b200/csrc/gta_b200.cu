@@ -237,6 +237,23 @@ int lpf_ensure(int dev, int which, size_t frames, int cap, int cap_e, LpfCache**
 
 int launch(const gt::KParams& p, const Shape& s, cudaStream_t st);
 
+// K0 for ONE frame that is too large for the batched kernels (gta_large.cu): the same corr_points() (gta_corr.cuh,
+// reference src/gta_tri.c:112-272), one CTA of 1,024 threads reading the atoms from global memory -- the per-interval
+// extremes it keeps are a few KB of shared memory however many atoms there are. out[0] = points appended, out[1] = status bits.
+constexpr int LC_T = 1024;
+__global__ void __launch_bounds__(LC_T) large_corr_kernel(const double* xyz, int natoms, int cap, double bx, double by, double espace, double* corr3, int* out) {
+    extern __shared__ __align__(16) unsigned char csm[];
+    uint32_t* ctl = reinterpret_cast<uint32_t*>(csm);                          // [0] status
+    double* red = reinterpret_cast<double*>(csm + 16);                         // 6 * (T / 32) doubles
+    unsigned long long* ckey = reinterpret_cast<unsigned long long*>(csm + 16 + 8 * 6 * (LC_T / 32));
+    if (threadIdx.x == 0) ctl[0] = 0;
+    __syncthreads();
+    int ncorr = 0;
+    const int n = gt::corr_points<LC_T>(xyz, 3, natoms, cap, bx, by, espace, ckey, red, ctl, corr3, nullptr, 0, 0, &ncorr);
+    __syncthreads();
+    if (threadIdx.x == 0) { out[0] = n - natoms; out[1] = (int)ctl[0]; }
+}
+
 // The star kernel (gta_star.cuh): one CTA per frame, a thread per point. Frames it does not certify go to ws.fb_list.
 int launch_star(const gt::KParams& p, const Shape& s, int* fb_list, unsigned int* fb_count, unsigned long long* counters, cudaStream_t st) {
     gt::StarParams sp; sp.k = p; sp.fb_list = fb_list; sp.fb_count = fb_count; sp.counters = counters;
@@ -383,6 +400,23 @@ bool have_device() {
 }
 
 }  // namespace
+
+// d_xyz: device [natoms + ncorr][3], atoms in front; the appended points are written behind them. ncorr = 4 + 2 nx + 2 ny as
+// the caller computed it from the box (the kernel computes the same and must agree). *st = GTA_B200_ST_* bits (0: done).
+int gta_b200_large_corr(double* d_xyz, int natoms, int ncorr, double bx, double by, double espace, int* st) {
+    const size_t smem = 16 + 8 * 6 * (LC_T / 32) + 12 * (size_t)(ncorr + 4) + 16;
+    if (smem > (size_t)smem_limit()) { *st = GTA_B200_ST_CAPACITY; return GTA_B200_OK; }       // (a box of > ~4,000 intervals per side)
+    int* d_out = nullptr; int h[2] = {0, 0};
+    CK(cudaMalloc((void**)&d_out, 8));
+    cudaError_t e = cudaFuncSetAttribute(large_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) { large_corr_kernel<<<1, LC_T, smem>>>(d_xyz, natoms, natoms + ncorr, bx, by, espace, d_xyz + 3 * (size_t)natoms, d_out); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpy(h, d_out, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(GTA_B200_E_CUDA, std::string("large_corr_kernel: ") + cudaGetErrorString(e));
+    *st = h[1];
+    if (h[1] == 0 && h[0] != ncorr) return fail(GTA_B200_E_CUDA, "large_corr_kernel: point count differs from the host's");
+    return GTA_B200_OK;
+}
 
 extern "C" {
 

@@ -131,17 +131,17 @@ void delaunay_tessellate(rvec** x, matrix* box, real espace, int nthreads, struc
     const int maxp = gta_b200_max_points_for(&box[0][0][0], 9, F, N, espace, fl);
     int rc;
     if (maxp > gta_b200_max_points()) {
-        // frames too large for the batched shared-memory kernel (e.g. a whole system without -n): one frame at a time
-        // through the large-frame path, which has no correction-point stage
+        // frames too large for the batched shared-memory kernels (e.g. a whole system without -n): one frame at a time
+        // through the large-frame path (its own correction-point stage, the same corr_points as the batched kernels)
         rc = GTA_B200_OK;
         for (int fr = 0; fr < F && rc == GTA_B200_OK; ++fr) {
-            double a3 = 0.0, a2 = 0.0; int st = 0;
-            rc = gta_b200_surface_area_large(&x[fr][0][0], N, fl, -1, &a3, &a2, nullptr, &st);
+            double a3 = 0.0, a2 = 0.0, ab = 0.0; int st = 0;
+            rc = gta_b200_tessellate_large(&x[fr][0][0], N, &box[fr][0][0], espace, fl, -1, &a3, &a2, &ab, nullptr, nullptr, &st);
             if (rc != GTA_B200_OK) break;
             g_frame_status[fr] = st;
             areas->area[fr] = st ? kNaN : a3;
             if (areas->area2D) areas->area2D[fr] = st ? kNaN : a2;
-            areas->area2Dbox[fr] = box[fr][XX][XX] * box[fr][YY][YY];
+            areas->area2Dbox[fr] = ab;
         }
     } else if (flags & GTA_PRINT) {
         // one frame at a time (the reference also serialises -print, g_tessla.c:116); files are numbered from 1

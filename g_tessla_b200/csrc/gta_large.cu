@@ -19,6 +19,8 @@
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <cstdio>
+#include <limits>
+#include <cmath>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -332,7 +334,7 @@ static int large_run(const double* points, const double* xyz3, int npoints, int 
     LCK(cudaMalloc((void**)&d_pts, sizeof(double) * 2 * (size_t)n));
     if (xyz3) {
         LCK(cudaMalloc((void**)&d_xyz, sizeof(double) * 3 * (size_t)n));
-        LCK(cudaMemcpy(d_xyz, xyz3, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice));
+        LCK(cudaMemcpy(d_xyz, xyz3, sizeof(double) * 3 * (size_t)n, cudaMemcpyDefault));      // (host, or device: gta_b200_tessellate_large)
         large_xy<<<G, B>>>(d_xyz, n, d_pts);
     } else LCK(cudaMemcpy(d_pts, points, sizeof(double) * 2 * (size_t)n, cudaMemcpyHostToDevice));
     LCK(cudaEventRecord(ev0));
@@ -450,6 +452,42 @@ extern "C" int gta_b200_triangulate_large(const double* points, int npoints, int
 }
 // One large frame of atoms [n][3] without correction points: triangulation of (x, y) + summed 3-D (and, with GTA_B200_2D,
 // projected) triangle areas. Serves delaunay_surface_area / delaunay_tessellate for frames beyond gta_b200_max_points().
+int gta_b200_large_corr(double* d_xyz, int natoms, int ncorr, double bx, double by, double espace, int* st);   // gta_b200.cu
+// One large frame the way delaunay_tessellate treats every frame (reference src/gta_tri.c:106-296): with GTA_B200_CORRECT
+// the box-edge points are generated on the device (the batched kernels' corr_points, one CTA), appended, and the frame of
+// natoms + ncorr points goes through the large-frame path; without it this is gta_b200_surface_area_large.
+extern "C" int gta_b200_tessellate_large(const double* xyz, int natoms, const double* box9, double espace, unsigned flags, int device,
+                                         double* area3, double* area2, double* areabox, int* ntri, int* ncorr_out, int* status) {
+    if (!xyz || !box9 || natoms < 0) { g_lerr = "bad argument"; return GTA_B200_E_ARG; }
+    const double bx = box9[0], by = box9[4];
+    if (areabox) *areabox = bx * by;
+    if (ncorr_out) *ncorr_out = 0;
+    if (!(flags & GTA_B200_CORRECT)) return large_run(nullptr, xyz, natoms, device, nullptr, 0, ntri, status, flags, area3, area2);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); g_lerr = "no CUDA device: libgtessla_b200 has no CPU path"; return GTA_B200_E_NO_DEVICE; }
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { g_lerr = "cudaSetDevice failed"; return GTA_B200_E_CUDA; }
+    if (status) *status = 0;
+    if (ntri) *ntri = 0;
+    const double qn = std::numeric_limits<double>::quiet_NaN();
+    if (area3) *area3 = qn;
+    if (area2) *area2 = qn;
+    const int nx = (int)(bx / espace), ny = (int)(by / espace);               // gta_tri.c:112-113
+    if (!std::isfinite(bx) || !std::isfinite(by) || nx < 0 || ny < 0 || natoms < 1) { if (status) *status = natoms < 1 ? GTA_B200_ST_TOO_FEW_POINTS : GTA_B200_ST_NONFINITE; return GTA_B200_OK; }
+    if (nx > (1 << 20) || ny > (1 << 20) || (long long)natoms + 4 + 2ll * nx + 2ll * ny > (1 << 27)) { if (status) *status = GTA_B200_ST_CAPACITY; return GTA_B200_OK; }
+    const int ncorr = 4 + 2 * nx + 2 * ny, n = natoms + ncorr;
+    double* d_all = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d_all, sizeof(double) * 3 * (size_t)n);
+    if (e == cudaSuccess) e = cudaMemcpy(d_all, xyz, sizeof(double) * 3 * (size_t)natoms, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d_all); g_lerr = std::string("gta_b200_tessellate_large: ") + cudaGetErrorString(e); return GTA_B200_E_CUDA; }
+    int st = 0;
+    int rc = gta_b200_large_corr(d_all, natoms, ncorr, bx, by, espace, &st);
+    if (rc != GTA_B200_OK) { g_lerr = gta_b200_last_error(); cudaFree(d_all); return rc; }
+    if (st) { if (status) *status = st; cudaFree(d_all); return GTA_B200_OK; }          // (atoms outside the box, ...: the batched calls' statuses)
+    if (ncorr_out) *ncorr_out = ncorr;
+    rc = large_run(nullptr, d_all, n, -1, nullptr, 0, ntri, status, flags & ~(unsigned)GTA_B200_CORRECT, area3, area2);
+    cudaFree(d_all);
+    return rc;
+}
 extern "C" int gta_b200_surface_area_large(const double* xyz, int natoms, unsigned flags, int device, double* area3, double* area2, int* ntri, int* status) {
     if (flags & GTA_B200_CORRECT) { g_lerr = "the correction points (-corr) are generated by the batched kernel only: frame too large"; return GTA_B200_E_TOO_LARGE; }
     return large_run(nullptr, xyz, natoms, device, nullptr, 0, ntri, status, flags, area3, area2);

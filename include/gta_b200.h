@@ -134,9 +134,15 @@ int gta_b200_triangulate_large(const double *points, int npoints, int device,
                                int *tri, int tri_cap, int *ntri, int *status);
 /* Same path for one large frame of atoms xyz [natoms][3] WITHOUT correction points: also sums the 3-D triangle areas
  * (*area3) and, with GTA_B200_2D, the projected ones (*area2). delaunay_surface_area / delaunay_tessellate use it for
- * frames beyond gta_b200_max_points(). GTA_B200_CORRECT is refused (GTA_B200_E_TOO_LARGE). */
+ * frames beyond gta_b200_max_points(). GTA_B200_CORRECT is refused here (GTA_B200_E_TOO_LARGE): gta_b200_tessellate_large. */
 int gta_b200_surface_area_large(const double *xyz, int natoms, unsigned flags, int device,
                                 double *area3, double *area2, int *ntri, int *status);
+/* One large frame the way delaunay_tessellate treats a frame (reference src/gta_tri.c:106-296): with GTA_B200_CORRECT the
+ * box-edge points are generated on the device, appended (*ncorr of them) and the natoms + *ncorr points go through the
+ * large-frame path; box9 = the frame's 3 x 3 box (box9[0], box9[4] are used), *areabox = their product. A frame the
+ * batched calls would refuse (atoms outside the box with -corr, non-finite input) gets the same status bits and NaN areas. */
+int gta_b200_tessellate_large(const double *xyz, int natoms, const double *box9, double espace, unsigned flags, int device,
+                              double *area3, double *area2, double *areabox, int *ntri, int *ncorr, int *status);
 /* device milliseconds (sort + all levels + enumeration, without the host copies) of the last call on this thread */
 double gta_b200_large_last_ms(void);
 /* engine of the last large-frame call on this thread: 1 = star engine (csrc/gta_large_star.cuh: areas by default,

@@ -178,3 +178,36 @@ def test_print_flag_writes_showme_files(gta, checker, tmp_path):
     node = open(tmp_path / nodes[0]).read().splitlines()
     assert node[0] == "%d\t2\t0\t0" % len(p) and node[1] == "0\t%f\t%f" % (p[0, 0], p[0, 1])
     L.free_tri_area(C.byref(a))
+
+
+def test_large_frames_with_correction_points(gta, checker):
+    """Frames beyond the shared-memory kernels WITH -corr (a whole leaflet of 80 x 80 lipids: 6,400 atoms + 324 box-edge
+    points; reference src/gta_tri.c:106-296 handles any size): the correction points are generated on the device by the
+    batched kernels' own corr_points, and the frame goes through the large-frame path. gta_b200_tessellate_large and the
+    kept delaunay_tessellate against the reference: areas within 1e-12, box area and point count equal; an atom outside the
+    box is refused with the batched calls' status, not reproduced."""
+    L = gta.lib()
+    xyz, box = synth.jittered_bilayer(3, 80, seed=12)
+    F, N = xyz.shape[:2]
+    assert N + 4 + 4 * int(box[:, :2].max() / 0.8 + 1) > L.gta_b200_max_points()
+    want = checker.tessellate(xyz, box, 0.8, 3, want_corr=True)
+    box9 = np.zeros((F, 3, 3)); box9[:, 0, 0] = box[:, 0]; box9[:, 1, 1] = box[:, 1]; box9[:, 2, 2] = box[:, 2]
+    for f in range(F):
+        r = gta.tessellate_large(xyz[f], box9[f], 0.8, flags=3)
+        assert r["status"] == 0 and r["ncorr"] == int(want["ncorr"][f]) and r["areabox"] == want["areabox"][f], (f, r)
+        assert r["ntri"] == 2 * (N + r["ncorr"] - 1) - (r["ncorr"])          # the hull is the box: every -corr point is on it
+        assert abs(r["area"] - want["area"][f]) <= 1e-12 * want["area"][f]
+        assert abs(r["area2d"] - want["area2d"][f]) <= 1e-12 * want["area2d"][f]
+    frames = [np.ascontiguousarray(xyz[f]) for f in range(F)]
+    xptr = (dp * F)(*[fr.ctypes.data_as(dp) for fr in frames])
+    a = TriArea(None, None, None, N, F)
+    L.delaunay_tessellate.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.POINTER(TriArea), C.c_ubyte]
+    L.delaunay_tessellate(xptr, box9.ctypes.data, 0.8, 0, C.byref(a), 3)
+    area = np.ctypeslib.as_array(a.area, shape=(F,)); a2 = np.ctypeslib.as_array(a.area2D, shape=(F,)); ab = np.ctypeslib.as_array(a.area2Dbox, shape=(F,))
+    assert np.allclose(area, want["area"], rtol=1e-12, atol=0) and np.allclose(a2, want["area2d"], rtol=1e-12, atol=0)
+    assert np.array_equal(ab, want["areabox"])
+    L.free_tri_area(C.byref(a))
+    bad = xyz[0].copy(); bad[17, 0] = box[0, 0] * 1.5
+    r = gta.tessellate_large(bad, box9[0], 0.8, flags=1)
+    assert r["status"] & 16                                              # GTA_B200_ST_OUT_OF_BOX
+    assert np.isnan(r["area"])
