@@ -13,4 +13,5 @@ python profiles/summarize_launches.py gpurun_out/launches.csv | tee gpurun_out/l
 ncu --set full --clock-control none --import-source on -k regex:star_kernel -s 1 -c 1 -o gpurun_out/star_full -f python scratch/star_time.py 16000 3 > gpurun_out/ncu_full.log 2>&1
 python scratch/large_once.py > gpurun_out/large_once.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_large.csv env GTA_B200_PATH=2 python scratch/large_star.py 1000000 > gpurun_out/ncu_large.log 2>&1
 python profiles/summarize_launches.py gpurun_out/launches_large.csv | tee gpurun_out/launches_large_summary.txt
+python scratch/large_corr.py 1000 2>&1 | tee gpurun_out/large_corr.log
 ls -la gpurun_out | head -40

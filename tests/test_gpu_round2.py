@@ -178,8 +178,8 @@ class TriArea(C.Structure):
 
 def test_large_frames_behind_kept_entry_points(gta, checker):
     """Frames beyond the shared-memory kernel (a whole system without -n) go through the large-frame path instead of
-    coming back as zeros: delaunay_surface_area and delaunay_tessellate without -corr; with -corr (whose point generation
-    lives in the batched kernel) the call fails loudly: NaN areas, INTERNAL status, nonzero gta_last_call_rc()."""
+    coming back as zeros: delaunay_surface_area, and delaunay_tessellate without and with -corr (gta_b200_tessellate_large
+    generates the box-edge points of such a frame), all against the reference."""
     L = gta.lib()
     n = L.gta_b200_max_points() + 1500
     rng = np.random.default_rng(9)
@@ -202,9 +202,10 @@ def test_large_frames_behind_kept_entry_points(gta, checker):
     assert np.array_equal(np.ctypeslib.as_array(a.area2Dbox, shape=(2,)), np.array([1600.0, 1600.0]))
     L.free_tri_area(C.byref(a))
     b = TriArea(None, None, None, n, 2)
-    L.delaunay_tessellate(xptr, box.ctypes.data, 0.8, 0, C.byref(b), 1)             # -corr on a frame this large: refused, loudly
-    assert L.gta_last_call_rc() != 0
-    assert np.isnan(np.ctypeslib.as_array(b.area, shape=(2,))).all()
+    L.delaunay_tessellate(xptr, box.ctypes.data, 0.8, 0, C.byref(b), 1)             # -corr on a frame this large: its own point stage
+    assert L.gta_last_call_rc() == 0
+    wc = checker.tessellate(xyz, np.full((2, 3), 40.0), 0.8, 1)
+    assert np.allclose(np.ctypeslib.as_array(b.area, shape=(2,)), wc["area"], rtol=RTOL, atol=0)
     L.free_tri_area(C.byref(b))
 
 
