@@ -198,6 +198,13 @@ static int large_star(const double* d_pts, const double* d_xyz, int n, unsigned 
         if (want_tri) { SCK(ls_alloc((void**)&d_pairs, 8 * (size_t)LS_MAXOWN * n)); SCK(ls_alloc((void**)&d_ovf, 12 * (size_t)ovf_cap)); }
         // cells, stable sort by cell (order inside a cell = input order), cell starts
         ls_cells<<<G, B>>>(d_pts, n, xmin, ymin, dm.sx, dm.sy, dm.gx, dm.gy, d_cell, d_idx, d_cstart + 1);
+        {
+            // strongly clustered input (a quarter of the points in cells of more than 24): not for the grid
+            uint32_t dense = 0;
+            ls_dense<<<(ncell + 255) / 256, 256>>>(d_cstart + 1, ncell, 24u, d_ctl + 6);
+            SCK(cudaMemcpy(&dense, d_ctl + 6, 4, cudaMemcpyDeviceToHost));
+            if ((long long)dense * 4 > (long long)n) { rc = 1; goto out; }
+        }
         int bits = 1; while ((1ll << bits) < ncell && bits < 32) ++bits;
         cub::DeviceRadixSort::SortPairs(nullptr, tb, d_cell, d_cell2, d_idx, d_idx2, n, 0, bits);
         cub::DeviceScan::InclusiveSum(nullptr, tb2, d_cstart + 1, d_cstart + 1, ncell);

@@ -67,6 +67,17 @@ __global__ void ls_gather(const double* pts, const double* xyz, const uint32_t* 
     if (sz) sz[i] = xyz ? xyz[3 * (size_t)o + 2] : 0.0;
 }
 
+// How many points sit in cells of more than `limit` points? The grid has one point per cell on average; where a cell holds
+// dozens, a point's 5 x 5 window overflows the lane's candidate list and its scans cost the square of the density. Strongly
+// clustered input is the level-by-level path's (whose cost does not depend on the density): the caller decides on *dense.
+__global__ void ls_dense(const uint32_t* count, int ncell, uint32_t limit, uint32_t* dense) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t v = c < ncell ? count[c] : 0u;
+    v = v > limit ? v : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(dense, v);
+}
 // smallest and largest x of every grid row's points (star_core.cuh: StarGrid::rowx); a row is one run of the cell-sorted array
 __global__ void ls_rowx(const SPt* spt, const uint32_t* cstart, int gx, int gy, double* rowx) {
     const int r = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;

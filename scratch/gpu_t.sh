@@ -1,3 +1,3 @@
 set -x
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -5 | tee gpurun_out/pytest_gpu.log
+timeout 900 python -m pytest tests/test_gpu_large.py tests/test_gpu_kept_api.py tests/test_gpu_round2.py -x -q -m gpu 2>&1 | tail -3 | tee gpurun_out/pytest_large.log
