@@ -374,6 +374,15 @@ def run_native(args):
                               "ncu_capture_of_the_kernel": ncu_extra},
             "clocks": clk,
         }
+        if ncu_extra and ncu_extra.get("warp_instructions_per_frame") and clk and clk.get("sm_mhz"):
+            # what does bound the kernel: warp instructions issued, against one per cycle per SM sub-partition (4 per SM).
+            # Instructions per frame from the committed ncu capture of the same sources, rate and clock from this run.
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            issue_peak = sms * 4 * clk["sm_mhz"] * 1e6
+            issue_ach = ncu_extra["warp_instructions_per_frame"] * frames_per_launch / (dom_ms / 1e3)
+            line["roofline_issue"] = {"achieved": issue_ach / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-instructions/s", "frac": issue_ach / issue_peak,
+                                      "active_lanes_per_instruction": ncu_extra.get("active_lanes_per_instruction"),
+                                      "note": "the kernel's own bound (DESIGN.md section 5): issue slots x lanes; instructions per frame from the ncu capture, stale with it"}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(xyz_h.numpy(), box_h.numpy(), area_dev, args)
             if kept and line["cpu_baseline"].get("value"):
