@@ -211,3 +211,19 @@ def test_large_frames_with_correction_points(gta, checker):
     r = gta.tessellate_large(bad, box9[0], 0.8, flags=1)
     assert r["status"] & 16                                              # GTA_B200_ST_OUT_OF_BOX
     assert np.isnan(r["area"])
+
+
+def test_cli_whole_system_frames_with_corr(gta, checker, tmp_path):
+    """The command line on a trajectory whose frames are beyond the shared-memory kernels (no index group: 4,900 atoms per
+    frame), with -corr -2d: tessellate_area -> delaunay_tessellate -> gta_b200_tessellate_large per frame; the .dat must be
+    the file the reference's numbers give."""
+    exe = os.path.join(ROOT, "g_tessla_b200", "g_tessla")
+    xyz, box = synth.jittered_bilayer(2, 70, seed=21)
+    xyz = np.round(xyz, 3); box = np.round(box, 5)
+    xyz[:, :, 0] = np.clip(xyz[:, :, 0], 0.001, box[:, None, 0] - 0.001); xyz[:, :, 1] = np.clip(xyz[:, :, 1], 0.001, box[:, None, 1] - 0.001)
+    assert xyz.shape[1] + 4 + 4 * int(box[:, :2].max() / 0.8 + 1) > gta.lib().gta_b200_max_points()
+    _write_gro(tmp_path / "traj.gro", xyz, box)
+    r = subprocess.run([exe, "-f", "traj.gro", "-o", "out.dat", "-espace", "0.8", "-corr", "-2d"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr + r.stdout
+    want = checker.tessellate(xyz, box, 0.8, 3)
+    assert open(tmp_path / "out.dat").read() == _expected_dat(want["area"], want["area2d"], want["areabox"], xyz.shape[1])
