@@ -19,7 +19,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 #include "../../include/gta_b200.h"
 #include "../../include/delaunay_tri.h"
@@ -130,19 +132,35 @@ void delaunay_tessellate(rvec** x, matrix* box, real espace, int nthreads, struc
     const unsigned fl = flags & (GTA_CORRECT | GTA_2D);
     const int maxp = gta_b200_max_points_for(&box[0][0][0], 9, F, N, espace, fl);
     int rc;
+    std::string large_msg;                                     // (an error of a worker thread of the large-frame branch)
     if (maxp > gta_b200_max_points()) {
         // frames too large for the batched shared-memory kernels (e.g. a whole system without -n): one frame at a time
         // through the large-frame path (its own correction-point stage, the same corr_points as the batched kernels)
-        rc = GTA_B200_OK;
-        for (int fr = 0; fr < F && rc == GTA_B200_OK; ++fr) {
-            double a3 = 0.0, a2 = 0.0, ab = 0.0; int st = 0;
-            rc = gta_b200_tessellate_large(&x[fr][0][0], N, &box[fr][0][0], espace, fl, -1, &a3, &a2, &ab, nullptr, nullptr, &st);
-            if (rc != GTA_B200_OK) break;
-            g_frame_status[fr] = st;
-            areas->area[fr] = st ? kNaN : a3;
-            if (areas->area2D) areas->area2D[fr] = st ? kNaN : a2;
-            areas->area2Dbox[fr] = ab;
+        // Frames are independent (gta_tri.c:106): with several GPUs every device takes every ng-th frame, one host thread each.
+        const int want = env_int("GTA_B200_NGPUS", 0);
+        const int ng = std::max(1, std::min(F, want <= 0 ? gta_b200_device_count() : std::min(want, gta_b200_device_count())));
+        std::vector<int> rcs((size_t)ng, GTA_B200_OK);
+        std::vector<std::string> msgs((size_t)ng);
+        int* const fstat = g_frame_status.data();                  // (thread_local: the workers must write the caller's)
+        auto work = [&, fstat](int g) {
+            for (int fr = g; fr < F; fr += ng) {
+                double a3 = 0.0, a2 = 0.0, ab = 0.0; int st = 0;
+                const int r = gta_b200_tessellate_large(&x[fr][0][0], N, &box[fr][0][0], espace, fl, ng > 1 ? g : -1, &a3, &a2, &ab, nullptr, nullptr, &st);
+                if (r != GTA_B200_OK) { rcs[(size_t)g] = r; msgs[(size_t)g] = gta_b200_last_error(); return; }     // (the message is this thread's)
+                fstat[fr] = st;
+                areas->area[fr] = st ? kNaN : a3;
+                if (areas->area2D) areas->area2D[fr] = st ? kNaN : a2;
+                areas->area2Dbox[fr] = ab;
+            }
+        };
+        if (ng == 1) work(0);
+        else {
+            std::vector<std::thread> th;
+            for (int g = 0; g < ng; ++g) th.emplace_back(work, g);
+            for (auto& t : th) t.join();
         }
+        rc = GTA_B200_OK;
+        for (int g = 0; g < ng; ++g) if (rcs[(size_t)g] != GTA_B200_OK && rc == GTA_B200_OK) { rc = rcs[(size_t)g]; large_msg = msgs[(size_t)g]; }
     } else if (flags & GTA_PRINT) {
         // one frame at a time (the reference also serialises -print, g_tessla.c:116); files are numbered from 1
         static int iter = 0;
@@ -169,7 +187,7 @@ void delaunay_tessellate(rvec** x, matrix* box, real espace, int nthreads, struc
     if (rc != GTA_B200_OK) {
         // every function of this interface is void (reference include/gta_tri.h): the failure is reported on the log, in
         // gta_last_call_rc(), and as NaN areas with an INTERNAL status on every frame -- never as a table of zeros
-        print_log("TESSELLATION ERROR: %s\n", gta_b200_last_error());
+        print_log("TESSELLATION ERROR: %s\n", large_msg.empty() ? gta_b200_last_error() : large_msg.c_str());
         g_call_rc = rc;
         for (int fr = 0; fr < F; ++fr) {
             areas->area[fr] = kNaN; if (areas->area2D) areas->area2D[fr] = kNaN;

@@ -159,7 +159,12 @@ static cudaError_t ls_alloc(void** p, size_t bytes) {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) { unsigned long long keep = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); }
     });
-    return cudaMallocAsync(p, bytes ? bytes : 1, 0);
+    // Sizes are rounded up (64 KB below 1 MB, 2 MB above): the frames of a trajectory differ by a few points, and blocks of
+    // slightly different sizes are not reused -- the pool then maps new memory on most calls (sporadic stalls of 20-600 ms
+    // per frame were measured on a trajectory of 10^5-atom frames).
+    const size_t gran = bytes >= (1u << 20) ? (size_t)2 << 20 : (size_t)64 << 10;
+    bytes = ((bytes ? bytes : 1) + gran - 1) / gran * gran;
+    return cudaMallocAsync(p, bytes, 0);
 }
 static void ls_free(void* p) { if (p) cudaFreeAsync(p, 0); }
 
@@ -338,9 +343,9 @@ static int large_run(const double* points, const double* xyz3, int npoints, int 
     const int B = 256, G = (n + B - 1) / B;
     uint32_t hctl[4] = {0, 0, 0, 0};
     LCK(cudaEventCreate(&ev0)); LCK(cudaEventCreate(&ev1));
-    LCK(cudaMalloc((void**)&d_pts, sizeof(double) * 2 * (size_t)n));
+    LCK(ls_alloc((void**)&d_pts, sizeof(double) * 2 * (size_t)n));                 // (pool: no device-wide synchronisation per frame)
     if (xyz3) {
-        LCK(cudaMalloc((void**)&d_xyz, sizeof(double) * 3 * (size_t)n));
+        LCK(ls_alloc((void**)&d_xyz, sizeof(double) * 3 * (size_t)n));
         LCK(cudaMemcpy(d_xyz, xyz3, sizeof(double) * 3 * (size_t)n, cudaMemcpyDefault));      // (host, or device: gta_b200_tessellate_large)
         large_xy<<<G, B>>>(d_xyz, n, d_pts);
     } else LCK(cudaMemcpy(d_pts, points, sizeof(double) * 2 * (size_t)n, cudaMemcpyHostToDevice));
@@ -446,9 +451,9 @@ static int large_run(const double* points, const double* xyz3, int npoints, int 
         float ms = 0.f; cudaEventElapsedTime(&ms, ev0, ev1); g_large_ms = ms;
     }
 done:
-    cudaFree(d_pts); cudaFree(d_pt); cudaFree(d_k0); cudaFree(d_k1); cudaFree(d_ky); cudaFree(d_i0); cudaFree(d_i1);
+    ls_free(d_pts); cudaFree(d_pt); cudaFree(d_k0); cudaFree(d_k1); cudaFree(d_ky); cudaFree(d_i0); cudaFree(d_i1);
     cudaFree(d_head); cudaFree(d_dst); cudaFree(d_nxt); cudaFree(d_prv); cudaFree(d_ctl); cudaFree(d_cnt); cudaFree(d_off);
-    cudaFree(d_tri); cudaFree(d_tmp); cudaFree(d_xyz); cudaFree(d_a3); cudaFree(d_a2); cudaFree(d_sum);
+    cudaFree(d_tri); cudaFree(d_tmp); ls_free(d_xyz); cudaFree(d_a3); cudaFree(d_a2); cudaFree(d_sum);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     return rc;
@@ -483,16 +488,16 @@ extern "C" int gta_b200_tessellate_large(const double* xyz, int natoms, const do
     if (nx > (1 << 20) || ny > (1 << 20) || (long long)natoms + 4 + 2ll * nx + 2ll * ny > (1 << 27)) { if (status) *status = GTA_B200_ST_CAPACITY; return GTA_B200_OK; }
     const int ncorr = 4 + 2 * nx + 2 * ny, n = natoms + ncorr;
     double* d_all = nullptr;
-    cudaError_t e = cudaMalloc((void**)&d_all, sizeof(double) * 3 * (size_t)n);
+    cudaError_t e = ls_alloc((void**)&d_all, sizeof(double) * 3 * (size_t)n);
     if (e == cudaSuccess) e = cudaMemcpy(d_all, xyz, sizeof(double) * 3 * (size_t)natoms, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { cudaFree(d_all); g_lerr = std::string("gta_b200_tessellate_large: ") + cudaGetErrorString(e); return GTA_B200_E_CUDA; }
+    if (e != cudaSuccess) { ls_free(d_all); g_lerr = std::string("gta_b200_tessellate_large: ") + cudaGetErrorString(e); return GTA_B200_E_CUDA; }
     int st = 0;
     int rc = gta_b200_large_corr(d_all, natoms, ncorr, bx, by, espace, &st);
-    if (rc != GTA_B200_OK) { g_lerr = gta_b200_last_error(); cudaFree(d_all); return rc; }
-    if (st) { if (status) *status = st; cudaFree(d_all); return GTA_B200_OK; }          // (atoms outside the box, ...: the batched calls' statuses)
+    if (rc != GTA_B200_OK) { g_lerr = gta_b200_last_error(); ls_free(d_all); return rc; }
+    if (st) { if (status) *status = st; ls_free(d_all); return GTA_B200_OK; }          // (atoms outside the box, ...: the batched calls' statuses)
     if (ncorr_out) *ncorr_out = ncorr;
     rc = large_run(nullptr, d_all, n, -1, nullptr, 0, ntri, status, flags & ~(unsigned)GTA_B200_CORRECT, area3, area2);
-    cudaFree(d_all);
+    ls_free(d_all);
     return rc;
 }
 extern "C" int gta_b200_surface_area_large(const double* xyz, int natoms, unsigned flags, int device, double* area3, double* area2, int* ntri, int* status) {

@@ -3,6 +3,7 @@ served by libgtessla_b200.so, against the oracle."""
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -227,3 +228,29 @@ def test_cli_whole_system_frames_with_corr(gta, checker, tmp_path):
     assert r.returncode == 0, r.stderr + r.stdout
     want = checker.tessellate(xyz, box, 0.8, 3)
     assert open(tmp_path / "out.dat").read() == _expected_dat(want["area"], want["area2d"], want["areabox"], xyz.shape[1])
+
+
+def test_large_frames_shard_over_the_gpus(gta, checker):
+    """delaunay_tessellate on a trajectory of frames beyond the shared-memory kernels with every GPU of the box (one host
+    thread per device, every ng-th frame): the same bits as on one GPU. Needs two devices (the driver's 1-GPU run skips it;
+    scratch/large_traj.py is the measured form: 282 -> 482 frames/s of 10^5 atoms on two B200s)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU")
+    code = ("import ctypes as C, sys, numpy as np; sys.path.insert(0, %r); import g_tessla_b200 as g; from g_tessla_b200 import synth\n"
+            "xyz, box = synth.jittered_bilayer(6, 70, seed=3); F, N = xyz.shape[:2]; L = g.lib(); dp = C.POINTER(C.c_double)\n"
+            "class T(C.Structure): _fields_ = [('area', dp), ('area2D', dp), ('area2Dbox', dp), ('natoms', C.c_int), ('nframes', C.c_int)]\n"
+            "fr = [np.ascontiguousarray(xyz[f]) for f in range(F)]; xp = (dp * F)(*[a.ctypes.data_as(dp) for a in fr])\n"
+            "b9 = np.zeros((F, 3, 3)); b9[:, 0, 0] = box[:, 0]; b9[:, 1, 1] = box[:, 1]; b9[:, 2, 2] = box[:, 2]\n"
+            "a = T(None, None, None, N, F); L.delaunay_tessellate.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.POINTER(T), C.c_ubyte]\n"
+            "L.delaunay_tessellate(xp, b9.ctypes.data, 0.8, 0, C.byref(a), 1); print('AREAS', ' '.join(repr(float(v)) for v in np.ctypeslib.as_array(a.area, shape=(F,))))\n") % ROOT
+    got = {}
+    for ng in (1, 2):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, GTA_B200_NGPUS=str(ng)), capture_output=True, text=True, timeout=600)
+        line = [l for l in r.stdout.splitlines() if l.startswith("AREAS")]
+        assert r.returncode == 0 and line, r.stdout[-1000:] + r.stderr[-2000:]
+        got[ng] = np.array([float(v) for v in line[0].split()[1:]])
+    assert np.array_equal(got[1], got[2])
+    xyz, box = synth.jittered_bilayer(6, 70, seed=3)
+    want = checker.tessellate(xyz, box, 0.8, 1)
+    assert np.allclose(got[2], want["area"], rtol=1e-12, atol=0)
