@@ -1,3 +1,3 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_kept_api.py -x -q -m gpu 2>&1 | tail -12 | tee gpurun_out/pytest_large.log
+python bench.py --steps 5 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"; tail -2 gpurun_out/bench_n1.err
