@@ -383,6 +383,8 @@ def run_native(args):
             line["roofline_issue"] = {"achieved": issue_ach / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-instructions/s", "frac": issue_ach / issue_peak,
                                       "active_lanes_per_instruction": ncu_extra.get("active_lanes_per_instruction"),
                                       "note": "the kernel's own bound (DESIGN.md section 5): issue slots x lanes; instructions per frame from the ncu capture, stale with it"}
+        if world == 1 and not args.no_large_frames:
+            line["large_frames"] = large_frames_arm(g, np)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(xyz_h.numpy(), box_h.numpy(), area_dev, args)
             if kept and line["cpu_baseline"].get("value"):
@@ -392,6 +394,35 @@ def run_native(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def large_frames_arm(g, np):
+    """Outside the headline metric, for the record (BASELINE configs[3] and the large-frame form of the kept entry points):
+    ONE frame of 10^6 points through gta_b200_triangulate_large (star engine, triangle list to the host) and one frame of
+    10^6 atoms with -corr through gta_b200_tessellate_large. Host buffers in, host results out; the second call of each is
+    timed. Never fails the bench: an error is reported in the object."""
+    from g_tessla_b200 import synth
+    out = {}
+    try:
+        p = synth.uniform_patch(1_000_000, seed=4)
+        old = g.set_path(g.PATH_STAR)
+        try:
+            g.triangulate_large(p)
+            t0 = time.perf_counter(); tri, st, ms = g.triangulate_large(p); t1 = time.perf_counter()
+        finally:
+            g.set_path(old)
+        out["cfg4_one_frame_1e6_points"] = {"triangles": int(len(tri)), "status": int(st), "engine": int(g.lib().gta_b200_large_last_engine()),
+                                            "device_ms": float(ms), "host_to_host_ms": (t1 - t0) * 1e3,
+                                            "note": "star engine: the reference's triangle set (tests/test_gpu_large.py::test_cfg4_star_engine), in cell order"}
+        xyz, box = synth.jittered_bilayer(1, 1000, seed=12)
+        b9 = np.zeros((3, 3)); b9[0, 0], b9[1, 1], b9[2, 2] = box[0]
+        g.tessellate_large(xyz[0], b9, 0.8, flags=3)
+        t0 = time.perf_counter(); r = g.tessellate_large(xyz[0], b9, 0.8, flags=3); t1 = time.perf_counter()
+        out["one_frame_1e6_atoms_corr_2d"] = {"ncorr": int(r["ncorr"]), "triangles": int(r["ntri"]), "status": int(r["status"]), "engine": int(r["engine"]),
+                                              "host_to_host_ms": (t1 - t0) * 1e3}
+    except Exception as e:                                              # noqa: BLE001 -- reported, not raised
+        out["error"] = "%s: %s" % (type(e).__name__, e)
+    return out
 
 
 def kept_api_arm(L, C, np, xyz_h, box_h, area_dev, ngpus, args):
@@ -481,6 +512,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-seconds-per-step", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-large-frames", action="store_true", help="skip the two large-frame measurements reported beside the headline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":
